@@ -1,0 +1,250 @@
+// Epilogue functors for gemm_bf16_kernel.  An epilogue thread owns ONE accumulator row (token or feature,
+// depending on the GEMM) and receives it 32 columns at a time.  Rows >= M and columns >= N hold garbage-free
+// zeros from TMA out-of-bounds fill, but they must still be masked out of every reduction and store.
+//
+// All floating-point reductions are written as per-(tile,warp) partials and summed later in a fixed order, so a
+// step is bit-reproducible run to run; integer activity bits use atomicOr (order-independent).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace svb {
+
+__device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i * 4 < nvalid) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i * 8 < nvalid) {
+      uint4 q;
+      q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      reinterpret_cast<uint4*>(dst)[i] = q;
+    }
+}
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, float (&o)[32], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (i * 8 < nvalid) q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    o[8 * i + 0] = bf16lo(q.x); o[8 * i + 1] = bf16hi(q.x);
+    o[8 * i + 2] = bf16lo(q.y); o[8 * i + 3] = bf16hi(q.y);
+    o[8 * i + 4] = bf16lo(q.z); o[8 * i + 5] = bf16hi(q.z);
+    o[8 * i + 6] = bf16lo(q.w); o[8 * i + 7] = bf16hi(q.w);
+  }
+}
+__device__ __forceinline__ void load_row_f32(const float* src, float (&o)[32], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i * 4 < nvalid) q = __ldg(reinterpret_cast<const float4*>(src) + i);
+    o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
+  }
+}
+
+// Sum over the 32 lanes of v[j] for every j with 31 shuffles: lane j returns column j's sum.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// OR the per-row activity word into the per-image bit matrix.  A warp's 32 rows usually lie in one image.
+__device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_per_img, int word_idx, uint32_t word,
+                                                 int row, int M, int hw, int row0_warp, int lane) {
+  const int last_row = min(row0_warp + 31, M - 1);
+  if (row0_warp > last_row) return;
+  const int b_first = row0_warp / hw, b_last = last_row / hw;
+  const int my_b = row < M ? row / hw : -1;
+  for (int b = b_first; b <= b_last; ++b) {
+    const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? word : 0u);
+    if (lane == 0 && ored) atomicOr(&act_bits[static_cast<size_t>(b) * words_per_img + word_idx], ored);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plain store
+// out = [relu](alpha*acc + bias), fp32 or bf16; split-K slices land split_stride elements apart.
+struct EpiStore {
+  struct Params {
+    void* out;
+    long long ld;
+    long long split_stride;
+    const float* bias;  // [N] or null
+    float alpha;
+    int relu;
+    int out_bf16;
+  };
+  static constexpr uint32_t kSmemBytes = 0;
+  const Params& p;
+  __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int, int) {
+    const int nvalid = min(32, g.N - col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j] * p.alpha;
+      if (p.bias && j < nvalid) x += __ldg(p.bias + col0 + j);
+      if (p.relu) x = fmaxf(x, 0.f);
+      v[j] = x;
+    }
+    if (row >= g.M) return;
+    const long long off = ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0;
+    if (p.out_bf16) store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, nvalid);
+    else store_row_f32(reinterpret_cast<float*>(p.out) + off, v, nvalid);
+  }
+  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+};
+
+// ------------------------------------------------------------------------------------------------ encoder
+// pre = acc + bias';  e = relu(pre)   (sae_mlp.py:49-51 with the pre-bias folded: bias' = b_enc - W_enc b_dec)
+// Fused: bf16/fp32 stores of e (and pre), per-image activity bits (utils.py:2033-2047), sum|e| partials
+// (sparse_loss.py:41).
+struct EpiEnc {
+  struct Params {
+    const float* bias;      // [N]
+    __nv_bfloat16* e_bf16;  // [M,N] or null
+    float* e_f32;           // [M,N] or null
+    float* pre_f32;         // [M,N] or null
+    uint32_t* act_bits;     // [n_img, words] or null
+    float* l1_partial;      // [tiles_m*tiles_n*4] or null
+    int hw;                 // tokens per image (1 for 2-D inputs)
+    int words;              // ceil(N/32)
+  };
+  static constexpr uint32_t kSmemBytes = 0;
+  const Params& p;
+  float sum;
+  __device__ EpiEnc(const Params& p_, uint8_t*) : p(p_), sum(0.f) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
+                        int lane) {
+    const int nvalid = min(32, g.N - col0);
+    const bool row_ok = row < g.M;
+    float b[32];
+    load_row_f32(p.bias + col0, b, nvalid);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += b[j];
+    const long long off = static_cast<long long>(row) * g.N + col0;
+    if (p.pre_f32 && row_ok) store_row_f32(p.pre_f32 + off, v, nvalid);
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float e = fmaxf(v[j], 0.f);
+      v[j] = e;
+      if (e > 0.f && j < nvalid) word |= (1u << j);
+      if (j < nvalid) sum += e;
+    }
+    if (!row_ok) word = 0;
+    if (row_ok) {
+      if (p.e_bf16) store_row_bf16(p.e_bf16 + off, v, nvalid);
+      if (p.e_f32) store_row_f32(p.e_f32 + off, v, nvalid);
+    }
+    if (p.act_bits) publish_activity(p.act_bits, p.words, col0 >> 5, word, row, g.M, p.hw, ti.m0 + wq * 32, lane);
+  }
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
+    if (!p.l1_partial) return;
+    const float s = warp_sum(row < g.M ? sum : 0.f);
+    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ decoder
+// d = acc + b_dec;  diff = d - x   (sae_mlp.py:52, sparse_loss.py:35).  Fused: stores of d / diff, sum diff^2.
+struct EpiDec {
+  struct Params {
+    const float* bias;           // [N] decoder bias
+    const __nv_bfloat16* x;      // [M,N] targets (SAE input) or null (then diff = d)
+    __nv_bfloat16* d_bf16;       // [M,N] or null
+    float* d_f32;                // [M,N] or null
+    __nv_bfloat16* diff_bf16;    // [M,N] or null
+    float* sq_partial;           // [tiles_m*tiles_n*4] or null
+  };
+  static constexpr uint32_t kSmemBytes = 0;
+  const Params& p;
+  float sq;
+  __device__ EpiDec(const Params& p_, uint8_t*) : p(p_), sq(0.f) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sq = 0.f; }
+  __device__ void chunk(const GemmProblem& g, const TileInfo&, int row, int col0, float (&v)[32], int, int) {
+    const int nvalid = min(32, g.N - col0);
+    if (row >= g.M) return;
+    float b[32];
+    load_row_f32(p.bias + col0, b, nvalid);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += b[j];
+    const long long off = static_cast<long long>(row) * g.N + col0;
+    if (p.d_bf16) store_row_bf16(p.d_bf16 + off, v, nvalid);
+    if (p.d_f32) store_row_f32(p.d_f32 + off, v, nvalid);
+    if (p.x) {
+      load_row_bf16(p.x + off, b, nvalid);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] -= b[j];
+        if (j < nvalid) sq += v[j] * v[j];
+      }
+      if (p.diff_bf16) store_row_bf16(p.diff_bf16 + off, v, nvalid);
+    }
+  }
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
+    if (!p.sq_partial) return;
+    const float s = warp_sum(row < g.M ? sq : 0.f);
+    if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ dE -> dPre
+// acc = diff * W_dec  (unscaled dE);  dPre' = 1[e>0] * (acc + l1c)  with l1c = lambda*C/(2F), i.e. the whole
+// backward is carried in units of T*C/2 and rescaled once in the gradient reduction (model_pipeline.py:385 autograd
+// of sparse_loss.py:35,41 through sae_mlp.py:51).  Fused: bf16 store of dPre', per-feature column sums (-> db_enc).
+struct EpiDPre {
+  struct Params {
+    const __nv_bfloat16* e;    // [M,N] encoder output
+    __nv_bfloat16* dpre;       // [M,N]
+    float* colsum_partial;     // [tiles_m, N]
+    float l1c;
+    int block_n;               // BLOCK_N of the launching GEMM
+  };
+  static constexpr uint32_t kSmemBytes = 4 * 256 * sizeof(float);
+  const Params& p;
+  float* s_col;  // [4][256]
+  __device__ EpiDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem)) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
+                        int lane) {
+    const int nvalid = min(32, g.N - col0);
+    const bool row_ok = row < g.M;
+    float e[32];
+    const long long off = static_cast<long long>(row) * g.N + col0;
+    load_row_bf16(p.e + (row_ok ? off : 0), e, row_ok ? nvalid : 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (e[j] > 0.f) ? v[j] + p.l1c : 0.f;
+    if (row_ok) store_row_bf16(p.dpre + off, v, nvalid);
+    const float cs = warp_colsum32(v, lane);
+    s_col[wq * 256 + (col0 - ti.n0) + lane] = cs;
+  }
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
+    epi_bar_sync();
+    const int t = wq * 32 + lane;
+#pragma unroll
+    for (int c = t; c < 256; c += 128) {
+      const int col = ti.n0 + c;
+      if (c < p.block_n && col < g.N) {
+        const float s = (s_col[c] + s_col[256 + c]) + (s_col[512 + c] + s_col[768 + c]);
+        p.colsum_partial[static_cast<size_t>(ti.tile_m) * g.N + col] = s;
+      }
+    }
+    epi_bar_sync();
+  }
+};
+
+}  // namespace svb

@@ -1,0 +1,118 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding (driver entry point fetched at run time, no -lcuda) and
+// the launcher that sizes the persistent grid and the split-K slices.
+#pragma once
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <cstring>
+#include "gemm_sm100.cuh"
+
+namespace svb {
+
+inline PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] with row pitch ld (elements); box = box_rows x 64 columns, 128B swizzle.
+// Out-of-bounds elements are zero-filled, which is what makes M/N/K tails free.
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows) {
+  auto fn = tmap_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return -2;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+inline int device_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// A: K-major -> memory [M, K] pitch lda;  MN-major -> memory [K, M] pitch lda.   B likewise with N.
+// k_splits_req <= 0 picks a split count that fills the machine when there are few output tiles.
+// Returns 0 or a negative svb error code; *splits_out receives the number of split-K slices used.
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, kBlockM);
+  else rc = make_tmap_bf16_2d(&tmA, A, K, M, lda, kBlockK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, BLOCK_N);
+  else rc = make_tmap_bf16_2d(&tmB, B, K, N, ldb, kBlockK);
+  if (rc) return rc;
+
+  GemmProblem p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + kBlockM - 1) / kBlockM;
+  p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int kblocks = (K + kBlockK - 1) / kBlockK;
+  const int sms = max_ctas > 0 ? max_ctas : device_sm_count();
+  int splits = k_splits_req;
+  if (splits <= 0) {
+    const int mn_tiles = p.tiles_m * p.tiles_n;
+    splits = mn_tiles >= sms ? 1 : (sms / mn_tiles);
+  }
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  const int kb_per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per - 1) / kb_per;  // drop empty slices
+  p.k_splits = splits;
+  p.k_per_split = kb_per * kBlockK;
+  if (splits_out) *splits_out = splits;
+
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, Epi>;
+  const uint32_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -4;
+    configured = true;
+  }
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p, ep);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// Split count the launcher would choose (needed to size split-K workspaces before launching).
+template <int BLOCK_N>
+inline int planned_splits(int M, int N, int K, int k_splits_req, int max_ctas = 0) {
+  const int tiles_m = (M + kBlockM - 1) / kBlockM, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int kblocks = (K + kBlockK - 1) / kBlockK;
+  const int sms = max_ctas > 0 ? max_ctas : device_sm_count();
+  int splits = k_splits_req;
+  if (splits <= 0) {
+    const int mn_tiles = tiles_m * tiles_n;
+    splits = mn_tiles >= sms ? 1 : (sms / mn_tiles);
+  }
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  const int kb_per = (kblocks + splits - 1) / splits;
+  return (kblocks + kb_per - 1) / kb_per;
+}
+
+}  // namespace svb

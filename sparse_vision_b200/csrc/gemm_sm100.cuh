@@ -1,0 +1,217 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (fp32 accumulate in TMEM).
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma, tcgen05.commit frees smem slots / publishes TMEM)
+//   warps 2..5  : epilogue      (tcgen05.ld TMEM -> registers -> Epi functor -> global)
+//
+// Either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers every GEMM of
+// the SAE step on row-major token tensors without a transpose copy:
+//   enc   pre = X   [T,C] * W_enc[F,C]^T      A K-major,  B K-major
+//   dec   d   = E   [T,F] * W_dec[C,F]^T      A K-major,  B K-major
+//   dE        = dD  [T,C] * W_dec[C,F]        A K-major,  B MN-major
+//   dW_dec    = dD^T[C,T] * E   [T,F]         A MN-major, B MN-major   (split-K over tokens)
+//   dW_enc    = dP^T[F,T] * X   [T,C]         A MN-major, B MN-major   (split-K over tokens)
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  The epilogue is a functor: see epilogues.cuh.
+#pragma once
+#include "ptx.cuh"
+
+namespace svb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct GemmProblem {
+  int M, N, K;
+  int k_splits;     // >= 1; every split is non-empty
+  int k_per_split;  // multiple of kBlockK
+  int tiles_m, tiles_n;
+};
+
+struct TileInfo {
+  int m0, n0;     // element offsets of this tile
+  int split;      // split-K slice
+  int tile_m;     // tile index along M
+  int tile_n;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+  static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  static constexpr uint32_t kBarrierBytes = 256;  // 2*stages + 4 mbarriers + tmem ptr
+  static constexpr uint32_t smem_bytes(uint32_t epi_bytes) {
+    return 1024 /*alignment slack*/ + kStages * kStageBytes + kBarrierBytes + epi_bytes;
+  }
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
+  TileInfo ti;
+  ti.tile_n = t % p.tiles_n;
+  const int r = t / p.tiles_n;
+  ti.tile_m = r % p.tiles_m;
+  ti.split = r / p.tiles_m;
+  ti.m0 = ti.tile_m * kBlockM;
+  ti.n0 = ti.tile_n * block_n;
+  return ti;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmProblem p, const typename Epi::Params ep) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
+  static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::kBarrierBytes, "barrier region too small");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes + Cfg::kBarrierBytes;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
+  const int lane = static_cast<int>(threadIdx.x) % 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(p, t, BLOCK_N);
+        const int k_begin = ti.split * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k0 = k_begin + kb * kBlockK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, ti.m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, ti.n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], ti.n0 + 64 * j, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(p, t, BLOCK_N);
+        const int k_begin = ti.split * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // K-major: 8-row groups are 1024 B apart (SBO); a k-step is 32 B inside the swizzled 128 B row.
+            // MN-major: each 64-wide MN atom holds kBlockK rows of 128 B (LBO = 8192 B between atoms),
+            //           8-row K groups are 1024 B apart (SBO); a k-step is 16 rows = 2048 B.
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int wq = warp % 4;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row_in_tile = wq * 32 + lane;
+    Epi epi(ep, epi_smem);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(p, t, BLOCK_N);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = ti.m0 + row_in_tile;
+      epi.begin_tile(p, ti, row, wq, lane);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = ti.n0 + c * 32;
+        if (col0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        epi.chunk(p, ti, row, col0, v, wq, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);  // accumulator stage free for the MMA warp
+      epi.end_tile(p, ti, row, wq, lane);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// Named barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads).
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+}  // namespace svb
