@@ -1,0 +1,233 @@
+/* svb.h — C ABI of libsvb.so, the B200 (sm_100a) implementation of sparse-vision's SAE training-and-attribution
+ * hot path.  The reference (jasper3100/sparse-vision) is pure Python and has no FFI; these entry points sit UNDER
+ * its Python module API and each one names the reference code it replaces (paths relative to the reference root).
+ * The ctypes binding a maintainer would add is shown in INTEGRATION.md and lives in sparse_vision_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the library never frees or retains caller
+ *     memory beyond the call; tensors are dense row-major;
+ *   - `stream` is a cudaStream_t passed as void* (PyTorch: torch.cuda.current_stream().cuda_stream); all work is
+ *     enqueued on it and nothing synchronises with the host;
+ *   - return value: 0 on success, negative svb_status otherwise; svb_last_error() gives a message (thread-local);
+ *   - parameters and Adam state are fp32 and are updated IN PLACE (the reference indexes them afterwards);
+ *   - there is no CPU fallback: a missing device or an unsupported shape is an error.
+ *   - shape limits: C % 8 == 0 and F % 8 == 0 (TMA pitch), T = n_images * hw < 2^31.
+ */
+#ifndef SVB_H_
+#define SVB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svb_handle svb_handle; /* opaque; owns workspaces for ONE device; not thread-safe */
+
+enum svb_status {
+  SVB_OK = 0,
+  SVB_ERR_DRIVER = -1,      /* cuTensorMapEncodeTiled entry point unavailable */
+  SVB_ERR_BAD_ARG = -2,     /* null pointer, misaligned pointer, bad enum, bad shape */
+  SVB_ERR_TMAP = -3,        /* tensor-map encoding failed */
+  SVB_ERR_CUDA = -4,        /* a CUDA runtime call failed */
+  SVB_ERR_UNSUPPORTED = -5, /* shape outside the limits above */
+  SVB_ERR_NOMEM = -6        /* workspace allocation failed */
+};
+
+enum svb_dtype { SVB_F32 = 0, SVB_BF16 = 1 };
+enum svb_layout {
+  SVB_TOKENS = 0, /* [T, C], C contiguous; token order t = (b*H + h)*W + w  (utils.py:2770-2774 reshape_tensor) */
+  SVB_NCHW = 1    /* [B, C, H, W] as the base model produces it */
+};
+enum svb_optimizer {
+  SVB_ADAM = 0,            /* utils.py:85-86  torch.optim.Adam, caller passes betas (0.9, 0.9999) */
+  SVB_CONSTRAINED_ADAM = 1 /* utils.py:50-81  project decoder grad, Adam (0.9, 0.999), renormalise columns */
+};
+
+const char* svb_last_error(void);
+int svb_version(void);
+int svb_create(svb_handle** out); /* binds to the calling thread's current CUDA device */
+int svb_destroy(svb_handle* h);
+/* bytes of device workspace currently held by the handle */
+int64_t svb_workspace_bytes(const svb_handle* h);
+
+/* A batch of SAE inputs: the hooked layer's output (model_pipeline.py:368). */
+typedef struct svb_acts {
+  const void* x;    /* activations */
+  int32_t dtype;    /* svb_dtype */
+  int32_t layout;   /* svb_layout */
+  int64_t n_images; /* B; for 2-D inputs the number of rows */
+  int32_t hw;       /* H*W pixels per image; 1 for 2-D inputs */
+  int32_t C;        /* act_size */
+} svb_acts;
+
+/* SaeMLP parameters, state_dict order (models/sae_mlp.py:26-40). */
+typedef struct svb_sae_params {
+  float* w_enc; /* encoder.weight [F, C] */
+  float* b_enc; /* encoder.bias   [F]    */
+  float* w_dec; /* decoder.weight [C, F] */
+  float* b_dec; /* decoder.bias   [C]    */
+  int32_t F;    /* hidden_size = C * expansion_factor */
+} svb_sae_params;
+
+/* GatedSae parameters, state_dict order (models/gated_sae.py:11-26). */
+typedef struct svb_gated_params {
+  float* w_gate; /* [F, C] */
+  float* b_gate; /* [F] */
+  float* b_mag;  /* [F] */
+  float* r_mag;  /* [F] */
+  float* w_dec;  /* decoder.weight [C, F] */
+  float* b_dec;  /* decoder.bias   [C] */
+  int32_t F;
+} svb_gated_params;
+
+/* Adam moments for the same tensors, same order (torch.optim.Adam state 'exp_avg' / 'exp_avg_sq'). */
+typedef struct svb_adam_state {
+  float* m[6];
+  float* v[6];
+} svb_adam_state;
+
+typedef struct svb_opt_config {
+  int32_t optimizer; /* svb_optimizer */
+  int32_t step;      /* Adam step count AFTER this update (1 on the first step) */
+  float lr, beta1, beta2, eps;
+} svb_opt_config;
+
+/* Scalars of one step, device float[SVB_STATS_LEN] (read them with one D2H copy per logging interval instead of
+ * the reference's six .item() syncs, model_pipeline.py:394-399). */
+enum svb_stat {
+  SVB_STAT_LOSS = 0, /* rec + lambda*l1 (+ aux)           utils.py:2470,2473 */
+  SVB_STAT_REC = 1,  /* mean (d-x)^2                      sparse_loss.py:35 */
+  SVB_STAT_L1 = 2,   /* mean |enc| (gated: |relu_pi|)     sparse_loss.py:41,71 */
+  SVB_STAT_NRMSE = 3,
+  SVB_STAT_RMSE = 4, /* sparse_loss.py:4-21 */
+  SVB_STAT_AUX = 5,  /* gated aux mse, else 0             sparse_loss.py:72 */
+  SVB_STAT_VAR_EXPL = 6, /* utils.py:2012-2030 */
+  SVB_STAT_SPARSITY = 7, /* utils.py:2063-2067 */
+  SVB_STAT_N_DEAD = 8,   /* number of units with no activity in this batch */
+  SVB_STATS_LEN = 16
+};
+
+/* Per-step outputs of the activity bookkeeping (utils.py:2032-2069 measure_inactive_units). */
+typedef struct svb_activity_out {
+  uint8_t* dead;     /* [F] 1 iff the unit was inactive for every image of the batch; may be NULL */
+  float* freq;       /* [F] fraction of images in which the unit fired; may be NULL */
+  int32_t* n_active; /* [n_images] active units per image; may be NULL */
+} svb_activity_out;
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SaeMLP forward — models/sae_mlp.py:42-53 (4-D branch: pixels as tokens).  Outputs are token-major 2-D like the
+ * reference's return values; any of them may be NULL.  enc / pre: [T, F]; dec: [T, C].
+ */
+typedef struct svb_sae_forward_out {
+  void* enc;  int32_t enc_dtype; /* svb_dtype */
+  float* pre;                    /* fp32 */
+  void* dec;  int32_t dec_dtype;
+} svb_sae_forward_out;
+int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                    const svb_sae_forward_out* out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One SaeMLP training step — the train branch of ModelPipeline.hook (model_pipeline.py:363-432):
+ * sae_inference_and_loss (utils.py:2448-2482) -> loss.backward() -> optimizer.step() (utils.py:50-97) ->
+ * measure_inactive_units (utils.py:2032-2069) -> variance_explained (utils.py:2012-2030).
+ *   dec_out: decoder output in the layout/dtype of `dec_layout`/`dec_dtype` (what the hook returns), or NULL.
+ *   global_tokens: tokens over ALL data-parallel ranks (loss means are global); 0 means "this batch only".
+ * svb_sae_step_grads + svb_sae_step_apply are the two halves used for data parallelism: the caller all-reduces
+ * (SUM) the flat buffer from svb_sae_grad_buffer() between them.  svb_sae_train_step runs both.
+ */
+typedef struct svb_train_out {
+  void* dec_out; int32_t dec_dtype; int32_t dec_layout;
+  float* stats;              /* device float[SVB_STATS_LEN] or NULL */
+  svb_activity_out activity;
+} svb_train_out;
+
+int svb_sae_train_step(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                       const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                       int32_t expansion_factor, const svb_train_out* out);
+int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p, float lambda_sparse,
+                       int64_t global_tokens, const svb_train_out* out);
+int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                       const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                       int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
+                       const svb_train_out* out);
+/* Flat fp32 reduction buffer of the last svb_*_step_grads call: gradients in state_dict order followed by the loss
+ * partial sums.  *sum_elems (SUM all-reduce) then *max_elems (MAX all-reduce) elements. */
+int svb_sae_grad_buffer(svb_handle* h, float** buf, int64_t* sum_elems, int64_t* max_elems);
+
+/* GatedSae forward / step — models/gated_sae.py:28-56, losses/sparse_loss.py:68-76. */
+typedef struct svb_gated_forward_out {
+  void* enc;     int32_t enc_dtype;
+  void* dec;     int32_t dec_dtype;
+  void* relu_pi; int32_t relu_pi_dtype;
+  void* via;     int32_t via_dtype;
+} svb_gated_forward_out;
+int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                      const svb_gated_forward_out* out);
+int svb_gated_train_step(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                         const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                         int32_t expansion_factor, const svb_train_out* out);
+int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                         float lambda_sparse, int64_t global_tokens, const svb_train_out* out);
+int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                         const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                         int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
+                         const svb_train_out* out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimiser step on caller-provided gradients — utils.py:50-97 (ConstrainedAdam.step / torch.optim.Adam).
+ * `decoder_index` is the position of decoder.weight in the lists (projected + renormalised when the optimizer is
+ * SVB_CONSTRAINED_ADAM; -1 for none); rows/cols give each tensor's 2-D shape (vectors: rows = 1).
+ */
+int svb_adam_step(svb_handle* h, void* stream, int32_t n_tensors, float* const* params, const float* const* grads,
+                  float* const* m, float* const* v, const int64_t* rows, const int64_t* cols, int32_t decoder_index,
+                  const svb_opt_config* opt);
+
+/* Dead-unit re-initialisation scatter — models/sae_mlp.py:133-176.  The caller draws the Kaiming matrices with
+ * PyTorch (generator parity) and passes them already rescaled (sae_mlp.py:106-130); this call scatters them into
+ * the dead rows / columns, renormalises ALL decoder columns (:138) and zeroes the Adam moments of the dead slices. */
+int svb_reinit_dead(svb_handle* h, void* stream, const svb_sae_params* p, int32_t C, const svb_adam_state* adam,
+                    const uint8_t* dead, const float* new_w_enc, const float* new_w_dec, float new_b_enc);
+
+/* measure_inactive_units (utils.py:2032-2069) on an existing tensor: [B, F, H, W] (layout NCHW) or [N, F]. */
+int svb_measure_inactive(svb_handle* h, void* stream, const void* out_tensor, int32_t dtype, int32_t layout,
+                         int64_t n_images, int32_t hw, int32_t F, const svb_activity_out* act);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Indirect-effect reductions — utils.py:2606-2637 compute_ie_channel_wise and utils.py:2574-2602
+ * compute_ie_all_channels.   a, g: [T, F] token-major (dtype f32/bf16); avg: fp32 [F, H, W].
+ *   out[f] = scale * sum_t | g[t,f] * (avg[f, t mod HW] - a[t,f]) |      scale = 1/T gives the reference's mean;
+ * pass scale = 1 to get partial sums for a data-parallel all-reduce.
+ */
+int svb_ie_channelwise(svb_handle* h, void* stream, const void* a, const void* g, int32_t dtype, const float* avg,
+                       int64_t n_images, int32_t hw, int32_t F, float scale, float* out);
+/* err, g: [B, C, H, W] (dtype f32/bf16); avg fp32 [C, H, W]; out[0] = scale * sum_t | sum_c g*(avg - err) |. */
+int svb_ie_allchannels(svb_handle* h, void* stream, const void* err, const void* g, int32_t dtype, const float* avg,
+                       int64_t n_images, int32_t C, int32_t hw, float scale, float* out);
+
+/* Node-IE for one layer of one batch, fused front to back (compute_ie.py:242-267,442-453 with the identity
+ * enc.grad == grad_original @ W_dec, supplementary_files_2/nnsight_intervention_check.py:194-213):
+ *   a = SAE_enc(x); G = g W_dec; err = x - dec;
+ *   ie_features[F], ie_error[1], ie_neurons[C]  (each scaled by `scale`).  x and g share dtype/layout. */
+int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x, const void* grad, const svb_sae_params* p,
+                      const float* enc_avg, const float* err_avg, const float* x_avg, float scale,
+                      float* ie_features, float* ie_error, float* ie_neurons);
+
+/* Generic bf16 GEMM on the same tcgen05 kernel:  D[M,N] = alpha * A[M,K] * B[N,K]^T (+ bias[N]) (optionally ReLU).
+ *   a_mn / b_mn: 0 = K contiguous (memory [M,K] / [N,K] with pitch lda / ldb), 1 = M / N contiguous (memory [K,M] /
+ *   [K,N]).  out: fp32 or bf16 with pitch ldo.  With few output tiles and fp32 output (no bias/ReLU) the K loop is
+ *   split over the SMs and reduced in a fixed order.  Used by the module-level autograd path (backward of
+ *   models/sae_mlp.py and models/gated_sae.py, i.e. what loss.backward() at model_pipeline.py:385 runs). */
+int svb_gemm_bf16(svb_handle* h, void* stream, const void* A, int32_t a_mn, int64_t lda, const void* B, int32_t b_mn,
+                  int64_t ldb, int32_t M, int32_t N, int32_t K, void* out, int32_t out_dtype, int64_t ldo, float alpha,
+                  const float* bias, int32_t relu);
+
+/* Layout helpers (einops rearrange at sae_mlp.py:44 / utils.py:2462-2480), exposed for callers and tests. */
+int svb_pack_tokens(svb_handle* h, void* stream, const svb_acts* x, void* out_bf16_tokens);
+int svb_unpack_tokens(svb_handle* h, void* stream, const void* tokens, int32_t tokens_dtype, int64_t n_images,
+                      int32_t hw, int32_t C, void* out_nchw, int32_t out_dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB_H_ */

@@ -1,0 +1,528 @@
+// Memory-bound helper kernels around the GEMMs: layout packing, weight preparation, deterministic reductions,
+// per-channel statistics, the fused (Constrained)Adam update, activity finalisation and the step scalars.
+// All reductions use a fixed summation order (no floating-point atomics) so a step is reproducible.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace svb {
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = lane < nw ? smem[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+// NCHW [B,C,HW] -> tokens [B*HW, C] (bf16), 32x32 smem transpose; sae_mlp.py:44 'b c h w -> (b h w) c'.
+template <typename TIn>
+static __global__ void pack_nchw_to_tokens_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const TIn* xb = x + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? to_f32<TIn>(xb[static_cast<size_t>(c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  bf16* ob = out + static_cast<size_t>(b) * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) ob[static_cast<size_t>(p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// tokens [B*HW, C] -> NCHW [B,C,HW]; utils.py:2478 '(b h w) c -> b c h w'.
+template <typename TIn, typename TOut>
+static __global__ void unpack_tokens_to_nchw_kernel(const TIn* __restrict__ tok, TOut* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const TIn* tb = tok + static_cast<size_t>(b) * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f32<TIn>(tb[static_cast<size_t>(p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  TOut* ob = out + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) ob[static_cast<size_t>(c) * HW + p] = from_f32<TOut>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename TIn, typename TOut>
+static __global__ void convert_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = from_f32<TOut>(to_f32<TIn>(in[i]));
+}
+
+static __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// One warp per encoder row f:  w_bf16[f,:] = bf16(w[f,:]);  fold[f] = b_enc[f] - sum_c bf16(w[f,c]) * b_dec[c]
+// (the pre-bias subtraction x - b_dec of sae_mlp.py:49 folded into the encoder bias).  dotw (optional) returns
+// the raw dot product sum_c bf16(w[f,c]) * b_dec[c] (used by the gated path).
+static __global__ void prep_encoder_kernel(const float* __restrict__ w, const float* __restrict__ b_enc,
+                                    const float* __restrict__ b_dec, bf16* __restrict__ w_bf16,
+                                    float* __restrict__ fold, float* __restrict__ dotw, int F, int C) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= F) return;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const bf16 q = __float2bfloat16_rn(w[static_cast<size_t>(f) * C + c]);
+    w_bf16[static_cast<size_t>(f) * C + c] = q;
+    acc += __bfloat162float(q) * b_dec[c];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (fold) fold[f] = (b_enc ? b_enc[f] : 0.f) - acc;
+    if (dotw) dotw[f] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// out[j] = scale * sum_{i<R} in[i*ld + j], rows summed in a fixed order.  Two stages when R is large:
+// stage 1 (gridDim.y row chunks) writes [gridDim.y, N] partials, stage 2 finishes them.
+static __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int N, size_t ld,
+                                   float scale) {
+  __shared__ float s[8][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int g = threadIdx.x >> 5;  // 8 row lanes
+  const int chunks = gridDim.y;
+  const int rows_per = (R + chunks - 1) / chunks;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float acc = 0.f;
+  if (j < N)
+    for (int i = r0 + g; i < r1; i += 8) acc += in[static_cast<size_t>(i) * ld + j];
+  s[g][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (g == 0 && j < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x & 31];
+    out[static_cast<size_t>(blockIdx.y) * N + j] = t * scale;
+  }
+}
+
+// Sum of a flat array in a fixed order, one block: out[0] = scale * sum(in[0..n)).
+static __global__ void reduce_flat_kernel(const float* __restrict__ in, size_t n, float scale, float* __restrict__ out) {
+  __shared__ float s[32];
+  float acc = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += in[i];
+  const float r = block_sum(acc, s);
+  if (threadIdx.x == 0) out[0] = r * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ channel stats
+// Per image b and channel c over the image's HW tokens (token-major bf16 inputs):
+//   st[b][0][c] = sum x, [1] = sum x^2, [2] = sum d, [3] = sum d^2, [4] = sum diff, [5] = sum diff^2,
+//   [6] = min x, [7] = max x.      grid (B, ceil(C/256)), 256 threads: warp w takes rows w, w+8, ...
+// Feeds variance_explained (utils.py:2012-2030), compute_rmse_nrmse (sparse_loss.py:4-21) and db_dec.
+static __global__ void channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d,
+                                     const bf16* __restrict__ diff, float* __restrict__ st, int C, int HW) {
+  __shared__ float s[8][8][33];  // [warp][stat][lane]  (one channel-of-8 at a time)
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float a[8][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[q][k] = 0.f;
+    a[6][k] = INFINITY;
+    a[7][k] = -INFINITY;
+  }
+  if (c0 < C) {
+    for (int r = w; r < HW; r += 8) {
+      const size_t off = (static_cast<size_t>(b) * HW + r) * C + c0;
+      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x + off));
+      const uint4 qd = d ? __ldg(reinterpret_cast<const uint4*>(d + off)) : make_uint4(0, 0, 0, 0);
+      const uint4 qf = diff ? __ldg(reinterpret_cast<const uint4*>(diff + off)) : make_uint4(0, 0, 0, 0);
+      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w},
+                     wf[4] = {qf.x, qf.y, qf.z, qf.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = bf16lo(wx[k]), x1 = bf16hi(wx[k]);
+        const float d0 = bf16lo(wd[k]), d1 = bf16hi(wd[k]);
+        const float f0 = bf16lo(wf[k]), f1 = bf16hi(wf[k]);
+        a[0][2 * k] += x0; a[0][2 * k + 1] += x1;
+        a[1][2 * k] += x0 * x0; a[1][2 * k + 1] += x1 * x1;
+        a[2][2 * k] += d0; a[2][2 * k + 1] += d1;
+        a[3][2 * k] += d0 * d0; a[3][2 * k + 1] += d1 * d1;
+        a[4][2 * k] += f0; a[4][2 * k + 1] += f1;
+        a[5][2 * k] += f0 * f0; a[5][2 * k + 1] += f1 * f1;
+        a[6][2 * k] = fminf(a[6][2 * k], x0); a[6][2 * k + 1] = fminf(a[6][2 * k + 1], x1);
+        a[7][2 * k] = fmaxf(a[7][2 * k], x0); a[7][2 * k + 1] = fmaxf(a[7][2 * k + 1], x1);
+      }
+    }
+  }
+  // cross-warp combine, one of the 8 per-lane channels at a time (fixed order over warps)
+  for (int k = 0; k < 8; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[w][q][lane] = a[q][k];
+    __syncthreads();
+    if (w == 0 && c0 + k < C) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float t = s[0][q][lane];
+        for (int ww = 1; ww < 8; ++ww) {
+          const float o = s[ww][q][lane];
+          t = q < 6 ? t + o : (q == 6 ? fminf(t, o) : fmaxf(t, o));
+        }
+        st[(static_cast<size_t>(b) * 8 + q) * C + c0 + k] = t;
+      }
+    }
+  }
+}
+
+// Collapse [B][8][C] image stats into: chan[0][c] = sum_b sum diff, chan[1][c] = sum_b sum diff^2,
+// chan[2][c] = min x, chan[3][c] = max x;  var[0] += sum_{b,c} Var_hw(x), var[1] += sum_{b,c} Var_hw(d)
+// (unbiased, utils.py:2015,2020).  One block per 32 channels, 8 image lanes; fixed order.
+static __global__ void channel_stats_finalize_kernel(const float* __restrict__ st, float* __restrict__ chan,
+                                              float* __restrict__ var_partial /* [gridDim.x][2] */, int B, int C,
+                                              int HW) {
+  __shared__ float s[8][6][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float sd = 0.f, sd2 = 0.f, mn = INFINITY, mx = -INFINITY, vx = 0.f, vd = 0.f;
+  if (c < C) {
+    const float inv = 1.f / static_cast<float>(HW), invm1 = HW > 1 ? 1.f / static_cast<float>(HW - 1) : 0.f;
+    for (int b = g; b < B; b += 8) {
+      const float* p = st + static_cast<size_t>(b) * 8 * C + c;
+      const float sx = p[0], sx2 = p[C], sdd = p[2 * C], sdd2 = p[3 * C];
+      sd += p[4 * C];
+      sd2 += p[5 * C];
+      mn = fminf(mn, p[6 * C]);
+      mx = fmaxf(mx, p[7 * C]);
+      vx += fmaxf(sx2 - sx * sx * inv, 0.f) * invm1;
+      vd += fmaxf(sdd2 - sdd * sdd * inv, 0.f) * invm1;
+    }
+  }
+  s[g][0][lane] = sd; s[g][1][lane] = sd2; s[g][2][lane] = mn; s[g][3][lane] = mx; s[g][4][lane] = vx; s[g][5][lane] = vd;
+  __syncthreads();
+  if (g == 0) {
+    float t[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) t[q] = s[0][q][lane];
+    for (int k = 1; k < 8; ++k) {
+      t[0] += s[k][0][lane]; t[1] += s[k][1][lane];
+      t[2] = fminf(t[2], s[k][2][lane]); t[3] = fmaxf(t[3], s[k][3][lane]);
+      t[4] += s[k][4][lane]; t[5] += s[k][5][lane];
+    }
+    if (c < C) {
+      chan[c] = t[0]; chan[C + c] = t[1]; chan[2 * C + c] = t[2]; chan[3 * C + c] = t[3];
+    } else {
+      t[4] = 0.f; t[5] = 0.f;
+    }
+    const float a = warp_sum(t[4]), bb = warp_sum(t[5]);
+    if (lane == 0) {
+      var_partial[blockIdx.x * 2] = a;
+      var_partial[blockIdx.x * 2 + 1] = bb;
+    }
+  }
+}
+
+// 2-D inputs (hw == 1): variance_explained takes the variance over the feature axis of each row
+// (utils.py:2022-2027).  One warp per row; rowvar[r*2] = Var_c(x[r,:]), [r*2+1] = Var_c(d[r,:]).
+static __global__ void row_variance_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, float* __restrict__ rowvar,
+                                    int T, int C) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= T) return;
+  float sx = 0.f, sx2 = 0.f, sd = 0.f, sd2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float a = __bfloat162float(x[static_cast<size_t>(r) * C + c]);
+    const float b = __bfloat162float(d[static_cast<size_t>(r) * C + c]);
+    sx += a; sx2 += a * a; sd += b; sd2 += b * b;
+  }
+  sx = warp_sum(sx); sx2 = warp_sum(sx2); sd = warp_sum(sd); sd2 = warp_sum(sd2);
+  if (lane == 0) {
+    const float inv = 1.f / C, invm1 = C > 1 ? 1.f / (C - 1) : 0.f;
+    rowvar[2 * r] = fmaxf(sx2 - sx * sx * inv, 0.f) * invm1;
+    rowvar[2 * r + 1] = fmaxf(sd2 - sd * sd * inv, 0.f) * invm1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ activity
+// act_bits [n_img, words] -> count[f] (#images in which unit f fired), n_active[b] (#units fired in image b).
+// utils.py:2047-2067.  grid.x over words (32 features each), 256 threads = 8 image lanes x 32 bit lanes.
+static __global__ void activity_count_kernel(const uint32_t* __restrict__ bits, int n_img, int words, int F,
+                                      float* __restrict__ count) {
+  __shared__ int s[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int wd = blockIdx.x;
+  int acc = 0;
+  for (int b = g; b < n_img; b += 8) acc += (bits[static_cast<size_t>(b) * words + wd] >> lane) & 1u;
+  s[g][lane] = acc;
+  __syncthreads();
+  if (g == 0) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][lane];
+    const int f = wd * 32 + lane;
+    if (f < F) count[f] = static_cast<float>(t);
+  }
+}
+static __global__ void activity_per_image_kernel(const uint32_t* __restrict__ bits, int n_img, int words,
+                                          int32_t* __restrict__ n_active, float* __restrict__ n_active_f) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= n_img) return;
+  int acc = 0;
+  for (int w = lane; w < words; w += 32) acc += __popc(bits[static_cast<size_t>(b) * words + w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (n_active) n_active[b] = acc;
+    if (n_active_f) n_active_f[b] = static_cast<float>(acc);
+  }
+}
+// count[f] (global, after any all-reduce) -> dead mask, frequency, number of dead units.
+static __global__ void activity_finalize_kernel(const float* __restrict__ count, int F, float n_images_global,
+                                         uint8_t* __restrict__ dead, float* __restrict__ freq,
+                                         float* __restrict__ n_dead_out) {
+  __shared__ float s[32];
+  float nd = 0.f;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const float c = count[f];
+    const bool is_dead = c == 0.f;
+    if (dead) dead[f] = is_dead ? 1 : 0;
+    // 1 - mean(inactive) evaluated as the reference does: inactive-count / B, then 1 - that (utils.py:2056)
+    if (freq) freq[f] = 1.f - (n_images_global - c) / n_images_global;
+    nd += is_dead ? 1.f : 0.f;
+  }
+  const float r = block_sum(nd, s);
+  if (threadIdx.x == 0 && n_dead_out) n_dead_out[0] = r;
+}
+
+// measure_inactive_units on a materialised tensor (API path): NCHW [B,F,HW] -> bits[b][f]; one warp per (b,f).
+template <typename T>
+static __global__ void activity_bits_nchw_kernel(const T* __restrict__ t, uint32_t* __restrict__ bits, int n_img, int F,
+                                          int HW, int words) {
+  const long long wid = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= static_cast<long long>(n_img) * F) return;
+  const int b = static_cast<int>(wid / F), f = static_cast<int>(wid % F);
+  const T* p = t + (static_cast<size_t>(b) * F + f) * HW;
+  bool any = false;
+  for (int i = lane; i < HW; i += 32) any |= (to_f32<T>(p[i]) != 0.f);
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0 && any) atomicOr(&bits[static_cast<size_t>(b) * words + (f >> 5)], 1u << (f & 31));
+}
+template <typename T>
+static __global__ void activity_bits_rows_kernel(const T* __restrict__ t, uint32_t* __restrict__ bits, long long n_rows,
+                                          int F, int words) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n_rows * words) return;
+  const long long r = i / words;
+  const int w = static_cast<int>(i % words);
+  uint32_t m = 0;
+  for (int j = 0; j < 32; ++j) {
+    const int f = w * 32 + j;
+    if (f < F && to_f32<T>(t[r * F + f]) != 0.f) m |= 1u << j;
+  }
+  bits[i] = m;
+}
+
+// ------------------------------------------------------------------------------------------------ gradients
+// Gradient assembly for the SaeMLP step.  All inputs are in "unscaled" units (see EpiDPre); s = 2/(T_global*C).
+//   g_wdec[i] = s * sum_k P_wd[k][i]
+//   g_wenc[f,c] = s * (sum_k P_we[k][f,c] - csum[f]*b_dec[c])     (G5 used x, not x - b_dec: rank-1 fix-up)
+//   g_benc[f] = s * csum[f]
+static __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, size_t n, float scale,
+                                  float* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < splits; ++k) a += part[static_cast<size_t>(k) * n + i];
+    out[i] = a * scale;
+  }
+}
+static __global__ void wenc_grad_kernel(const float* __restrict__ part, int splits, int F, int C,
+                                 const float* __restrict__ csum, const float* __restrict__ b_dec, float scale,
+                                 float* __restrict__ out) {
+  const size_t n = static_cast<size_t>(F) * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < splits; ++k) a += part[static_cast<size_t>(k) * n + i];
+    const int f = static_cast<int>(i / C), c = static_cast<int>(i % C);
+    out[i] = (a - csum[f] * b_dec[c]) * scale;
+  }
+}
+// vecmat partials: out[chunk][c] = sum_{f in chunk} v[f] * W[f,c]   (W row-major [F,C]); 256 threads over c.
+template <typename TW>
+static __global__ void vecmat_partial_kernel(const float* __restrict__ v, const TW* __restrict__ W, int F, int C,
+                                      float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = gridDim.y;
+  const int per = (F + chunks - 1) / chunks;
+  const int f0 = blockIdx.y * per, f1 = min(F, f0 + per);
+  if (c >= C) return;
+  float a = 0.f;
+  for (int f = f0; f < f1; ++f) a += v[f] * to_f32<TW>(W[static_cast<size_t>(f) * C + c]);
+  out[static_cast<size_t>(blockIdx.y) * C + c] = a;
+}
+// g_bdec[c] = s * (dsum[c] - sum_chunks vm[chunk][c])
+static __global__ void bdec_grad_kernel(const float* __restrict__ dsum, const float* __restrict__ vm, int chunks, int C,
+                                 float scale, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int k = 0; k < chunks; ++k) a += vm[static_cast<size_t>(k) * C + c];
+  out[c] = (dsum[c] - a) * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ optimiser
+struct AdamCoef {
+  float lr_over_bc1;    // lr / (1 - beta1^t)
+  float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^t)
+  float beta1, beta2, eps;
+};
+__device__ __forceinline__ float adam_elem(float w, float g, float& m, float& v, const AdamCoef& k) {
+  // torch.optim.Adam single-tensor update: m.lerp_(g, 1-b1); v = b2*v + (1-b2) g^2;
+  // w -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+  m = m + (g - m) * (1.f - k.beta1);
+  v = v * k.beta2 + (1.f - k.beta2) * g * g;
+  const float denom = sqrtf(v) * k.inv_sqrt_bc2 + k.eps;
+  return w - k.lr_over_bc1 * (m / denom);
+}
+static __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, AdamCoef k, bf16* __restrict__ w_bf16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float mi = m[i], vi = v[i];
+    const float wn = adam_elem(w[i], g[i], mi, vi, k);
+    w[i] = wn; m[i] = mi; v[i] = vi;
+    if (w_bf16) w_bf16[i] = __float2bfloat16_rn(wn);
+  }
+}
+// ConstrainedAdam on decoder.weight [C,F] (utils.py:65-81): per column f
+//   w^ = w/|w|;  g' = g - (g.w^) w^;  Adam(g');  w /= |w|.      block = 32 columns x 8 row lanes.
+static __global__ void constrained_adam_decoder_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m,
+                                                float* __restrict__ v, int C, int F, AdamCoef k) {
+  __shared__ float s[8][33];
+  __shared__ float col_a[32], col_b[32];
+  const int lane = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + lane;
+  const bool ok = f < F;
+  // pass 1: |w|^2 and g.w
+  float nw = 0.f, gw = 0.f;
+  if (ok)
+    for (int c = gl; c < C; c += 8) {
+      const float wi = w[static_cast<size_t>(c) * F + f], gi = g[static_cast<size_t>(c) * F + f];
+      nw += wi * wi;
+      gw += gi * wi;
+    }
+  s[gl][lane] = nw;
+  __syncthreads();
+  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_a[lane] = t; }
+  __syncthreads();
+  s[gl][lane] = gw;
+  __syncthreads();
+  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_b[lane] = t; }
+  __syncthreads();
+  const float norm = sqrtf(col_a[lane]);
+  const float proj = col_b[lane] / norm;  // g . w^
+  // pass 2: projected gradient (written back, as the reference mutates p.grad), Adam, new norm
+  float nn = 0.f;
+  if (ok)
+    for (int c = gl; c < C; c += 8) {
+      const size_t i = static_cast<size_t>(c) * F + f;
+      const float wi = w[i];
+      const float gp = g[i] - proj * (wi / norm);
+      g[i] = gp;
+      float mi = m[i], vi = v[i];
+      const float wn = adam_elem(wi, gp, mi, vi, k);
+      w[i] = wn; m[i] = mi; v[i] = vi;
+      nn += wn * wn;
+    }
+  __syncthreads();
+  s[gl][lane] = nn;
+  __syncthreads();
+  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_a[lane] = t; }
+  __syncthreads();
+  const float inv = 1.f / sqrtf(col_a[lane]);
+  if (ok)
+    for (int c = gl; c < C; c += 8) {
+      const size_t i = static_cast<size_t>(c) * F + f;
+      w[i] *= inv;
+    }
+}
+// Column renormalisation of a [C,F] matrix (sae_mlp.py:39,138).
+static __global__ void renorm_columns_kernel(float* __restrict__ w, int C, int F) {
+  __shared__ float s[8][33];
+  __shared__ float col[32];
+  const int lane = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + lane;
+  float nw = 0.f;
+  if (f < F)
+    for (int c = gl; c < C; c += 8) { const float wi = w[static_cast<size_t>(c) * F + f]; nw += wi * wi; }
+  s[gl][lane] = nw;
+  __syncthreads();
+  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col[lane] = t; }
+  __syncthreads();
+  const float inv = 1.f / sqrtf(col[lane]);
+  if (f < F)
+    for (int c = gl; c < C; c += 8) w[static_cast<size_t>(c) * F + f] *= inv;
+}
+
+// Dead-unit scatter (sae_mlp.py:133-135,148-176): rows of W_enc / entries of b_enc / columns of W_dec of dead
+// units are replaced and their Adam moments zeroed.
+static __global__ void reinit_scatter_kernel(const uint8_t* __restrict__ dead, int F, int C, float* w_enc, float* b_enc,
+                                      float* w_dec, const float* __restrict__ new_w_enc,
+                                      const float* __restrict__ new_w_dec, float new_b_enc, float* m_we, float* v_we,
+                                      float* m_be, float* v_be, float* m_wd, float* v_wd) {
+  const size_t n = static_cast<size_t>(F) * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    {  // encoder layout [F,C]
+      const int f = static_cast<int>(i / C);
+      if (dead[f]) {
+        w_enc[i] = new_w_enc[i];
+        if (m_we) { m_we[i] = 0.f; v_we[i] = 0.f; }
+        if (i % C == 0) {
+          b_enc[f] = new_b_enc;
+          if (m_be) { m_be[f] = 0.f; v_be[f] = 0.f; }
+        }
+      }
+    }
+    {  // decoder layout [C,F]
+      const int f = static_cast<int>(i % F);
+      if (dead[f]) {
+        w_dec[i] = new_w_dec[i];
+        if (m_wd) { m_wd[i] = 0.f; v_wd[i] = 0.f; }
+      }
+    }
+  }
+}
+
+}  // namespace svb

@@ -1,0 +1,184 @@
+// Handle, error plumbing and the bump-allocated workspace shared by the svb_* entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "../../include/svb.h"
+#include "gemm_host.cuh"
+#include "epilogues.cuh"
+#include "kernels_misc.cuh"
+#include "kernels_ie.cuh"
+
+namespace svb {
+
+inline char* err_buf() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define SVB_CUDA(expr)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t e_ = (expr);                                                                              \
+    if (e_ != cudaSuccess) return svb::fail(SVB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+#define SVB_LAUNCH_CHECK(what)                                                                              \
+  do {                                                                                                      \
+    cudaError_t e_ = cudaGetLastError();                                                                    \
+    if (e_ != cudaSuccess) return svb::fail(SVB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
+  } while (0)
+#define SVB_TRY(expr)                \
+  do {                               \
+    int rc_ = (expr);                \
+    if (rc_ != 0) return rc_;        \
+  } while (0)
+#define SVB_GEMM(expr, what)                                                             \
+  do {                                                                                   \
+    int rc_ = (expr);                                                                    \
+    if (rc_ != 0) return svb::fail(rc_, "GEMM %s could not be launched (rc=%d)", what, rc_); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+inline int grid_for(size_t n, int threads = 256, int cap = 148 * 16) {
+  size_t g = (n + threads - 1) / threads;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// Bump allocator over one cudaMalloc'd arena.  A call first measures (dry = true), grows the arena if needed, then
+// carves for real; two calls with the same shapes carve identical addresses (step_grads / step_apply rely on it).
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool dry = false;
+  template <typename T>
+  T* take(size_t n) {
+    const size_t bytes = align_up(n * sizeof(T), 256);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace svb
+
+struct svb_handle {
+  int device = 0;
+  int sms = 0;
+  svb::Arena arena;
+  // description of the flat reduction buffer of the last *_step_grads call
+  float* gradbuf = nullptr;
+  int64_t sum_elems = 0, max_elems = 0;
+};
+
+namespace svb {
+
+inline int ensure_arena(svb_handle* h, size_t need) {
+  if (need <= h->arena.cap) return 0;
+  if (h->arena.base) {
+    cudaError_t e = cudaFree(h->arena.base);  // synchronises with any work still using the old arena
+    h->arena.base = nullptr;
+    h->arena.cap = 0;
+    if (e != cudaSuccess) return fail(SVB_ERR_CUDA, "cudaFree failed: %s", cudaGetErrorString(e));
+  }
+  const size_t want = align_up(need + need / 8, 1 << 20);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SVB_ERR_NOMEM, "workspace of %zu bytes could not be allocated: %s", want, cudaGetErrorString(e));
+  }
+  h->arena.base = static_cast<uint8_t*>(p);
+  h->arena.cap = want;
+  return 0;
+}
+
+inline int check_acts(const svb_acts* x) {
+  if (!x || !x->x) return fail(SVB_ERR_BAD_ARG, "activations pointer is null");
+  if (x->dtype != SVB_F32 && x->dtype != SVB_BF16) return fail(SVB_ERR_BAD_ARG, "bad activation dtype %d", x->dtype);
+  if (x->layout != SVB_TOKENS && x->layout != SVB_NCHW) return fail(SVB_ERR_BAD_ARG, "bad layout %d", x->layout);
+  if (x->n_images <= 0 || x->hw <= 0 || x->C <= 0) return fail(SVB_ERR_BAD_ARG, "empty activation batch");
+  if (x->C % 8) return fail(SVB_ERR_UNSUPPORTED, "act_size C=%d must be a multiple of 8", x->C);
+  if (x->n_images * static_cast<long long>(x->hw) >= (1LL << 31)) return fail(SVB_ERR_UNSUPPORTED, "too many tokens");
+  return 0;
+}
+
+// Token-major bf16 view of the SAE input: zero-copy when the caller already provides it, else packed into `buf`.
+inline bool acts_are_bf16_tokens(const svb_acts* x) {
+  return x->dtype == SVB_BF16 && (x->layout == SVB_TOKENS || x->hw == 1) &&
+         (reinterpret_cast<uintptr_t>(x->x) & 15) == 0;
+}
+inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
+  const long long T = x->n_images * static_cast<long long>(x->hw);
+  if (x->layout == SVB_TOKENS || x->hw == 1) {
+    const size_t n = static_cast<size_t>(T) * x->C;
+    if (x->dtype == SVB_F32)
+      convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const float*>(x->x), buf, n);
+    else
+      convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, n);
+  } else {
+    dim3 grid(cdiv(x->hw, 32), cdiv(x->C, 32), static_cast<unsigned>(x->n_images));
+    dim3 block(32, 8);
+    if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
+    if (x->dtype == SVB_F32)
+      pack_nchw_to_tokens_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x->x), buf, x->C, x->hw);
+    else
+      pack_nchw_to_tokens_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw);
+  }
+  SVB_LAUNCH_CHECK("pack_acts");
+  return 0;
+}
+inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int hw, int C, void* out, int out_dtype,
+                     int out_layout) {
+  const size_t n = static_cast<size_t>(n_images) * hw * C;
+  if (out_layout == SVB_TOKENS || hw == 1) {
+    if (out_dtype == SVB_F32) convert_kernel<bf16, float><<<grid_for(n), 256, 0, st>>>(tok, static_cast<float*>(out), n);
+    else convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(tok, static_cast<bf16*>(out), n);
+  } else {
+    if (n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
+    dim3 grid(cdiv(hw, 32), cdiv(C, 32), static_cast<unsigned>(n_images));
+    dim3 block(32, 8);
+    if (out_dtype == SVB_F32)
+      unpack_tokens_to_nchw_kernel<bf16, float><<<grid, block, 0, st>>>(tok, static_cast<float*>(out), C, hw);
+    else
+      unpack_tokens_to_nchw_kernel<bf16, bf16><<<grid, block, 0, st>>>(tok, static_cast<bf16*>(out), C, hw);
+  }
+  SVB_LAUNCH_CHECK("unpack");
+  return 0;
+}
+
+// out[j] = scale * sum_i in[i, j] over R rows with a fixed order; `stage` holds up to 32*N floats.
+inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float scale, float* stage, float* out) {
+  int chunks = R >= 256 ? 32 : 1;
+  if (chunks > 1) {
+    reduce_rows_kernel<<<dim3(cdiv(N, 32), chunks), 256, 0, st>>>(in, stage, R, N, static_cast<size_t>(N), 1.f);
+    reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(stage, out, chunks, N, static_cast<size_t>(N), scale);
+  } else {
+    reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(in, out, R, N, static_cast<size_t>(N), scale);
+  }
+  SVB_LAUNCH_CHECK("reduce_rows");
+  return 0;
+}
+
+inline AdamCoef adam_coef(const svb_opt_config* o) {
+  AdamCoef k;
+  const double bc1 = 1.0 - pow(static_cast<double>(o->beta1), o->step);
+  const double bc2 = 1.0 - pow(static_cast<double>(o->beta2), o->step);
+  k.lr_over_bc1 = static_cast<float>(static_cast<double>(o->lr) / bc1);
+  k.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  k.beta1 = o->beta1;
+  k.beta2 = o->beta2;
+  k.eps = o->eps;
+  return k;
+}
+
+}  // namespace svb

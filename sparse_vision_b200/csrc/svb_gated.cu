@@ -1,0 +1,339 @@
+// GatedSae forward and fused training step (models/gated_sae.py:28-56, losses/sparse_loss.py:68-76,
+// utils.py:2455-2473, model_pipeline.py:380-388).  Six GEMMs: shared gate/magnitude encoder, decoder, frozen-decoder
+// "via gate" pass (loss value only — it is computed under no_grad in the reference and carries no gradient), dE,
+// dW_dec and a single dW_gate GEMM whose operand A' = dPi + exp(r_mag) * dMag merges both sub-layer gradients.
+#include "svb_common.cuh"
+#include "epilogues_gated.cuh"
+
+using namespace svb;
+
+namespace {
+
+struct GatedPlan {
+  long long T, n_img;
+  int C, F, hw, words, tiles_m, tn_f, tn_c, s_wd, s_wg;
+  bool zero_copy_x;
+  bf16 *X, *Wgb, *Wdb, *E, *RP, *A, *D, *DIFF;
+  float *dot, *exp_r, *l1_part, *sq_part, *aux_part, *cs_mag, *cs_pi, *cs_mage, *stage, *csum_mag, *csum_pi,
+      *csum_mage, *csum_a, *st, *chan, *var_part, *rowvar, *P_wd, *P_wg, *vm, *nact_f, *flat;
+  uint32_t* act_bits;
+  size_t o_gwg, o_gbg, o_gbm, o_gr, o_gwd, o_gbd, o_sums, o_chansq, o_count, o_max, sum_elems, max_elems;
+};
+
+constexpr int kVmChunks = 32;
+
+void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
+  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images;
+  p.T = x->n_images * static_cast<long long>(x->hw);
+  p.words = (F + 31) / 32;
+  p.tiles_m = cdiv(p.T, kBlockM);
+  p.tn_f = cdiv(F, 256);
+  p.tn_c = cdiv(p.C, 256);
+  p.zero_copy_x = acts_are_bf16_tokens(x);
+  const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
+  p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
+  p.Wgb = a.take<bf16>(FC);
+  p.Wdb = a.take<bf16>(FC);
+  p.dot = a.take<float>(F);
+  p.exp_r = a.take<float>(F);
+  p.E = a.take<bf16>(TF);
+  p.RP = a.take<bf16>(TF);
+  p.D = a.take<bf16>(TC);
+  if (!train) return;
+  p.A = a.take<bf16>(TF);
+  p.DIFF = a.take<bf16>(TC);
+  p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 4);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
+  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
+  p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.cs_pi = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.cs_mage = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
+  p.csum_mag = a.take<float>(F);
+  p.csum_pi = a.take<float>(F);
+  p.csum_mage = a.take<float>(F);
+  p.csum_a = a.take<float>(F);
+  p.st = a.take<float>(p.hw > 1 ? static_cast<size_t>(p.n_img) * 8 * p.C : 8 * p.C);
+  p.chan = a.take<float>(4 * p.C);
+  p.var_part = a.take<float>(2 * cdiv(p.C, 32) + 2);
+  p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
+  p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
+  p.s_wg = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
+  p.P_wg = a.take<float>(static_cast<size_t>(p.s_wg) * FC);
+  p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
+  p.nact_f = a.take<float>(p.n_img);
+  p.o_gwg = 0; p.o_gbg = FC; p.o_gbm = FC + F; p.o_gr = FC + 2 * static_cast<size_t>(F);
+  p.o_gwd = FC + 3 * static_cast<size_t>(F);
+  p.o_gbd = 2 * FC + 3 * static_cast<size_t>(F);
+  p.o_sums = p.o_gbd + p.C;
+  p.o_chansq = p.o_sums + 8;
+  p.o_count = p.o_chansq + p.C;
+  p.sum_elems = p.o_count + F;
+  p.o_max = p.sum_elems;
+  p.max_elems = 2 * static_cast<size_t>(p.C);
+  p.flat = a.take<float>(p.sum_elems + p.max_elems);
+}
+
+int plan(svb_handle* h, GatedPlan& p, const svb_acts* x, int F, bool train) {
+  Arena dry;
+  dry.dry = true;
+  carve(dry, p, x, F, train);
+  SVB_TRY(ensure_arena(h, dry.off));
+  h->arena.off = 0;
+  h->arena.dry = false;
+  carve(h->arena, p, x, F, train);
+  return 0;
+}
+
+int check_params(const svb_acts* x, const svb_gated_params* p) {
+  SVB_TRY(check_acts(x));
+  if (!p || !p->w_gate || !p->b_gate || !p->b_mag || !p->r_mag || !p->w_dec || !p->b_dec)
+    return fail(SVB_ERR_BAD_ARG, "null Gated-SAE parameter");
+  if (p->F <= 0 || p->F % 8) return fail(SVB_ERR_UNSUPPORTED, "hidden_size F=%d must be a positive multiple of 8", p->F);
+  return 0;
+}
+
+__global__ void exp_kernel(const float* __restrict__ r, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = expf(r[i]);
+}
+
+// per-feature vector gradients:  csum_a = csum_pi + exp(r)*csum_mag;  gb_gate = s*csum_pi;  gb_mag = s*csum_mag;
+// gr_mag = s*(csum_mage - b_mag*csum_mag)      (d mag_pre / d r = exp(r)*raw = mag_pre - b_mag)
+__global__ void gated_vec_grads_kernel(const float* __restrict__ cs_mag, const float* __restrict__ cs_pi,
+                                       const float* __restrict__ cs_mage, const float* __restrict__ exp_r,
+                                       const float* __restrict__ b_mag, float s, int F, float* __restrict__ csum_a,
+                                       float* __restrict__ g_bgate, float* __restrict__ g_bmag,
+                                       float* __restrict__ g_r) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float m = cs_mag[f], pi = cs_pi[f];
+  csum_a[f] = pi + exp_r[f] * m;
+  g_bgate[f] = s * pi;
+  g_bmag[f] = s * m;
+  g_r[f] = s * (cs_mage[f] - b_mag[f] * m);
+}
+
+__global__ void gated_stats_pack_kernel(const float* __restrict__ chan, const float* __restrict__ var_part,
+                                        int n_var_part, const float* __restrict__ rowvar, long long n_rows, int C,
+                                        float* __restrict__ flat, size_t o_sums, size_t o_chansq, size_t o_max) {
+  __shared__ float s[32];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    flat[o_chansq + c] = chan[C + c];
+    flat[o_max + c] = chan[3 * C + c];
+    flat[o_max + C + c] = -chan[2 * C + c];
+  }
+  float vx = 0.f, vd = 0.f;
+  if (n_rows > 0) {
+    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) { vx += rowvar[2 * r]; vd += rowvar[2 * r + 1]; }
+  } else {
+    for (int i = threadIdx.x; i < n_var_part; i += blockDim.x) { vx += var_part[2 * i]; vd += var_part[2 * i + 1]; }
+  }
+  const float a = block_sum(vx, s);
+  const float b = block_sum(vd, s);
+  if (threadIdx.x == 0) {
+    flat[o_sums + 3] = a;
+    flat[o_sums + 4] = b;
+    flat[o_sums + 6] = 0.f;
+    flat[o_sums + 7] = 0.f;
+  }
+}
+
+__global__ void gated_stats_finalize_kernel(const float* __restrict__ flat, size_t o_sums, size_t o_chansq,
+                                            size_t o_max, int C, int F, float T_g, float B_g, float lambda,
+                                            int expansion, float* __restrict__ stats) {
+  __shared__ float s[32];
+  float r = 0.f, nr = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float rm = sqrtf(flat[o_chansq + c] / T_g);
+    r += rm;
+    nr += rm / (flat[o_max + c] + flat[o_max + C + c]);
+  }
+  const float rs = block_sum(r, s);
+  const float nrs = block_sum(nr, s);
+  if (threadIdx.x == 0) {
+    const float rec = flat[o_sums + 0] / (T_g * C);
+    const float l1 = flat[o_sums + 1] / (T_g * F);
+    const float aux = flat[o_sums + 2] / (T_g * C);
+    stats[SVB_STAT_REC] = rec;
+    stats[SVB_STAT_L1] = l1;
+    stats[SVB_STAT_AUX] = aux;
+    stats[SVB_STAT_LOSS] = rec + lambda * l1 + aux;   // utils.py:2473
+    stats[SVB_STAT_RMSE] = rs / C;
+    stats[SVB_STAT_NRMSE] = nrs / C;
+    stats[SVB_STAT_VAR_EXPL] = 1.f - flat[o_sums + 4] / flat[o_sums + 3];
+    stats[SVB_STAT_SPARSITY] = (flat[o_sums + 5] / B_g) / (static_cast<float>(F) / expansion);
+  }
+}
+
+int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p) {
+  prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_gate, nullptr, p->b_dec, pl.Wgb, nullptr, pl.dot, pl.F, pl.C);
+  const size_t n = static_cast<size_t>(pl.F) * pl.C;
+  convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n);
+  exp_kernel<<<cdiv(pl.F, 256), 256, 0, st>>>(p->r_mag, pl.exp_r, pl.F);
+  SVB_LAUNCH_CHECK("gated prep");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                                 const svb_gated_forward_out* out) {
+  if (!h || !out) return fail(SVB_ERR_BAD_ARG, "null handle/out");
+  SVB_TRY(check_params(x, p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GatedPlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, false));
+  h->gradbuf = nullptr;
+  const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  SVB_TRY(run_prep(st, pl, p));
+  const int T = static_cast<int>(pl.T);
+  EpiGatedEnc::Params e1{};
+  e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
+  e1.e_bf16 = (out->enc && out->enc_dtype == SVB_BF16) ? static_cast<bf16*>(out->enc) : pl.E;
+  e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
+  e1.rp_bf16 = (out->relu_pi && out->relu_pi_dtype == SVB_BF16) ? static_cast<bf16*>(out->relu_pi) : pl.RP;
+  e1.rp_f32 = (out->relu_pi && out->relu_pi_dtype == SVB_F32) ? static_cast<float*>(out->relu_pi) : nullptr;
+  e1.hw = pl.hw; e1.words = pl.words;
+  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, pl.C, pl.Wgb, pl.C, T, pl.F, pl.C, 1, e1)), "gated enc");
+  if (out->dec) {
+    EpiDec::Params e2{};
+    e2.bias = p->b_dec;
+    e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
+    e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
+    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
+  }
+  if (out->via) {
+    EpiDec::Params e3{};
+    e3.bias = p->b_dec;
+    e3.d_bf16 = out->via_dtype == SVB_BF16 ? static_cast<bf16*>(out->via) : nullptr;
+    e3.d_f32 = out->via_dtype == SVB_F32 ? static_cast<float*>(out->via) : nullptr;
+    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.rp_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e3)), "via");
+  }
+  return 0;
+}
+
+extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                                    float lambda_sparse, int64_t global_tokens, const svb_train_out* out) {
+  if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  SVB_TRY(check_params(x, p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GatedPlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, true));
+  const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
+  const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
+  const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  SVB_TRY(run_prep(st, pl, p));
+  fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
+      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u);
+
+  EpiGatedEnc::Params e1{};
+  e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
+  e1.e_bf16 = pl.E; e1.rp_bf16 = pl.RP; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
+  e1.hw = pl.hw; e1.words = pl.words;
+  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
+  EpiDec::Params e2{};
+  e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
+  EpiDec::Params e2v{};
+  e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v)), "via");
+  if (pl.hw > 1) {
+    channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw);
+    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw);
+  } else {
+    channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T);
+    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T);
+    row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C);
+  }
+  SVB_LAUNCH_CHECK("channel_stats");
+  EpiGatedDPre::Params e3{};
+  e3.e = pl.E; e3.rp = pl.RP; e3.exp_r = pl.exp_r; e3.a_out = pl.A;
+  e3.colsum_mag = pl.cs_mag; e3.colsum_pi = pl.cs_pi; e3.colsum_mage = pl.cs_mage;
+  e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
+  e3.block_n = 256;
+  SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
+  const size_t FC = static_cast<size_t>(F) * C;
+  EpiStore::Params e4{pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  EpiStore::Params e5{pl.P_wg, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
+
+  const float s = static_cast<float>(2.0 / (Tg * C));
+  float* flat = pl.flat;
+  SVB_TRY(reduce_rows(st, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
+  SVB_TRY(reduce_rows(st, pl.cs_pi, pl.tiles_m, F, 1.f, pl.stage, pl.csum_pi));
+  SVB_TRY(reduce_rows(st, pl.cs_mage, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mage));
+  gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.csum_pi, pl.csum_mage, pl.exp_r, p->b_mag, s, F,
+                                                      pl.csum_a, flat + pl.o_gbg, flat + pl.o_gbm, flat + pl.o_gr);
+  sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd);
+  wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg);
+  vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm);
+  bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 2);
+  gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+                                             pl.o_sums, pl.o_chansq, pl.o_max);
+  activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count);
+  activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
+                                                               out ? out->activity.n_active : nullptr, pl.nact_f);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5);
+  SVB_LAUNCH_CHECK("gated grad assembly");
+  if (out && out->dec_out)
+    SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
+  h->gradbuf = flat;
+  h->sum_elems = static_cast<int64_t>(pl.sum_elems);
+  h->max_elems = static_cast<int64_t>(pl.max_elems);
+  return 0;
+}
+
+extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                                    const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                                    int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
+                                    const svb_train_out* out) {
+  if (!h || !adam || !opt) return fail(SVB_ERR_BAD_ARG, "null handle/adam/opt");
+  SVB_TRY(check_params(x, p));
+  for (int i = 0; i < 6; ++i)
+    if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);
+  if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GatedPlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, true));
+  if (pl.flat != h->gradbuf) return fail(SVB_ERR_BAD_ARG, "svb_gated_step_apply called without a matching svb_gated_step_grads");
+  const int C = pl.C, F = pl.F;
+  const size_t FC = static_cast<size_t>(F) * C;
+  float* flat = pl.flat;
+  const AdamCoef k = adam_coef(opt);
+  adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC, k, nullptr);
+  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_gate, flat + pl.o_gbg, adam->m[1], adam->v[1], F, k, nullptr);
+  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_mag, flat + pl.o_gbm, adam->m[2], adam->v[2], F, k, nullptr);
+  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], F, k, nullptr);
+  if (opt->optimizer == SVB_CONSTRAINED_ADAM)
+    constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k);
+  else
+    adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC, k, nullptr);
+  adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], C, k, nullptr);
+  SVB_LAUNCH_CHECK("gated adam");
+  const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
+  const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
+  if (out && out->stats)
+    gated_stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
+                                                   expansion_factor, out->stats);
+  if (out && (out->activity.dead || out->activity.freq || out->stats))
+    activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
+                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr);
+  SVB_LAUNCH_CHECK("gated finalize");
+  return 0;
+}
+
+extern "C" int svb_gated_train_step(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
+                                    const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                                    int32_t expansion_factor, const svb_train_out* out) {
+  SVB_TRY(svb_gated_step_grads(h, stream, x, p, lambda_sparse, 0, out));
+  return svb_gated_step_apply(h, stream, x, p, adam, opt, lambda_sparse, expansion_factor, 0, 0, out);
+}

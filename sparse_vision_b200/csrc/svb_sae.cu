@@ -1,0 +1,328 @@
+// SaeMLP forward and the fused SaeMLP training step (model_pipeline.py:363-432 train branch) as a stream of
+// tcgen05 GEMMs with fused epilogues plus a handful of small memory-bound kernels.
+//
+// Data flow of one step (T tokens, C channels, F features; all big tensors bf16, token-major):
+//   prep      W_enc,W_dec -> bf16 shadows; fold = b_enc - W_enc b_dec
+//   pack      x (NCHW / fp32) -> X [T,C]                                  (skipped when x is already bf16 tokens)
+//   G1 enc    E = relu(X W_enc^T + fold)              + activity bits + sum|E| partials
+//   G2 dec    D = E W_dec^T + b_dec; DIFF = D - X     + sum DIFF^2 partials
+//   stats     per-(image,channel) sums of X, D, DIFF  -> rmse/nrmse, variance explained, colsum(DIFF)
+//   G3 dE     DP = 1[E>0] (DIFF W_dec + lambda*C/(2F)) + per-feature column sums (-> db_enc)
+//   G4        P_wd = DIFF^T E      (split-K over tokens, fp32 partials)
+//   G5        P_we = DP^T X        (split-K over tokens, fp32 partials)
+//   grads     flat buffer [gW_enc | gb_enc | gW_dec | gb_dec | loss sums | max section], scaled by 2/(T_global*C)
+//   -- data parallel: the caller all-reduces the flat buffer here --
+//   adam      (Constrained)Adam on all four tensors; stats + activity outputs finalised
+// The backward runs in units of T*C/2 (dPre' = dPre * T*C/2) so bf16 intermediates stay O(1).
+#include "svb_common.cuh"
+
+using namespace svb;
+
+namespace {
+
+struct SaePlan {
+  long long T;
+  int C, F, hw, words;
+  long long n_img;
+  int tiles_m, tn_f, tn_c;
+  int s_wd, s_we;  // split-K slices
+  bool zero_copy_x;
+  // workspace
+  bf16 *X, *Web, *Wdb, *E, *DP, *D, *DIFF;
+  float *fold, *l1_part, *sq_part, *colsum_part, *stage, *csum, *st, *chan, *var_part, *rowvar, *P_wd, *P_we, *vm,
+      *nact_f, *flat;
+  uint32_t* act_bits;
+  // flat buffer offsets
+  size_t o_gwe, o_gbe, o_gwd, o_gbd, o_sums, o_chansq, o_count, o_max;
+  size_t sum_elems, max_elems;
+};
+
+constexpr int kVmChunks = 32;
+
+void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
+  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images;
+  p.T = x->n_images * static_cast<long long>(x->hw);
+  p.words = (F + 31) / 32;
+  p.tiles_m = cdiv(p.T, kBlockM);
+  p.tn_f = cdiv(F, 256);
+  p.tn_c = cdiv(p.C, 256);
+  p.zero_copy_x = acts_are_bf16_tokens(x);
+  const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
+  p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
+  p.Web = a.take<bf16>(FC);
+  p.Wdb = a.take<bf16>(FC);
+  p.fold = a.take<float>(F);
+  p.E = a.take<bf16>(TF);
+  p.D = a.take<bf16>(TC);
+  if (!train) return;
+  p.DP = a.take<bf16>(TF);
+  p.DIFF = a.take<bf16>(TC);
+  p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 4);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
+  p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
+  p.csum = a.take<float>(F);
+  p.st = a.take<float>(p.hw > 1 ? static_cast<size_t>(p.n_img) * 8 * p.C : 8 * p.C);
+  p.chan = a.take<float>(4 * p.C);
+  p.var_part = a.take<float>(2 * cdiv(p.C, 32) + 2);
+  p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
+  p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
+  p.s_we = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
+  p.P_we = a.take<float>(static_cast<size_t>(p.s_we) * FC);
+  p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
+  p.nact_f = a.take<float>(p.n_img);
+  p.o_gwe = 0; p.o_gbe = FC; p.o_gwd = FC + F; p.o_gbd = 2 * FC + F;
+  p.o_sums = 2 * FC + F + p.C;
+  p.o_chansq = p.o_sums + 8;
+  p.o_count = p.o_chansq + p.C;
+  p.sum_elems = p.o_count + F;
+  p.o_max = p.sum_elems;
+  p.max_elems = 2 * static_cast<size_t>(p.C);
+  p.flat = a.take<float>(p.sum_elems + p.max_elems);
+}
+
+int plan(svb_handle* h, SaePlan& p, const svb_acts* x, int F, bool train) {
+  Arena dry;
+  dry.dry = true;
+  carve(dry, p, x, F, train);
+  SVB_TRY(ensure_arena(h, dry.off));
+  h->arena.off = 0;
+  h->arena.dry = false;
+  carve(h->arena, p, x, F, train);
+  return 0;
+}
+
+int check_params(const svb_acts* x, const svb_sae_params* p) {
+  SVB_TRY(check_acts(x));
+  if (!p || !p->w_enc || !p->b_enc || !p->w_dec || !p->b_dec) return fail(SVB_ERR_BAD_ARG, "null SAE parameter");
+  if (p->F <= 0 || p->F % 8) return fail(SVB_ERR_UNSUPPORTED, "hidden_size F=%d must be a positive multiple of 8", p->F);
+  return 0;
+}
+
+// sums section layout: [0]=sum sq, [1]=sum l1, [2]=sum aux sq, [3]=sum var x, [4]=sum var d, [5]=sum n_active
+__global__ void stats_pack_kernel(const float* __restrict__ chan, const float* __restrict__ var_part, int n_var_part,
+                                  const float* __restrict__ rowvar, long long n_rows, int C, float* __restrict__ flat,
+                                  size_t o_sums, size_t o_chansq, size_t o_max) {
+  __shared__ float s[32];
+  // per-channel sum diff^2 and max / -min of x
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    flat[o_chansq + c] = chan[C + c];
+    flat[o_max + c] = chan[3 * C + c];
+    flat[o_max + C + c] = -chan[2 * C + c];
+  }
+  float vx = 0.f, vd = 0.f;
+  if (n_rows > 0) {
+    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) { vx += rowvar[2 * r]; vd += rowvar[2 * r + 1]; }
+  } else {
+    for (int i = threadIdx.x; i < n_var_part; i += blockDim.x) { vx += var_part[2 * i]; vd += var_part[2 * i + 1]; }
+  }
+  const float a = block_sum(vx, s);
+  const float b = block_sum(vd, s);
+  if (threadIdx.x == 0) {
+    flat[o_sums + 3] = a;
+    flat[o_sums + 4] = b;
+    flat[o_sums + 6] = 0.f;
+    flat[o_sums + 7] = 0.f;
+  }
+}
+
+// For 2-D inputs the per-channel stats come from one "image" holding all rows.
+__global__ void stats_finalize_kernel(const float* __restrict__ flat, size_t o_sums, size_t o_chansq, size_t o_max,
+                                      int C, int F, float T_g, float B_g, float lambda, int expansion,
+                                      float* __restrict__ stats) {
+  __shared__ float s[32];
+  float r = 0.f, nr = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float rm = sqrtf(flat[o_chansq + c] / T_g);
+    const float range = flat[o_max + c] + flat[o_max + C + c];  // max - min
+    r += rm;
+    nr += rm / range;
+  }
+  const float rs = block_sum(r, s);
+  const float nrs = block_sum(nr, s);
+  if (threadIdx.x == 0) {
+    const float rec = flat[o_sums + 0] / (T_g * C);
+    const float l1 = flat[o_sums + 1] / (T_g * F);
+    const float aux = flat[o_sums + 2] / (T_g * C);
+    stats[SVB_STAT_REC] = rec;
+    stats[SVB_STAT_L1] = l1;
+    stats[SVB_STAT_AUX] = aux;
+    stats[SVB_STAT_LOSS] = rec + lambda * l1 + aux;
+    stats[SVB_STAT_RMSE] = rs / C;
+    stats[SVB_STAT_NRMSE] = nrs / C;
+    stats[SVB_STAT_VAR_EXPL] = 1.f - flat[o_sums + 4] / flat[o_sums + 3];
+    stats[SVB_STAT_SPARSITY] = (flat[o_sums + 5] / B_g) / (static_cast<float>(F) / expansion);
+  }
+}
+
+int run_prep(cudaStream_t st, const SaePlan& pl, const svb_sae_params* p) {
+  prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, pl.Web, pl.fold, nullptr, pl.F, pl.C);
+  const size_t n = static_cast<size_t>(pl.F) * pl.C;
+  convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n);
+  SVB_LAUNCH_CHECK("prep");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                               const svb_sae_forward_out* out) {
+  if (!h || !out) return fail(SVB_ERR_BAD_ARG, "null handle/out");
+  SVB_TRY(check_params(x, p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SaePlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, false));
+  h->gradbuf = nullptr;
+  const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  SVB_TRY(run_prep(st, pl, p));
+  const int T = static_cast<int>(pl.T);
+  EpiEnc::Params e1{};
+  e1.bias = pl.fold;
+  e1.e_bf16 = (out->enc && out->enc_dtype == SVB_BF16) ? static_cast<bf16*>(out->enc) : pl.E;
+  e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
+  e1.pre_f32 = out->pre;
+  e1.hw = pl.hw; e1.words = pl.words;
+  SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
+  if (out->dec) {
+    EpiDec::Params e2{};
+    e2.bias = p->b_dec;
+    e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
+    e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
+    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
+  }
+  return 0;
+}
+
+extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                                  float lambda_sparse, int64_t global_tokens, const svb_train_out* out) {
+  if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  SVB_TRY(check_params(x, p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SaePlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, true));
+  const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
+  const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
+  const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  SVB_TRY(run_prep(st, pl, p));
+  fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
+      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u);
+
+  // G1 encoder
+  EpiEnc::Params e1{};
+  e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
+  e1.hw = pl.hw; e1.words = pl.words;
+  SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
+  // G2 decoder
+  EpiDec::Params e2{};
+  e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
+  // channel statistics
+  if (pl.hw > 1) {
+    channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw);
+    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw);
+  } else {
+    channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T);
+    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T);
+    row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C);
+  }
+  SVB_LAUNCH_CHECK("channel_stats");
+  // G3 dE -> dPre'
+  EpiDPre::Params e3{};
+  e3.e = pl.E; e3.dpre = pl.DP; e3.colsum_partial = pl.colsum_part;
+  e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
+  e3.block_n = 256;
+  SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
+  // G4 / G5 weight gradients, split-K over tokens
+  const size_t FC = static_cast<size_t>(F) * C;
+  EpiStore::Params e4{pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  EpiStore::Params e5{pl.P_we, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
+
+  // gradient assembly
+  const float s = static_cast<float>(2.0 / (Tg * C));
+  float* flat = pl.flat;
+  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.tiles_m, F, 1.f, pl.stage, pl.csum));
+  sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd);
+  wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_we, pl.s_we, F, C, pl.csum, p->b_dec, s, flat + pl.o_gwe);
+  vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum, pl.Web, F, C, pl.vm);
+  bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd);
+  sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe);  // gb_enc = s * csum
+  // loss partial sums
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1);
+  stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+                                       pl.o_sums, pl.o_chansq, pl.o_max);
+  cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);
+  // activity
+  activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count);
+  activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
+                                                               out ? out->activity.n_active : nullptr, pl.nact_f);
+  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5);
+  SVB_LAUNCH_CHECK("grad assembly");
+  // decoder output handed back to the model (model_pipeline.py:425,432)
+  if (out && out->dec_out)
+    SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
+  h->gradbuf = flat;
+  h->sum_elems = static_cast<int64_t>(pl.sum_elems);
+  h->max_elems = static_cast<int64_t>(pl.max_elems);
+  return 0;
+}
+
+extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                                  const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                                  int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
+                                  const svb_train_out* out) {
+  if (!h || !adam || !opt) return fail(SVB_ERR_BAD_ARG, "null handle/adam/opt");
+  SVB_TRY(check_params(x, p));
+  for (int i = 0; i < 4; ++i)
+    if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);
+  if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SaePlan pl;
+  SVB_TRY(plan(h, pl, x, p->F, true));
+  if (pl.flat != h->gradbuf) return fail(SVB_ERR_BAD_ARG, "svb_sae_step_apply called without a matching svb_sae_step_grads");
+  const int C = pl.C, F = pl.F;
+  const size_t FC = static_cast<size_t>(F) * C;
+  float* flat = pl.flat;
+  const AdamCoef k = adam_coef(opt);
+  adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC, k, nullptr);
+  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_enc, flat + pl.o_gbe, adam->m[1], adam->v[1], F, k, nullptr);
+  if (opt->optimizer == SVB_CONSTRAINED_ADAM)
+    constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], C, F, k);
+  else
+    adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], FC, k, nullptr);
+  adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[3], adam->v[3], C, k, nullptr);
+  SVB_LAUNCH_CHECK("adam");
+  const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
+  const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
+  if (out && out->stats) {
+    stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
+                                             expansion_factor, out->stats);
+  }
+  if (out && (out->activity.dead || out->activity.freq || out->stats)) {
+    activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
+                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr);
+  }
+  SVB_LAUNCH_CHECK("finalize");
+  return 0;
+}
+
+extern "C" int svb_sae_train_step(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
+                                  const svb_adam_state* adam, const svb_opt_config* opt, float lambda_sparse,
+                                  int32_t expansion_factor, const svb_train_out* out) {
+  SVB_TRY(svb_sae_step_grads(h, stream, x, p, lambda_sparse, 0, out));
+  return svb_sae_step_apply(h, stream, x, p, adam, opt, lambda_sparse, expansion_factor, 0, 0, out);
+}
+
+extern "C" int svb_sae_grad_buffer(svb_handle* h, float** buf, int64_t* sum_elems, int64_t* max_elems) {
+  if (!h || !h->gradbuf) return fail(SVB_ERR_BAD_ARG, "no gradient buffer: call svb_*_step_grads first");
+  if (buf) *buf = h->gradbuf;
+  if (sum_elems) *sum_elems = h->sum_elems;
+  if (max_elems) *max_elems = h->max_elems;
+  return 0;
+}

@@ -1,0 +1,301 @@
+"""Thin functional layer over the C ABI: allocates outputs with torch, passes raw pointers, raises on error.
+These are what the reference-shaped modules in models/, losses/, utils.py, model_pipeline.py and compute_ie.py call.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise ValueError("parameters / optimizer state must be float32 CUDA tensors")
+    if not t.is_contiguous():
+        raise ValueError("parameters / optimizer state must be contiguous (they are updated in place)")
+    return t
+
+
+def _sae_params(w_enc, b_enc, w_dec, b_dec):
+    F, Cc = w_enc.shape
+    if tuple(w_dec.shape) != (Cc, F) or b_enc.numel() != F or b_dec.numel() != Cc:
+        raise ValueError("inconsistent SAE parameter shapes")
+    return L.SaeParams(L.ptr(_f32c(w_enc)), L.ptr(_f32c(b_enc)), L.ptr(_f32c(w_dec)), L.ptr(_f32c(b_dec)), F)
+
+
+def _gated_params(w_gate, b_gate, b_mag, r_mag, w_dec, b_dec):
+    F, Cc = w_gate.shape
+    if tuple(w_dec.shape) != (Cc, F):
+        raise ValueError("inconsistent Gated-SAE parameter shapes")
+    return L.GatedParams(L.ptr(_f32c(w_gate)), L.ptr(_f32c(b_gate)), L.ptr(_f32c(b_mag)), L.ptr(_f32c(r_mag)),
+                         L.ptr(_f32c(w_dec)), L.ptr(_f32c(b_dec)), F)
+
+
+def _adam_state(ms, vs):
+    st = L.AdamState()
+    for i, (m, v) in enumerate(zip(ms, vs)):
+        st.m[i] = _f32c(m).data_ptr()
+        st.v[i] = _f32c(v).data_ptr()
+    return st
+
+
+def _opt(optimizer, step, lr, betas, eps):
+    code = {"adam": L.SVB_ADAM, "constrained_adam": L.SVB_CONSTRAINED_ADAM}[optimizer]
+    return L.OptConfig(code, int(step), float(lr), float(betas[0]), float(betas[1]), float(eps))
+
+
+def _tokens(x):
+    return x.shape[0] * (x.shape[2] * x.shape[3] if x.dim() == 4 else 1)
+
+
+# --------------------------------------------------------------------------------------------------- forward
+def sae_forward(x, w_enc, b_enc, w_dec, b_dec, want_pre=True, want_dec=True, out_dtype=torch.float32):
+    """models/sae_mlp.py:42-53 -> (encoder_output [T,F], decoder_output [T,C], prerelu [T,F] | None), token-major."""
+    a, x = L.acts_of(x)
+    p = _sae_params(w_enc, b_enc, w_dec, b_dec)
+    T, F, Cc = _tokens(x), p.F, a.C
+    enc = torch.empty((T, F), device=x.device, dtype=out_dtype)
+    pre = torch.empty((T, F), device=x.device, dtype=torch.float32) if want_pre else None
+    dec = torch.empty((T, Cc), device=x.device, dtype=out_dtype) if want_dec else None
+    out = L.SaeForwardOut(L.ptr(enc), L.dtype_code(enc), L.ptr(pre), L.ptr(dec), L.dtype_code(dec) if want_dec else 0)
+    L.check(L.load().svb_sae_forward(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(out)),
+            "svb_sae_forward")
+    return enc, dec, pre
+
+
+def gated_forward(x, w_gate, b_gate, b_mag, r_mag, w_dec, b_dec, out_dtype=torch.float32):
+    """models/gated_sae.py:28-56 -> (encoder_output, decoder_output, relu_pi_gate, via_gate), token-major."""
+    a, x = L.acts_of(x)
+    p = _gated_params(w_gate, b_gate, b_mag, r_mag, w_dec, b_dec)
+    T, F, Cc = _tokens(x), p.F, a.C
+    enc = torch.empty((T, F), device=x.device, dtype=out_dtype)
+    rp = torch.empty((T, F), device=x.device, dtype=out_dtype)
+    dec = torch.empty((T, Cc), device=x.device, dtype=out_dtype)
+    via = torch.empty((T, Cc), device=x.device, dtype=out_dtype)
+    code = L.dtype_code(enc)
+    out = L.GatedForwardOut(L.ptr(enc), code, L.ptr(dec), code, L.ptr(rp), code, L.ptr(via), code)
+    L.check(L.load().svb_gated_forward(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(out)),
+            "svb_gated_forward")
+    return enc, dec, rp, via
+
+
+# --------------------------------------------------------------------------------------------------- train step
+class StepResult:
+    """Device-side results of one training step.  `stats` is a float32[16] CUDA tensor (see _lib.STAT); nothing
+    here synchronises with the host until the caller reads a value."""
+
+    def __init__(self, stats, dead, freq, n_active, dec):
+        self.stats, self.dead, self.freq, self.n_active, self.dec = stats, dead, freq, n_active, dec
+
+    def scalars(self):
+        s = self.stats.tolist()          # ONE device->host copy for all scalars
+        return {k: s[i] for k, i in L.STAT.items()}
+
+
+def _train_out(x, a, F, want_dec, dec_dtype):
+    dev = x.device
+    stats = torch.zeros(L.STATS_LEN, device=dev, dtype=torch.float32)
+    dead = torch.empty(F, device=dev, dtype=torch.uint8)
+    freq = torch.empty(F, device=dev, dtype=torch.float32)
+    n_active = torch.empty(a.n_images, device=dev, dtype=torch.int32)
+    dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype) if want_dec else None
+    out = L.TrainOut(L.ptr(dec), L.dtype_code(dec) if want_dec else 0, a.layout, L.ptr(stats),
+                     L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active)))
+    return out, StepResult(stats, dead, freq, n_active, dec)
+
+
+def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
+                   betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None):
+    """One pass of ModelPipeline.hook's train branch (model_pipeline.py:380-420) for SaeMLP, fully on device.
+    params = (encoder.weight, encoder.bias, decoder.weight, decoder.bias); updated in place with the Adam moments."""
+    a, x = L.acts_of(x)
+    p = _sae_params(*params)
+    out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
+    st = _adam_state(adam_m, adam_v)
+    opt = _opt(optimizer, step, lr, betas, eps)
+    L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
+                                        C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
+            "svb_sae_train_step")
+    return res
+
+
+def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
+                     betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None):
+    """Same for GatedSae; params = (W_gate, b_gate, b_mag, r_mag, decoder.weight, decoder.bias)."""
+    a, x = L.acts_of(x)
+    p = _gated_params(*params)
+    out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
+    st = _adam_state(adam_m, adam_v)
+    opt = _opt(optimizer, step, lr, betas, eps)
+    L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
+                                          C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
+            "svb_gated_train_step")
+    return res
+
+
+class SplitStep:
+    """The two halves of a data-parallel step: grads() -> (all-reduce the flat buffer) -> apply()."""
+
+    def __init__(self, kind, x, params, lam, want_dec=True, dec_dtype=None):
+        self.kind = kind
+        self.a, self.x = L.acts_of(x)
+        self.params = params
+        self.p = _sae_params(*params) if kind == "sae_mlp" else _gated_params(*params)
+        self.lam = float(lam)
+        self.out, self.res = _train_out(self.x, self.a, self.p.F, want_dec, dec_dtype)
+        self.lib = L.load()
+        self.h = L.handle(self.x.device)
+
+    def grads(self, global_tokens=0):
+        fn = self.lib.svb_sae_step_grads if self.kind == "sae_mlp" else self.lib.svb_gated_step_grads
+        L.check(fn(self.h, L.stream_ptr(), C.byref(self.a), C.byref(self.p), self.lam, int(global_tokens),
+                   C.byref(self.out)), "svb_*_step_grads")
+        buf, n_sum, n_max = L._vp(), C.c_int64(), C.c_int64()
+        L.check(self.lib.svb_sae_grad_buffer(self.h, C.byref(buf), C.byref(n_sum), C.byref(n_max)),
+                "svb_sae_grad_buffer")
+        return buf.value, n_sum.value, n_max.value
+
+    def apply(self, adam_m, adam_v, step, lr, expansion_factor, optimizer, betas, eps=1e-8, global_tokens=0,
+              global_images=0):
+        fn = self.lib.svb_sae_step_apply if self.kind == "sae_mlp" else self.lib.svb_gated_step_apply
+        st = _adam_state(adam_m, adam_v)
+        opt = _opt(optimizer, step, lr, betas, eps)
+        L.check(fn(self.h, L.stream_ptr(), C.byref(self.a), C.byref(self.p), C.byref(st), C.byref(opt), self.lam,
+                   int(expansion_factor), int(global_tokens), int(global_images), C.byref(self.out)),
+                "svb_*_step_apply")
+        return self.res
+
+
+def wrap_device_buffer(address, n_elems, device):
+    """A float32 torch view over library-owned device memory (the flat gradient buffer) for torch.distributed."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(n_elems),), "typestr": "<f4", "data": (int(address), False),
+                                  "version": 3}
+    return torch.as_tensor(h, device=device)
+
+
+# --------------------------------------------------------------------------------------------------- optimiser
+def adam_step(params, grads, ms, vs, step, lr, betas, eps=1e-8, optimizer="adam", decoder_index=-1):
+    """utils.py:50-97 on caller-provided gradients (None grads are skipped like torch.optim.Adam does)."""
+    n = len(params)
+    dev = params[0].device
+    arr = L._vp * n
+    rows = (C.c_int64 * n)(*[p.shape[0] if p.dim() == 2 else 1 for p in params])
+    cols = (C.c_int64 * n)(*[p.shape[1] if p.dim() == 2 else p.numel() for p in params])
+    gs = [None if g is None else g.contiguous() for g in grads]
+    L.check(L.load().svb_adam_step(
+        L.handle(dev), L.stream_ptr(), n, arr(*[_f32c(p).data_ptr() for p in params]),
+        arr(*[0 if g is None else _f32c(g).data_ptr() for g in gs]), arr(*[_f32c(m).data_ptr() for m in ms]),
+        arr(*[_f32c(v).data_ptr() for v in vs]), rows, cols, int(decoder_index),
+        C.byref(_opt(optimizer, step, lr, betas, eps))), "svb_adam_step")
+    return gs
+
+
+def reinit_dead(params, adam_m, adam_v, dead_mask_u8, new_w_enc, new_w_dec, new_b_enc):
+    """models/sae_mlp.py:133-176 scatter + column renorm + Adam-moment reset for the dead units."""
+    p = _sae_params(*params)
+    Cc = params[0].shape[1]
+    st = _adam_state(adam_m, adam_v) if adam_m is not None else None
+    L.check(L.load().svb_reinit_dead(L.handle(params[0].device), L.stream_ptr(), C.byref(p), Cc,
+                                     C.byref(st) if st is not None else None, L.ptr(dead_mask_u8.contiguous()),
+                                     L.ptr(_f32c(new_w_enc)), L.ptr(_f32c(new_w_dec)), float(new_b_enc)),
+            "svb_reinit_dead")
+
+
+# --------------------------------------------------------------------------------------------------- activity
+def measure_inactive(t):
+    """utils.py:2032-2069 on a [B,F,H,W] or [N,F] tensor -> (dead uint8 [F], freq [F], n_active int32 [rows])."""
+    if not t.is_cuda:
+        raise ValueError("CUDA tensor required")
+    t = t.contiguous()
+    if t.dim() == 4:
+        b, f, h, w = t.shape
+        layout, n_img, hw, rows = L.SVB_NCHW, b, h * w, b
+    elif t.dim() == 2:
+        n, f = t.shape
+        layout, n_img, hw, rows = L.SVB_TOKENS, n, 1, n
+    else:
+        raise ValueError(f"Output has unexpected shape {t.dim()}.")
+    dead = torch.empty(f, device=t.device, dtype=torch.uint8)
+    freq = torch.empty(f, device=t.device, dtype=torch.float32)
+    n_active = torch.empty(rows, device=t.device, dtype=torch.int32)
+    act = L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active))
+    L.check(L.load().svb_measure_inactive(L.handle(t.device), L.stream_ptr(), L.ptr(t), L.dtype_code(t), layout,
+                                          n_img, hw, f, C.byref(act)), "svb_measure_inactive")
+    return dead, freq, n_active
+
+
+# --------------------------------------------------------------------------------------------------- IE
+def ie_channelwise(a, avg, g, batch_size, scale=None):
+    """utils.py:2606-2637: a, g [B*H*W, F] (f32/bf16), avg [F,H,W] f32 -> [F]."""
+    F, H, W = avg.shape
+    if a.shape != g.shape or a.shape[0] != batch_size * H * W or a.shape[1] != F:
+        raise ValueError("compute_ie_channel_wise: inconsistent shapes")
+    a, g = a.contiguous(), g.contiguous()
+    if g.dtype != a.dtype:
+        g = g.to(a.dtype)
+    avg = avg.contiguous().float()
+    out = torch.empty(F, device=a.device, dtype=torch.float32)
+    sc = (1.0 / a.shape[0]) if scale is None else scale
+    L.check(L.load().svb_ie_channelwise(L.handle(a.device), L.stream_ptr(), L.ptr(a), L.ptr(g), L.dtype_code(a),
+                                        L.ptr(avg), batch_size, H * W, F, float(sc), L.ptr(out)),
+            "svb_ie_channelwise")
+    return out
+
+
+def ie_allchannels(err, avg, g, batch_size, scale=None):
+    """utils.py:2574-2602: err, g [B,C,H,W], avg [C,H,W] -> scalar tensor."""
+    B, Cc, H, W = err.shape
+    if B != batch_size or tuple(avg.shape) != (Cc, H, W) or g.shape != err.shape:
+        raise ValueError("compute_ie_all_channels: inconsistent shapes")
+    err, g = err.contiguous(), g.contiguous()
+    if g.dtype != err.dtype:
+        g = g.to(err.dtype)
+    avg = avg.contiguous().float()
+    out = torch.empty(1, device=err.device, dtype=torch.float32)
+    sc = (1.0 / (B * H * W)) if scale is None else scale
+    L.check(L.load().svb_ie_allchannels(L.handle(err.device), L.stream_ptr(), L.ptr(err), L.ptr(g),
+                                        L.dtype_code(err), L.ptr(avg), B, Cc, H * W, float(sc), L.ptr(out)),
+            "svb_ie_allchannels")
+    return out[0]
+
+
+def node_ie_layer(x, grad, params, enc_avg, err_avg, x_avg, scale=None):
+    """compute_ie.py:242-267,442-453 for one layer / one batch -> (ie_sae_features [F], ie_sae_error, ie_neurons [C])."""
+    a, x = L.acts_of(x)
+    grad = grad.contiguous()
+    if grad.dtype != x.dtype or grad.shape != x.shape:
+        raise ValueError("grad must match x in dtype and shape")
+    p = _sae_params(*params)
+    dev = x.device
+    feat = torch.empty(p.F, device=dev, dtype=torch.float32)
+    err = torch.empty(1, device=dev, dtype=torch.float32)
+    neur = torch.empty(a.C, device=dev, dtype=torch.float32)
+    sc = (1.0 / _tokens(x)) if scale is None else scale
+    L.check(L.load().svb_node_ie_layer(L.handle(dev), L.stream_ptr(), C.byref(a), L.ptr(grad), C.byref(p),
+                                       L.ptr(enc_avg.contiguous().float()), L.ptr(err_avg.contiguous().float()),
+                                       L.ptr(x_avg.contiguous().float()), float(sc), L.ptr(feat), L.ptr(err),
+                                       L.ptr(neur)), "svb_node_ie_layer")
+    return feat, err[0], neur
+
+
+# --------------------------------------------------------------------------------------------------- generic GEMM
+def gemm_bf16(A, B, a_mn=False, b_mn=False, out_dtype=torch.float32, alpha=1.0, bias=None, relu=False):
+    """D[M,N] = alpha * A[M,K] @ B[N,K]^T on the tcgen05 kernel.  With a_mn / b_mn the operand is given as its
+    transpose ([K,M] / [K,N] row-major), which is how the backward GEMMs read token-major tensors without a copy."""
+    A = A.contiguous() if A.dtype == torch.bfloat16 else A.to(torch.bfloat16).contiguous()
+    B = B.contiguous() if B.dtype == torch.bfloat16 else B.to(torch.bfloat16).contiguous()
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
+    if K != Kb:
+        raise ValueError(f"gemm_bf16: inner dimensions differ ({K} vs {Kb})")
+    out = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    L.check(L.load().svb_gemm_bf16(L.handle(A.device), L.stream_ptr(), L.ptr(A), int(a_mn), A.shape[1], L.ptr(B),
+                                   int(b_mn), B.shape[1], M, N, K, L.ptr(out), L.dtype_code(out), N, float(alpha),
+                                   L.ptr(bias.contiguous().float()) if bias is not None else None, int(relu)),
+            "svb_gemm_bf16")
+    return out
