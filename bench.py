@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — SAE train activation-vectors/sec (BASELINE.json metric) on configs[1]:
+SaeMLP (the reference's pixels-as-tokens "Conv-SAE") on GoogLeNet inception3a-shaped activations, C=256, 28x28,
+expansion 8 (F=2048), constrained_adam, lambda=5, batch 256 images = 200,704 tokens per GPU, bf16 compute.
+
+    python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference ...                      the reference algorithm's CPU path (oracle port)
+
+A step = one pass of ModelPipeline.hook's train branch (model_pipeline.py:380-420): forward, loss, backward,
+optimizer step, activity metrics, decoder output handed back.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C_ACT, HW_SIDE, EXPANSION, LAMBDA, LR = 256, 28, 8, 5.0, 1e-3
+METRIC = "sae_train_activation_vectors_per_sec"
+UNIT = "act-vec/s"
+
+
+def _env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def _make_params(seed=0, dead_frac=0.05):
+    """Reference constructor draws under torch.manual_seed(0) + a planted 5 % dead subset."""
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    torch.manual_seed(seed)
+    m = SaeMLP(C_ACT, EXPANSION)
+    F = m.hidden_size
+    idx = torch.randperm(F, generator=torch.Generator().manual_seed(1))[: int(F * dead_frac)]
+    with torch.no_grad():
+        m.encoder.bias[idx] = -50.0
+    return m
+
+
+def _synthetic_acts(n_images, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.relu(torch.randn(n_images, C_ACT, HW_SIDE, HW_SIDE, generator=g))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_sustained": p.get("bf16_tflops_sustained"), "bf16_burst": p.get("bf16_tflops"),
+                "hbm": p.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def _traffic():
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+def cpu_reference_throughput(n_images, steps, warmup, threads=None):
+    """The reference algorithm on the host cores: oracle/sae_oracle.py (a restatement pinned to the real reference by
+    tests/golden) running the same step on a bounded sample of the same workload (same C, F, HW, optimizer)."""
+    from oracle import sae_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    p = O.init_sae_mlp(C_ACT, EXPANSION)
+    st = O.new_adam_state(p, O.SAE_MLP_KEYS)
+    x = _synthetic_acts(n_images, 1234)
+    tokens = n_images * HW_SIDE * HW_SIDE
+    for _ in range(warmup):
+        O.train_step("sae_mlp", p, st, x, LAMBDA, "constrained_adam", LR, EXPANSION)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step("sae_mlp", p, st, x, LAMBDA, "constrained_adam", LR, EXPANSION)
+    dt = (time.perf_counter() - t0) / steps
+    return tokens / dt, dt * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    n_img = args.cpu_images
+    value, ms, cores = cpu_reference_throughput(n_img, args.steps, max(args.warmup, 1), os.cpu_count())
+    sample = f"{n_img} images = {n_img * HW_SIDE * HW_SIDE} tokens per step of the same workload (fp32, torch CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: SaeMLP C=256 28x28 k=8 constrained_adam lambda=5 (CPU sample)",
+                   "images_per_step": n_img, "tokens_per_step": n_img * HW_SIDE * HW_SIDE},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_svb(args):
+    import torch.distributed as dist
+    from sparse_vision_b200 import _lib as L, ops
+    from sparse_vision_b200.parallel import DataParallelStep
+    import ctypes as C
+
+    world, rank, local = _env_int("WORLD_SIZE", 1), _env_int("RANK", 0), _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.images
+    T = B * HW_SIDE * HW_SIDE
+    F = C_ACT * EXPANSION
+    model = _make_params()
+    params = [p.detach().clone().to(dev) for p in model.param_list()]
+    ms_ = [torch.zeros_like(p) for p in params]
+    vs_ = [torch.zeros_like(p) for p in params]
+    # two distinct resident batches (2 x 103 MB > 126 MB L2), bf16 NCHW as the base model would emit them
+    host = [_synthetic_acts(B, 1234 + 17 * rank + i).to(torch.bfloat16).pin_memory() for i in range(2)]
+    xdev = [h.to(dev) for h in host]
+    lib, h = L.load(), L.handle(dev)
+    dp = DataParallelStep("sae_mlp") if world > 1 else None
+    g_images, g_tokens = B * world, T * world
+    step_no = [0]
+
+    def one_step(x):
+        step_no[0] += 1
+        if dp is None:
+            return ops.sae_train_step(x, params, ms_, vs_, step_no[0], LR, LAMBDA, EXPANSION,
+                                      optimizer="constrained_adam", betas=(0.9, 0.999), want_dec=True)
+        return dp.step(x, params, ms_, vs_, step_no[0], LR, LAMBDA, EXPANSION, "constrained_adam", (0.9, 0.999),
+                       g_images, g_tokens, want_dec=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        res = one_step(xdev[i % 2])
+    barrier()
+
+    # ---------------------------------------------------------------- timed region: inputs resident in HBM
+    L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.svb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        res = one_step(xdev[i % 2])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.svb_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    phase_ms = (C.c_float * 16)()
+    n_ph, n_st = C.c_int32(), C.c_int32()
+    L.check(lib.svb_profile_read(h, 16, phase_ms, C.byref(n_ph), C.byref(n_st)), "svb_profile_read")
+    L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
+    phases = {lib.svb_profile_phase_name(i).decode(): float(phase_ms[i]) for i in range(n_ph.value)}
+    last_stats = res.scalars()
+
+    # ---------------------------------------------------------------- e2e: host buffers in, result scalars out
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(xdev[0]) for _ in range(2)]
+    stats_host = torch.empty(L.STATS_LEN, dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    copy_stream.wait_event(e0)
+    n_e2e = args.steps
+    with torch.cuda.stream(copy_stream):
+        stage[0].copy_(host[0], non_blocking=True)
+        ready[0].record(copy_stream)
+    for i in range(n_e2e):
+        cur, nxt = i % 2, (i + 1) % 2
+        if i + 1 < n_e2e:
+            with torch.cuda.stream(copy_stream):
+                if i >= 1:
+                    copy_stream.wait_event(freed[nxt])
+                stage[nxt].copy_(host[nxt], non_blocking=True)     # H2D of step i+1 overlaps the compute of step i
+                ready[nxt].record(copy_stream)
+        main.wait_event(ready[cur])
+        r = one_step(stage[cur])
+        freed[cur].record(main)
+        stats_host.copy_(r.stats, non_blocking=True)               # D2H of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = g_tokens / (ms_step * 1e-3)
+    e2e_value = g_tokens / (ms_e2e / n_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = _peaks()
+        gemm_phases = {k: v for k, v in phases.items() if k.endswith("_gemm")}
+        dom = max(gemm_phases, key=gemm_phases.get) if gemm_phases else None
+        flops_per_gemm = 2.0 * T * C_ACT * F
+        achieved = flops_per_gemm / (gemm_phases[dom] * 1e-3) / 1e12 if dom else None
+        peak = peaks["bf16_sustained"]
+        traffic = _traffic()
+        roofline = {
+            "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved and peak else None,
+            "traffic": traffic.get(dom), "peak_source": peaks["source"] + ", sustained bf16",
+            "algorithmic_flops_per_launch": flops_per_gemm,
+            "step_tflops": 10.0 * C_ACT * F * T / (ms_step * 1e-3) / 1e12,
+            "step_frac_of_peak": 10.0 * C_ACT * F * T / (ms_step * 1e-3) / 1e12 / peak if peak else None,
+            "phases_ms": phases,
+        }
+        cpu_v, cpu_ms, cores = cpu_reference_throughput(args.cpu_images, 2, 1, os.cpu_count()) if world == 1 else (None, None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: SaeMLP (pixels-as-tokens) C=256 28x28 k=8 F=2048 constrained_adam "
+                                   "lambda=5, 256 images = 200704 tokens per GPU, bf16 NCHW activations",
+                       "images_per_gpu": B, "tokens_per_gpu": T, "parallelism": f"dp{world}",
+                       "l2": "two rotating 103 MB input batches + ~2.2 GB per-step working set, both > 126 MB L2"},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host[0].numel() * 2 * world,
+                    "d2h_bytes_per_step": L.STATS_LEN * 4 * world, "ms_per_step": ms_e2e / n_e2e,
+                    "note": "pinned host activations -> svb_sae_train_step -> stats block to host, H2D of step i+1 "
+                            "overlapped with step i on a copy stream"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "final_step_stats": {k: last_stats[k] for k in ("loss", "rec", "l1", "n_dead")},
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {
+                "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_images} images = {args.cpu_images * HW_SIDE * HW_SIDE} tokens per step, "
+                          f"1 warm-up + 2 timed steps of oracle/sae_oracle.py (fp32 torch CPU)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="svb", choices=["svb", "reference"])
+    ap.add_argument("--images", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--cpu-images", type=int, default=8, help="images per step of the CPU reference sample")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "svb":
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_svb(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -51,6 +51,17 @@ int svb_destroy(svb_handle* h);
 /* bytes of device workspace currently held by the handle */
 int64_t svb_workspace_bytes(const svb_handle* h);
 
+/* Number of kernels the library has launched in this process (bench.py reports the per-step delta). */
+int64_t svb_launch_count(void);
+
+/* Per-phase timing of the SaeMLP training step with CUDA events recorded on the caller's stream between the phases
+ * (pack+prep, enc GEMM, dec GEMM, channel stats, dE GEMM, dW_dec GEMM, dW_enc GEMM, gradient assembly, Adam).
+ * svb_profile_read synchronises the device and returns the mean milliseconds per phase over the recorded steps
+ * (a ring of the last 128).  ms_avg_host is a HOST array. */
+int svb_profile_enable(svb_handle* h, int32_t enable);
+int svb_profile_read(svb_handle* h, int32_t max_phases, float* ms_avg_host, int32_t* n_phases, int32_t* n_steps);
+const char* svb_profile_phase_name(int32_t i);
+
 /* A batch of SAE inputs: the hooked layer's output (model_pipeline.py:368). */
 typedef struct svb_acts {
   const void* x;    /* activations */

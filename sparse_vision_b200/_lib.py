@@ -75,6 +75,10 @@ SYMBOLS = {
     "svb_create": (C.c_int, [_P(_vp)]),
     "svb_destroy": (C.c_int, [_vp]),
     "svb_workspace_bytes": (C.c_int64, [_vp]),
+    "svb_launch_count": (C.c_int64, []),
+    "svb_profile_enable": (C.c_int, [_vp, C.c_int32]),
+    "svb_profile_read": (C.c_int, [_vp, C.c_int32, _P(C.c_float), _P(C.c_int32), _P(C.c_int32)]),
+    "svb_profile_phase_name": (C.c_char_p, [C.c_int32]),
     "svb_sae_forward": (C.c_int, [_vp, _vp, _P(Acts), _P(SaeParams), _P(SaeForwardOut)]),
     "svb_sae_train_step": (C.c_int, [_vp, _vp, _P(Acts), _P(SaeParams), _P(AdamState), _P(OptConfig), C.c_float,
                                      C.c_int32, _P(TrainOut)]),

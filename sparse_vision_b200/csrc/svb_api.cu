@@ -31,6 +31,57 @@ extern "C" int svb_destroy(svb_handle* h) {
   return 0;
 }
 
+extern "C" int64_t svb_launch_count(void) { return static_cast<int64_t>(launch_counter()); }
+
+// ---------------------------------------------------------------------------------------------------- profiling
+static const char* kPhaseNames[] = {"pack+prep", "enc_gemm", "dec_gemm", "channel_stats", "dE_gemm",
+                                    "dWdec_gemm", "dWenc_gemm", "grad_assembly", "adam+finalize"};
+
+extern "C" int svb_profile_enable(svb_handle* h, int32_t enable) {
+  if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  Profiler& p = h->prof;
+  if (enable && !p.created) {
+    for (int s = 0; s < kProfMaxSteps; ++s)
+      for (int m = 0; m < kProfMaxMarks; ++m) SVB_CUDA(cudaEventCreate(&p.ev[s][m]));
+    p.created = true;
+  }
+  p.on = enable != 0;
+  p.step = -1;
+  p.steps_recorded = 0;
+  return 0;
+}
+
+extern "C" int svb_profile_read(svb_handle* h, int32_t max_phases, float* ms_avg_host, int32_t* n_phases,
+                                int32_t* n_steps) {
+  if (!h || !ms_avg_host || !n_phases || !n_steps) return fail(SVB_ERR_BAD_ARG, "null argument");
+  Profiler& p = h->prof;
+  if (!p.created) return fail(SVB_ERR_BAD_ARG, "profiling was never enabled");
+  SVB_CUDA(cudaDeviceSynchronize());
+  const int ns = static_cast<int>(p.steps_recorded < kProfMaxSteps ? p.steps_recorded : kProfMaxSteps);
+  int phases = 0;
+  double acc[kProfMaxMarks] = {0};
+  int used = 0;
+  for (int s = 0; s < ns; ++s) {
+    const int marks = p.marks[s];
+    if (marks < 2) continue;
+    if (marks - 1 > phases) phases = marks - 1;
+    for (int m = 0; m + 1 < marks; ++m) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.ev[s][m], p.ev[s][m + 1]) == cudaSuccess) acc[m] += ms;
+    }
+    ++used;
+  }
+  if (phases > max_phases) phases = max_phases;
+  for (int m = 0; m < phases; ++m) ms_avg_host[m] = used ? static_cast<float>(acc[m] / used) : 0.f;
+  *n_phases = phases;
+  *n_steps = used;
+  return 0;
+}
+
+extern "C" const char* svb_profile_phase_name(int32_t i) {
+  return (i >= 0 && i < static_cast<int>(sizeof(kPhaseNames) / sizeof(kPhaseNames[0]))) ? kPhaseNames[i] : "";
+}
+
 extern "C" int64_t svb_workspace_bytes(const svb_handle* h) { return h ? static_cast<int64_t>(h->arena.cap) : 0; }
 
 // ---------------------------------------------------------------------------------------------------- optimiser
@@ -46,18 +97,18 @@ extern "C" int svb_adam_step(svb_handle* h, void* stream, int32_t n_tensors, flo
     if (!grads[i]) continue;  // parameter without gradient: torch.optim.Adam skips it
     const size_t n = static_cast<size_t>(rows[i]) * cols[i];
     if (i == decoder_index && opt->optimizer == SVB_CONSTRAINED_ADAM) {
-      constrained_adam_decoder_kernel<<<cdiv(cols[i], 32), 256, 0, st>>>(params[i], const_cast<float*>(grads[i]), m[i],
+      (constrained_adam_decoder_kernel<<<cdiv(cols[i], 32), 256, 0, st>>>(params[i], const_cast<float*>(grads[i]), m[i],
                                                                         v[i], static_cast<int>(rows[i]),
-                                                                        static_cast<int>(cols[i]), k);
+                                                                        static_cast<int>(cols[i]), k), svb::count_launch());
     } else {
-      adam_kernel<<<grid_for(n), 256, 0, st>>>(params[i], grads[i], m[i], v[i], n, k, nullptr);
+      (adam_kernel<<<grid_for(n), 256, 0, st>>>(params[i], grads[i], m[i], v[i], n, k, nullptr), svb::count_launch());
     }
   }
   // ConstrainedAdam renormalises the decoder columns even when it had no gradient (utils.py:76-79)
   if (decoder_index >= 0 && decoder_index < n_tensors && opt->optimizer == SVB_CONSTRAINED_ADAM &&
       !grads[decoder_index])
-    renorm_columns_kernel<<<cdiv(cols[decoder_index], 32), 256, 0, st>>>(
-        params[decoder_index], static_cast<int>(rows[decoder_index]), static_cast<int>(cols[decoder_index]));
+    (renorm_columns_kernel<<<cdiv(cols[decoder_index], 32), 256, 0, st>>>(
+        params[decoder_index], static_cast<int>(rows[decoder_index]), static_cast<int>(cols[decoder_index])), svb::count_launch());
   SVB_LAUNCH_CHECK("adam_step");
   return 0;
 }
@@ -68,11 +119,11 @@ extern "C" int svb_reinit_dead(svb_handle* h, void* stream, const svb_sae_params
   if (!h || !p || !dead || !new_w_enc || !new_w_dec) return fail(SVB_ERR_BAD_ARG, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(p->F) * C;
-  reinit_scatter_kernel<<<grid_for(n), 256, 0, st>>>(dead, p->F, C, p->w_enc, p->b_enc, p->w_dec, new_w_enc, new_w_dec,
+  (reinit_scatter_kernel<<<grid_for(n), 256, 0, st>>>(dead, p->F, C, p->w_enc, p->b_enc, p->w_dec, new_w_enc, new_w_dec,
                                                      new_b_enc, adam ? adam->m[0] : nullptr, adam ? adam->v[0] : nullptr,
                                                      adam ? adam->m[1] : nullptr, adam ? adam->v[1] : nullptr,
-                                                     adam ? adam->m[2] : nullptr, adam ? adam->v[2] : nullptr);
-  renorm_columns_kernel<<<cdiv(p->F, 32), 256, 0, st>>>(p->w_dec, C, p->F);
+                                                     adam ? adam->m[2] : nullptr, adam ? adam->v[2] : nullptr), svb::count_launch());
+  (renorm_columns_kernel<<<cdiv(p->F, 32), 256, 0, st>>>(p->w_dec, C, p->F), svb::count_launch());
   SVB_LAUNCH_CHECK("reinit_dead");
   return 0;
 }
@@ -96,22 +147,22 @@ extern "C" int svb_measure_inactive(svb_handle* h, void* stream, const void* t, 
   h->gradbuf = nullptr;
   if (n_rows >= (1LL << 31)) return fail(SVB_ERR_UNSUPPORTED, "too many rows");
   if (layout == SVB_NCHW && hw > 1) {
-    fill_u32_kernel<<<grid_for(static_cast<size_t>(n_rows) * words), 256, 0, st>>>(bits, static_cast<size_t>(n_rows) * words, 0u);
+    (fill_u32_kernel<<<grid_for(static_cast<size_t>(n_rows) * words), 256, 0, st>>>(bits, static_cast<size_t>(n_rows) * words, 0u), svb::count_launch());
     const long long warps = n_images * F;
     if (dtype == SVB_F32)
-      activity_bits_nchw_kernel<float><<<cdiv(warps, 8), 256, 0, st>>>(static_cast<const float*>(t), bits, static_cast<int>(n_images), F, hw, words);
+      (activity_bits_nchw_kernel<float><<<cdiv(warps, 8), 256, 0, st>>>(static_cast<const float*>(t), bits, static_cast<int>(n_images), F, hw, words), svb::count_launch());
     else
-      activity_bits_nchw_kernel<bf16><<<cdiv(warps, 8), 256, 0, st>>>(static_cast<const bf16*>(t), bits, static_cast<int>(n_images), F, hw, words);
+      (activity_bits_nchw_kernel<bf16><<<cdiv(warps, 8), 256, 0, st>>>(static_cast<const bf16*>(t), bits, static_cast<int>(n_images), F, hw, words), svb::count_launch());
   } else {
     const long long n = n_rows * words;
     if (dtype == SVB_F32)
-      activity_bits_rows_kernel<float><<<cdiv(n, 256), 256, 0, st>>>(static_cast<const float*>(t), bits, n_rows, F, words);
+      (activity_bits_rows_kernel<float><<<cdiv(n, 256), 256, 0, st>>>(static_cast<const float*>(t), bits, n_rows, F, words), svb::count_launch());
     else
-      activity_bits_rows_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>(static_cast<const bf16*>(t), bits, n_rows, F, words);
+      (activity_bits_rows_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>(static_cast<const bf16*>(t), bits, n_rows, F, words), svb::count_launch());
   }
-  activity_count_kernel<<<words, 256, 0, st>>>(bits, static_cast<int>(n_rows), words, F, count);
-  activity_per_image_kernel<<<cdiv(n_rows, 8), 256, 0, st>>>(bits, static_cast<int>(n_rows), words, act->n_active, nact);
-  activity_finalize_kernel<<<1, 1024, 0, st>>>(count, F, static_cast<float>(n_rows), act->dead, act->freq, nullptr);
+  (activity_count_kernel<<<words, 256, 0, st>>>(bits, static_cast<int>(n_rows), words, F, count), svb::count_launch());
+  (activity_per_image_kernel<<<cdiv(n_rows, 8), 256, 0, st>>>(bits, static_cast<int>(n_rows), words, act->n_active, nact), svb::count_launch());
+  (activity_finalize_kernel<<<1, 1024, 0, st>>>(count, F, static_cast<float>(n_rows), act->dead, act->freq, nullptr), svb::count_launch());
   SVB_LAUNCH_CHECK("measure_inactive");
   return 0;
 }
@@ -149,7 +200,7 @@ int launch_ie_channelwise(cudaStream_t st, int sms, const T* a, const T* g, cons
                           int F, float scale, float* partial, int chunks, float* stage, float* out) {
   constexpr int V = Vec16<T>::kN;
   dim3 grid(cdiv(F, 32 * V), chunks);
-  ie_channelwise_kernel<T, 4><<<grid, 256, 0, st>>>(a, g, avgT, Tn, HW, F, partial);
+  (ie_channelwise_kernel<T, 4><<<grid, 256, 0, st>>>(a, g, avgT, Tn, HW, F, partial), svb::count_launch());
   SVB_LAUNCH_CHECK("ie_channelwise");
   return reduce_rows(st, partial, chunks, F, scale, stage, out);
 }
@@ -174,7 +225,7 @@ extern "C" int svb_ie_channelwise(svb_handle* h, void* stream, const void* a, co
   float* avgT = h->arena.take<float>(static_cast<size_t>(hw) * F);
   float* partial = h->arena.take<float>(static_cast<size_t>(chunks) * F);
   float* stage = h->arena.take<float>(32 * static_cast<size_t>(F));
-  transpose_f32_kernel<<<dim3(cdiv(hw, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(avg, avgT, F, hw);
+  (transpose_f32_kernel<<<dim3(cdiv(hw, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(avg, avgT, F, hw), svb::count_launch());
   SVB_LAUNCH_CHECK("transpose avg");
   if (dtype == SVB_F32)
     return launch_ie_channelwise<float>(st, h->sms, static_cast<const float*>(a), static_cast<const float*>(g), avgT, T,
@@ -198,12 +249,12 @@ extern "C" int svb_ie_allchannels(svb_handle* h, void* stream, const void* err, 
   h->arena.off = 0; h->arena.dry = false; h->gradbuf = nullptr;
   float* partial = h->arena.take<float>(blocks);
   if (dtype == SVB_F32)
-    ie_allchannels_nchw_kernel<float><<<blocks, dim3(32, 8), 0, st>>>(static_cast<const float*>(err), static_cast<const float*>(g), avg, n_pix, C, hw, partial);
+    (ie_allchannels_nchw_kernel<float><<<blocks, dim3(32, 8), 0, st>>>(static_cast<const float*>(err), static_cast<const float*>(g), avg, n_pix, C, hw, partial), svb::count_launch());
   else if (dtype == SVB_BF16)
-    ie_allchannels_nchw_kernel<bf16><<<blocks, dim3(32, 8), 0, st>>>(static_cast<const bf16*>(err), static_cast<const bf16*>(g), avg, n_pix, C, hw, partial);
+    (ie_allchannels_nchw_kernel<bf16><<<blocks, dim3(32, 8), 0, st>>>(static_cast<const bf16*>(err), static_cast<const bf16*>(g), avg, n_pix, C, hw, partial), svb::count_launch());
   else
     return fail(SVB_ERR_BAD_ARG, "bad dtype %d", dtype);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(partial, static_cast<size_t>(blocks), scale, out);
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(partial, static_cast<size_t>(blocks), scale, out), svb::count_launch());
   SVB_LAUNCH_CHECK("ie_allchannels");
   return 0;
 }
@@ -250,11 +301,11 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   const bf16* Gp = zg ? static_cast<const bf16*>(grad) : G;
   if (!zx) SVB_TRY(pack_acts(st, x, X));
   if (!zg) SVB_TRY(pack_acts(st, &gx, G));
-  prep_encoder_kernel<<<cdiv(F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, Web, fold, nullptr, F, C);
-  convert_kernel<float, bf16><<<grid_for(FC), 256, 0, st>>>(p->w_dec, Wdb, FC);
-  transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(enc_avg, avgT_f, F, HW);
-  transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(x_avg, avgT_c, C, HW);
-  transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(err_avg, avgT_e, C, HW);
+  (prep_encoder_kernel<<<cdiv(F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, Web, fold, nullptr, F, C), svb::count_launch());
+  (convert_kernel<float, bf16><<<grid_for(FC), 256, 0, st>>>(p->w_dec, Wdb, FC), svb::count_launch());
+  (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(enc_avg, avgT_f, F, HW), svb::count_launch());
+  (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(x_avg, avgT_c, C, HW), svb::count_launch());
+  (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(err_avg, avgT_e, C, HW), svb::count_launch());
   SVB_LAUNCH_CHECK("node_ie prep");
   // a = SAE_enc(x)
   EpiEnc::Params e1{};
@@ -272,8 +323,8 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   if (ie_neurons)
     SVB_TRY(launch_ie_channelwise<bf16>(st, h->sms, Xp, Gp, avgT_c, T, HW, C, scale, partial, chunks_c, stage, ie_neurons));
   if (ie_error) {
-    ie_allchannels_tokens_kernel<<<tok_blocks, 256, 0, st>>>(DIFF, Gp, avgT_e, T, C, HW, -1.f, tokpart);
-    reduce_flat_kernel<<<1, 1024, 0, st>>>(tokpart, static_cast<size_t>(tok_blocks), scale, ie_error);
+    (ie_allchannels_tokens_kernel<<<tok_blocks, 256, 0, st>>>(DIFF, Gp, avgT_e, T, C, HW, -1.f, tokpart), svb::count_launch());
+    (reduce_flat_kernel<<<1, 1024, 0, st>>>(tokpart, static_cast<size_t>(tok_blocks), scale, ie_error), svb::count_launch());
     SVB_LAUNCH_CHECK("ie_error");
   }
   return 0;
@@ -300,7 +351,7 @@ int gemm_dispatch(svb_handle* h, cudaStream_t st, const void* A, int64_t lda, co
   EpiStore::Params ep{part, N, static_cast<long long>(MN), nullptr, 1.f, 0, 0};
   int used = 0;
   SVB_GEMM((launch_gemm<256, AMN, BMN, EpiStore>(st, A, lda, B, ldb, M, N, K, splits, ep, &used)), "svb_gemm_bf16");
-  sum_splits_kernel<<<grid_for(MN), 256, 0, st>>>(part, used, MN, alpha, static_cast<float*>(out));
+  (sum_splits_kernel<<<grid_for(MN), 256, 0, st>>>(part, used, MN, alpha, static_cast<float*>(out)), svb::count_launch());
   SVB_LAUNCH_CHECK("sum_splits");
   return 0;
 }

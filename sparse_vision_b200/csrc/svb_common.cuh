@@ -71,16 +71,44 @@ struct Arena {
 
 }  // namespace svb
 
+namespace svb {
+// Optional per-phase timing of the training step with CUDA events on the caller's stream (bench.py's roofline).
+constexpr int kProfMaxSteps = 128, kProfMaxMarks = 12;
+struct Profiler {
+  bool on = false;
+  int step = -1;                       // ring slot of the step being recorded
+  long long steps_recorded = 0;
+  cudaEvent_t ev[kProfMaxSteps][kProfMaxMarks];
+  int marks[kProfMaxSteps];
+  bool created = false;
+};
+}  // namespace svb
+
 struct svb_handle {
   int device = 0;
   int sms = 0;
   svb::Arena arena;
+  svb::Profiler prof;
   // description of the flat reduction buffer of the last *_step_grads call
   float* gradbuf = nullptr;
   int64_t sum_elems = 0, max_elems = 0;
 };
 
 namespace svb {
+
+inline void prof_begin_step(svb_handle* h) {
+  Profiler& p = h->prof;
+  if (!p.on) return;
+  p.step = static_cast<int>(p.steps_recorded % kProfMaxSteps);
+  p.marks[p.step] = 0;
+  ++p.steps_recorded;
+}
+inline void prof_mark(svb_handle* h, cudaStream_t st, int idx) {
+  Profiler& p = h->prof;
+  if (!p.on || p.step < 0 || idx >= kProfMaxMarks) return;
+  cudaEventRecord(p.ev[p.step][idx], st);
+  if (idx + 1 > p.marks[p.step]) p.marks[p.step] = idx + 1;
+}
 
 inline int ensure_arena(svb_handle* h, size_t need) {
   if (need <= h->arena.cap) return 0;
@@ -122,17 +150,17 @@ inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
   if (x->layout == SVB_TOKENS || x->hw == 1) {
     const size_t n = static_cast<size_t>(T) * x->C;
     if (x->dtype == SVB_F32)
-      convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const float*>(x->x), buf, n);
+      (convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const float*>(x->x), buf, n), svb::count_launch());
     else
-      convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, n);
+      (convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, n), svb::count_launch());
   } else {
     dim3 grid(cdiv(x->hw, 32), cdiv(x->C, 32), static_cast<unsigned>(x->n_images));
     dim3 block(32, 8);
     if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
     if (x->dtype == SVB_F32)
-      pack_nchw_to_tokens_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x->x), buf, x->C, x->hw);
+      (pack_nchw_to_tokens_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x->x), buf, x->C, x->hw), svb::count_launch());
     else
-      pack_nchw_to_tokens_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw);
+      (pack_nchw_to_tokens_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("pack_acts");
   return 0;
@@ -141,16 +169,16 @@ inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int h
                      int out_layout) {
   const size_t n = static_cast<size_t>(n_images) * hw * C;
   if (out_layout == SVB_TOKENS || hw == 1) {
-    if (out_dtype == SVB_F32) convert_kernel<bf16, float><<<grid_for(n), 256, 0, st>>>(tok, static_cast<float*>(out), n);
-    else convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(tok, static_cast<bf16*>(out), n);
+    if (out_dtype == SVB_F32) (convert_kernel<bf16, float><<<grid_for(n), 256, 0, st>>>(tok, static_cast<float*>(out), n), svb::count_launch());
+    else (convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(tok, static_cast<bf16*>(out), n), svb::count_launch());
   } else {
     if (n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
     dim3 grid(cdiv(hw, 32), cdiv(C, 32), static_cast<unsigned>(n_images));
     dim3 block(32, 8);
     if (out_dtype == SVB_F32)
-      unpack_tokens_to_nchw_kernel<bf16, float><<<grid, block, 0, st>>>(tok, static_cast<float*>(out), C, hw);
+      (unpack_tokens_to_nchw_kernel<bf16, float><<<grid, block, 0, st>>>(tok, static_cast<float*>(out), C, hw), svb::count_launch());
     else
-      unpack_tokens_to_nchw_kernel<bf16, bf16><<<grid, block, 0, st>>>(tok, static_cast<bf16*>(out), C, hw);
+      (unpack_tokens_to_nchw_kernel<bf16, bf16><<<grid, block, 0, st>>>(tok, static_cast<bf16*>(out), C, hw), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("unpack");
   return 0;
@@ -160,10 +188,10 @@ inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int h
 inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float scale, float* stage, float* out) {
   int chunks = R >= 256 ? 32 : 1;
   if (chunks > 1) {
-    reduce_rows_kernel<<<dim3(cdiv(N, 32), chunks), 256, 0, st>>>(in, stage, R, N, static_cast<size_t>(N), 1.f);
-    reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(stage, out, chunks, N, static_cast<size_t>(N), scale);
+    (reduce_rows_kernel<<<dim3(cdiv(N, 32), chunks), 256, 0, st>>>(in, stage, R, N, static_cast<size_t>(N), 1.f), svb::count_launch());
+    (reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(stage, out, chunks, N, static_cast<size_t>(N), scale), svb::count_launch());
   } else {
-    reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(in, out, R, N, static_cast<size_t>(N), scale);
+    (reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(in, out, R, N, static_cast<size_t>(N), scale), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("reduce_rows");
   return 0;

@@ -169,10 +169,10 @@ __global__ void gated_stats_finalize_kernel(const float* __restrict__ flat, size
 }
 
 int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p) {
-  prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_gate, nullptr, p->b_dec, pl.Wgb, nullptr, pl.dot, pl.F, pl.C);
+  (prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_gate, nullptr, p->b_dec, pl.Wgb, nullptr, pl.dot, pl.F, pl.C), svb::count_launch());
   const size_t n = static_cast<size_t>(pl.F) * pl.C;
-  convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n);
-  exp_kernel<<<cdiv(pl.F, 256), 256, 0, st>>>(p->r_mag, pl.exp_r, pl.F);
+  (convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n), svb::count_launch());
+  (exp_kernel<<<cdiv(pl.F, 256), 256, 0, st>>>(p->r_mag, pl.exp_r, pl.F), svb::count_launch());
   SVB_LAUNCH_CHECK("gated prep");
   return 0;
 }
@@ -228,8 +228,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
   SVB_TRY(run_prep(st, pl, p));
-  fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
-      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u);
+  (fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
+      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u), svb::count_launch());
 
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
@@ -243,12 +243,12 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v)), "via");
   if (pl.hw > 1) {
-    channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw);
-    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw);
+    (channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw), svb::count_launch());
+    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw), svb::count_launch());
   } else {
-    channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T);
-    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T);
-    row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C);
+    (channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T), svb::count_launch());
+    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T), svb::count_launch());
+    (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("channel_stats");
   EpiGatedDPre::Params e3{};
@@ -268,21 +268,21 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   SVB_TRY(reduce_rows(st, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
   SVB_TRY(reduce_rows(st, pl.cs_pi, pl.tiles_m, F, 1.f, pl.stage, pl.csum_pi));
   SVB_TRY(reduce_rows(st, pl.cs_mage, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mage));
-  gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.csum_pi, pl.csum_mage, pl.exp_r, p->b_mag, s, F,
-                                                      pl.csum_a, flat + pl.o_gbg, flat + pl.o_gbm, flat + pl.o_gr);
-  sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd);
-  wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg);
-  vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm);
-  bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 2);
-  gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
-                                             pl.o_sums, pl.o_chansq, pl.o_max);
-  activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count);
-  activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
-                                                               out ? out->activity.n_active : nullptr, pl.nact_f);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5);
+  (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.csum_pi, pl.csum_mage, pl.exp_r, p->b_mag, s, F,
+                                                      pl.csum_a, flat + pl.o_gbg, flat + pl.o_gbm, flat + pl.o_gr), svb::count_launch());
+  (sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd), svb::count_launch());
+  (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg), svb::count_launch());
+  (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm), svb::count_launch());
+  (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 2), svb::count_launch());
+  (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+                                             pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
+  (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());
+  (activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
+                                                               out ? out->activity.n_active : nullptr, pl.nact_f), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5), svb::count_launch());
   SVB_LAUNCH_CHECK("gated grad assembly");
   if (out && out->dec_out)
     SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
@@ -309,24 +309,24 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
   const AdamCoef k = adam_coef(opt);
-  adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC, k, nullptr);
-  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_gate, flat + pl.o_gbg, adam->m[1], adam->v[1], F, k, nullptr);
-  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_mag, flat + pl.o_gbm, adam->m[2], adam->v[2], F, k, nullptr);
-  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], F, k, nullptr);
+  (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_gate, flat + pl.o_gbg, adam->m[1], adam->v[1], F, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_mag, flat + pl.o_gbm, adam->m[2], adam->v[2], F, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], F, k, nullptr), svb::count_launch());
   if (opt->optimizer == SVB_CONSTRAINED_ADAM)
-    constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k);
+    (constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k), svb::count_launch());
   else
-    adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC, k, nullptr);
-  adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], C, k, nullptr);
+    (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], C, k, nullptr), svb::count_launch());
   SVB_LAUNCH_CHECK("gated adam");
   const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
   const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
   if (out && out->stats)
-    gated_stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
-                                                   expansion_factor, out->stats);
+    (gated_stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
+                                                   expansion_factor, out->stats), svb::count_launch());
   if (out && (out->activity.dead || out->activity.freq || out->stats))
-    activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
-                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr);
+    (activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
+                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr), svb::count_launch());
   SVB_LAUNCH_CHECK("gated finalize");
   return 0;
 }

@@ -158,9 +158,9 @@ __global__ void stats_finalize_kernel(const float* __restrict__ flat, size_t o_s
 }
 
 int run_prep(cudaStream_t st, const SaePlan& pl, const svb_sae_params* p) {
-  prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, pl.Web, pl.fold, nullptr, pl.F, pl.C);
+  (prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, pl.Web, pl.fold, nullptr, pl.F, pl.C), svb::count_launch());
   const size_t n = static_cast<size_t>(pl.F) * pl.C;
-  convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n);
+  (convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n), svb::count_launch());
   SVB_LAUNCH_CHECK("prep");
   return 0;
 }
@@ -206,67 +206,77 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  prof_begin_step(h);
+  prof_mark(h, st, 0);
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
   SVB_TRY(run_prep(st, pl, p));
-  fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
-      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u);
+  (fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
+      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u), svb::count_launch());
 
+  prof_mark(h, st, 1);
   // G1 encoder
   EpiEnc::Params e1{};
   e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
   e1.hw = pl.hw; e1.words = pl.words;
   SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
+  prof_mark(h, st, 2);
   // G2 decoder
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
+  prof_mark(h, st, 3);
   // channel statistics
   if (pl.hw > 1) {
-    channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw);
-    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw);
+    (channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw), svb::count_launch());
+    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw), svb::count_launch());
   } else {
-    channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T);
-    channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T);
-    row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C);
+    (channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T), svb::count_launch());
+    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T), svb::count_launch());
+    (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("channel_stats");
+  prof_mark(h, st, 4);
   // G3 dE -> dPre'
   EpiDPre::Params e3{};
   e3.e = pl.E; e3.dpre = pl.DP; e3.colsum_partial = pl.colsum_part;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   e3.block_n = 256;
   SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
+  prof_mark(h, st, 5);
   // G4 / G5 weight gradients, split-K over tokens
   const size_t FC = static_cast<size_t>(F) * C;
   EpiStore::Params e4{pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  prof_mark(h, st, 6);
   EpiStore::Params e5{pl.P_we, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
 
+  prof_mark(h, st, 7);
   // gradient assembly
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
   SVB_TRY(reduce_rows(st, pl.colsum_part, pl.tiles_m, F, 1.f, pl.stage, pl.csum));
-  sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd);
-  wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_we, pl.s_we, F, C, pl.csum, p->b_dec, s, flat + pl.o_gwe);
-  vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum, pl.Web, F, C, pl.vm);
-  bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd);
-  sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe);  // gb_enc = s * csum
+  (sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd), svb::count_launch());
+  (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_we, pl.s_we, F, C, pl.csum, p->b_dec, s, flat + pl.o_gwe), svb::count_launch());
+  (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum, pl.Web, F, C, pl.vm), svb::count_launch());
+  (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
+  (sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe), svb::count_launch());  // gb_enc = s * csum
   // loss partial sums
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1);
-  stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
-                                       pl.o_sums, pl.o_chansq, pl.o_max);
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+                                       pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);
   // activity
-  activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count);
-  activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
-                                                               out ? out->activity.n_active : nullptr, pl.nact_f);
-  reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5);
+  (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());
+  (activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
+                                                               out ? out->activity.n_active : nullptr, pl.nact_f), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5), svb::count_launch());
   SVB_LAUNCH_CHECK("grad assembly");
   // decoder output handed back to the model (model_pipeline.py:425,432)
   if (out && out->dec_out)
     SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
+  prof_mark(h, st, 8);
   h->gradbuf = flat;
   h->sum_elems = static_cast<int64_t>(pl.sum_elems);
   h->max_elems = static_cast<int64_t>(pl.max_elems);
@@ -290,25 +300,26 @@ extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
   const AdamCoef k = adam_coef(opt);
-  adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC, k, nullptr);
-  adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_enc, flat + pl.o_gbe, adam->m[1], adam->v[1], F, k, nullptr);
+  (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_enc, flat + pl.o_gbe, adam->m[1], adam->v[1], F, k, nullptr), svb::count_launch());
   if (opt->optimizer == SVB_CONSTRAINED_ADAM)
-    constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], C, F, k);
+    (constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], C, F, k), svb::count_launch());
   else
-    adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], FC, k, nullptr);
-  adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[3], adam->v[3], C, k, nullptr);
+    (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], FC, k, nullptr), svb::count_launch());
+  (adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[3], adam->v[3], C, k, nullptr), svb::count_launch());
   SVB_LAUNCH_CHECK("adam");
   const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
   const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
   if (out && out->stats) {
-    stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
-                                             expansion_factor, out->stats);
+    (stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
+                                             expansion_factor, out->stats), svb::count_launch());
   }
   if (out && (out->activity.dead || out->activity.freq || out->stats)) {
-    activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
-                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr);
+    (activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
+                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("finalize");
+  prof_mark(h, st, 9);
   return 0;
 }
 

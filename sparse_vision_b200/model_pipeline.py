@@ -1,0 +1,189 @@
+"""The SAE-training slice of the reference's model_pipeline.py: the forward-hook train step (model_pipeline.py:363-432),
+the per-batch metric capture (:278-360), the dead-neuron AND-accumulation and re-initialisation schedule (:744-793)
+and the per-epoch checkpoint (:233-263, :1266-1280).  Base-model training, evaluation aggregation, plotting and MIS
+are out of scope.
+
+What changes relative to the reference: the train branch of the hook is ONE C-ABI call (svb_*_train_step) instead of
+forward + criterion + autograd backward + optimizer.step() + three metric passes; its scalars stay on the device in a
+stats block (one D2H copy when `batch_*` values are read) instead of six .item() syncs per step; the dead-unit mask is
+AND-accumulated on the device.  The optimizer object is still a torch.optim.Adam-shaped ConstrainedAdam / Adam whose
+state tensors (exp_avg / exp_avg_sq / step) the fused step updates in place, so reset_encoder_weights, state_dict()
+and checkpoints behave as in the reference.
+"""
+import os
+
+import torch
+
+from . import ops
+from ._lib import STAT
+from .parallel import DataParallelStep, global_counts
+from .utils import get_criterion, get_optimizer, measure_inactive_units, sae_inference_and_loss, variance_explained
+
+
+def dead_neuron_action(train_batch_idx, dead_neurons_steps):
+    """The two conditions of model_pipeline.py:771 and :792, evaluated after train_batch_idx was incremented.
+    'reinit': re-initialise units dead over the last n steps, then clear; 'clear': clear only; None: keep measuring."""
+    n, i = dead_neurons_steps, train_batch_idx
+    if (i - 1) % n == 0 and ((i - 1) // n) % 2 == 0 and (i - 1) != 0:
+        return "reinit"
+    if i == n or (i > n and i % n == 0 and (i // n) % 2 == 1):
+        return "clear"
+    return None
+
+
+class ModelPipeline:
+    """Trains an SAE on the output of one layer of a frozen base model through a forward hook."""
+
+    def __init__(self, model, sae_model, sae_model_name, sae_layer, sae_optimizer_name="constrained_adam",
+                 sae_learning_rate=1e-3, sae_lambda_sparse=5.0, sae_expansion_factor=8, dead_neurons_steps=None,
+                 device=None, reinit_index_dir=None, data_parallel=False):
+        self.model = model
+        self.sae_model = sae_model
+        self.sae_model_name = sae_model_name
+        if sae_model_name not in ("sae_mlp", "gated_sae"):
+            raise ValueError(f"Unknown SAE model name {sae_model_name}.")
+        self.sae_criterion_name = "sae_loss" if sae_model_name == "sae_mlp" else "gated_sae_loss"
+        self.sae_criterion = get_criterion(self.sae_criterion_name)
+        self.sae_layer = sae_layer
+        self.sae_optimizer_name = sae_optimizer_name
+        self.sae_lambda_sparse = sae_lambda_sparse
+        self.sae_expansion_factor = sae_expansion_factor
+        self.dead_neurons_steps = dead_neurons_steps
+        self.device = device or next(sae_model.parameters()).device
+        self.sae_optimizer, _ = get_optimizer(sae_optimizer_name, sae_model, sae_learning_rate)
+        if self.sae_optimizer.__class__.__name__ not in ("Adam", "ConstrainedAdam"):
+            raise ValueError("the fused SAE step supports 'adam' and 'constrained_adam'")
+        self.reinit_index_dir = reinit_index_dir
+        self.dp = DataParallelStep(sae_model_name) if data_parallel else None
+        self.train_batch_idx = 0
+        self.epoch_batch_idx = 0
+        self.train_dead_neurons = {}
+        self.hooks = []
+        self.train_sae = True
+        self._last = None
+        for p in self.model.parameters():
+            p.requires_grad = False
+        # per-batch quantities, keyed like the reference (model_pipeline.py:394-420)
+        self.batch_dead_units, self.batch_sparsity, self.batch_neuron_frequency = {}, {}, {}
+
+    # ------------------------------------------------------------------ optimizer state shared with the fused step
+    def _adam_tensors(self):
+        params = self.sae_model.param_list()
+        ms, vs = [], []
+        for p in params:
+            st = self.sae_optimizer.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            ms.append(st["exp_avg"])
+            vs.append(st["exp_avg_sq"])
+        for p in params:
+            self.sae_optimizer.state[p]["step"] += 1
+        step = int(self.sae_optimizer.state[params[0]]["step"].item())
+        return [p.data for p in params], ms, vs, step
+
+    # ------------------------------------------------------------------ the hook (model_pipeline.py:363-432)
+    def hook(self, module, input, output, name, use_sae=True, train_sae=True):
+        output = output.detach()
+        if not (use_sae and name == self.sae_layer):
+            return output
+        group = self.sae_optimizer.param_groups[0]
+        if train_sae:
+            params, ms, vs, step = self._adam_tensors()
+            kw = dict(optimizer=self.sae_optimizer_name, betas=group["betas"], eps=group["eps"])
+            if self.dp is not None:
+                n_img = output.shape[0]
+                hw = output.shape[2] * output.shape[3] if output.dim() == 4 else 1
+                g_img, g_tok = global_counts(n_img, hw, device=output.device)
+                res = self.dp.step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
+                                   self.sae_expansion_factor, self.sae_optimizer_name, group["betas"], g_img, g_tok,
+                                   eps=group["eps"])
+            elif self.sae_model_name == "sae_mlp":
+                res = ops.sae_train_step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
+                                         self.sae_expansion_factor, **kw)
+            else:
+                res = ops.gated_train_step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
+                                           self.sae_expansion_factor, **kw)
+            self._last = res
+            self.batch_dead_units[(name, "sae")] = res.dead          # uint8 on the device; AND-ed in train_batch()
+            self.batch_neuron_frequency[(name, "sae")] = res.freq
+            return res.dec                                           # replaces the layer output (:425,432)
+        with torch.no_grad():
+            r = sae_inference_and_loss(self.sae_model_name, self.sae_model, self.sae_criterion_name, output,
+                                       self.sae_criterion, self.sae_lambda_sparse)
+        loss, rec, l1, nrmse, rmse, aux, enc, pre, dec = r
+        dead, sparsity, freq = measure_inactive_units(enc, self.sae_expansion_factor)
+        self._last = {"loss": loss, "rec": rec, "l1": l1, "nrmse": nrmse, "rmse": rmse, "aux": aux,
+                      "sparsity": sparsity, "var_expl": variance_explained(output, dec)}
+        self.batch_dead_units[(name, "sae")] = dead.to(torch.uint8)
+        self.batch_neuron_frequency[(name, "sae")] = freq
+        return dec.to(output.dtype)
+
+    def register_hooks(self, train_sae=True):
+        """model_pipeline.py:445-475: a forward hook on the SAE layer."""
+        self.remove_hooks()
+        self.train_sae = train_sae
+        module = dict(self.model.named_modules())[self.sae_layer]
+        name = self.sae_layer
+        self.hooks.append(module.register_forward_hook(
+            lambda m, i, o: self.hook(m, i, o, name, use_sae=True, train_sae=self.train_sae)))
+
+    def remove_hooks(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+    def batch_scalars(self):
+        """loss / rec / l1 / nrmse / rmse / aux / var_expl / sparsity of the last batch as python floats
+        (the values the reference stores in batch_sae_* at model_pipeline.py:394-399,420) — one D2H copy."""
+        if self._last is None:
+            return {}
+        if isinstance(self._last, dict):
+            return {k: float(v) for k, v in self._last.items()}
+        return self._last.scalars()
+
+    # ------------------------------------------------------------------ one training batch + dead-neuron schedule
+    def train_batch(self, inputs, epoch=0):
+        """model_pipeline.py:603-793 for one batch: frozen base-model forward (the hook trains the SAE), then
+        train_batch_idx bookkeeping, dead-mask accumulation and the re-initialisation schedule."""
+        self.epoch_batch_idx += 1
+        with torch.no_grad():
+            outputs = self.model(inputs)
+        self.train_batch_idx += 1
+        for key, dead in self.batch_dead_units.items():                      # :744-748 (AND == product of bools)
+            self.train_dead_neurons[key] = dead if key not in self.train_dead_neurons \
+                else self.train_dead_neurons[key] & dead
+        action = None
+        if self.dead_neurons_steps:
+            action = dead_neuron_action(self.train_batch_idx, self.dead_neurons_steps)
+            if action == "reinit":
+                dead = self.train_dead_neurons[(self.sae_layer, "sae")].bool()
+                file_path = None
+                if self.reinit_index_dir:
+                    os.makedirs(self.reinit_index_dir, exist_ok=True)
+                    file_path = os.path.join(
+                        self.reinit_index_dir,
+                        f"epoch_{epoch}_train_batch_idx_{self.train_batch_idx}_epoch_batch_idx_{self.epoch_batch_idx}.txt")
+                self.sae_model.reset_encoder_weights(dead, self.device, self.sae_optimizer, epoch,
+                                                     self.train_batch_idx, self.epoch_batch_idx, file_path)
+                self.train_dead_neurons = {}
+            elif action == "clear":
+                self.train_dead_neurons = {}
+        return outputs, action
+
+    # ------------------------------------------------------------------ checkpoints (reference dict keys)
+    def save_checkpoint(self, path, epoch):
+        torch.save({"epoch": epoch, "model_state_dict": self.sae_model.state_dict(),
+                    "optimizer_state_dict": self.sae_optimizer.state_dict(),
+                    "training_step": self.train_batch_idx}, path)                 # model_pipeline.py:1268-1273
+
+    def load_checkpoint(self, path):
+        ckpt = torch.load(path, map_location=self.device)
+        self.sae_model.load_state_dict(ckpt["model_state_dict"])
+        self.sae_optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        self.train_batch_idx = ckpt["training_step"]                              # model_pipeline.py:255-262
+        return ckpt["epoch"]
+
+
+STAT_NAMES = tuple(STAT)

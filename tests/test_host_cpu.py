@@ -1,0 +1,181 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/svb.h declares, the host logic
+mirrors the reference (initialisation RNG stream, schedule, error behaviour) and the data-parallel plumbing works on
+gloo with world_size 2.  No compute entry point is called here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sparse_vision_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from sparse_vision_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "svb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.svb_version() >= 100
+    assert isinstance(lib.svb_launch_count(), int)
+
+
+def test_no_cpu_fallback():
+    from sparse_vision_b200 import _lib
+    from sparse_vision_b200.models import GatedSae, SaeMLP
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less machine")
+    with pytest.raises(_lib.SvbError):
+        _lib.handle()
+    with pytest.raises(ValueError):
+        SaeMLP(16, 4)(torch.randn(3, 16))
+    with pytest.raises(ValueError):
+        GatedSae(16, 4)(torch.randn(3, 16))
+
+
+def test_product_package_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sparse_vision_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_module_init_matches_reference_rng_stream(golden_dir):
+    from sparse_vision_b200.models import GatedSae, SaeMLP
+    g = dict(np.load(os.path.join(golden_dir, "cfg1_mlp_adam.npz")))
+    torch.manual_seed(0)
+    m = SaeMLP((16,), 4)
+    assert [k for k, _ in m.named_parameters()] == ["encoder.weight", "encoder.bias", "decoder.weight", "decoder.bias"]
+    for k, v in m.state_dict().items():
+        assert np.array_equal(v.numpy(), g["init." + k]), k
+    g = dict(np.load(os.path.join(golden_dir, "conv_gated_cadam.npz")))
+    torch.manual_seed(0)
+    m = GatedSae(32, 4)
+    assert [k for k, _ in m.named_parameters()] == ["W_gate", "b_gate", "b_mag", "r_mag", "decoder.weight",
+                                                    "decoder.bias"]
+    # the planted-dead fixture edits b_gate / b_mag after construction; weights must match bit for bit
+    for k in ("W_gate", "decoder.weight", "r_mag", "decoder.bias"):
+        assert np.array_equal(m.state_dict()[k].numpy(), g["init." + k]), k
+
+
+def test_sae_conv_shell_matches_reference(golden_dir):
+    from sparse_vision_b200.models import SaeConv
+    g = dict(np.load(os.path.join(golden_dir, "sae_conv.npz")))
+    m = SaeConv((8, 6, 6), 2)
+    m.load_state_dict({k[len("init."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("init.")})
+    with torch.no_grad():
+        enc, dec = m(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(enc.numpy(), g["enc"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dec.numpy(), g["dec"], rtol=1e-5, atol=1e-6)
+
+
+def test_dead_neuron_schedule_matches_reference(golden_dir):
+    from sparse_vision_b200.model_pipeline import dead_neuron_action
+    g = dict(np.load(os.path.join(golden_dir, "schedule.npz")))
+    for n, upto in ((9912, 100000), (8, 70)):
+        assert [i for i in range(1, upto + 1) if dead_neuron_action(i, n) == "reinit"] == list(g[f"reinit_{n}"])
+        assert [i for i in range(1, upto + 1) if dead_neuron_action(i, n) == "clear"] == list(g[f"wait_{n}"])
+
+
+def test_optimizer_and_criterion_factories():
+    from sparse_vision_b200 import utils as U
+    from sparse_vision_b200.models import SaeMLP
+    m = SaeMLP(16, 2)
+    opt, sched = U.get_optimizer("constrained_adam", m, 1e-3)
+    assert opt.__class__.__name__ == "ConstrainedAdam" and sched is None
+    assert opt.param_groups[0]["betas"] == (0.9, 0.999) and opt.p is m.decoder.weight
+    opt, _ = U.get_optimizer("adam", m, 1e-3)
+    assert opt.__class__.__name__ == "Adam" and opt.param_groups[0]["betas"] == (0.9, 0.9999)
+    with pytest.raises(ValueError, match="Unsupported optimizer"):
+        U.get_optimizer("lion", m, 1e-3)
+    assert U.get_criterion("sae_loss").__class__.__name__ == "SparseLoss"
+    assert U.get_criterion("gated_sae_loss").__class__.__name__ == "GatedSAELoss"
+    with pytest.raises(ValueError, match="Unsupported criterion"):
+        U.get_criterion("nope")
+    with pytest.raises(ValueError, match="Unknown SAE model name"):
+        U.sae_inference_and_loss("sae_conv", m, "sae_loss", torch.randn(2, 16), None, 0.1)
+
+
+def test_loss_modules_match_reference_golden(golden_dir):
+    from oracle import sae_oracle as O
+    from sparse_vision_b200.losses import GatedSAELoss, SparseLoss
+    g = dict(np.load(os.path.join(golden_dir, "conv_mlp_cadam.npz")))
+    enc = torch.from_numpy(g["step0.enc"])
+    dec = O.to_tokens(torch.from_numpy(g["step0.dec"]))[0]
+    x = O.to_tokens(torch.from_numpy(g["x"][0]))[0]
+    rec, l1, nrmse, rmse = SparseLoss()(enc, dec, x)
+    ref = g["step0.scalars"]
+    np.testing.assert_allclose([rec.item(), l1.item(), nrmse.item(), rmse.item()], ref[1:5], rtol=1e-5)
+    with pytest.raises(AssertionError):
+        SparseLoss()(enc, dec[:, :-1], x)
+    assert len(GatedSAELoss()(enc, dec, dec, x)) == 5
+
+
+def test_shard_images():
+    from sparse_vision_b200.parallel import shard_images
+    for n, w in ((256, 8), (10, 4), (3, 8)):
+        spans = [shard_images(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sparse_vision_b200.parallel import all_reduce_flat, global_counts, shard_images
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = shard_images(10, r, w)
+g_img, g_tok = global_counts(hi - lo, 49)
+assert (g_img, g_tok) == (10, 490), (g_img, g_tok)
+# flat buffer: 6 SUM elements then 4 MAX elements
+flat = torch.cat([torch.arange(6, dtype=torch.float32) * (r + 1), torch.tensor([1.0, -2.0, 3.0, 4.0]) * (1 if r == 0 else -1)])
+all_reduce_flat(flat, 6, 4)
+want_sum = torch.arange(6, dtype=torch.float32) * sum(range(1, w + 1))
+assert torch.equal(flat[:6], want_sum), flat
+assert torch.equal(flat[6:], torch.tensor([1.0, 2.0, 3.0, 4.0])), flat
+# sharded means equal the global mean: the identity the IE / loss reductions rely on
+x = torch.arange(10, dtype=torch.float64)
+part = torch.tensor([x[lo:hi].sum()])
+dist.all_reduce(part)
+assert abs(part.item() / g_img - x.mean().item()) < 1e-12
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_prints_contract_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-images", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    import json
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "act-vec/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
