@@ -309,7 +309,7 @@ def run_svb(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="svb", choices=["svb", "reference"])
     ap.add_argument("--images", type=int, default=256, help="images per GPU per step")
