@@ -1,9 +1,12 @@
-// Epilogue functors for gemm_bf16_kernel.  An epilogue thread owns ONE accumulator row (token or feature,
-// depending on the GEMM) and receives it 32 columns at a time.  Rows >= M and columns >= N hold garbage-free
-// zeros from TMA out-of-bounds fill, but they must still be masked out of every reduction and store.
+// Epilogue functors for gemm_bf16_kernel.  An epilogue thread owns ONE accumulator row (a token, or a feature in the
+// weight-gradient GEMMs) and receives it 32 columns at a time.  Rows >= M and columns >= N hold zeros from TMA
+// out-of-bounds fill, but they must still be masked out of every reduction and store.
 //
-// All floating-point reductions are written as per-(tile,warp) partials and summed later in a fixed order, so a
-// step is bit-reproducible run to run; integer activity bits use atomicOr (order-independent).
+// bf16 outputs on the hot path leave through shared memory: each warp stages 32-row x 64-column slabs (128-byte rows,
+// 128B swizzle, bank-conflict free) and one lane issues a TMA tensor store, so global writes are full 128-byte lines
+// instead of 32 scattered 16-byte pieces per instruction (which made the first version of the encoder GEMM 4x
+// slower than its MMA time).  All floating-point reductions are written as per-(tile,warp) partials and summed later
+// in a fixed order, so a step is bit-reproducible; integer activity bits use atomicOr (order-independent).
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -14,17 +17,18 @@ __device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32], 
   for (int i = 0; i < 8; ++i)
     if (i * 4 < nvalid) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  return q;
+}
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32], int nvalid) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    if (i * 8 < nvalid) {
-      uint4 q;
-      q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      reinterpret_cast<uint4*>(dst)[i] = q;
-    }
+    if (i * 8 < nvalid) reinterpret_cast<uint4*>(dst)[i] = pack8_bf16(v + 8 * i);
 }
 __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, float (&o)[32], int nvalid) {
 #pragma unroll
@@ -74,10 +78,53 @@ __device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_p
   }
 }
 
+// Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores (two 4 KB buffers).
+struct SlabWriter {
+  static constexpr uint32_t kBytesPerWarp = 2 * 4096;
+  static constexpr uint32_t kBytes = 4 * kBytesPerWarp;  // four epilogue warps
+  uint8_t* base;
+  uint32_t which;
+  bool half_pending;
+  __device__ void init(uint8_t* epi_smem, int wq) {
+    base = epi_smem + wq * kBytesPerWarp;
+    which = 0;
+    half_pending = false;
+  }
+  // columns [half*32, half*32+32) of this lane's row; 16-byte pieces land XOR-swizzled like the tensor map expects
+  __device__ void put(int half, int lane, const float (&v)[32]) {
+    uint8_t* row = base + which * 4096 + lane * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = half * 4 + i;
+      *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+    }
+    half_pending = (half == 0);
+  }
+  // col0 / row0: element coordinates of the slab's first column / row in the output tensor
+  __device__ void flush(const CUtensorMap* tm, int col0, int row0, int lane) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, base + which * 4096, col0, row0);
+      bulk_commit();
+      bulk_wait_read<1>();  // the OTHER buffer's store has finished reading: it may be overwritten next
+    }
+    __syncwarp();
+    which ^= 1;
+    half_pending = false;
+  }
+  __device__ void drain(int lane) {
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ plain store
-// out = [relu](alpha*acc + bias), fp32 or bf16; split-K slices land split_stride elements apart.
+// out = [relu](alpha*acc + bias), fp32 (direct) or bf16 (TMA slabs when tm_valid); split-K slices land
+// split_stride elements apart.
 struct EpiStore {
   struct Params {
+    alignas(64) CUtensorMap tm;  // bf16 output map (box 64 x 32) when tm_valid
     void* out;
     long long ld;
     long long split_stride;
@@ -85,12 +132,14 @@ struct EpiStore {
     float alpha;
     int relu;
     int out_bf16;
+    int tm_valid;
   };
-  static constexpr uint32_t kSmemBytes = 0;
+  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes;
   const Params& p;
-  __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
+  SlabWriter slab;
+  __device__ EpiStore(const Params& p_, uint8_t* smem) : p(p_) { slab.init(smem, (threadIdx.x / 32) % 4); }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int, int) {
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
     const int nvalid = min(32, g.N - col0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -99,34 +148,52 @@ struct EpiStore {
       if (p.relu) x = fmaxf(x, 0.f);
       v[j] = x;
     }
+    if (p.out_bf16 && p.tm_valid) {
+      const int half = (col0 >> 5) & 1;
+      slab.put(half, lane, v);
+      if (half == 1) slab.flush(&p.tm, col0 - 32, ti.m0 + wq * 32, lane);
+      return;
+    }
     if (row >= g.M) return;
     const long long off = ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0;
     if (p.out_bf16) store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, nvalid);
     else store_row_f32(reinterpret_cast<float*>(p.out) + off, v, nvalid);
   }
-  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
+    if (slab.half_pending) slab.flush(&p.tm, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
+  }
+  __device__ void finish(int, int lane) { slab.drain(lane); }
 };
 
 // ------------------------------------------------------------------------------------------------ encoder
 // pre = acc + bias';  e = relu(pre)   (sae_mlp.py:49-51 with the pre-bias folded: bias' = b_enc - W_enc b_dec)
-// Fused: bf16/fp32 stores of e (and pre), per-image activity bits (utils.py:2033-2047), sum|e| partials
-// (sparse_loss.py:41).
+// Fused: bf16 store of e (TMA slabs), optional fp32 stores of e / pre (API forward), per-row activity words
+// (1 bit per element: the ReLU mask the backward needs), per-image activity bits (utils.py:2033-2047) and sum|e|
+// partials (sparse_loss.py:41).
 struct EpiEnc {
   struct Params {
-    const float* bias;      // [N]
-    __nv_bfloat16* e_bf16;  // [M,N] or null
-    float* e_f32;           // [M,N] or null
-    float* pre_f32;         // [M,N] or null
-    uint32_t* act_bits;     // [n_img, words] or null
-    float* l1_partial;      // [tiles_m*tiles_n*4] or null
-    int hw;                 // tokens per image (1 for 2-D inputs)
-    int words;              // ceil(N/32)
+    alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], box 64 x 32 (valid when e_bf16 != null)
+    const float* bias;             // [N]
+    __nv_bfloat16* e_bf16;         // [M,N] or null
+    float* e_f32;                  // [M,N] or null
+    float* pre_f32;                // [M,N] or null
+    uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
+    uint32_t* act_bits;            // [n_img, words] or null
+    float* l1_partial;             // [tiles_m*tiles_n*4] or null
+    int hw;                        // tokens per image (1 for 2-D inputs)
+    int words;                     // ceil(N/32)
   };
-  static constexpr uint32_t kSmemBytes = 0;
+  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes;
   const Params& p;
+  SlabWriter slab;
   float sum;
-  __device__ EpiEnc(const Params& p_, uint8_t*) : p(p_), sum(0.f) {}
-  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
+  uint32_t words[8];
+  __device__ EpiEnc(const Params& p_, uint8_t* smem) : p(p_), sum(0.f) { slab.init(smem, (threadIdx.x / 32) % 4); }
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) words[i] = 0;
+  }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
                         int lane) {
     const int nvalid = min(32, g.N - col0);
@@ -146,93 +213,161 @@ struct EpiEnc {
       if (j < nvalid) sum += e;
     }
     if (!row_ok) word = 0;
-    if (row_ok) {
-      if (p.e_bf16) store_row_bf16(p.e_bf16 + off, v, nvalid);
-      if (p.e_f32) store_row_f32(p.e_f32 + off, v, nvalid);
+    const int c = (col0 - ti.n0) >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i == c) words[i] = word;
+    if (p.e_bf16) {
+      const int half = c & 1;
+      slab.put(half, lane, v);
+      if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane);
     }
+    if (p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
     if (p.act_bits) publish_activity(p.act_bits, p.words, col0 >> 5, word, row, g.M, p.hw, ti.m0 + wq * 32, lane);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
-    if (!p.l1_partial) return;
-    const float s = warp_sum(row < g.M ? sum : 0.f);
-    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+    if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
+    if (p.mask_words && row < g.M) {
+      uint32_t* dst = p.mask_words + static_cast<size_t>(row) * p.words + (ti.n0 >> 5);
+      const int nw = min(8, p.words - (ti.n0 >> 5));
+      if (nw == 8 && (p.words & 3) == 0) {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nw) dst[i] = words[i];
+      }
+    }
+    if (p.l1_partial) {
+      const float s = warp_sum(row < g.M ? sum : 0.f);
+      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+    }
   }
+  __device__ void finish(int, int lane) { slab.drain(lane); }
 };
 
 // ------------------------------------------------------------------------------------------------ decoder
 // d = acc + b_dec;  diff = d - x   (sae_mlp.py:52, sparse_loss.py:35).  Fused: stores of d / diff, sum diff^2.
 struct EpiDec {
   struct Params {
-    const float* bias;           // [N] decoder bias
-    const __nv_bfloat16* x;      // [M,N] targets (SAE input) or null (then diff = d)
-    __nv_bfloat16* d_bf16;       // [M,N] or null
-    float* d_f32;                // [M,N] or null
-    __nv_bfloat16* diff_bf16;    // [M,N] or null
-    float* sq_partial;           // [tiles_m*tiles_n*4] or null
+    alignas(64) CUtensorMap tm_d;     // bf16 d [M,N]   (valid when d_bf16 != null)
+    alignas(64) CUtensorMap tm_diff;  // bf16 diff [M,N] (valid when diff_bf16 != null)
+    const float* bias;                // [N] decoder bias
+    const __nv_bfloat16* x;           // [M,N] targets (SAE input) or null
+    __nv_bfloat16* d_bf16;            // [M,N] or null
+    float* d_f32;                     // [M,N] or null
+    __nv_bfloat16* diff_bf16;         // [M,N] or null
+    float* sq_partial;                // [tiles_m*tiles_n*4] or null
   };
-  static constexpr uint32_t kSmemBytes = 0;
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter::kBytes;
   const Params& p;
+  SlabWriter slab_d, slab_f;
   float sq;
-  __device__ EpiDec(const Params& p_, uint8_t*) : p(p_), sq(0.f) {}
+  __device__ EpiDec(const Params& p_, uint8_t* smem) : p(p_), sq(0.f) {
+    slab_d.init(smem, (threadIdx.x / 32) % 4);
+    slab_f.init(smem + SlabWriter::kBytes, (threadIdx.x / 32) % 4);
+  }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sq = 0.f; }
-  __device__ void chunk(const GemmProblem& g, const TileInfo&, int row, int col0, float (&v)[32], int, int) {
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
+                        int lane) {
     const int nvalid = min(32, g.N - col0);
-    if (row >= g.M) return;
+    const bool row_ok = row < g.M;
+    const int half = ((col0 - ti.n0) >> 5) & 1;
     float b[32];
     load_row_f32(p.bias + col0, b, nvalid);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     const long long off = static_cast<long long>(row) * g.N + col0;
-    if (p.d_bf16) store_row_bf16(p.d_bf16 + off, v, nvalid);
-    if (p.d_f32) store_row_f32(p.d_f32 + off, v, nvalid);
+    if (p.d_bf16) {
+      slab_d.put(half, lane, v);
+      if (half == 1) slab_d.flush(&p.tm_d, col0 - 32, ti.m0 + wq * 32, lane);
+    }
+    if (p.d_f32 && row_ok) store_row_f32(p.d_f32 + off, v, nvalid);
     if (p.x) {
-      load_row_bf16(p.x + off, b, nvalid);
+      load_row_bf16(p.x + (row_ok ? off : 0), b, row_ok ? nvalid : 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         v[j] -= b[j];
-        if (j < nvalid) sq += v[j] * v[j];
+        if (j < nvalid && row_ok) sq += v[j] * v[j];
       }
-      if (p.diff_bf16) store_row_bf16(p.diff_bf16 + off, v, nvalid);
+      if (p.diff_bf16) {
+        slab_f.put(half, lane, v);
+        if (half == 1) slab_f.flush(&p.tm_diff, col0 - 32, ti.m0 + wq * 32, lane);
+      }
     }
   }
-  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
-    if (!p.sq_partial) return;
-    const float s = warp_sum(row < g.M ? sq : 0.f);
-    if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
+    const int last = ((g.N - 1) >> 6) << 6;
+    if (slab_d.half_pending) slab_d.flush(&p.tm_d, last, ti.m0 + wq * 32, lane);
+    if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane);
+    if (p.sq_partial) {
+      const float s = warp_sum(sq);
+      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+    }
+  }
+  __device__ void finish(int, int lane) {
+    slab_d.drain(lane);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ dE -> dPre
 // acc = diff * W_dec  (unscaled dE);  dPre' = 1[e>0] * (acc + l1c)  with l1c = lambda*C/(2F), i.e. the whole
 // backward is carried in units of T*C/2 and rescaled once in the gradient reduction (model_pipeline.py:385 autograd
-// of sparse_loss.py:35,41 through sae_mlp.py:51).  Fused: bf16 store of dPre', per-feature column sums (-> db_enc).
+// of sparse_loss.py:35,41 through sae_mlp.py:51).  The ReLU mask comes from the encoder's 1-bit activity words
+// (32 B per row and tile instead of re-reading 512 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
+// column sums (-> db_enc).
 struct EpiDPre {
   struct Params {
-    const __nv_bfloat16* e;    // [M,N] encoder output
-    __nv_bfloat16* dpre;       // [M,N]
-    float* colsum_partial;     // [tiles_m, N]
+    alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
+    const uint32_t* mask_words;        // [M, words]
+    float* colsum_partial;             // [tiles_m, N]
     float l1c;
-    int block_n;               // BLOCK_N of the launching GEMM
+    int words;
+    int block_n;                       // BLOCK_N of the launching GEMM
   };
-  static constexpr uint32_t kSmemBytes = 4 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 4 * 256 * sizeof(float);
   const Params& p;
+  SlabWriter slab;
   float* s_col;  // [4][256]
-  __device__ EpiDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem)) {}
-  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
-                        int lane) {
-    const int nvalid = min(32, g.N - col0);
-    const bool row_ok = row < g.M;
-    float e[32];
-    const long long off = static_cast<long long>(row) * g.N + col0;
-    load_row_bf16(p.e + (row_ok ? off : 0), e, row_ok ? nvalid : 0);
+  uint32_t words[8];
+  __device__ EpiDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter::kBytes)) {
+    slab.init(smem, (threadIdx.x / 32) % 4);
+  }
+  __device__ void begin_tile(const GemmProblem& g, const TileInfo& ti, int row, int, int) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (e[j] > 0.f) ? v[j] + p.l1c : 0.f;
-    if (row_ok) store_row_bf16(p.dpre + off, v, nvalid);
+    for (int i = 0; i < 8; ++i) words[i] = 0;
+    if (row < g.M) {
+      const uint32_t* src = p.mask_words + static_cast<size_t>(row) * p.words + (ti.n0 >> 5);
+      const int nw = min(8, p.words - (ti.n0 >> 5));
+      if (nw == 8 && (p.words & 3) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+        words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
+        words[4] = b.x; words[5] = b.y; words[6] = b.z; words[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nw) words[i] = __ldg(src + i);
+      }
+    }
+  }
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
+    const int c = (col0 - ti.n0) >> 5;
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i == c) word = words[i];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] + p.l1c : 0.f;
+    const int half = c & 1;
+    slab.put(half, lane, v);
+    if (half == 1) slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
     const float cs = warp_colsum32(v, lane);
     s_col[wq * 256 + (col0 - ti.n0) + lane] = cs;
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
+    if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
     epi_bar_sync();
     const int t = wq * 32 + lane;
 #pragma unroll
@@ -245,6 +380,7 @@ struct EpiDPre {
     }
     epi_bar_sync();
   }
+  __device__ void finish(int, int lane) { slab.drain(lane); }
 };
 
 }  // namespace svb

@@ -66,6 +66,7 @@ struct EpiGatedEnc {
     const float s = warp_sum(row < g.M ? sum : 0.f);
     if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
   }
+  __device__ void finish(int, int) {}
 };
 
 // ------------------------------------------------------------------------------------------------ gated dE
@@ -131,6 +132,7 @@ struct EpiGatedDPre {
     }
     epi_bar_sync();
   }
+  __device__ void finish(int, int) {}
 };
 
 }  // namespace svb

@@ -46,6 +46,11 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, u
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+// Row-major bf16 output [rows, cols] written in 32-row x 64-column slabs by the epilogue warps (128B swizzle).
+inline int make_store_tmap_bf16(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  return make_tmap_bf16_2d(out, ptr, rows, cols, ld, 32);
+}
+
 inline int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -62,7 +67,7 @@ inline int device_sm_count() {
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
   int rc;
@@ -93,7 +98,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   if (splits_out) *splits_out = splits;
 
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, Epi>;
-  const uint32_t smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  const uint32_t smem = Cfg::kSmemBytes;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -4;

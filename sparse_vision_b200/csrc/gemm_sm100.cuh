@@ -38,17 +38,21 @@ struct TileInfo {
   int tile_n;
 };
 
-template <int BLOCK_N>
+constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
+
+template <int BLOCK_N, uint32_t EPI_BYTES>
 struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static constexpr uint32_t kBarrierBytes = 256;  // 2*stages + 4 mbarriers + tmem ptr
-  static constexpr uint32_t smem_bytes(uint32_t epi_bytes) {
-    return 1024 /*alignment slack*/ + kStages * kStageBytes + kBarrierBytes + epi_bytes;
-  }
+  static constexpr uint32_t kEpiBytes = (EPI_BYTES + 1023u) & ~1023u;  // epilogue staging, 1024-aligned (TMA swizzle)
+  static constexpr int kFit = static_cast<int>((kMaxDynSmem - 1024 - kBarrierBytes - kEpiBytes) / kStageBytes);
+  static constexpr int kCap = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = kFit < kCap ? kFit : kCap;
+  static constexpr uint32_t kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kEpiBytes + kBarrierBytes;
+  static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
@@ -65,20 +69,20 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmProblem p, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                 const GemmProblem p, const __grid_constant__ typename Epi::Params ep) {
+  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes>;
   constexpr int STAGES = Cfg::kStages;
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
   static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::kBarrierBytes, "barrier region too small");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;  // 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes + Cfg::kBarrierBytes;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
   const int lane = static_cast<int>(threadIdx.x) % 32;
@@ -204,6 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    epi.finish(wq, lane);  // e.g. drain outstanding bulk stores before the CTA's smem goes away
   }
 
   tc_fence_before();

@@ -310,13 +310,16 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   // a = SAE_enc(x)
   EpiEnc::Params e1{};
   e1.bias = fold; e1.e_bf16 = E; e1.hw = HW; e1.words = (F + 31) / 32;
+  if (make_store_tmap_bf16(&e1.tm_e, E, Ti, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
   SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, Xp, C, Web, C, Ti, F, C, 1, e1)), "enc");
   // DIFF = dec - x = -(sae error)
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = Xp; e2.diff_bf16 = DIFF;
+  if (make_store_tmap_bf16(&e2.tm_diff, DIFF, Ti, C, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, E, F, Wdb, F, Ti, C, F, 1, e2)), "dec");
   // enc.grad = g W_dec   (nnsight_intervention_check.py:194-195)
-  EpiStore::Params e3{GE, F, 0, nullptr, 1.f, 0, 1};
+  EpiStore::Params e3;
+  make_store_params(&e3, GE, F, 0, nullptr, 1.f, 0, 1, Ti, F);
   SVB_GEMM((launch_gemm<256, false, true, EpiStore>(st, Gp, C, Wdb, F, Ti, F, C, 1, e3)), "g W_dec");
   if (ie_features)
     SVB_TRY(launch_ie_channelwise<bf16>(st, h->sms, E, GE, avgT_f, T, HW, F, scale, partial, chunks_f, stage, ie_features));
@@ -338,7 +341,8 @@ int gemm_dispatch(svb_handle* h, cudaStream_t st, const void* A, int64_t lda, co
   const bool can_split = out_dtype == SVB_F32 && !bias && !relu && ldo == N;
   const int splits = can_split ? planned_splits<256>(M, N, K, 0) : 1;
   if (splits <= 1) {
-    EpiStore::Params ep{out, ldo, 0, bias, alpha, relu, out_dtype == SVB_BF16 ? 1 : 0};
+    EpiStore::Params ep;
+    make_store_params(&ep, out, ldo, 0, bias, alpha, relu, out_dtype == SVB_BF16 ? 1 : 0, M, N);
     SVB_GEMM((launch_gemm<256, AMN, BMN, EpiStore>(st, A, lda, B, ldb, M, N, K, 1, ep)), "svb_gemm_bf16");
     return 0;
   }
@@ -348,7 +352,8 @@ int gemm_dispatch(svb_handle* h, cudaStream_t st, const void* A, int64_t lda, co
   SVB_TRY(ensure_arena(h, dry.off));
   h->arena.off = 0; h->arena.dry = false; h->gradbuf = nullptr;
   float* part = h->arena.take<float>(static_cast<size_t>(splits) * MN);
-  EpiStore::Params ep{part, N, static_cast<long long>(MN), nullptr, 1.f, 0, 0};
+  EpiStore::Params ep;
+  make_store_params(&ep, part, N, static_cast<long long>(MN), nullptr, 1.f, 0, 0, M, N);
   int used = 0;
   SVB_GEMM((launch_gemm<256, AMN, BMN, EpiStore>(st, A, lda, B, ldb, M, N, K, splits, ep, &used)), "svb_gemm_bf16");
   (sum_splits_kernel<<<grid_for(MN), 256, 0, st>>>(part, used, MN, alpha, static_cast<float*>(out)), svb::count_launch());

@@ -184,6 +184,18 @@ inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int h
   return 0;
 }
 
+// EpiStore parameters; bf16 outputs with a dense pitch get a TMA store map (rows x cols), others store directly.
+inline int make_store_params(EpiStore::Params* ep, void* out, long long ld, long long split_stride, const float* bias,
+                             float alpha, int relu, int out_bf16, long long rows, long long cols) {
+  memset(ep, 0, sizeof(*ep));
+  ep->out = out; ep->ld = ld; ep->split_stride = split_stride; ep->bias = bias; ep->alpha = alpha; ep->relu = relu;
+  ep->out_bf16 = out_bf16;
+  if (out_bf16 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ld % 8) == 0) {
+    if (make_store_tmap_bf16(&ep->tm, out, rows, cols, ld) == 0) ep->tm_valid = 1;
+  }
+  return 0;
+}
+
 // out[j] = scale * sum_i in[i, j] over R rows with a fixed order; `stage` holds up to 32*N floats.
 inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float scale, float* stage, float* out) {
   int chunks = R >= 256 ? 32 : 1;

@@ -204,6 +204,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
     e2.bias = p->b_dec;
     e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
     e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
+    if (e2.d_bf16 && make_store_tmap_bf16(&e2.tm_d, e2.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map");
     SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
   }
   if (out->via) {
@@ -211,6 +212,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
     e3.bias = p->b_dec;
     e3.d_bf16 = out->via_dtype == SVB_BF16 ? static_cast<bf16*>(out->via) : nullptr;
     e3.d_f32 = out->via_dtype == SVB_F32 ? static_cast<float*>(out->via) : nullptr;
+    if (e3.d_bf16 && make_store_tmap_bf16(&e3.tm_d, e3.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map");
     SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.rp_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e3)), "via");
   }
   return 0;
@@ -238,6 +240,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+  if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))
+    return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
   EpiDec::Params e2v{};
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
@@ -258,9 +262,11 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.block_n = 256;
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiStore::Params e4{pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  EpiStore::Params e4;
+  make_store_params(&e4, pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0, C, F);
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
-  EpiStore::Params e5{pl.P_wg, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  EpiStore::Params e5;
+  make_store_params(&e5, pl.P_wg, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0, F, C);
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
 
   const float s = static_cast<float>(2.0 / (Tg * C));

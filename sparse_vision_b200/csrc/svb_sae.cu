@@ -31,7 +31,7 @@ struct SaePlan {
   bf16 *X, *Web, *Wdb, *E, *DP, *D, *DIFF;
   float *fold, *l1_part, *sq_part, *colsum_part, *stage, *csum, *st, *chan, *var_part, *rowvar, *P_wd, *P_we, *vm,
       *nact_f, *flat;
-  uint32_t* act_bits;
+  uint32_t *act_bits, *mask;
   // flat buffer offsets
   size_t o_gwe, o_gbe, o_gwd, o_gbd, o_sums, o_chansq, o_count, o_max;
   size_t sum_elems, max_elems;
@@ -58,6 +58,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   p.DP = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
+  p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
   p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 4);
   p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
   p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
@@ -185,12 +186,14 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
   e1.pre_f32 = out->pre;
   e1.hw = pl.hw; e1.words = pl.words;
+  if (make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
   SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
   if (out->dec) {
     EpiDec::Params e2{};
     e2.bias = p->b_dec;
     e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
     e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
+    if (e2.d_bf16 && make_store_tmap_bf16(&e2.tm_d, e2.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map for dec output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
   }
   return 0;
@@ -217,12 +220,16 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // G1 encoder
   EpiEnc::Params e1{};
   e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
+  e1.mask_words = pl.mask;
   e1.hw = pl.hw; e1.words = pl.words;
+  if (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
   SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
   prof_mark(h, st, 2);
   // G2 decoder
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+  if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))
+    return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
   prof_mark(h, st, 3);
   // channel statistics
@@ -238,17 +245,20 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
   EpiDPre::Params e3{};
-  e3.e = pl.E; e3.dpre = pl.DP; e3.colsum_partial = pl.colsum_part;
+  e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   e3.block_n = 256;
+  if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
   SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
   prof_mark(h, st, 5);
   // G4 / G5 weight gradients, split-K over tokens
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiStore::Params e4{pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  EpiStore::Params e4;
+  make_store_params(&e4, pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0, C, F);
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
   prof_mark(h, st, 6);
-  EpiStore::Params e5{pl.P_we, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0};
+  EpiStore::Params e5;
+  make_store_params(&e5, pl.P_we, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0, F, C);
   SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
 
   prof_mark(h, st, 7);

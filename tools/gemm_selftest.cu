@@ -38,6 +38,7 @@ struct Case {
   bool a_mn, b_mn;
   int bn;
   int splits;  // 0 = auto, 1 = none
+  bool bf16_out = false;  // bf16 output through the TMA slab store (K must keep |sums| <= 256 so bf16 is exact)
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -60,7 +61,14 @@ static int run(const Case& c) {
   const int splits = planned_splits<BN>(c.M, c.N, c.K, c.splits);
   CK(cudaMalloc(&dC, (size_t)splits * c.M * c.N * 4));
   CK(cudaMemset(dC, 0xFF, (size_t)splits * c.M * c.N * 4));
-  EpiStore::Params ep{dC, c.N, (long long)c.M * c.N, nullptr, 1.0f, 0, 0};
+  EpiStore::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out = dC; ep.ld = c.N; ep.split_stride = (long long)c.M * c.N; ep.alpha = 1.0f;
+  if (c.bf16_out) {
+    ep.out_bf16 = 1;
+    if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
+    else { printf("[%s] store tensor map failed\n", c.name); return 1; }
+  }
   int used = 0;
   int rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
                                                &used);
@@ -78,7 +86,14 @@ static int run(const Case& c) {
       double ref = 0;
       for (int k = 0; k < c.K; ++k) ref += (double)A[(size_t)m * c.K + k] * B[(size_t)n * c.K + k];
       double got = 0;
-      for (int s = 0; s < used; ++s) got += C[((size_t)s * c.M + m) * c.N + n];
+      if (c.bf16_out) {
+        const uint16_t* hb = reinterpret_cast<const uint16_t*>(C.data());
+        uint32_t u = (uint32_t)hb[(size_t)m * c.N + n] << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        got = f;
+      } else
+        for (int s = 0; s < used; ++s) got += C[((size_t)s * c.M + m) * c.N + n];
       double err = fabs(got - ref);
       if (!(err <= 1e-3)) {
         if (bad < 8) printf("  mismatch m=%d n=%d got=%f ref=%f\n", m, n, got, ref);
@@ -120,6 +135,10 @@ static const Case kCases[] = {
     {"mnmn_auto", 256, 2048, 6272, true, true, 256, 0},
     {"mnmn_tail", 200, 264, 1000, true, true, 256, 0},
     {"mnk", 136, 128, 520, true, false, 128, 2},
+    {"kk_bf16_tma", 300, 256, 16, false, false, 256, 1, true},
+    {"kk_bf16_tma_ntail", 200, 200, 24, false, false, 256, 1, true},
+    {"kk_bf16_tma_n96", 130, 96, 16, false, false, 128, 1, true},
+    {"kk_bf16_tma_many", 128 * 300 + 40, 512, 16, false, false, 256, 1, true},
 };
 
 static int perf() {
@@ -134,7 +153,10 @@ static int perf() {
   CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
   CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
   CK(cudaMemset(dbias, 0, N * 4));
-  EpiStore::Params ep{dE, N, 0, dbias, 1.0f, 1, 1};
+  EpiStore::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out = dE; ep.ld = N; ep.bias = dbias; ep.alpha = 1.0f; ep.relu = 1; ep.out_bf16 = 1;
+  if (make_store_tmap_bf16(&ep.tm, dE, M, N, N) == 0) ep.tm_valid = 1;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -156,7 +178,9 @@ static int perf() {
     float* dP;
     const int splits = planned_splits<256>(M2, N2, K2, 0);
     CK(cudaMalloc(&dP, (size_t)splits * M2 * N2 * 4));
-    EpiStore::Params ep2{dP, N2, (long long)M2 * N2, nullptr, 1.0f, 0, 0};
+    EpiStore::Params ep2;
+    memset(&ep2, 0, sizeof(ep2));
+    ep2.out = dP; ep2.ld = N2; ep2.split_stride = (long long)M2 * N2; ep2.alpha = 1.0f;
     for (int it = 0; it < 3; ++it) launch_gemm<256, true, true, EpiStore>(0, dA, M2, dE, N2, M2, N2, K2, 0, ep2);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
