@@ -50,6 +50,14 @@ __device__ __forceinline__ void load_row_f32(const float* src, float (&o)[32], i
   }
 }
 
+__device__ __forceinline__ void lds_row_f32(const float* src, float (&o)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 q = reinterpret_cast<const float4*>(src)[i];
+    o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
+  }
+}
+
 // Sum over the 32 lanes of v[j] for every j with 31 shuffles: lane j returns column j's sum.  Destroys v.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -134,19 +142,38 @@ struct EpiStore {
     int out_bf16;
     int tm_valid;
   };
-  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes;
+  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 2 * 256 * sizeof(float);
   const Params& p;
   SlabWriter slab;
-  __device__ EpiStore(const Params& p_, uint8_t* smem) : p(p_) { slab.init(smem, (threadIdx.x / 32) % 4); }
+  float* cv_base;
+  const float* cv;
+  __device__ EpiStore(const Params& p_, uint8_t* smem)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr) {
+    slab.init(smem, (threadIdx.x / 32) % 4);
+  }
+  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+    if (!p.bias) return false;
+    const float* const src[1] = {p.bias};
+    float* dst = cv_base + parity * 256;
+    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    cv = dst;
+    return true;
+  }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
     const int nvalid = min(32, g.N - col0);
+    if (p.bias) {
+      float b[32];
+      lds_row_f32(cv + (col0 - ti.n0), b);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = v[j] * p.alpha;
-      if (p.bias && j < nvalid) x += __ldg(p.bias + col0 + j);
-      if (p.relu) x = fmaxf(x, 0.f);
-      v[j] = x;
+      for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + b[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (p.out_bf16 && p.tm_valid) {
       const int half = (col0 >> 5) & 1;
@@ -183,12 +210,24 @@ struct EpiEnc {
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
   };
-  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes;
+  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 2 * 256 * sizeof(float);
   const Params& p;
   SlabWriter slab;
+  float* cv_base;
+  const float* cv;
   float sum;
   uint32_t words[8];
-  __device__ EpiEnc(const Params& p_, uint8_t* smem) : p(p_), sum(0.f) { slab.init(smem, (threadIdx.x / 32) % 4); }
+  __device__ EpiEnc(const Params& p_, uint8_t* smem)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr), sum(0.f) {
+    slab.init(smem, (threadIdx.x / 32) % 4);
+  }
+  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+    const float* const src[1] = {p.bias};
+    float* dst = cv_base + parity * 256;
+    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    cv = dst;
+    return true;
+  }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
     sum = 0.f;
 #pragma unroll
@@ -199,7 +238,7 @@ struct EpiEnc {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float b[32];
-    load_row_f32(p.bias + col0, b, nvalid);
+    lds_row_f32(cv + (col0 - ti.n0), b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     const long long off = static_cast<long long>(row) * g.N + col0;
@@ -260,13 +299,23 @@ struct EpiDec {
     __nv_bfloat16* diff_bf16;         // [M,N] or null
     float* sq_partial;                // [tiles_m*tiles_n*4] or null
   };
-  static constexpr uint32_t kSmemBytes = 2 * SlabWriter::kBytes;
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter::kBytes + 2 * 256 * sizeof(float);
   const Params& p;
   SlabWriter slab_d, slab_f;
+  float* cv_base;
+  const float* cv;
   float sq;
-  __device__ EpiDec(const Params& p_, uint8_t* smem) : p(p_), sq(0.f) {
+  __device__ EpiDec(const Params& p_, uint8_t* smem)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter::kBytes)), cv(nullptr), sq(0.f) {
     slab_d.init(smem, (threadIdx.x / 32) % 4);
     slab_f.init(smem + SlabWriter::kBytes, (threadIdx.x / 32) % 4);
+  }
+  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+    const float* const src[1] = {p.bias};
+    float* dst = cv_base + parity * 256;
+    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    cv = dst;
+    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sq = 0.f; }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
@@ -275,20 +324,21 @@ struct EpiDec {
     const bool row_ok = row < g.M;
     const int half = ((col0 - ti.n0) >> 5) & 1;
     float b[32];
-    load_row_f32(p.bias + col0, b, nvalid);
+    const long long off = static_cast<long long>(row) * g.N + col0;
+    float xv[32];
+    if (p.x) load_row_bf16(p.x + (row_ok ? off : 0), xv, row_ok ? nvalid : 0);   // issued early: an L2 round trip
+    lds_row_f32(cv + (col0 - ti.n0), b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
-    const long long off = static_cast<long long>(row) * g.N + col0;
     if (p.d_bf16) {
       slab_d.put(half, lane, v);
       if (half == 1) slab_d.flush(&p.tm_d, col0 - 32, ti.m0 + wq * 32, lane);
     }
     if (p.d_f32 && row_ok) store_row_f32(p.d_f32 + off, v, nvalid);
     if (p.x) {
-      load_row_bf16(p.x + (row_ok ? off : 0), b, row_ok ? nvalid : 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] -= b[j];
+        v[j] -= xv[j];
         if (j < nvalid && row_ok) sq += v[j] * v[j];
       }
       if (p.diff_bf16) {
@@ -334,6 +384,7 @@ struct EpiDPre {
   __device__ EpiDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter::kBytes)) {
     slab.init(smem, (threadIdx.x / 32) % 4);
   }
+  __device__ bool prefetch_tile(const GemmProblem&, const TileInfo&, uint32_t, int) { return false; }
   __device__ void begin_tile(const GemmProblem& g, const TileInfo& ti, int row, int, int) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) words[i] = 0;

@@ -25,10 +25,20 @@ struct EpiGatedEnc {
     float* l1_partial;
     int hw, words;
   };
-  static constexpr uint32_t kSmemBytes = 0;
+  static constexpr uint32_t kSmemBytes = 2 * 4 * 256 * sizeof(float);
   const Params& p;
+  float* cv_base;
+  const float* cv;
   float sum;
-  __device__ EpiGatedEnc(const Params& p_, uint8_t*) : p(p_), sum(0.f) {}
+  __device__ EpiGatedEnc(const Params& p_, uint8_t* smem)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(nullptr), sum(0.f) {}
+  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+    const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
+    float* dst = cv_base + parity * 4 * 256;
+    stage_colvecs<4>(dst, src, ti.n0, g.N, tid);
+    cv = dst;
+    return true;
+  }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
                         int lane) {
@@ -36,12 +46,12 @@ struct EpiGatedEnc {
     const bool row_ok = row < g.M;
     float rp[32];
     uint32_t word = 0;
+    const float* cvt = cv + (col0 - ti.n0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int c = col0 + (j < nvalid ? j : 0);
-      const float raw = v[j] - __ldg(p.dot + c);
-      const float pi = raw + __ldg(p.b_gate + c);
-      const float mag = fmaxf(__ldg(p.exp_r + c) * raw + __ldg(p.b_mag + c), 0.f);
+      const float raw = v[j] - cvt[j];
+      const float pi = raw + cvt[256 + j];
+      const float mag = fmaxf(cvt[768 + j] * raw + cvt[512 + j], 0.f);
       const float gate = pi > 0.f ? 1.f : (pi == 0.f ? 0.5f : 0.f);
       const float e = gate * mag;
       rp[j] = fmaxf(pi, 0.f);
@@ -87,10 +97,21 @@ struct EpiGatedDPre {
     float l1c;
     int block_n;
   };
-  static constexpr uint32_t kSmemBytes = 3 * 4 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = 3 * 4 * 256 * sizeof(float) + 2 * 256 * sizeof(float);
   const Params& p;
   float* s_col;  // [3][4][256]
-  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem)) {}
+  float* cv_base;
+  const float* cv;
+  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem)
+      : p(p_), s_col(reinterpret_cast<float*>(smem)), cv_base(reinterpret_cast<float*>(smem) + 3 * 4 * 256),
+        cv(nullptr) {}
+  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+    const float* const src[1] = {p.exp_r};
+    float* dst = cv_base + parity * 256;
+    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    cv = dst;
+    return true;
+  }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
                         int lane) {
@@ -105,8 +126,7 @@ struct EpiGatedDPre {
     for (int j = 0; j < 32; ++j) {
       const float dmag = e[j] > 0.f ? v[j] : 0.f;
       const float dpi = t[j] > 0.f ? p.l1c : 0.f;
-      const int c = col0 + (j < nvalid ? j : 0);
-      a[j] = dpi + __ldg(p.exp_r + c) * dmag;
+      a[j] = dpi + cv[(col0 - ti.n0) + j] * dmag;
       v[j] = dmag;
       t[j] = dpi;
       e[j] = dmag * e[j];

@@ -55,6 +55,21 @@ struct GemmCfg {
   static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
+// Named barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads).
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Stage NV per-column float vectors for columns [n0, n0+256) into dst[NV][256] (zero beyond N) with the 128 epilogue
+// threads.  dst alternates between two buffers by accumulator stage, so only one barrier per tile is needed: a warp
+// can run at most one tile ahead of the others (the TMEM full/empty handshake), never two.
+template <int NV>
+__device__ __forceinline__ void stage_colvecs(float* dst, const float* const (&src)[NV], int n0, int N, int tid) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int c = tid; c < 256; c += kEpiThreads)
+      dst[v * 256 + c] = (src[v] != nullptr && n0 + c < N) ? __ldg(src[v] + n0 + c) : 0.f;
+}
+
 __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
   TileInfo ti;
   ti.tile_n = t % p.tiles_n;
@@ -187,6 +202,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t, BLOCK_N);
+      // Per-column vectors (biases ...) are staged into shared memory while the MMAs of this tile are still running:
+      // with ~227 KB of dynamic smem there is next to no L1, so a global load in the chunk loop is an L2 round trip.
+      if (epi.prefetch_tile(p, ti, acc, row_in_tile)) epi_bar_sync();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = ti.m0 + row_in_tile;
@@ -216,7 +234,5 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// Named barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads).
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 }  // namespace svb
