@@ -1,5 +1,6 @@
 // Epilogue functors for gemm_bf16_kernel.  An epilogue thread owns ONE accumulator row (a token, or a feature in the
-// weight-gradient GEMMs) and receives it 32 columns at a time.  Rows >= M and columns >= N hold zeros from TMA
+// weight-gradient GEMMs) and receives its warp's share of the columns 32 at a time (8 epilogue warps: warp `ew` owns
+// TMEM lane quarter ew%4... and column half ew/4 of the tile).  Rows >= M and columns >= N hold zeros from TMA
 // out-of-bounds fill, but they must still be masked out of every reduction and store.
 //
 // bf16 outputs on the hot path leave through shared memory: each warp stages 32-row x 64-column slabs (128-byte rows,
@@ -86,21 +87,24 @@ __device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_p
   }
 }
 
-// Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores (two 4 KB buffers).
+// Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores (one 4 KB buffer per
+// epilogue warp; the two warps of an SM sub-partition overlap each other's store waits).
 struct SlabWriter {
-  static constexpr uint32_t kBytesPerWarp = 2 * 4096;
-  static constexpr uint32_t kBytes = 4 * kBytesPerWarp;  // four epilogue warps
+  static constexpr uint32_t kBytesPerWarp = 4096;
+  static constexpr uint32_t kBytes = 8 * kBytesPerWarp;  // eight epilogue warps
   uint8_t* base;
-  uint32_t which;
   bool half_pending;
-  __device__ void init(uint8_t* epi_smem, int wq) {
-    base = epi_smem + wq * kBytesPerWarp;
-    which = 0;
+  __device__ void init(uint8_t* epi_smem, int ew) {
+    base = epi_smem + ew * kBytesPerWarp;
     half_pending = false;
   }
   // columns [half*32, half*32+32) of this lane's row; 16-byte pieces land XOR-swizzled like the tensor map expects
   __device__ void put(int half, int lane, const float (&v)[32]) {
-    uint8_t* row = base + which * 4096 + lane * 128;
+    if (half == 0) {  // the previous slab's store must have finished READING the buffer
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
+    uint8_t* row = base + lane * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = half * 4 + i;
@@ -113,12 +117,9 @@ struct SlabWriter {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tm, base + which * 4096, col0, row0);
+      tma_store_2d(tm, base, col0, row0);
       bulk_commit();
-      bulk_wait_read<1>();  // the OTHER buffer's store has finished reading: it may be overwritten next
     }
-    __syncwarp();
-    which ^= 1;
     half_pending = false;
   }
   __device__ void drain(int lane) {
@@ -127,15 +128,36 @@ struct SlabWriter {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ fp32 partials
+// Split-K slices of the weight-gradient GEMMs: out[split][row][col] = acc (fp32, direct 16-byte stores; the
+// epilogue is a negligible part of these K = T GEMMs, so no staging and a full 4-stage operand ring).
+struct EpiPartial {
+  struct Params {
+    float* out;
+    long long ld;
+    long long split_stride;
+  };
+  static constexpr uint32_t kSmemBytes = 0;
+  const Params& p;
+  __device__ EpiPartial(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ bool prefetch_tile(const GemmProblem&, const TileInfo&, uint32_t, int) { return false; }
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int, int) {
+    if (row >= g.M) return;
+    store_row_f32(p.out + ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0, v,
+                  min(32, g.N - col0));
+  }
+  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void finish(int, int) {}
+};
+
 // ------------------------------------------------------------------------------------------------ plain store
-// out = [relu](alpha*acc + bias), fp32 (direct) or bf16 (TMA slabs when tm_valid); split-K slices land
-// split_stride elements apart.
+// out = [relu](alpha*acc + bias), fp32 (direct) or bf16 (TMA slabs when tm_valid).
 struct EpiStore {
   struct Params {
     alignas(64) CUtensorMap tm;  // bf16 output map (box 64 x 32) when tm_valid
     void* out;
     long long ld;
-    long long split_stride;
     const float* bias;  // [N] or null
     float alpha;
     int relu;
@@ -147,9 +169,9 @@ struct EpiStore {
   SlabWriter slab;
   float* cv_base;
   const float* cv;
-  __device__ EpiStore(const Params& p_, uint8_t* smem)
+  __device__ EpiStore(const Params& p_, uint8_t* smem, int ew, int)
       : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr) {
-    slab.init(smem, (threadIdx.x / 32) % 4);
+    slab.init(smem, ew);
   }
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     if (!p.bias) return false;
@@ -182,7 +204,7 @@ struct EpiStore {
       return;
     }
     if (row >= g.M) return;
-    const long long off = ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0;
+    const long long off = static_cast<long long>(row) * p.ld + col0;
     if (p.out_bf16) store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, nvalid);
     else store_row_f32(reinterpret_cast<float*>(p.out) + off, v, nvalid);
   }
@@ -196,7 +218,7 @@ struct EpiStore {
 // pre = acc + bias';  e = relu(pre)   (sae_mlp.py:49-51 with the pre-bias folded: bias' = b_enc - W_enc b_dec)
 // Fused: bf16 store of e (TMA slabs), optional fp32 stores of e / pre (API forward), per-row activity words
 // (1 bit per element: the ReLU mask the backward needs), per-image activity bits (utils.py:2033-2047) and sum|e|
-// partials (sparse_loss.py:41).
+// partials (sparse_loss.py:41).  All generic-proxy global writes happen once per tile in end_tile.
 struct EpiEnc {
   struct Params {
     alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], box 64 x 32 (valid when e_bf16 != null)
@@ -206,7 +228,7 @@ struct EpiEnc {
     float* pre_f32;                // [M,N] or null
     uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
     uint32_t* act_bits;            // [n_img, words] or null
-    float* l1_partial;             // [tiles_m*tiles_n*4] or null
+    float* l1_partial;             // [tiles_m*tiles_n*8] or null
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
   };
@@ -216,10 +238,12 @@ struct EpiEnc {
   float* cv_base;
   const float* cv;
   float sum;
-  uint32_t words[8];
-  __device__ EpiEnc(const Params& p_, uint8_t* smem)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr), sum(0.f) {
-    slab.init(smem, (threadIdx.x / 32) % 4);
+  uint32_t words[4];
+  int ew, c_first;  // this warp's first 32-column chunk inside the tile
+  __device__ EpiEnc(const Params& p_, uint8_t* smem, int ew_, int block_n)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr), sum(0.f), ew(ew_),
+        c_first((ew_ / 4) * (block_n / 64)) {
+    slab.init(smem, ew_);
   }
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     const float* const src[1] = {p.bias};
@@ -231,7 +255,7 @@ struct EpiEnc {
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
     sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) words[i] = 0;
+    for (int i = 0; i < 4; ++i) words[i] = 0;
   }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
                         int lane) {
@@ -245,16 +269,17 @@ struct EpiEnc {
     if (p.pre_f32 && row_ok) store_row_f32(p.pre_f32 + off, v, nvalid);
     uint32_t word = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float e = fmaxf(v[j], 0.f);
-      v[j] = e;
-      if (e > 0.f && j < nvalid) word |= (1u << j);
-      if (j < nvalid) sum += e;
+    for (int j = 31; j >= 0; --j) {
+      // sign bit of (0 - pre) is set exactly when pre > 0; funnel it into the word MSB-first
+      word = __funnelshift_l(__float_as_uint(0.f - v[j]), word, 1);
+      v[j] = fmaxf(v[j], 0.f);
+      sum += v[j];
     }
+    if (nvalid < 32) word &= (1u << nvalid) - 1u;
     if (!row_ok) word = 0;
-    const int c = (col0 - ti.n0) >> 5;
+    const int c = ((col0 - ti.n0) >> 5) - c_first;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
       if (i == c) words[i] = word;
     if (p.e_bf16) {
       const int half = c & 1;
@@ -262,25 +287,42 @@ struct EpiEnc {
       if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane);
     }
     if (p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
-    if (p.act_bits) publish_activity(p.act_bits, p.words, col0 >> 5, word, row, g.M, p.hw, ti.m0 + wq * 32, lane);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
-    if (p.mask_words && row < g.M) {
-      uint32_t* dst = p.mask_words + static_cast<size_t>(row) * p.words + (ti.n0 >> 5);
-      const int nw = min(8, p.words - (ti.n0 >> 5));
-      if (nw == 8 && (p.words & 3) == 0) {
-        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
-        reinterpret_cast<uint4*>(dst)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+    const int w0 = (ti.n0 >> 5) + c_first;            // first word index of this warp
+    const int nw = max(0, min(4, p.words - w0));
+    if (p.mask_words && row < g.M && nw > 0) {
+      uint32_t* dst = p.mask_words + static_cast<size_t>(row) * p.words + w0;
+      if (nw == 4 && (p.words & 3) == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
           if (i < nw) dst[i] = words[i];
+      }
+    }
+    if (p.act_bits && nw > 0) {
+      // OR the rows of each image this warp touches; lanes 0..3 publish one word each (one RED per segment)
+      const int row0 = ti.m0 + wq * 32;
+      const int last_row = min(row0 + 31, g.M - 1);
+      if (row0 <= last_row) {
+        const int b_first = row0 / p.hw, b_last = last_row / p.hw;
+        const int my_b = row < g.M ? row / p.hw : -1;
+        for (int b = b_first; b <= b_last; ++b) {
+          uint32_t mine = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? words[i] : 0u);
+            if (lane == i) mine = ored;
+          }
+          if (lane < nw && mine) atomicOr(&p.act_bits[static_cast<size_t>(b) * p.words + w0 + lane], mine);
+        }
       }
     }
     if (p.l1_partial) {
       const float s = warp_sum(row < g.M ? sum : 0.f);
-      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
     }
   }
   __device__ void finish(int, int lane) { slab.drain(lane); }
@@ -297,7 +339,7 @@ struct EpiDec {
     __nv_bfloat16* d_bf16;            // [M,N] or null
     float* d_f32;                     // [M,N] or null
     __nv_bfloat16* diff_bf16;         // [M,N] or null
-    float* sq_partial;                // [tiles_m*tiles_n*4] or null
+    float* sq_partial;                // [tiles_m*tiles_n*8] or null
   };
   static constexpr uint32_t kSmemBytes = 2 * SlabWriter::kBytes + 2 * 256 * sizeof(float);
   const Params& p;
@@ -305,10 +347,11 @@ struct EpiDec {
   float* cv_base;
   const float* cv;
   float sq;
-  __device__ EpiDec(const Params& p_, uint8_t* smem)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter::kBytes)), cv(nullptr), sq(0.f) {
-    slab_d.init(smem, (threadIdx.x / 32) % 4);
-    slab_f.init(smem + SlabWriter::kBytes, (threadIdx.x / 32) % 4);
+  int ew;
+  __device__ EpiDec(const Params& p_, uint8_t* smem, int ew_, int)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter::kBytes)), cv(nullptr), sq(0.f), ew(ew_) {
+    slab_d.init(smem, ew_);
+    slab_f.init(smem + SlabWriter::kBytes, ew_);
   }
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     const float* const src[1] = {p.bias};
@@ -353,19 +396,17 @@ struct EpiDec {
     if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane);
     if (p.sq_partial) {
       const float s = warp_sum(sq);
-      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
     }
   }
-  __device__ void finish(int, int lane) {
-    slab_d.drain(lane);
-  }
+  __device__ void finish(int, int lane) { slab_d.drain(lane); }
 };
 
 // ------------------------------------------------------------------------------------------------ dE -> dPre
 // acc = diff * W_dec  (unscaled dE);  dPre' = 1[e>0] * (acc + l1c)  with l1c = lambda*C/(2F), i.e. the whole
 // backward is carried in units of T*C/2 and rescaled once in the gradient reduction (model_pipeline.py:385 autograd
 // of sparse_loss.py:35,41 through sae_mlp.py:51).  The ReLU mask comes from the encoder's 1-bit activity words
-// (32 B per row and tile instead of re-reading 512 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
+// (16 B per row and warp instead of re-reading 256 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
 // column sums (-> db_enc).
 struct EpiDPre {
   struct Params {
@@ -374,40 +415,41 @@ struct EpiDPre {
     float* colsum_partial;             // [tiles_m, N]
     float l1c;
     int words;
-    int block_n;                       // BLOCK_N of the launching GEMM
   };
   static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 4 * 256 * sizeof(float);
   const Params& p;
   SlabWriter slab;
-  float* s_col;  // [4][256]
-  uint32_t words[8];
-  __device__ EpiDPre(const Params& p_, uint8_t* smem) : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter::kBytes)) {
-    slab.init(smem, (threadIdx.x / 32) % 4);
+  float* s_col;  // [4 lane quarters][256 columns]
+  uint32_t words[4];
+  int ew, c_first, block_n;
+  __device__ EpiDPre(const Params& p_, uint8_t* smem, int ew_, int block_n_)
+      : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), ew(ew_),
+        c_first((ew_ / 4) * (block_n_ / 64)), block_n(block_n_) {
+    slab.init(smem, ew_);
   }
   __device__ bool prefetch_tile(const GemmProblem&, const TileInfo&, uint32_t, int) { return false; }
   __device__ void begin_tile(const GemmProblem& g, const TileInfo& ti, int row, int, int) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) words[i] = 0;
-    if (row < g.M) {
-      const uint32_t* src = p.mask_words + static_cast<size_t>(row) * p.words + (ti.n0 >> 5);
-      const int nw = min(8, p.words - (ti.n0 >> 5));
-      if (nw == 8 && (p.words & 3) == 0) {
+    for (int i = 0; i < 4; ++i) words[i] = 0;
+    const int w0 = (ti.n0 >> 5) + c_first;
+    const int nw = max(0, min(4, p.words - w0));
+    if (row < g.M && nw > 0) {
+      const uint32_t* src = p.mask_words + static_cast<size_t>(row) * p.words + w0;
+      if (nw == 4 && (p.words & 3) == 0) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
         words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
-        words[4] = b.x; words[5] = b.y; words[6] = b.z; words[7] = b.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
           if (i < nw) words[i] = __ldg(src + i);
       }
     }
   }
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
-    const int c = (col0 - ti.n0) >> 5;
+  __device__ void chunk(const GemmProblem&, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
+    const int c = ((col0 - ti.n0) >> 5) - c_first;
     uint32_t word = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
       if (i == c) word = words[i];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] + p.l1c : 0.f;
@@ -420,14 +462,11 @@ struct EpiDPre {
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
     epi_bar_sync();
-    const int t = wq * 32 + lane;
-#pragma unroll
-    for (int c = t; c < 256; c += 128) {
-      const int col = ti.n0 + c;
-      if (c < p.block_n && col < g.N) {
-        const float s = (s_col[c] + s_col[256 + c]) + (s_col[512 + c] + s_col[768 + c]);
-        p.colsum_partial[static_cast<size_t>(ti.tile_m) * g.N + col] = s;
-      }
+    const int c = ew * 32 + lane;  // 256 epilogue threads, one column each
+    const int col = ti.n0 + c;
+    if (c < block_n && col < g.N) {
+      const float s = (s_col[c] + s_col[256 + c]) + (s_col[512 + c] + s_col[768 + c]);
+      p.colsum_partial[static_cast<size_t>(ti.tile_m) * g.N + col] = s;
     }
     epi_bar_sync();
   }

@@ -30,8 +30,9 @@ struct EpiGatedEnc {
   float* cv_base;
   const float* cv;
   float sum;
-  __device__ EpiGatedEnc(const Params& p_, uint8_t* smem)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(nullptr), sum(0.f) {}
+  int ew;
+  __device__ EpiGatedEnc(const Params& p_, uint8_t* smem, int ew_, int)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(nullptr), sum(0.f), ew(ew_) {}
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
     float* dst = cv_base + parity * 4 * 256;
@@ -74,7 +75,7 @@ struct EpiGatedEnc {
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
     if (!p.l1_partial) return;
     const float s = warp_sum(row < g.M ? sum : 0.f);
-    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 4 + wq] = s;
+    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
   }
   __device__ void finish(int, int) {}
 };
@@ -102,9 +103,10 @@ struct EpiGatedDPre {
   float* s_col;  // [3][4][256]
   float* cv_base;
   const float* cv;
-  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem)
+  int ew;
+  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem, int ew_, int)
       : p(p_), s_col(reinterpret_cast<float*>(smem)), cv_base(reinterpret_cast<float*>(smem) + 3 * 4 * 256),
-        cv(nullptr) {}
+        cv(nullptr), ew(ew_) {}
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     const float* const src[1] = {p.exp_r};
     float* dst = cv_base + parity * 256;
@@ -139,15 +141,14 @@ struct EpiGatedDPre {
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     epi_bar_sync();
-    const int t = wq * 32 + lane;
+    const int c = ew * 32 + lane;  // 256 epilogue threads, one column each
+    const int col = ti.n0 + c;
     float* outs[3] = {p.colsum_mag, p.colsum_pi, p.colsum_mage};
+    if (c < p.block_n && col < g.N) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float* s = s_col + q * 4 * 256;
-      for (int c = t; c < 256; c += 128) {
-        const int col = ti.n0 + c;
-        if (c < p.block_n && col < g.N)
-          outs[q][static_cast<size_t>(ti.tile_m) * g.N + col] = (s[c] + s[256 + c]) + (s[512 + c] + s[768 + c]);
+      for (int q = 0; q < 3; ++q) {
+        const float* s = s_col + q * 4 * 256;
+        outs[q][static_cast<size_t>(ti.tile_m) * g.N + col] = (s[c] + s[256 + c]) + (s[512 + c] + s[768 + c]);
       }
     }
     epi_bar_sync();

@@ -2,7 +2,10 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer    (one thread issues tcgen05.mma, tcgen05.commit frees smem slots / publishes TMEM)
-//   warps 2..5  : epilogue      (tcgen05.ld TMEM -> registers -> Epi functor -> global)
+//   warps 2..9  : epilogue      (tcgen05.ld TMEM -> registers -> Epi functor -> global).  Eight warps, two per SM
+//                 sub-partition: warps w and w+4 share a TMEM lane quarter and split the tile's columns, because
+//                 one warp per sub-partition cannot issue the per-element epilogue work of a K=256 tile (bias, ReLU,
+//                 mask, sums, bf16 pack) inside its 2048 MMA cycles.
 //
 // Either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers every GEMM of
 // the SAE step on row-major token tensors without a transpose copy:
@@ -21,8 +24,8 @@ namespace svb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiThreads = 256;
 
 struct GemmProblem {
   int M, N, K;
@@ -55,10 +58,10 @@ struct GemmCfg {
   static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
-// Named barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads).
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Named barrier among the 256 epilogue threads only (id 1; id 0 is __syncthreads).
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// Stage NV per-column float vectors for columns [n0, n0+256) into dst[NV][256] (zero beyond N) with the 128 epilogue
+// Stage NV per-column float vectors for columns [n0, n0+256) into dst[NV][256] (zero beyond N) with the 256 epilogue
 // threads.  dst alternates between two buffers by accumulator stage, so only one barrier per tile is needed: a warp
 // can run at most one tile ahead of the others (the TMEM full/empty handshake), never two.
 template <int NV>
@@ -195,23 +198,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
+    const int ew = warp - 2;  // 0..7
     const int wq = warp % 4;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int chalf = ew / 4;
     const int row_in_tile = wq * 32 + lane;
-    Epi epi(ep, epi_smem);
+    const int tid = ew * 32 + lane;
+    constexpr int kChunksPerWarp = BLOCK_N / 64;
+    Epi epi(ep, epi_smem, ew, BLOCK_N);
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t, BLOCK_N);
       // Per-column vectors (biases ...) are staged into shared memory while the MMAs of this tile are still running:
       // with ~227 KB of dynamic smem there is next to no L1, so a global load in the chunk loop is an L2 round trip.
-      if (epi.prefetch_tile(p, ti, acc, row_in_tile)) epi_bar_sync();
+      if (epi.prefetch_tile(p, ti, acc, tid)) epi_bar_sync();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = ti.m0 + row_in_tile;
       epi.begin_tile(p, ti, row, wq, lane);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = chalf * kChunksPerWarp; c < (chalf + 1) * kChunksPerWarp; ++c) {
         const int col0 = ti.n0 + c * 32;
         if (col0 >= p.N) break;
         float v[32];

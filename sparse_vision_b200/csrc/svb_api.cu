@@ -319,7 +319,7 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, E, F, Wdb, F, Ti, C, F, 1, e2)), "dec");
   // enc.grad = g W_dec   (nnsight_intervention_check.py:194-195)
   EpiStore::Params e3;
-  make_store_params(&e3, GE, F, 0, nullptr, 1.f, 0, 1, Ti, F);
+  make_store_params(&e3, GE, F, nullptr, 1.f, 0, 1, Ti, F);
   SVB_GEMM((launch_gemm<256, false, true, EpiStore>(st, Gp, C, Wdb, F, Ti, F, C, 1, e3)), "g W_dec");
   if (ie_features)
     SVB_TRY(launch_ie_channelwise<bf16>(st, h->sms, E, GE, avgT_f, T, HW, F, scale, partial, chunks_f, stage, ie_features));
@@ -342,7 +342,7 @@ int gemm_dispatch(svb_handle* h, cudaStream_t st, const void* A, int64_t lda, co
   const int splits = can_split ? planned_splits<256>(M, N, K, 0) : 1;
   if (splits <= 1) {
     EpiStore::Params ep;
-    make_store_params(&ep, out, ldo, 0, bias, alpha, relu, out_dtype == SVB_BF16 ? 1 : 0, M, N);
+    make_store_params(&ep, out, ldo, bias, alpha, relu, out_dtype == SVB_BF16 ? 1 : 0, M, N);
     SVB_GEMM((launch_gemm<256, AMN, BMN, EpiStore>(st, A, lda, B, ldb, M, N, K, 1, ep)), "svb_gemm_bf16");
     return 0;
   }
@@ -352,10 +352,9 @@ int gemm_dispatch(svb_handle* h, cudaStream_t st, const void* A, int64_t lda, co
   SVB_TRY(ensure_arena(h, dry.off));
   h->arena.off = 0; h->arena.dry = false; h->gradbuf = nullptr;
   float* part = h->arena.take<float>(static_cast<size_t>(splits) * MN);
-  EpiStore::Params ep;
-  make_store_params(&ep, part, N, static_cast<long long>(MN), nullptr, 1.f, 0, 0, M, N);
+  EpiPartial::Params ep{part, N, static_cast<long long>(MN)};
   int used = 0;
-  SVB_GEMM((launch_gemm<256, AMN, BMN, EpiStore>(st, A, lda, B, ldb, M, N, K, splits, ep, &used)), "svb_gemm_bf16");
+  SVB_GEMM((launch_gemm<256, AMN, BMN, EpiPartial>(st, A, lda, B, ldb, M, N, K, splits, ep, &used)), "svb_gemm_bf16");
   (sum_splits_kernel<<<grid_for(MN), 256, 0, st>>>(part, used, MN, alpha, static_cast<float*>(out)), svb::count_launch());
   SVB_LAUNCH_CHECK("sum_splits");
   return 0;

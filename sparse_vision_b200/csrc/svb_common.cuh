@@ -185,10 +185,10 @@ inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int h
 }
 
 // EpiStore parameters; bf16 outputs with a dense pitch get a TMA store map (rows x cols), others store directly.
-inline int make_store_params(EpiStore::Params* ep, void* out, long long ld, long long split_stride, const float* bias,
-                             float alpha, int relu, int out_bf16, long long rows, long long cols) {
+inline int make_store_params(EpiStore::Params* ep, void* out, long long ld, const float* bias, float alpha, int relu,
+                             int out_bf16, long long rows, long long cols) {
   memset(ep, 0, sizeof(*ep));
-  ep->out = out; ep->ld = ld; ep->split_stride = split_stride; ep->bias = bias; ep->alpha = alpha; ep->relu = relu;
+  ep->out = out; ep->ld = ld; ep->bias = bias; ep->alpha = alpha; ep->relu = relu;
   ep->out_bf16 = out_bf16;
   if (out_bf16 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ld % 8) == 0) {
     if (make_store_tmap_bf16(&ep->tm, out, rows, cols, ld) == 0) ep->tm_valid = 1;

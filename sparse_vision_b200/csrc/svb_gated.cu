@@ -43,9 +43,9 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
   p.A = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 4);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
-  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 8);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
+  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
   p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_pi = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_mage = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
@@ -262,12 +262,10 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.block_n = 256;
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiStore::Params e4;
-  make_store_params(&e4, pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0, C, F);
-  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
-  EpiStore::Params e5;
-  make_store_params(&e5, pl.P_wg, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0, F, C);
-  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
 
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
@@ -280,9 +278,9 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg), svb::count_launch());
   (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm), svb::count_launch());
   (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 2), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 2), svb::count_launch());
   (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                              pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());

@@ -59,8 +59,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   p.DIFF = a.take<bf16>(TC);
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
   p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 4);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 4);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 8);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
   p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
@@ -247,19 +247,16 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   EpiDPre::Params e3{};
   e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
-  e3.block_n = 256;
   if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
   SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
   prof_mark(h, st, 5);
   // G4 / G5 weight gradients, split-K over tokens
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiStore::Params e4;
-  make_store_params(&e4, pl.P_wd, F, static_cast<long long>(FC), nullptr, 1.f, 0, 0, C, F);
-  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
   prof_mark(h, st, 6);
-  EpiStore::Params e5;
-  make_store_params(&e5, pl.P_we, C, static_cast<long long>(FC), nullptr, 1.f, 0, 0, F, C);
-  SVB_GEMM((launch_gemm<256, true, true, EpiStore>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
+  EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
 
   prof_mark(h, st, 7);
   // gradient assembly
@@ -272,8 +269,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
   (sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe), svb::count_launch());  // gb_enc = s * csum
   // loss partial sums
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 4, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 4, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
   (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                        pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);

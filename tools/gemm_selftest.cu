@@ -61,17 +61,20 @@ static int run(const Case& c) {
   const int splits = planned_splits<BN>(c.M, c.N, c.K, c.splits);
   CK(cudaMalloc(&dC, (size_t)splits * c.M * c.N * 4));
   CK(cudaMemset(dC, 0xFF, (size_t)splits * c.M * c.N * 4));
-  EpiStore::Params ep;
-  memset(&ep, 0, sizeof(ep));
-  ep.out = dC; ep.ld = c.N; ep.split_stride = (long long)c.M * c.N; ep.alpha = 1.0f;
+  int used = 0;
+  int rc;
   if (c.bf16_out) {
-    ep.out_bf16 = 1;
+    EpiStore::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = dC; ep.ld = c.N; ep.alpha = 1.0f; ep.out_bf16 = 1;
     if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
     else { printf("[%s] store tensor map failed\n", c.name); return 1; }
-  }
-  int used = 0;
-  int rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
+    rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+  } else {
+    EpiPartial::Params ep{dC, c.N, (long long)c.M * c.N};
+    rc = launch_gemm<BN, AMN, BMN, EpiPartial>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
                                                &used);
+  }
   if (rc) {
     printf("[%s] launch failed rc=%d\n", c.name, rc);
     return 1;
@@ -178,18 +181,60 @@ static int perf() {
     float* dP;
     const int splits = planned_splits<256>(M2, N2, K2, 0);
     CK(cudaMalloc(&dP, (size_t)splits * M2 * N2 * 4));
-    EpiStore::Params ep2;
-    memset(&ep2, 0, sizeof(ep2));
-    ep2.out = dP; ep2.ld = N2; ep2.split_stride = (long long)M2 * N2; ep2.alpha = 1.0f;
-    for (int it = 0; it < 3; ++it) launch_gemm<256, true, true, EpiStore>(0, dA, M2, dE, N2, M2, N2, K2, 0, ep2);
+    EpiPartial::Params ep2{dP, N2, (long long)M2 * N2};
+    for (int it = 0; it < 3; ++it) launch_gemm<256, true, true, EpiPartial>(0, dA, M2, dE, N2, M2, N2, K2, 0, ep2);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    for (int it = 0; it < iters; ++it) launch_gemm<256, true, true, EpiStore>(0, dA, M2, dE, N2, M2, N2, K2, 0, ep2);
+    for (int it = 0; it < iters; ++it) launch_gemm<256, true, true, EpiPartial>(0, dA, M2, dE, N2, M2, N2, K2, 0, ep2);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
     printf("[perf dWdec splits=%d] %.3f ms  %.1f TFLOP/s\n", splits, ms, 2.0 * M2 * N2 * K2 / ms * 1e-9);
+  }
+  return 0;
+}
+
+// EpiEnc feature toggles: which fused output costs what (cfg2 shape)
+static int perf_enc_variants() {
+  const int M = 200704, N = 2048, K = 256, HW = 784, words = N / 32;
+  void *dA, *dB, *dE;
+  float *dbias, *dl1;
+  uint32_t *dact, *dmask;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dE, (size_t)M * N * 2));
+  CK(cudaMalloc(&dbias, N * 4));
+  CK(cudaMalloc(&dl1, (size_t)(M / 128 + 1) * (N / 256) * 8 * 4));
+  CK(cudaMalloc(&dact, (size_t)(M / HW) * words * 4));
+  CK(cudaMalloc(&dmask, (size_t)M * words * 4));
+  CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
+  CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
+  CK(cudaMemset(dbias, 0, N * 4));
+  CK(cudaMemset(dact, 0, (size_t)(M / HW) * words * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int variant = 0; variant < 5; ++variant) {
+    EpiEnc::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.hw = HW; ep.words = words;
+    make_store_tmap_bf16(&ep.tm_e, dE, M, N, N);
+    if (variant == 1 || variant == 4) ep.act_bits = dact;
+    if (variant == 2 || variant == 4) ep.mask_words = dmask;
+    if (variant == 3 || variant == 4) ep.l1_partial = dl1;
+    for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiEnc>(0, dA, K, dB, K, M, N, K, 1, ep);
+    CK(cudaDeviceSynchronize());
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int it = 0; it < iters; ++it) launch_gemm<256, false, false, EpiEnc>(0, dA, K, dB, K, M, N, K, 1, ep);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    printf("[perf EpiEnc variant %d: act=%d mask=%d l1=%d] %.3f ms  %.1f TFLOP/s\n", variant, ep.act_bits != nullptr,
+           ep.mask_words != nullptr, ep.l1_partial != nullptr, ms, 2.0 * M * N * K / ms * 1e-9);
   }
   return 0;
 }
@@ -200,6 +245,7 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (std::string(argv[1]) == "perf") return perf();
+  if (std::string(argv[1]) == "perf_enc") return perf_enc_variants();
   const int i = atoi(argv[1]);
   if (i < 0 || i >= (int)(sizeof(kCases) / sizeof(kCases[0]))) return 3;
   return dispatch(kCases[i]);
