@@ -71,6 +71,61 @@ static __global__ void unpack_tokens_to_nchw_kernel(const TIn* __restrict__ tok,
   }
 }
 
+// Fast paths for HW % 8 == 0 and C % 8 == 0: 64 x 64 tiles, 16-byte global accesses on both sides, bf16 staged in
+// shared memory with a 2-element row pad (conflict-free column gathers).
+// NCHW bf16 [B,C,HW] -> tokens [B*HW, C] bf16.    grid (ceil(HW/64), ceil(C/64), B), 256 threads.
+static __global__ void __launch_bounds__(256)
+pack_nchw_bf16_fast_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
+  __shared__ uint16_t tile[64][66];  // [c][hw]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int c = i >> 3, po = (i & 7) * 8;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (c0 + c < C && p0 + po < HW) q = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(c0 + c) * HW + p0 + po));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[c][po]);
+    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+  }
+  __syncthreads();
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out) + static_cast<size_t>(b) * HW * C;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int p = i >> 3, co = (i & 7) * 8;
+    if (p0 + p < HW && c0 + co < C) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = static_cast<uint32_t>(tile[co + 2 * k][p]) | (static_cast<uint32_t>(tile[co + 2 * k + 1][p]) << 16);
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(p0 + p) * C + c0 + co) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+// tokens [B*HW, C] bf16 -> NCHW bf16 [B,C,HW].
+static __global__ void __launch_bounds__(256)
+unpack_tokens_bf16_fast_kernel(const bf16* __restrict__ tok, bf16* __restrict__ out, int C, int HW) {
+  __shared__ uint16_t tile[64][66];  // [hw][c]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const uint16_t* tb = reinterpret_cast<const uint16_t*>(tok) + static_cast<size_t>(b) * HW * C;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int p = i >> 3, co = (i & 7) * 8;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (p0 + p < HW && c0 + co < C) q = __ldg(reinterpret_cast<const uint4*>(tb + static_cast<size_t>(p0 + p) * C + c0 + co));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[p][co]);
+    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+  }
+  __syncthreads();
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out) + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int c = i >> 3, po = (i & 7) * 8;
+    if (c0 + c < C && p0 + po < HW) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = static_cast<uint32_t>(tile[po + 2 * k][c]) | (static_cast<uint32_t>(tile[po + 2 * k + 1][c]) << 16);
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(c0 + c) * HW + p0 + po) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 static __global__ void convert_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -141,16 +196,20 @@ static __global__ void reduce_flat_kernel(const float* __restrict__ in, size_t n
 }
 
 // ------------------------------------------------------------------------------------------------ channel stats
-// Per image b and channel c over the image's HW tokens (token-major bf16 inputs):
-//   st[b][0][c] = sum x, [1] = sum x^2, [2] = sum d, [3] = sum d^2, [4] = sum diff, [5] = sum diff^2,
-//   [6] = min x, [7] = max x.      grid (B, ceil(C/256)), 256 threads: warp w takes rows w, w+8, ...
-// Feeds variance_explained (utils.py:2012-2030), compute_rmse_nrmse (sparse_loss.py:4-21) and db_dec.
-static __global__ void channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d,
-                                     const bf16* __restrict__ diff, float* __restrict__ st, int C, int HW) {
+// Per image b, row chunk r and channel c over the chunk's tokens (token-major bf16 inputs):
+//   st[b][r][0][c] = sum x, [1] = sum x^2, [2] = sum d, [3] = sum d^2, [4] = sum diff, [5] = sum diff^2,
+//   [6] = min x, [7] = max x          (diff = d - x when no diff tensor is given)
+// grid (n_img, row_chunks, ceil(C/256)), 256 threads: lane owns 8 channels (one 16-byte load), warp w takes rows
+// w, w+8, ... of the chunk.  Feeds variance_explained (utils.py:2012-2030), compute_rmse_nrmse
+// (sparse_loss.py:4-21) and db_dec.
+static __global__ void __launch_bounds__(256)
+channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, const bf16* __restrict__ diff,
+                     float* __restrict__ st, int C, int HW, int rows_per_chunk) {
   __shared__ float s[8][8][33];  // [warp][stat][lane]  (one channel-of-8 at a time)
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, rc = blockIdx.y, R = gridDim.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * 256 + lane * 8;
+  const int c0 = blockIdx.z * 256 + lane * 8;
+  const int r_begin = rc * rows_per_chunk, r_end = min(HW, r_begin + rows_per_chunk);
   float a[8][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -160,18 +219,20 @@ static __global__ void channel_stats_kernel(const bf16* __restrict__ x, const bf
     a[7][k] = -INFINITY;
   }
   if (c0 < C) {
-    for (int r = w; r < HW; r += 8) {
+#pragma unroll 2
+    for (int r = r_begin + w; r < r_end; r += 8) {
       const size_t off = (static_cast<size_t>(b) * HW + r) * C + c0;
       const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x + off));
       const uint4 qd = d ? __ldg(reinterpret_cast<const uint4*>(d + off)) : make_uint4(0, 0, 0, 0);
-      const uint4 qf = diff ? __ldg(reinterpret_cast<const uint4*>(diff + off)) : make_uint4(0, 0, 0, 0);
+      uint4 qf = make_uint4(0, 0, 0, 0);
+      if (diff) qf = __ldg(reinterpret_cast<const uint4*>(diff + off));
       const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w},
                      wf[4] = {qf.x, qf.y, qf.z, qf.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0 = bf16lo(wx[k]), x1 = bf16hi(wx[k]);
         const float d0 = bf16lo(wd[k]), d1 = bf16hi(wd[k]);
-        const float f0 = bf16lo(wf[k]), f1 = bf16hi(wf[k]);
+        const float f0 = diff ? bf16lo(wf[k]) : d0 - x0, f1 = diff ? bf16hi(wf[k]) : d1 - x1;
         a[0][2 * k] += x0; a[0][2 * k + 1] += x1;
         a[1][2 * k] += x0 * x0; a[1][2 * k + 1] += x1 * x1;
         a[2][2 * k] += d0; a[2][2 * k + 1] += d1;
@@ -197,56 +258,64 @@ static __global__ void channel_stats_kernel(const bf16* __restrict__ x, const bf
           const float o = s[ww][q][lane];
           t = q < 6 ? t + o : (q == 6 ? fminf(t, o) : fmaxf(t, o));
         }
-        st[(static_cast<size_t>(b) * 8 + q) * C + c0 + k] = t;
+        st[((static_cast<size_t>(b) * R + rc) * 8 + q) * C + c0 + k] = t;
       }
     }
   }
 }
 
-// Collapse [B][8][C] image stats into: chan[0][c] = sum_b sum diff, chan[1][c] = sum_b sum diff^2,
-// chan[2][c] = min x, chan[3][c] = max x;  var[0] += sum_{b,c} Var_hw(x), var[1] += sum_{b,c} Var_hw(d)
-// (unbiased, utils.py:2015,2020).  One block per 32 channels, 8 image lanes; fixed order.
-static __global__ void channel_stats_finalize_kernel(const float* __restrict__ st, float* __restrict__ chan,
-                                              float* __restrict__ var_partial /* [gridDim.x][2] */, int B, int C,
-                                              int HW) {
-  __shared__ float s[8][6][33];
-  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+// Collapse [B][R][8][C] chunk stats into: chan[0][c] = sum diff, chan[1][c] = sum diff^2, chan[2][c] = min x,
+// chan[3][c] = max x;  var_partial[blk] = (sum_{b,c in blk} Var_hw(x), Var_hw(d))  (unbiased, utils.py:2015,2020).
+// One block per 8 channels: 8 channel lanes x 32 image lanes; chunks and images combined in a fixed order.
+static __global__ void __launch_bounds__(256)
+channel_stats_finalize_kernel(const float* __restrict__ st, float* __restrict__ chan,
+                              float* __restrict__ var_partial /* [gridDim.x][2] */, int B, int R, int C, int HW) {
+  __shared__ float s[6][8][33];
+  const int cl = threadIdx.x & 7, bl = threadIdx.x >> 3;  // channel lane, image lane
+  const int c = blockIdx.x * 8 + cl;
   float sd = 0.f, sd2 = 0.f, mn = INFINITY, mx = -INFINITY, vx = 0.f, vd = 0.f;
   if (c < C) {
     const float inv = 1.f / static_cast<float>(HW), invm1 = HW > 1 ? 1.f / static_cast<float>(HW - 1) : 0.f;
-    for (int b = g; b < B; b += 8) {
-      const float* p = st + static_cast<size_t>(b) * 8 * C + c;
-      const float sx = p[0], sx2 = p[C], sdd = p[2 * C], sdd2 = p[3 * C];
-      sd += p[4 * C];
-      sd2 += p[5 * C];
-      mn = fminf(mn, p[6 * C]);
-      mx = fmaxf(mx, p[7 * C]);
+    for (int b = bl; b < B; b += 32) {
+      float sx = 0.f, sx2 = 0.f, sdd = 0.f, sdd2 = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const float* p = st + (static_cast<size_t>(b) * R + r) * 8 * C + c;
+        sx += p[0]; sx2 += p[C]; sdd += p[2 * C]; sdd2 += p[3 * C];
+        sd += p[4 * C];
+        sd2 += p[5 * C];
+        mn = fminf(mn, p[6 * C]);
+        mx = fmaxf(mx, p[7 * C]);
+      }
       vx += fmaxf(sx2 - sx * sx * inv, 0.f) * invm1;
       vd += fmaxf(sdd2 - sdd * sdd * inv, 0.f) * invm1;
     }
   }
-  s[g][0][lane] = sd; s[g][1][lane] = sd2; s[g][2][lane] = mn; s[g][3][lane] = mx; s[g][4][lane] = vx; s[g][5][lane] = vd;
+  s[0][cl][bl] = sd; s[1][cl][bl] = sd2; s[2][cl][bl] = mn; s[3][cl][bl] = mx; s[4][cl][bl] = vx; s[5][cl][bl] = vd;
   __syncthreads();
-  if (g == 0) {
+  if (bl == 0) {
     float t[6];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) t[q] = s[0][q][lane];
-    for (int k = 1; k < 8; ++k) {
-      t[0] += s[k][0][lane]; t[1] += s[k][1][lane];
-      t[2] = fminf(t[2], s[k][2][lane]); t[3] = fmaxf(t[3], s[k][3][lane]);
-      t[4] += s[k][4][lane]; t[5] += s[k][5][lane];
+    for (int q = 0; q < 6; ++q) t[q] = s[q][cl][0];
+    for (int k = 1; k < 32; ++k) {
+      t[0] += s[0][cl][k]; t[1] += s[1][cl][k];
+      t[2] = fminf(t[2], s[2][cl][k]); t[3] = fmaxf(t[3], s[3][cl][k]);
+      t[4] += s[4][cl][k]; t[5] += s[5][cl][k];
     }
     if (c < C) {
       chan[c] = t[0]; chan[C + c] = t[1]; chan[2 * C + c] = t[2]; chan[3 * C + c] = t[3];
     } else {
       t[4] = 0.f; t[5] = 0.f;
     }
-    const float a = warp_sum(t[4]), bb = warp_sum(t[5]);
-    if (lane == 0) {
-      var_partial[blockIdx.x * 2] = a;
-      var_partial[blockIdx.x * 2 + 1] = bb;
-    }
+    // threads 0..7 (bl == 0) hold the block's 8 channels: fixed-order sum
+    s[4][cl][0] = t[4];
+    s[5][cl][0] = t[5];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bb = 0.f;
+    for (int k = 0; k < 8; ++k) { a += s[4][k][0]; bb += s[5][k][0]; }
+    var_partial[blockIdx.x * 2] = a;
+    var_partial[blockIdx.x * 2 + 1] = bb;
   }
 }
 

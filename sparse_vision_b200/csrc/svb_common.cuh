@@ -159,6 +159,8 @@ inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
     if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
     if (x->dtype == SVB_F32)
       (pack_nchw_to_tokens_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x->x), buf, x->C, x->hw), svb::count_launch());
+    else if (x->hw % 8 == 0 && (reinterpret_cast<uintptr_t>(x->x) & 15) == 0)
+      (pack_nchw_bf16_fast_kernel<<<dim3(cdiv(x->hw, 64), cdiv(x->C, 64), static_cast<unsigned>(x->n_images)), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw), svb::count_launch());
     else
       (pack_nchw_to_tokens_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw), svb::count_launch());
   }
@@ -177,6 +179,8 @@ inline int unpack_to(cudaStream_t st, const bf16* tok, long long n_images, int h
     dim3 block(32, 8);
     if (out_dtype == SVB_F32)
       (unpack_tokens_to_nchw_kernel<bf16, float><<<grid, block, 0, st>>>(tok, static_cast<float*>(out), C, hw), svb::count_launch());
+    else if (hw % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+      (unpack_tokens_bf16_fast_kernel<<<dim3(cdiv(hw, 64), cdiv(C, 64), static_cast<unsigned>(n_images)), 256, 0, st>>>(tok, static_cast<bf16*>(out), C, hw), svb::count_launch());
     else
       (unpack_tokens_to_nchw_kernel<bf16, bf16><<<grid, block, 0, st>>>(tok, static_cast<bf16*>(out), C, hw), svb::count_launch());
   }
@@ -206,6 +210,24 @@ inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float sca
     (reduce_rows_kernel<<<dim3(cdiv(N, 32), 1), 256, 0, st>>>(in, out, R, N, static_cast<size_t>(N), scale), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("reduce_rows");
+  return 0;
+}
+
+// Channel statistics of one batch (see channel_stats_kernel).  st holds stats_elems(...) floats.
+constexpr int kStatRows = 112;
+inline size_t stats_elems(long long n_img, int hw, long long T, int C) {
+  const long long imgs = hw > 1 ? n_img : 1, rows = hw > 1 ? hw : T;
+  return static_cast<size_t>(imgs) * cdiv(rows, kStatRows) * 8 * C;
+}
+inline int run_channel_stats(cudaStream_t st, const bf16* X, const bf16* D, long long n_img, int hw, long long T,
+                             int C, float* stbuf, float* chan, float* var_part, float* rowvar) {
+  const long long imgs = hw > 1 ? n_img : 1, rows = hw > 1 ? hw : T;
+  const int R = cdiv(rows, kStatRows);
+  if (imgs > 2147483647LL || R > 65535) return fail(SVB_ERR_UNSUPPORTED, "batch too large for the stats kernel");
+  (channel_stats_kernel<<<dim3(static_cast<unsigned>(imgs), R, cdiv(C, 256)), 256, 0, st>>>(X, D, nullptr, stbuf, C, static_cast<int>(rows), kStatRows), svb::count_launch());
+  (channel_stats_finalize_kernel<<<cdiv(C, 8), 256, 0, st>>>(stbuf, chan, var_part, static_cast<int>(imgs), R, C, static_cast<int>(rows)), svb::count_launch());
+  if (hw == 1) (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, D, rowvar, static_cast<int>(T), C), svb::count_launch());
+  SVB_LAUNCH_CHECK("channel_stats");
   return 0;
 }
 

@@ -54,9 +54,9 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
   p.csum_pi = a.take<float>(F);
   p.csum_mage = a.take<float>(F);
   p.csum_a = a.take<float>(F);
-  p.st = a.take<float>(p.hw > 1 ? static_cast<size_t>(p.n_img) * 8 * p.C : 8 * p.C);
+  p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
   p.chan = a.take<float>(4 * p.C);
-  p.var_part = a.take<float>(2 * cdiv(p.C, 32) + 2);
+  p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
   p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
   p.s_wg = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
@@ -246,15 +246,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   EpiDec::Params e2v{};
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v)), "via");
-  if (pl.hw > 1) {
-    (channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw), svb::count_launch());
-    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw), svb::count_launch());
-  } else {
-    (channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T), svb::count_launch());
-    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T), svb::count_launch());
-    (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C), svb::count_launch());
-  }
-  SVB_LAUNCH_CHECK("channel_stats");
+  SVB_TRY(run_channel_stats(st, X, pl.D, pl.n_img, pl.hw, pl.T, C, pl.st, pl.chan, pl.var_part, pl.rowvar));
   EpiGatedDPre::Params e3{};
   e3.e = pl.E; e3.rp = pl.RP; e3.exp_r = pl.exp_r; e3.a_out = pl.A;
   e3.colsum_mag = pl.cs_mag; e3.colsum_pi = pl.cs_pi; e3.colsum_mage = pl.cs_mage;
@@ -281,7 +273,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
   (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
   (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 2), svb::count_launch());
-  (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+  (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                              pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());
   (activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,

@@ -64,9 +64,9 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
-  p.st = a.take<float>(p.hw > 1 ? static_cast<size_t>(p.n_img) * 8 * p.C : 8 * p.C);
+  p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
   p.chan = a.take<float>(4 * p.C);
-  p.var_part = a.take<float>(2 * cdiv(p.C, 32) + 2);
+  p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
   p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
   p.s_we = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
@@ -233,15 +233,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
   prof_mark(h, st, 3);
   // channel statistics
-  if (pl.hw > 1) {
-    (channel_stats_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, pl.hw), svb::count_launch());
-    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C, pl.hw), svb::count_launch());
-  } else {
-    (channel_stats_kernel<<<dim3(1, cdiv(C, 256)), 256, 0, st>>>(X, pl.D, pl.DIFF, pl.st, C, T), svb::count_launch());
-    (channel_stats_finalize_kernel<<<cdiv(C, 32), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, 1, C, T), svb::count_launch());
-    (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, pl.D, pl.rowvar, T, C), svb::count_launch());
-  }
-  SVB_LAUNCH_CHECK("channel_stats");
+  SVB_TRY(run_channel_stats(st, X, pl.D, pl.n_img, pl.hw, pl.T, C, pl.st, pl.chan, pl.var_part, pl.rowvar));
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
   EpiDPre::Params e3{};
@@ -271,7 +263,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // loss partial sums
   (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
   (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
-  (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 32), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
+  (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                        pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);
   // activity
