@@ -198,13 +198,13 @@ static __global__ void reduce_flat_kernel(const float* __restrict__ in, size_t n
 // ------------------------------------------------------------------------------------------------ channel stats
 // Per image b, row chunk r and channel c over the chunk's tokens (token-major bf16 inputs):
 //   st[b][r][0][c] = sum x, [1] = sum x^2, [2] = sum d, [3] = sum d^2, [4] = sum diff, [5] = sum diff^2,
-//   [6] = min x, [7] = max x          (diff = d - x when no diff tensor is given)
+//   [6] = min x, [7] = max x          (diff = d - x, from the stored bf16 d)
 // grid (n_img, row_chunks, ceil(C/256)), 256 threads: lane owns 8 channels (one 16-byte load), warp w takes rows
 // w, w+8, ... of the chunk.  Feeds variance_explained (utils.py:2012-2030), compute_rmse_nrmse
 // (sparse_loss.py:4-21) and db_dec.
 static __global__ void __launch_bounds__(256)
-channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, const bf16* __restrict__ diff,
-                     float* __restrict__ st, int C, int HW, int rows_per_chunk) {
+channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, float* __restrict__ st, int C, int HW,
+                     int rows_per_chunk) {
   __shared__ float s[8][8][33];  // [warp][stat][lane]  (one channel-of-8 at a time)
   const int b = blockIdx.x, rc = blockIdx.y, R = gridDim.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -218,31 +218,40 @@ channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, con
     a[6][k] = INFINITY;
     a[7][k] = -INFINITY;
   }
-  if (c0 < C) {
-#pragma unroll 2
-    for (int r = r_begin + w; r < r_end; r += 8) {
-      const size_t off = (static_cast<size_t>(b) * HW + r) * C + c0;
-      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x + off));
-      const uint4 qd = d ? __ldg(reinterpret_cast<const uint4*>(d + off)) : make_uint4(0, 0, 0, 0);
-      uint4 qf = make_uint4(0, 0, 0, 0);
-      if (diff) qf = __ldg(reinterpret_cast<const uint4*>(diff + off));
-      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w},
-                     wf[4] = {qf.x, qf.y, qf.z, qf.w};
+  auto accumulate = [&](const uint4& qx, const uint4& qd) {
+    const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x0 = bf16lo(wx[k]), x1 = bf16hi(wx[k]);
-        const float d0 = bf16lo(wd[k]), d1 = bf16hi(wd[k]);
-        const float f0 = diff ? bf16lo(wf[k]) : d0 - x0, f1 = diff ? bf16hi(wf[k]) : d1 - x1;
-        a[0][2 * k] += x0; a[0][2 * k + 1] += x1;
-        a[1][2 * k] += x0 * x0; a[1][2 * k + 1] += x1 * x1;
-        a[2][2 * k] += d0; a[2][2 * k + 1] += d1;
-        a[3][2 * k] += d0 * d0; a[3][2 * k + 1] += d1 * d1;
-        a[4][2 * k] += f0; a[4][2 * k + 1] += f1;
-        a[5][2 * k] += f0 * f0; a[5][2 * k + 1] += f1 * f1;
-        a[6][2 * k] = fminf(a[6][2 * k], x0); a[6][2 * k + 1] = fminf(a[6][2 * k + 1], x1);
-        a[7][2 * k] = fmaxf(a[7][2 * k], x0); a[7][2 * k + 1] = fmaxf(a[7][2 * k + 1], x1);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = bf16lo(wx[k]), x1 = bf16hi(wx[k]);
+      const float d0 = bf16lo(wd[k]), d1 = bf16hi(wd[k]);
+      const float f0 = d0 - x0, f1 = d1 - x1;
+      a[0][2 * k] += x0; a[0][2 * k + 1] += x1;
+      a[1][2 * k] += x0 * x0; a[1][2 * k + 1] += x1 * x1;
+      a[2][2 * k] += d0; a[2][2 * k + 1] += d1;
+      a[3][2 * k] += d0 * d0; a[3][2 * k + 1] += d1 * d1;
+      a[4][2 * k] += f0; a[4][2 * k + 1] += f1;
+      a[5][2 * k] += f0 * f0; a[5][2 * k + 1] += f1 * f1;
+      a[6][2 * k] = fminf(a[6][2 * k], x0); a[6][2 * k + 1] = fminf(a[6][2 * k + 1], x1);
+      a[7][2 * k] = fmaxf(a[7][2 * k], x0); a[7][2 * k + 1] = fmaxf(a[7][2 * k + 1], x1);
     }
+  };
+  if (c0 < C) {
+    const bf16* xb = x + static_cast<size_t>(b) * HW * C + c0;
+    const bf16* db = d + static_cast<size_t>(b) * HW * C + c0;
+    int r = r_begin + w;
+    for (; r + 24 < r_end; r += 32) {  // 4 rows (8 independent 16-byte loads) in flight per thread
+      uint4 qx[4], qd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        qx[u] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r + 8 * u) * C));
+        qd[u] = __ldg(reinterpret_cast<const uint4*>(db + static_cast<size_t>(r + 8 * u) * C));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accumulate(qx[u], qd[u]);
+    }
+    for (; r < r_end; r += 8)
+      accumulate(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r) * C)),
+                 __ldg(reinterpret_cast<const uint4*>(db + static_cast<size_t>(r) * C)));
   }
   // cross-warp combine, one of the 8 per-lane channels at a time (fixed order over warps)
   for (int k = 0; k < 8; ++k) {

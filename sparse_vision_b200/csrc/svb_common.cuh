@@ -214,7 +214,7 @@ inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float sca
 }
 
 // Channel statistics of one batch (see channel_stats_kernel).  st holds stats_elems(...) floats.
-constexpr int kStatRows = 112;
+constexpr int kStatRows = 392;
 inline size_t stats_elems(long long n_img, int hw, long long T, int C) {
   const long long imgs = hw > 1 ? n_img : 1, rows = hw > 1 ? hw : T;
   return static_cast<size_t>(imgs) * cdiv(rows, kStatRows) * 8 * C;
@@ -224,7 +224,7 @@ inline int run_channel_stats(cudaStream_t st, const bf16* X, const bf16* D, long
   const long long imgs = hw > 1 ? n_img : 1, rows = hw > 1 ? hw : T;
   const int R = cdiv(rows, kStatRows);
   if (imgs > 2147483647LL || R > 65535) return fail(SVB_ERR_UNSUPPORTED, "batch too large for the stats kernel");
-  (channel_stats_kernel<<<dim3(static_cast<unsigned>(imgs), R, cdiv(C, 256)), 256, 0, st>>>(X, D, nullptr, stbuf, C, static_cast<int>(rows), kStatRows), svb::count_launch());
+  (channel_stats_kernel<<<dim3(static_cast<unsigned>(imgs), R, cdiv(C, 256)), 256, 0, st>>>(X, D, stbuf, C, static_cast<int>(rows), kStatRows), svb::count_launch());
   (channel_stats_finalize_kernel<<<cdiv(C, 8), 256, 0, st>>>(stbuf, chan, var_part, static_cast<int>(imgs), R, C, static_cast<int>(rows)), svb::count_launch());
   if (hw == 1) (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, D, rowvar, static_cast<int>(T), C), svb::count_launch());
   SVB_LAUNCH_CHECK("channel_stats");
