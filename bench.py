@@ -132,6 +132,60 @@ def cpu_reference_throughput(n_images, steps, warmup, threads=None):
     return tokens / dt, dt * 1e3, torch.get_num_threads()
 
 
+def ie_section(dev, peaks, n_images=64, iters=20):
+    """IE images/sec (second half of the BASELINE.json metric) at cfg5 / mixed3a: F=2048 SAE features on 28x28 maps.
+    Times (a) the stand-alone compute_ie_channel_wise reduction (utils.py:2606-2637) on fp32 and bf16 [T,F] inputs —
+    HBM roofline, algorithmic bytes 2*T*F*s + F*HW*4 + F*4 — and (b) the fused per-layer node-IE
+    (encoder GEMM, decoder GEMM, g W_dec GEMM and the three reductions) in images/s."""
+    from sparse_vision_b200 import ops
+    F, HW, Cc = C_ACT * EXPANSION, HW_SIDE * HW_SIDE, C_ACT
+    T = n_images * HW
+    g = torch.Generator(device="cpu").manual_seed(7)
+    out = {}
+    avg = torch.rand(F, HW_SIDE, HW_SIDE, generator=g).to(dev)
+    for name, dt, sz in (("f32", torch.float32, 4), ("bf16", torch.bfloat16, 2)):
+        # two rotating input sets so that every timed launch reads from HBM, not L2 (2 x 2 x T*F*sz > 126 MB)
+        sets = [(torch.rand(T, F, device=dev, dtype=torch.float32).to(dt), torch.randn(T, F, device=dev).to(dt))
+                for _ in range(2)]
+        for i in range(3):
+            ops.ie_channelwise(*[sets[i % 2][0], avg, sets[i % 2][1]], n_images)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            ops.ie_channelwise(sets[i % 2][0], avg, sets[i % 2][1], n_images)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nbytes = 2.0 * T * F * sz + F * HW * 4 + F * 4
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm"] if peaks["hbm"] else None, "images_per_s": n_images / (ms * 1e-3)}
+        del sets
+    # fused node-IE of one layer on bf16 NCHW activations / gradients
+    model = _make_params()
+    params = [p.detach().clone().to(dev) for p in model.param_list()]
+    x = [_synthetic_acts(n_images, 900 + i).to(torch.bfloat16).to(dev) for i in range(2)]
+    gr = [torch.randn(n_images, Cc, HW_SIDE, HW_SIDE, generator=g).to(torch.bfloat16).to(dev) for _ in range(2)]
+    err_avg = torch.zeros(Cc, HW_SIDE, HW_SIDE, device=dev)
+    x_avg = x[0].float().mean(0)
+    for i in range(3):
+        ops.node_ie_layer(x[i % 2], gr[i % 2], params, avg, err_avg, x_avg)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.node_ie_layer(x[i % 2], gr[i % 2], params, avg, err_avg, x_avg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["node_ie_layer"] = {"ms": ms, "images_per_s": n_images / (ms * 1e-3),
+                            "what": "svb_node_ie_layer: enc + dec + g*W_dec GEMMs and 3 reductions, one layer"}
+    out["config"] = {"workload": "configs[4] / mixed3a: C=256, F=2048, 28x28, %d images per call" % n_images,
+                     "peak_source": peaks["source"] + ", hbm copy"}
+    return out
+
+
 def run_reference(args):
     rank = _env_int("RANK", 0)
     if rank != 0:
@@ -295,6 +349,8 @@ def run_svb(args):
             "clocks": clocks,
             "final_step_stats": {k: last_stats[k] for k in ("loss", "rec", "l1", "n_dead")},
         }
+        if world == 1 and not args.no_ie:
+            line["ie"] = ie_section(dev, peaks)
         if cpu_v is not None:
             line["cpu_baseline"] = {
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -314,6 +370,7 @@ def main():
     ap.add_argument("--impl", default="svb", choices=["svb", "reference"])
     ap.add_argument("--images", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--cpu-images", type=int, default=8, help="images per step of the CPU reference sample")
+    ap.add_argument("--no-ie", action="store_true", help="skip the indirect-effect section")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "svb":
         args.warmup = 3

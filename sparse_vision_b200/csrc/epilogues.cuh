@@ -87,24 +87,27 @@ __device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_p
   }
 }
 
-// Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores (one 4 KB buffer per
-// epilogue warp; the two warps of an SM sub-partition overlap each other's store waits).
-struct SlabWriter {
-  static constexpr uint32_t kBytesPerWarp = 4096;
+// Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores.  NBUF = 2 double-buffers
+// (a slab is written while the previous one is still being read by the TMA engine); NBUF = 1 waits for the read.
+template <int NBUF>
+struct SlabWriterT {
+  static constexpr uint32_t kBytesPerWarp = NBUF * 4096;
   static constexpr uint32_t kBytes = 8 * kBytesPerWarp;  // eight epilogue warps
   uint8_t* base;
+  uint32_t which;
   bool half_pending;
   __device__ void init(uint8_t* epi_smem, int ew) {
     base = epi_smem + ew * kBytesPerWarp;
+    which = 0;
     half_pending = false;
   }
   // columns [half*32, half*32+32) of this lane's row; 16-byte pieces land XOR-swizzled like the tensor map expects
   __device__ void put(int half, int lane, const float (&v)[32]) {
-    if (half == 0) {  // the previous slab's store must have finished READING the buffer
-      if (lane == 0) bulk_wait_read<0>();
+    if (half == 0) {  // the store that last used this buffer must have finished READING it
+      if (lane == 0) bulk_wait_read<NBUF - 1>();
       __syncwarp();
     }
-    uint8_t* row = base + lane * 128;
+    uint8_t* row = base + which * 4096 + lane * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = half * 4 + i;
@@ -117,9 +120,10 @@ struct SlabWriter {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tm, base, col0, row0);
+      tma_store_2d(tm, base + which * 4096, col0, row0);
       bulk_commit();
     }
+    if (NBUF > 1) which ^= 1;
     half_pending = false;
   }
   __device__ void drain(int lane) {
@@ -127,6 +131,8 @@ struct SlabWriter {
     __syncwarp();
   }
 };
+typedef SlabWriterT<2> SlabWriter;   // single-output epilogues
+typedef SlabWriterT<1> SlabWriter1;  // two-output epilogues (shared-memory budget)
 
 // ------------------------------------------------------------------------------------------------ fp32 partials
 // Split-K slices of the weight-gradient GEMMs: out[split][row][col] = acc (fp32, direct 16-byte stores; the
@@ -267,14 +273,23 @@ struct EpiEnc {
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     const long long off = static_cast<long long>(row) * g.N + col0;
     if (p.pre_f32 && row_ok) store_row_f32(p.pre_f32 + off, v, nvalid);
-    uint32_t word = 0;
+    // four independent chains (8 columns each) for the mask bits and the partial sums: the serial versions are
+    // 32-deep dependency chains that two warps per sub-partition cannot hide
+    uint32_t wq4[4] = {0, 0, 0, 0};
+    float sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 31; j >= 0; --j) {
-      // sign bit of (0 - pre) is set exactly when pre > 0; funnel it into the word MSB-first
-      word = __funnelshift_l(__float_as_uint(0.f - v[j]), word, 1);
-      v[j] = fmaxf(v[j], 0.f);
-      sum += v[j];
+    for (int j = 7; j >= 0; --j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = q * 8 + j;
+        // sign bit of (0 - pre) is set exactly when pre > 0; funnel it into the byte MSB-first
+        wq4[q] = __funnelshift_l(__float_as_uint(0.f - v[i]), wq4[q], 1);
+        v[i] = fmaxf(v[i], 0.f);
+        sq4[q] += v[i];
+      }
     }
+    uint32_t word = (wq4[0] | (wq4[1] << 8)) | ((wq4[2] << 16) | (wq4[3] << 24));
+    sum += (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
     if (nvalid < 32) word &= (1u << nvalid) - 1u;
     if (!row_ok) word = 0;
     const int c = ((col0 - ti.n0) >> 5) - c_first;
@@ -341,17 +356,17 @@ struct EpiDec {
     __nv_bfloat16* diff_bf16;         // [M,N] or null
     float* sq_partial;                // [tiles_m*tiles_n*8] or null
   };
-  static constexpr uint32_t kSmemBytes = 2 * SlabWriter::kBytes + 2 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::kBytes + 2 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter slab_d, slab_f;
+  SlabWriter1 slab_d, slab_f;
   float* cv_base;
   const float* cv;
   float sq;
   int ew;
   __device__ EpiDec(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter::kBytes)), cv(nullptr), sq(0.f), ew(ew_) {
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::kBytes)), cv(nullptr), sq(0.f), ew(ew_) {
     slab_d.init(smem, ew_);
-    slab_f.init(smem + SlabWriter::kBytes, ew_);
+    slab_f.init(smem + SlabWriter1::kBytes, ew_);
   }
   __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
     const float* const src[1] = {p.bias};
