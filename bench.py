@@ -108,7 +108,7 @@ def _traffic():
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(path):
         with open(path) as fh:
-            return json.load(fh)
+            return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
     return {}
 
 
