@@ -1,6 +1,6 @@
 // Epilogue functors for gemm_bf16_kernel.  An epilogue thread owns ONE accumulator row (a token, or a feature in the
-// weight-gradient GEMMs) and receives its warp's share of the columns 32 at a time (8 epilogue warps: warp `ew` owns
-// TMEM lane quarter ew%4... and column half ew/4 of the tile).  Rows >= M and columns >= N hold zeros from TMA
+// weight-gradient GEMMs) and receives its warp's share of the columns 32 at a time (Epi::kWarps = 8 or 16 epilogue warps: warp `ew`
+// owns a TMEM lane quarter and column group ew/4 of the tile).  Rows >= M and columns >= N hold zeros from TMA
 // out-of-bounds fill, but they must still be masked out of every reduction and store.
 //
 // bf16 outputs on the hot path leave through shared memory: each warp stages 32-row x 64-column slabs (128-byte rows,
@@ -88,11 +88,12 @@ __device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_p
 }
 
 // Per-warp staging of 32-row x 64-column bf16 slabs that leave through TMA tensor stores.  NBUF = 2 double-buffers
-// (a slab is written while the previous one is still being read by the TMA engine); NBUF = 1 waits for the read.
+// (a slab is written while the previous one is still being read by the TMA engine); NBUF = 1 waits for the read
+// (free when a warp produces one slab per tile).
 template <int NBUF>
 struct SlabWriterT {
   static constexpr uint32_t kBytesPerWarp = NBUF * 4096;
-  static constexpr uint32_t kBytes = 8 * kBytesPerWarp;  // eight epilogue warps
+  __host__ __device__ static constexpr uint32_t bytes(int warps) { return warps * kBytesPerWarp; }
   uint8_t* base;
   uint32_t which;
   bool half_pending;
@@ -131,8 +132,8 @@ struct SlabWriterT {
     __syncwarp();
   }
 };
-typedef SlabWriterT<2> SlabWriter;   // single-output epilogues
-typedef SlabWriterT<1> SlabWriter1;  // two-output epilogues (shared-memory budget)
+typedef SlabWriterT<1> SlabWriter1;
+typedef SlabWriterT<2> SlabWriter2;
 
 // ------------------------------------------------------------------------------------------------ fp32 partials
 // Split-K slices of the weight-gradient GEMMs: out[split][row][col] = acc (fp32, direct 16-byte stores; the
@@ -143,10 +144,13 @@ struct EpiPartial {
     long long ld;
     long long split_stride;
   };
+  static constexpr int kWarps = 8;
+  static constexpr int kColVecs = 0;
   static constexpr uint32_t kSmemBytes = 0;
   const Params& p;
   __device__ EpiPartial(const Params& p_, uint8_t*, int, int) : p(p_) {}
-  __device__ bool prefetch_tile(const GemmProblem&, const TileInfo&, uint32_t, int) { return false; }
+  __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
+  __device__ void colvec_commit(uint32_t, int) {}
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int, int) {
     if (row >= g.M) return;
@@ -170,35 +174,34 @@ struct EpiStore {
     int out_bf16;
     int tm_valid;
   };
-  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 2 * 256 * sizeof(float);
+  static constexpr int kWarps = 16;
+  static constexpr int kColVecs = 1;
+  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter slab;
+  SlabWriter1 slab;
+  ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   __device__ EpiStore(const Params& p_, uint8_t* smem, int ew, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr) {
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base) {
     slab.init(smem, ew);
   }
-  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
-    if (!p.bias) return false;
+  __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.bias};
+    stage.fetch(src, ti.n0, g.N, tid);
+  }
+  __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 256;
-    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    stage.commit(dst, tid);
     cv = dst;
-    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
     const int nvalid = min(32, g.N - col0);
-    if (p.bias) {
-      float b[32];
-      lds_row_f32(cv + (col0 - ti.n0), b);
+    float b[32];
+    lds_row_f32(cv + (col0 - ti.n0), b);  // zeros when there is no bias
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + b[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-    }
+    for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + b[j];
     if (p.relu) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -234,29 +237,34 @@ struct EpiEnc {
     float* pre_f32;                // [M,N] or null
     uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
     uint32_t* act_bits;            // [n_img, words] or null
-    float* l1_partial;             // [tiles_m*tiles_n*8] or null
+    float* l1_partial;             // [tiles_m*tiles_n*kWarps] or null
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
   };
-  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 2 * 256 * sizeof(float);
+  static constexpr int kWarps = 16;
+  static constexpr int kColVecs = 1;
+  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter slab;
+  SlabWriter1 slab;
+  ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   float sum;
   uint32_t words[4];
-  int ew, c_first;  // this warp's first 32-column chunk inside the tile
+  int ew, cpw, c_first;  // chunks per warp, this warp's first 32-column chunk inside the tile
   __device__ EpiEnc(const Params& p_, uint8_t* smem, int ew_, int block_n)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), cv(nullptr), sum(0.f), ew(ew_),
-        c_first((ew_ / 4) * (block_n / 64)) {
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f), ew(ew_),
+        cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
     slab.init(smem, ew_);
   }
-  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+  __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.bias};
+    stage.fetch(src, ti.n0, g.N, tid);
+  }
+  __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 256;
-    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    stage.commit(dst, tid);
     cv = dst;
-    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
     sum = 0.f;
@@ -273,8 +281,7 @@ struct EpiEnc {
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     const long long off = static_cast<long long>(row) * g.N + col0;
     if (p.pre_f32 && row_ok) store_row_f32(p.pre_f32 + off, v, nvalid);
-    // four independent chains (8 columns each) for the mask bits and the partial sums: the serial versions are
-    // 32-deep dependency chains that two warps per sub-partition cannot hide
+    // four independent chains (8 columns each) for the mask bits and the partial sums
     uint32_t wq4[4] = {0, 0, 0, 0};
     float sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -306,11 +313,13 @@ struct EpiEnc {
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
     const int w0 = (ti.n0 >> 5) + c_first;            // first word index of this warp
-    const int nw = max(0, min(4, p.words - w0));
+    const int nw = max(0, min(cpw, p.words - w0));
     if (p.mask_words && row < g.M && nw > 0) {
       uint32_t* dst = p.mask_words + static_cast<size_t>(row) * p.words + w0;
       if (nw == 4 && (p.words & 3) == 0) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+      } else if (nw == 2 && (p.words & 1) == 0) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(words[0], words[1]);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -318,7 +327,7 @@ struct EpiEnc {
       }
     }
     if (p.act_bits && nw > 0) {
-      // OR the rows of each image this warp touches; lanes 0..3 publish one word each (one RED per segment)
+      // OR the rows of each image this warp touches; lanes 0..nw-1 publish one word each (one RED per segment)
       const int row0 = ti.m0 + wq * 32;
       const int last_row = min(row0 + 31, g.M - 1);
       if (row0 <= last_row) {
@@ -328,8 +337,10 @@ struct EpiEnc {
           uint32_t mine = 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? words[i] : 0u);
-            if (lane == i) mine = ored;
+            if (i < cpw) {
+              const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? words[i] : 0u);
+              if (lane == i) mine = ored;
+            }
           }
           if (lane < nw && mine) atomicOr(&p.act_bits[static_cast<size_t>(b) * p.words + w0 + lane], mine);
         }
@@ -337,7 +348,7 @@ struct EpiEnc {
     }
     if (p.l1_partial) {
       const float s = warp_sum(row < g.M ? sum : 0.f);
-      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
+      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
     }
   }
   __device__ void finish(int, int lane) { slab.drain(lane); }
@@ -345,6 +356,7 @@ struct EpiEnc {
 
 // ------------------------------------------------------------------------------------------------ decoder
 // d = acc + b_dec;  diff = d - x   (sae_mlp.py:52, sparse_loss.py:35).  Fused: stores of d / diff, sum diff^2.
+// HBM-bound (it streams E once), so 8 epilogue warps are enough.
 struct EpiDec {
   struct Params {
     alignas(64) CUtensorMap tm_d;     // bf16 d [M,N]   (valid when d_bf16 != null)
@@ -354,26 +366,32 @@ struct EpiDec {
     __nv_bfloat16* d_bf16;            // [M,N] or null
     float* d_f32;                     // [M,N] or null
     __nv_bfloat16* diff_bf16;         // [M,N] or null
-    float* sq_partial;                // [tiles_m*tiles_n*8] or null
+    float* sq_partial;                // [tiles_m*tiles_n*kWarps] or null
   };
-  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::kBytes + 2 * 256 * sizeof(float);
+  static constexpr int kWarps = 8;
+  static constexpr int kColVecs = 1;
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
   SlabWriter1 slab_d, slab_f;
+  ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   float sq;
   int ew;
   __device__ EpiDec(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::kBytes)), cv(nullptr), sq(0.f), ew(ew_) {
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps))), cv(cv_base), sq(0.f),
+        ew(ew_) {
     slab_d.init(smem, ew_);
-    slab_f.init(smem + SlabWriter1::kBytes, ew_);
+    slab_f.init(smem + SlabWriter1::bytes(kWarps), ew_);
   }
-  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+  __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.bias};
+    stage.fetch(src, ti.n0, g.N, tid);
+  }
+  __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 256;
-    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    stage.commit(dst, tid);
     cv = dst;
-    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sq = 0.f; }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
@@ -411,7 +429,7 @@ struct EpiDec {
     if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane);
     if (p.sq_partial) {
       const float s = warp_sum(sq);
-      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
+      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
     }
   }
   __device__ void finish(int, int lane) { slab_d.drain(lane); }
@@ -421,7 +439,7 @@ struct EpiDec {
 // acc = diff * W_dec  (unscaled dE);  dPre' = 1[e>0] * (acc + l1c)  with l1c = lambda*C/(2F), i.e. the whole
 // backward is carried in units of T*C/2 and rescaled once in the gradient reduction (model_pipeline.py:385 autograd
 // of sparse_loss.py:35,41 through sae_mlp.py:51).  The ReLU mask comes from the encoder's 1-bit activity words
-// (16 B per row and warp instead of re-reading 256 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
+// (8 B per row and warp instead of re-reading 128 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
 // column sums (-> db_enc).
 struct EpiDPre {
   struct Params {
@@ -431,28 +449,35 @@ struct EpiDPre {
     float l1c;
     int words;
   };
-  static constexpr uint32_t kSmemBytes = SlabWriter::kBytes + 4 * 256 * sizeof(float);
+  static constexpr int kWarps = 16;
+  static constexpr int kColVecs = 0;
+  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 4 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter slab;
+  SlabWriter1 slab;
   float* s_col;  // [4 lane quarters][256 columns]
   uint32_t words[4];
-  int ew, c_first, block_n;
+  int ew, cpw, c_first, block_n;
   __device__ EpiDPre(const Params& p_, uint8_t* smem, int ew_, int block_n_)
-      : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter::kBytes)), ew(ew_),
-        c_first((ew_ / 4) * (block_n_ / 64)), block_n(block_n_) {
+      : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), ew(ew_),
+        cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
+        block_n(block_n_) {
     slab.init(smem, ew_);
   }
-  __device__ bool prefetch_tile(const GemmProblem&, const TileInfo&, uint32_t, int) { return false; }
+  __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
+  __device__ void colvec_commit(uint32_t, int) {}
   __device__ void begin_tile(const GemmProblem& g, const TileInfo& ti, int row, int, int) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) words[i] = 0;
     const int w0 = (ti.n0 >> 5) + c_first;
-    const int nw = max(0, min(4, p.words - w0));
+    const int nw = max(0, min(cpw, p.words - w0));
     if (row < g.M && nw > 0) {
       const uint32_t* src = p.mask_words + static_cast<size_t>(row) * p.words + w0;
       if (nw == 4 && (p.words & 3) == 0) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
         words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
+      } else if (nw == 2 && (p.words & 1) == 0) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+        words[0] = a.x; words[1] = a.y;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -476,14 +501,14 @@ struct EpiDPre {
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
-    epi_bar_sync();
-    const int c = ew * 32 + lane;  // 256 epilogue threads, one column each
+    epi_bar_sync(kWarps * 32);
+    const int c = ew * 32 + lane;  // the first 256 epilogue threads take one column each
     const int col = ti.n0 + c;
-    if (c < block_n && col < g.N) {
+    if (c < block_n && c < 256 && col < g.N) {
       const float s = (s_col[c] + s_col[256 + c]) + (s_col[512 + c] + s_col[768 + c]);
       p.colsum_partial[static_cast<size_t>(ti.tile_m) * g.N + col] = s;
     }
-    epi_bar_sync();
+    epi_bar_sync(kWarps * 32);
   }
   __device__ void finish(int, int lane) { slab.drain(lane); }
 };

@@ -25,20 +25,25 @@ struct EpiGatedEnc {
     float* l1_partial;
     int hw, words;
   };
+  static constexpr int kWarps = 8;
+  static constexpr int kColVecs = 4;
   static constexpr uint32_t kSmemBytes = 2 * 4 * 256 * sizeof(float);
   const Params& p;
+  ColVecStage<4, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   float sum;
   int ew;
   __device__ EpiGatedEnc(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(nullptr), sum(0.f), ew(ew_) {}
-  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(cv_base), sum(0.f), ew(ew_) {}
+  __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
+    stage.fetch(src, ti.n0, g.N, tid);
+  }
+  __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 4 * 256;
-    stage_colvecs<4>(dst, src, ti.n0, g.N, tid);
+    stage.commit(dst, tid);
     cv = dst;
-    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
@@ -75,7 +80,7 @@ struct EpiGatedEnc {
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
     if (!p.l1_partial) return;
     const float s = warp_sum(row < g.M ? sum : 0.f);
-    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * 8 + ew] = s;
+    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
   }
   __device__ void finish(int, int) {}
 };
@@ -98,21 +103,26 @@ struct EpiGatedDPre {
     float l1c;
     int block_n;
   };
+  static constexpr int kWarps = 8;
+  static constexpr int kColVecs = 1;
   static constexpr uint32_t kSmemBytes = 3 * 4 * 256 * sizeof(float) + 2 * 256 * sizeof(float);
   const Params& p;
+  ColVecStage<1, kWarps * 32> stage;
   float* s_col;  // [3][4][256]
   float* cv_base;
   const float* cv;
   int ew;
   __device__ EpiGatedDPre(const Params& p_, uint8_t* smem, int ew_, int)
       : p(p_), s_col(reinterpret_cast<float*>(smem)), cv_base(reinterpret_cast<float*>(smem) + 3 * 4 * 256),
-        cv(nullptr), ew(ew_) {}
-  __device__ bool prefetch_tile(const GemmProblem& g, const TileInfo& ti, uint32_t parity, int tid) {
+        cv(cv_base), ew(ew_) {}
+  __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.exp_r};
+    stage.fetch(src, ti.n0, g.N, tid);
+  }
+  __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 256;
-    stage_colvecs<1>(dst, src, ti.n0, g.N, tid);
+    stage.commit(dst, tid);
     cv = dst;
-    return true;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
@@ -140,7 +150,7 @@ struct EpiGatedDPre {
     s_col[(2 * 4 + wq) * 256 + cc] = warp_colsum32(e, lane);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
-    epi_bar_sync();
+    epi_bar_sync(kWarps * 32);
     const int c = ew * 32 + lane;  // 256 epilogue threads, one column each
     const int col = ti.n0 + c;
     float* outs[3] = {p.colsum_mag, p.colsum_pi, p.colsum_mage};
@@ -151,7 +161,7 @@ struct EpiGatedDPre {
         outs[q][static_cast<size_t>(ti.tile_m) * g.N + col] = (s[c] + s[256 + c]) + (s[512 + c] + s[768 + c]);
       }
     }
-    epi_bar_sync();
+    epi_bar_sync(kWarps * 32);
   }
   __device__ void finish(int, int) {}
 };

@@ -106,7 +106,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  (kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p, ep), svb::count_launch());
+  (kern<<<grid, 64 + Epi::kWarps * 32, smem, stream>>>(tmA, tmB, p, ep), svb::count_launch());
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

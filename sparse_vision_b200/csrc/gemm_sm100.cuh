@@ -2,10 +2,11 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer    (one thread issues tcgen05.mma, tcgen05.commit frees smem slots / publishes TMEM)
-//   warps 2..9  : epilogue      (tcgen05.ld TMEM -> registers -> Epi functor -> global).  Eight warps, two per SM
-//                 sub-partition: warps w and w+4 share a TMEM lane quarter and split the tile's columns, because
-//                 one warp per sub-partition cannot issue the per-element epilogue work of a K=256 tile (bias, ReLU,
-//                 mask, sums, bf16 pack) inside its 2048 MMA cycles.
+//   warps 2..    : epilogue     (tcgen05.ld TMEM -> registers -> Epi functor -> global).  Epi::kWarps = 8 or 16
+//                 warps (2 or 4 per SM sub-partition): warps that share a TMEM lane quarter split the tile's columns.
+//                 A K=256 tile gives the epilogue only 2048 MMA cycles, and the per-warp latency chain (TMEM load,
+//                 bias, ReLU, mask, sums, bf16 pack, slab store) of 4 chunks is ~3x that; 16 warps with 2 chunks each
+//                 and per-column vectors staged one tile ahead bring it under the MMA time.
 //
 // Either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers every GEMM of
 // the SAE step on row-major token tensors without a transpose copy:
@@ -24,8 +25,6 @@ namespace svb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;
-constexpr int kEpiThreads = 256;
 
 struct GemmProblem {
   int M, N, K;
@@ -58,20 +57,36 @@ struct GemmCfg {
   static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
-// Named barrier among the 256 epilogue threads only (id 1; id 0 is __syncthreads).
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// Stage NV per-column float vectors for columns [n0, n0+256) into dst[NV][256] (zero beyond N) with the 256 epilogue
-// threads.  dst alternates between two buffers by accumulator stage, so only one barrier per tile is needed: a warp
-// can run at most one tile ahead of the others (the TMEM full/empty handshake), never two.
-template <int NV>
-__device__ __forceinline__ void stage_colvecs(float* dst, const float* const (&src)[NV], int n0, int N, int tid) {
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int c = tid; c < 256; c += kEpiThreads)
-      dst[v * 256 + c] = (src[v] != nullptr && n0 + c < N) ? __ldg(src[v] + n0 + c) : 0.f;
+// Named barrier among the epilogue threads only (id 1; id 0 is __syncthreads).
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
+
+// Per-column float vectors (biases ...) of a tile, staged through registers into shared memory ONE TILE AHEAD:
+// fetch() issues the global loads for the next tile right after the barrier of the current one, commit() writes them
+// to smem at the top of the next iteration, so the L2 round trip (there is next to no L1 beside ~200 KB of dynamic
+// smem) overlaps a whole tile of epilogue work.  dst alternates between two buffers by accumulator stage; the one
+// barrier per tile also bounds the skew between epilogue warps to less than a tile, which makes that safe.
+template <int NV, int NTHREADS>
+struct ColVecStage {
+  static constexpr int kPer = (NV * 256 + NTHREADS - 1) / NTHREADS;
+  float r[kPer];
+  __device__ __forceinline__ void fetch(const float* const (&src)[NV], int n0, int N, int tid) {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int idx = tid + i * NTHREADS;
+      const int v = idx >> 8, c = idx & 255;
+      r[i] = (idx < NV * 256 && src[v < NV ? v : 0] != nullptr && n0 + c < N) ? __ldg(src[v < NV ? v : 0] + n0 + c) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void commit(float* dst, int tid) const {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int idx = tid + i * NTHREADS;
+      if (idx < NV * 256) dst[idx] = r[i];
+    }
+  }
+};
 
 __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
   TileInfo ti;
@@ -85,7 +100,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(64 + Epi::kWarps * 32, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmProblem p, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes>;
@@ -114,7 +129,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiThreads / 32);
+      mbar_init(&tmem_empty_bar[a], Epi::kWarps);
     }
     fence_barrier_init();
   }
@@ -198,27 +213,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
-    const int ew = warp - 2;  // 0..7
+    // ------------------------------------------------------------------ epilogue (4 lane quarters x kWarps/4 column groups)
+    constexpr int EW = Epi::kWarps;
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+    constexpr int kChunksPerWarp = (BLOCK_N / 32) / (EW / 4);
+    static_assert(kChunksPerWarp >= 2 && kChunksPerWarp % 2 == 0, "each epilogue warp owns whole 64-column slabs");
+    const int ew = warp - 2;  // 0..EW-1
     const int wq = warp % 4;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int chalf = ew / 4;
+    const int cgroup = ew / 4;
     const int row_in_tile = wq * 32 + lane;
     const int tid = ew * 32 + lane;
-    constexpr int kChunksPerWarp = BLOCK_N / 64;
     Epi epi(ep, epi_smem, ew, BLOCK_N);
     uint32_t acc = 0, acc_phase = 0;
+    if (Epi::kColVecs > 0 && static_cast<int>(blockIdx.x) < num_tiles)
+      epi.colvec_fetch(p, decode_tile(p, blockIdx.x, BLOCK_N), tid);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t, BLOCK_N);
-      // Per-column vectors (biases ...) are staged into shared memory while the MMAs of this tile are still running:
-      // with ~227 KB of dynamic smem there is next to no L1, so a global load in the chunk loop is an L2 round trip.
-      if (epi.prefetch_tile(p, ti, acc, tid)) epi_bar_sync();
+      if (Epi::kColVecs > 0) {
+        epi.colvec_commit(acc, tid);
+        epi_bar_sync(EW * 32);
+        if (t + static_cast<int>(gridDim.x) < num_tiles) epi.colvec_fetch(p, decode_tile(p, t + gridDim.x, BLOCK_N), tid);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = ti.m0 + row_in_tile;
       epi.begin_tile(p, ti, row, wq, lane);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = chalf * kChunksPerWarp; c < (chalf + 1) * kChunksPerWarp; ++c) {
+      for (int c = cgroup * kChunksPerWarp; c < (cgroup + 1) * kChunksPerWarp; ++c) {
         const int col0 = ti.n0 + c * 32;
         if (col0 >= p.N) break;
         float v[32];

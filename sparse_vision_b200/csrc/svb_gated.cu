@@ -43,9 +43,9 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
   p.A = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 8);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
-  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 16);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
+  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
   p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_pi = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_mage = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
@@ -270,9 +270,9 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg), svb::count_launch());
   (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm), svb::count_launch());
   (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 2), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * EpiGatedEnc::kWarps, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 2), svb::count_launch());
   (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                              pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());

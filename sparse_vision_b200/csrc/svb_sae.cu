@@ -59,8 +59,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   p.DIFF = a.take<bf16>(TC);
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
   p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 8);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 8);
+  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 16);
+  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
   p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
@@ -261,8 +261,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
   (sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe), svb::count_launch());  // gb_enc = s * csum
   // loss partial sums
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * 8, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * 8, 1.f, flat + pl.o_sums + 1), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 0), svb::count_launch());
+  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * EpiEnc::kWarps, 1.f, flat + pl.o_sums + 1), svb::count_launch());
   (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
                                        pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
   cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);

@@ -64,12 +64,14 @@ static int run(const Case& c) {
   int used = 0;
   int rc;
   if (c.bf16_out) {
+   if constexpr (BN == 256) {
     EpiStore::Params ep;
     memset(&ep, 0, sizeof(ep));
     ep.out = dC; ep.ld = c.N; ep.alpha = 1.0f; ep.out_bf16 = 1;
     if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
     else { printf("[%s] store tensor map failed\n", c.name); return 1; }
     rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+   } else { printf("[%s] bf16 slab output needs BLOCK_N=256\n", c.name); return 1; }
   } else {
     EpiPartial::Params ep{dC, c.N, (long long)c.M * c.N};
     rc = launch_gemm<BN, AMN, BMN, EpiPartial>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
@@ -140,7 +142,7 @@ static const Case kCases[] = {
     {"mnk", 136, 128, 520, true, false, 128, 2},
     {"kk_bf16_tma", 300, 256, 16, false, false, 256, 1, true},
     {"kk_bf16_tma_ntail", 200, 200, 24, false, false, 256, 1, true},
-    {"kk_bf16_tma_n96", 130, 96, 16, false, false, 128, 1, true},
+    {"kk_bf16_tma_n96", 130, 96, 16, false, false, 256, 1, true},
     {"kk_bf16_tma_many", 128 * 300 + 40, 512, 16, false, false, 256, 1, true},
 };
 
@@ -205,7 +207,7 @@ static int perf_enc_variants() {
   CK(cudaMalloc(&dB, (size_t)N * K * 2));
   CK(cudaMalloc(&dE, (size_t)M * N * 2));
   CK(cudaMalloc(&dbias, N * 4));
-  CK(cudaMalloc(&dl1, (size_t)(M / 128 + 1) * (N / 256) * 8 * 4));
+  CK(cudaMalloc(&dl1, (size_t)(M / 128 + 1) * (N / 256) * 16 * 4));
   CK(cudaMalloc(&dact, (size_t)(M / HW) * words * 4));
   CK(cudaMalloc(&dmask, (size_t)M * words * 4));
   CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
