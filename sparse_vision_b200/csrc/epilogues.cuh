@@ -174,7 +174,7 @@ struct EpiStore {
     int out_bf16;
     int tm_valid;
   };
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
   static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
@@ -241,7 +241,7 @@ struct EpiEnc {
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
   };
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
   static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
@@ -445,21 +445,19 @@ struct EpiDPre {
   struct Params {
     alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
     const uint32_t* mask_words;        // [M, words]
-    float* colsum_partial;             // [tiles_m, N]
+    float* colsum_partial;             // [tiles_m * 4 lane quarters, N]: one row per 32 tokens
     float l1c;
     int words;
   };
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = 8;
   static constexpr int kColVecs = 0;
-  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 4 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps);
   const Params& p;
   SlabWriter1 slab;
-  float* s_col;  // [4 lane quarters][256 columns]
   uint32_t words[4];
   int ew, cpw, c_first, block_n;
   __device__ EpiDPre(const Params& p_, uint8_t* smem, int ew_, int block_n_)
-      : p(p_), s_col(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), ew(ew_),
-        cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
+      : p(p_), ew(ew_), cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
         block_n(block_n_) {
     slab.init(smem, ew_);
   }
@@ -485,7 +483,7 @@ struct EpiDPre {
       }
     }
   }
-  __device__ void chunk(const GemmProblem&, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
     const int c = ((col0 - ti.n0) >> 5) - c_first;
     uint32_t word = 0;
 #pragma unroll
@@ -496,19 +494,12 @@ struct EpiDPre {
     const int half = c & 1;
     slab.put(half, lane, v);
     if (half == 1) slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
+    // column sums over this warp's 32 tokens: lane j ends up with column col0 + j (one coalesced 128-byte store)
     const float cs = warp_colsum32(v, lane);
-    s_col[wq * 256 + (col0 - ti.n0) + lane] = cs;
+    if (col0 + lane < g.N) p.colsum_partial[(static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col0 + lane] = cs;
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
-    epi_bar_sync(kWarps * 32);
-    const int c = ew * 32 + lane;  // the first 256 epilogue threads take one column each
-    const int col = ti.n0 + c;
-    if (c < block_n && c < 256 && col < g.N) {
-      const float s = (s_col[c] + s_col[256 + c]) + (s_col[512 + c] + s_col[768 + c]);
-      p.colsum_partial[static_cast<size_t>(ti.tile_m) * g.N + col] = s;
-    }
-    epi_bar_sync(kWarps * 32);
   }
   __device__ void finish(int, int lane) { slab.drain(lane); }
 };

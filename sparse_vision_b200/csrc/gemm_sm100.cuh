@@ -50,10 +50,10 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static constexpr uint32_t kBarrierBytes = 256;  // 2*stages + 4 mbarriers + tmem ptr
   static constexpr uint32_t kEpiBytes = (EPI_BYTES + 1023u) & ~1023u;  // epilogue staging, 1024-aligned (TMA swizzle)
-  static constexpr int kFit = static_cast<int>((kMaxDynSmem - 1024 - kBarrierBytes - kEpiBytes) / kStageBytes);
+  static constexpr int kFit = static_cast<int>((kMaxDynSmem - kBarrierBytes - kEpiBytes) / kStageBytes);
   static constexpr int kCap = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kStages = kFit < kCap ? kFit : kCap;
-  static constexpr uint32_t kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kEpiBytes + kBarrierBytes;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes;
   static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
@@ -108,8 +108,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
   static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::kBarrierBytes, "barrier region too small");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // No static __shared__ anywhere in this kernel, so the dynamic window starts at the CTA's shared-memory base and
+  // the 1024-byte alignment the 128B swizzle needs holds without slack (checked once below).
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;  // 1024-aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -121,6 +122,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = static_cast<int>(threadIdx.x) % 32;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("svb: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {

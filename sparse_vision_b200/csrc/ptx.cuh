@@ -2,6 +2,7 @@
 // Everything here is device-only plumbing used by gemm_sm100.cuh.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_bf16.h>
 

@@ -61,7 +61,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
   p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 16);
   p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
-  p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * 4 * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
   p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
@@ -254,7 +254,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // gradient assembly
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
-  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.tiles_m, F, 1.f, pl.stage, pl.csum));
+  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.tiles_m * 4, F, 1.f, pl.stage, pl.csum));
   (sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd), svb::count_launch());
   (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_we, pl.s_we, F, C, pl.csum, p->b_dec, s, flat + pl.o_gwe), svb::count_launch());
   (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum, pl.Web, F, C, pl.vm), svb::count_launch());
