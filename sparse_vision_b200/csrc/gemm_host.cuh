@@ -64,10 +64,10 @@ inline int device_sm_count() {
 // A: K-major -> memory [M, K] pitch lda;  MN-major -> memory [K, M] pitch lda.   B likewise with N.
 // k_splits_req <= 0 picks a split count that fills the machine when there are few output tiles.
 // Returns 0 or a negative svb error code; *splits_out receives the number of split-K slices used.
-template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0) {
-  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes>;
+  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
   int rc;
@@ -97,7 +97,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   p.k_per_split = kb_per * kBlockK;
   if (splits_out) *splits_out = splits;
 
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, Epi>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, Epi, BSTAT>;
   const uint32_t smem = Cfg::kSmemBytes;
   static bool configured = false;
   if (!configured) {
@@ -105,7 +105,13 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
     configured = true;
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
-  const int grid = num_tiles < sms ? num_tiles : sms;
+  int grid = num_tiles < sms ? num_tiles : sms;
+  if (BSTAT) {  // whole groups of tiles_n CTAs, each group walking a strided set of M tiles
+    if (p.k_splits != 1 || K > Cfg::kResidentKBlocks * kBlockK || p.tiles_n > sms) return -5;
+    int groups = sms / p.tiles_n;
+    if (groups > p.tiles_m) groups = p.tiles_m;
+    grid = groups * p.tiles_n;
+  }
   (kern<<<grid, 64 + Epi::kWarps * 32, smem, stream>>>(tmA, tmB, p, ep), svb::count_launch());
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }

@@ -42,18 +42,24 @@ struct TileInfo {
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
 
-template <int BLOCK_N, uint32_t EPI_BYTES>
+// BSTAT ("B-stationary"): for K <= 256 the whole [BLOCK_N x K] B tile (<= 128 KB) stays resident in shared memory
+// and a CTA walks the M tiles of ONE N tile, so only A is streamed.  Shared-memory bandwidth (~128 B/clk/SM shared
+// by TMA writes, UMMA operand reads and the epilogue's staging) is what bounds the K=256 GEMMs; not re-writing B
+// for every tile removes a quarter of that traffic.
+template <int BLOCK_N, uint32_t EPI_BYTES, bool BSTAT = false>
 struct GemmCfg {
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kResidentKBlocks = BSTAT ? 4 : 0;  // K <= 256
+  static constexpr uint32_t kResidentBytes = kResidentKBlocks * kBBytes;
+  static constexpr uint32_t kStageBytes = BSTAT ? kABytes : kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-  static constexpr uint32_t kBarrierBytes = 256;  // 2*stages + 4 mbarriers + tmem ptr
+  static constexpr uint32_t kBarrierBytes = 256;  // 2*stages + 5 mbarriers + tmem ptr
   static constexpr uint32_t kEpiBytes = (EPI_BYTES + 1023u) & ~1023u;  // epilogue staging, 1024-aligned (TMA swizzle)
-  static constexpr int kFit = static_cast<int>((kMaxDynSmem - kBarrierBytes - kEpiBytes) / kStageBytes);
-  static constexpr int kCap = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kFit = static_cast<int>((kMaxDynSmem - kBarrierBytes - kEpiBytes - kResidentBytes) / kStageBytes);
+  static constexpr int kCap = BSTAT ? 8 : ((BLOCK_N == 256) ? 4 : 6);
   static constexpr int kStages = kFit < kCap ? kFit : kCap;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes;
+  static constexpr uint32_t kSmemBytes = kResidentBytes + kStages * kStageBytes + kEpiBytes + kBarrierBytes;
   static_assert(kStages >= 2, "epilogue staging leaves no room for a pipelined operand ring");
 };
 
@@ -99,24 +105,26 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int
   return ti;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 __global__ void __launch_bounds__(64 + Epi::kWarps * 32, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmProblem p, const __grid_constant__ typename Epi::Params ep) {
-  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes>;
+  using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   constexpr int STAGES = Cfg::kStages;
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N must be 128 or 256");
-  static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::kBarrierBytes, "barrier region too small");
+  static_assert((2 * STAGES + 5) * 8 + 8 <= Cfg::kBarrierBytes, "barrier region too small");
 
   // No static __shared__ anywhere in this kernel, so the dynamic window starts at the CTA's shared-memory base and
   // the 1024-byte alignment the 128B swizzle needs holds without slack (checked once below).
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes;  // 1024-aligned
+  uint8_t* smem_ring = smem + Cfg::kResidentBytes;              // operand ring (after the resident B tile, if any)
+  uint8_t* epi_smem = smem_ring + STAGES * Cfg::kStageBytes;    // 1024-aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* b_full_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x) / 32, 0);
   const int lane = static_cast<int>(threadIdx.x) % 32;
@@ -136,6 +144,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], Epi::kWarps);
     }
+    mbar_init(b_full_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -148,20 +157,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+  // Tile sequence of this CTA.  Streaming: t = blockIdx.x, += gridDim.x over all (split, m, n) tiles.
+  // B-stationary: the CTA owns N tile blockIdx.x % tiles_n and walks M tiles t = blockIdx.x / tiles_n, += groups.
+  const int fixed_n = BSTAT ? static_cast<int>(blockIdx.x) % p.tiles_n : 0;
+  const int t_first = BSTAT ? static_cast<int>(blockIdx.x) / p.tiles_n : static_cast<int>(blockIdx.x);
+  const int t_step = BSTAT ? static_cast<int>(gridDim.x) / p.tiles_n : static_cast<int>(gridDim.x);
+  const int t_end = BSTAT ? p.tiles_m : num_tiles;
+  auto decode = [&](int t) -> TileInfo {
+    if constexpr (BSTAT) {
+      TileInfo ti;
+      ti.tile_n = fixed_n; ti.tile_m = t; ti.split = 0; ti.m0 = t * kBlockM; ti.n0 = fixed_n * BLOCK_N;
+      return ti;
+    } else {
+      return decode_tile(p, t, BLOCK_N);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(p, t, BLOCK_N);
+      auto load_b = [&](uint8_t* sb, uint64_t* bar, int k0, int n0) {
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmB, bar, k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, bar, n0 + 64 * j, k0);
+        }
+      };
+      if constexpr (BSTAT) {
+        if (t_first < t_end) {  // the whole B tile of this CTA's N tile, once
+          const int nkb_all = (p.K + kBlockK - 1) / kBlockK;
+          mbar_arrive_expect_tx(b_full_bar, nkb_all * Cfg::kBBytes);
+          for (int kb = 0; kb < nkb_all; ++kb) load_b(smem + kb * Cfg::kBBytes, b_full_bar, kb * kBlockK, fixed_n * BLOCK_N);
+        }
+      }
+      for (int t = t_first; t < t_end; t += t_step) {
+        const TileInfo ti = decode(t);
         const int k_begin = ti.split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+          uint8_t* sa = smem_ring + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = k_begin + kb * kBlockK;
           if constexpr (!A_MN) {
@@ -170,12 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.m0 + 64 * j, k0);
           }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, ti.n0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], ti.n0 + 64 * j, k0);
-          }
+          if constexpr (!BSTAT) load_b(sa + Cfg::kABytes, &full_bar[stage], k0, ti.n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -185,8 +218,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(p, t, BLOCK_N);
+      if constexpr (BSTAT) {
+        if (t_first < t_end) mbar_wait(b_full_bar, 0);
+      }
+      for (int t = t_first; t < t_end; t += t_step) {
+        const TileInfo ti = decode(t);
         const int k_begin = ti.split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
@@ -196,8 +232,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_base = a_base + Cfg::kABytes;
+          const uint32_t a_base = smem_u32(smem_ring + stage * Cfg::kStageBytes);
+          const uint32_t b_base = BSTAT ? smem_u32(smem + kb * Cfg::kBBytes) : a_base + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // K-major: 8-row groups are 1024 B apart (SBO); a k-step is 32 B inside the swizzled 128 B row.
@@ -230,14 +266,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tid = ew * 32 + lane;
     Epi epi(ep, epi_smem, ew, BLOCK_N);
     uint32_t acc = 0, acc_phase = 0;
-    if (Epi::kColVecs > 0 && static_cast<int>(blockIdx.x) < num_tiles)
-      epi.colvec_fetch(p, decode_tile(p, blockIdx.x, BLOCK_N), tid);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(p, t, BLOCK_N);
+    if (Epi::kColVecs > 0 && t_first < t_end) epi.colvec_fetch(p, decode(t_first), tid);
+    for (int t = t_first; t < t_end; t += t_step) {
+      const TileInfo ti = decode(t);
       if (Epi::kColVecs > 0) {
         epi.colvec_commit(acc, tid);
         epi_bar_sync(EW * 32);
-        if (t + static_cast<int>(gridDim.x) < num_tiles) epi.colvec_fetch(p, decode_tile(p, t + gridDim.x, BLOCK_N), tid);
+        if (t + t_step < t_end) epi.colvec_fetch(p, decode(t + t_step), tid);
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();

@@ -223,7 +223,11 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   e1.mask_words = pl.mask;
   e1.hw = pl.hw; e1.words = pl.words;
   if (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
-  SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
+  if (C <= 256 && pl.tn_f <= h->sms) {
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc (B-stationary)");
+  } else {
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
+  }
   prof_mark(h, st, 2);
   // G2 decoder
   EpiDec::Params e2{};
@@ -240,7 +244,11 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
-  SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
+  if (C <= 256 && pl.tn_f <= h->sms) {
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPre, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE (B-stationary)");
+  } else {
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
+  }
   prof_mark(h, st, 5);
   // G4 / G5 weight gradients, split-K over tokens
   const size_t FC = static_cast<size_t>(F) * C;

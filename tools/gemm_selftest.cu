@@ -39,6 +39,7 @@ struct Case {
   int bn;
   int splits;  // 0 = auto, 1 = none
   bool bf16_out = false;  // bf16 output through the TMA slab store (K must keep |sums| <= 256 so bf16 is exact)
+  bool bstat = false;     // B-stationary schedule (K <= 256)
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -70,7 +71,8 @@ static int run(const Case& c) {
     ep.out = dC; ep.ld = c.N; ep.alpha = 1.0f; ep.out_bf16 = 1;
     if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
     else { printf("[%s] store tensor map failed\n", c.name); return 1; }
-    rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+    if (c.bstat) rc = launch_gemm<BN, AMN, BMN, EpiStore, true>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+    else rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
    } else { printf("[%s] bf16 slab output needs BLOCK_N=256\n", c.name); return 1; }
   } else {
     EpiPartial::Params ep{dC, c.N, (long long)c.M * c.N};
@@ -144,6 +146,9 @@ static const Case kCases[] = {
     {"kk_bf16_tma_ntail", 200, 200, 24, false, false, 256, 1, true},
     {"kk_bf16_tma_n96", 130, 96, 16, false, false, 256, 1, true},
     {"kk_bf16_tma_many", 128 * 300 + 40, 512, 16, false, false, 256, 1, true},
+    {"kk_bstat", 128 * 300 + 40, 512, 16, false, false, 256, 1, true, true},
+    {"kk_bstat_k24_ntail", 5000, 200, 24, false, false, 256, 1, true, true},
+    {"kmn_bstat", 3000, 768, 16, false, true, 256, 1, true, true},
 };
 
 static int perf() {
@@ -176,6 +181,16 @@ static int perf() {
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
   printf("[perf enc] %.3f ms  %.1f TFLOP/s  out %.1f GB/s\n", ms, 2.0 * M * N * K / ms * 1e-9,
+         (double)M * N * 2 / ms * 1e-6);
+  for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiStore, true>(0, dA, K, dB, K, M, N, K, 1, ep);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int it = 0; it < iters; ++it) launch_gemm<256, false, false, EpiStore, true>(0, dA, K, dB, K, M, N, K, 1, ep);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("[perf enc B-stationary] %.3f ms  %.1f TFLOP/s  out %.1f GB/s\n", ms, 2.0 * M * N * K / ms * 1e-9,
          (double)M * N * 2 / ms * 1e-6);
   // split-K weight-gradient shape: dW_dec[C,F] = diff^T[C,T] e[T,F]
   {
@@ -225,11 +240,11 @@ static int perf_enc_variants() {
     if (variant == 1 || variant == 4) ep.act_bits = dact;
     if (variant == 2 || variant == 4) ep.mask_words = dmask;
     if (variant == 3 || variant == 4) ep.l1_partial = dl1;
-    for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiEnc>(0, dA, K, dB, K, M, N, K, 1, ep);
+    for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiEnc, true>(0, dA, K, dB, K, M, N, K, 1, ep);
     CK(cudaDeviceSynchronize());
     const int iters = 10;
     cudaEventRecord(e0);
-    for (int it = 0; it < iters; ++it) launch_gemm<256, false, false, EpiEnc>(0, dA, K, dB, K, M, N, K, 1, ep);
+    for (int it = 0; it < iters; ++it) launch_gemm<256, false, false, EpiEnc, true>(0, dA, K, dB, K, M, N, K, 1, ep);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
