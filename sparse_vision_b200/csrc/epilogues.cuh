@@ -263,6 +263,8 @@ struct EpiEnc {
   }
   __device__ void colvec_commit(uint32_t parity, int tid) {
     float* dst = cv_base + parity * 256;
+#pragma unroll
+    for (int i = 0; i < decltype(stage)::kPer; ++i) stage.r[i] = 0.f - stage.r[i];  // stage -bias' (+0 stays +0)
     stage.commit(dst, tid);
     cv = dst;
   }
@@ -275,13 +277,17 @@ struct EpiEnc {
                         int lane) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
-    float b[32];
-    lds_row_f32(cv + (col0 - ti.n0), b);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += b[j];
+    float nb[32];
+    lds_row_f32(cv + (col0 - ti.n0), nb);  // -bias'
     const long long off = static_cast<long long>(row) * g.N + col0;
-    if (p.pre_f32 && row_ok) store_row_f32(p.pre_f32 + off, v, nvalid);
-    // four independent chains (8 columns each) for the mask bits and the partial sums
+    if (p.pre_f32) {                       // API forward only: materialise pre = acc + bias'
+      float pre[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pre[j] = v[j] - nb[j];
+      if (row_ok) store_row_f32(p.pre_f32 + off, pre, nvalid);
+    }
+    // t = (-bias') - acc = -pre: its sign bit is set exactly when pre > 0 (pre == +-0 gives +0), e = max(-t, 0).
+    // Four independent chains (8 columns each) for the mask bits and the partial sums.
     uint32_t wq4[4] = {0, 0, 0, 0};
     float sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -289,9 +295,9 @@ struct EpiEnc {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = q * 8 + j;
-        // sign bit of (0 - pre) is set exactly when pre > 0; funnel it into the byte MSB-first
-        wq4[q] = __funnelshift_l(__float_as_uint(0.f - v[i]), wq4[q], 1);
-        v[i] = fmaxf(v[i], 0.f);
+        const float t = nb[i] - v[i];
+        wq4[q] = __funnelshift_l(__float_as_uint(t), wq4[q], 1);
+        v[i] = fmaxf(-t, 0.f);
         sq4[q] += v[i];
       }
     }
@@ -490,7 +496,7 @@ struct EpiDPre {
     for (int i = 0; i < 4; ++i)
       if (i == c) word = words[i];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] + p.l1c : 0.f;
+    for (int j = 0; j < 32; ++j) v[j] = (word & (1u << j)) ? v[j] + p.l1c : 0.f;
     const int half = c & 1;
     slab.put(half, lane, v);
     if (half == 1) slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);

@@ -46,11 +46,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, P1;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): sleep in hardware, not in the issue slots
       : "memory");
   return ok != 0;
 }
