@@ -237,7 +237,7 @@ struct EpiEnc {
     float* pre_f32;                // [M,N] or null
     uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
     uint32_t* act_bits;            // [n_img, words] or null
-    float* l1_partial;             // [tiles_m*tiles_n*kWarps] or null
+    float* l1_partial;             // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
   };
@@ -249,11 +249,11 @@ struct EpiEnc {
   ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
-  float sum;
+  float sum, total;
   uint32_t words[4];
   int ew, cpw, c_first;  // chunks per warp, this warp's first 32-column chunk inside the tile
   __device__ EpiEnc(const Params& p_, uint8_t* smem, int ew_, int block_n)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f), ew(ew_),
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
         cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
     slab.init(smem, ew_);
   }
@@ -352,12 +352,15 @@ struct EpiEnc {
         }
       }
     }
+    if (row < g.M) total += sum;  // rows >= M hold relu(bias'), not data
+  }
+  __device__ void finish(int, int lane) {
+    slab.drain(lane);
     if (p.l1_partial) {
-      const float s = warp_sum(row < g.M ? sum : 0.f);
-      if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
+      const float s = warp_sum(total);
+      if (lane == 0) p.l1_partial[static_cast<size_t>(blockIdx.x) * kWarps + ew] = s;
     }
   }
-  __device__ void finish(int, int lane) { slab.drain(lane); }
 };
 
 // ------------------------------------------------------------------------------------------------ decoder
@@ -372,7 +375,7 @@ struct EpiDec {
     __nv_bfloat16* d_bf16;            // [M,N] or null
     float* d_f32;                     // [M,N] or null
     __nv_bfloat16* diff_bf16;         // [M,N] or null
-    float* sq_partial;                // [tiles_m*tiles_n*kWarps] or null
+    float* sq_partial;                // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -382,7 +385,7 @@ struct EpiDec {
   ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
-  float sq;
+  float sq;  // running over all tiles of this CTA (rows >= M and columns >= N never enter it)
   int ew;
   __device__ EpiDec(const Params& p_, uint8_t* smem, int ew_, int)
       : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps))), cv(cv_base), sq(0.f),
@@ -399,7 +402,7 @@ struct EpiDec {
     stage.commit(dst, tid);
     cv = dst;
   }
-  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sq = 0.f; }
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
                         int lane) {
     const int nvalid = min(32, g.N - col0);
@@ -433,12 +436,14 @@ struct EpiDec {
     const int last = ((g.N - 1) >> 6) << 6;
     if (slab_d.half_pending) slab_d.flush(&p.tm_d, last, ti.m0 + wq * 32, lane);
     if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane);
+  }
+  __device__ void finish(int, int lane) {
+    slab_d.drain(lane);
     if (p.sq_partial) {
       const float s = warp_sum(sq);
-      if (lane == 0) p.sq_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
+      if (lane == 0) p.sq_partial[static_cast<size_t>(blockIdx.x) * kWarps + ew] = s;
     }
   }
-  __device__ void finish(int, int lane) { slab_d.drain(lane); }
 };
 
 // ------------------------------------------------------------------------------------------------ dE -> dPre
@@ -451,9 +456,12 @@ struct EpiDPre {
   struct Params {
     alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
     const uint32_t* mask_words;        // [M, words]
-    float* colsum_partial;             // [tiles_m * 4 lane quarters, N]: one row per 32 tokens
+    float* colsum_partial;             // per_cta == 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens;
+                                       // per_cta == 1 (B-stationary launch: a CTA keeps ONE N tile): [groups * 4, N],
+                                       //   group = blockIdx.x / tiles_n, summed over all M tiles the CTA walks
     float l1c;
     int words;
+    int per_cta;
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 0;
@@ -461,11 +469,14 @@ struct EpiDPre {
   const Params& p;
   SlabWriter1 slab;
   uint32_t words[4];
-  int ew, cpw, c_first, block_n;
+  float csacc[4];  // per_cta: lane j holds the running sum of column (chunk c, j) over this CTA's tiles
+  int ew, cpw, c_first, block_n, n0_last, tiles_n_last, N_last;
   __device__ EpiDPre(const Params& p_, uint8_t* smem, int ew_, int block_n_)
       : p(p_), ew(ew_), cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
-        block_n(block_n_) {
+        block_n(block_n_), n0_last(-1), tiles_n_last(1), N_last(0) {
     slab.init(smem, ew_);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csacc[i] = 0.f;
   }
   __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
   __device__ void colvec_commit(uint32_t, int) {}
@@ -502,12 +513,29 @@ struct EpiDPre {
     if (half == 1) slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
     // column sums over this warp's 32 tokens: lane j ends up with column col0 + j (one coalesced 128-byte store)
     const float cs = warp_colsum32(v, lane);
-    if (col0 + lane < g.N) p.colsum_partial[(static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col0 + lane] = cs;
+    if (p.per_cta) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i == c) csacc[i] += cs;
+    } else if (col0 + lane < g.N) {
+      p.colsum_partial[(static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col0 + lane] = cs;
+    }
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
+    n0_last = ti.n0; tiles_n_last = g.tiles_n; N_last = g.N;
   }
-  __device__ void finish(int, int lane) { slab.drain(lane); }
+  __device__ void finish(int wq, int lane) {
+    slab.drain(lane);
+    if (p.per_cta && n0_last >= 0) {
+      const size_t rowp = static_cast<size_t>(blockIdx.x / tiles_n_last) * 4 + wq;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = n0_last + (c_first + i) * 32 + lane;
+        if (i < cpw && col < N_last) p.colsum_partial[rowp * N_last + col] = csacc[i];
+      }
+    }
+  }
 };
 
 }  // namespace svb

@@ -22,7 +22,7 @@ struct EpiGatedEnc {
     __nv_bfloat16* rp_bf16;
     float* rp_f32;
     uint32_t* act_bits;
-    float* l1_partial;
+    float* l1_partial;  // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
     int hw, words;
   };
   static constexpr int kWarps = 8;
@@ -32,10 +32,10 @@ struct EpiGatedEnc {
   ColVecStage<4, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
-  float sum;
+  float sum, total;
   int ew;
   __device__ EpiGatedEnc(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(cv_base), sum(0.f), ew(ew_) {}
+      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(cv_base), sum(0.f), total(0.f), ew(ew_) {}
   __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
     stage.fetch(src, ti.n0, g.N, tid);
@@ -77,12 +77,14 @@ struct EpiGatedEnc {
     }
     if (p.act_bits) publish_activity(p.act_bits, p.words, col0 >> 5, word, row, g.M, p.hw, ti.m0 + wq * 32, lane);
   }
-  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
-    if (!p.l1_partial) return;
-    const float s = warp_sum(row < g.M ? sum : 0.f);
-    if (lane == 0) p.l1_partial[(static_cast<size_t>(ti.tile_m) * g.tiles_n + ti.tile_n) * kWarps + ew] = s;
+  __device__ void end_tile(const GemmProblem& g, const TileInfo&, int row, int, int) {
+    if (row < g.M) total += sum;
   }
-  __device__ void finish(int, int) {}
+  __device__ void finish(int, int lane) {
+    if (!p.l1_partial) return;
+    const float s = warp_sum(total);
+    if (lane == 0) p.l1_partial[static_cast<size_t>(blockIdx.x) * kWarps + ew] = s;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ gated dE

@@ -66,7 +66,8 @@ inline int device_sm_count() {
 // Returns 0 or a negative svb error code; *splits_out receives the number of split-K slices used.
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0) {
+                int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0,
+                unsigned long long a_policy = 0) {
   using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
@@ -80,6 +81,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
 
   GemmProblem p;
   p.M = M; p.N = N; p.K = K;
+  p.a_policy = a_policy;
   p.tiles_m = (M + kBlockM - 1) / kBlockM;
   p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int kblocks = (K + kBlockK - 1) / kBlockK;

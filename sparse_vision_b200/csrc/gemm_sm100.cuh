@@ -31,6 +31,7 @@ struct GemmProblem {
   int k_splits;     // >= 1; every split is non-empty
   int k_per_split;  // multiple of kBlockK
   int tiles_m, tiles_n;
+  unsigned long long a_policy = 0, b_policy = 0;  // L2 eviction policy of the operand loads (0 = default)
 };
 
 struct TileInfo {
@@ -93,6 +94,10 @@ struct ColVecStage {
     }
   }
 };
+
+// Epilogues may define `static constexpr bool kSkipAccLoad = true` (bring-up probes only) to skip the TMEM read.
+template <class E, class = void> struct epi_skips_acc_load { static constexpr bool value = false; };
+template <class E> struct epi_skips_acc_load<E, decltype(void(E::kSkipAccLoad))> { static constexpr bool value = E::kSkipAccLoad; };
 
 __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
   TileInfo ti;
@@ -203,7 +208,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = k_begin + kb * kBlockK;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, ti.m0);
+            if (p.a_policy) tma_load_2d_hint(sa, &tmA, &full_bar[stage], k0, ti.m0, p.a_policy);
+            else tma_load_2d(sa, &tmA, &full_bar[stage], k0, ti.m0);
           } else {
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.m0 + 64 * j, k0);
@@ -284,8 +290,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = ti.n0 + c * 32;
         if (col0 >= p.N) break;
         float v[32];
-        tmem_ld_32x32(t_addr + c * 32, v);
-        tmem_ld_wait();
+        if constexpr (!epi_skips_acc_load<Epi>::value) {
+          tmem_ld_32x32(t_addr + c * 32, v);
+          tmem_ld_wait();
+        }
         epi.chunk(p, ti, row, col0, v, wq, lane);
       }
       tc_fence_before();

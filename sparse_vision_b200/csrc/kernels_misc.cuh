@@ -33,25 +33,6 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats 
 }
 
 // ------------------------------------------------------------------------------------------------ layout
-// NCHW [B,C,HW] -> tokens [B*HW, C] (bf16), 32x32 smem transpose; sae_mlp.py:44 'b c h w -> (b h w) c'.
-template <typename TIn>
-static __global__ void pack_nchw_to_tokens_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z;
-  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  const TIn* xb = x + static_cast<size_t>(b) * C * HW;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && p < HW) ? to_f32<TIn>(xb[static_cast<size_t>(c) * HW + p]) : 0.f;
-  }
-  __syncthreads();
-  bf16* ob = out + static_cast<size_t>(b) * HW * C;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int p = p0 + i, c = c0 + threadIdx.x;
-    if (p < HW && c < C) ob[static_cast<size_t>(p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-  }
-}
-
 // tokens [B*HW, C] -> NCHW [B,C,HW]; utils.py:2478 '(b h w) c -> b c h w'.
 template <typename TIn, typename TOut>
 static __global__ void unpack_tokens_to_nchw_kernel(const TIn* __restrict__ tok, TOut* __restrict__ out, int C, int HW) {
@@ -71,34 +52,7 @@ static __global__ void unpack_tokens_to_nchw_kernel(const TIn* __restrict__ tok,
   }
 }
 
-// Fast paths for HW % 8 == 0 and C % 8 == 0: 64 x 64 tiles, 16-byte global accesses on both sides, bf16 staged in
-// shared memory with a 2-element row pad (conflict-free column gathers).
-// NCHW bf16 [B,C,HW] -> tokens [B*HW, C] bf16.    grid (ceil(HW/64), ceil(C/64), B), 256 threads.
-static __global__ void __launch_bounds__(256)
-pack_nchw_bf16_fast_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
-  __shared__ uint16_t tile[64][66];  // [c][hw]
-  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
-  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + static_cast<size_t>(b) * C * HW;
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
-    const int c = i >> 3, po = (i & 7) * 8;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (c0 + c < C && p0 + po < HW) q = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(c0 + c) * HW + p0 + po));
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[c][po]);
-    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
-  }
-  __syncthreads();
-  uint16_t* ob = reinterpret_cast<uint16_t*>(out) + static_cast<size_t>(b) * HW * C;
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
-    const int p = i >> 3, co = (i & 7) * 8;
-    if (p0 + p < HW && c0 + co < C) {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        w[k] = static_cast<uint32_t>(tile[co + 2 * k][p]) | (static_cast<uint32_t>(tile[co + 2 * k + 1][p]) << 16);
-      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(p0 + p) * C + c0 + co) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-}
+// Fast path for HW % 8 == 0 and C % 8 == 0: 64 x 64 tiles, 16-byte global accesses on both sides.
 // tokens [B*HW, C] bf16 -> NCHW bf16 [B,C,HW].
 static __global__ void __launch_bounds__(256)
 unpack_tokens_bf16_fast_kernel(const bf16* __restrict__ tok, bf16* __restrict__ out, int C, int HW) {
@@ -122,6 +76,205 @@ unpack_tokens_bf16_fast_kernel(const bf16* __restrict__ tok, bf16* __restrict__ 
       for (int k = 0; k < 4; ++k)
         w[k] = static_cast<uint32_t>(tile[po + 2 * k][c]) | (static_cast<uint32_t>(tile[po + 2 * k + 1][c]) << 16);
       *reinterpret_cast<uint4*>(ob + static_cast<size_t>(c0 + c) * HW + p0 + po) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// ---- 64 x 64 tile movers between NCHW and token-major ------------------------------------------------------------
+// 8 consecutive spatial positions of one channel row, read / written with the widest access the row pitch allows:
+// VEC = 8 (HW % 8 == 0), 4 (HW % 4 == 0) or 1 elements per access.  nv = number of valid positions (0..8).
+template <typename T, int VEC> struct Row8;
+template <int VEC> struct Row8<bf16, VEC> {
+  static __device__ __forceinline__ void load(const bf16* p, int nv, float (&o)[8]) {
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    if (VEC == 8) {
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (nv > 0) w = __ldg(reinterpret_cast<const uint4*>(q));
+      o[0] = bf16lo(w.x); o[1] = bf16hi(w.x); o[2] = bf16lo(w.y); o[3] = bf16hi(w.y);
+      o[4] = bf16lo(w.z); o[5] = bf16hi(w.z); o[6] = bf16lo(w.w); o[7] = bf16hi(w.w);
+    } else if (VEC == 4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint2 w = make_uint2(0, 0);
+        if (nv > 4 * h) w = __ldg(reinterpret_cast<const uint2*>(q + 4 * h));
+        o[4 * h] = bf16lo(w.x); o[4 * h + 1] = bf16hi(w.x); o[4 * h + 2] = bf16lo(w.y); o[4 * h + 3] = bf16hi(w.y);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = j < nv ? __uint_as_float(static_cast<uint32_t>(__ldg(q + j)) << 16) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, int nv, const float (&v)[8]) {
+    uint16_t* q = reinterpret_cast<uint16_t*>(p);
+    if (VEC == 8) {
+      if (nv > 0)
+        *reinterpret_cast<uint4*>(q) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    } else if (VEC == 4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (nv > 4 * h)
+          *reinterpret_cast<uint2*>(q + 4 * h) = make_uint2(pack_bf16x2(v[4 * h], v[4 * h + 1]), pack_bf16x2(v[4 * h + 2], v[4 * h + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) p[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+};
+template <int VEC> struct Row8<float, VEC> {
+  static __device__ __forceinline__ void load(const float* p, int nv, float (&o)[8]) {
+    if (VEC >= 4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nv > 4 * h) w = __ldg(reinterpret_cast<const float4*>(p + 4 * h));
+        o[4 * h] = w.x; o[4 * h + 1] = w.y; o[4 * h + 2] = w.z; o[4 * h + 3] = w.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = j < nv ? __ldg(p + j) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ void store(float* p, int nv, const float (&v)[8]) {
+    if (VEC >= 4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (nv > 4 * h) *reinterpret_cast<float4*>(p + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) p[j] = v[j];
+    }
+  }
+};
+
+// NCHW [B,C,HW] (bf16 or fp32) -> bf16 tokens [B*HW, C]; sae_mlp.py:44 'b c h w -> (b h w) c'.
+// grid (ceil(HW/64), ceil(C/64), B), 256 threads; bf16 staged in smem with a 2-element row pad.
+template <typename TIn, int VEC>
+static __global__ void __launch_bounds__(256)
+pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
+  __shared__ uint16_t tile[64][66];  // [c][hw]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const TIn* xb = x + static_cast<size_t>(b) * C * HW;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int c = i >> 3, po = (i & 7) * 8;
+    float v[8];
+    const int nv = (c0 + c < C) ? max(0, min(8, HW - (p0 + po))) : 0;
+    Row8<TIn, VEC>::load(xb + static_cast<size_t>(c0 + c) * HW + p0 + po, nv, v);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[c][po]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+  }
+  __syncthreads();
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out) + static_cast<size_t>(b) * HW * C;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int p = i >> 3, co = (i & 7) * 8;
+    if (p0 + p < HW && c0 + co < C) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = static_cast<uint32_t>(tile[co + 2 * k][p]) | (static_cast<uint32_t>(tile[co + 2 * k + 1][p]) << 16);
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(p0 + p) * C + c0 + co) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// Fused "after the decoder" pass for NCHW inputs: ONE sweep over d (token-major bf16) and x (NCHW) that
+//   * writes d back in NCHW (what the hook returns, model_pipeline.py:425,432; utils.py:2478) when d_out != null, and
+//   * accumulates, per image and channel, sum x, sum x^2, sum d, sum d^2, sum (d-x), sum (d-x)^2, min x, max x
+//     (variance_explained utils.py:2012-2030, compute_rmse_nrmse sparse_loss.py:4-21, db_dec).
+// x is rounded to bf16 first, like the GEMM operand.  st layout: [b][chunk][8][C] (the channel_stats layout).
+// grid (ceil(C/64), B, chunks), 256 threads: a block walks tiles_per_chunk HW tiles of its 64 channels; thread i owns
+// channel (i>>3) [+32] and 8 consecutive positions per tile, so the statistics stay in registers until the end.
+template <typename TIn, typename TOut, int VEC>
+static __global__ void __launch_bounds__(256, 3)
+post_dec_nchw_kernel(const bf16* __restrict__ d_tok, const TIn* __restrict__ x, TOut* __restrict__ d_out,
+                     float* __restrict__ st, int C, int HW, int tiles_per_chunk) {
+  __shared__ uint16_t tile[64][66];  // [hw][c]
+  const int b = blockIdx.y, c0 = blockIdx.x * 64, rc = blockIdx.z, R = gridDim.z;
+  const uint16_t* tb = reinterpret_cast<const uint16_t*>(d_tok) + static_cast<size_t>(b) * HW * C;
+  const TIn* xb = x + static_cast<size_t>(b) * C * HW;
+  TOut* ob = d_out ? d_out + static_cast<size_t>(b) * C * HW : nullptr;
+  const int p_begin = rc * tiles_per_chunk * 64, p_end = min(HW, p_begin + tiles_per_chunk * 64);
+  float a[2][8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a[k][q] = 0.f;
+    a[k][6] = INFINITY;
+    a[k][7] = -INFINITY;
+  }
+  // Both streams of a tile (16 bytes of d and 8 positions of x per thread and half) are fetched one tile ahead.
+  uint4 dq[2];
+  float xv[2][8];
+  int nv[2];
+  auto fetch = [&](int p0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int p = i >> 3, co = (i & 7) * 8;
+      dq[k] = make_uint4(0, 0, 0, 0);
+      if (p0 + p < p_end && c0 + co < C) dq[k] = __ldg(reinterpret_cast<const uint4*>(tb + static_cast<size_t>(p0 + p) * C + c0 + co));
+      const int c = i >> 3, po = (i & 7) * 8;
+      nv[k] = (c0 + c < C) ? max(0, min(8, p_end - (p0 + po))) : 0;
+      Row8<TIn, VEC>::load(xb + static_cast<size_t>(c0 + c) * HW + p0 + po, nv[k], xv[k]);
+    }
+  };
+  if (p_begin < p_end) fetch(p_begin);
+  for (int p0 = p_begin; p0 < p_end; p0 += 64) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[i >> 3][(i & 7) * 8]);
+      dst[0] = dq[k].x; dst[1] = dq[k].y; dst[2] = dq[k].z; dst[3] = dq[k].w;
+    }
+    float xc[2][8];
+    int nc[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      nc[k] = nv[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xc[k][j] = xv[k][j];
+    }
+    if (p0 + 64 < p_end) fetch(p0 + 64);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int c = i >> 3, po = (i & 7) * 8;
+      if (nc[k] == 0) continue;
+      float dv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(static_cast<uint32_t>(tile[po + j][c]) << 16);
+      if (ob) Row8<TOut, VEC>::store(ob + static_cast<size_t>(c0 + c) * HW + p0 + po, nc[k], dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nc[k]) {
+          const float xr = sizeof(TIn) == 2 ? xc[k][j] : __bfloat162float(__float2bfloat16_rn(xc[k][j]));
+          const float f = dv[j] - xr;
+          a[k][0] += xr; a[k][1] += xr * xr;
+          a[k][2] += dv[j]; a[k][3] += dv[j] * dv[j];
+          a[k][4] += f; a[k][5] += f * f;
+          a[k][6] = fminf(a[k][6], xr); a[k][7] = fmaxf(a[k][7], xr);
+        }
+      }
+    }
+  }
+  // the 8 lanes that share a channel combine in a fixed (butterfly) order
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = a[k][q];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const float u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = q < 6 ? v + u : (q == 6 ? fminf(v, u) : fmaxf(v, u));
+      }
+      const int c = c0 + (threadIdx.x >> 3) + 32 * k;
+      if ((threadIdx.x & 7) == 0 && c < C) st[((static_cast<size_t>(b) * R + rc) * 8 + q) * C + c] = v;
     }
   }
 }
@@ -479,6 +632,235 @@ static __global__ void bdec_grad_kernel(const float* __restrict__ dsum, const fl
   out[c] = (dsum[c] - a) * scale;
 }
 
+// ------------------------------------------------------------------------------------------------ merged step kernels
+// The small kernels around the GEMMs are launch-latency bound, so independent pieces share one launch: a block
+// picks its job from its index ("roles").  Nothing here synchronises across blocks.
+
+// Step prologue: bf16 shadow + folded bias of the encoder weight (role 0, one warp per row, see
+// prep_encoder_kernel), bf16 shadow of the decoder weight (role 1), zeroing of the per-step accumulators (role 2)
+// and, for the gated SAE, exp(r_mag) (role 3).
+struct PrepArgs {
+  const float* w_enc; const float* b_enc; const float* b_dec; bf16* w_enc_bf16; float* fold; float* dotw;
+  const float* w_dec; bf16* w_dec_bf16;
+  uint32_t* zero; unsigned long long n_zero;
+  const float* r_mag; float* exp_r;
+  int F, C;
+  int nb_enc, nb_dec, nb_zero, nb_exp;
+};
+static __global__ void __launch_bounds__(256) prep_step_kernel(const PrepArgs a) {
+  int blk = blockIdx.x;
+  if (blk < a.nb_enc) {
+    const int f = blk * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= a.F) return;
+    float acc = 0.f;
+    for (int c = lane; c < a.C; c += 32) {
+      const bf16 q = __float2bfloat16_rn(a.w_enc[static_cast<size_t>(f) * a.C + c]);
+      a.w_enc_bf16[static_cast<size_t>(f) * a.C + c] = q;
+      acc += __bfloat162float(q) * a.b_dec[c];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (a.fold) a.fold[f] = (a.b_enc ? a.b_enc[f] : 0.f) - acc;
+      if (a.dotw) a.dotw[f] = acc;
+    }
+    return;
+  }
+  blk -= a.nb_enc;
+  if (blk < a.nb_dec) {
+    const size_t n = static_cast<size_t>(a.F) * a.C;
+    for (size_t i = (static_cast<size_t>(blk) * 256 + threadIdx.x) * 4; i < n; i += static_cast<size_t>(a.nb_dec) * 1024) {
+      const float4 q = *reinterpret_cast<const float4*>(a.w_dec + i);  // F*C is a multiple of 64
+      *reinterpret_cast<uint2*>(a.w_dec_bf16 + i) = make_uint2(pack_bf16x2(q.x, q.y), pack_bf16x2(q.z, q.w));
+    }
+    return;
+  }
+  blk -= a.nb_dec;
+  if (blk < a.nb_zero) {
+    for (size_t i = static_cast<size_t>(blk) * 256 + threadIdx.x; i < a.n_zero; i += static_cast<size_t>(a.nb_zero) * 256)
+      a.zero[i] = 0u;
+    return;
+  }
+  blk -= a.nb_zero;
+  const int i = blk * 256 + threadIdx.x;
+  if (i < a.F) a.exp_r[i] = expf(a.r_mag[i]);
+}
+
+// Gradient assembly after the two weight-gradient GEMMs (see the formulas above sum_splits_kernel):
+//   role 0  g_wdec = s * sum_k P_wd[k]                       role 1  g_wenc = s * (sum_k P_we[k] - csum (x) b_dec)
+//   role 2  g_benc = s * csum   (skipped when null)           role 3  vm[chunk] = csum[chunk] . W_enc_bf16[chunk, :]
+//   role 4  activity count per unit                           role 5  active units per image
+struct AssembleArgs {
+  const float* P_wd; float* g_wdec; int s_wd;
+  const float* P_we; float* g_wenc; int s_we;
+  const float* csum; const float* b_dec; float* g_benc;
+  const bf16* w_enc_bf16; float* vm; int vm_chunks;
+  const uint32_t* act_bits; float* count; int32_t* n_active; float* nact_f; int n_img, words;
+  int F, C;
+  float s;
+  int nb_w, nb_b, nb_vm, nb_cnt, nb_img;
+};
+static __global__ void __launch_bounds__(256) assemble_grads_kernel(const AssembleArgs a) {
+  __shared__ int sh[8][33];
+  int blk = blockIdx.x;
+  const size_t n = static_cast<size_t>(a.F) * a.C;
+  if (blk < 2 * a.nb_w) {
+    const bool enc = blk >= a.nb_w;
+    if (enc) blk -= a.nb_w;
+    const float* part = enc ? a.P_we : a.P_wd;
+    const int splits = enc ? a.s_we : a.s_wd;
+    float* out = enc ? a.g_wenc : a.g_wdec;
+    for (size_t i = (static_cast<size_t>(blk) * 256 + threadIdx.x) * 4; i < n; i += static_cast<size_t>(a.nb_w) * 1024) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < splits; ++k) {
+        const float4 q = *reinterpret_cast<const float4*>(part + static_cast<size_t>(k) * n + i);
+        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+      }
+      if (enc) {  // C % 8 == 0: the four elements share the row f
+        const int f = static_cast<int>(i / a.C), c = static_cast<int>(i % a.C);
+        const float cs = a.csum[f];
+        const float4 b = *reinterpret_cast<const float4*>(a.b_dec + c);
+        acc.x -= cs * b.x; acc.y -= cs * b.y; acc.z -= cs * b.z; acc.w -= cs * b.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = make_float4(acc.x * a.s, acc.y * a.s, acc.z * a.s, acc.w * a.s);
+    }
+    return;
+  }
+  blk -= 2 * a.nb_w;
+  if (blk < a.nb_b) {
+    const int f = blk * 256 + threadIdx.x;
+    if (a.g_benc && f < a.F) a.g_benc[f] = a.csum[f] * a.s;
+    return;
+  }
+  blk -= a.nb_b;
+  if (blk < a.nb_vm) {
+    const int cblocks = (a.C + 255) / 256;
+    const int chunk = blk / cblocks, c = (blk % cblocks) * 256 + threadIdx.x;
+    const int per = (a.F + a.vm_chunks - 1) / a.vm_chunks;
+    const int f0 = chunk * per, f1 = min(a.F, f0 + per);
+    if (c >= a.C) return;
+    float acc = 0.f;
+    for (int f = f0; f < f1; ++f) acc += a.csum[f] * __bfloat162float(a.w_enc_bf16[static_cast<size_t>(f) * a.C + c]);
+    a.vm[static_cast<size_t>(chunk) * a.C + c] = acc;
+    return;
+  }
+  blk -= a.nb_vm;
+  if (blk < a.nb_cnt) {  // utils.py:2047-2056: number of images in which unit f fired
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    int acc = 0;
+    for (int b = g; b < a.n_img; b += 8) acc += (a.act_bits[static_cast<size_t>(b) * a.words + blk] >> lane) & 1u;
+    sh[g][lane] = acc;
+    __syncthreads();
+    if (g == 0) {
+      int t = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sh[k][lane];
+      const int f = blk * 32 + lane;
+      if (f < a.F) a.count[f] = static_cast<float>(t);
+    }
+    return;
+  }
+  blk -= a.nb_cnt;
+  {  // utils.py:2063-2067: active units per image
+    const int b = blk * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= a.n_img) return;
+    int acc = 0;
+    for (int w = lane; w < a.words; w += 32) acc += __popc(a.act_bits[static_cast<size_t>(b) * a.words + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (a.n_active) a.n_active[b] = acc;
+      a.nact_f[b] = static_cast<float>(acc);
+    }
+  }
+}
+
+// Last kernel of the gradient half (ONE block): decoder-bias gradient, the loss partial sums and the per-channel
+// statistics go into the flat reduction buffer.  sums section: [0] sum (d-x)^2, [1] sum |enc|, [2] sum aux^2,
+// [3] sum Var(x), [4] sum Var(d), [5] sum active units, [6..7] zero.
+struct TailArgs {
+  const float* chan;  // [4][C]: sum diff, sum diff^2, min x, max x
+  const float* vm; int vm_chunks; float* g_bdec; float s;
+  const float* sq_part; int n_sq;
+  const float* l1_part; int n_l1;
+  const float* aux_part; int n_aux;  // null: no aux term
+  const float* nact_f; int n_img;
+  const float* var_part; int n_var_part; const float* rowvar; long long n_rows;
+  float* flat; unsigned long long o_sums, o_chansq, o_max;
+  int C;
+};
+static __global__ void __launch_bounds__(1024) grads_tail_kernel(const TailArgs a) {
+  __shared__ float sh[32];
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < a.vm_chunks; ++k) acc += a.vm[static_cast<size_t>(k) * a.C + c];
+    a.g_bdec[c] = (a.chan[c] - acc) * a.s;
+    a.flat[a.o_chansq + c] = a.chan[a.C + c];
+    a.flat[a.o_max + c] = a.chan[3 * a.C + c];
+    a.flat[a.o_max + a.C + c] = -a.chan[2 * a.C + c];
+  }
+  auto total = [&](const float* p, long long n, long long stride, long long off) {
+    float acc = 0.f;
+    if (p)
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += p[i * stride + off];
+    return block_sum(acc, sh);
+  };
+  const float sq = total(a.sq_part, a.n_sq, 1, 0);
+  const float l1 = total(a.l1_part, a.n_l1, 1, 0);
+  const float aux = total(a.aux_part, a.n_aux, 1, 0);
+  const float na = total(a.nact_f, a.n_img, 1, 0);
+  const float vx = a.n_rows > 0 ? total(a.rowvar, a.n_rows, 2, 0) : total(a.var_part, a.n_var_part, 2, 0);
+  const float vd = a.n_rows > 0 ? total(a.rowvar, a.n_rows, 2, 1) : total(a.var_part, a.n_var_part, 2, 1);
+  if (threadIdx.x == 0) {
+    float* o = a.flat + a.o_sums;
+    o[0] = sq; o[1] = l1; o[2] = aux; o[3] = vx; o[4] = vd; o[5] = na; o[6] = 0.f; o[7] = 0.f;
+  }
+}
+
+// Step epilogue (ONE block, after any data-parallel all-reduce of the flat buffer): scalars of the step
+// (utils.py:2470-2473, sparse_loss.py:4-21, utils.py:2012-2030,2063-2067) and the activity outputs
+// (utils.py:2047-2060).
+struct FinalizeArgs {
+  const float* flat; unsigned long long o_sums, o_chansq, o_max, o_count;
+  int C, F, expansion;
+  float T_g, B_g, lambda;
+  float* stats; uint8_t* dead; float* freq;
+};
+static __global__ void __launch_bounds__(1024) step_finalize_kernel(const FinalizeArgs a) {
+  __shared__ float sh[32];
+  float r = 0.f, nr = 0.f;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float rm = sqrtf(a.flat[a.o_chansq + c] / a.T_g);
+    const float range = a.flat[a.o_max + c] + a.flat[a.o_max + a.C + c];  // max - min
+    r += rm;
+    nr += rm / range;
+  }
+  const float rs = block_sum(r, sh);
+  const float nrs = block_sum(nr, sh);
+  float nd = 0.f;
+  for (int f = threadIdx.x; f < a.F; f += blockDim.x) {
+    const float c = a.flat[a.o_count + f];
+    const bool is_dead = c == 0.f;
+    if (a.dead) a.dead[f] = is_dead ? 1 : 0;
+    if (a.freq) a.freq[f] = 1.f - (a.B_g - c) / a.B_g;  // 1 - mean(inactive), evaluated like utils.py:2056
+    nd += is_dead ? 1.f : 0.f;
+  }
+  const float nds = block_sum(nd, sh);
+  if (threadIdx.x == 0 && a.stats) {
+    const float* o = a.flat + a.o_sums;
+    const float rec = o[0] / (a.T_g * a.C), l1 = o[1] / (a.T_g * a.F), aux = o[2] / (a.T_g * a.C);
+    a.stats[SVB_STAT_REC] = rec;
+    a.stats[SVB_STAT_L1] = l1;
+    a.stats[SVB_STAT_AUX] = aux;
+    a.stats[SVB_STAT_LOSS] = rec + a.lambda * l1 + aux;
+    a.stats[SVB_STAT_RMSE] = rs / a.C;
+    a.stats[SVB_STAT_NRMSE] = nrs / a.C;
+    a.stats[SVB_STAT_VAR_EXPL] = 1.f - o[4] / o[3];
+    a.stats[SVB_STAT_SPARSITY] = (o[5] / a.B_g) / (static_cast<float>(a.F) / a.expansion);
+    a.stats[SVB_STAT_N_DEAD] = nds;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ optimiser
 struct AdamCoef {
   float lr_over_bc1;    // lr / (1 - beta1^t)
@@ -503,37 +885,66 @@ static __global__ void adam_kernel(float* __restrict__ w, const float* __restric
     if (w_bf16) w_bf16[i] = __float2bfloat16_rn(wn);
   }
 }
+// Plain Adam over several tensors in ONE launch: segment i owns blocks [blk0[i], blk0[i+1]).
+struct AdamSeg { float* w; const float* g; float* m; float* v; unsigned long long n; };
+struct AdamMultiArgs {
+  AdamSeg seg[6];
+  int blk0[7];
+  int nseg;
+};
+static __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamMultiArgs a, const AdamCoef k) {
+  int sgi = 0;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (i < a.nseg && static_cast<int>(blockIdx.x) >= a.blk0[i]) sgi = i;
+  const AdamSeg sg = a.seg[sgi];
+  const int nb = a.blk0[sgi + 1] - a.blk0[sgi], lb = blockIdx.x - a.blk0[sgi];
+  for (size_t i = static_cast<size_t>(lb) * 256 + threadIdx.x; i < sg.n; i += static_cast<size_t>(nb) * 256) {
+    float mi = sg.m[i], vi = sg.v[i];
+    const float wn = adam_elem(sg.w[i], sg.g[i], mi, vi, k);
+    sg.w[i] = wn; sg.m[i] = mi; sg.v[i] = vi;
+  }
+}
+
 // ConstrainedAdam on decoder.weight [C,F] (utils.py:65-81): per column f
-//   w^ = w/|w|;  g' = g - (g.w^) w^;  Adam(g');  w /= |w|.      block = 32 columns x 8 row lanes.
-static __global__ void constrained_adam_decoder_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m,
-                                                float* __restrict__ v, int C, int F, AdamCoef k) {
-  __shared__ float s[8][33];
-  __shared__ float col_a[32], col_b[32];
-  const int lane = threadIdx.x & 31, gl = threadIdx.x >> 5;
-  const int f = blockIdx.x * 32 + lane;
+//   w^ = w/|w|;  g' = g - (g.w^) w^;  Adam(g');  w /= |w|.      block = 16 columns x 64 row lanes (1024 threads):
+// a warp covers two 64-byte row segments, and F/16 blocks keep most SMs busy for the three dependent passes.
+constexpr int kCadamCols = 16, kCadamRows = 64;
+static __global__ void __launch_bounds__(kCadamCols * kCadamRows)
+constrained_adam_decoder_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int C, int F, AdamCoef k) {
+  __shared__ float s[kCadamRows][kCadamCols + 1];
+  __shared__ float col_a[kCadamCols], col_b[kCadamCols];
+  const int cl = threadIdx.x % kCadamCols, gl = threadIdx.x / kCadamCols;
+  const int f = blockIdx.x * kCadamCols + cl;
   const bool ok = f < F;
+  auto colsum = [&](float val, float* dst) {  // fixed order over the row lanes
+    __syncthreads();
+    s[gl][cl] = val;
+    __syncthreads();
+    if (gl == 0) {
+      float t = 0.f;
+      for (int q = 0; q < kCadamRows; ++q) t += s[q][cl];
+      dst[cl] = t;
+    }
+    __syncthreads();
+  };
   // pass 1: |w|^2 and g.w
   float nw = 0.f, gw = 0.f;
   if (ok)
-    for (int c = gl; c < C; c += 8) {
+    for (int c = gl; c < C; c += kCadamRows) {
       const float wi = w[static_cast<size_t>(c) * F + f], gi = g[static_cast<size_t>(c) * F + f];
       nw += wi * wi;
       gw += gi * wi;
     }
-  s[gl][lane] = nw;
-  __syncthreads();
-  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_a[lane] = t; }
-  __syncthreads();
-  s[gl][lane] = gw;
-  __syncthreads();
-  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_b[lane] = t; }
-  __syncthreads();
-  const float norm = sqrtf(col_a[lane]);
-  const float proj = col_b[lane] / norm;  // g . w^
+  colsum(nw, col_a);
+  colsum(gw, col_b);
+  const float norm = sqrtf(col_a[cl]);
+  const float proj = col_b[cl] / norm;  // g . w^
   // pass 2: projected gradient (written back, as the reference mutates p.grad), Adam, new norm
   float nn = 0.f;
   if (ok)
-    for (int c = gl; c < C; c += 8) {
+    for (int c = gl; c < C; c += kCadamRows) {
       const size_t i = static_cast<size_t>(c) * F + f;
       const float wi = w[i];
       const float gp = g[i] - proj * (wi / norm);
@@ -543,14 +954,10 @@ static __global__ void constrained_adam_decoder_kernel(float* __restrict__ w, fl
       w[i] = wn; m[i] = mi; v[i] = vi;
       nn += wn * wn;
     }
-  __syncthreads();
-  s[gl][lane] = nn;
-  __syncthreads();
-  if (gl == 0) { float t = 0.f; for (int q = 0; q < 8; ++q) t += s[q][lane]; col_a[lane] = t; }
-  __syncthreads();
-  const float inv = 1.f / sqrtf(col_a[lane]);
+  colsum(nn, col_a);
+  const float inv = 1.f / sqrtf(col_a[cl]);
   if (ok)
-    for (int c = gl; c < C; c += 8) {
+    for (int c = gl; c < C; c += kCadamRows) {
       const size_t i = static_cast<size_t>(c) * F + f;
       w[i] *= inv;
     }

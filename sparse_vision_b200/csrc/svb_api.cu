@@ -97,9 +97,8 @@ extern "C" int svb_adam_step(svb_handle* h, void* stream, int32_t n_tensors, flo
     if (!grads[i]) continue;  // parameter without gradient: torch.optim.Adam skips it
     const size_t n = static_cast<size_t>(rows[i]) * cols[i];
     if (i == decoder_index && opt->optimizer == SVB_CONSTRAINED_ADAM) {
-      (constrained_adam_decoder_kernel<<<cdiv(cols[i], 32), 256, 0, st>>>(params[i], const_cast<float*>(grads[i]), m[i],
-                                                                        v[i], static_cast<int>(rows[i]),
-                                                                        static_cast<int>(cols[i]), k), svb::count_launch());
+      launch_cadam(st, params[i], const_cast<float*>(grads[i]), m[i], v[i], static_cast<int>(rows[i]),
+                   static_cast<int>(cols[i]), k);
     } else {
       (adam_kernel<<<grid_for(n), 256, 0, st>>>(params[i], grads[i], m[i], v[i], n, k, nullptr), svb::count_launch());
     }

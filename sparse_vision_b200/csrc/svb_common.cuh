@@ -145,6 +145,13 @@ inline bool acts_are_bf16_tokens(const svb_acts* x) {
   return x->dtype == SVB_BF16 && (x->layout == SVB_TOKENS || x->hw == 1) &&
          (reinterpret_cast<uintptr_t>(x->x) & 15) == 0;
 }
+// Widest per-row access (in elements) that an NCHW tensor with HW positions per row and base pointer p allows.
+inline int nchw_vec(const void* p, int hw, int elem_bytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if (hw % 8 == 0 && (a & 15) == 0) return 8;
+  if (hw % 4 == 0 && (a % (4 * elem_bytes)) == 0) return 4;
+  return 1;
+}
 inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
   const long long T = x->n_images * static_cast<long long>(x->hw);
   if (x->layout == SVB_TOKENS || x->hw == 1) {
@@ -154,15 +161,13 @@ inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
     else
       (convert_kernel<bf16, bf16><<<grid_for(n), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, n), svb::count_launch());
   } else {
-    dim3 grid(cdiv(x->hw, 32), cdiv(x->C, 32), static_cast<unsigned>(x->n_images));
-    dim3 block(32, 8);
     if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
-    if (x->dtype == SVB_F32)
-      (pack_nchw_to_tokens_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x->x), buf, x->C, x->hw), svb::count_launch());
-    else if (x->hw % 8 == 0 && (reinterpret_cast<uintptr_t>(x->x) & 15) == 0)
-      (pack_nchw_bf16_fast_kernel<<<dim3(cdiv(x->hw, 64), cdiv(x->C, 64), static_cast<unsigned>(x->n_images)), 256, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw), svb::count_launch());
-    else
-      (pack_nchw_to_tokens_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x->x), buf, x->C, x->hw), svb::count_launch());
+    const dim3 grid(cdiv(x->hw, 64), cdiv(x->C, 64), static_cast<unsigned>(x->n_images));
+    const int vec = nchw_vec(x->x, x->hw, x->dtype == SVB_F32 ? 4 : 2);
+#define SVB_PACK(T, V) (pack_nchw_tile_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x->x), buf, x->C, x->hw), svb::count_launch())
+    if (x->dtype == SVB_F32) { if (vec >= 4) SVB_PACK(float, 4); else SVB_PACK(float, 1); }
+    else { if (vec == 8) SVB_PACK(bf16, 8); else if (vec == 4) SVB_PACK(bf16, 4); else SVB_PACK(bf16, 1); }
+#undef SVB_PACK
   }
   SVB_LAUNCH_CHECK("pack_acts");
   return 0;
@@ -217,7 +222,9 @@ inline int reduce_rows(cudaStream_t st, const float* in, int R, int N, float sca
 constexpr int kStatRows = 392;
 inline size_t stats_elems(long long n_img, int hw, long long T, int C) {
   const long long imgs = hw > 1 ? n_img : 1, rows = hw > 1 ? hw : T;
-  return static_cast<size_t>(imgs) * cdiv(rows, kStatRows) * 8 * C;
+  const int chunks = cdiv(rows, kStatRows);
+  const int chunks64 = hw > 1 ? cdiv(hw, 64) : 1;  // post_dec_nchw_kernel may split down to one 64-position tile per chunk
+  return static_cast<size_t>(imgs) * (chunks > chunks64 ? chunks : chunks64) * 8 * C;
 }
 inline int run_channel_stats(cudaStream_t st, const bf16* X, const bf16* D, long long n_img, int hw, long long T,
                              int C, float* stbuf, float* chan, float* var_part, float* rowvar) {
@@ -229,6 +236,96 @@ inline int run_channel_stats(cudaStream_t st, const bf16* X, const bf16* D, long
   if (hw == 1) (row_variance_kernel<<<cdiv(T, 8), 256, 0, st>>>(X, D, rowvar, static_cast<int>(T), C), svb::count_launch());
   SVB_LAUNCH_CHECK("channel_stats");
   return 0;
+}
+
+// Fused statistics + NCHW write-back after the decoder GEMM (post_dec_nchw_kernel) when the SAE input is NCHW;
+// otherwise the token-major statistics kernel followed by a layout/dtype conversion of d.
+//   x: the caller's activations; X / D: token-major bf16 views; dec_out may be null.
+inline int run_post_dec(cudaStream_t st, const svb_acts* x, const bf16* X, const bf16* D, long long T, void* dec_out,
+                        int dec_dtype, int dec_layout, float* stbuf, float* chan, float* var_part, float* rowvar) {
+  const int C = x->C, hw = x->hw;
+  const bool nchw_in = x->layout == SVB_NCHW && hw > 1;
+  const bool out_ok = !dec_out || (dec_layout == SVB_NCHW);
+  if (nchw_in && out_ok && x->n_images <= 65535) {
+    int vec = nchw_vec(x->x, hw, x->dtype == SVB_F32 ? 4 : 2);
+    if (dec_out) {
+      const int vo = nchw_vec(dec_out, hw, dec_dtype == SVB_F32 ? 4 : 2);
+      if (vo < vec) vec = vo;
+    }
+    // enough blocks for ~4 per SM: split the HW range when images x channel groups alone are too few
+    const int tiles = cdiv(hw, 64);
+    int R = 1;
+    while (R < tiles && static_cast<long long>(cdiv(C, 64)) * x->n_images * R < 4LL * device_sm_count()) ++R;
+    const int tpc = cdiv(tiles, R);
+    R = cdiv(tiles, tpc);
+    if (stats_elems(x->n_images, hw, T, C) < static_cast<size_t>(x->n_images) * R * 8 * C) { R = 1; }
+    const int tiles_per_chunk = R == 1 ? tiles : tpc;
+    const dim3 grid(cdiv(C, 64), static_cast<unsigned>(x->n_images), R);
+#define SVB_POST(TI, TO, V)                                                                                          \
+  (post_dec_nchw_kernel<TI, TO, V><<<grid, 256, 0, st>>>(D, static_cast<const TI*>(x->x), static_cast<TO*>(dec_out), \
+                                                          stbuf, C, hw, tiles_per_chunk), svb::count_launch())
+#define SVB_POST_V(TI, TO)                                     \
+  do {                                                         \
+    if (vec == 8) SVB_POST(TI, TO, 8);                         \
+    else if (vec == 4) SVB_POST(TI, TO, 4);                    \
+    else SVB_POST(TI, TO, 1);                                  \
+  } while (0)
+    const bool out_f32 = dec_out && dec_dtype == SVB_F32;
+    if (x->dtype == SVB_F32) { if (out_f32) SVB_POST_V(float, float); else SVB_POST_V(float, bf16); }
+    else { if (out_f32) SVB_POST_V(bf16, float); else SVB_POST_V(bf16, bf16); }
+#undef SVB_POST_V
+#undef SVB_POST
+    (channel_stats_finalize_kernel<<<cdiv(C, 8), 256, 0, st>>>(stbuf, chan, var_part, static_cast<int>(x->n_images), R, C, hw), svb::count_launch());
+    SVB_LAUNCH_CHECK("post_dec");
+    return 0;
+  }
+  SVB_TRY(run_channel_stats(st, X, D, x->n_images, hw, T, C, stbuf, chan, var_part, rowvar));
+  if (dec_out) SVB_TRY(unpack_to(st, D, x->n_images, hw, C, dec_out, dec_dtype, dec_layout));
+  return 0;
+}
+
+inline int run_prep_step(cudaStream_t st, PrepArgs a) {
+  a.nb_enc = cdiv(a.F, 8);
+  a.nb_dec = grid_for(static_cast<size_t>(a.F) * a.C / 4, 256, 512);
+  a.nb_zero = a.n_zero ? grid_for(a.n_zero, 256, 64) : 0;
+  a.nb_exp = a.exp_r ? cdiv(a.F, 256) : 0;
+  (prep_step_kernel<<<a.nb_enc + a.nb_dec + a.nb_zero + a.nb_exp, 256, 0, st>>>(a), svb::count_launch());
+  SVB_LAUNCH_CHECK("prep_step");
+  return 0;
+}
+inline int run_assemble(cudaStream_t st, AssembleArgs a) {
+  a.nb_w = grid_for(static_cast<size_t>(a.F) * a.C / 4, 256, 1024);
+  a.nb_b = cdiv(a.F, 256);
+  a.nb_vm = a.vm_chunks * cdiv(a.C, 256);
+  a.nb_cnt = a.words;
+  a.nb_img = cdiv(a.n_img, 8);
+  (assemble_grads_kernel<<<2 * a.nb_w + a.nb_b + a.nb_vm + a.nb_cnt + a.nb_img, 256, 0, st>>>(a), svb::count_launch());
+  SVB_LAUNCH_CHECK("assemble_grads");
+  return 0;
+}
+inline int run_adam_multi(cudaStream_t st, const AdamSeg* segs, int nseg, const AdamCoef& k) {
+  AdamMultiArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nseg = nseg;
+  int blk = 0;
+  for (int i = 0; i < nseg; ++i) {
+    a.seg[i] = segs[i];
+    a.blk0[i] = blk;
+    blk += grid_for(static_cast<size_t>(segs[i].n), 256, 1024);
+  }
+  for (int i = nseg; i < 7; ++i) a.blk0[i] = blk;
+  (adam_multi_kernel<<<blk, 256, 0, st>>>(a, k), svb::count_launch());
+  SVB_LAUNCH_CHECK("adam_multi");
+  return 0;
+}
+inline void launch_cadam(cudaStream_t st, float* w, float* g, float* m, float* v, int C, int F, const AdamCoef& k) {
+  (constrained_adam_decoder_kernel<<<cdiv(F, kCadamCols), kCadamCols * kCadamRows, 0, st>>>(w, g, m, v, C, F, k), svb::count_launch());
+}
+// Rows of EpiDPre's per-CTA column-sum partials for a B-stationary launch (mirrors launch_gemm's grid choice).
+inline int bstat_groups(int sms, int tiles_n, int tiles_m) {
+  int groups = sms / tiles_n;
+  if (groups > tiles_m) groups = tiles_m;
+  return groups;
 }
 
 inline AdamCoef adam_coef(const svb_opt_config* o) {

@@ -11,7 +11,8 @@ namespace {
 
 struct GatedPlan {
   long long T, n_img;
-  int C, F, hw, words, tiles_m, tn_f, tn_c, s_wd, s_wg;
+  int C, F, hw, words, tiles_m, tn_f, tn_c, s_wd, s_wg, sms;
+  size_t zero_words;  // 32-bit words cleared by the step prologue, from act_bits on
   bool zero_copy_x;
   bf16 *X, *Wgb, *Wdb, *E, *RP, *A, *D, *DIFF;
   float *dot, *exp_r, *l1_part, *sq_part, *aux_part, *cs_mag, *cs_pi, *cs_mage, *stage, *csum_mag, *csum_pi,
@@ -22,8 +23,8 @@ struct GatedPlan {
 
 constexpr int kVmChunks = 32;
 
-void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
-  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images;
+void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms) {
+  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
   p.T = x->n_images * static_cast<long long>(x->hw);
   p.words = (F + 31) / 32;
   p.tiles_m = cdiv(p.T, kBlockM);
@@ -42,10 +43,12 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
   if (!train) return;
   p.A = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
+  const size_t z0 = a.off;
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 16);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
-  p.aux_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
+  p.l1_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.aux_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.zero_words = (a.off - z0) / 4;
   p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_pi = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.cs_mage = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
@@ -79,11 +82,11 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train) {
 int plan(svb_handle* h, GatedPlan& p, const svb_acts* x, int F, bool train) {
   Arena dry;
   dry.dry = true;
-  carve(dry, p, x, F, train);
+  carve(dry, p, x, F, train, h->sms);
   SVB_TRY(ensure_arena(h, dry.off));
   h->arena.off = 0;
   h->arena.dry = false;
-  carve(h->arena, p, x, F, train);
+  carve(h->arena, p, x, F, train, h->sms);
   return 0;
 }
 
@@ -93,11 +96,6 @@ int check_params(const svb_acts* x, const svb_gated_params* p) {
     return fail(SVB_ERR_BAD_ARG, "null Gated-SAE parameter");
   if (p->F <= 0 || p->F % 8) return fail(SVB_ERR_UNSUPPORTED, "hidden_size F=%d must be a positive multiple of 8", p->F);
   return 0;
-}
-
-__global__ void exp_kernel(const float* __restrict__ r, float* __restrict__ out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = expf(r[i]);
 }
 
 // per-feature vector gradients:  csum_a = csum_pi + exp(r)*csum_mag;  gb_gate = s*csum_pi;  gb_mag = s*csum_mag;
@@ -116,65 +114,14 @@ __global__ void gated_vec_grads_kernel(const float* __restrict__ cs_mag, const f
   g_r[f] = s * (cs_mage[f] - b_mag[f] * m);
 }
 
-__global__ void gated_stats_pack_kernel(const float* __restrict__ chan, const float* __restrict__ var_part,
-                                        int n_var_part, const float* __restrict__ rowvar, long long n_rows, int C,
-                                        float* __restrict__ flat, size_t o_sums, size_t o_chansq, size_t o_max) {
-  __shared__ float s[32];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    flat[o_chansq + c] = chan[C + c];
-    flat[o_max + c] = chan[3 * C + c];
-    flat[o_max + C + c] = -chan[2 * C + c];
-  }
-  float vx = 0.f, vd = 0.f;
-  if (n_rows > 0) {
-    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) { vx += rowvar[2 * r]; vd += rowvar[2 * r + 1]; }
-  } else {
-    for (int i = threadIdx.x; i < n_var_part; i += blockDim.x) { vx += var_part[2 * i]; vd += var_part[2 * i + 1]; }
-  }
-  const float a = block_sum(vx, s);
-  const float b = block_sum(vd, s);
-  if (threadIdx.x == 0) {
-    flat[o_sums + 3] = a;
-    flat[o_sums + 4] = b;
-    flat[o_sums + 6] = 0.f;
-    flat[o_sums + 7] = 0.f;
-  }
-}
-
-__global__ void gated_stats_finalize_kernel(const float* __restrict__ flat, size_t o_sums, size_t o_chansq,
-                                            size_t o_max, int C, int F, float T_g, float B_g, float lambda,
-                                            int expansion, float* __restrict__ stats) {
-  __shared__ float s[32];
-  float r = 0.f, nr = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float rm = sqrtf(flat[o_chansq + c] / T_g);
-    r += rm;
-    nr += rm / (flat[o_max + c] + flat[o_max + C + c]);
-  }
-  const float rs = block_sum(r, s);
-  const float nrs = block_sum(nr, s);
-  if (threadIdx.x == 0) {
-    const float rec = flat[o_sums + 0] / (T_g * C);
-    const float l1 = flat[o_sums + 1] / (T_g * F);
-    const float aux = flat[o_sums + 2] / (T_g * C);
-    stats[SVB_STAT_REC] = rec;
-    stats[SVB_STAT_L1] = l1;
-    stats[SVB_STAT_AUX] = aux;
-    stats[SVB_STAT_LOSS] = rec + lambda * l1 + aux;   // utils.py:2473
-    stats[SVB_STAT_RMSE] = rs / C;
-    stats[SVB_STAT_NRMSE] = nrs / C;
-    stats[SVB_STAT_VAR_EXPL] = 1.f - flat[o_sums + 4] / flat[o_sums + 3];
-    stats[SVB_STAT_SPARSITY] = (flat[o_sums + 5] / B_g) / (static_cast<float>(F) / expansion);
-  }
-}
-
-int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p) {
-  (prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_gate, nullptr, p->b_dec, pl.Wgb, nullptr, pl.dot, pl.F, pl.C), svb::count_launch());
-  const size_t n = static_cast<size_t>(pl.F) * pl.C;
-  (convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n), svb::count_launch());
-  (exp_kernel<<<cdiv(pl.F, 256), 256, 0, st>>>(p->r_mag, pl.exp_r, pl.F), svb::count_launch());
-  SVB_LAUNCH_CHECK("gated prep");
-  return 0;
+int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p, bool train) {
+  PrepArgs a{};
+  a.w_enc = p->w_gate; a.b_dec = p->b_dec; a.w_enc_bf16 = pl.Wgb; a.dotw = pl.dot;
+  a.w_dec = p->w_dec; a.w_dec_bf16 = pl.Wdb;
+  a.zero = train ? pl.act_bits : nullptr; a.n_zero = train ? pl.zero_words : 0;
+  a.r_mag = p->r_mag; a.exp_r = pl.exp_r;
+  a.F = pl.F; a.C = pl.C;
+  return run_prep_step(st, a);
 }
 
 }  // namespace
@@ -189,7 +136,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
   h->gradbuf = nullptr;
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
-  SVB_TRY(run_prep(st, pl, p));
+  SVB_TRY(run_prep(st, pl, p, false));
   const int T = static_cast<int>(pl.T);
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
@@ -229,9 +176,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
-  SVB_TRY(run_prep(st, pl, p));
-  (fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
-      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u), svb::count_launch());
+  SVB_TRY(run_prep(st, pl, p, true));
 
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
@@ -246,7 +191,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   EpiDec::Params e2v{};
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v)), "via");
-  SVB_TRY(run_channel_stats(st, X, pl.D, pl.n_img, pl.hw, pl.T, C, pl.st, pl.chan, pl.var_part, pl.rowvar));
+  SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
+                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
   EpiGatedDPre::Params e3{};
   e3.e = pl.E; e3.rp = pl.RP; e3.exp_r = pl.exp_r; e3.a_out = pl.A;
   e3.colsum_mag = pl.cs_mag; e3.colsum_pi = pl.cs_pi; e3.colsum_mage = pl.cs_mage;
@@ -266,22 +212,25 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   SVB_TRY(reduce_rows(st, pl.cs_mage, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mage));
   (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.csum_pi, pl.csum_mage, pl.exp_r, p->b_mag, s, F,
                                                       pl.csum_a, flat + pl.o_gbg, flat + pl.o_gbm, flat + pl.o_gr), svb::count_launch());
-  (sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd), svb::count_launch());
-  (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wg, pl.s_wg, F, C, pl.csum_a, p->b_dec, s, flat + pl.o_gwg), svb::count_launch());
-  (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum_a, pl.Wgb, F, C, pl.vm), svb::count_launch());
-  (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * EpiGatedEnc::kWarps, 1.f, flat + pl.o_sums + 1), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.aux_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 2), svb::count_launch());
-  (gated_stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
-                                             pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
-  (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());
-  (activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
-                                                               out ? out->activity.n_active : nullptr, pl.nact_f), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5), svb::count_launch());
+  AssembleArgs aa{};
+  aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
+  aa.P_we = pl.P_wg; aa.g_wenc = flat + pl.o_gwg; aa.s_we = pl.s_wg;
+  aa.csum = pl.csum_a; aa.b_dec = p->b_dec; aa.g_benc = nullptr;  // the three vector gradients are written above
+  aa.w_enc_bf16 = pl.Wgb; aa.vm = pl.vm; aa.vm_chunks = kVmChunks;
+  aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
+  aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
+  aa.F = F; aa.C = C; aa.s = s;
+  SVB_TRY(run_assemble(st, aa));
+  TailArgs ta{};
+  ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
+  ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
+  ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 8;
+  ta.aux_part = pl.aux_part; ta.n_aux = pl.sms * 8;
+  ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
+  ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
+  ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
+  (grads_tail_kernel<<<1, 1024, 0, st>>>(ta), svb::count_launch());
   SVB_LAUNCH_CHECK("gated grad assembly");
-  if (out && out->dec_out)
-    SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
   h->gradbuf = flat;
   h->sum_elems = static_cast<int64_t>(pl.sum_elems);
   h->max_elems = static_cast<int64_t>(pl.max_elems);
@@ -305,25 +254,28 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
   const AdamCoef k = adam_coef(opt);
-  (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_gate, flat + pl.o_gbg, adam->m[1], adam->v[1], F, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_mag, flat + pl.o_gbm, adam->m[2], adam->v[2], F, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], F, k, nullptr), svb::count_launch());
-  if (opt->optimizer == SVB_CONSTRAINED_ADAM)
-    (constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k), svb::count_launch());
-  else
-    (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], C, k, nullptr), svb::count_launch());
+  AdamSeg segs[6];
+  int ns = 0;
+  segs[ns++] = AdamSeg{p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC};
+  segs[ns++] = AdamSeg{p->b_gate, flat + pl.o_gbg, adam->m[1], adam->v[1], static_cast<unsigned long long>(F)};
+  segs[ns++] = AdamSeg{p->b_mag, flat + pl.o_gbm, adam->m[2], adam->v[2], static_cast<unsigned long long>(F)};
+  segs[ns++] = AdamSeg{p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], static_cast<unsigned long long>(F)};
+  segs[ns++] = AdamSeg{p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], static_cast<unsigned long long>(C)};
+  if (opt->optimizer != SVB_CONSTRAINED_ADAM) segs[ns++] = AdamSeg{p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC};
+  SVB_TRY(run_adam_multi(st, segs, ns, k));
+  if (opt->optimizer == SVB_CONSTRAINED_ADAM) launch_cadam(st, p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k);
   SVB_LAUNCH_CHECK("gated adam");
-  const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
-  const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
-  if (out && out->stats)
-    (gated_stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
-                                                   expansion_factor, out->stats), svb::count_launch());
-  if (out && (out->activity.dead || out->activity.freq || out->stats))
-    (activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
-                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr), svb::count_launch());
-  SVB_LAUNCH_CHECK("gated finalize");
+  if (out && (out->stats || out->activity.dead || out->activity.freq)) {
+    FinalizeArgs fa{};
+    fa.flat = flat; fa.o_sums = pl.o_sums; fa.o_chansq = pl.o_chansq; fa.o_max = pl.o_max; fa.o_count = pl.o_count;
+    fa.C = C; fa.F = F; fa.expansion = expansion_factor;
+    fa.T_g = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
+    fa.B_g = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
+    fa.lambda = lambda_sparse;   // utils.py:2473: loss = rec + lambda * l1 + aux
+    fa.stats = out->stats; fa.dead = out->activity.dead; fa.freq = out->activity.freq;
+    (step_finalize_kernel<<<1, 1024, 0, st>>>(fa), svb::count_launch());
+    SVB_LAUNCH_CHECK("gated finalize");
+  }
   return 0;
 }
 

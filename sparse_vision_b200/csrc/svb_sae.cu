@@ -26,7 +26,10 @@ struct SaePlan {
   long long n_img;
   int tiles_m, tn_f, tn_c;
   int s_wd, s_we;  // split-K slices
-  bool zero_copy_x;
+  int sms;
+  bool zero_copy_x, bstat;  // bstat: the K <= 256 GEMMs run B-stationary (per-CTA column-sum partials)
+  int cs_rows;              // rows of colsum_part
+  size_t zero_words;        // 32-bit words to clear at the start of a step, from act_bits on
   // workspace
   bf16 *X, *Web, *Wdb, *E, *DP, *D, *DIFF;
   float *fold, *l1_part, *sq_part, *colsum_part, *stage, *csum, *st, *chan, *var_part, *rowvar, *P_wd, *P_we, *vm,
@@ -39,8 +42,8 @@ struct SaePlan {
 
 constexpr int kVmChunks = 32;
 
-void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
-  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images;
+void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) {
+  p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
   p.T = x->n_images * static_cast<long long>(x->hw);
   p.words = (F + 31) / 32;
   p.tiles_m = cdiv(p.T, kBlockM);
@@ -57,11 +60,16 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
   if (!train) return;
   p.DP = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
-  p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
   p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_f * 16);
-  p.sq_part = a.take<float>(static_cast<size_t>(p.tiles_m) * p.tn_c * 16);
-  p.colsum_part = a.take<float>(static_cast<size_t>(p.tiles_m) * 4 * F);
+  // cleared by the step prologue: activity bits and the per-(CTA, warp) loss partials (contiguous on purpose)
+  const size_t z0 = a.off;
+  p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
+  p.l1_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.zero_words = (a.off - z0) / 4;
+  p.bstat = p.C <= 256 && p.tn_f <= sms;
+  p.cs_rows = p.bstat ? 4 * bstat_groups(sms, p.tn_f, p.tiles_m) : 4 * p.tiles_m;
+  p.colsum_part = a.take<float>(static_cast<size_t>(p.cs_rows) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
   p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
@@ -87,11 +95,11 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train) {
 int plan(svb_handle* h, SaePlan& p, const svb_acts* x, int F, bool train) {
   Arena dry;
   dry.dry = true;
-  carve(dry, p, x, F, train);
+  carve(dry, p, x, F, train, h->sms);
   SVB_TRY(ensure_arena(h, dry.off));
   h->arena.off = 0;
   h->arena.dry = false;
-  carve(h->arena, p, x, F, train);
+  carve(h->arena, p, x, F, train, h->sms);
   return 0;
 }
 
@@ -102,68 +110,13 @@ int check_params(const svb_acts* x, const svb_sae_params* p) {
   return 0;
 }
 
-// sums section layout: [0]=sum sq, [1]=sum l1, [2]=sum aux sq, [3]=sum var x, [4]=sum var d, [5]=sum n_active
-__global__ void stats_pack_kernel(const float* __restrict__ chan, const float* __restrict__ var_part, int n_var_part,
-                                  const float* __restrict__ rowvar, long long n_rows, int C, float* __restrict__ flat,
-                                  size_t o_sums, size_t o_chansq, size_t o_max) {
-  __shared__ float s[32];
-  // per-channel sum diff^2 and max / -min of x
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    flat[o_chansq + c] = chan[C + c];
-    flat[o_max + c] = chan[3 * C + c];
-    flat[o_max + C + c] = -chan[2 * C + c];
-  }
-  float vx = 0.f, vd = 0.f;
-  if (n_rows > 0) {
-    for (long long r = threadIdx.x; r < n_rows; r += blockDim.x) { vx += rowvar[2 * r]; vd += rowvar[2 * r + 1]; }
-  } else {
-    for (int i = threadIdx.x; i < n_var_part; i += blockDim.x) { vx += var_part[2 * i]; vd += var_part[2 * i + 1]; }
-  }
-  const float a = block_sum(vx, s);
-  const float b = block_sum(vd, s);
-  if (threadIdx.x == 0) {
-    flat[o_sums + 3] = a;
-    flat[o_sums + 4] = b;
-    flat[o_sums + 6] = 0.f;
-    flat[o_sums + 7] = 0.f;
-  }
-}
-
-// For 2-D inputs the per-channel stats come from one "image" holding all rows.
-__global__ void stats_finalize_kernel(const float* __restrict__ flat, size_t o_sums, size_t o_chansq, size_t o_max,
-                                      int C, int F, float T_g, float B_g, float lambda, int expansion,
-                                      float* __restrict__ stats) {
-  __shared__ float s[32];
-  float r = 0.f, nr = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float rm = sqrtf(flat[o_chansq + c] / T_g);
-    const float range = flat[o_max + c] + flat[o_max + C + c];  // max - min
-    r += rm;
-    nr += rm / range;
-  }
-  const float rs = block_sum(r, s);
-  const float nrs = block_sum(nr, s);
-  if (threadIdx.x == 0) {
-    const float rec = flat[o_sums + 0] / (T_g * C);
-    const float l1 = flat[o_sums + 1] / (T_g * F);
-    const float aux = flat[o_sums + 2] / (T_g * C);
-    stats[SVB_STAT_REC] = rec;
-    stats[SVB_STAT_L1] = l1;
-    stats[SVB_STAT_AUX] = aux;
-    stats[SVB_STAT_LOSS] = rec + lambda * l1 + aux;
-    stats[SVB_STAT_RMSE] = rs / C;
-    stats[SVB_STAT_NRMSE] = nrs / C;
-    stats[SVB_STAT_VAR_EXPL] = 1.f - flat[o_sums + 4] / flat[o_sums + 3];
-    stats[SVB_STAT_SPARSITY] = (flat[o_sums + 5] / B_g) / (static_cast<float>(F) / expansion);
-  }
-}
-
-int run_prep(cudaStream_t st, const SaePlan& pl, const svb_sae_params* p) {
-  (prep_encoder_kernel<<<cdiv(pl.F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, pl.Web, pl.fold, nullptr, pl.F, pl.C), svb::count_launch());
-  const size_t n = static_cast<size_t>(pl.F) * pl.C;
-  (convert_kernel<float, bf16><<<grid_for(n), 256, 0, st>>>(p->w_dec, pl.Wdb, n), svb::count_launch());
-  SVB_LAUNCH_CHECK("prep");
-  return 0;
+int run_prep(cudaStream_t st, const SaePlan& pl, const svb_sae_params* p, bool train) {
+  PrepArgs a{};
+  a.w_enc = p->w_enc; a.b_enc = p->b_enc; a.b_dec = p->b_dec; a.w_enc_bf16 = pl.Web; a.fold = pl.fold;
+  a.w_dec = p->w_dec; a.w_dec_bf16 = pl.Wdb;
+  a.zero = train ? pl.act_bits : nullptr; a.n_zero = train ? pl.zero_words : 0;
+  a.F = pl.F; a.C = pl.C;
+  return run_prep_step(st, a);
 }
 
 }  // namespace
@@ -178,7 +131,7 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   h->gradbuf = nullptr;
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
-  SVB_TRY(run_prep(st, pl, p));
+  SVB_TRY(run_prep(st, pl, p, false));
   const int T = static_cast<int>(pl.T);
   EpiEnc::Params e1{};
   e1.bias = pl.fold;
@@ -212,9 +165,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   prof_begin_step(h);
   prof_mark(h, st, 0);
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
-  SVB_TRY(run_prep(st, pl, p));
-  (fill_u32_kernel<<<grid_for(static_cast<size_t>(pl.n_img) * pl.words), 256, 0, st>>>(
-      pl.act_bits, static_cast<size_t>(pl.n_img) * pl.words, 0u), svb::count_launch());
+  SVB_TRY(run_prep(st, pl, p, true));
 
   prof_mark(h, st, 1);
   // G1 encoder
@@ -223,7 +174,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   e1.mask_words = pl.mask;
   e1.hw = pl.hw; e1.words = pl.words;
   if (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
-  if (C <= 256 && pl.tn_f <= h->sms) {
+  if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc (B-stationary)");
   } else {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
@@ -236,15 +187,17 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
   prof_mark(h, st, 3);
-  // channel statistics
-  SVB_TRY(run_channel_stats(st, X, pl.D, pl.n_img, pl.hw, pl.T, C, pl.st, pl.chan, pl.var_part, pl.rowvar));
+  // channel statistics + the decoder output handed back to the model (model_pipeline.py:425,432), one pass
+  SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
+                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
   EpiDPre::Params e3{};
   e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
+  e3.per_cta = pl.bstat ? 1 : 0;
   if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
-  if (C <= 256 && pl.tn_f <= h->sms) {
+  if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, true, EpiDPre, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE (B-stationary)");
   } else {
     SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
@@ -259,30 +212,28 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
 
   prof_mark(h, st, 7);
-  // gradient assembly
+  // gradient assembly: column sums -> merged assembly kernel -> one-block tail
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
-  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.tiles_m * 4, F, 1.f, pl.stage, pl.csum));
-  (sum_splits_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_wd, pl.s_wd, FC, s, flat + pl.o_gwd), svb::count_launch());
-  (wenc_grad_kernel<<<grid_for(FC), 256, 0, st>>>(pl.P_we, pl.s_we, F, C, pl.csum, p->b_dec, s, flat + pl.o_gwe), svb::count_launch());
-  (vecmat_partial_kernel<bf16><<<dim3(cdiv(C, 256), kVmChunks), 256, 0, st>>>(pl.csum, pl.Web, F, C, pl.vm), svb::count_launch());
-  (bdec_grad_kernel<<<cdiv(C, 256), 256, 0, st>>>(pl.chan /* sum diff */, pl.vm, kVmChunks, C, s, flat + pl.o_gbd), svb::count_launch());
-  (sum_splits_kernel<<<grid_for(F), 256, 0, st>>>(pl.csum, 1, F, s, flat + pl.o_gbe), svb::count_launch());  // gb_enc = s * csum
-  // loss partial sums
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.sq_part, static_cast<size_t>(pl.tiles_m) * pl.tn_c * EpiDec::kWarps, 1.f, flat + pl.o_sums + 0), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.l1_part, static_cast<size_t>(pl.tiles_m) * pl.tn_f * EpiEnc::kWarps, 1.f, flat + pl.o_sums + 1), svb::count_launch());
-  (stats_pack_kernel<<<1, 256, 0, st>>>(pl.chan, pl.var_part, cdiv(C, 8), pl.rowvar, pl.hw == 1 ? pl.T : 0, C, flat,
-                                       pl.o_sums, pl.o_chansq, pl.o_max), svb::count_launch());
-  cudaMemsetAsync(flat + pl.o_sums + 2, 0, sizeof(float), st);
-  // activity
-  (activity_count_kernel<<<pl.words, 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words, F, flat + pl.o_count), svb::count_launch());
-  (activity_per_image_kernel<<<cdiv(pl.n_img, 8), 256, 0, st>>>(pl.act_bits, static_cast<int>(pl.n_img), pl.words,
-                                                               out ? out->activity.n_active : nullptr, pl.nact_f), svb::count_launch());
-  (reduce_flat_kernel<<<1, 1024, 0, st>>>(pl.nact_f, static_cast<size_t>(pl.n_img), 1.f, flat + pl.o_sums + 5), svb::count_launch());
+  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));
+  AssembleArgs aa{};
+  aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
+  aa.P_we = pl.P_we; aa.g_wenc = flat + pl.o_gwe; aa.s_we = pl.s_we;
+  aa.csum = pl.csum; aa.b_dec = p->b_dec; aa.g_benc = flat + pl.o_gbe;
+  aa.w_enc_bf16 = pl.Web; aa.vm = pl.vm; aa.vm_chunks = kVmChunks;
+  aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
+  aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
+  aa.F = F; aa.C = C; aa.s = s;
+  SVB_TRY(run_assemble(st, aa));
+  TailArgs ta{};
+  ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
+  ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
+  ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 8;
+  ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
+  ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
+  ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
+  (grads_tail_kernel<<<1, 1024, 0, st>>>(ta), svb::count_launch());
   SVB_LAUNCH_CHECK("grad assembly");
-  // decoder output handed back to the model (model_pipeline.py:425,432)
-  if (out && out->dec_out)
-    SVB_TRY(unpack_to(st, pl.D, pl.n_img, pl.hw, C, out->dec_out, out->dec_dtype, out->dec_layout));
   prof_mark(h, st, 8);
   h->gradbuf = flat;
   h->sum_elems = static_cast<int64_t>(pl.sum_elems);
@@ -307,25 +258,26 @@ extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
   const AdamCoef k = adam_coef(opt);
-  (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(F), 256, 0, st>>>(p->b_enc, flat + pl.o_gbe, adam->m[1], adam->v[1], F, k, nullptr), svb::count_launch());
-  if (opt->optimizer == SVB_CONSTRAINED_ADAM)
-    (constrained_adam_decoder_kernel<<<cdiv(F, 32), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], C, F, k), svb::count_launch());
-  else
-    (adam_kernel<<<grid_for(FC), 256, 0, st>>>(p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], FC, k, nullptr), svb::count_launch());
-  (adam_kernel<<<grid_for(C), 256, 0, st>>>(p->b_dec, flat + pl.o_gbd, adam->m[3], adam->v[3], C, k, nullptr), svb::count_launch());
+  AdamSeg segs[4];
+  int ns = 0;
+  segs[ns++] = AdamSeg{p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC};
+  segs[ns++] = AdamSeg{p->b_enc, flat + pl.o_gbe, adam->m[1], adam->v[1], static_cast<unsigned long long>(F)};
+  segs[ns++] = AdamSeg{p->b_dec, flat + pl.o_gbd, adam->m[3], adam->v[3], static_cast<unsigned long long>(C)};
+  if (opt->optimizer != SVB_CONSTRAINED_ADAM) segs[ns++] = AdamSeg{p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], FC};
+  SVB_TRY(run_adam_multi(st, segs, ns, k));
+  if (opt->optimizer == SVB_CONSTRAINED_ADAM) launch_cadam(st, p->w_dec, flat + pl.o_gwd, adam->m[2], adam->v[2], C, F, k);
   SVB_LAUNCH_CHECK("adam");
-  const float Tg = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
-  const float Bg = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
-  if (out && out->stats) {
-    (stats_finalize_kernel<<<1, 256, 0, st>>>(flat, pl.o_sums, pl.o_chansq, pl.o_max, C, F, Tg, Bg, lambda_sparse,
-                                             expansion_factor, out->stats), svb::count_launch());
+  if (out && (out->stats || out->activity.dead || out->activity.freq)) {
+    FinalizeArgs fa{};
+    fa.flat = flat; fa.o_sums = pl.o_sums; fa.o_chansq = pl.o_chansq; fa.o_max = pl.o_max; fa.o_count = pl.o_count;
+    fa.C = C; fa.F = F; fa.expansion = expansion_factor;
+    fa.T_g = static_cast<float>(global_tokens > 0 ? global_tokens : pl.T);
+    fa.B_g = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
+    fa.lambda = lambda_sparse;
+    fa.stats = out->stats; fa.dead = out->activity.dead; fa.freq = out->activity.freq;
+    (step_finalize_kernel<<<1, 1024, 0, st>>>(fa), svb::count_launch());
+    SVB_LAUNCH_CHECK("finalize");
   }
-  if (out && (out->activity.dead || out->activity.freq || out->stats)) {
-    (activity_finalize_kernel<<<1, 1024, 0, st>>>(flat + pl.o_count, F, Bg, out->activity.dead, out->activity.freq,
-                                                 out->stats ? out->stats + SVB_STAT_N_DEAD : nullptr), svb::count_launch());
-  }
-  SVB_LAUNCH_CHECK("finalize");
   prof_mark(h, st, 9);
   return 0;
 }

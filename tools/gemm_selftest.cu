@@ -256,6 +256,263 @@ static int perf_enc_variants() {
   return 0;
 }
 
+// Bring-up probe: what bounds a K=256 tile?  MODE 0 = epilogue does nothing (no TMEM read), 1 = TMEM read only,
+// 2 = TMEM read + bf16 pack + TMA slab store, 3 = TMEM read + ALU work (relu, mask bits, sum) without stores.
+template <int MODE, int WARPS>
+struct EpiProbe {
+  struct Params {
+    alignas(64) CUtensorMap tm;
+    float* sink;
+  };
+  static constexpr int kWarps = WARPS;
+  static constexpr int kColVecs = 0;
+  static constexpr bool kSkipAccLoad = (MODE == 0);
+  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(WARPS);
+  const Params& p;
+  SlabWriter1 slab;
+  float sum;
+  uint32_t bits;
+  int ew;
+  __device__ EpiProbe(const Params& p_, uint8_t* smem, int ew_, int) : p(p_), sum(0.f), bits(0), ew(ew_) { slab.init(smem, ew_); }
+  __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
+  __device__ void colvec_commit(uint32_t, int) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
+    if (MODE == 2 || MODE == 9 || MODE == 10) {
+      const int half = (col0 >> 5) & 1;
+      const bool skip = MODE == 10 && ((col0 >> 6) & 1);
+      if (!skip) {
+        slab.put(half, lane, v);
+        if (half == 1) slab.flush(&p.tm, col0 - 32, MODE == 9 ? ((ti.m0 & 4095) + wq * 32) : (ti.m0 + wq * 32), lane);
+      }
+    }
+    if (MODE == 12 || MODE == 13) {  // row-major slabs with an evict-first hint on the stores (13: plus evict-last A loads)
+      const int half = (col0 >> 5) & 1;
+      if (half == 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+      uint8_t* rowp = slab.base + lane * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = half * 4 + i;
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+      }
+      if (half == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d_hint(&p.tm, slab.base, col0 - 32, ti.m0 + wq * 32, kL2EvictFirst); bulk_commit(); }
+      }
+    }
+    if (MODE == 11) {  // slab-major output [N/64][M][64]: every 32 x 64 slab is 4 KB of contiguous memory
+      const int half = (col0 >> 5) & 1;
+      if (half == 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+      uint8_t* rowp = slab.base + lane * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = half * 4 + i;
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+      }
+      if (half == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&p.tm),
+                       "r"(smem_u32(slab.base)), "r"(0), "r"(ti.m0 + wq * 32), "r"((col0 - 32) >> 6) : "memory");
+          bulk_commit();
+        }
+      }
+    }
+    if (MODE >= 4 && MODE <= 6) {  // 4 = STS only, 5 = TMA store only (with the read wait), 6 = STS + TMA store without the read wait
+      const int half = (col0 >> 5) & 1;
+      if (MODE == 5 && half == 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+      if (MODE != 5) {
+        uint8_t* rowp = slab.base + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = half * 4 + i;
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+        }
+      }
+      if (MODE != 4 && half == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(&p.tm, slab.base, col0 - 32, ti.m0 + wq * 32); bulk_commit(); }
+      }
+    }
+    if (MODE == 7 || MODE == 8) {  // STS into the slab, then coalesced st.global.v4 (4 rows x 128 B per instruction); 8 = small L2-resident window
+      const int half = (col0 >> 5) & 1;
+      uint8_t* rowp = slab.base + lane * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = half * 4 + i;
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+      }
+      if (half == 1) {
+        __syncwarp();
+        const int r0 = ti.m0 + wq * 32;
+        const int rwrap = MODE == 8 ? (r0 & 4095) : r0;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.sink) + 1024;  // sink doubles as the output base (offset keeps slot 0 free)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), j = lane & 7;
+          const uint4 q = *reinterpret_cast<const uint4*>(slab.base + r * 128 + ((j ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(out + (size_t)(rwrap + r) * g.N + (col0 - 32) + j * 8) = q;
+        }
+        __syncwarp();
+      }
+    }
+    if (MODE == 3) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = 1.0f - v[j];
+        bits = __funnelshift_l(__float_as_uint(t), bits, 1);
+        sum += fmaxf(-t, 0.f);
+      }
+    }
+  }
+  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void finish(int, int lane) {
+    if (MODE == 2 || (MODE >= 5 && MODE != 7 && MODE != 8)) slab.drain(lane);  // (mode 11 included)
+    if (MODE == 3 && sum == 12345.678f && bits == 77) p.sink[0] = sum;
+  }
+};
+
+template <int MODE, int WARPS>
+static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int M, int N, int K) {
+  typename EpiProbe<MODE, WARPS>::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.sink = sink;
+  make_store_tmap_bf16(&ep.tm, dE, M, N, N);
+  if (MODE == 11) {
+    cuuint64_t gdim[3] = {64, (cuuint64_t)M, (cuuint64_t)N / 64};
+    cuuint64_t gstride[2] = {128, (cuuint64_t)M * 128};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = tmap_encode_fn()(&ep.tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dE, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) printf("3-D tensor map failed: %d\n", (int)r);
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int bstat = 0; bstat < 2; ++bstat) {
+    auto go = [&]() {
+      const unsigned long long apol = MODE == 13 ? kL2EvictLast : 0ull;
+      if (bstat) launch_gemm<256, false, false, EpiProbe<MODE, WARPS>, true>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, apol);
+      else launch_gemm<256, false, false, EpiProbe<MODE, WARPS>, false>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, apol);
+    };
+    for (int it = 0; it < 3; ++it) go();
+    CK(cudaDeviceSynchronize());
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int it = 0; it < iters; ++it) go();
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    printf("[probe mode %d warps %2d bstat %d] %.3f ms  %.1f TFLOP/s\n", MODE, WARPS, bstat, ms, 2.0 * M * N * K / ms * 1e-9);
+  }
+}
+
+static int perf_probe() {
+  const int M = 200704, N = 2048, K = 256;
+  void *dA, *dB, *dE;
+  float* sink;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dE, (size_t)M * N * 2 + 4096));
+  CK(cudaMalloc(&sink, 64));
+  CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
+  CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
+  probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
+  probe_one<2, 8>(dA, dB, dE, sink, M, N, K);
+  probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
+  probe_one<12, 8>(dA, dB, dE, sink, M, N, K);
+  probe_one<13, 8>(dA, dB, dE, sink, M, N, K);
+  return 0;
+}
+
+// Write-path microbenchmarks: what does a pure 822 MB output stream cost without any GEMM in front of it?
+__global__ void wr_plain_kernel(uint4* out, size_t n16) {
+  const uint4 q = make_uint4(1, 2, 3, 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) out[i] = q;
+}
+// every warp stores 32-row x 64-col bf16 slabs (like the GEMM epilogue) or, ROWS=128, one 128 x 64 slab per CTA pass
+template <int ROWS>
+__global__ void wr_tma_kernel(const __grid_constant__ CUtensorMap tm, int M, int N) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  const int col_slabs = N / 64;
+  if (ROWS == 32) {
+    const long long total = (long long)(M / 32) * col_slabs;
+    for (long long s = (long long)blockIdx.x * nw + warp; s < total; s += (long long)gridDim.x * nw) {
+      const int r = (int)(s / col_slabs), c = (int)(s % col_slabs);
+      if (lane == 0) {
+        bulk_wait_read<0>();
+        tma_store_2d(&tm, sm + warp * 4096, c * 64, r * 32);
+        bulk_commit();
+      }
+      __syncwarp();
+    }
+  } else {
+    const long long total = (long long)(M / ROWS) * col_slabs;
+    for (long long s = blockIdx.x; s < total; s += gridDim.x) {
+      const int r = (int)(s / col_slabs), c = (int)(s % col_slabs);
+      if (threadIdx.x == 0) {
+        bulk_wait_read<1>();
+        tma_store_2d(&tm, sm + (s & 1) * ROWS * 128, c * 64, r * ROWS);
+        bulk_commit();
+      }
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+static int make_tmap_rows(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_bf16_2d(out, ptr, rows, cols, cols, box_rows);
+}
+static int perf_write() {
+  const int M = 200704, N = 2048;
+  void* dE;
+  CK(cudaMalloc(&dE, (size_t)M * N * 2));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const size_t bytes = (size_t)M * N * 2;
+  auto timeit = [&](const char* name, auto&& fn) {
+    for (int it = 0; it < 2; ++it) fn();
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int it = 0; it < 10; ++it) fn();
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10;
+    printf("[write %-28s] %.3f ms  %.1f GB/s\n", name, ms, bytes / ms * 1e-6);
+  };
+  timeit("cudaMemsetAsync", [&]() { cudaMemsetAsync(dE, 1, bytes, 0); });
+  timeit("st.global.v4 148x8x256", [&]() { wr_plain_kernel<<<148 * 8, 256>>>((uint4*)dE, bytes / 16); });
+  timeit("st.global.v4 148x2x1024", [&]() { wr_plain_kernel<<<148 * 2, 1024>>>((uint4*)dE, bytes / 16); });
+  CUtensorMap tm32, tm128, tm256;
+  make_tmap_rows(&tm32, dE, M, N, 32);
+  make_tmap_rows(&tm128, dE, M, N, 128);
+  make_tmap_rows(&tm256, dE, M, N, 256);
+  cudaFuncSetAttribute(wr_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(wr_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(wr_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  timeit("TMA 32x64 slabs, 8 warps/CTA", [&]() { wr_tma_kernel<32><<<148, 256, 32768>>>(tm32, M, N); });
+  timeit("TMA 32x64 slabs, 16 warps/CTA", [&]() { wr_tma_kernel<32><<<148, 512, 65536>>>(tm32, M, N); });
+  timeit("TMA 128x64 slabs, 1/CTA", [&]() { wr_tma_kernel<128><<<148, 32, 32768>>>(tm128, M, N); });
+  timeit("TMA 256x64 slabs, 1/CTA", [&]() { wr_tma_kernel<256><<<148, 32, 65536>>>(tm256, M, N); });
+  timeit("TMA 128x64 slabs, 2 CTA/SM", [&]() { wr_tma_kernel<128><<<296, 32, 32768>>>(tm128, M, N); });
+  {  // same byte count into a 16 MB window (L2-resident): the SM-side store rate without HBM behind it
+    CUtensorMap tmw;
+    make_tmap_rows(&tmw, dE, 4096, N, 32);
+    timeit("TMA 32x64 slabs, 16 MB window x49", [&]() { for (int r = 0; r < 7; ++r) wr_tma_kernel<32><<<148, 256, 32768>>>(tmw, 4096, N); });
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("%d\n", (int)(sizeof(kCases) / sizeof(kCases[0])));
@@ -263,6 +520,8 @@ int main(int argc, char** argv) {
   }
   if (std::string(argv[1]) == "perf") return perf();
   if (std::string(argv[1]) == "perf_enc") return perf_enc_variants();
+  if (std::string(argv[1]) == "probe") return perf_probe();
+  if (std::string(argv[1]) == "write") return perf_write();
   const int i = atoi(argv[1]);
   if (i < 0 || i >= (int)(sizeof(kCases) / sizeof(kCases[0]))) return 3;
   return dispatch(kCases[i]);
