@@ -152,7 +152,8 @@ struct EpiPartial {
   __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
   __device__ void colvec_commit(uint32_t, int) {}
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int, int) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int, int, int) {
     if (row >= g.M) return;
     store_row_f32(p.out + ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0, v,
                   min(32, g.N - col0));
@@ -196,7 +197,8 @@ struct EpiStore {
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int) {
     const int nvalid = min(32, g.N - col0);
     float b[32];
     lds_row_f32(cv + (col0 - ti.n0), b);  // zeros when there is no bias
@@ -228,13 +230,15 @@ struct EpiStore {
 // Fused: bf16 store of e (TMA slabs), optional fp32 stores of e / pre (API forward), per-row activity words
 // (1 bit per element: the ReLU mask the backward needs), per-image activity bits (utils.py:2033-2047) and sum|e|
 // partials (sparse_loss.py:41).  All generic-proxy global writes happen once per tile in end_tile.
-struct EpiEnc {
+// API = true additionally offers fp32 stores of e / pre (svb_sae_forward); the training step instantiates API = false.
+template <bool API>
+struct EpiEncT {
   struct Params {
     alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], box 64 x 32 (valid when e_bf16 != null)
     const float* bias;             // [N]
     __nv_bfloat16* e_bf16;         // [M,N] or null
-    float* e_f32;                  // [M,N] or null
-    float* pre_f32;                // [M,N] or null
+    float* e_f32;                  // [M,N] or null   (API only)
+    float* pre_f32;                // [M,N] or null   (API only)
     uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
     uint32_t* act_bits;            // [n_img, words] or null
     float* l1_partial;             // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
@@ -243,6 +247,7 @@ struct EpiEnc {
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
+  static constexpr bool kPrefetchAcc = true;
   static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
   SlabWriter1 slab;
@@ -252,7 +257,7 @@ struct EpiEnc {
   float sum, total;
   uint32_t words[4];
   int ew, cpw, c_first;  // chunks per warp, this warp's first 32-column chunk inside the tile
-  __device__ EpiEnc(const Params& p_, uint8_t* smem, int ew_, int block_n)
+  __device__ EpiEncT(const Params& p_, uint8_t* smem, int ew_, int block_n)
       : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
         cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
     slab.init(smem, ew_);
@@ -273,14 +278,15 @@ struct EpiEnc {
 #pragma unroll
     for (int i = 0; i < 4; ++i) words[i] = 0;
   }
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
-                        int lane) {
+  // ci: index of the chunk among this warp's chunks (a compile-time constant after the caller's unrolling)
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int ci) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float nb[32];
     lds_row_f32(cv + (col0 - ti.n0), nb);  // -bias'
     const long long off = static_cast<long long>(row) * g.N + col0;
-    if (p.pre_f32) {                       // API forward only: materialise pre = acc + bias'
+    if (API && p.pre_f32) {                // materialise pre = acc + bias'
       float pre[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) pre[j] = v[j] - nb[j];
@@ -305,16 +311,13 @@ struct EpiEnc {
     sum += (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
     if (nvalid < 32) word &= (1u << nvalid) - 1u;
     if (!row_ok) word = 0;
-    const int c = ((col0 - ti.n0) >> 5) - c_first;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i == c) words[i] = word;
+    words[ci] = word;
     if (p.e_bf16) {
-      const int half = c & 1;
+      const int half = ci & 1;
       slab.put(half, lane, v);
       if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane);
     }
-    if (p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
+    if (API && p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
     if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
@@ -362,6 +365,8 @@ struct EpiEnc {
     }
   }
 };
+typedef EpiEncT<false> EpiEnc;     // training step
+typedef EpiEncT<true> EpiEncApi;   // svb_sae_forward (optional fp32 e / pre outputs)
 
 // ------------------------------------------------------------------------------------------------ decoder
 // d = acc + b_dec;  diff = d - x   (sae_mlp.py:52, sparse_loss.py:35).  Fused: stores of d / diff, sum diff^2.
@@ -403,8 +408,8 @@ struct EpiDec {
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
-                        int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     const int half = ((col0 - ti.n0) >> 5) & 1;
@@ -452,16 +457,20 @@ struct EpiDec {
 // of sparse_loss.py:35,41 through sae_mlp.py:51).  The ReLU mask comes from the encoder's 1-bit activity words
 // (8 B per row and warp instead of re-reading 128 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
 // column sums (-> db_enc).
-struct EpiDPre {
+// Column sums over tokens (-> db_enc) are read back from the finished 32 x 64 bf16 slab in shared memory: lane l owns
+// columns 2l, 2l+1 of the slab, adds the rows 8 at a time as packed bf16 pairs (HADD2) and accumulates the four
+// groups in fp32 -- about one instruction per element instead of four for a 31-step shuffle transpose.
+// CS = 0: one partial row per (M tile, lane quarter).  CS = 1 (B-stationary launches: a CTA keeps ONE N tile): the
+// sums are carried in registers over all M tiles of the CTA and written once.  CS = 2: no column sums.
+template <int CS>
+struct EpiDPreT {
   struct Params {
     alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
     const uint32_t* mask_words;        // [M, words]
-    float* colsum_partial;             // per_cta == 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens;
-                                       // per_cta == 1 (B-stationary launch: a CTA keeps ONE N tile): [groups * 4, N],
-                                       //   group = blockIdx.x / tiles_n, summed over all M tiles the CTA walks
+    float* colsum_partial;             // CS = 1: [groups * 4, N] with group = blockIdx.x / tiles_n;
+                                       // CS = 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens
     float l1c;
     int words;
-    int per_cta;
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 0;
@@ -469,14 +478,14 @@ struct EpiDPre {
   const Params& p;
   SlabWriter1 slab;
   uint32_t words[4];
-  float csacc[4];  // per_cta: lane j holds the running sum of column (chunk c, j) over this CTA's tiles
-  int ew, cpw, c_first, block_n, n0_last, tiles_n_last, N_last;
-  __device__ EpiDPre(const Params& p_, uint8_t* smem, int ew_, int block_n_)
+  float2 csacc[2];  // CS = 1: running sums of this lane's two columns, per slab of the warp
+  int ew, cpw, c_first, n0_last, tiles_n_last, N_last;
+  __device__ EpiDPreT(const Params& p_, uint8_t* smem, int ew_, int block_n_)
       : p(p_), ew(ew_), cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
-        block_n(block_n_), n0_last(-1), tiles_n_last(1), N_last(0) {
+        n0_last(-1), tiles_n_last(1), N_last(0) {
     slab.init(smem, ew_);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) csacc[i] = 0.f;
+    csacc[0] = make_float2(0.f, 0.f);
+    csacc[1] = make_float2(0.f, 0.f);
   }
   __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
   __device__ void colvec_commit(uint32_t, int) {}
@@ -500,42 +509,77 @@ struct EpiDPre {
       }
     }
   }
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq, int lane) {
-    const int c = ((col0 - ti.n0) >> 5) - c_first;
-    uint32_t word = 0;
+  // Sum of the slab's 32 rows for this lane's column pair (2*lane, 2*lane+1); the slab must be completely written.
+  __device__ __forceinline__ float2 slab_colsum(int lane) const {
+    float2 s = make_float2(0.f, 0.f);  // this lane reads 16-byte piece lane/4, word lane%4 of every row
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i == c) word = words[i];
+    for (int g8 = 0; g8 < 4; ++g8) {
+      __nv_bfloat162 acc;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {  // row 8*g8 + r: its pieces are XOR-swizzled with r
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(
+            slab.base + (g8 * 8 + r) * 128 + ((((lane >> 2) ^ r) << 4) | ((lane & 3) << 2)));
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
+        acc = r == 0 ? h : __hadd2(acc, h);
+      }
+      const uint32_t aw = *reinterpret_cast<const uint32_t*>(&acc);
+      s.x += bf16lo(aw);
+      s.y += bf16hi(aw);
+    }
+    return s;
+  }
+  __device__ __forceinline__ void slab_done(const GemmProblem& g, const TileInfo& ti, int col_slab0, int wq, int lane,
+                                            int si) {
+    if (CS == 2) return;
+    __syncwarp();  // every lane's row of the slab is in shared memory
+    const float2 cs = slab_colsum(lane);
+    if (CS == 1) {
+      csacc[si].x += cs.x;
+      csacc[si].y += cs.y;
+    } else {
+      const int col = col_slab0 + 2 * lane;  // N % 8 == 0: a column pair is inside or outside together
+      if (col < g.N)
+        *reinterpret_cast<float2*>(p.colsum_partial + (static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col) = cs;
+    }
+  }
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq,
+                                        int lane, int ci) {
+    const uint32_t word = words[ci];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (word & (1u << j)) ? v[j] + p.l1c : 0.f;
-    const int half = c & 1;
+    const int half = ci & 1;
     slab.put(half, lane, v);
-    if (half == 1) slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
-    // column sums over this warp's 32 tokens: lane j ends up with column col0 + j (one coalesced 128-byte store)
-    const float cs = warp_colsum32(v, lane);
-    if (p.per_cta) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i == c) csacc[i] += cs;
-    } else if (col0 + lane < g.N) {
-      p.colsum_partial[(static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col0 + lane] = cs;
+    if (half == 1) {
+      slab_done(g, ti, col0 - 32, wq, lane, ci >> 1);
+      slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
     }
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
-    if (slab.half_pending) slab.flush(&p.tm_dpre, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
+    if (slab.half_pending) {  // N tail: the slab's second half was never written for this tile -> clear it first
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      slab.put(1, lane, z);
+      const int col_slab0 = ((g.N - 1) >> 6) << 6;
+      slab_done(g, ti, col_slab0, wq, lane, ((col_slab0 - ti.n0) >> 6) & 1);
+      slab.flush(&p.tm_dpre, col_slab0, ti.m0 + wq * 32, lane);
+    }
     n0_last = ti.n0; tiles_n_last = g.tiles_n; N_last = g.N;
   }
   __device__ void finish(int wq, int lane) {
     slab.drain(lane);
-    if (p.per_cta && n0_last >= 0) {
+    if (CS == 1 && n0_last >= 0) {
       const size_t rowp = static_cast<size_t>(blockIdx.x / tiles_n_last) * 4 + wq;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = n0_last + (c_first + i) * 32 + lane;
-        if (i < cpw && col < N_last) p.colsum_partial[rowp * N_last + col] = csacc[i];
+      for (int si = 0; si < 2; ++si) {
+        const int col = n0_last + c_first * 32 + si * 64 + 2 * lane;
+        if (col < N_last) *reinterpret_cast<float2*>(p.colsum_partial + rowp * N_last + col) = csacc[si];
       }
     }
   }
 };
+typedef EpiDPreT<0> EpiDPre;
+typedef EpiDPreT<1> EpiDPreCta;
+typedef EpiDPreT<2> EpiDPreNoSum;
 
 }  // namespace svb

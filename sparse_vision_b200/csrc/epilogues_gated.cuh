@@ -46,8 +46,8 @@ struct EpiGatedEnc {
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
-                        int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float rp[32];
@@ -127,8 +127,8 @@ struct EpiGatedDPre {
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq,
-                        int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float e[32], t[32];

@@ -98,6 +98,9 @@ struct ColVecStage {
 // Epilogues may define `static constexpr bool kSkipAccLoad = true` (bring-up probes only) to skip the TMEM read.
 template <class E, class = void> struct epi_skips_acc_load { static constexpr bool value = false; };
 template <class E> struct epi_skips_acc_load<E, decltype(void(E::kSkipAccLoad))> { static constexpr bool value = E::kSkipAccLoad; };
+// Epilogues may define `static constexpr bool kPrefetchAcc = true` to double-buffer the TMEM reads in registers.
+template <class E, class = void> struct epi_prefetches_acc { static constexpr bool value = false; };
+template <class E> struct epi_prefetches_acc<E, decltype(void(E::kPrefetchAcc))> { static constexpr bool value = E::kPrefetchAcc; };
 
 __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int block_n) {
   TileInfo ti;
@@ -285,16 +288,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = ti.m0 + row_in_tile;
       epi.begin_tile(p, ti, row, wq, lane);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = cgroup * kChunksPerWarp; c < (cgroup + 1) * kChunksPerWarp; ++c) {
-        const int col0 = ti.n0 + c * 32;
-        if (col0 >= p.N) break;
-        float v[32];
-        if constexpr (!epi_skips_acc_load<Epi>::value) {
-          tmem_ld_32x32(t_addr + c * 32, v);
-          tmem_ld_wait();
+      // The warp's chunks are unrolled so that the chunk index `ci` is a compile-time constant inside Epi::chunk
+      // (per-chunk state lives in registers without select chains).  Epilogues with kPrefetchAcc read the next
+      // chunk's accumulators from TMEM while the current chunk is being processed.
+      if constexpr (epi_prefetches_acc<Epi>::value) {
+        float v[2][32];
+        const int c_begin = cgroup * kChunksPerWarp;
+        if (ti.n0 + c_begin * 32 < p.N) tmem_ld_32x32(t_addr + c_begin * 32, v[0]);
+#pragma unroll
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+          const int c = c_begin + ci;
+          const int col0 = ti.n0 + c * 32;
+          if (col0 < p.N) {
+            tmem_ld_wait();
+            if (ci + 1 < kChunksPerWarp && col0 + 32 < p.N) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(ci + 1) & 1]);
+            epi.chunk(p, ti, row, col0, v[ci & 1], wq, lane, ci);
+          }
         }
-        epi.chunk(p, ti, row, col0, v, wq, lane);
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+          const int c = cgroup * kChunksPerWarp + ci;
+          const int col0 = ti.n0 + c * 32;
+          if (col0 < p.N) {
+            float v[32];
+            if constexpr (!epi_skips_acc_load<Epi>::value) {
+              tmem_ld_32x32(t_addr + c * 32, v);
+              tmem_ld_wait();
+            }
+            epi.chunk(p, ti, row, col0, v, wq, lane, ci);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -133,14 +133,14 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
   SVB_TRY(run_prep(st, pl, p, false));
   const int T = static_cast<int>(pl.T);
-  EpiEnc::Params e1{};
+  EpiEncApi::Params e1{};
   e1.bias = pl.fold;
   e1.e_bf16 = (out->enc && out->enc_dtype == SVB_BF16) ? static_cast<bf16*>(out->enc) : pl.E;
   e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
   e1.pre_f32 = out->pre;
   e1.hw = pl.hw; e1.words = pl.words;
   if (make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
-  SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
+  SVB_GEMM((launch_gemm<256, false, false, EpiEncApi>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
   if (out->dec) {
     EpiDec::Params e2{};
     e2.bias = p->b_dec;
@@ -192,14 +192,16 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
                        out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
-  EpiDPre::Params e3{};
-  e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part;
-  e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
-  e3.per_cta = pl.bstat ? 1 : 0;
-  if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
+  const float l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   if (pl.bstat) {
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPre, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE (B-stationary)");
+    EpiDPreCta::Params e3{};
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c;
+    if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE (B-stationary)");
   } else {
+    EpiDPre::Params e3{};
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c;
+    if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
     SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
   }
   prof_mark(h, st, 5);

@@ -277,7 +277,7 @@ struct EpiProbe {
   __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
   __device__ void colvec_commit(uint32_t, int) {}
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32], int wq, int lane, int) {
     if (MODE == 2 || MODE == 9 || MODE == 10) {
       const int half = (col0 >> 5) & 1;
       const bool skip = MODE == 10 && ((col0 >> 6) & 1);
@@ -513,6 +513,46 @@ static int perf_write() {
   return 0;
 }
 
+// dE-shaped GEMM at cfg2 (A K-major [T,C], B MN-major [C,F], K = C = 256) with the three column-sum strategies
+template <class Epi>
+static void perf_de_one(const char* name, const void* dA, const void* dB, void* dE, uint32_t* mask, float* cs, int M, int N, int K) {
+  typename Epi::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mask_words = mask; ep.words = N / 32; ep.colsum_partial = cs; ep.l1c = 0.5f;
+  make_store_tmap_bf16(&ep.tm_dpre, dE, M, N, N);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) launch_gemm<256, false, true, Epi, true>(0, dA, K, dB, N, M, N, K, 1, ep);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int it = 0; it < 10; ++it) launch_gemm<256, false, true, Epi, true>(0, dA, K, dB, N, M, N, K, 1, ep);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= 10;
+  printf("[perf dE %-22s] %.3f ms  %.1f TFLOP/s\n", name, ms, 2.0 * M * N * K / ms * 1e-9);
+}
+static int perf_de() {
+  const int M = 200704, N = 2048, K = 256;
+  void *dA, *dB, *dE;
+  uint32_t* mask;
+  float* cs;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dE, (size_t)M * N * 2));
+  CK(cudaMalloc(&mask, (size_t)M * (N / 32) * 4));
+  CK(cudaMalloc(&cs, (size_t)(M / 32 + 4) * N * 4));
+  CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
+  CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
+  CK(cudaMemset(mask, 0x5a, (size_t)M * (N / 32) * 4));
+  perf_de_one<EpiDPre>("shuffle per tile", dA, dB, dE, mask, cs, M, N, K);
+  perf_de_one<EpiDPreCta>("per-thread accumulators", dA, dB, dE, mask, cs, M, N, K);
+  perf_de_one<EpiDPreNoSum>("no column sums", dA, dB, dE, mask, cs, M, N, K);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("%d\n", (int)(sizeof(kCases) / sizeof(kCases[0])));
@@ -522,6 +562,7 @@ int main(int argc, char** argv) {
   if (std::string(argv[1]) == "perf_enc") return perf_enc_variants();
   if (std::string(argv[1]) == "probe") return perf_probe();
   if (std::string(argv[1]) == "write") return perf_write();
+  if (std::string(argv[1]) == "perf_de") return perf_de();
   const int i = atoi(argv[1]);
   if (i < 0 || i >= (int)(sizeof(kCases) / sizeof(kCases[0]))) return 3;
   return dispatch(kCases[i]);
