@@ -13,6 +13,11 @@
 
 namespace svb {
 
+// Element offset of (row, col) in a slab-major [cols/64][rows][64] matrix (see make_tmap_bf16_slab in gemm_host.cuh).
+__host__ __device__ __forceinline__ size_t slab_offset(long long row, int col, long long rows) {
+  return (static_cast<size_t>(col >> 6) * static_cast<size_t>(rows) + static_cast<size_t>(row)) * 64 + (col & 63);
+}
+
 __device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32], int nvalid) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -116,12 +121,14 @@ struct SlabWriterT {
     }
     half_pending = (half == 0);
   }
-  // col0 / row0: element coordinates of the slab's first column / row in the output tensor
-  __device__ void flush(const CUtensorMap* tm, int col0, int row0, int lane) {
+  // col0 / row0: element coordinates of the slab's first column / row in the output tensor; slab_major: the
+  // tensor map is the 3-D slab-major one (gemm_host.cuh), coordinates {0, row, col / 64}
+  __device__ void flush(const CUtensorMap* tm, int col0, int row0, int lane, int slab_major = 0) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tm, base + which * 4096, col0, row0);
+      if (slab_major) tma_store_3d(tm, base + which * 4096, 0, row0, col0 >> 6);
+      else tma_store_2d(tm, base + which * 4096, col0, row0);
       bulk_commit();
     }
     if (NBUF > 1) which ^= 1;
@@ -244,6 +251,7 @@ struct EpiEncT {
     float* l1_partial;             // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
     int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
+    int e_slab;                    // e_bf16 / tm_e are slab-major (gemm_host.cuh)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -315,12 +323,12 @@ struct EpiEncT {
     if (p.e_bf16) {
       const int half = ci & 1;
       slab.put(half, lane, v);
-      if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane);
+      if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane, p.e_slab);
     }
     if (API && p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
-    if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane);
+    if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane, p.e_slab);
     const int w0 = (ti.n0 >> 5) + c_first;            // first word index of this warp
     const int nw = max(0, min(cpw, p.words - w0));
     if (p.mask_words && row < g.M && nw > 0) {
@@ -381,6 +389,8 @@ struct EpiDec {
     float* d_f32;                     // [M,N] or null
     __nv_bfloat16* diff_bf16;         // [M,N] or null
     float* sq_partial;                // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
+    int out_slab;                     // d_bf16 / diff_bf16 and their maps are slab-major
+    int x_slab;                       // x is slab-major
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -416,13 +426,15 @@ struct EpiDec {
     float b[32];
     const long long off = static_cast<long long>(row) * g.N + col0;
     float xv[32];
-    if (p.x) load_row_bf16(p.x + (row_ok ? off : 0), xv, row_ok ? nvalid : 0);   // issued early: an L2 round trip
+    if (p.x)  // issued early: an L2 round trip
+      load_row_bf16(p.x + (row_ok ? (p.x_slab ? static_cast<long long>(slab_offset(row, col0, g.M)) : off) : 0), xv,
+                    row_ok ? nvalid : 0);
     lds_row_f32(cv + (col0 - ti.n0), b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     if (p.d_bf16) {
       slab_d.put(half, lane, v);
-      if (half == 1) slab_d.flush(&p.tm_d, col0 - 32, ti.m0 + wq * 32, lane);
+      if (half == 1) slab_d.flush(&p.tm_d, col0 - 32, ti.m0 + wq * 32, lane, p.out_slab);
     }
     if (p.d_f32 && row_ok) store_row_f32(p.d_f32 + off, v, nvalid);
     if (p.x) {
@@ -433,14 +445,14 @@ struct EpiDec {
       }
       if (p.diff_bf16) {
         slab_f.put(half, lane, v);
-        if (half == 1) slab_f.flush(&p.tm_diff, col0 - 32, ti.m0 + wq * 32, lane);
+        if (half == 1) slab_f.flush(&p.tm_diff, col0 - 32, ti.m0 + wq * 32, lane, p.out_slab);
       }
     }
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
     const int last = ((g.N - 1) >> 6) << 6;
-    if (slab_d.half_pending) slab_d.flush(&p.tm_d, last, ti.m0 + wq * 32, lane);
-    if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane);
+    if (slab_d.half_pending) slab_d.flush(&p.tm_d, last, ti.m0 + wq * 32, lane, p.out_slab);
+    if (slab_f.half_pending) slab_f.flush(&p.tm_diff, last, ti.m0 + wq * 32, lane, p.out_slab);
   }
   __device__ void finish(int, int lane) {
     slab_d.drain(lane);
@@ -471,6 +483,7 @@ struct EpiDPreT {
                                        // CS = 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens
     float l1c;
     int words;
+    int out_slab;                      // dPre' and tm_dpre are slab-major
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 0;
@@ -551,7 +564,7 @@ struct EpiDPreT {
     slab.put(half, lane, v);
     if (half == 1) {
       slab_done(g, ti, col0 - 32, wq, lane, ci >> 1);
-      slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane);
+      slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane, p.out_slab);
     }
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
@@ -562,7 +575,7 @@ struct EpiDPreT {
       slab.put(1, lane, z);
       const int col_slab0 = ((g.N - 1) >> 6) << 6;
       slab_done(g, ti, col_slab0, wq, lane, ((col_slab0 - ti.n0) >> 6) & 1);
-      slab.flush(&p.tm_dpre, col_slab0, ti.m0 + wq * 32, lane);
+      slab.flush(&p.tm_dpre, col_slab0, ti.m0 + wq * 32, lane, p.out_slab);
     }
     n0_last = ti.n0; tiles_n_last = g.tiles_n; N_last = g.N;
   }

@@ -46,9 +46,31 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, u
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+// Slab-major bf16 matrix: logical [rows, cols] stored as [cols/64][rows][64], i.e. every 64-column slab keeps all its
+// rows contiguous (128 bytes per row).  A 128 x 64 operand tile or a 32 x 64 epilogue slab is then ONE contiguous
+// block of memory instead of 128-byte pieces at a row pitch of cols*2 bytes, which is what DRAM pages like; rows
+// beyond `rows` are clipped / zero-filled exactly as in the row-major case.  Needs cols % 64 == 0.
+// Coordinates are {0, row, col / 64}; box = 64 x box_rows x 1.
+inline int make_tmap_bf16_slab(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = tmap_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (cols % 64)) return -2;
+  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  cuuint64_t gstride[2] = {128, rows * 128};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
 // Row-major bf16 output [rows, cols] written in 32-row x 64-column slabs by the epilogue warps (128B swizzle).
 inline int make_store_tmap_bf16(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
   return make_tmap_bf16_2d(out, ptr, rows, cols, ld, 32);
+}
+inline int make_store_tmap_bf16_slab(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols) {
+  return make_tmap_bf16_slab(out, ptr, rows, cols, 32);
 }
 
 inline int device_sm_count() {
@@ -67,21 +89,26 @@ inline int device_sm_count() {
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0,
-                unsigned long long a_policy = 0) {
+                unsigned long long a_policy = 0, bool a_slab = false, bool b_slab = false) {
   using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
   int rc;
-  if (!A_MN) rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, kBlockM);
+  // slab-major operands: the logical matrix is [M, K] (K-major) or [K, M] (MN-major); lda / ldb are ignored
+  if (a_slab) rc = !A_MN ? make_tmap_bf16_slab(&tmA, A, M, K, kBlockM) : make_tmap_bf16_slab(&tmA, A, K, M, kBlockK);
+  else if (!A_MN) rc = make_tmap_bf16_2d(&tmA, A, M, K, lda, kBlockM);
   else rc = make_tmap_bf16_2d(&tmA, A, K, M, lda, kBlockK);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, BLOCK_N);
+  if (b_slab) rc = !B_MN ? make_tmap_bf16_slab(&tmB, B, N, K, BLOCK_N) : make_tmap_bf16_slab(&tmB, B, K, N, kBlockK);
+  else if (!B_MN) rc = make_tmap_bf16_2d(&tmB, B, N, K, ldb, BLOCK_N);
   else rc = make_tmap_bf16_2d(&tmB, B, K, N, ldb, kBlockK);
   if (rc) return rc;
 
   GemmProblem p;
   p.M = M; p.N = N; p.K = K;
   p.a_policy = a_policy;
+  p.a_slab = a_slab ? 1 : 0;
+  p.b_slab = b_slab ? 1 : 0;
   p.tiles_m = (M + kBlockM - 1) / kBlockM;
   p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int kblocks = (K + kBlockK - 1) / kBlockK;

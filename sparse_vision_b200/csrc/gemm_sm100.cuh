@@ -32,6 +32,7 @@ struct GemmProblem {
   int k_per_split;  // multiple of kBlockK
   int tiles_m, tiles_n;
   unsigned long long a_policy = 0, b_policy = 0;  // L2 eviction policy of the operand loads (0 = default)
+  int a_slab = 0, b_slab = 0;  // operand stored slab-major ([cols/64][rows][64], 3-D tensor map; see gemm_host.cuh)
 };
 
 struct TileInfo {
@@ -187,10 +188,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       auto load_b = [&](uint8_t* sb, uint64_t* bar, int k0, int n0) {
         if constexpr (!B_MN) {
-          tma_load_2d(sb, &tmB, bar, k0, n0);
+          if (p.b_slab) tma_load_3d(sb, &tmB, bar, 0, n0, k0 >> 6);
+          else tma_load_2d(sb, &tmB, bar, k0, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, bar, n0 + 64 * j, k0);
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            if (p.b_slab) tma_load_3d(sb + j * 8192, &tmB, bar, 0, k0, (n0 >> 6) + j);
+            else tma_load_2d(sb + j * 8192, &tmB, bar, n0 + 64 * j, k0);
+          }
         }
       };
       if constexpr (BSTAT) {
@@ -211,11 +216,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = k_begin + kb * kBlockK;
           if constexpr (!A_MN) {
-            if (p.a_policy) tma_load_2d_hint(sa, &tmA, &full_bar[stage], k0, ti.m0, p.a_policy);
+            if (p.a_slab) tma_load_3d(sa, &tmA, &full_bar[stage], 0, ti.m0, k0 >> 6);
+            else if (p.a_policy) tma_load_2d_hint(sa, &tmA, &full_bar[stage], k0, ti.m0, p.a_policy);
             else tma_load_2d(sa, &tmA, &full_bar[stage], k0, ti.m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.m0 + 64 * j, k0);
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if (p.a_slab) tma_load_3d(sa + j * 8192, &tmA, &full_bar[stage], 0, k0, (ti.m0 >> 6) + j);
+              else tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.m0 + 64 * j, k0);
+            }
           }
           if constexpr (!BSTAT) load_b(sa + Cfg::kABytes, &full_bar[stage], k0, ti.n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -151,9 +151,10 @@ template <int VEC> struct Row8<float, VEC> {
 
 // NCHW [B,C,HW] (bf16 or fp32) -> bf16 tokens [B*HW, C]; sae_mlp.py:44 'b c h w -> (b h w) c'.
 // grid (ceil(HW/64), ceil(C/64), B), 256 threads; bf16 staged in smem with a 2-element row pad.
+// slab_rows > 0: write the slab-major layout [C/64][slab_rows = B*HW][64] (gemm_host.cuh) instead of [B*HW, C].
 template <typename TIn, int VEC>
 static __global__ void __launch_bounds__(256)
-pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW) {
+pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW, long long slab_rows) {
   __shared__ uint16_t tile[64][66];  // [c][hw]
   const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const TIn* xb = x + static_cast<size_t>(b) * C * HW;
@@ -167,7 +168,7 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
     for (int k = 0; k < 4; ++k) dst[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
   }
   __syncthreads();
-  uint16_t* ob = reinterpret_cast<uint16_t*>(out) + static_cast<size_t>(b) * HW * C;
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out);
   for (int i = threadIdx.x; i < 64 * 8; i += 256) {
     const int p = i >> 3, co = (i & 7) * 8;
     if (p0 + p < HW && c0 + co < C) {
@@ -175,7 +176,9 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         w[k] = static_cast<uint32_t>(tile[co + 2 * k][p]) | (static_cast<uint32_t>(tile[co + 2 * k + 1][p]) << 16);
-      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(p0 + p) * C + c0 + co) = make_uint4(w[0], w[1], w[2], w[3]);
+      const size_t t = static_cast<size_t>(b) * HW + p0 + p;
+      const size_t off = slab_rows > 0 ? (static_cast<size_t>(blockIdx.y) * slab_rows + t) * 64 + co : t * C + c0 + co;
+      *reinterpret_cast<uint4*>(ob + off) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
@@ -190,10 +193,14 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
 template <typename TIn, typename TOut, int VEC>
 static __global__ void __launch_bounds__(256, 3)
 post_dec_nchw_kernel(const bf16* __restrict__ d_tok, const TIn* __restrict__ x, TOut* __restrict__ d_out,
-                     float* __restrict__ st, int C, int HW, int tiles_per_chunk) {
+                     float* __restrict__ st, int C, int HW, int tiles_per_chunk, long long slab_rows) {
   __shared__ uint16_t tile[64][66];  // [hw][c]
   const int b = blockIdx.y, c0 = blockIdx.x * 64, rc = blockIdx.z, R = gridDim.z;
-  const uint16_t* tb = reinterpret_cast<const uint16_t*>(d_tok) + static_cast<size_t>(b) * HW * C;
+  // d_tok: [B*HW, C] or, slab_rows > 0, slab-major [C/64][slab_rows][64]; tb points at (token b*HW, channel c0)
+  const size_t d_pitch = slab_rows > 0 ? 64 : static_cast<size_t>(C);
+  const uint16_t* tb = reinterpret_cast<const uint16_t*>(d_tok) +
+                       (slab_rows > 0 ? (static_cast<size_t>(blockIdx.x) * slab_rows + static_cast<size_t>(b) * HW) * 64
+                                      : static_cast<size_t>(b) * HW * C + c0);
   const TIn* xb = x + static_cast<size_t>(b) * C * HW;
   TOut* ob = d_out ? d_out + static_cast<size_t>(b) * C * HW : nullptr;
   const int p_begin = rc * tiles_per_chunk * 64, p_end = min(HW, p_begin + tiles_per_chunk * 64);
@@ -215,7 +222,7 @@ post_dec_nchw_kernel(const bf16* __restrict__ d_tok, const TIn* __restrict__ x, 
       const int i = threadIdx.x + 256 * k;
       const int p = i >> 3, co = (i & 7) * 8;
       dq[k] = make_uint4(0, 0, 0, 0);
-      if (p0 + p < p_end && c0 + co < C) dq[k] = __ldg(reinterpret_cast<const uint4*>(tb + static_cast<size_t>(p0 + p) * C + c0 + co));
+      if (p0 + p < p_end && c0 + co < C) dq[k] = __ldg(reinterpret_cast<const uint4*>(tb + static_cast<size_t>(p0 + p) * d_pitch + co));
       const int c = i >> 3, po = (i & 7) * 8;
       nv[k] = (c0 + c < C) ? max(0, min(8, p_end - (p0 + po))) : 0;
       Row8<TIn, VEC>::load(xb + static_cast<size_t>(c0 + c) * HW + p0 + po, nv[k], xv[k]);

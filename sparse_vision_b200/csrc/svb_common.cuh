@@ -152,8 +152,11 @@ inline int nchw_vec(const void* p, int hw, int elem_bytes) {
   if (hw % 4 == 0 && (a % (4 * elem_bytes)) == 0) return 4;
   return 1;
 }
-inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
+// slab_major: write [C/64][T][64] instead of [T, C] (NCHW inputs with C % 64 == 0 only; see gemm_host.cuh)
+inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf, bool slab_major = false) {
   const long long T = x->n_images * static_cast<long long>(x->hw);
+  if (slab_major && (x->layout != SVB_NCHW || x->hw == 1 || x->C % 64)) return fail(SVB_ERR_BAD_ARG, "slab-major pack needs NCHW input with C % 64 == 0");
+  const long long slab_rows = slab_major ? T : 0;
   if (x->layout == SVB_TOKENS || x->hw == 1) {
     const size_t n = static_cast<size_t>(T) * x->C;
     if (x->dtype == SVB_F32)
@@ -164,7 +167,7 @@ inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf) {
     if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
     const dim3 grid(cdiv(x->hw, 64), cdiv(x->C, 64), static_cast<unsigned>(x->n_images));
     const int vec = nchw_vec(x->x, x->hw, x->dtype == SVB_F32 ? 4 : 2);
-#define SVB_PACK(T, V) (pack_nchw_tile_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x->x), buf, x->C, x->hw), svb::count_launch())
+#define SVB_PACK(T, V) (pack_nchw_tile_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x->x), buf, x->C, x->hw, slab_rows), svb::count_launch())
     if (x->dtype == SVB_F32) { if (vec >= 4) SVB_PACK(float, 4); else SVB_PACK(float, 1); }
     else { if (vec == 8) SVB_PACK(bf16, 8); else if (vec == 4) SVB_PACK(bf16, 4); else SVB_PACK(bf16, 1); }
 #undef SVB_PACK
@@ -241,12 +244,16 @@ inline int run_channel_stats(cudaStream_t st, const bf16* X, const bf16* D, long
 // Fused statistics + NCHW write-back after the decoder GEMM (post_dec_nchw_kernel) when the SAE input is NCHW;
 // otherwise the token-major statistics kernel followed by a layout/dtype conversion of d.
 //   x: the caller's activations; X / D: token-major bf16 views; dec_out may be null.
+// The fused kernel is used when post_dec_fusable() holds; only then may D be slab-major.
+inline bool post_dec_fusable(const svb_acts* x, const void* dec_out, int dec_layout) {
+  return x->layout == SVB_NCHW && x->hw > 1 && (!dec_out || dec_layout == SVB_NCHW) && x->n_images <= 65535;
+}
 inline int run_post_dec(cudaStream_t st, const svb_acts* x, const bf16* X, const bf16* D, long long T, void* dec_out,
-                        int dec_dtype, int dec_layout, float* stbuf, float* chan, float* var_part, float* rowvar) {
+                        int dec_dtype, int dec_layout, float* stbuf, float* chan, float* var_part, float* rowvar,
+                        bool d_slab = false) {
   const int C = x->C, hw = x->hw;
-  const bool nchw_in = x->layout == SVB_NCHW && hw > 1;
-  const bool out_ok = !dec_out || (dec_layout == SVB_NCHW);
-  if (nchw_in && out_ok && x->n_images <= 65535) {
+  const long long slab_rows = d_slab ? T : 0;
+  if (post_dec_fusable(x, dec_out, dec_layout)) {
     int vec = nchw_vec(x->x, hw, x->dtype == SVB_F32 ? 4 : 2);
     if (dec_out) {
       const int vo = nchw_vec(dec_out, hw, dec_dtype == SVB_F32 ? 4 : 2);
@@ -263,7 +270,7 @@ inline int run_post_dec(cudaStream_t st, const svb_acts* x, const bf16* X, const
     const dim3 grid(cdiv(C, 64), static_cast<unsigned>(x->n_images), R);
 #define SVB_POST(TI, TO, V)                                                                                          \
   (post_dec_nchw_kernel<TI, TO, V><<<grid, 256, 0, st>>>(D, static_cast<const TI*>(x->x), static_cast<TO*>(dec_out), \
-                                                          stbuf, C, hw, tiles_per_chunk), svb::count_launch())
+                                                          stbuf, C, hw, tiles_per_chunk, slab_rows), svb::count_launch())
 #define SVB_POST_V(TI, TO)                                     \
   do {                                                         \
     if (vec == 8) SVB_POST(TI, TO, 8);                         \
@@ -279,6 +286,7 @@ inline int run_post_dec(cudaStream_t st, const svb_acts* x, const bf16* X, const
     SVB_LAUNCH_CHECK("post_dec");
     return 0;
   }
+  if (d_slab) return fail(SVB_ERR_BAD_ARG, "slab-major decoder output needs the fused post-decoder pass");
   SVB_TRY(run_channel_stats(st, X, D, x->n_images, hw, T, C, stbuf, chan, var_part, rowvar));
   if (dec_out) SVB_TRY(unpack_to(st, D, x->n_images, hw, C, dec_out, dec_dtype, dec_layout));
   return 0;

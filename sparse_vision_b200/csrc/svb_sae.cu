@@ -28,6 +28,7 @@ struct SaePlan {
   int s_wd, s_we;  // split-K slices
   int sms;
   bool zero_copy_x, bstat;  // bstat: the K <= 256 GEMMs run B-stationary (per-CTA column-sum partials)
+  bool xs, es;              // slab-major workspaces: X / D / DIFF (xs) and E / dPre' (es), see gemm_host.cuh
   int cs_rows;              // rows of colsum_part
   size_t zero_words;        // 32-bit words to clear at the start of a step, from act_bits on
   // workspace
@@ -50,6 +51,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.tn_f = cdiv(F, 256);
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
+  p.xs = false; p.es = false;
   const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
   p.Web = a.take<bf16>(FC);
@@ -162,9 +164,13 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  // Slab-major workspaces (every 128 x 64 operand tile / 32 x 64 epilogue slab is one contiguous block):
+  // E and dPre' whenever F % 64 == 0; X, D, DIFF when we pack X ourselves from NCHW and the fused post-decoder pass runs.
+  pl.es = F % 64 == 0;
+  pl.xs = !pl.zero_copy_x && C % 64 == 0 && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
   prof_begin_step(h);
   prof_mark(h, st, 0);
-  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs));
   SVB_TRY(run_prep(st, pl, p, true));
 
   prof_mark(h, st, 1);
@@ -172,46 +178,51 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   EpiEnc::Params e1{};
   e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
   e1.mask_words = pl.mask;
-  e1.hw = pl.hw; e1.words = pl.words;
-  if (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
+  e1.hw = pl.hw; e1.words = pl.words; e1.e_slab = pl.es;
+  if (pl.es ? make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F))
+    return fail(SVB_ERR_TMAP, "tensor map for E");
   if (pl.bstat) {
-    SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc (B-stationary)");
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc (B-stationary)");
   } else {
-    SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1)), "enc");
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");
   }
   prof_mark(h, st, 2);
   // G2 decoder
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
-  if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))
+  e2.out_slab = pl.xs; e2.x_slab = pl.xs;
+  if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
+            : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
     return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
   prof_mark(h, st, 3);
   // channel statistics + the decoder output handed back to the model (model_pipeline.py:425,432), one pass
   SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
-                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
+                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
   const float l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   if (pl.bstat) {
     EpiDPreCta::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c;
-    if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE (B-stationary)");
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
+    if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F))
+      return fail(SVB_ERR_TMAP, "tensor map for dPre");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE (B-stationary)");
   } else {
     EpiDPre::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c;
-    if (make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F)) return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "dE");
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
+    if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F))
+      return fail(SVB_ERR_TMAP, "tensor map for dPre");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
   }
   prof_mark(h, st, 5);
   // G4 / G5 weight gradients, split-K over tokens
   const size_t FC = static_cast<size_t>(F) * C;
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
   prof_mark(h, st, 6);
   EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5)), "dW_enc");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
 
   prof_mark(h, st, 7);
   // gradient assembly: column sums -> merged assembly kernel -> one-block tail
