@@ -152,20 +152,48 @@ template <int VEC> struct Row8<float, VEC> {
 // NCHW [B,C,HW] (bf16 or fp32) -> bf16 tokens [B*HW, C]; sae_mlp.py:44 'b c h w -> (b h w) c'.
 // grid (ceil(HW/64), ceil(C/64), B), 256 threads; bf16 staged in smem with a 2-element row pad.
 // slab_rows > 0: write the slab-major layout [C/64][slab_rows = B*HW][64] (gemm_host.cuh) instead of [B*HW, C].
+// xpart != null: also emit, per image, HW tile and channel, the statistics of the bf16-rounded x that the loss
+// metrics need (sum, sum of squares, min, max): xpart[((b * gridDim.x + tile) * 4 + q) * C + c].
 template <typename TIn, int VEC>
 static __global__ void __launch_bounds__(256)
-pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW, long long slab_rows) {
+pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW, long long slab_rows,
+                      float* __restrict__ xpart) {
   __shared__ uint16_t tile[64][66];  // [c][hw]
   const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const TIn* xb = x + static_cast<size_t>(b) * C * HW;
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int i = threadIdx.x + 256 * it;
     const int c = i >> 3, po = (i & 7) * 8;
     float v[8];
     const int nv = (c0 + c < C) ? max(0, min(8, HW - (p0 + po))) : 0;
     Row8<TIn, VEC>::load(xb + static_cast<size_t>(c0 + c) * HW + p0 + po, nv, v);
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[c][po]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+    for (int k = 0; k < 4; ++k) dst[k] = w[k];
+    if (xpart) {  // the 8 lanes that share channel c combine their 8 positions each (fixed butterfly order)
+      float sx = 0.f, sx2 = 0.f, mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = bf16lo(w[k]), hi = bf16hi(w[k]);
+        if (2 * k < nv) { sx += lo; sx2 += lo * lo; mn = fminf(mn, lo); mx = fmaxf(mx, lo); }
+        if (2 * k + 1 < nv) { sx += hi; sx2 += hi * hi; mn = fminf(mn, hi); mx = fmaxf(mx, hi); }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sx2 += __shfl_xor_sync(0xffffffffu, sx2, o);
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if ((threadIdx.x & 7) == 0 && c0 + c < C) {
+        float* o = xpart + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 4 * C + c0 + c;
+        o[0] = sx; o[C] = sx2; o[2 * C] = mn; o[3 * C] = mx;
+      }
+    }
   }
   __syncthreads();
   uint16_t* ob = reinterpret_cast<uint16_t*>(out);
@@ -431,6 +459,39 @@ channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, flo
       }
     }
   }
+}
+
+// Per-image channel statistics when the decoder epilogue (EpiDecNchw) and the pack kernel produced the partials:
+//   dpart[((g * 2 + slot) * 3 + q) * C + c]   g = 32-token row group, slot = image index relative to the group's first
+//                                             image, q = sum d, sum d^2 (per image) and sum (d-x)^2 (whole group, slot 0)
+//   xpart[((b * NT + tile) * 4 + q) * C + c]  q = sum x, sum x^2, min x, max x per HW tile of 64 positions
+// -> st[(b * 8 + q) * C + c] in the channel_stats layout with one chunk (sum x, x^2, d, d^2, d-x, (d-x)^2, min x, max x).
+// A group's sum (d-x)^2 is credited to its first image; only its total over images is used downstream.
+static __global__ void __launch_bounds__(256)
+dec_stats_gather_kernel(const float* __restrict__ dpart, const float* __restrict__ xpart, float* __restrict__ st, int C,
+                        int HW, int NT, long long T) {
+  const int b = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  const long long t0 = static_cast<long long>(b) * HW, t1 = t0 + HW - 1;
+  const long long g0 = t0 >> 5, g1 = min(t1, T - 1) >> 5;
+  float sd = 0.f, sd2 = 0.f, sq = 0.f;
+  for (long long g = g0; g <= g1; ++g) {
+    const int slot = b - static_cast<int>((g << 5) / HW);
+    const float* p = dpart + (static_cast<size_t>(g) * 2 + slot) * 3 * C + c;
+    sd += p[0];
+    sd2 += p[C];
+    if (slot == 0) sq += p[2 * C];
+  }
+  float sx = 0.f, sx2 = 0.f, mn = INFINITY, mx = -INFINITY;
+  for (int t = 0; t < NT; ++t) {
+    const float* p = xpart + (static_cast<size_t>(b) * NT + t) * 4 * C + c;
+    sx += p[0];
+    sx2 += p[C];
+    mn = fminf(mn, p[2 * C]);
+    mx = fmaxf(mx, p[3 * C]);
+  }
+  float* o = st + static_cast<size_t>(b) * 8 * C + c;
+  o[0] = sx; o[C] = sx2; o[2 * C] = sd; o[3 * C] = sd2; o[4 * C] = sd - sx; o[5 * C] = sq; o[6 * C] = mn; o[7 * C] = mx;
 }
 
 // Collapse [B][R][8][C] chunk stats into: chan[0][c] = sum diff, chan[1][c] = sum diff^2, chan[2][c] = min x,

@@ -153,7 +153,7 @@ inline int nchw_vec(const void* p, int hw, int elem_bytes) {
   return 1;
 }
 // slab_major: write [C/64][T][64] instead of [T, C] (NCHW inputs with C % 64 == 0 only; see gemm_host.cuh)
-inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf, bool slab_major = false) {
+inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf, bool slab_major = false, float* xpart = nullptr) {
   const long long T = x->n_images * static_cast<long long>(x->hw);
   if (slab_major && (x->layout != SVB_NCHW || x->hw == 1 || x->C % 64)) return fail(SVB_ERR_BAD_ARG, "slab-major pack needs NCHW input with C % 64 == 0");
   const long long slab_rows = slab_major ? T : 0;
@@ -167,7 +167,7 @@ inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf, bool slab_ma
     if (x->n_images > 65535) return fail(SVB_ERR_UNSUPPORTED, "more than 65535 images per call");
     const dim3 grid(cdiv(x->hw, 64), cdiv(x->C, 64), static_cast<unsigned>(x->n_images));
     const int vec = nchw_vec(x->x, x->hw, x->dtype == SVB_F32 ? 4 : 2);
-#define SVB_PACK(T, V) (pack_nchw_tile_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x->x), buf, x->C, x->hw, slab_rows), svb::count_launch())
+#define SVB_PACK(T, V) (pack_nchw_tile_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x->x), buf, x->C, x->hw, slab_rows, xpart), svb::count_launch())
     if (x->dtype == SVB_F32) { if (vec >= 4) SVB_PACK(float, 4); else SVB_PACK(float, 1); }
     else { if (vec == 8) SVB_PACK(bf16, 8); else if (vec == 4) SVB_PACK(bf16, 4); else SVB_PACK(bf16, 1); }
 #undef SVB_PACK

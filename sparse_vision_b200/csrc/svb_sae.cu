@@ -29,6 +29,9 @@ struct SaePlan {
   int sms;
   bool zero_copy_x, bstat;  // bstat: the K <= 256 GEMMs run B-stationary (per-CTA column-sum partials)
   bool xs, es;              // slab-major workspaces: X / D / DIFF (xs) and E / dPre' (es), see gemm_host.cuh
+  bool fused_dec;           // decoder epilogue writes NCHW d and the channel statistics itself (EpiDecNchw)
+  int nt_hw;                // HW tiles of 64 positions (x statistics of the pack kernel)
+  float *xpart, *dpart;
   int cs_rows;              // rows of colsum_part
   size_t zero_words;        // 32-bit words to clear at the start of a step, from act_bits on
   // workspace
@@ -51,7 +54,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.tn_f = cdiv(F, 256);
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
-  p.xs = false; p.es = false;
+  p.xs = false; p.es = false; p.fused_dec = false;
   const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
   p.Web = a.take<bf16>(FC);
@@ -83,6 +86,9 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
   p.P_we = a.take<float>(static_cast<size_t>(p.s_we) * FC);
   p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
+  p.nt_hw = cdiv(p.hw, 64);
+  p.xpart = a.take<float>(static_cast<size_t>(p.n_img) * p.nt_hw * 4 * p.C);
+  p.dpart = a.take<float>(static_cast<size_t>(p.tiles_m) * 4 * 2 * 3 * p.C);
   p.nact_f = a.take<float>(p.n_img);
   p.o_gwe = 0; p.o_gbe = FC; p.o_gwd = FC + F; p.o_gbd = 2 * FC + F;
   p.o_sums = 2 * FC + F + p.C;
@@ -168,9 +174,14 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // E and dPre' whenever F % 64 == 0; X, D, DIFF when we pack X ourselves from NCHW and the fused post-decoder pass runs.
   pl.es = F % 64 == 0;
   pl.xs = !pl.zero_copy_x && C % 64 == 0 && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
+  // Fused decoder epilogue: needs the slab-major path, >= 32 tokens per image (a warp's 32 tokens then touch at most
+  // two images) and, if d is handed back, a bf16 NCHW tensor TMA can address (16-byte row pitch).
+  void* dec_out = out ? out->dec_out : nullptr;
+  pl.fused_dec = pl.xs && pl.hw >= 32 &&
+                 (!dec_out || (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0));
   prof_begin_step(h);
   prof_mark(h, st, 0);
-  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs));
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs, pl.fused_dec ? pl.xpart : nullptr));
   SVB_TRY(run_prep(st, pl, p, true));
 
   prof_mark(h, st, 1);
@@ -188,17 +199,30 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   }
   prof_mark(h, st, 2);
   // G2 decoder
-  EpiDec::Params e2{};
-  e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
-  e2.out_slab = pl.xs; e2.x_slab = pl.xs;
-  if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
-            : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
-    return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
-  prof_mark(h, st, 3);
-  // channel statistics + the decoder output handed back to the model (model_pipeline.py:425,432), one pass
-  SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
-                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
+  if (pl.fused_dec) {
+    EpiDecNchw::Params e2{};
+    e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
+    e2.out = static_cast<bf16*>(dec_out);
+    if (make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
+    if (dec_out && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
+    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
+    prof_mark(h, st, 3);
+    (dec_stats_gather_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
+    (channel_stats_finalize_kernel<<<cdiv(C, 8), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), 1, C, pl.hw), svb::count_launch());
+    SVB_LAUNCH_CHECK("decoder statistics");
+  } else {
+    EpiDec::Params e2{};
+    e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+    e2.out_slab = pl.xs; e2.x_slab = pl.xs;
+    if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
+              : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
+      return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
+    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
+    prof_mark(h, st, 3);
+    // channel statistics + the decoder output handed back to the model (model_pipeline.py:425,432), one pass
+    SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, dec_out, out ? out->dec_dtype : SVB_BF16,
+                         out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
+  }
   prof_mark(h, st, 4);
   // G3 dE -> dPre'
   const float l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));

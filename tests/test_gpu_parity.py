@@ -224,6 +224,8 @@ def test_adam_step_and_reinit(golden_dir):
     (5, 64, 7, 7, 4, "sae_mlp"),         # 49-pixel images: warps straddle image boundaries, ragged token count
     (6, 128, 14, 14, 4, "gated_sae"),    # cfg3 family
     (3, 528, 14, 14, 4, "sae_mlp"),      # C not a multiple of 64/128/256 (K and N tails)
+    (3, 64, 12, 12, 4, "sae_mlp"),       # fused NCHW decoder epilogue: 144-pixel images straddle warps, ragged last tile
+    (5, 128, 8, 8, 8, "sae_mlp"),        # fused path with two images per 128-token tile
 ])
 def test_train_step_vs_oracle_larger(B, C, H, W, k, kind):
     ops = _ops()
