@@ -465,33 +465,90 @@ channel_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ d, flo
 //   dpart[((g * 2 + slot) * 3 + q) * C + c]   g = 32-token row group, slot = image index relative to the group's first
 //                                             image, q = sum d, sum d^2 (per image) and sum (d-x)^2 (whole group, slot 0)
 //   xpart[((b * NT + tile) * 4 + q) * C + c]  q = sum x, sum x^2, min x, max x per HW tile of 64 positions
-// -> st[(b * 8 + q) * C + c] in the channel_stats layout with one chunk (sum x, x^2, d, d^2, d-x, (d-x)^2, min x, max x).
+// Stage 1, grid (B, ceil(C/64)), 256 threads = 4 group lanes x 64 channels (a warp reads 32 consecutive channels):
+//   vb[(b * 6 + q) * C + c] = Var_hw(x), Var_hw(d) (unbiased, utils.py:2015,2020), sum (d-x), sum (d-x)^2, min x, max x.
 // A group's sum (d-x)^2 is credited to its first image; only its total over images is used downstream.
 static __global__ void __launch_bounds__(256)
-dec_stats_gather_kernel(const float* __restrict__ dpart, const float* __restrict__ xpart, float* __restrict__ st, int C,
-                        int HW, int NT, long long T) {
-  const int b = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= C) return;
-  const long long t0 = static_cast<long long>(b) * HW, t1 = t0 + HW - 1;
-  const long long g0 = t0 >> 5, g1 = min(t1, T - 1) >> 5;
-  float sd = 0.f, sd2 = 0.f, sq = 0.f;
-  for (long long g = g0; g <= g1; ++g) {
-    const int slot = b - static_cast<int>((g << 5) / HW);
-    const float* p = dpart + (static_cast<size_t>(g) * 2 + slot) * 3 * C + c;
-    sd += p[0];
-    sd2 += p[C];
-    if (slot == 0) sq += p[2 * C];
+dec_stats_image_kernel(const float* __restrict__ dpart, const float* __restrict__ xpart, float* __restrict__ vb, int C,
+                       int HW, int NT, long long T) {
+  __shared__ float sh[4][7][64];
+  const int b = blockIdx.x, cl = threadIdx.x & 63, gl = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  const long long t0 = static_cast<long long>(b) * HW, t1 = min(t0 + HW, T) - 1;
+  const long long g0 = t0 >> 5, g1 = t1 >> 5;
+  float sd = 0.f, sd2 = 0.f, sq = 0.f, sx = 0.f, sx2 = 0.f, mn = INFINITY, mx = -INFINITY;
+  if (c < C) {
+    for (long long g = g0 + gl; g <= g1; g += 4) {
+      const int slot = b - static_cast<int>((g << 5) / HW);
+      const float* p = dpart + (static_cast<size_t>(g) * 2 + slot) * 3 * C + c;
+      sd += p[0];
+      sd2 += p[C];
+      if (slot == 0) sq += p[2 * C];
+    }
+    for (int t = gl; t < NT; t += 4) {
+      const float* p = xpart + (static_cast<size_t>(b) * NT + t) * 4 * C + c;
+      sx += p[0];
+      sx2 += p[C];
+      mn = fminf(mn, p[2 * C]);
+      mx = fmaxf(mx, p[3 * C]);
+    }
   }
-  float sx = 0.f, sx2 = 0.f, mn = INFINITY, mx = -INFINITY;
-  for (int t = 0; t < NT; ++t) {
-    const float* p = xpart + (static_cast<size_t>(b) * NT + t) * 4 * C + c;
-    sx += p[0];
-    sx2 += p[C];
-    mn = fminf(mn, p[2 * C]);
-    mx = fmaxf(mx, p[3 * C]);
+  sh[gl][0][cl] = sd; sh[gl][1][cl] = sd2; sh[gl][2][cl] = sq; sh[gl][3][cl] = sx; sh[gl][4][cl] = sx2;
+  sh[gl][5][cl] = mn; sh[gl][6][cl] = mx;
+  __syncthreads();
+  if (gl == 0 && c < C) {
+    for (int k = 1; k < 4; ++k) {
+      sd += sh[k][0][cl]; sd2 += sh[k][1][cl]; sq += sh[k][2][cl]; sx += sh[k][3][cl]; sx2 += sh[k][4][cl];
+      mn = fminf(mn, sh[k][5][cl]); mx = fmaxf(mx, sh[k][6][cl]);
+    }
+    const float inv = 1.f / static_cast<float>(HW), invm1 = HW > 1 ? 1.f / static_cast<float>(HW - 1) : 0.f;
+    float* o = vb + static_cast<size_t>(b) * 6 * C + c;
+    o[0] = fmaxf(sx2 - sx * sx * inv, 0.f) * invm1;
+    o[C] = fmaxf(sd2 - sd * sd * inv, 0.f) * invm1;
+    o[2 * C] = sd - sx;
+    o[3 * C] = sq;
+    o[4 * C] = mn;
+    o[5 * C] = mx;
   }
-  float* o = st + static_cast<size_t>(b) * 8 * C + c;
-  o[0] = sx; o[C] = sx2; o[2 * C] = sd; o[3 * C] = sd2; o[4 * C] = sd - sx; o[5 * C] = sq; o[6 * C] = mn; o[7 * C] = mx;
+}
+// Stage 2, grid ceil(C/32), 1024 threads = 32 image lanes x 32 channels: the same outputs as
+// channel_stats_finalize_kernel (chan[4][C] and one (sum Var x, sum Var d) pair per block), images in a fixed order.
+static __global__ void __launch_bounds__(1024)
+dec_stats_channel_kernel(const float* __restrict__ vb, float* __restrict__ chan, float* __restrict__ var_partial, int B,
+                         int C) {
+  __shared__ float sh[32][6][33];
+  __shared__ float sv[2][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float vx = 0.f, vd = 0.f, sdf = 0.f, sq = 0.f, mn = INFINITY, mx = -INFINITY;
+  if (c < C)
+    for (int b = bl; b < B; b += 32) {
+      const float* p = vb + static_cast<size_t>(b) * 6 * C + c;
+      vx += p[0]; vd += p[C]; sdf += p[2 * C]; sq += p[3 * C];
+      mn = fminf(mn, p[4 * C]); mx = fmaxf(mx, p[5 * C]);
+    }
+  sh[bl][0][cl] = vx; sh[bl][1][cl] = vd; sh[bl][2][cl] = sdf; sh[bl][3][cl] = sq; sh[bl][4][cl] = mn; sh[bl][5][cl] = mx;
+  __syncthreads();
+  if (bl < 6) {  // warp q combines statistic q over the 32 image lanes
+    const int q = bl;
+    float t = sh[0][q][cl];
+    for (int k = 1; k < 32; ++k) {
+      const float o = sh[k][q][cl];
+      t = q < 4 ? t + o : (q == 4 ? fminf(t, o) : fmaxf(t, o));
+    }
+    if (q >= 2) {
+      if (c < C) chan[(q - 2) * C + c] = t;
+    } else {
+      sv[q][cl] = c < C ? t : 0.f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bb = 0.f;
+    for (int k = 0; k < 32; ++k) { a += sv[0][k]; bb += sv[1][k]; }
+    var_partial[blockIdx.x * 2] = a;
+    var_partial[blockIdx.x * 2 + 1] = bb;
+  }
 }
 
 // Collapse [B][R][8][C] chunk stats into: chan[0][c] = sum diff, chan[1][c] = sum diff^2, chan[2][c] = min x,

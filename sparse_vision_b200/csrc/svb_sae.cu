@@ -207,8 +207,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (dec_out && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
-    (dec_stats_gather_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 256)), 256, 0, st>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
-    (channel_stats_finalize_kernel<<<cdiv(C, 8), 256, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), 1, C, pl.hw), svb::count_launch());
+    (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, st>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
+    (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
     SVB_LAUNCH_CHECK("decoder statistics");
   } else {
     EpiDec::Params e2{};
@@ -267,7 +267,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
   ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 8;
   ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
-  ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
+  ta.var_part = pl.var_part; ta.n_var_part = pl.fused_dec ? cdiv(C, 32) : cdiv(C, 8);
+  ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
   ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
   (grads_tail_kernel<<<1, 1024, 0, st>>>(ta), svb::count_launch());
   SVB_LAUNCH_CHECK("grad assembly");
