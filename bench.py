@@ -203,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -356,10 +356,28 @@ def run_svb(args):
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_images} images = {args.cpu_images * HW_SIDE * HW_SIDE} tokens per step, "
                           f"1 warm-up + 2 timed steps of oracle/sae_oracle.py (fp32 torch CPU)"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout) must not share the channel of the ONE JSON line: fd 1 is
+    pointed at stderr for the whole run and the line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -374,6 +392,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "svb":
         args.warmup = 3
+    _quiet_stdout()
     return run_reference(args) if args.impl == "reference" else run_svb(args)
 
 

@@ -166,6 +166,26 @@ int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x, const svb
  * partial sums.  *sum_elems (SUM all-reduce) then *max_elems (MAX all-reduce) elements. */
 int svb_sae_grad_buffer(svb_handle* h, float** buf, int64_t* sum_elems, int64_t* max_elems);
 
+/* Data-parallel overlap (the reference has no distributed code).  With a communication stream
+ * set, svb_*_step_grads makes that stream wait until the LEADING svb_grad_early_elems() elements of the flat buffer
+ * (the encoder-side gradients, [gW_enc | gb_enc] resp. [gW_gate | gb_gate | gb_mag | gr_mag]) are final; the caller
+ * all-reduces them on it while the decoder weight-gradient GEMM is still running on `stream`, and the rest of the
+ * SUM section afterwards.  Pass NULL to switch the early release off (the default). */
+int svb_set_comm_stream(svb_handle* h, void* stream);
+int svb_grad_early_elems(svb_handle* h, int64_t* elems);
+
+/* Data-parallel exchange in peer memory (one node, <= 8 ranks).  svb_comm_alloc creates the
+ * exchange buffer (capacity n_floats >= sum_elems + max_elems of the steps that will use it) and returns its 64-byte
+ * CUDA IPC handle; the caller gathers the handles of all ranks (e.g. torch.distributed.all_gather_object) and passes
+ * them, in rank order, to svb_comm_connect.  From then on svb_*_step_grads builds its flat buffer there and
+ * svb_comm_allreduce reduces it in place on every rank with ONE kernel over NVLink (SUM section and MAX section,
+ * fixed rank order => bit-identical results everywhere).  All ranks must call it once per step, in step order. */
+int svb_comm_alloc(svb_handle* h, int64_t n_floats, void* ipc_handle_out_host);
+int svb_comm_connect(svb_handle* h, int32_t rank, int32_t world, const void* ipc_handles_host);
+int svb_comm_capacity(svb_handle* h, int64_t* n_floats);
+int svb_comm_allreduce(svb_handle* h, void* stream);
+int svb_comm_destroy(svb_handle* h);
+
 /* GatedSae forward / step — models/gated_sae.py:28-56, losses/sparse_loss.py:68-76. */
 typedef struct svb_gated_forward_out {
   void* enc;     int32_t enc_dtype;

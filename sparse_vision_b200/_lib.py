@@ -86,6 +86,13 @@ SYMBOLS = {
     "svb_sae_step_apply": (C.c_int, [_vp, _vp, _P(Acts), _P(SaeParams), _P(AdamState), _P(OptConfig), C.c_float,
                                      C.c_int32, C.c_int64, C.c_int64, _P(TrainOut)]),
     "svb_sae_grad_buffer": (C.c_int, [_vp, _P(_vp), _P(C.c_int64), _P(C.c_int64)]),
+    "svb_set_comm_stream": (C.c_int, [_vp, _vp]),
+    "svb_comm_alloc": (C.c_int, [_vp, C.c_int64, _vp]),
+    "svb_comm_connect": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp]),
+    "svb_comm_capacity": (C.c_int, [_vp, _P(C.c_int64)]),
+    "svb_comm_allreduce": (C.c_int, [_vp, _vp]),
+    "svb_comm_destroy": (C.c_int, [_vp]),
+    "svb_grad_early_elems": (C.c_int, [_vp, _P(C.c_int64)]),
     "svb_gated_forward": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), _P(GatedForwardOut)]),
     "svb_gated_train_step": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), _P(AdamState), _P(OptConfig), C.c_float,
                                        C.c_int32, _P(TrainOut)]),

@@ -823,19 +823,20 @@ struct AssembleArgs {
   const uint32_t* act_bits; float* count; int32_t* n_active; float* nact_f; int n_img, words;
   int F, C;
   float s;
-  int nb_w, nb_b, nb_vm, nb_cnt, nb_img;
+  int nb_wd, nb_w, nb_b, nb_vm, nb_cnt, nb_img;  // nb_wd = 0 / nb_w..nb_img = 0: that part is not run by this launch
 };
 static __global__ void __launch_bounds__(256) assemble_grads_kernel(const AssembleArgs a) {
   __shared__ int sh[8][33];
   int blk = blockIdx.x;
   const size_t n = static_cast<size_t>(a.F) * a.C;
-  if (blk < 2 * a.nb_w) {
-    const bool enc = blk >= a.nb_w;
-    if (enc) blk -= a.nb_w;
+  if (blk < a.nb_wd + a.nb_w) {
+    const bool enc = blk >= a.nb_wd;
+    if (enc) blk -= a.nb_wd;
     const float* part = enc ? a.P_we : a.P_wd;
     const int splits = enc ? a.s_we : a.s_wd;
     float* out = enc ? a.g_wenc : a.g_wdec;
-    for (size_t i = (static_cast<size_t>(blk) * 256 + threadIdx.x) * 4; i < n; i += static_cast<size_t>(a.nb_w) * 1024) {
+    const int nb = enc ? a.nb_w : a.nb_wd;
+    for (size_t i = (static_cast<size_t>(blk) * 256 + threadIdx.x) * 4; i < n; i += static_cast<size_t>(nb) * 1024) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < splits; ++k) {
         const float4 q = *reinterpret_cast<const float4*>(part + static_cast<size_t>(k) * n + i);
@@ -851,7 +852,7 @@ static __global__ void __launch_bounds__(256) assemble_grads_kernel(const Assemb
     }
     return;
   }
-  blk -= 2 * a.nb_w;
+  blk -= a.nb_wd + a.nb_w;
   if (blk < a.nb_b) {
     const int f = blk * 256 + threadIdx.x;
     if (a.g_benc && f < a.F) a.g_benc[f] = a.csum[f] * a.s;

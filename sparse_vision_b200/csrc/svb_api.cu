@@ -27,6 +27,8 @@ extern "C" int svb_create(svb_handle** out) {
 extern "C" int svb_destroy(svb_handle* h) {
   if (!h) return 0;
   if (h->arena.base) cudaFree(h->arena.base);
+  if (h->ev_early) cudaEventDestroy(h->ev_early);
+  svb_comm_destroy(h);
   delete h;
   return 0;
 }
@@ -35,7 +37,18 @@ extern "C" int64_t svb_launch_count(void) { return static_cast<int64_t>(launch_c
 
 // ---------------------------------------------------------------------------------------------------- profiling
 static const char* kPhaseNames[] = {"pack+prep", "enc_gemm", "dec_gemm", "channel_stats", "dE_gemm",
-                                    "dWdec_gemm", "dWenc_gemm", "grad_assembly", "adam+finalize"};
+                                    "dWenc_gemm", "dWdec_gemm", "grad_assembly", "adam+finalize"};
+
+extern "C" int svb_set_comm_stream(svb_handle* h, void* stream) {
+  if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  h->comm = static_cast<cudaStream_t>(stream);
+  return 0;
+}
+extern "C" int svb_grad_early_elems(svb_handle* h, int64_t* elems) {
+  if (!h || !elems) return fail(SVB_ERR_BAD_ARG, "null argument");
+  *elems = h->gradbuf ? h->early_elems : 0;
+  return 0;
+}
 
 extern "C" int svb_profile_enable(svb_handle* h, int32_t enable) {
   if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");

@@ -84,6 +84,8 @@ struct Profiler {
 };
 }  // namespace svb
 
+struct svb_comm;  // svb_comm.cu
+
 struct svb_handle {
   int device = 0;
   int sms = 0;
@@ -92,7 +94,16 @@ struct svb_handle {
   // description of the flat reduction buffer of the last *_step_grads call
   float* gradbuf = nullptr;
   int64_t sum_elems = 0, max_elems = 0;
+  int64_t early_elems = 0;          // leading elements that are final when `comm` is released (0: no early bucket)
+  // data-parallel overlap: an optional caller stream that is made to wait for the early bucket (svb_set_comm_stream)
+  cudaStream_t comm = nullptr;
+  cudaEvent_t ev_early = nullptr;
+  svb_comm* comm_ctx = nullptr;     // peer-memory exchange buffer (svb_comm_alloc)
 };
+
+namespace svb {
+float* comm_flat_or(svb_handle* h, float* arena_flat, size_t need_floats);
+}
 
 namespace svb {
 
@@ -127,6 +138,16 @@ inline int ensure_arena(svb_handle* h, size_t need) {
   }
   h->arena.base = static_cast<uint8_t*>(p);
   h->arena.cap = want;
+  return 0;
+}
+
+// Releases the caller's communication stream once everything enqueued on `st` so far has finished.
+inline int release_comm_stream(svb_handle* h, cudaStream_t st) {
+  if (!h->comm) return 0;
+  if (!h->ev_early && cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess)
+    return fail(SVB_ERR_CUDA, "cudaEventCreate failed");
+  SVB_CUDA(cudaEventRecord(h->ev_early, st));
+  SVB_CUDA(cudaStreamWaitEvent(h->comm, h->ev_early, 0));
   return 0;
 }
 
@@ -301,13 +322,20 @@ inline int run_prep_step(cudaStream_t st, PrepArgs a) {
   SVB_LAUNCH_CHECK("prep_step");
   return 0;
 }
-inline int run_assemble(cudaStream_t st, AssembleArgs a) {
-  a.nb_w = grid_for(static_cast<size_t>(a.F) * a.C / 4, 256, 1024);
-  a.nb_b = cdiv(a.F, 256);
-  a.nb_vm = a.vm_chunks * cdiv(a.C, 256);
-  a.nb_cnt = a.words;
-  a.nb_img = cdiv(a.n_img, 8);
-  (assemble_grads_kernel<<<2 * a.nb_w + a.nb_b + a.nb_vm + a.nb_cnt + a.nb_img, 256, 0, st>>>(a), svb::count_launch());
+// part: 1 = everything that depends on the encoder-side GEMM only (g_wenc, g_benc, the vecmat partials for g_bdec) plus
+// the activity counts, 2 = the decoder weight gradient, 3 = both.  The split lets the encoder-side gradients leave
+// for the data-parallel all-reduce while the decoder weight-gradient GEMM is still running.
+inline int run_assemble(cudaStream_t st, AssembleArgs a, int part = 3) {
+  const int nbw = grid_for(static_cast<size_t>(a.F) * a.C / 4, 256, 1024);
+  a.nb_wd = (part & 2) ? nbw : 0;
+  a.nb_w = (part & 1) ? nbw : 0;
+  a.nb_b = (part & 1) ? cdiv(a.F, 256) : 0;
+  a.nb_vm = (part & 1) ? a.vm_chunks * cdiv(a.C, 256) : 0;
+  a.nb_cnt = (part & 1) ? a.words : 0;
+  a.nb_img = (part & 1) ? cdiv(a.n_img, 8) : 0;
+  const int grid = a.nb_wd + a.nb_w + a.nb_b + a.nb_vm + a.nb_cnt + a.nb_img;
+  if (grid == 0) return 0;
+  (assemble_grads_kernel<<<grid, 256, 0, st>>>(a), svb::count_launch());
   SVB_LAUNCH_CHECK("assemble_grads");
   return 0;
 }

@@ -87,6 +87,7 @@ int plan(svb_handle* h, GatedPlan& p, const svb_acts* x, int F, bool train) {
   h->arena.off = 0;
   h->arena.dry = false;
   carve(h->arena, p, x, F, train, h->sms);
+  if (train) p.flat = comm_flat_or(h, p.flat, p.sum_elems + p.max_elems);  // data parallel: exchange buffer in peer memory
   return 0;
 }
 
@@ -199,14 +200,13 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   e3.block_n = 256;
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
+  // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
+  // decoder weight-gradient GEMM runs (svb_set_comm_stream).
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
-  EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
-
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
+  EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
   SVB_TRY(reduce_rows(st, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
   SVB_TRY(reduce_rows(st, pl.cs_pi, pl.tiles_m, F, 1.f, pl.stage, pl.csum_pi));
   SVB_TRY(reduce_rows(st, pl.cs_mage, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mage));
@@ -220,7 +220,12 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
   aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
   aa.F = F; aa.C = C; aa.s = s;
-  SVB_TRY(run_assemble(st, aa));
+  SVB_TRY(run_assemble(st, aa, 1));
+  SVB_TRY(release_comm_stream(h, st));
+  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  SVB_TRY(run_assemble(st, aa, 2));
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;

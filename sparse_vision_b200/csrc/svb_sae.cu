@@ -108,6 +108,7 @@ int plan(svb_handle* h, SaePlan& p, const svb_acts* x, int F, bool train) {
   h->arena.off = 0;
   h->arena.dry = false;
   carve(h->arena, p, x, F, train, h->sms);
+  if (train) p.flat = comm_flat_or(h, p.flat, p.sum_elems + p.max_elems);  // data parallel: exchange buffer in peer memory
   return 0;
 }
 
@@ -240,18 +241,13 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
   }
   prof_mark(h, st, 5);
-  // G4 / G5 weight gradients, split-K over tokens
+  // Weight gradients, split-K over tokens.  The encoder side goes first: with its assembly done, the leading part of
+  // the flat buffer [gW_enc | gb_enc] is final and can be all-reduced while the decoder weight-gradient GEMM runs.
   const size_t FC = static_cast<size_t>(F) * C;
-  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
-  prof_mark(h, st, 6);
-  EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
-
-  prof_mark(h, st, 7);
-  // gradient assembly: column sums -> merged assembly kernel -> one-block tail
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
+  EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
   SVB_TRY(reduce_rows(st, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));
   AssembleArgs aa{};
   aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
@@ -261,7 +257,15 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
   aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
   aa.F = F; aa.C = C; aa.s = s;
-  SVB_TRY(run_assemble(st, aa));
+  SVB_TRY(run_assemble(st, aa, 1));
+  SVB_TRY(release_comm_stream(h, st));
+  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
+  prof_mark(h, st, 6);
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
+  prof_mark(h, st, 7);
+  // rest of the gradient assembly: decoder weight gradient -> one-block tail
+  SVB_TRY(run_assemble(st, aa, 2));
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;

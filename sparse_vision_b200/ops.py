@@ -155,6 +155,17 @@ class SplitStep:
                 "svb_sae_grad_buffer")
         return buf.value, n_sum.value, n_max.value
 
+    def peer_allreduce(self):
+        """In-place all-reduce of the flat buffer over NVLink peer memory (parallel.connect_peer_memory first)."""
+        L.check(self.lib.svb_comm_allreduce(self.h, L.stream_ptr()), "svb_comm_allreduce")
+
+    def early_elems(self):
+        """Leading elements of the flat buffer that are final once the communication stream set with
+        set_comm_stream() is released (0 when no communication stream is set)."""
+        n = C.c_int64()
+        L.check(self.lib.svb_grad_early_elems(self.h, C.byref(n)), "svb_grad_early_elems")
+        return n.value
+
     def apply(self, adam_m, adam_v, step, lr, expansion_factor, optimizer, betas, eps=1e-8, global_tokens=0,
               global_images=0):
         fn = self.lib.svb_sae_step_apply if self.kind == "sae_mlp" else self.lib.svb_gated_step_apply
@@ -164,6 +175,13 @@ class SplitStep:
                    int(expansion_factor), int(global_tokens), int(global_images), C.byref(self.out)),
                 "svb_*_step_apply")
         return self.res
+
+
+def set_comm_stream(device, stream):
+    """Data-parallel overlap: `stream` (a torch.cuda.Stream or None) is made to wait for the early gradient bucket of
+    every following svb_*_step_grads call on `device` (include/svb.h: svb_set_comm_stream)."""
+    L.check(L.load().svb_set_comm_stream(L.handle(device), None if stream is None else stream.cuda_stream),
+            "svb_set_comm_stream")
 
 
 def wrap_device_buffer(address, n_elems, device):
