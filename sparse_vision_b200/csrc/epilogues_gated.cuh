@@ -10,9 +10,13 @@ namespace svb {
 //   pi   = raw' + b_gate;            relu_pi = relu(pi)
 //   mag  = relu(exp(r) * raw' + b_mag)
 //   e    = heaviside(pi, 0.5) * mag
-// Fused: stores of e and relu_pi, activity bits of e, sum|relu_pi| partials (sparse_loss.py:71).
+// Fused: bf16 stores of e and relu_pi (two swizzled smem slabs per warp + TMA tensor stores when the maps are valid,
+// else direct / fp32 stores for the API forward), 1-bit masks of e > 0 and relu_pi > 0 for the backward, activity
+// bits of e (utils.py:2033-2047), sum|relu_pi| (sparse_loss.py:71) kept per CTA and warp.
 struct EpiGatedEnc {
   struct Params {
+    alignas(64) CUtensorMap tm_e;   // bf16 e       [M,N] (valid when tma != 0)
+    alignas(64) CUtensorMap tm_rp;  // bf16 relu_pi [M,N]
     const float* dot;     // [N]
     const float* b_gate;  // [N]
     const float* b_mag;   // [N]
@@ -21,21 +25,31 @@ struct EpiGatedEnc {
     float* e_f32;
     __nv_bfloat16* rp_bf16;
     float* rp_f32;
+    uint32_t* mask_e;     // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
+    uint32_t* mask_rp;    // [M, words] or null: relu_pi > 0
     uint32_t* act_bits;
-    float* l1_partial;  // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
+    float* l1_partial;    // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
     int hw, words;
+    int tma;              // 1: e_bf16 / rp_bf16 leave through the TMA maps; slab_major: those maps are slab-major
+    int slab_major;
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 4;
-  static constexpr uint32_t kSmemBytes = 2 * 4 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::bytes(kWarps) + 2 * 4 * 256 * sizeof(float);
   const Params& p;
+  SlabWriter1 slab_e, slab_r;
   ColVecStage<4, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   float sum, total;
-  int ew;
-  __device__ EpiGatedEnc(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem)), cv(cv_base), sum(0.f), total(0.f), ew(ew_) {}
+  uint32_t we[4], wr[4];
+  int ew, cpw, c_first;
+  __device__ EpiGatedEnc(const Params& p_, uint8_t* smem, int ew_, int block_n)
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f),
+        total(0.f), ew(ew_), cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
+    slab_e.init(smem, ew_);
+    slab_r.init(smem + SlabWriter1::bytes(kWarps), ew_);
+  }
   __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
     stage.fetch(src, ti.n0, g.N, tid);
@@ -45,13 +59,17 @@ struct EpiGatedEnc {
     stage.commit(dst, tid);
     cv = dst;
   }
-  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) { sum = 0.f; }
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { we[i] = 0; wr[i] = 0; }
+  }
   __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
-                                        int wq, int lane, int) {
+                                        int wq, int lane, int ci) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float rp[32];
-    uint32_t word = 0;
+    uint32_t word_e = 0, word_r = 0;
     const float* cvt = cv + (col0 - ti.n0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -63,24 +81,72 @@ struct EpiGatedEnc {
       rp[j] = fmaxf(pi, 0.f);
       v[j] = e;
       if (j < nvalid) {
-        if (e != 0.f) word |= (1u << j);
+        if (e != 0.f) word_e |= (1u << j);
+        if (pi > 0.f) word_r |= (1u << j);
         sum += rp[j];
       }
     }
-    if (!row_ok) word = 0;
+    if (!row_ok) { word_e = 0; word_r = 0; }
+    we[ci] = word_e;
+    wr[ci] = word_r;
     const long long off = static_cast<long long>(row) * g.N + col0;
-    if (row_ok) {
+    if (p.tma) {
+      const int half = ci & 1;
+      slab_e.put(half, lane, v);
+      slab_r.put(half, lane, rp);
+      if (half == 1) {
+        slab_e.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane, p.slab_major);
+        slab_r.flush(&p.tm_rp, col0 - 32, ti.m0 + wq * 32, lane, p.slab_major);
+      }
+    } else if (row_ok) {
       if (p.e_bf16) store_row_bf16(p.e_bf16 + off, v, nvalid);
-      if (p.e_f32) store_row_f32(p.e_f32 + off, v, nvalid);
       if (p.rp_bf16) store_row_bf16(p.rp_bf16 + off, rp, nvalid);
+    }
+    if (row_ok) {
+      if (p.e_f32) store_row_f32(p.e_f32 + off, v, nvalid);
       if (p.rp_f32) store_row_f32(p.rp_f32 + off, rp, nvalid);
     }
-    if (p.act_bits) publish_activity(p.act_bits, p.words, col0 >> 5, word, row, g.M, p.hw, ti.m0 + wq * 32, lane);
   }
-  __device__ void end_tile(const GemmProblem& g, const TileInfo&, int row, int, int) {
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
+    if (p.tma) {
+      const int last = ((g.N - 1) >> 6) << 6;
+      if (slab_e.half_pending) slab_e.flush(&p.tm_e, last, ti.m0 + wq * 32, lane, p.slab_major);
+      if (slab_r.half_pending) slab_r.flush(&p.tm_rp, last, ti.m0 + wq * 32, lane, p.slab_major);
+    }
+    const int w0 = (ti.n0 >> 5) + c_first;
+    const int nw = max(0, min(cpw, p.words - w0));
+    if (row < g.M && nw > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < nw) {
+          if (p.mask_e) p.mask_e[static_cast<size_t>(row) * p.words + w0 + i] = we[i];
+          if (p.mask_rp) p.mask_rp[static_cast<size_t>(row) * p.words + w0 + i] = wr[i];
+        }
+      }
+    }
+    if (p.act_bits && nw > 0) {
+      const int row0 = ti.m0 + wq * 32;
+      const int last_row = min(row0 + 31, g.M - 1);
+      if (row0 <= last_row) {
+        const int b_first = row0 / p.hw, b_last = last_row / p.hw;
+        const int my_b = row < g.M ? row / p.hw : -1;
+        for (int b = b_first; b <= b_last; ++b) {
+          uint32_t mine = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < cpw) {
+              const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? we[i] : 0u);
+              if (lane == i) mine = ored;
+            }
+          }
+          if (lane < nw && mine) atomicOr(&p.act_bits[static_cast<size_t>(b) * p.words + w0 + lane], mine);
+        }
+      }
+    }
     if (row < g.M) total += sum;
   }
   __device__ void finish(int, int lane) {
+    if (p.tma) { slab_e.drain(lane); }
     if (!p.l1_partial) return;
     const float s = warp_sum(total);
     if (lane == 0) p.l1_partial[static_cast<size_t>(blockIdx.x) * kWarps + ew] = s;
@@ -92,31 +158,41 @@ struct EpiGatedEnc {
 //   dMag' = 1[e>0] * acc                     (gradient of the magnitude pre-activation)
 //   dPi'  = 1[relu_pi>0] * l1c               (only the L1 term reaches pi), l1c = lambda*C/(2F)
 //   A'    = dPi' + exp(r) * dMag'            -> bf16, the single operand of the dW_gate GEMM
-// Column sums over tokens: sum dMag' (-> db_mag), sum dPi' (-> db_gate), sum dMag'*e (-> dr_mag).
+// The two indicator functions come from the encoder's 1-bit masks (8 B per row and warp instead of 2 x 128 B of bf16).
+// Column sums over tokens, read back from two staged bf16 slabs per warp (see EpiDPreT): sum dMag' (-> db_mag) and
+// sum A' (-> the rank-1 fix-up, and db_gate = sum A' - exp(r) * sum dMag').  dr_mag needs sum_t dMag' * e, which is
+// sum_c W_dec[c,f] * (DIFF^T E)[c,f] -- a by-product of the dW_dec GEMM (gated_rmag_kernel), so e is never re-read.
 struct EpiGatedDPre {
   struct Params {
-    const __nv_bfloat16* e;
-    const __nv_bfloat16* rp;
-    const float* exp_r;    // [N]
-    __nv_bfloat16* a_out;  // [M,N]
-    float* colsum_mag;     // [tiles_m, N]
-    float* colsum_pi;      // [tiles_m, N]
-    float* colsum_mage;    // [tiles_m, N]
+    alignas(64) CUtensorMap tm_a;  // bf16 A' [M,N]
+    const uint32_t* mask_e;        // [M, words]
+    const uint32_t* mask_rp;       // [M, words]
+    const float* exp_r;            // [N]
+    float* colsum_mag;             // [tiles_m, N]
+    float* colsum_a;               // [tiles_m, N]
     float l1c;
+    int words;
     int block_n;
+    int slab_major;
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
-  static constexpr uint32_t kSmemBytes = 3 * 4 * 256 * sizeof(float) + 2 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::bytes(kWarps) + 2 * 4 * 256 * sizeof(float) + 2 * 256 * sizeof(float);
   const Params& p;
+  SlabWriter1 slab_a, slab_m;  // slab_m is only staged (never stored)
   ColVecStage<1, kWarps * 32> stage;
-  float* s_col;  // [3][4][256]
+  float* s_col;  // [2][4][256]
   float* cv_base;
   const float* cv;
-  int ew;
-  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), s_col(reinterpret_cast<float*>(smem)), cv_base(reinterpret_cast<float*>(smem) + 3 * 4 * 256),
-        cv(cv_base), ew(ew_) {}
+  uint32_t we[4], wr[4];
+  int ew, cpw, c_first;
+  __device__ EpiGatedDPre(const Params& p_, uint8_t* smem, int ew_, int block_n)
+      : p(p_), s_col(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps))),
+        cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps)) + 2 * 4 * 256), cv(cv_base), ew(ew_),
+        cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
+    slab_a.init(smem, ew_);
+    slab_m.init(smem + SlabWriter1::bytes(kWarps), ew_);
+  }
   __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.exp_r};
     stage.fetch(src, ti.n0, g.N, tid);
@@ -126,46 +202,93 @@ struct EpiGatedDPre {
     stage.commit(dst, tid);
     cv = dst;
   }
-  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
-                                        int wq, int lane, int) {
-    const int nvalid = min(32, g.N - col0);
-    const bool row_ok = row < g.M;
-    float e[32], t[32];
-    const long long off = static_cast<long long>(row) * g.N + col0;
-    load_row_bf16(p.e + (row_ok ? off : 0), e, row_ok ? nvalid : 0);
-    load_row_bf16(p.rp + (row_ok ? off : 0), t, row_ok ? nvalid : 0);
+  __device__ void begin_tile(const GemmProblem& g, const TileInfo& ti, int row, int, int) {
+    const int w0 = (ti.n0 >> 5) + c_first;
+    const int nw = max(0, min(cpw, p.words - w0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool ok = row < g.M && i < nw;
+      we[i] = ok ? __ldg(p.mask_e + static_cast<size_t>(row) * p.words + w0 + i) : 0u;
+      wr[i] = ok ? __ldg(p.mask_rp + static_cast<size_t>(row) * p.words + w0 + i) : 0u;
+    }
+  }
+  // column sums of a finished slab for this lane's column pair (same access pattern as EpiDPreT::slab_colsum)
+  __device__ __forceinline__ float2 colsum(const SlabWriter1& s, int lane) const {
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      __nv_bfloat162 acc;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(
+            s.base + (g8 * 8 + q) * 128 + ((((lane >> 2) ^ q) << 4) | ((lane & 3) << 2)));
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
+        acc = q == 0 ? h : __hadd2(acc, h);
+      }
+      const uint32_t aw = *reinterpret_cast<const uint32_t*>(&acc);
+      r.x += bf16lo(aw);
+      r.y += bf16hi(aw);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void slab_done(const TileInfo& ti, int col_slab0, int wq, int lane) {
+    __syncwarp();
+    const float2 cm = colsum(slab_m, lane), ca = colsum(slab_a, lane);
+    const int cc = (col_slab0 - ti.n0) + 2 * lane;  // column inside the tile
+    *reinterpret_cast<float2*>(s_col + (0 * 4 + wq) * 256 + cc) = cm;
+    *reinterpret_cast<float2*>(s_col + (1 * 4 + wq) * 256 + cc) = ca;
+  }
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq,
+                                        int lane, int ci) {
+    const uint32_t be = we[ci], br = wr[ci];
     float a[32];
+    const float* er = cv + (col0 - ti.n0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float dmag = e[j] > 0.f ? v[j] : 0.f;
-      const float dpi = t[j] > 0.f ? p.l1c : 0.f;
-      a[j] = dpi + cv[(col0 - ti.n0) + j] * dmag;
-      v[j] = dmag;
-      t[j] = dpi;
-      e[j] = dmag * e[j];
+      v[j] = (be & (1u << j)) ? v[j] : 0.f;                       // dMag'
+      a[j] = ((br & (1u << j)) ? p.l1c : 0.f) + er[j] * v[j];     // A'
     }
-    if (row_ok) store_row_bf16(p.a_out + off, a, nvalid);
-    const int cc = (col0 - ti.n0) + lane;
-    s_col[(0 * 4 + wq) * 256 + cc] = warp_colsum32(v, lane);
-    s_col[(1 * 4 + wq) * 256 + cc] = warp_colsum32(t, lane);
-    s_col[(2 * 4 + wq) * 256 + cc] = warp_colsum32(e, lane);
+    const int half = ci & 1;
+    slab_a.put(half, lane, a);
+    {  // dMag' is only staged for its column sums: same swizzled layout, no store
+      uint8_t* rowp = slab_m.base + lane * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = half * 4 + i;
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
+      }
+    }
+    if (half == 1) {
+      slab_done(ti, col0 - 32, wq, lane);
+      slab_a.flush(&p.tm_a, col0 - 32, ti.m0 + wq * 32, lane, p.slab_major);
+    }
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
+    if (slab_a.half_pending) {  // N tail: clear the never-written second half of both slabs
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      slab_a.put(1, lane, z);
+      uint8_t* rowp = slab_m.base + lane * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(rowp + (((4 + i) ^ (lane & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      const int col_slab0 = ((g.N - 1) >> 6) << 6;
+      slab_done(ti, col_slab0, wq, lane);
+      slab_a.flush(&p.tm_a, col_slab0, ti.m0 + wq * 32, lane, p.slab_major);
+    }
+    // combine the four lane quarters (fixed order) and write one partial row per M tile
     epi_bar_sync(kWarps * 32);
     const int c = ew * 32 + lane;  // 256 epilogue threads, one column each
     const int col = ti.n0 + c;
-    float* outs[3] = {p.colsum_mag, p.colsum_pi, p.colsum_mage};
     if (c < p.block_n && col < g.N) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float* s = s_col + q * 4 * 256;
-        outs[q][static_cast<size_t>(ti.tile_m) * g.N + col] = (s[c] + s[256 + c]) + (s[512 + c] + s[768 + c]);
-      }
+      const float* s0 = s_col;
+      const float* s1 = s_col + 4 * 256;
+      p.colsum_mag[static_cast<size_t>(ti.tile_m) * g.N + col] = (s0[c] + s0[256 + c]) + (s0[512 + c] + s0[768 + c]);
+      p.colsum_a[static_cast<size_t>(ti.tile_m) * g.N + col] = (s1[c] + s1[256 + c]) + (s1[512 + c] + s1[768 + c]);
     }
     epi_bar_sync(kWarps * 32);
   }
-  __device__ void finish(int, int) {}
+  __device__ void finish(int, int lane) { slab_a.drain(lane); }
 };
 
 }  // namespace svb

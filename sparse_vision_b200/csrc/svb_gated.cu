@@ -15,13 +15,16 @@ struct GatedPlan {
   size_t zero_words;  // 32-bit words cleared by the step prologue, from act_bits on
   bool zero_copy_x;
   bf16 *X, *Wgb, *Wdb, *E, *RP, *A, *D, *DIFF;
-  float *dot, *exp_r, *l1_part, *sq_part, *aux_part, *cs_mag, *cs_pi, *cs_mage, *stage, *csum_mag, *csum_pi,
-      *csum_mage, *csum_a, *st, *chan, *var_part, *rowvar, *P_wd, *P_wg, *vm, *nact_f, *flat;
-  uint32_t* act_bits;
+  float *dot, *exp_r, *l1_part, *sq_part, *aux_part, *cs_mag, *cs_a, *stage, *csum_mag, *csum_a, *st, *chan,
+      *var_part, *rowvar, *P_wd, *P_wg, *vm, *nact_f, *flat;
+  uint32_t *act_bits, *mask_e, *mask_rp, *cnt_part;
+  int cnt_chunks;
+  bool es;  // slab-major E / relu_pi / A' (F % 64 == 0), see gemm_host.cuh
   size_t o_gwg, o_gbg, o_gbm, o_gr, o_gwd, o_gbd, o_sums, o_chansq, o_count, o_max, sum_elems, max_elems;
 };
 
 constexpr int kVmChunks = 32;
+constexpr int kCountRows = 128;  // rows per block of mask_colcount_kernel (byte-lane counters: must stay <= 255)
 
 void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms) {
   p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
@@ -31,6 +34,7 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.tn_f = cdiv(F, 256);
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
+  p.es = F % 64 == 0;
   const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
   p.Wgb = a.take<bf16>(FC);
@@ -49,13 +53,14 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
   p.aux_part = a.take<float>(static_cast<size_t>(sms) * 8);
   p.zero_words = (a.off - z0) / 4;
+  p.mask_e = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
+  p.mask_rp = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
+  p.cnt_chunks = cdiv(p.T, kCountRows);
+  p.cnt_part = a.take<uint32_t>(static_cast<size_t>(p.cnt_chunks) * p.words * 32);
   p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
-  p.cs_pi = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
-  p.cs_mage = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
+  p.cs_a = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum_mag = a.take<float>(F);
-  p.csum_pi = a.take<float>(F);
-  p.csum_mage = a.take<float>(F);
   p.csum_a = a.take<float>(F);
   p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
   p.chan = a.take<float>(4 * p.C);
@@ -99,20 +104,62 @@ int check_params(const svb_acts* x, const svb_gated_params* p) {
   return 0;
 }
 
-// per-feature vector gradients:  csum_a = csum_pi + exp(r)*csum_mag;  gb_gate = s*csum_pi;  gb_mag = s*csum_mag;
-// gr_mag = s*(csum_mage - b_mag*csum_mag)      (d mag_pre / d r = exp(r)*raw = mag_pre - b_mag)
-__global__ void gated_vec_grads_kernel(const float* __restrict__ cs_mag, const float* __restrict__ cs_pi,
-                                       const float* __restrict__ cs_mage, const float* __restrict__ exp_r,
-                                       const float* __restrict__ b_mag, float s, int F, float* __restrict__ csum_a,
-                                       float* __restrict__ g_bgate, float* __restrict__ g_bmag,
-                                       float* __restrict__ g_r) {
+// Number of tokens with relu_pi > 0 per feature, from the encoder's 1-bit mask [T, words] (exact integers; db_gate
+// = l1c * count must not be formed as the difference of two bf16-staged column sums).  A thread owns one 32-feature
+// word column over a chunk of 128 rows and counts 4 bit positions per add in byte lanes (bits k, k+8, k+16, k+24).
+// grid (ceil(words/128), row chunks), 128 threads;  part[chunk][f] uint32.
+__global__ void __launch_bounds__(128)
+mask_colcount_kernel(const uint32_t* __restrict__ mask, long long T, int words, uint32_t* __restrict__ part) {
+  const int w = blockIdx.x * 128 + threadIdx.x;
+  if (w >= words) return;
+  const long long r0 = static_cast<long long>(blockIdx.y) * kCountRows, r1 = min(T, r0 + kCountRows);
+  uint32_t lanes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0; r < r1; ++r) {
+    const uint32_t v = __ldg(mask + r * words + w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lanes[k] += (v >> k) & 0x01010101u;
+  }
+  uint32_t* o = part + (static_cast<size_t>(blockIdx.y) * words + w) * 32;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[k + 8 * q] = (lanes[k] >> (8 * q)) & 0xFFu;
+}
+// per-feature vector gradients:  gb_gate = s * l1c * count(relu_pi > 0);  gb_mag = s * csum_mag
+__global__ void gated_vec_grads_kernel(const float* __restrict__ cs_mag, const uint32_t* __restrict__ cnt_part,
+                                       int chunks, int pitch /* words * 32 */, float l1c, float s, int F,
+                                       float* __restrict__ g_bgate, float* __restrict__ g_bmag) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
-  const float m = cs_mag[f], pi = cs_pi[f];
-  csum_a[f] = pi + exp_r[f] * m;
-  g_bgate[f] = s * pi;
-  g_bmag[f] = s * m;
-  g_r[f] = s * (cs_mage[f] - b_mag[f] * m);
+  uint32_t n = 0;
+  for (int k = 0; k < chunks; ++k) n += cnt_part[static_cast<size_t>(k) * pitch + f];
+  g_bgate[f] = s * l1c * static_cast<float>(n);
+  g_bmag[f] = s * cs_mag[f];
+}
+// gr_mag = s * (sum_t dMag'*e - b_mag*sum_t dMag')      (d mag_pre / d r = exp(r)*raw = mag_pre - b_mag, and
+// mag_pre = e wherever dMag' != 0).  sum_t dMag'[t,f] e[t,f] = sum_c W_dec[c,f] * (DIFF^T E)[c,f]: the unscaled dW_dec
+// that the weight-gradient GEMM just produced, so g_r = sum_c W_dec_bf16[c,f] * g_wdec[c,f] - s*b_mag*csum_mag.
+// grid ceil(F/32), 256 threads = 8 row lanes x 32 features.
+__global__ void gated_rmag_kernel(const float* __restrict__ g_wdec, const bf16* __restrict__ w_dec_bf16,
+                                  const float* __restrict__ b_mag, const float* __restrict__ cs_mag, float s, int C,
+                                  int F, float* __restrict__ g_r) {
+  __shared__ float sh[8][33];
+  const int fl = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + fl;
+  float acc = 0.f;
+  if (f < F)
+    for (int c = cl; c < C; c += 8) {
+      const size_t i = static_cast<size_t>(c) * F + f;
+      acc += __bfloat162float(w_dec_bf16[i]) * g_wdec[i];
+    }
+  sh[cl][fl] = acc;
+  __syncthreads();
+  if (cl == 0 && f < F) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][fl];
+    g_r[f] = t - s * b_mag[f] * cs_mag[f];
+  }
 }
 
 int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p, bool train) {
@@ -146,6 +193,8 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
   e1.rp_bf16 = (out->relu_pi && out->relu_pi_dtype == SVB_BF16) ? static_cast<bf16*>(out->relu_pi) : pl.RP;
   e1.rp_f32 = (out->relu_pi && out->relu_pi_dtype == SVB_F32) ? static_cast<float*>(out->relu_pi) : nullptr;
   e1.hw = pl.hw; e1.words = pl.words;
+  e1.tma = make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F) == 0 &&
+           make_store_tmap_bf16(&e1.tm_rp, e1.rp_bf16, T, pl.F, pl.F) == 0;
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, pl.C, pl.Wgb, pl.C, T, pl.F, pl.C, 1, e1)), "gated enc");
   if (out->dec) {
     EpiDec::Params e2{};
@@ -182,23 +231,29 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
   e1.e_bf16 = pl.E; e1.rp_bf16 = pl.RP; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
-  e1.hw = pl.hw; e1.words = pl.words;
+  e1.mask_e = pl.mask_e; e1.mask_rp = pl.mask_rp;
+  e1.hw = pl.hw; e1.words = pl.words; e1.tma = 1; e1.slab_major = pl.es;
+  if (pl.es ? (make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) || make_store_tmap_bf16_slab(&e1.tm_rp, pl.RP, T, F))
+            : (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F) || make_store_tmap_bf16(&e1.tm_rp, pl.RP, T, F, F)))
+    return fail(SVB_ERR_TMAP, "tensor maps for E / relu_pi");
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
   if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))
     return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2)), "dec");
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
   EpiDec::Params e2v{};
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v)), "via");
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
   SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
                        out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
   EpiGatedDPre::Params e3{};
-  e3.e = pl.E; e3.rp = pl.RP; e3.exp_r = pl.exp_r; e3.a_out = pl.A;
-  e3.colsum_mag = pl.cs_mag; e3.colsum_pi = pl.cs_pi; e3.colsum_mage = pl.cs_mage;
+  e3.mask_e = pl.mask_e; e3.mask_rp = pl.mask_rp; e3.exp_r = pl.exp_r; e3.words = pl.words;
+  e3.colsum_mag = pl.cs_mag; e3.colsum_a = pl.cs_a;
   e3.l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
-  e3.block_n = 256;
+  e3.block_n = 256; e3.slab_major = pl.es;
+  if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_a, pl.A, T, F) : make_store_tmap_bf16(&e3.tm_a, pl.A, T, F, F))
+    return fail(SVB_ERR_TMAP, "tensor map for A'");
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
   // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
   // decoder weight-gradient GEMM runs (svb_set_comm_stream).
@@ -206,12 +261,12 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
   EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5)), "dW_gate");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, false)), "dW_gate");
   SVB_TRY(reduce_rows(st, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
-  SVB_TRY(reduce_rows(st, pl.cs_pi, pl.tiles_m, F, 1.f, pl.stage, pl.csum_pi));
-  SVB_TRY(reduce_rows(st, pl.cs_mage, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mage));
-  (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.csum_pi, pl.csum_mage, pl.exp_r, p->b_mag, s, F,
-                                                      pl.csum_a, flat + pl.o_gbg, flat + pl.o_gbm, flat + pl.o_gr), svb::count_launch());
+  SVB_TRY(reduce_rows(st, pl.cs_a, pl.tiles_m, F, 1.f, pl.stage, pl.csum_a));
+  (mask_colcount_kernel<<<dim3(cdiv(pl.words, 128), pl.cnt_chunks), 128, 0, st>>>(pl.mask_rp, pl.T, pl.words, pl.cnt_part), svb::count_launch());
+  (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.cnt_part, pl.cnt_chunks, pl.words * 32, e3.l1c, s, F,
+                                                      flat + pl.o_gbg, flat + pl.o_gbm), svb::count_launch());
   AssembleArgs aa{};
   aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
   aa.P_we = pl.P_wg; aa.g_wenc = flat + pl.o_gwg; aa.s_we = pl.s_wg;
@@ -222,10 +277,11 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   aa.F = F; aa.C = C; aa.s = s;
   SVB_TRY(run_assemble(st, aa, 1));
   SVB_TRY(release_comm_stream(h, st));
-  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
+  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gr) : 0;   // gr_mag needs the decoder weight gradient
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4)), "dW_dec");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, false, pl.es)), "dW_dec");
   SVB_TRY(run_assemble(st, aa, 2));
+  (gated_rmag_kernel<<<cdiv(F, 32), 256, 0, st>>>(flat + pl.o_gwd, pl.Wdb, p->b_mag, pl.csum_mag, s, C, F, flat + pl.o_gr), svb::count_launch());
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
