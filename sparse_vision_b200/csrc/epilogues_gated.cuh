@@ -54,9 +54,15 @@ struct EpiGatedEnc {
     const float* const src[4] = {p.dot, p.b_gate, p.b_mag, p.exp_r};
     stage.fetch(src, ti.n0, g.N, tid);
   }
+  // staged per column: c1 = b_gate - dot, c2 = b_mag - exp(r)*dot, exp(r)   (pi = acc + c1, mag_pre = exp(r)*acc + c2);
+  // thread tid holds the four source vectors of column tid (ColVecStage layout with 256 threads)
   __device__ void colvec_commit(uint32_t parity, int tid) {
+    static_assert(decltype(stage)::kPer == 4, "one column per epilogue thread");
     float* dst = cv_base + parity * 4 * 256;
-    stage.commit(dst, tid);
+    const float dot = stage.r[0], bg = stage.r[1], bm = stage.r[2], er = stage.r[3];
+    dst[tid] = bg - dot;
+    dst[256 + tid] = bm - er * dot;
+    dst[512 + tid] = er;
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {
@@ -68,24 +74,37 @@ struct EpiGatedEnc {
                                         int wq, int lane, int ci) {
     const int nvalid = min(32, g.N - col0);
     const bool row_ok = row < g.M;
-    float rp[32];
-    uint32_t word_e = 0, word_r = 0;
+    float rp[32], c1[32], c2[32], er[32];
     const float* cvt = cv + (col0 - ti.n0);
+    lds_row_f32(cvt, c1);
+    lds_row_f32(cvt + 256, c2);
+    lds_row_f32(cvt + 512, er);
+    // Columns >= N see acc = 0 and zero column vectors, so they produce e = relu_pi = 0 by themselves.
+    // gate = heaviside(pi, 0.5) as one saturating FMA: sat(pi * 2^127 + 0.5) is 1 / 0.5 / 0 for pi > 0 / == 0 / < 0
+    // (exact down to |pi| ~ 3e-39).  Mask bits come from the sign of 0 - e and 0 - relu_pi, four chains of 8 columns.
+    uint32_t we4[4] = {0, 0, 0, 0}, wr4[4] = {0, 0, 0, 0};
+    float sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float raw = v[j] - cvt[j];
-      const float pi = raw + cvt[256 + j];
-      const float mag = fmaxf(cvt[768 + j] * raw + cvt[512 + j], 0.f);
-      const float gate = pi > 0.f ? 1.f : (pi == 0.f ? 0.5f : 0.f);
-      const float e = gate * mag;
-      rp[j] = fmaxf(pi, 0.f);
-      v[j] = e;
-      if (j < nvalid) {
-        if (e != 0.f) word_e |= (1u << j);
-        if (pi > 0.f) word_r |= (1u << j);
-        sum += rp[j];
+    for (int j = 7; j >= 0; --j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = q * 8 + j;
+        const float pi = v[i] + c1[i];
+        const float mag = fmaxf(fmaf(er[i], v[i], c2[i]), 0.f);
+        const float gate = __saturatef(fmaf(pi, 1.7014118e38f, 0.5f));
+        const float e = gate * mag;
+        const float r = fmaxf(pi, 0.f);
+        we4[q] = __funnelshift_l(__float_as_uint(0.f - e), we4[q], 1);
+        wr4[q] = __funnelshift_l(__float_as_uint(0.f - r), wr4[q], 1);
+        sq4[q] += r;
+        v[i] = e;
+        rp[i] = r;
       }
     }
+    uint32_t word_e = (we4[0] | (we4[1] << 8)) | ((we4[2] << 16) | (we4[3] << 24));
+    uint32_t word_r = (wr4[0] | (wr4[1] << 8)) | ((wr4[2] << 16) | (wr4[3] << 24));
+    sum += (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
+    if (nvalid < 32) { word_e &= (1u << nvalid) - 1u; word_r &= (1u << nvalid) - 1u; }
     if (!row_ok) { word_e = 0; word_r = 0; }
     we[ci] = word_e;
     wr[ci] = word_r;
