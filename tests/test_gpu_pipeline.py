@@ -1,0 +1,80 @@
+"""cfg4-style check of the hook-driven training loop (model_pipeline.py:363-432, :744-793): a frozen base model, the
+SAE trained through the forward hook with the fused step, dead-unit masks AND-ed over steps and dead units
+re-initialised on the reference's schedule -- against the CPU oracle run on the same activations and RNG stream."""
+import collections
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import sae_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("hw,steps", [(16, 11), (7, 8)])
+def test_hook_training_with_reinit_matches_oracle(tmp_path, monkeypatch, hw, steps):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import sparse_vision_b200.models.sae_mlp as M
+    from sparse_vision_b200.model_pipeline import ModelPipeline
+
+    C, k, B, n_dead, every = 64, 4, 6, 13, 3
+    torch.manual_seed(0)
+    base = nn.Sequential(collections.OrderedDict(conv=nn.Conv2d(3, C, 3, padding=1), act=nn.ReLU())).eval()
+    sae = M.SaeMLP(C, k)
+    with torch.no_grad():
+        sae.encoder.bias[:n_dead] = -50.0          # planted dead units
+    p = {key: v.detach().clone() for key, v in sae.state_dict().items()}
+    assert list(p) == list(O.SAE_MLP_KEYS)
+    base, sae = base.cuda(), sae.cuda()
+    # the fixtures of the oracle come from the CPU generator: draw the re-initialisation matrices there too
+    orig = M.draw_reinit
+    monkeypatch.setattr(M, "draw_reinit", lambda w, b, d, dead, draw_device=None: orig(w, b, d, dead, "cpu"))
+    pipe = ModelPipeline(base, sae, "sae_mlp", "act", "constrained_adam", 1e-3, 5.0, k, dead_neurons_steps=every,
+                         reinit_index_dir=str(tmp_path))
+    pipe.register_hooks(train_sae=True)
+    xs = [torch.randn(B, 3, hw, hw, generator=torch.Generator().manual_seed(100 + i)) for i in range(steps)]
+    pipe.remove_hooks()
+    with torch.no_grad():                              # raw layer outputs for the oracle (no hook installed)
+        acts = [base(x.cuda()).cpu().bfloat16().float() for x in xs]   # the fused step consumes bf16-rounded activations
+    pipe.register_hooks(train_sae=True)
+
+    torch.manual_seed(777)
+    got = []
+    for x in xs:
+        out, action = pipe.train_batch(x.cuda())
+        assert out.shape == (B, C, hw, hw) and out.dtype == torch.float32      # the hook returns dec in the layer's format
+        got.append((pipe.batch_scalars(), pipe._last.dead.cpu().bool().clone(), action))
+    assert any(a == "reinit" for _, _, a in got), "the schedule never fired in this test"
+    assert len(os.listdir(tmp_path)) == sum(a == "reinit" for _, _, a in got)   # one index file per re-initialisation
+
+    torch.manual_seed(777)
+    st = O.new_adam_state(p, O.SAE_MLP_KEYS)
+    acc = None
+    for i, x in enumerate(xs):
+        ref = O.train_step("sae_mlp", p, st, acts[i], 5.0, "constrained_adam", 1e-3, k)
+        sc, dead, action = got[i]
+        for key in ("loss", "rec", "l1", "var_expl"):
+            assert abs(sc[key] - float(ref[key])) <= 2e-2 * max(abs(float(ref[key])), 1e-3), (i, key, sc[key], float(ref[key]))
+        assert torch.equal(dead, ref["dead"]), f"dead-unit mask differs at step {i}"
+        acc = ref["dead"].clone() if acc is None else acc & ref["dead"]
+        want = O.dead_neuron_action(i + 1, every)
+        assert action == want, (i, action, want)
+        if want == "reinit":
+            n = O.reset_encoder_weights(p, st, acc)
+            assert n >= n_dead
+            acc = None
+        elif want == "clear":
+            acc = None
+    for key, q in zip(O.SAE_MLP_KEYS, sae.param_list()):
+        d = (q.detach().cpu() - p[key]).abs()
+        assert d.max().item() <= 2e-2 and d.mean().item() <= 5e-4, (key, d.max().item(), d.mean().item())
+    # Adam moments of re-initialised units were reset on both sides
+    m_gpu = pipe.sae_optimizer.state[sae.encoder.weight]["exp_avg"].cpu()
+    assert np.allclose(m_gpu.numpy(), st["m"]["encoder.weight"].numpy(), atol=5e-3)
