@@ -28,6 +28,7 @@ extern "C" int svb_destroy(svb_handle* h) {
   if (!h) return 0;
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ev_early) cudaEventDestroy(h->ev_early);
+  if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   svb_comm_destroy(h);
   delete h;
   return 0;

@@ -99,6 +99,9 @@ struct svb_handle {
   cudaStream_t comm = nullptr;
   cudaEvent_t ev_early = nullptr;
   svb_comm* comm_ctx = nullptr;     // peer-memory exchange buffer (svb_comm_alloc)
+  // internal side stream: small kernels that only feed the end of the step run beside the GEMMs (fork / join below)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace svb {
@@ -138,6 +141,26 @@ inline int ensure_arena(svb_handle* h, size_t need) {
   }
   h->arena.base = static_cast<uint8_t*>(p);
   h->arena.cap = want;
+  return 0;
+}
+
+// Fork / join of the handle's side stream around the caller's stream `st`.  The GEMMs leave 4 of the 148 SMs idle
+// (144-CTA grids) and are bandwidth / tensor bound, so the latency-bound helper kernels (statistics folds, column-sum
+// reduction, gradient assembly, weight prologue) cost nothing when they run beside them.  Everything forked is joined
+// again before the call returns, so the caller still sees plain stream semantics (and may capture the call in a graph).
+inline int side_fork(svb_handle* h, cudaStream_t st) {
+  if (!h->side) {
+    SVB_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    SVB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    SVB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  SVB_CUDA(cudaEventRecord(h->ev_fork, st));
+  SVB_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  return 0;
+}
+inline int side_join(svb_handle* h, cudaStream_t st) {
+  SVB_CUDA(cudaEventRecord(h->ev_join, h->side));
+  SVB_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   return 0;
 }
 

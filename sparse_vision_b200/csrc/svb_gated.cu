@@ -225,8 +225,11 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
+  SVB_TRY(side_fork(h, st));
+  SVB_TRY(run_prep(h->side, pl, p, true));
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
-  SVB_TRY(run_prep(st, pl, p, true));
+  SVB_TRY(side_join(h, st));
 
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
@@ -244,9 +247,11 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
   EpiDec::Params e2v{};
   e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
-  SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
+  // statistics + NCHW write-back of d only feed the end of the step: side stream, beside the via / dE GEMMs
+  SVB_TRY(side_fork(h, st));
+  SVB_TRY(run_post_dec(h->side, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
                        out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
+  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
   EpiGatedDPre::Params e3{};
   e3.mask_e = pl.mask_e; e3.mask_rp = pl.mask_rp; e3.exp_r = pl.exp_r; e3.words = pl.words;
   e3.colsum_mag = pl.cs_mag; e3.colsum_a = pl.cs_a;
@@ -262,10 +267,13 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   float* flat = pl.flat;
   EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
   SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, false)), "dW_gate");
-  SVB_TRY(reduce_rows(st, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
-  SVB_TRY(reduce_rows(st, pl.cs_a, pl.tiles_m, F, 1.f, pl.stage, pl.csum_a));
-  (mask_colcount_kernel<<<dim3(cdiv(pl.words, 128), pl.cnt_chunks), 128, 0, st>>>(pl.mask_rp, pl.T, pl.words, pl.cnt_part), svb::count_launch());
-  (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, st>>>(pl.csum_mag, pl.cnt_part, pl.cnt_chunks, pl.words * 32, e3.l1c, s, F,
+  // reductions + gate-side assembly + tail on the side stream, beside the dW_dec GEMM
+  SVB_TRY(side_fork(h, st));
+  cudaStream_t ss = h->side;
+  SVB_TRY(reduce_rows(ss, pl.cs_mag, pl.tiles_m, F, 1.f, pl.stage, pl.csum_mag));
+  SVB_TRY(reduce_rows(ss, pl.cs_a, pl.tiles_m, F, 1.f, pl.stage, pl.csum_a));
+  (mask_colcount_kernel<<<dim3(cdiv(pl.words, 128), pl.cnt_chunks), 128, 0, ss>>>(pl.mask_rp, pl.T, pl.words, pl.cnt_part), svb::count_launch());
+  (gated_vec_grads_kernel<<<cdiv(F, 256), 256, 0, ss>>>(pl.csum_mag, pl.cnt_part, pl.cnt_chunks, pl.words * 32, e3.l1c, s, F,
                                                       flat + pl.o_gbg, flat + pl.o_gbm), svb::count_launch());
   AssembleArgs aa{};
   aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
@@ -275,13 +283,9 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
   aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
   aa.F = F; aa.C = C; aa.s = s;
-  SVB_TRY(run_assemble(st, aa, 1));
-  SVB_TRY(release_comm_stream(h, st));
+  SVB_TRY(run_assemble(ss, aa, 1));
+  SVB_TRY(release_comm_stream(h, ss));
   h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gr) : 0;   // gr_mag needs the decoder weight gradient
-  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, false, pl.es)), "dW_dec");
-  SVB_TRY(run_assemble(st, aa, 2));
-  (gated_rmag_kernel<<<cdiv(F, 32), 256, 0, st>>>(flat + pl.o_gwd, pl.Wdb, p->b_mag, pl.csum_mag, s, C, F, flat + pl.o_gr), svb::count_launch());
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
@@ -290,7 +294,12 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
   ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
   ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
-  (grads_tail_kernel<<<1, 1024, 0, st>>>(ta), svb::count_launch());
+  (grads_tail_kernel<<<1, 1024, 0, ss>>>(ta), svb::count_launch());
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, false, pl.es)), "dW_dec");
+  SVB_TRY(side_join(h, st));
+  SVB_TRY(run_assemble(st, aa, 2));
+  (gated_rmag_kernel<<<cdiv(F, 32), 256, 0, st>>>(flat + pl.o_gwd, pl.Wdb, p->b_mag, pl.csum_mag, s, C, F, flat + pl.o_gr), svb::count_launch());
   SVB_LAUNCH_CHECK("gated grad assembly");
   h->gradbuf = flat;
   h->sum_elems = static_cast<int64_t>(pl.sum_elems);

@@ -182,8 +182,11 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
                  (!dec_out || (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0));
   prof_begin_step(h);
   prof_mark(h, st, 0);
+  // weight prologue on the side stream, next to the activation pack
+  SVB_TRY(side_fork(h, st));
+  SVB_TRY(run_prep(h->side, pl, p, true));
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs, pl.fused_dec ? pl.xpart : nullptr));
-  SVB_TRY(run_prep(st, pl, p, true));
+  SVB_TRY(side_join(h, st));
 
   prof_mark(h, st, 1);
   // G1 encoder
@@ -208,8 +211,10 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (dec_out && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
-    (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, st>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
-    (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, st>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
+    // the statistics folds only feed the tail of the step: side stream, beside the dE GEMM
+    SVB_TRY(side_fork(h, st));
+    (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, h->side>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
+    (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, h->side>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
     SVB_LAUNCH_CHECK("decoder statistics");
   } else {
     EpiDec::Params e2{};
@@ -248,7 +253,9 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   float* flat = pl.flat;
   EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
   SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
-  SVB_TRY(reduce_rows(st, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));
+  // column-sum reduction + encoder-side assembly on the side stream, beside the dW_dec GEMM
+  SVB_TRY(side_fork(h, st));
+  SVB_TRY(reduce_rows(h->side, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));
   AssembleArgs aa{};
   aa.P_wd = pl.P_wd; aa.g_wdec = flat + pl.o_gwd; aa.s_wd = pl.s_wd;
   aa.P_we = pl.P_we; aa.g_wenc = flat + pl.o_gwe; aa.s_we = pl.s_we;
@@ -257,15 +264,9 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   aa.act_bits = pl.act_bits; aa.count = flat + pl.o_count; aa.n_active = out ? out->activity.n_active : nullptr;
   aa.nact_f = pl.nact_f; aa.n_img = static_cast<int>(pl.n_img); aa.words = pl.words;
   aa.F = F; aa.C = C; aa.s = s;
-  SVB_TRY(run_assemble(st, aa, 1));
-  SVB_TRY(release_comm_stream(h, st));
-  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
-  prof_mark(h, st, 6);
-  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
-  prof_mark(h, st, 7);
-  // rest of the gradient assembly: decoder weight gradient -> one-block tail
-  SVB_TRY(run_assemble(st, aa, 2));
+  SVB_TRY(run_assemble(h->side, aa, 1));
+  SVB_TRY(release_comm_stream(h, h->side));
+  // the one-block tail (decoder-bias gradient, loss sums, per-channel statistics) needs nothing from the dW_dec GEMM
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
   ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
@@ -274,7 +275,16 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   ta.var_part = pl.var_part; ta.n_var_part = pl.fused_dec ? cdiv(C, 32) : cdiv(C, 8);
   ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
   ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
-  (grads_tail_kernel<<<1, 1024, 0, st>>>(ta), svb::count_launch());
+  (grads_tail_kernel<<<1, 1024, 0, h->side>>>(ta), svb::count_launch());
+
+  h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
+  prof_mark(h, st, 6);
+  EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
+  prof_mark(h, st, 7);
+  // rest of the gradient assembly: the decoder weight gradient, after everything forked above has joined
+  SVB_TRY(side_join(h, st));
+  SVB_TRY(run_assemble(st, aa, 2));
   SVB_LAUNCH_CHECK("grad assembly");
   prof_mark(h, st, 8);
   h->gradbuf = flat;
