@@ -466,41 +466,42 @@ struct EpiDec {
 // ------------------------------------------------------------------------------------------------ decoder, fused
 // Training-step decoder epilogue for NCHW activations (slab-major X / DIFF, C % 64 == 0, >= 32 tokens per image):
 //   d = acc + b_dec;  diff = d - x;  sum diff^2                                  (sae_mlp.py:52, sparse_loss.py:35)
-// and, from the two staged 64-column tiles of every warp, everything the separate post-decoder pass did:
+// and, from two small staged tiles per 32-column chunk, everything the separate post-decoder pass did:
 //   * d goes straight back to the caller's NCHW bf16 tensor (model_pipeline.py:425,432; utils.py:2478): the warp
-//     stages a channel-major [64 channels][32 tokens] copy and one TMA tensor store writes it (positions past the end
+//     stages a channel-major [32 channels][32 tokens] copy and one TMA tensor store writes it (positions past the end
 //     of the image are clipped by the tensor map; TMA stores reject negative coordinates, so when the warp's 32
 //     tokens straddle an image boundary the few positions of the second image are copied with 16-byte stores);
 //   * per 32-token group and channel: sum d, sum d^2 per image (variance_explained, utils.py:2012-2030) read back
 //     from the channel-major copy, and sum diff^2 (compute_rmse_nrmse, sparse_loss.py:4-21) read back from the diff
-//     slab.  dec_stats_gather_kernel folds the groups of an image together.  No token-major d is written at all.
+//     tile.  dec_stats_image_kernel folds the groups of an image together.  No token-major d is written at all.
+// Staging is per chunk (2 x 2 KB per warp) on purpose: 34 KB of epilogue smem leave room for FOUR 48 KB operand
+// stages, and this GEMM streams E from HBM -- with three stages it ran at 4.1 TB/s, with four at 4.9 TB/s.
 struct EpiDecNchw {
   struct Params {
-    alignas(64) CUtensorMap tm_diff;  // slab-major bf16 diff [M, N], box 64 x 32 x 1
-    alignas(64) CUtensorMap tm_out;   // NCHW bf16 output seen as {HW, C, B}, box {32, 64, 1}, no swizzle (has_out)
+    alignas(64) CUtensorMap tm_diff;  // slab-major bf16 diff [M, N], box 32 cols x 32 rows x 1, 64B swizzle
+    alignas(64) CUtensorMap tm_out;   // NCHW bf16 output seen as {HW, C, B}, box {32, 32, 1}, no swizzle (out != null)
     const float* bias;                // [N] decoder bias
     const __nv_bfloat16* x;           // slab-major [M, N] targets (the SAE input)
     float* sq_partial;                // [gridDim.x * kWarps]: one running sum per CTA and epilogue warp
-    float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_gather_kernel
+    float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_image_kernel
     __nv_bfloat16* out;               // the NCHW output tensor behind tm_out (null: d is not handed back)
     int hw;                           // tokens per image (>= 32, multiple of 8 when out != null)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
-  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
+  static constexpr bool kPrefetchAcc = true;
+  static constexpr uint32_t kSmemBytes = kWarps * 4096 + 2 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter1 slab_f;
-  uint8_t* tbuf;  // channel-major [64 channels][32 tokens] bf16 copy of d (4 KB per warp)
+  uint8_t* tbuf;  // channel-major [32 channels][32 tokens] bf16 copy of d (2 KB)
+  uint8_t* fbuf;  // token-major [32 tokens][32 channels] bf16 diff, 64B-swizzled (2 KB)
   ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
   float sq;
   int ew;
   __device__ EpiDecNchw(const Params& p_, uint8_t* smem, int ew_, int)
-      : p(p_), tbuf(smem + ew_ * 4096), cv_base(reinterpret_cast<float*>(smem + 2 * SlabWriter1::bytes(kWarps))),
-        cv(cv_base), sq(0.f), ew(ew_) {
-    slab_f.init(smem + SlabWriter1::bytes(kWarps), ew_);
-  }
+      : p(p_), tbuf(smem + ew_ * 4096), fbuf(smem + ew_ * 4096 + 2048),
+        cv_base(reinterpret_cast<float*>(smem + kWarps * 4096)), cv(cv_base), sq(0.f), ew(ew_) {}
   __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.bias};
     stage.fetch(src, ti.n0, g.N, tid);
@@ -511,9 +512,40 @@ struct EpiDecNchw {
     cv = dst;
   }
   __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
-  // statistics + stores of one finished 64-column pair of tiles; cbase = first column of the slab
-  __device__ __forceinline__ void slab_done(const GemmProblem& g, const TileInfo& ti, int cbase, int wq, int lane) {
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int wq, int lane, int) {
+    const bool row_ok = row < g.M;
+    float xv[32], b[32];
+    load_row_bf16(p.x + (row_ok ? slab_offset(row, col0, g.M) : 0), xv, row_ok ? 32 : 0);  // issued early
+    lds_row_f32(cv + (col0 - ti.n0), b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += b[j];
+    if (!row_ok) {  // only in a ragged last tile: keep padding rows out of the stores and the statistics
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    uint32_t dpk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dpk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] -= xv[j];
+      sq += v[j] * v[j];
+    }
+    // the stores of the previous chunk must have finished READING the two staging tiles
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+    uint16_t* tb = reinterpret_cast<uint16_t*>(tbuf) + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      tb[(2 * j) * 32] = static_cast<uint16_t>(dpk[j] & 0xFFFFu);
+      tb[(2 * j + 1) * 32] = static_cast<uint16_t>(dpk[j] >> 16);
+    }
+    uint8_t* frow = fbuf + lane * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(frow + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8_bf16(v + 8 * i);
     __syncwarp();  // both staged tiles are complete in shared memory
+
     const int row0 = ti.m0 + wq * 32;
     const int nrows = max(0, min(32, g.M - row0));
     const int b0 = row0 / p.hw;
@@ -521,10 +553,9 @@ struct EpiDecNchw {
     const size_t grp = static_cast<size_t>(ti.tile_m) * 4 + wq;
     float* part0 = p.part + (grp * 2 + 0) * 3 * g.N;
     float* part1 = p.part + (grp * 2 + 1) * 3 * g.N;
-    // (1) sum d, sum d^2: lane owns channels cbase + lane and cbase + 32 + lane (rows of the channel-major copy)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint4* rp = reinterpret_cast<const uint4*>(tbuf + (h * 32 + lane) * 64);
+    const int col = col0 + lane;  // this lane's channel (N % 64 == 0: always < N)
+    {  // (1) sum d, sum d^2 of channel col0 + lane from its row of the channel-major copy
+      const uint4* rp = reinterpret_cast<const uint4*>(tbuf + lane * 64);
       uint32_t w[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -547,90 +578,37 @@ struct EpiDecNchw {
           else if (i < nrows) { a1 += d; q1 += d * d; }
         }
       }
-      const int col = cbase + h * 32 + lane;
-      if (col < g.N) {
-        part0[col] = a0;
-        part0[g.N + col] = q0;
-        if (n1 > 0) { part1[col] = a1; part1[g.N + col] = q1; }
-      }
+      part0[col] = a0;
+      part0[g.N + col] = q0;
+      if (n1 > 0) { part1[col] = a1; part1[g.N + col] = q1; }
     }
-    // (2) sum diff^2: lane owns columns cbase + 2*lane, +1 of the (128B-swizzled) diff slab; rows >= M hold zeros
-    {
-      float2 s = make_float2(0.f, 0.f);
+    {  // (2) sum diff^2 of the same channel from the (64B-swizzled) diff tile; rows >= M hold zeros
+      float s = 0.f;
+      const uint8_t* cp = fbuf + ((lane & 7) << 1);
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(
-            slab_f.base + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-        const float lo = bf16lo(w), hi = bf16hi(w);
-        s.x += lo * lo;
-        s.y += hi * hi;
+        const uint16_t h = *reinterpret_cast<const uint16_t*>(cp + r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4));
+        const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
+        s += f * f;
       }
-      const int col = cbase + 2 * lane;
-      if (col < g.N) *reinterpret_cast<float2*>(part0 + 2 * g.N + col) = s;
+      part0[2 * g.N + col] = s;
     }
-    // (3) asynchronous stores of both tiles
+    // (3) second image of a straddling warp: positions 0 .. n1-1 (n0 and n1 are multiples of 8), 16-byte copies
+    if (p.out && n1 > 0) {
+      const uint4* src = reinterpret_cast<const uint4*>(tbuf + lane * 64 + n0 * 2);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
+      for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
+    }
+    // (4) asynchronous stores of both tiles
     fence_proxy_async_smem();
     __syncwarp();
-    if (p.out && n1 > 0) {  // second image of a straddling warp: positions 0 .. n1-1, n0 and n1 are multiples of 8
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = cbase + h * 32 + lane;
-        if (col < g.N) {
-          const uint4* src = reinterpret_cast<const uint4*>(tbuf + (h * 32 + lane) * 64 + n0 * 2);
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
-          for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
-        }
-      }
-    }
     if (lane == 0) {
-      if (p.out) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, cbase, b0);
-      tma_store_3d(&p.tm_diff, slab_f.base, 0, row0, cbase >> 6);
+      if (p.out) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);
+      tma_store_3d(&p.tm_diff, fbuf, col0 & 63, row0, col0 >> 6);
       bulk_commit();
     }
-    slab_f.half_pending = false;
   }
-  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
-                                        int wq, int lane, int ci) {
-    const bool row_ok = row < g.M;
-    const int half = ci & 1;
-    float xv[32], b[32];
-    load_row_bf16(p.x + (row_ok ? slab_offset(row, col0, g.M) : 0), xv, row_ok ? 32 : 0);  // issued early
-    lds_row_f32(cv + (col0 - ti.n0), b);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += b[j];
-    if (!row_ok) {  // only in a ragged last tile: keep padding rows out of the stores and the statistics
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    }
-    if (half == 0) {  // the stores that last used this warp's two staging tiles must have finished READING them
-      if (lane == 0) bulk_wait_read<0>();
-      __syncwarp();
-    }
-    uint16_t* tb = reinterpret_cast<uint16_t*>(tbuf) + half * 32 * 32 + lane;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const uint32_t pr = pack_bf16x2(v[j], v[j + 1]);
-      tb[j * 32] = static_cast<uint16_t>(pr & 0xFFFFu);
-      tb[(j + 1) * 32] = static_cast<uint16_t>(pr >> 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] -= xv[j];
-      sq += v[j] * v[j];
-    }
-    uint8_t* rowp = slab_f.base + lane * 128;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = half * 4 + i;
-      *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v + 8 * i);
-    }
-    slab_f.half_pending = (half == 0);
-    if (half == 1) slab_done(g, ti, col0 - 32, wq, lane);
-  }
-  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
-    // N % 64 == 0 on this path, so a slab is never left half written
-    (void)g; (void)ti; (void)wq; (void)lane;
-  }
+  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void finish(int, int lane) {
     if (lane == 0) bulk_wait<0>();
     __syncwarp();

@@ -73,7 +73,21 @@ inline int make_store_tmap_bf16_slab(CUtensorMap* out, void* ptr, uint64_t rows,
   return make_tmap_bf16_slab(out, ptr, rows, cols, 32);
 }
 
-// The caller's NCHW bf16 tensor [B, C, HW] as a 3-D map {HW, C, B}; box = 32 positions x 64 channels x 1 image, no
+// Slab-major store map for 32-column x 32-row chunks (2 KB staging tiles, 64B swizzle): coordinates {col % 64, row, col / 64}.
+inline int make_store_tmap_bf16_slab32(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols) {
+  auto fn = tmap_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (cols % 64)) return -2;
+  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  cuuint64_t gstride[2] = {128, rows * 128};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+// The caller's NCHW bf16 tensor [B, C, HW] as a 3-D map {HW, C, B}; box = 32 positions x 32 channels x 1 image, no
 // swizzle (the epilogue stages channel-major tiles).  Needs HW % 8 == 0 (16-byte row pitch) and a 16-byte aligned base.
 inline int make_tmap_nchw_bf16(CUtensorMap* out, void* ptr, uint64_t B, uint64_t C, uint64_t HW) {
   auto fn = tmap_encode_fn();
@@ -81,7 +95,7 @@ inline int make_tmap_nchw_bf16(CUtensorMap* out, void* ptr, uint64_t B, uint64_t
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (HW % 8)) return -2;
   cuuint64_t gdim[3] = {HW, C, B};
   cuuint64_t gstride[2] = {HW * 2, C * HW * 2};
-  cuuint32_t box[3] = {32, 64, 1};
+  cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

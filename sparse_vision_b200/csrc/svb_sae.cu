@@ -207,7 +207,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     EpiDecNchw::Params e2{};
     e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
     e2.out = static_cast<bf16*>(dec_out);
-    if (make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
+    if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
     if (dec_out && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     prof_mark(h, st, 3);

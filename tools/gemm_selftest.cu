@@ -553,6 +553,49 @@ static int perf_de() {
   return 0;
 }
 
+// decoder-shaped GEMM at cfg2 (M = T, N = C = 256, K = F = 2048): how much does the operand-ring depth matter?
+// EpiStore has 34 KB of epilogue smem (4 stages of 48 KB); EpiStorePad pretends to need 66 KB like EpiDec (3 stages).
+struct EpiStorePad : EpiStore {
+  static constexpr uint32_t kSmemBytes = 2 * SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
+  using EpiStore::EpiStore;
+};
+template <class Epi>
+static void perf_dec_one(const char* name, const void* dA, const void* dB, void* dD, float* bias, int M, int N, int K) {
+  EpiStore::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out = dD; ep.ld = N; ep.bias = bias; ep.alpha = 1.f; ep.relu = 0; ep.out_bf16 = 1;
+  if (make_store_tmap_bf16(&ep.tm, dD, M, N, N) == 0) ep.tm_valid = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, Epi>(0, dA, K, dB, K, M, N, K, 1, ep);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int it = 0; it < 10; ++it) launch_gemm<256, false, false, Epi>(0, dA, K, dB, K, M, N, K, 1, ep);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= 10;
+  printf("[perf dec %-18s stages=%d] %.3f ms  %.1f TFLOP/s  A stream %.1f GB/s\n", name,
+         GemmCfg<256, Epi::kSmemBytes>::kStages, ms, 2.0 * M * N * K / ms * 1e-9, (double)M * K * 2 / ms * 1e-6);
+}
+static int perf_dec() {
+  const int M = 200704, N = 256, K = 2048;
+  void *dA, *dB, *dD;
+  float* bias;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dD, (size_t)M * N * 2));
+  CK(cudaMalloc(&bias, N * 4));
+  CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
+  CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
+  CK(cudaMemset(bias, 0, N * 4));
+  perf_dec_one<EpiStore>("EpiStore", dA, dB, dD, bias, M, N, K);
+  perf_dec_one<EpiStorePad>("EpiStore padded", dA, dB, dD, bias, M, N, K);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("%d\n", (int)(sizeof(kCases) / sizeof(kCases[0])));
@@ -563,6 +606,7 @@ int main(int argc, char** argv) {
   if (std::string(argv[1]) == "probe") return perf_probe();
   if (std::string(argv[1]) == "write") return perf_write();
   if (std::string(argv[1]) == "perf_de") return perf_de();
+  if (std::string(argv[1]) == "perf_dec") return perf_dec();
   const int i = atoi(argv[1]);
   if (i < 0 || i >= (int)(sizeof(kCases) / sizeof(kCases[0]))) return 3;
   return dispatch(kCases[i]);
