@@ -132,6 +132,38 @@ def cpu_reference_throughput(n_images, steps, warmup, threads=None):
     return tokens / dt, dt * 1e3, torch.get_num_threads()
 
 
+def gated_section(dev, peaks, n_images=256, iters=10):
+    """configs[2]: GatedSae on inception4c-shaped activations (C=512, 14x14, expansion 16 -> F=8192), one fused training
+    step per call on bf16 NCHW activations resident in HBM; 12*C*F FLOP per token."""
+    from sparse_vision_b200 import ops
+    from sparse_vision_b200.models.gated_sae import GatedSae
+    Cc, side, k = 512, 14, 16
+    F, T = Cc * k, n_images * side * side
+    torch.manual_seed(0)
+    model = GatedSae(Cc, k)
+    params = [p.detach().clone().to(dev) for p in model.param_list()]
+    ms_ = [torch.zeros_like(p) for p in params]
+    vs_ = [torch.zeros_like(p) for p in params]
+    g = torch.Generator(device="cpu").manual_seed(21)
+    xs = [torch.relu(torch.randn(n_images, Cc, side, side, generator=g)).to(torch.bfloat16).to(dev) for _ in range(2)]
+    for i in range(3):
+        res = ops.gated_train_step(xs[i % 2], params, ms_, vs_, i + 1, LR, 0.1, k, optimizer="constrained_adam")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        res = ops.gated_train_step(xs[i % 2], params, ms_, vs_, i + 4, LR, 0.1, k, optimizer="constrained_adam")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 12.0 * Cc * F * T / (ms * 1e-3) / 1e12
+    sc = res.scalars()
+    return {"workload": "configs[2]: GatedSae C=512 14x14 k=16 F=8192, 256 images = 50176 tokens, constrained_adam, bf16 NCHW",
+            "ms_per_step": ms, "act_vec_per_s": T / (ms * 1e-3), "algorithmic_tflops": tf,
+            "frac_of_sustained_peak": tf / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
+            "final_step_stats": {kk: sc[kk] for kk in ("loss", "rec", "l1", "aux")}}
+
+
 def ie_section(dev, peaks, n_images=64, iters=20):
     """IE images/sec (second half of the BASELINE.json metric) at cfg5 / mixed3a: F=2048 SAE features on 28x28 maps.
     Times (a) the stand-alone compute_ie_channel_wise reduction (utils.py:2606-2637) on fp32 and bf16 [T,F] inputs —
@@ -351,6 +383,7 @@ def run_svb(args):
         }
         if world == 1 and not args.no_ie:
             line["ie"] = ie_section(dev, peaks)
+            line["gated"] = gated_section(dev, peaks)
         if cpu_v is not None:
             line["cpu_baseline"] = {
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -635,7 +635,7 @@ struct EpiDPreT {
   struct Params {
     alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
     const uint32_t* mask_words;        // [M, words]
-    float* colsum_partial;             // CS = 1: [groups * 4, N] with group = blockIdx.x / tiles_n;
+    float* colsum_partial;             // CS = 1: [slots * 4, N] with slot = TileInfo::cta_slot;
                                        // CS = 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens
     float l1c;
     int words;
@@ -648,10 +648,10 @@ struct EpiDPreT {
   SlabWriter1 slab;
   uint32_t words[4];
   float2 csacc[2];  // CS = 1: running sums of this lane's two columns, per slab of the warp
-  int ew, cpw, c_first, n0_last, tiles_n_last, N_last;
+  int ew, cpw, c_first, n0_last, slot_last, N_last;
   __device__ EpiDPreT(const Params& p_, uint8_t* smem, int ew_, int block_n_)
       : p(p_), ew(ew_), cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
-        n0_last(-1), tiles_n_last(1), N_last(0) {
+        n0_last(-1), slot_last(0), N_last(0) {
     slab.init(smem, ew_);
     csacc[0] = make_float2(0.f, 0.f);
     csacc[1] = make_float2(0.f, 0.f);
@@ -733,12 +733,12 @@ struct EpiDPreT {
       slab_done(g, ti, col_slab0, wq, lane, ((col_slab0 - ti.n0) >> 6) & 1);
       slab.flush(&p.tm_dpre, col_slab0, ti.m0 + wq * 32, lane, p.out_slab);
     }
-    n0_last = ti.n0; tiles_n_last = g.tiles_n; N_last = g.N;
+    n0_last = ti.n0; slot_last = ti.cta_slot; N_last = g.N;
   }
   __device__ void finish(int wq, int lane) {
     slab.drain(lane);
     if (CS == 1 && n0_last >= 0) {
-      const size_t rowp = static_cast<size_t>(blockIdx.x / tiles_n_last) * 4 + wq;
+      const size_t rowp = static_cast<size_t>(slot_last) * 4 + wq;
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
         const int col = n0_last + c_first * 32 + si * 64 + 2 * lane;

@@ -40,6 +40,7 @@ struct TileInfo {
   int split;      // split-K slice
   int tile_m;     // tile index along M
   int tile_n;
+  int cta_slot;   // B-stationary schedules: index of this CTA among the CTAs that share its N tile
 };
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
@@ -111,6 +112,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int
   ti.split = r / p.tiles_m;
   ti.m0 = ti.tile_m * kBlockM;
   ti.n0 = ti.tile_n * block_n;
+  ti.cta_slot = 0;
   return ti;
 }
 
@@ -176,6 +178,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if constexpr (BSTAT) {
       TileInfo ti;
       ti.tile_n = fixed_n; ti.tile_m = t; ti.split = 0; ti.m0 = t * kBlockM; ti.n0 = fixed_n * BLOCK_N;
+      ti.cta_slot = static_cast<int>(blockIdx.x) / p.tiles_n;
       return ti;
     } else {
       return decode_tile(p, t, BLOCK_N);

@@ -40,6 +40,7 @@ struct Case {
   int splits;  // 0 = auto, 1 = none
   bool bf16_out = false;  // bf16 output through the TMA slab store (K must keep |sums| <= 256 so bf16 is exact)
   bool bstat = false;     // B-stationary schedule (K <= 256)
+  bool two_cta = false;   // cta_group::2 B-stationary kernel (gemm2_sm100.cuh)
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -71,7 +72,10 @@ static int run(const Case& c) {
     ep.out = dC; ep.ld = c.N; ep.alpha = 1.0f; ep.out_bf16 = 1;
     if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
     else { printf("[%s] store tensor map failed\n", c.name); return 1; }
-    if (c.bstat) rc = launch_gemm<BN, AMN, BMN, EpiStore, true>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+    if (c.two_cta) {
+      if constexpr (!AMN) { rc = launch_gemm2_bstat<BMN, EpiStore>(0, dA, c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, ep); used = 1; }
+      else { printf("[%s] the 2-CTA kernel needs a K-major A\n", c.name); return 1; }
+    } else if (c.bstat) rc = launch_gemm<BN, AMN, BMN, EpiStore, true>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
     else rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
    } else { printf("[%s] bf16 slab output needs BLOCK_N=256\n", c.name); return 1; }
   } else {
@@ -149,6 +153,11 @@ static const Case kCases[] = {
     {"kk_bstat", 128 * 300 + 40, 512, 16, false, false, 256, 1, true, true},
     {"kk_bstat_k24_ntail", 5000, 200, 24, false, false, 256, 1, true, true},
     {"kmn_bstat", 3000, 768, 16, false, true, 256, 1, true, true},
+    {"kk_2cta_one_pair", 256, 256, 16, false, false, 256, 1, true, true, true},
+    {"kk_2cta", 128 * 300 + 40, 512, 16, false, false, 256, 1, true, true, true},
+    {"kk_2cta_k24_ntail", 5000, 200, 24, false, false, 256, 1, true, true, true},
+    {"kmn_2cta", 3000, 768, 16, false, true, 256, 1, true, true, true},
+    {"kk_2cta_mtail_odd", 128 * 7 + 3, 256, 16, false, false, 256, 1, true, true, true},
 };
 
 static int perf() {
@@ -191,6 +200,16 @@ static int perf() {
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
   printf("[perf enc B-stationary] %.3f ms  %.1f TFLOP/s  out %.1f GB/s\n", ms, 2.0 * M * N * K / ms * 1e-9,
+         (double)M * N * 2 / ms * 1e-6);
+  for (int it = 0; it < 3; ++it) launch_gemm2_bstat<false, EpiStore>(0, dA, K, dB, K, M, N, K, ep);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int it = 0; it < iters; ++it) launch_gemm2_bstat<false, EpiStore>(0, dA, K, dB, K, M, N, K, ep);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("[perf enc 2-CTA B-stationary] %.3f ms  %.1f TFLOP/s  out %.1f GB/s\n", ms, 2.0 * M * N * K / ms * 1e-9,
          (double)M * N * 2 / ms * 1e-6);
   // split-K weight-gradient shape: dW_dec[C,F] = diff^T[C,T] e[T,F]
   {
@@ -414,6 +433,27 @@ static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int
   }
 }
 
+template <int MODE>
+static void probe_two_cta(const void* dA, const void* dB, void* dE, float* sink, int M, int N, int K) {
+  typename EpiProbe<MODE, 8>::Params ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.sink = sink;
+  make_store_tmap_bf16(&ep.tm, dE, M, N, N);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) launch_gemm2_bstat<false, EpiProbe<MODE, 8>>(0, dA, K, dB, K, M, N, K, ep);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int it = 0; it < 10; ++it) launch_gemm2_bstat<false, EpiProbe<MODE, 8>>(0, dA, K, dB, K, M, N, K, ep);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= 10;
+  printf("[probe mode %d 2-CTA] %.3f ms  %.1f TFLOP/s\n", MODE, ms, 2.0 * M * N * K / ms * 1e-9);
+}
+
 static int perf_probe() {
   const int M = 200704, N = 2048, K = 256;
   void *dA, *dB, *dE;
@@ -424,6 +464,8 @@ static int perf_probe() {
   CK(cudaMalloc(&sink, 64));
   CK(cudaMemset(dA, 0x3c, (size_t)M * K * 2));
   CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
+  probe_two_cta<0>(dA, dB, dE, sink, M, N, K);
+  probe_two_cta<2>(dA, dB, dE, sink, M, N, K);
   probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<2, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
