@@ -5,6 +5,8 @@ indirect-effect reductions (:2574-2660) and apply_sae (:2786-2820).  Everything 
 """
 import logging
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -262,3 +264,65 @@ def apply_sae(sae, model_output, nodes=None, ablation=None):
     else:
         new_decoder_output = decoder_output
     return encoder_output, _to_bchw(decoder_output, b, h, w), _to_bchw(new_decoder_output, b, h, w)
+
+# --------------------------------------------------------------------------------------------------- a17: trained SAEs
+def get_file_path(folder_path=None, sae_layer=None, params=None, file_name=None, params2=None):
+    """utils.py:151-185: `<folder>/<layer>[_<params>[_<params2>]]<ending>` where a file name that starts with '.' is an
+    extension and anything else is appended with '_' (None included, as in the reference).  Dict parameters are
+    joined by '_' in insertion order with None spelled "None"; the folder is created."""
+    ending = file_name if (file_name is not None and file_name.startswith(".")) else f"_{file_name}"
+    if folder_path is not None:
+        os.makedirs(folder_path, exist_ok=True)
+
+    def joined(prm):
+        return "_".join("None" if v is None else str(v) for v in prm.values()) if isinstance(prm, dict) else prm
+
+    stem = sae_layer if params is None else (
+        f"{sae_layer}_{joined(params)}" if params2 is None else f"{sae_layer}_{joined(params)}_{joined(params2)}")
+    name = f"{stem}{ending}"
+    return name if folder_path is None else os.path.join(folder_path, name)
+
+
+# layer suffix -> (dead_neurons_steps, checkpoint epoch, lambda_sparse, expansion factor); utils.py:2671-2724.  The
+# learning rate (0.001) and the SAE batch size ('256') are the same for every layer.
+_SAE_LAYER_TABLE = {
+    "3a": (626, 7, 5.0, 8), "3b": (625, 6, 0.1, 4), "4a": (625, 6, 0.1, 4), "4b": (625, 6, 0.1, 4),
+    "4c": (625, 5, 0.1, 4), "4d": (625, 7, 0.1, 4), "4e": (625, 9, 0.1, 4), "5a": (625, 5, 0.1, 4),
+    "5b": (625, 12, 0.1, 4),
+}
+
+
+def get_specific_sae_params(layer_name, sae_model_name, model_params_temp, sae_optimizer_name):
+    """utils.py:2662-2741: the hyper-parameters a layer's SAE was trained with and the two parameter strings that name
+    its checkpoint / MIS files.  Returns (params_string_ie, checkpoint_epoch, expansion_factor, params_string_mis,
+    dead_neurons_steps).  Layer names are `mixedXY` or `inceptionXY`."""
+    for prefix in ("mixed", "inception"):
+        if layer_name.startswith(prefix) and layer_name[len(prefix):] in _SAE_LAYER_TABLE:
+            steps, ckpt_epoch, lam, k = _SAE_LAYER_TABLE[layer_name[len(prefix):]]
+            break
+    else:
+        raise UnboundLocalError(f"no SAE parameters are recorded for layer {layer_name}")   # the reference fails the same way
+    base = "_".join(model_params_temp.values())
+    tail = [str(v) for v in (0.001, "256", sae_optimizer_name, k, lam, steps)]
+    ie = f"{base}_{sae_model_name}_" + "_".join(tail) + f"_sae_checkpoint_epoch_{ckpt_epoch}"
+    sae_epoch = "11" if layer_name[-2:] == "3a" else "13"       # part of the MIS file name only (:2733-2736)
+    mis = f"{base}_{sae_model_name}_{sae_epoch}_" + "_".join(tail) + f"_mis_epoch_{ckpt_epoch}"
+    return ie, ckpt_epoch, k, mis, steps
+
+
+def get_specific_sae_model(layer_name, layer_size, sae_model_name, sae_weights_folder_path, model_params_temp, device,
+                           sae_optimizer_name):
+    """utils.py:2745-2767: build the layer's SAE, load `<folder>/<layer>_<params>.pth` ('model_state_dict', the
+    checkpoint format of model_pipeline.py:1268-1273) and freeze it in eval mode.
+    Returns (sae_model, params_string, expansion_factor)."""
+    params_string, ckpt_epoch, k, _, _ = get_specific_sae_params(layer_name, sae_model_name, model_params_temp,
+                                                                 sae_optimizer_name)
+    sae_model = load_model(sae_model_name, img_size=layer_size, expansion_factor=k)
+    if ckpt_epoch > 0:
+        path = get_file_path(sae_weights_folder_path, layer_name, params=params_string, file_name=".pth")
+        sae_model.load_state_dict(torch.load(path, map_location=device)["model_state_dict"])
+        print(f"Use SAE on layer {layer_name} from epoch {ckpt_epoch}")
+    sae_model = sae_model.to(device).eval()
+    for param in sae_model.parameters():
+        param.requires_grad = False
+    return sae_model, params_string, int(k)

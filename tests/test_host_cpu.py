@@ -179,3 +179,39 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "act-vec/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_sae_params_table_and_file_paths_match_reference(golden_dir, tmp_path):
+    """SURVEY.md section 8 row a17 against outputs of the reference's own get_specific_sae_params / get_file_path
+    (tests/golden/sae_params_table.json, made by oracle/gen_golden_params.py)."""
+    import json
+    from sparse_vision_b200 import utils as U
+    g = json.load(open(os.path.join(golden_dir, "sae_params_table.json")))
+    for key, want in g["layers"].items():
+        layer, sae, opt = key.split("|")
+        got = U.get_specific_sae_params(layer, sae, {k: v for k, v in g["model_params_temp"]}, opt)
+        assert list(got) == want, key
+    for c in g["paths"]:
+        folder = None if c["folder"] is None else os.path.join(str(tmp_path), c["folder"])
+        fp = U.get_file_path(folder, c["layer"], c["params"], c["file_name"], c["params2"])
+        rel = fp if folder is None else os.path.relpath(fp, str(tmp_path))
+        assert rel == c["result"], c
+        if folder is not None:
+            assert os.path.isdir(folder)
+
+
+def test_get_specific_sae_model_loads_reference_format_checkpoint(tmp_path):
+    """A checkpoint written in the reference's format (model_pipeline.py:1268-1273 keys, utils.py:151-185 file name)
+    is found, loaded and frozen (utils.py:2745-2767)."""
+    from sparse_vision_b200 import utils as U
+    mp = {"model_name": "inceptionv1", "epochs": "0", "lr": "0.001", "bs": "512", "opt": "sgd"}
+    ps, _, k, _, _ = U.get_specific_sae_params("mixed4c", "sae_mlp", mp, "constrained_adam")
+    torch.manual_seed(9)
+    src = U.load_model("sae_mlp", img_size=512, expansion_factor=k)
+    torch.save({"epoch": 5, "model_state_dict": src.state_dict(), "optimizer_state_dict": {}, "training_step": 7},
+               U.get_file_path(str(tmp_path), "mixed4c", params=ps, file_name=".pth"))
+    sae, ps2, k2 = U.get_specific_sae_model("mixed4c", 512, "sae_mlp", str(tmp_path), mp, "cpu", "constrained_adam")
+    assert ps2 == ps and k2 == 4 and not sae.training
+    assert all(not p.requires_grad for p in sae.parameters())
+    for a, b in zip(sae.state_dict().values(), src.state_dict().values()):
+        assert torch.equal(a, b)
