@@ -52,7 +52,7 @@ def main():
         lab = next((v for k, v in PHASE.items() if k in d[kn]), None)
         if lab is None:
             seen["dW"] += 1
-            lab = "dWdec_gemm" if seen["dW"] == 1 else "dWenc_gemm"
+            lab = "dWenc_gemm" if seen["dW"] == 1 else "dWdec_gemm"   # the encoder-side weight gradient runs first
         labels.append(lab)
     md = [f"# {tag} — `ncu --set full --clock-control none` of the five GEMM launches of one training step", "",
           f"Command: `ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 15 -c 5 python bench.py --steps 3 --warmup 3` (report: `{os.path.basename(rep)}`).",
