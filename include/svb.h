@@ -168,7 +168,7 @@ int svb_sae_grad_buffer(svb_handle* h, float** buf, int64_t* sum_elems, int64_t*
 
 /* Data-parallel overlap (the reference has no distributed code).  With a communication stream
  * set, svb_*_step_grads makes that stream wait until the LEADING svb_grad_early_elems() elements of the flat buffer
- * (the encoder-side gradients, [gW_enc | gb_enc] resp. [gW_gate | gb_gate | gb_mag | gr_mag]) are final; the caller
+ * (the encoder-side gradients, [gW_enc | gb_enc] resp. [gW_gate | gb_gate | gb_mag]) are final; the caller
  * all-reduces them on it while the decoder weight-gradient GEMM is still running on `stream`, and the rest of the
  * SUM section afterwards.  Pass NULL to switch the early release off (the default). */
 int svb_set_comm_stream(svb_handle* h, void* stream);
