@@ -280,3 +280,47 @@ def test_step_is_deterministic():
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         assert torch.equal(a, b)
+
+
+def test_full_size_cfg2_step_properties():
+    """BASELINE configs[1] at its FULL size (256 images, C=256, 28x28, F=2048): properties that do not need the CPU
+    oracle -- bit-reproducibility, the step's scalars against what the returned tensors imply, and the dead-unit mask
+    against the encoder output of the forward API."""
+    ops = _ops()
+    B, C, H, W, k = 256, 256, 28, 28, 8
+    F = C * k
+    torch.manual_seed(0)
+    p = O.init_sae_mlp(C, k)
+    p["encoder.bias"][torch.randperm(F, generator=torch.Generator().manual_seed(1))[:F // 20]] = -50.0
+    x = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5))).bfloat16().cuda()
+
+    def run():
+        params = [p[key].clone().cuda() for key in O.SAE_MLP_KEYS]
+        ms = [torch.zeros_like(q) for q in params]
+        vs = [torch.zeros_like(q) for q in params]
+        res = ops.sae_train_step(x, params, ms, vs, 1, 1e-3, 5.0, k, optimizer="constrained_adam")
+        return params, res, res.scalars(), res.dec.clone(), res.dead.clone()
+
+    params1, res1, sc1, dec1, dead1 = run()
+    params2, res2, sc2, dec2, dead2 = run()
+    assert sc1 == sc2 and torch.equal(dec1, dec2) and torch.equal(dead1, dead2)          # bit-reproducible
+    for a, b in zip(params1, params2):
+        assert torch.equal(a, b)
+    # scalars vs the returned reconstruction (bf16 NCHW, like the input)
+    xf, df = x.float(), dec1.float()
+    rec = ((df - xf) ** 2).mean().item()
+    assert abs(sc1["rec"] - rec) <= 1e-2 * rec
+    var_expl = 1.0 - (df.var(dim=(2, 3)).mean() / xf.var(dim=(2, 3)).mean()).item()       # utils.py:2012-2030
+    assert abs(sc1["var_expl"] - var_expl) <= 1e-2 * max(abs(var_expl), 1e-3)
+    rmse_c = ((df - xf) ** 2).mean(dim=(0, 2, 3)).sqrt()
+    assert abs(sc1["rmse"] - rmse_c.mean().item()) <= 1e-2 * rmse_c.mean().item()
+    rng = xf.amax(dim=(0, 2, 3)) - xf.amin(dim=(0, 2, 3))
+    assert abs(sc1["nrmse"] - (rmse_c / rng).mean().item()) <= 1e-2 * (rmse_c / rng).mean().item()
+    # the planted dead units and nothing else (utils.py:2032-2069), checked against the forward API's encoder output
+    enc, dec_f, _ = ops.sae_forward(x, *[p[key].clone().cuda() for key in O.SAE_MLP_KEYS], want_pre=False)
+    active = (enc.reshape(B, H * W, F) != 0).any(dim=1).any(dim=0)
+    assert torch.equal(dead1.bool(), ~active)
+    assert int(sc1["n_dead"]) == int((~active).sum().item()) >= F // 20
+    l1 = enc.float().abs().mean().item()
+    assert abs(sc1["l1"] - l1) <= 1e-2 * l1
+    assert abs(sc1["loss"] - (sc1["rec"] + 5.0 * sc1["l1"])) <= 1e-5 * sc1["loss"]

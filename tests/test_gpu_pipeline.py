@@ -78,3 +78,41 @@ def test_hook_training_with_reinit_matches_oracle(tmp_path, monkeypatch, hw, ste
     # Adam moments of re-initialised units were reset on both sides
     m_gpu = pipe.sae_optimizer.state[sae.encoder.weight]["exp_avg"].cpu()
     assert np.allclose(m_gpu.numpy(), st["m"]["encoder.weight"].numpy(), atol=5e-3)
+
+
+def test_checkpoint_round_trip_resumes_bit_exact(tmp_path):
+    """model_pipeline.py:233-263,1266-1280: a checkpoint with the reference's keys, written mid-training and loaded into
+    a fresh pipeline, continues exactly like the uninterrupted run (the fused step is deterministic)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import sparse_vision_b200.models.sae_mlp as M
+    from sparse_vision_b200.model_pipeline import ModelPipeline
+
+    C, k, B = 64, 4, 4
+
+    def make():
+        torch.manual_seed(0)
+        base = nn.Sequential(collections.OrderedDict(conv=nn.Conv2d(3, C, 3, padding=1), act=nn.ReLU())).eval().cuda()
+        sae = M.SaeMLP(C, k).cuda()
+        pipe = ModelPipeline(base, sae, "sae_mlp", "act", "constrained_adam", 1e-3, 5.0, k)
+        pipe.register_hooks(train_sae=True)
+        return pipe, sae
+
+    xs = [torch.randn(B, 3, 16, 16, generator=torch.Generator().manual_seed(7 + i)).cuda() for i in range(6)]
+    pipe_a, sae_a = make()
+    for x in xs:
+        pipe_a.train_batch(x)
+    pipe_b, sae_b = make()
+    for x in xs[:3]:
+        pipe_b.train_batch(x)
+    path = os.path.join(str(tmp_path), "ckpt.pth")
+    pipe_b.save_checkpoint(path, epoch=2)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "training_step"}      # reference keys
+    assert list(ck["model_state_dict"]) == ["encoder.weight", "encoder.bias", "decoder.weight", "decoder.bias"]
+    pipe_c, sae_c = make()
+    assert pipe_c.load_checkpoint(path) == 2 and pipe_c.train_batch_idx == 3
+    for x in xs[3:]:
+        pipe_c.train_batch(x)
+    for a, c in zip(sae_a.param_list(), sae_c.param_list()):
+        assert torch.equal(a, c), "resumed training diverged from the uninterrupted run"
