@@ -484,8 +484,10 @@ struct EpiDecNchw {
     const __nv_bfloat16* x;           // slab-major [M, N] targets (the SAE input)
     float* sq_partial;                // [gridDim.x * kWarps]: one running sum per CTA and epilogue warp
     float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_image_kernel
-    __nv_bfloat16* out;               // the NCHW output tensor behind tm_out (null: d is not handed back)
-    int hw;                           // tokens per image (>= 32, multiple of 8 when out != null)
+    void* out;                        // the caller's NCHW output tensor (null: d is not handed back)
+    int hw;                           // tokens per image (>= 32)
+    int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base); 2: bf16 and
+                                      // 3: fp32 with plain stores from the staged tile (any HW / alignment)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -593,17 +595,50 @@ struct EpiDecNchw {
       }
       part0[2 * g.N + col] = s;
     }
-    // (3) second image of a straddling warp: positions 0 .. n1-1 (n0 and n1 are multiples of 8), 16-byte copies
-    if (p.out && n1 > 0) {
-      const uint4* src = reinterpret_cast<const uint4*>(tbuf + lane * 64 + n0 * 2);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
-      for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
+    // (3) d back to NCHW.  out_kind 1: one TMA store for the positions of image b0 (clipped at the image end); the
+    // positions of a second image in a straddling warp (n0, n1 multiples of 8 there) are copied with 16-byte stores.
+    // out_kind 2 / 3: rows that TMA cannot address (HW % 8 != 0) or fp32 outputs -- every lane writes its channel's
+    // tokens from the staged tile itself, one image segment after the other.
+    if (p.out_kind == 1) {
+      if (n1 > 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(tbuf + lane * 64 + n0 * 2);
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
+        for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
+      }
+    } else if (p.out_kind != 0) {
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(tbuf + lane * 64);
+      const int hw0 = row0 - b0 * p.hw;
+#pragma unroll
+      for (int seg = 0; seg < 2; ++seg) {
+        const int cnt = seg == 0 ? n0 : n1, first = seg == 0 ? 0 : n0;
+        const size_t base = (static_cast<size_t>(b0 + seg) * g.N + col) * p.hw + (seg == 0 ? hw0 : 0);
+        if (cnt <= 0) continue;
+        if (p.out_kind == 2) {
+          uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + base;
+          if (((reinterpret_cast<uintptr_t>(dst) & 7) | (first & 3) | (cnt & 3)) == 0) {   // 14x14 maps: 8-byte pieces
+            for (int i = 0; i < cnt; i += 4)
+              *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<const uint2*>(src + first + i);
+          } else {
+            for (int i = 0; i < cnt; ++i) dst[i] = src[first + i];
+          }
+        } else {
+          float* dst = static_cast<float*>(p.out) + base;
+          if (((reinterpret_cast<uintptr_t>(dst) & 15) | (first & 3) | (cnt & 3)) == 0) {
+            for (int i = 0; i < cnt; i += 4) {
+              const uint2 w = *reinterpret_cast<const uint2*>(src + first + i);
+              *reinterpret_cast<float4*>(dst + i) = make_float4(bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y));
+            }
+          } else {
+            for (int i = 0; i < cnt; ++i) dst[i] = __uint_as_float(static_cast<uint32_t>(src[first + i]) << 16);
+          }
+        }
+      }
     }
     // (4) asynchronous stores of both tiles
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (p.out) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);
+      if (p.out_kind == 1) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);
       tma_store_3d(&p.tm_diff, fbuf, col0 & 63, row0, col0 >> 6);
       bulk_commit();
     }

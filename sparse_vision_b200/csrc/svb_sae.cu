@@ -175,11 +175,15 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // E and dPre' whenever F % 64 == 0; X, D, DIFF when we pack X ourselves from NCHW and the fused post-decoder pass runs.
   pl.es = F % 64 == 0;
   pl.xs = !pl.zero_copy_x && C % 64 == 0 && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
-  // Fused decoder epilogue: needs the slab-major path, >= 32 tokens per image (a warp's 32 tokens then touch at most
-  // two images) and, if d is handed back, a bf16 NCHW tensor TMA can address (16-byte row pitch).
+  // Fused decoder epilogue: needs the slab-major path and >= 32 tokens per image (a warp's 32 tokens then touch at
+  // most two images).  d goes back to the caller's NCHW tensor by TMA when that can address it (bf16, 16-byte row
+  // pitch), else by 8- / 16-byte stores from the staged tiles (fp32 outputs, 14x14 maps).
   void* dec_out = out ? out->dec_out : nullptr;
-  pl.fused_dec = pl.xs && pl.hw >= 32 &&
-                 (!dec_out || (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0));
+  pl.fused_dec = pl.xs && pl.hw >= 32 && (!dec_out || pl.hw % 4 == 0);   // 7x7 maps: element-wise stores are too slow
+  int out_kind = 0;
+  if (dec_out)
+    out_kind = out->dec_dtype == SVB_F32 ? 3
+               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 2;
   prof_begin_step(h);
   prof_mark(h, st, 0);
   // weight prologue on the side stream, next to the activation pack
@@ -206,9 +210,9 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   if (pl.fused_dec) {
     EpiDecNchw::Params e2{};
     e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
-    e2.out = static_cast<bf16*>(dec_out);
+    e2.out = dec_out; e2.out_kind = out_kind;
     if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
-    if (dec_out && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
+    if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
     // the statistics folds only feed the tail of the step: side stream, beside the dE GEMM

@@ -226,6 +226,7 @@ def test_adam_step_and_reinit(golden_dir):
     (3, 528, 14, 14, 4, "sae_mlp"),      # C not a multiple of 64/128/256 (K and N tails)
     (3, 64, 12, 12, 4, "sae_mlp"),       # fused NCHW decoder epilogue: 144-pixel images straddle warps, ragged last tile
     (5, 128, 8, 8, 8, "sae_mlp"),        # fused path with two images per 128-token tile
+    (4, 128, 14, 14, 4, "sae_mlp"),      # fused path, 196-pixel maps: rows TMA cannot address -> plain NCHW stores
 ])
 def test_train_step_vs_oracle_larger(B, C, H, W, k, kind):
     ops = _ops()
