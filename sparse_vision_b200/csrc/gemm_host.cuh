@@ -17,6 +17,13 @@ inline unsigned long long& launch_counter() {
 }
 inline void count_launch() { ++launch_counter(); }
 
+#ifdef SVB_GEMM_TRACE
+inline long long*& gemm_trace_ptr() {  // bring-up only (tools/gemm_selftest.cu): device buffer [grid][4] of wait cycles
+  static long long* p = nullptr;
+  return p;
+}
+#endif
+
 inline PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -119,7 +126,7 @@ inline int device_sm_count() {
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0,
-                unsigned long long a_policy = 0, bool a_slab = false, bool b_slab = false) {
+                unsigned long long a_policy = 0, bool a_slab = false, bool b_slab = false, int a_prefetch = 0) {
   using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
@@ -139,6 +146,10 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   p.a_policy = a_policy;
   p.a_slab = a_slab ? 1 : 0;
   p.b_slab = b_slab ? 1 : 0;
+  p.a_prefetch = a_prefetch;
+#ifdef SVB_GEMM_TRACE
+  p.trace = gemm_trace_ptr();
+#endif
   p.tiles_m = (M + kBlockM - 1) / kBlockM;
   p.tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int kblocks = (K + kBlockK - 1) / kBlockK;

@@ -33,7 +33,16 @@ struct GemmProblem {
   int tiles_m, tiles_n;
   unsigned long long a_policy = 0, b_policy = 0;  // L2 eviction policy of the operand loads (0 = default)
   int a_slab = 0, b_slab = 0;  // operand stored slab-major ([cols/64][rows][64], 3-D tensor map; see gemm_host.cuh)
+  int a_prefetch = 0;          // B-stationary schedule: L2-prefetch the A tiles this many steps of the CTA's walk ahead
+#ifdef SVB_GEMM_TRACE
+  long long* trace = nullptr;  // bring-up only: [gridDim.x][4] cycles the producer / MMA thread / epilogue spent waiting
+#endif
 };
+#ifdef SVB_GEMM_TRACE
+#define SVB_TRACED_WAIT(acc, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); acc += clock64() - t0_; } while (0)
+#else
+#define SVB_TRACED_WAIT(acc, bar, par) mbar_wait(bar, par)
+#endif
 
 struct TileInfo {
   int m0, n0;     // element offsets of this tile
@@ -189,6 +198,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
+      (void)w_empty;
       auto load_b = [&](uint8_t* sb, uint64_t* bar, int k0, int n0) {
         if constexpr (!B_MN) {
           if (p.b_slab) tma_load_3d(sb, &tmB, bar, 0, n0, k0 >> 6);
@@ -213,8 +224,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int k_begin = ti.split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
+        if constexpr (BSTAT && !A_MN) {
+          // The A tile is shared by the tiles_n CTAs of a group and its first touch is an HBM read that queues behind
+          // this kernel's own output stream: one CTA of the group pulls it into L2 well ahead of its use.
+          const int tp = t + p.a_prefetch * t_step;
+          if (p.a_prefetch > 0 && fixed_n == 0 && tp < t_end) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (p.a_slab) tma_prefetch_l2_3d(&tmA, 0, tp * kBlockM, kb);
+              else tma_prefetch_l2_2d(&tmA, kb * kBlockK, tp * kBlockM);
+            }
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          SVB_TRACED_WAIT(w_empty, &empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ring + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = k_begin + kb * kBlockK;
@@ -233,12 +255,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef SVB_GEMM_TRACE
+      if (p.trace) p.trace[blockIdx.x * 4 + 0] = w_empty;
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long w_full = 0, w_tmem = 0;
+      (void)w_full; (void)w_tmem;
       if constexpr (BSTAT) {
         if (t_first < t_end) mbar_wait(b_full_bar, 0);
       }
@@ -247,11 +274,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int k_begin = ti.split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         const int nkb = (k_end - k_begin + kBlockK - 1) / kBlockK;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        SVB_TRACED_WAIT(w_tmem, &tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          SVB_TRACED_WAIT(w_full, &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem_ring + stage * Cfg::kStageBytes);
           const uint32_t b_base = BSTAT ? smem_u32(smem + kb * Cfg::kBBytes) : a_base + Cfg::kABytes;
@@ -273,6 +300,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+#ifdef SVB_GEMM_TRACE
+      if (p.trace) { p.trace[blockIdx.x * 4 + 1] = w_full; p.trace[blockIdx.x * 4 + 2] = w_tmem; }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 lane quarters x kWarps/4 column groups)
@@ -287,6 +317,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tid = ew * 32 + lane;
     Epi epi(ep, epi_smem, ew, BLOCK_N);
     uint32_t acc = 0, acc_phase = 0;
+    long long w_acc = 0;
+    (void)w_acc;
     if (Epi::kColVecs > 0 && t_first < t_end) epi.colvec_fetch(p, decode(t_first), tid);
     for (int t = t_first; t < t_end; t += t_step) {
       const TileInfo ti = decode(t);
@@ -295,7 +327,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epi_bar_sync(EW * 32);
         if (t + t_step < t_end) epi.colvec_fetch(p, decode(t + t_step), tid);
       }
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      SVB_TRACED_WAIT(w_acc, &tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = ti.m0 + row_in_tile;
       epi.begin_tile(p, ti, row, wq, lane);
@@ -340,6 +372,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (acc == 0) acc_phase ^= 1;
     }
     epi.finish(wq, lane);  // e.g. drain outstanding bulk stores before the CTA's smem goes away
+#ifdef SVB_GEMM_TRACE
+    if (p.trace && ew == 0 && lane == 0) p.trace[blockIdx.x * 4 + 3] = w_acc;
+#endif
   }
 
   tc_fence_before();

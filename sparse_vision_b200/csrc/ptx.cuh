@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// Prefetch of a tensor tile into L2 only (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // L2 eviction-priority policies for TMA (.L2::cache_hint operand; the encodings createpolicy would produce).
 constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;

@@ -45,6 +45,11 @@ struct SaePlan {
 };
 
 constexpr int kVmChunks = 32;
+// B-stationary GEMMs can let one CTA per group pull the shared A tile into L2 some steps ahead of its use
+// (GemmProblem::a_prefetch).  In the stand-alone probe that takes the output-bound GEMM from 0.193 to 0.180 ms at 2
+// steps (0.187 / 0.193 at 4 / 8: the lines are evicted again), but inside the step, where X / DIFF were written just
+// before, it changes nothing (0.241 vs 0.236 ms), so it is off.
+constexpr int kAPrefetch = 0;
 
 void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) {
   p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
@@ -201,7 +206,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   if (pl.es ? make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for E");
   if (pl.bstat) {
-    SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc (B-stationary)");
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary)");
   } else {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");
   }
@@ -241,7 +246,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
     if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE (B-stationary)");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "dE (B-stationary)");
   } else {
     EpiDPre::Params e3{};
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;

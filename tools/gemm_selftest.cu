@@ -7,6 +7,7 @@
 #include <vector>
 #include <cstring>
 #include <string>
+#define SVB_GEMM_TRACE 1
 #include "../sparse_vision_b200/csrc/gemm_host.cuh"
 #include "../sparse_vision_b200/csrc/epilogues.cuh"
 
@@ -394,6 +395,7 @@ struct EpiProbe {
   }
 };
 
+static int g_prefetch = 0;
 template <int MODE, int WARPS>
 static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int M, int N, int K) {
   typename EpiProbe<MODE, WARPS>::Params ep;
@@ -416,7 +418,7 @@ static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int
   for (int bstat = 0; bstat < 2; ++bstat) {
     auto go = [&]() {
       const unsigned long long apol = MODE == 13 ? kL2EvictLast : 0ull;
-      if (bstat) launch_gemm<256, false, false, EpiProbe<MODE, WARPS>, true>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, apol);
+      if (bstat) launch_gemm<256, false, false, EpiProbe<MODE, WARPS>, true>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, apol, false, false, g_prefetch);
       else launch_gemm<256, false, false, EpiProbe<MODE, WARPS>, false>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, apol);
     };
     for (int it = 0; it < 3; ++it) go();
@@ -430,6 +432,26 @@ static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
     printf("[probe mode %d warps %2d bstat %d] %.3f ms  %.1f TFLOP/s\n", MODE, WARPS, bstat, ms, 2.0 * M * N * K / ms * 1e-9);
+    {  // who waits for whom: one traced launch
+      long long* tr;
+      CK(cudaMalloc(&tr, 148 * 4 * sizeof(long long)));
+      CK(cudaMemset(tr, 0, 148 * 4 * sizeof(long long)));
+      gemm_trace_ptr() = tr;
+      go();
+      CK(cudaDeviceSynchronize());
+      gemm_trace_ptr() = nullptr;
+      long long h[148 * 4];
+      CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      int n = 0;
+      for (int b = 0; b < 148; ++b) {
+        if (h[b * 4 + 1] == 0 && h[b * 4 + 0] == 0) continue;
+        s0 += h[b * 4]; s1 += h[b * 4 + 1]; s2 += h[b * 4 + 2]; s3 += h[b * 4 + 3]; ++n;
+      }
+      if (n) printf("    wait kcycles per CTA: producer on free slot %.0f | MMA on operands %.0f | MMA on free accumulator %.0f | epilogue warp 0 on accumulator %.0f   (kernel ~%.0f kcycles at 1.9 GHz)\n",
+                    s0 / n / 1e3, s1 / n / 1e3, s2 / n / 1e3, s3 / n / 1e3, ms * 1.9e6 / 1e3);
+      cudaFree(tr);
+    }
   }
 }
 
@@ -469,6 +491,12 @@ static int perf_probe() {
   probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<2, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
+  for (int pf : {2, 4, 8, 16}) {
+    g_prefetch = pf;
+    printf("-- A tiles L2-prefetched %d steps ahead\n", pf);
+    probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
+  }
+  g_prefetch = 0;
   probe_one<12, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<13, 8>(dA, dB, dE, sink, M, N, K);
   return 0;
