@@ -180,10 +180,12 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
+      (void)w_empty;
       for (int tp = group; tp < pair_tiles; tp += groups) {
         const TileInfo ti = tile_of(tp);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          SVB_TRACED_WAIT(w_empty, &empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ring + stage * Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * Cfg::kABytes);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -192,19 +194,24 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef SVB_GEMM_TRACE
+      if (p.trace) p.trace[blockIdx.x * 4 + 0] = w_empty;
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BLOCK_N, false, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long w_full = 0, w_tmem = 0;
+      (void)w_full; (void)w_tmem;
       if (group < pair_tiles) mbar_wait(b_full_bar, 0);
       for (int tp = group; tp < pair_tiles; tp += groups) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        SVB_TRACED_WAIT(w_tmem, &tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          SVB_TRACED_WAIT(w_full, &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem_ring + stage * Cfg::kABytes);
           const uint32_t b_base = smem_u32(smem + kb * Cfg::kBHalfBytes);
@@ -222,6 +229,9 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+#ifdef SVB_GEMM_TRACE
+      if (p.trace) { p.trace[blockIdx.x * 4 + 1] = w_full; p.trace[blockIdx.x * 4 + 2] = w_tmem; }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, own TMEM)
@@ -235,6 +245,8 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int tid = ew * 32 + lane;
     Epi epi(ep, epi_smem, ew, BLOCK_N);
     uint32_t acc = 0, acc_phase = 0;
+    long long w_acc = 0;
+    (void)w_acc;
     uint32_t tmem_empty_leader[2];
     tmem_empty_leader[0] = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     tmem_empty_leader[1] = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
@@ -246,7 +258,7 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         epi_bar_sync(EW * 32);
         if (tp + groups < pair_tiles) epi.colvec_fetch(p, tile_of(tp + groups), tid);
       }
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      SVB_TRACED_WAIT(w_acc, &tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = ti.m0 + row_in_tile;
       epi.begin_tile(p, ti, row, wq, lane);
@@ -288,6 +300,9 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (acc == 0) acc_phase ^= 1;
     }
     epi.finish(wq, lane);
+#ifdef SVB_GEMM_TRACE
+    if (p.trace && ew == 0 && lane == 0) p.trace[blockIdx.x * 4 + 3] = w_acc;
+#endif
   }
 
   tc_fence_before();

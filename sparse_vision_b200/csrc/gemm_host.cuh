@@ -22,6 +22,10 @@ inline long long*& gemm_trace_ptr() {  // bring-up only (tools/gemm_selftest.cu)
   static long long* p = nullptr;
   return p;
 }
+inline int& gemm_a_skip() {
+  static int v = 0;
+  return v;
+}
 #endif
 
 inline PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
@@ -213,6 +217,9 @@ int launch_gemm2_bstat(cudaStream_t stream, const void* A, int64_t lda, const vo
   p.tiles_m = (M + kBlockM - 1) / kBlockM;
   p.tiles_n = (N + 255) / 256;
   p.a_slab = a_slab ? 1 : 0;
+#ifdef SVB_GEMM_TRACE
+  p.trace = gemm_trace_ptr();
+#endif
   const int groups = gemm2_groups(M, N, max_ctas);
   if (groups < 1) return -5;
   auto kern = gemm2_bstat_kernel<B_MN, Epi>;

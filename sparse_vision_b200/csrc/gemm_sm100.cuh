@@ -36,6 +36,7 @@ struct GemmProblem {
   int a_prefetch = 0;          // B-stationary schedule: L2-prefetch the A tiles this many steps of the CTA's walk ahead
 #ifdef SVB_GEMM_TRACE
   long long* trace = nullptr;  // bring-up only: [gridDim.x][4] cycles the producer / MMA thread / epilogue spent waiting
+  int a_skip = 0;              // bring-up only (timing, wrong results): load only every a_skip-th A stage from memory
 #endif
 };
 #ifdef SVB_GEMM_TRACE
@@ -238,6 +239,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           SVB_TRACED_WAIT(w_empty, &empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ring + stage * Cfg::kStageBytes;
+#ifdef SVB_GEMM_TRACE
+          if (p.a_skip > 1 && ((t / t_step) * nkb + kb) % p.a_skip != 0) {  // pretend the tile arrived (e.g. by multicast)
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+#endif
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = k_begin + kb * kBlockK;
           if constexpr (!A_MN) {

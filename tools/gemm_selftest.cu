@@ -321,6 +321,29 @@ struct EpiProbe {
         if (lane == 0) { tma_store_2d_hint(&p.tm, slab.base, col0 - 32, ti.m0 + wq * 32, kL2EvictFirst); bulk_commit(); }
       }
     }
+    if (MODE == 14 || MODE == 15) {  // no shared memory at all: packed bf16 straight from registers into the slab-major
+      // layout, every lane writes the 64 bytes of its row with two 32-byte stores (14) or four 16-byte stores (15)
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      const int r = ti.m0 + wq * 32 + lane;
+      if (r < g.M) {
+        char* dst = reinterpret_cast<char*>(p.sink) +
+                    ((static_cast<size_t>(col0 >> 6) * g.M + r) * 64 + (col0 & 63)) * 2;
+        if (MODE == 14) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * h), "r"(w[8 * h]),
+                         "r"(w[8 * h + 1]), "r"(w[8 * h + 2]), "r"(w[8 * h + 3]), "r"(w[8 * h + 4]), "r"(w[8 * h + 5]),
+                         "r"(w[8 * h + 6]), "r"(w[8 * h + 7])
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            *reinterpret_cast<uint4*>(dst + 16 * h) = make_uint4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
+        }
+      }
+    }
     if (MODE == 11) {  // slab-major output [N/64][M][64]: every 32 x 64 slab is 4 KB of contiguous memory
       const int half = (col0 >> 5) & 1;
       if (half == 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
@@ -461,6 +484,7 @@ static void probe_two_cta(const void* dA, const void* dB, void* dE, float* sink,
   memset(&ep, 0, sizeof(ep));
   ep.sink = sink;
   make_store_tmap_bf16(&ep.tm, dE, M, N, N);
+  if (MODE == 11) make_store_tmap_bf16_slab(&ep.tm, dE, M, N);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -474,6 +498,24 @@ static void probe_two_cta(const void* dA, const void* dB, void* dE, float* sink,
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= 10;
   printf("[probe mode %d 2-CTA] %.3f ms  %.1f TFLOP/s\n", MODE, ms, 2.0 * M * N * K / ms * 1e-9);
+  long long* tr;
+  CK(cudaMalloc(&tr, 148 * 4 * sizeof(long long)));
+  CK(cudaMemset(tr, 0, 148 * 4 * sizeof(long long)));
+  gemm_trace_ptr() = tr;
+  launch_gemm2_bstat<false, EpiProbe<MODE, 8>>(0, dA, K, dB, K, M, N, K, ep);
+  CK(cudaDeviceSynchronize());
+  gemm_trace_ptr() = nullptr;
+  long long h[148 * 4];
+  CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int n = 0, nl = 0;
+  for (int b = 0; b < 144; ++b) {
+    s0 += h[b * 4]; s3 += h[b * 4 + 3]; ++n;
+    if ((b & 1) == 0) { s1 += h[b * 4 + 1]; s2 += h[b * 4 + 2]; ++nl; }
+  }
+  printf("    wait kcycles per CTA: producer on free slot %.0f | leader MMA on operands %.0f | leader MMA on free accumulator %.0f | epilogue warp 0 on accumulator %.0f   (kernel ~%.0f kcycles at 1.9 GHz)\n",
+         s0 / n / 1e3, s1 / nl / 1e3, s2 / nl / 1e3, s3 / n / 1e3, ms * 1.9e6 / 1e3);
+  cudaFree(tr);
 }
 
 static int perf_probe() {
@@ -488,15 +530,27 @@ static int perf_probe() {
   CK(cudaMemset(dB, 0x3c, (size_t)N * K * 2));
   probe_two_cta<0>(dA, dB, dE, sink, M, N, K);
   probe_two_cta<2>(dA, dB, dE, sink, M, N, K);
+  probe_two_cta<4>(dA, dB, dE, sink, M, N, K);
+  probe_two_cta<6>(dA, dB, dE, sink, M, N, K);
+  probe_two_cta<11>(dA, dB, dE, sink, M, N, K);
   probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<2, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
-  for (int pf : {2, 4, 8, 16}) {
+  probe_one<14, 8>(dA, dB, dE, (float*)dE, M, N, K);
+  probe_one<15, 8>(dA, dB, dE, (float*)dE, M, N, K);
+  for (int pf : {2, 4}) {
     g_prefetch = pf;
     printf("-- A tiles L2-prefetched %d steps ahead\n", pf);
     probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
   }
   g_prefetch = 0;
+  for (int sk : {2, 4, 8}) {
+    gemm_a_skip() = sk;
+    printf("-- only every %d-th A stage is actually loaded (what a %d-CTA multicast would leave per SM)\n", sk, sk);
+    probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
+    probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
+  }
+  gemm_a_skip() = 0;
   probe_one<12, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<13, 8>(dA, dB, dE, sink, M, N, K);
   return 0;
