@@ -287,7 +287,7 @@ struct EpiProbe {
   static constexpr int kWarps = WARPS;
   static constexpr int kColVecs = 0;
   static constexpr bool kSkipAccLoad = (MODE == 0);
-  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(WARPS);
+  static constexpr uint32_t kSmemBytes = MODE == 16 ? WARPS * 2048 : SlabWriter1::bytes(WARPS);  // 16: per-chunk tiles -> 5 A stages
   const Params& p;
   SlabWriter1 slab;
   float sum;
@@ -343,6 +343,17 @@ struct EpiProbe {
             *reinterpret_cast<uint4*>(dst + 16 * h) = make_uint4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
         }
       }
+    }
+    if (MODE == 16) {  // slab-major output staged per 32-column chunk (2 KB per warp, 64B swizzle): one more A stage fits
+      uint8_t* buf = slab.base - ew * 4096 + ew * 2048;
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      uint8_t* frow = buf + lane * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(frow + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8_bf16(v + 8 * i);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_3d(&p.tm, buf, col0 & 63, ti.m0 + wq * 32, col0 >> 6); bulk_commit(); }
     }
     if (MODE == 11) {  // slab-major output [N/64][M][64]: every 32 x 64 slab is 4 KB of contiguous memory
       const int half = (col0 >> 5) & 1;
@@ -413,7 +424,7 @@ struct EpiProbe {
   }
   __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
   __device__ void finish(int, int lane) {
-    if (MODE == 2 || (MODE >= 5 && MODE != 7 && MODE != 8)) slab.drain(lane);  // (mode 11 included)
+    if (MODE == 2 || (MODE >= 5 && MODE != 7 && MODE != 8 && MODE != 14 && MODE != 15)) slab.drain(lane);  // (modes 11, 16 included)
     if (MODE == 3 && sum == 12345.678f && bits == 77) p.sink[0] = sum;
   }
 };
@@ -425,6 +436,7 @@ static void probe_one(const void* dA, const void* dB, void* dE, float* sink, int
   memset(&ep, 0, sizeof(ep));
   ep.sink = sink;
   make_store_tmap_bf16(&ep.tm, dE, M, N, N);
+  if (MODE == 16) make_store_tmap_bf16_slab32(&ep.tm, dE, M, N);
   if (MODE == 11) {
     cuuint64_t gdim[3] = {64, (cuuint64_t)M, (cuuint64_t)N / 64};
     cuuint64_t gstride[2] = {128, (cuuint64_t)M * 128};
@@ -536,6 +548,7 @@ static int perf_probe() {
   probe_one<0, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<2, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<11, 8>(dA, dB, dE, sink, M, N, K);
+  probe_one<16, 8>(dA, dB, dE, sink, M, N, K);
   probe_one<14, 8>(dA, dB, dE, (float*)dE, M, N, K);
   probe_one<15, 8>(dA, dB, dE, (float*)dE, M, N, K);
   for (int pf : {2, 4}) {
