@@ -13,6 +13,14 @@
 
 namespace svb {
 
+// 1-bit ReLU masks: word w of row r (32 columns each) lives at [(w / 4) * rows + r] * 4 + w % 4, i.e. the four words
+// (128 columns) that one epilogue warp produces for a row are 16 contiguous bytes and the 32 rows of the warp 512
+// contiguous bytes -- full-line stores and loads instead of 16-byte pieces at a pitch of words*4 bytes.  w must be a
+// multiple of 4 here (a warp's first word).  Buffer size: ceil(words / 4) * rows * 4 words.
+__host__ __device__ __forceinline__ size_t mask_index(long long row, int w, long long rows) {
+  return (static_cast<size_t>(w >> 2) * static_cast<size_t>(rows) + static_cast<size_t>(row)) * 4 + (w & 3);
+}
+
 // Element offset of (row, col) in a slab-major [cols/64][rows][64] matrix (see make_tmap_bf16_slab in gemm_host.cuh).
 __host__ __device__ __forceinline__ size_t slab_offset(long long row, int col, long long rows) {
   return (static_cast<size_t>(col >> 6) * static_cast<size_t>(rows) + static_cast<size_t>(row)) * 64 + (col & 63);
@@ -142,6 +150,43 @@ struct SlabWriterT {
 typedef SlabWriterT<1> SlabWriter1;
 typedef SlabWriterT<2> SlabWriter2;
 
+// Per-warp staging of ONE 32-row x 32-column bf16 chunk (2 KB, 64-byte rows, 64B swizzle) that leaves through a TMA
+// tensor store.  Half the shared memory of a slab writer: with the 128 KB resident weight tile of the B-stationary
+// GEMMs that is the difference between a 4-stage and a 5-stage A ring, and ring depth is what those GEMMs are short of
+// (0.193 -> 0.171 ms in the probe).  Tensor maps: make_store_tmap_bf16_chunk (row-major, {col, row})
+// or make_store_tmap_bf16_slab32 (slab-major, {col % 64, row, col / 64}).
+struct ChunkWriter {
+  static constexpr uint32_t kBytesPerWarp = 2048;
+  __host__ __device__ static constexpr uint32_t bytes(int warps) { return warps * kBytesPerWarp; }
+  uint8_t* base;
+  __device__ void init(uint8_t* epi_smem, int ew) { base = epi_smem + ew * kBytesPerWarp; }
+  // this lane's row of the chunk; the store that last used the tile must have finished READING it
+  __device__ __forceinline__ void put(int lane, const float (&v)[32]) {
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+    uint8_t* row = base + lane * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(row + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8_bf16(v + 8 * i);
+  }
+  // bf16 element (r, c) of the staged chunk
+  __device__ __forceinline__ const uint8_t* at(int r, int c) const {
+    return base + r * 64 + ((((c >> 3) ^ ((r >> 1) & 3)) << 4) | ((c & 7) << 1));
+  }
+  __device__ __forceinline__ void flush(const CUtensorMap* tm, int col0, int row0, int lane, int slab_major) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (slab_major) tma_store_3d(tm, base, col0 & 63, row0, col0 >> 6);
+      else tma_store_2d(tm, base, col0, row0);
+      bulk_commit();
+    }
+  }
+  __device__ void drain(int lane) {
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ fp32 partials
 // Split-K slices of the weight-gradient GEMMs: out[split][row][col] = acc (fp32, direct 16-byte stores; the
 // epilogue is a negligible part of these K = T GEMMs, so no staging and a full 4-stage operand ring).
@@ -241,12 +286,12 @@ struct EpiStore {
 template <bool API>
 struct EpiEncT {
   struct Params {
-    alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], box 64 x 32 (valid when e_bf16 != null)
+    alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], 32 x 32 chunks (make_store_tmap_bf16_chunk / _slab32; valid when e_bf16 != null)
     const float* bias;             // [N]
     __nv_bfloat16* e_bf16;         // [M,N] or null
     float* e_f32;                  // [M,N] or null   (API only)
     float* pre_f32;                // [M,N] or null   (API only)
-    uint32_t* mask_words;          // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
+    uint32_t* mask_words;          // group-major (mask_index) or null: bit j of word w <=> e[row, 32w+j] > 0
     uint32_t* act_bits;            // [n_img, words] or null
     float* l1_partial;             // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
     int hw;                        // tokens per image (1 for 2-D inputs)
@@ -256,9 +301,9 @@ struct EpiEncT {
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
   static constexpr bool kPrefetchAcc = true;
-  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps) + 2 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = ChunkWriter::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
-  SlabWriter1 slab;
+  ChunkWriter slab;
   ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
@@ -266,7 +311,7 @@ struct EpiEncT {
   uint32_t words[4];
   int ew, cpw, c_first;  // chunks per warp, this warp's first 32-column chunk inside the tile
   __device__ EpiEncT(const Params& p_, uint8_t* smem, int ew_, int block_n)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + SlabWriter1::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + ChunkWriter::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
         cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
     slab.init(smem, ew_);
   }
@@ -321,22 +366,19 @@ struct EpiEncT {
     if (!row_ok) word = 0;
     words[ci] = word;
     if (p.e_bf16) {
-      const int half = ci & 1;
-      slab.put(half, lane, v);
-      if (half == 1) slab.flush(&p.tm_e, col0 - 32, ti.m0 + wq * 32, lane, p.e_slab);
+      slab.put(lane, v);
+      slab.flush(&p.tm_e, col0, ti.m0 + wq * 32, lane, p.e_slab);
     }
     if (API && p.e_f32 && row_ok) store_row_f32(p.e_f32 + off, v, nvalid);
   }
   __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int row, int wq, int lane) {
-    if (slab.half_pending) slab.flush(&p.tm_e, ((g.N - 1) >> 6) << 6, ti.m0 + wq * 32, lane, p.e_slab);
     const int w0 = (ti.n0 >> 5) + c_first;            // first word index of this warp
     const int nw = max(0, min(cpw, p.words - w0));
     if (p.mask_words && row < g.M && nw > 0) {
-      uint32_t* dst = p.mask_words + static_cast<size_t>(row) * p.words + w0;
-      if (nw == 4 && (p.words & 3) == 0) {
+      // group-major layout [ceil(words/4)][M][4]: the 32 rows of a warp are 512 contiguous bytes (see mask_index)
+      uint32_t* dst = p.mask_words + mask_index(row, w0, g.M);
+      if (nw == 4) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-      } else if (nw == 2 && (p.words & 1) == 0) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2(words[0], words[1]);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -669,7 +711,7 @@ template <int CS>
 struct EpiDPreT {
   struct Params {
     alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
-    const uint32_t* mask_words;        // [M, words]
+    const uint32_t* mask_words;        // group-major 1-bit ReLU masks of the encoder (mask_index)
     float* colsum_partial;             // CS = 1: [slots * 4, N] with slot = TileInfo::cta_slot;
                                        // CS = 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens
     float l1c;
@@ -699,13 +741,10 @@ struct EpiDPreT {
     const int w0 = (ti.n0 >> 5) + c_first;
     const int nw = max(0, min(cpw, p.words - w0));
     if (row < g.M && nw > 0) {
-      const uint32_t* src = p.mask_words + static_cast<size_t>(row) * p.words + w0;
-      if (nw == 4 && (p.words & 3) == 0) {
+      const uint32_t* src = p.mask_words + mask_index(row, w0, g.M);
+      if (nw == 4) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
         words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
-      } else if (nw == 2 && (p.words & 1) == 0) {
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
-        words[0] = a.x; words[1] = a.y;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)

@@ -85,6 +85,20 @@ inline int make_store_tmap_bf16_slab(CUtensorMap* out, void* ptr, uint64_t rows,
   return make_tmap_bf16_slab(out, ptr, rows, cols, 32);
 }
 
+// Row-major bf16 output written in 32-row x 32-column chunks (2 KB staging tiles, 64B swizzle); coordinates {col, row}.
+inline int make_store_tmap_bf16_chunk(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  auto fn = tmap_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return -2;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
 // Slab-major store map for 32-column x 32-row chunks (2 KB staging tiles, 64B swizzle): coordinates {col % 64, row, col / 64}.
 inline int make_store_tmap_bf16_slab32(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols) {
   auto fn = tmap_encode_fn();

@@ -70,7 +70,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   if (!train) return;
   p.DP = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
-  p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
+  p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * 4 * cdiv(p.words, 4));   // group-major, see mask_index
   // cleared by the step prologue: activity bits and the per-(CTA, warp) loss partials (contiguous on purpose)
   const size_t z0 = a.off;
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
@@ -153,7 +153,7 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
   e1.pre_f32 = out->pre;
   e1.hw = pl.hw; e1.words = pl.words;
-  if (make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
+  if (make_store_tmap_bf16_chunk(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
   SVB_GEMM((launch_gemm<256, false, false, EpiEncApi>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
   if (out->dec) {
     EpiDec::Params e2{};
@@ -203,7 +203,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
   e1.mask_words = pl.mask;
   e1.hw = pl.hw; e1.words = pl.words; e1.e_slab = pl.es;
-  if (pl.es ? make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F))
+  if (pl.es ? make_store_tmap_bf16_slab32(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16_chunk(&e1.tm_e, pl.E, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for E");
   if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary)");

@@ -256,7 +256,7 @@ static int perf_enc_variants() {
     EpiEnc::Params ep;
     memset(&ep, 0, sizeof(ep));
     ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.hw = HW; ep.words = words;
-    make_store_tmap_bf16(&ep.tm_e, dE, M, N, N);
+    make_store_tmap_bf16_chunk(&ep.tm_e, dE, M, N, N);
     if (variant == 1 || variant == 4) ep.act_bits = dact;
     if (variant == 2 || variant == 4) ep.mask_words = dmask;
     if (variant == 3 || variant == 4) ep.l1_partial = dl1;
