@@ -628,6 +628,30 @@ static __global__ void row_variance_kernel(const bf16* __restrict__ x, const bf1
 }
 
 // ------------------------------------------------------------------------------------------------ activity
+// Per-image activity bits (utils.py:2033-2047: a unit is active for an image iff any of its pixels is non-zero) from
+// the encoder's group-major 1-bit masks (epilogues.cuh: mask_index): bits[b][4*wg + i] = OR over the image's rows of
+// word i of group wg.  One coalesced pass over the 26 MB mask on the side stream replaces ~400 k global atomics and
+// the warp-wide ORs in the encoder epilogue (which cost that GEMM 0.025 ms).  grid (n_img, word groups), 128 threads.
+static __global__ void __launch_bounds__(128)
+mask_to_activity_kernel(const uint32_t* __restrict__ mask, uint32_t* __restrict__ bits, long long T, int hw, int words) {
+  __shared__ uint32_t sh[4][4];
+  const int b = blockIdx.x, wg = blockIdx.y;
+  const uint4* src = reinterpret_cast<const uint4*>(mask) + static_cast<size_t>(wg) * T + static_cast<size_t>(b) * hw;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (int r = threadIdx.x; r < hw; r += 128) {
+    const uint4 v = __ldg(src + r);
+    acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  acc.x = __reduce_or_sync(0xffffffffu, acc.x); acc.y = __reduce_or_sync(0xffffffffu, acc.y);
+  acc.z = __reduce_or_sync(0xffffffffu, acc.z); acc.w = __reduce_or_sync(0xffffffffu, acc.w);
+  if (lane == 0) { sh[w][0] = acc.x; sh[w][1] = acc.y; sh[w][2] = acc.z; sh[w][3] = acc.w; }
+  __syncthreads();
+  if (threadIdx.x < 4 && wg * 4 + static_cast<int>(threadIdx.x) < words)
+    bits[static_cast<size_t>(b) * words + wg * 4 + threadIdx.x] =
+        (sh[0][threadIdx.x] | sh[1][threadIdx.x]) | (sh[2][threadIdx.x] | sh[3][threadIdx.x]);
+}
+
 // act_bits [n_img, words] -> count[f] (#images in which unit f fired), n_active[b] (#units fired in image b).
 // utils.py:2047-2067.  grid.x over words (32 features each), 256 threads = 8 image lanes x 32 bit lanes.
 static __global__ void activity_count_kernel(const uint32_t* __restrict__ bits, int n_img, int words, int F,

@@ -200,8 +200,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   prof_mark(h, st, 1);
   // G1 encoder
   EpiEnc::Params e1{};
-  e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
-  e1.mask_words = pl.mask;
+  e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.l1_partial = pl.l1_part;
+  e1.mask_words = pl.mask;   // the per-image activity bits are derived from the masks below, not in the epilogue
   e1.hw = pl.hw; e1.words = pl.words; e1.e_slab = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab32(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16_chunk(&e1.tm_e, pl.E, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for E");
@@ -211,6 +211,11 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");
   }
   prof_mark(h, st, 2);
+  // per-image activity bits from the masks: side stream, beside the decoder GEMM (joined before the assembly)
+  SVB_TRY(side_fork(h, st));
+  (mask_to_activity_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(pl.words, 4)), 128, 0, h->side>>>(
+      pl.mask, pl.act_bits, pl.T, pl.hw, pl.words), svb::count_launch());
+  SVB_LAUNCH_CHECK("mask_to_activity");
   // G2 decoder
   if (pl.fused_dec) {
     EpiDecNchw::Params e2{};
