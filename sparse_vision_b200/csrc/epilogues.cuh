@@ -702,15 +702,16 @@ struct EpiDecNchw {
 // of sparse_loss.py:35,41 through sae_mlp.py:51).  The ReLU mask comes from the encoder's 1-bit activity words
 // (8 B per row and warp instead of re-reading 128 B of e).  Fused: bf16 store of dPre' (TMA slabs), per-feature
 // column sums (-> db_enc).
-// Column sums over tokens (-> db_enc) are read back from the finished 32 x 64 bf16 slab in shared memory: lane l owns
-// columns 2l, 2l+1 of the slab, adds the rows 8 at a time as packed bf16 pairs (HADD2) and accumulates the four
-// groups in fp32 -- about one instruction per element instead of four for a 31-step shuffle transpose.
+// Column sums over tokens (-> db_enc) are read back from the staged 32 x 32 bf16 chunk in shared memory: the two
+// half-warps take the even / odd rows, lane l % 16 owns columns 2l, 2l+1, adds its 16 rows 8 at a time as packed
+// bf16 pairs (HADD2) and the two groups and the two halves in fp32 -- about one instruction per element instead of four
+// for a 31-step shuffle transpose.
 // CS = 0: one partial row per (M tile, lane quarter).  CS = 1 (B-stationary launches: a CTA keeps ONE N tile): the
 // sums are carried in registers over all M tiles of the CTA and written once.  CS = 2: no column sums.
 template <int CS>
 struct EpiDPreT {
   struct Params {
-    alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N]
+    alignas(64) CUtensorMap tm_dpre;   // bf16 dPre' [M,N], 32 x 32 chunks (make_store_tmap_bf16_chunk / _slab32)
     const uint32_t* mask_words;        // group-major 1-bit ReLU masks of the encoder (mask_index)
     float* colsum_partial;             // CS = 1: [slots * 4, N] with slot = TileInfo::cta_slot;
                                        // CS = 0: [tiles_m * 4 lane quarters, N], one row per 32 tokens
@@ -720,18 +721,18 @@ struct EpiDPreT {
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 0;
-  static constexpr uint32_t kSmemBytes = SlabWriter1::bytes(kWarps);
+  static constexpr uint32_t kSmemBytes = ChunkWriter::bytes(kWarps);
   const Params& p;
-  SlabWriter1 slab;
+  ChunkWriter slab;
   uint32_t words[4];
-  float2 csacc[2];  // CS = 1: running sums of this lane's two columns, per slab of the warp
+  float2 csacc[4];  // CS = 1: running sums of this lane's two columns, per chunk of the warp
   int ew, cpw, c_first, n0_last, slot_last, N_last;
   __device__ EpiDPreT(const Params& p_, uint8_t* smem, int ew_, int block_n_)
       : p(p_), ew(ew_), cpw((block_n_ / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n_ / 32) / (kWarps / 4))),
         n0_last(-1), slot_last(0), N_last(0) {
     slab.init(smem, ew_);
-    csacc[0] = make_float2(0.f, 0.f);
-    csacc[1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csacc[i] = make_float2(0.f, 0.f);
   }
   __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
   __device__ void colvec_commit(uint32_t, int) {}
@@ -752,71 +753,58 @@ struct EpiDPreT {
       }
     }
   }
-  // Sum of the slab's 32 rows for this lane's column pair (2*lane, 2*lane+1); the slab must be completely written.
-  __device__ __forceinline__ float2 slab_colsum(int lane) const {
-    float2 s = make_float2(0.f, 0.f);  // this lane reads 16-byte piece lane/4, word lane%4 of every row
+  // Sum of the staged chunk's 32 rows for columns 2*(lane%16), +1 (every lane of a pair l, l+16 gets the total).
+  __device__ __forceinline__ float2 chunk_colsum(int lane) const {
+    const int cp = lane & 15, par = lane >> 4;  // column pair, row parity of this half-warp
+    float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
+    for (int g8 = 0; g8 < 2; ++g8) {
       __nv_bfloat162 acc;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {  // row 8*g8 + r: its pieces are XOR-swizzled with r
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(
-            slab.base + (g8 * 8 + r) * 128 + ((((lane >> 2) ^ r) << 4) | ((lane & 3) << 2)));
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(slab.at(2 * (g8 * 8 + i) + par, 2 * cp));
         const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
-        acc = r == 0 ? h : __hadd2(acc, h);
+        acc = i == 0 ? h : __hadd2(acc, h);
       }
       const uint32_t aw = *reinterpret_cast<const uint32_t*>(&acc);
       s.x += bf16lo(aw);
       s.y += bf16hi(aw);
     }
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, 16);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
     return s;
-  }
-  __device__ __forceinline__ void slab_done(const GemmProblem& g, const TileInfo& ti, int col_slab0, int wq, int lane,
-                                            int si) {
-    if (CS == 2) return;
-    __syncwarp();  // every lane's row of the slab is in shared memory
-    const float2 cs = slab_colsum(lane);
-    if (CS == 1) {
-      csacc[si].x += cs.x;
-      csacc[si].y += cs.y;
-    } else {
-      const int col = col_slab0 + 2 * lane;  // N % 8 == 0: a column pair is inside or outside together
-      if (col < g.N)
-        *reinterpret_cast<float2*>(p.colsum_partial + (static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col) = cs;
-    }
   }
   __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int, int col0, float (&v)[32], int wq,
                                         int lane, int ci) {
     const uint32_t word = words[ci];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (word & (1u << j)) ? v[j] + p.l1c : 0.f;
-    const int half = ci & 1;
-    slab.put(half, lane, v);
-    if (half == 1) {
-      slab_done(g, ti, col0 - 32, wq, lane, ci >> 1);
-      slab.flush(&p.tm_dpre, col0 - 32, ti.m0 + wq * 32, lane, p.out_slab);
+    slab.put(lane, v);
+    if (CS != 2) {
+      __syncwarp();  // every lane's row of the chunk is in shared memory
+      const float2 cs = chunk_colsum(lane);
+      if (CS == 1) {
+        csacc[ci].x += cs.x;
+        csacc[ci].y += cs.y;
+      } else {
+        const int col = col0 + 2 * (lane & 15);  // N % 8 == 0: a column pair is inside or outside together
+        if (lane < 16 && col < g.N)
+          *reinterpret_cast<float2*>(p.colsum_partial + (static_cast<size_t>(ti.tile_m) * 4 + wq) * g.N + col) = cs;
+      }
     }
+    slab.flush(&p.tm_dpre, col0, ti.m0 + wq * 32, lane, p.out_slab);
   }
-  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int wq, int lane) {
-    if (slab.half_pending) {  // N tail: the slab's second half was never written for this tile -> clear it first
-      float z[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) z[j] = 0.f;
-      slab.put(1, lane, z);
-      const int col_slab0 = ((g.N - 1) >> 6) << 6;
-      slab_done(g, ti, col_slab0, wq, lane, ((col_slab0 - ti.n0) >> 6) & 1);
-      slab.flush(&p.tm_dpre, col_slab0, ti.m0 + wq * 32, lane, p.out_slab);
-    }
+  __device__ void end_tile(const GemmProblem& g, const TileInfo& ti, int, int, int) {
     n0_last = ti.n0; slot_last = ti.cta_slot; N_last = g.N;
   }
   __device__ void finish(int wq, int lane) {
     slab.drain(lane);
-    if (CS == 1 && n0_last >= 0) {
+    if (CS == 1 && n0_last >= 0 && lane < 16) {
       const size_t rowp = static_cast<size_t>(slot_last) * 4 + wq;
 #pragma unroll
-      for (int si = 0; si < 2; ++si) {
-        const int col = n0_last + c_first * 32 + si * 64 + 2 * lane;
-        if (col < N_last) *reinterpret_cast<float2*>(p.colsum_partial + rowp * N_last + col) = csacc[si];
+      for (int ci = 0; ci < 4; ++ci) {
+        const int col = n0_last + (c_first + ci) * 32 + 2 * lane;
+        if (ci < cpw && col < N_last) *reinterpret_cast<float2*>(p.colsum_partial + rowp * N_last + col) = csacc[ci];
       }
     }
   }

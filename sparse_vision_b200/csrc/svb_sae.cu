@@ -249,13 +249,13 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   if (pl.bstat) {
     EpiDPreCta::Params e3{};
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
-    if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F))
+    if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
     SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "dE (B-stationary)");
   } else {
     EpiDPre::Params e3{};
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
-    if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16(&e3.tm_dpre, pl.DP, T, F, F))
+    if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
     SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
   }

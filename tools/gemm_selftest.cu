@@ -656,7 +656,7 @@ static void perf_de_one(const char* name, const void* dA, const void* dB, void* 
   typename Epi::Params ep;
   memset(&ep, 0, sizeof(ep));
   ep.mask_words = mask; ep.words = N / 32; ep.colsum_partial = cs; ep.l1c = 0.5f;
-  make_store_tmap_bf16(&ep.tm_dpre, dE, M, N, N);
+  make_store_tmap_bf16_chunk(&ep.tm_dpre, dE, M, N, N);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
