@@ -214,6 +214,39 @@ struct EpiPartial {
   __device__ void finish(int, int) {}
 };
 
+// Split-K partials plus the row sums of A over this split's K range (kOnesCol, see gemm_sm100.cuh):
+// row_out[split][row] = sum_k A[row, k].  In the dW_enc GEMM A = dPre'^T, so these are the per-feature column sums of
+// dPre' (-> db_enc and the rank-1 fix-up) at the price of one N = 16 MMA per k-step -- the dE epilogue, which is the
+// one that has no cycles to spare, computes none.
+struct EpiPartialOnes {
+  struct Params {
+    float* out;
+    long long ld;
+    long long split_stride;
+    float* row_out;  // [k_splits][M]
+  };
+  static constexpr int kWarps = 8;
+  static constexpr int kColVecs = 0;
+  static constexpr bool kOnesCol = true;
+  static constexpr uint32_t kSmemBytes = 2048;  // the constant ones tile
+  const Params& p;
+  __device__ EpiPartialOnes(const Params& p_, uint8_t*, int, int) : p(p_) {}
+  __device__ void colvec_fetch(const GemmProblem&, const TileInfo&, int) {}
+  __device__ void colvec_commit(uint32_t, int) {}
+  __device__ void begin_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const GemmProblem& g, const TileInfo& ti, int row, int col0, float (&v)[32],
+                                        int, int, int) {
+    if (row >= g.M) return;
+    store_row_f32(p.out + ti.split * p.split_stride + static_cast<long long>(row) * p.ld + col0, v,
+                  min(32, g.N - col0));
+  }
+  __device__ void row_sum(const GemmProblem& g, const TileInfo& ti, int row, float v) {
+    if (row < g.M) p.row_out[static_cast<size_t>(ti.split) * g.M + row] = v;
+  }
+  __device__ void end_tile(const GemmProblem&, const TileInfo&, int, int, int) {}
+  __device__ void finish(int, int) {}
+};
+
 // ------------------------------------------------------------------------------------------------ plain store
 // out = [relu](alpha*acc + bias), fp32 (direct) or bf16 (TMA slabs when tm_valid).
 struct EpiStore {

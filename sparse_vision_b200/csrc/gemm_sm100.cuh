@@ -110,6 +110,12 @@ struct ColVecStage {
 // Epilogues may define `static constexpr bool kSkipAccLoad = true` (bring-up probes only) to skip the TMEM read.
 template <class E, class = void> struct epi_skips_acc_load { static constexpr bool value = false; };
 template <class E> struct epi_skips_acc_load<E, decltype(void(E::kSkipAccLoad))> { static constexpr bool value = E::kSkipAccLoad; };
+// Epilogues may define `static constexpr bool kOnesCol = true`: besides D = A B^T the kernel accumulates the ROW SUMS
+// of A over K (A times a column of ones, one extra N = 16 MMA per k-step on a constant shared-memory tile) into TMEM
+// column BLOCK_N and hands them to Epi::row_sum().  The accumulator is then single-buffered (the second half of TMEM
+// holds the extra column), which is free for the split-K weight-gradient GEMMs: every CTA computes one tile.
+template <class E, class = void> struct epi_ones_col { static constexpr bool value = false; };
+template <class E> struct epi_ones_col<E, decltype(void(E::kOnesCol))> { static constexpr bool value = E::kOnesCol; };
 // Epilogues may define `static constexpr bool kPrefetchAcc = true` to double-buffer the TMEM reads in registers.
 template <class E, class = void> struct epi_prefetches_acc { static constexpr bool value = false; };
 template <class E> struct epi_prefetches_acc<E, decltype(void(E::kPrefetchAcc))> { static constexpr bool value = E::kPrefetchAcc; };
@@ -167,6 +173,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(b_full_bar, 1);
     fence_barrier_init();
+  }
+  constexpr bool ONES = epi_ones_col<Epi>::value;
+  if constexpr (ONES) {  // 16 rows x 128 B of bf16 1.0 at the start of the epilogue staging area (any swizzle of ones is ones)
+    static_assert(Epi::kSmemBytes >= 2048, "the ones tile lives in the epilogue staging area");
+    if (warp >= 2 && threadIdx.x - 64 < 128) {
+      reinterpret_cast<uint4*>(epi_smem)[threadIdx.x - 64] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      fence_proxy_async_smem();
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -300,13 +314,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
                                         : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
             umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (ONES) {  // row sums of A: the same A descriptor against the constant ones tile (N = 16)
+              constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, 16, A_MN, false);
+              umma_f16(tmem_base + BLOCK_N, adesc, make_smem_desc_sw128(smem_u32(epi_smem), 16, 1024), idesc1,
+                       (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
           if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if constexpr (ONES) {
+          acc_phase ^= 1;  // single accumulator stage
+        } else {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
       }
 #ifdef SVB_GEMM_TRACE
       if (p.trace) { p.trace[blockIdx.x * 4 + 1] = w_full; p.trace[blockIdx.x * 4 + 2] = w_tmem; }
@@ -372,12 +395,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if constexpr (ONES) {
+        if (cgroup == 0) {  // one warp per lane quarter reads the extra column
+          const float rs = tmem_ld_32x1(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + BLOCK_N);
+          tmem_ld_wait();
+          epi.row_sum(p, ti, row, rs);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);  // accumulator stage free for the MMA warp
       epi.end_tile(p, ti, row, wq, lane);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if constexpr (ONES) {
+        acc_phase ^= 1;
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
     epi.finish(wq, lane);  // e.g. drain outstanding bulk stores before the CTA's smem goes away
 #ifdef SVB_GEMM_TRACE

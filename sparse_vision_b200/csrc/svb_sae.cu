@@ -78,8 +78,6 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
   p.zero_words = (a.off - z0) / 4;
   p.bstat = p.C <= 256 && p.tn_f <= sms;
-  p.cs_rows = p.bstat ? 4 * bstat_groups(sms, p.tn_f, p.tiles_m) : 4 * p.tiles_m;
-  p.colsum_part = a.take<float>(static_cast<size_t>(p.cs_rows) * F);
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
   p.csum = a.take<float>(F);
   p.st = a.take<float>(stats_elems(p.n_img, p.hw, p.T, p.C));
@@ -88,6 +86,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
   p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
   p.s_we = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  p.cs_rows = p.s_we;   // per-feature column sums of dPre': one row per split of the dW_enc GEMM (EpiPartialOnes)
+  p.colsum_part = a.take<float>(static_cast<size_t>(p.cs_rows) * F);
   p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
   p.P_we = a.take<float>(static_cast<size_t>(p.s_we) * FC);
   p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
@@ -247,17 +247,17 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // G3 dE -> dPre'
   const float l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
   if (pl.bstat) {
-    EpiDPreCta::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
+    EpiDPreNoSum::Params e3{};
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
     if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreCta, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "dE (B-stationary)");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "dE (B-stationary)");
   } else {
-    EpiDPre::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = pl.colsum_part; e3.l1c = l1c; e3.out_slab = pl.es;
+    EpiDPreNoSum::Params e3{};
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
     if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
   }
   prof_mark(h, st, 5);
   // Weight gradients, split-K over tokens.  The encoder side goes first: with its assembly done, the leading part of
@@ -265,8 +265,9 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   const size_t FC = static_cast<size_t>(F) * C;
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
-  EpiPartial::Params e5{pl.P_we, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
+  // (its extra ones column yields the per-feature column sums of dPre' that db_enc and the rank-1 fix-up need)
+  EpiPartialOnes::Params e5{pl.P_we, C, static_cast<long long>(FC), pl.colsum_part};
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartialOnes>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
   // column-sum reduction + encoder-side assembly on the side stream, beside the dW_dec GEMM
   SVB_TRY(side_fork(h, st));
   SVB_TRY(reduce_rows(h->side, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));

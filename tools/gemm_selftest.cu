@@ -42,6 +42,7 @@ struct Case {
   bool bf16_out = false;  // bf16 output through the TMA slab store (K must keep |sums| <= 256 so bf16 is exact)
   bool bstat = false;     // B-stationary schedule (K <= 256)
   bool two_cta = false;   // cta_group::2 B-stationary kernel (gemm2_sm100.cuh)
+  bool ones = false;      // EpiPartialOnes: also check the row sums of A from the extra ones column
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -57,6 +58,7 @@ static int run(const Case& c) {
     for (int k = 0; k < c.K; ++k) Bh[BMN ? (size_t)k * c.N + n : (size_t)n * c.K + k] = f2bf(B[(size_t)n * c.K + k]);
   void *dA, *dB;
   float* dC;
+  float* dRow = nullptr;
   CK(cudaMalloc(&dA, Ah.size() * 2));
   CK(cudaMalloc(&dB, Bh.size() * 2));
   CK(cudaMemcpy(dA, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice));
@@ -79,6 +81,14 @@ static int run(const Case& c) {
     } else if (c.bstat) rc = launch_gemm<BN, AMN, BMN, EpiStore, true>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
     else rc = launch_gemm<BN, AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
    } else { printf("[%s] bf16 slab output needs BLOCK_N=256\n", c.name); return 1; }
+  } else if (c.ones) {
+   if constexpr (BN == 256) {
+    CK(cudaMalloc(&dRow, (size_t)splits * c.M * 4));
+    CK(cudaMemset(dRow, 0xFF, (size_t)splits * c.M * 4));
+    EpiPartialOnes::Params ep{dC, c.N, (long long)c.M * c.N, dRow};
+    rc = launch_gemm<BN, AMN, BMN, EpiPartialOnes>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
+                                                   &used);
+   } else { printf("[%s] the ones column needs BLOCK_N=256\n", c.name); return 1; }
   } else {
     EpiPartial::Params ep{dC, c.N, (long long)c.M * c.N};
     rc = launch_gemm<BN, AMN, BMN, EpiPartial>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
@@ -113,6 +123,20 @@ static int run(const Case& c) {
       }
       if (err > maxerr) maxerr = err;
     }
+  if (dRow) {
+    std::vector<float> R((size_t)used * c.M);
+    CK(cudaMemcpy(R.data(), dRow, R.size() * 4, cudaMemcpyDeviceToHost));
+    for (int m = 0; m < c.M; ++m) {
+      double ref = 0, got = 0;
+      for (int k = 0; k < c.K; ++k) ref += A[(size_t)m * c.K + k];
+      for (int s = 0; s < used; ++s) got += R[(size_t)s * c.M + m];
+      if (!(fabs(got - ref) <= 1e-3)) {
+        if (bad < 8) printf("  row-sum mismatch m=%d got=%f ref=%f\n", m, got, ref);
+        ++bad;
+      }
+    }
+    cudaFree(dRow);
+  }
   printf("[%s] M=%d N=%d K=%d aMN=%d bMN=%d BN=%d splits=%d : %s (bad=%lld maxerr=%g)\n", c.name, c.M, c.N, c.K, AMN,
          BMN, BN, used, bad ? "FAIL" : "PASS", bad, maxerr);
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
@@ -159,6 +183,9 @@ static const Case kCases[] = {
     {"kk_2cta_k24_ntail", 5000, 200, 24, false, false, 256, 1, true, true, true},
     {"kmn_2cta", 3000, 768, 16, false, true, 256, 1, true, true, true},
     {"kk_2cta_mtail_odd", 128 * 7 + 3, 256, 16, false, false, 256, 1, true, true, true},
+    {"mnmn_ones_splitk", 256, 512, 3000, true, true, 256, 3, false, false, false, true},
+    {"mnmn_ones_auto_tail", 200, 264, 1000, true, true, 256, 0, false, false, false, true},
+    {"kk_ones", 300, 256, 192, false, false, 256, 1, false, false, false, true},
 };
 
 static int perf() {
