@@ -312,9 +312,9 @@ struct EpiStore {
 
 // ------------------------------------------------------------------------------------------------ encoder
 // pre = acc + bias';  e = relu(pre)   (sae_mlp.py:49-51 with the pre-bias folded: bias' = b_enc - W_enc b_dec)
-// Fused: bf16 store of e (TMA slabs), optional fp32 stores of e / pre (API forward), per-row activity words
-// (1 bit per element: the ReLU mask the backward needs), per-image activity bits (utils.py:2033-2047) and sum|e|
-// partials (sparse_loss.py:41).  All generic-proxy global writes happen once per tile in end_tile.
+// Fused: bf16 store of e (TMA chunks), optional fp32 stores of e / pre (API forward), per-row mask words (1 bit per
+// element: the ReLU mask the backward needs, and what the per-image activity bits of utils.py:2033-2047 are derived
+// from by mask_to_activity_kernel) and sum|e| partials (sparse_loss.py:41).
 // API = true additionally offers fp32 stores of e / pre (svb_sae_forward); the training step instantiates API = false.
 template <bool API>
 struct EpiEncT {
@@ -325,9 +325,7 @@ struct EpiEncT {
     float* e_f32;                  // [M,N] or null   (API only)
     float* pre_f32;                // [M,N] or null   (API only)
     uint32_t* mask_words;          // group-major (mask_index) or null: bit j of word w <=> e[row, 32w+j] > 0
-    uint32_t* act_bits;            // [n_img, words] or null
     float* l1_partial;             // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
-    int hw;                        // tokens per image (1 for 2-D inputs)
     int words;                     // ceil(N/32)
     int e_slab;                    // e_bf16 / tm_e are slab-major (gemm_host.cuh)
   };
@@ -416,26 +414,6 @@ struct EpiEncT {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (i < nw) dst[i] = words[i];
-      }
-    }
-    if (p.act_bits && nw > 0) {
-      // OR the rows of each image this warp touches; lanes 0..nw-1 publish one word each (one RED per segment)
-      const int row0 = ti.m0 + wq * 32;
-      const int last_row = min(row0 + 31, g.M - 1);
-      if (row0 <= last_row) {
-        const int b_first = row0 / p.hw, b_last = last_row / p.hw;
-        const int my_b = row < g.M ? row / p.hw : -1;
-        for (int b = b_first; b <= b_last; ++b) {
-          uint32_t mine = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < cpw) {
-              const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? words[i] : 0u);
-              if (lane == i) mine = ored;
-            }
-          }
-          if (lane < nw && mine) atomicOr(&p.act_bits[static_cast<size_t>(b) * p.words + w0 + lane], mine);
-        }
       }
     }
     if (row < g.M) total += sum;  // rows >= M hold relu(bias'), not data

@@ -25,11 +25,11 @@ struct EpiGatedEnc {
     float* e_f32;
     __nv_bfloat16* rp_bf16;
     float* rp_f32;
-    uint32_t* mask_e;     // [M, words] or null: bit j of word w <=> e[row, 32w+j] > 0
-    uint32_t* mask_rp;    // [M, words] or null: relu_pi > 0
-    uint32_t* act_bits;
+    uint32_t* mask_e;     // group-major (mask_index) or null: bit j of word w <=> e[row, 32w+j] > 0; the per-image
+                          // activity bits (utils.py:2033-2047) are derived from it by mask_to_activity_kernel
+    uint32_t* mask_rp;    // group-major or null: relu_pi > 0
     float* l1_partial;    // [gridDim.x * kWarps] or null: one running sum per CTA and epilogue warp
-    int hw, words;
+    int words;
     int tma;              // 1: e_bf16 / rp_bf16 leave through the TMA maps; slab_major: those maps are slab-major
     int slab_major;
   };
@@ -135,30 +135,17 @@ struct EpiGatedEnc {
     const int w0 = (ti.n0 >> 5) + c_first;
     const int nw = max(0, min(cpw, p.words - w0));
     if (row < g.M && nw > 0) {
+      const size_t mi = mask_index(row, w0, g.M);
+      if (nw == 4) {
+        if (p.mask_e) *reinterpret_cast<uint4*>(p.mask_e + mi) = make_uint4(we[0], we[1], we[2], we[3]);
+        if (p.mask_rp) *reinterpret_cast<uint4*>(p.mask_rp + mi) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < nw) {
-          if (p.mask_e) p.mask_e[static_cast<size_t>(row) * p.words + w0 + i] = we[i];
-          if (p.mask_rp) p.mask_rp[static_cast<size_t>(row) * p.words + w0 + i] = wr[i];
-        }
-      }
-    }
-    if (p.act_bits && nw > 0) {
-      const int row0 = ti.m0 + wq * 32;
-      const int last_row = min(row0 + 31, g.M - 1);
-      if (row0 <= last_row) {
-        const int b_first = row0 / p.hw, b_last = last_row / p.hw;
-        const int my_b = row < g.M ? row / p.hw : -1;
-        for (int b = b_first; b <= b_last; ++b) {
-          uint32_t mine = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < cpw) {
-              const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? we[i] : 0u);
-              if (lane == i) mine = ored;
-            }
+        for (int i = 0; i < 4; ++i) {
+          if (i < nw) {
+            if (p.mask_e) p.mask_e[mi + i] = we[i];
+            if (p.mask_rp) p.mask_rp[mi + i] = wr[i];
           }
-          if (lane < nw && mine) atomicOr(&p.act_bits[static_cast<size_t>(b) * p.words + w0 + lane], mine);
         }
       }
     }
@@ -184,8 +171,8 @@ struct EpiGatedEnc {
 struct EpiGatedDPre {
   struct Params {
     alignas(64) CUtensorMap tm_a;  // bf16 A' [M,N]
-    const uint32_t* mask_e;        // [M, words]
-    const uint32_t* mask_rp;       // [M, words]
+    const uint32_t* mask_e;        // group-major 1-bit masks of the encoder (mask_index)
+    const uint32_t* mask_rp;
     const float* exp_r;            // [N]
     float* colsum_mag;             // [tiles_m, N]
     float* colsum_a;               // [tiles_m, N]
@@ -225,10 +212,19 @@ struct EpiGatedDPre {
     const int w0 = (ti.n0 >> 5) + c_first;
     const int nw = max(0, min(cpw, p.words - w0));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool ok = row < g.M && i < nw;
-      we[i] = ok ? __ldg(p.mask_e + static_cast<size_t>(row) * p.words + w0 + i) : 0u;
-      wr[i] = ok ? __ldg(p.mask_rp + static_cast<size_t>(row) * p.words + w0 + i) : 0u;
+    for (int i = 0; i < 4; ++i) { we[i] = 0; wr[i] = 0; }
+    if (row < g.M && nw > 0) {
+      const size_t mi = mask_index(row, w0, g.M);
+      if (nw == 4) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.mask_e + mi));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.mask_rp + mi));
+        we[0] = a.x; we[1] = a.y; we[2] = a.z; we[3] = a.w;
+        wr[0] = b.x; wr[1] = b.y; wr[2] = b.z; wr[3] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nw) { we[i] = __ldg(p.mask_e + mi + i); wr[i] = __ldg(p.mask_rp + mi + i); }
+      }
     }
   }
   // column sums of a finished slab for this lane's column pair (same access pattern as EpiDPreT::slab_colsum)

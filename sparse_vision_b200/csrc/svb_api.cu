@@ -322,7 +322,7 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   SVB_LAUNCH_CHECK("node_ie prep");
   // a = SAE_enc(x)
   EpiEnc::Params e1{};
-  e1.bias = fold; e1.e_bf16 = E; e1.hw = HW; e1.words = (F + 31) / 32;
+  e1.bias = fold; e1.e_bf16 = E; e1.words = (F + 31) / 32;
   if (make_store_tmap_bf16_chunk(&e1.tm_e, E, Ti, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
   SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, Xp, C, Web, C, Ti, F, C, 1, e1)), "enc");
   // DIFF = dec - x = -(sae error)

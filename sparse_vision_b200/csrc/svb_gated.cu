@@ -53,8 +53,8 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
   p.aux_part = a.take<float>(static_cast<size_t>(sms) * 8);
   p.zero_words = (a.off - z0) / 4;
-  p.mask_e = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
-  p.mask_rp = a.take<uint32_t>(static_cast<size_t>(p.T) * p.words);
+  p.mask_e = a.take<uint32_t>(static_cast<size_t>(p.T) * 4 * cdiv(p.words, 4));    // group-major, see mask_index
+  p.mask_rp = a.take<uint32_t>(static_cast<size_t>(p.T) * 4 * cdiv(p.words, 4));
   p.cnt_chunks = cdiv(p.T, kCountRows);
   p.cnt_part = a.take<uint32_t>(static_cast<size_t>(p.cnt_chunks) * p.words * 32);
   p.cs_mag = a.take<float>(static_cast<size_t>(p.tiles_m) * F);
@@ -104,7 +104,7 @@ int check_params(const svb_acts* x, const svb_gated_params* p) {
   return 0;
 }
 
-// Number of tokens with relu_pi > 0 per feature, from the encoder's 1-bit mask [T, words] (exact integers; db_gate
+// Number of tokens with relu_pi > 0 per feature, from the encoder's group-major 1-bit mask (exact integers; db_gate
 // = l1c * count must not be formed as the difference of two bf16-staged column sums).  A thread owns one 32-feature
 // word column over a chunk of 128 rows and counts 4 bit positions per add in byte lanes (bits k, k+8, k+16, k+24).
 // grid (ceil(words/128), row chunks), 128 threads;  part[chunk][f] uint32.
@@ -115,7 +115,7 @@ mask_colcount_kernel(const uint32_t* __restrict__ mask, long long T, int words, 
   const long long r0 = static_cast<long long>(blockIdx.y) * kCountRows, r1 = min(T, r0 + kCountRows);
   uint32_t lanes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long r = r0; r < r1; ++r) {
-    const uint32_t v = __ldg(mask + r * words + w);
+    const uint32_t v = __ldg(mask + mask_index(r, w & ~3, T) + (w & 3));
 #pragma unroll
     for (int k = 0; k < 8; ++k) lanes[k] += (v >> k) & 0x01010101u;
   }
@@ -192,7 +192,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
   e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
   e1.rp_bf16 = (out->relu_pi && out->relu_pi_dtype == SVB_BF16) ? static_cast<bf16*>(out->relu_pi) : pl.RP;
   e1.rp_f32 = (out->relu_pi && out->relu_pi_dtype == SVB_F32) ? static_cast<float*>(out->relu_pi) : nullptr;
-  e1.hw = pl.hw; e1.words = pl.words;
+  e1.words = pl.words;
   e1.tma = make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F) == 0 &&
            make_store_tmap_bf16(&e1.tm_rp, e1.rp_bf16, T, pl.F, pl.F) == 0;
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, pl.C, pl.Wgb, pl.C, T, pl.F, pl.C, 1, e1)), "gated enc");
@@ -233,13 +233,17 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
 
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
-  e1.e_bf16 = pl.E; e1.rp_bf16 = pl.RP; e1.act_bits = pl.act_bits; e1.l1_partial = pl.l1_part;
+  e1.e_bf16 = pl.E; e1.rp_bf16 = pl.RP; e1.l1_partial = pl.l1_part;
   e1.mask_e = pl.mask_e; e1.mask_rp = pl.mask_rp;
-  e1.hw = pl.hw; e1.words = pl.words; e1.tma = 1; e1.slab_major = pl.es;
+  e1.words = pl.words; e1.tma = 1; e1.slab_major = pl.es;
   if (pl.es ? (make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) || make_store_tmap_bf16_slab(&e1.tm_rp, pl.RP, T, F))
             : (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F) || make_store_tmap_bf16(&e1.tm_rp, pl.RP, T, F, F)))
     return fail(SVB_ERR_TMAP, "tensor maps for E / relu_pi");
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
+  // per-image activity bits of e from its 1-bit mask: side stream, beside the decoder GEMM
+  SVB_TRY(side_fork(h, st));
+  (mask_to_activity_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(pl.words, 4)), 128, 0, h->side>>>(
+      pl.mask_e, pl.act_bits, pl.T, pl.hw, pl.words), svb::count_launch());
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
   if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))

@@ -152,7 +152,7 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   e1.e_bf16 = (out->enc && out->enc_dtype == SVB_BF16) ? static_cast<bf16*>(out->enc) : pl.E;
   e1.e_f32 = (out->enc && out->enc_dtype == SVB_F32) ? static_cast<float*>(out->enc) : nullptr;
   e1.pre_f32 = out->pre;
-  e1.hw = pl.hw; e1.words = pl.words;
+  e1.words = pl.words;
   if (make_store_tmap_bf16_chunk(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
   SVB_GEMM((launch_gemm<256, false, false, EpiEncApi>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
   if (out->dec) {
@@ -202,7 +202,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   EpiEnc::Params e1{};
   e1.bias = pl.fold; e1.e_bf16 = pl.E; e1.l1_partial = pl.l1_part;
   e1.mask_words = pl.mask;   // the per-image activity bits are derived from the masks below, not in the epilogue
-  e1.hw = pl.hw; e1.words = pl.words; e1.e_slab = pl.es;
+  e1.words = pl.words; e1.e_slab = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab32(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16_chunk(&e1.tm_e, pl.E, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for E");
   if (pl.bstat) {

@@ -282,9 +282,8 @@ static int perf_enc_variants() {
   for (int variant = 0; variant < 5; ++variant) {
     EpiEnc::Params ep;
     memset(&ep, 0, sizeof(ep));
-    ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.hw = HW; ep.words = words;
+    ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.words = words;
     make_store_tmap_bf16_chunk(&ep.tm_e, dE, M, N, N);
-    if (variant == 1 || variant == 4) ep.act_bits = dact;
     if (variant == 2 || variant == 4) ep.mask_words = dmask;
     if (variant == 3 || variant == 4) ep.l1_partial = dl1;
     for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiEnc, true>(0, dA, K, dB, K, M, N, K, 1, ep);
@@ -297,7 +296,7 @@ static int perf_enc_variants() {
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
-    printf("[perf EpiEnc variant %d: act=%d mask=%d l1=%d] %.3f ms  %.1f TFLOP/s\n", variant, ep.act_bits != nullptr,
+    printf("[perf EpiEnc variant %d: mask=%d l1=%d] %.3f ms  %.1f TFLOP/s\n", variant,
            ep.mask_words != nullptr, ep.l1_partial != nullptr, ms, 2.0 * M * N * K / ms * 1e-9);
   }
   return 0;
