@@ -1,10 +1,11 @@
 """Development timing of the SaeMLP training step on the InceptionV1 layer shapes the reference trains SAEs on
 (utils.py:2662-2741: mixed3a k=8, the others k=4), B=256 images per GPU, bf16 NCHW input."""
 import sys, os
+import ctypes as C_
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sae_oracle as O
-from sparse_vision_b200 import ops
+from sparse_vision_b200 import ops, _lib as L
 
 LAYERS = [("mixed3a", 256, 28, 8), ("mixed3b", 480, 28, 4), ("mixed4a", 508, 14, 4), ("mixed4b", 512, 14, 4),
           ("mixed4d", 528, 14, 4), ("mixed4e", 832, 14, 4), ("mixed5a", 832, 7, 4), ("mixed5b", 1024, 7, 4)]
@@ -34,6 +35,17 @@ def main():
             T, F = B * S * S, C * k
             print(f"{name}: C={C} {S}x{S} F={F} T={T}: {t:.3f} ms/step  {T / t * 1e3 / 1e6:.1f} M act-vec/s  "
                   f"{10 * C * F * T / t * 1e-9:.0f} TFLOP/s", flush=True)
+            # per-phase times from the library's CUDA-event profiler (adds a few us per phase)
+            lib, h = L.load(), L.handle(dev)
+            L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
+            for i in range(5):
+                ops.sae_train_step(xs[i % 2], params, ms, vs, i + 20, 1e-3, 0.1, k, optimizer="constrained_adam")
+            torch.cuda.synchronize()
+            ph = (C_.c_float * 16)()
+            n_ph, n_st = C_.c_int32(0), C_.c_int32(0)
+            L.check(lib.svb_profile_read(h, 16, ph, C_.byref(n_ph), C_.byref(n_st)), "svb_profile_read")
+            L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
+            print("    " + "  ".join(f"{lib.svb_profile_phase_name(i).decode()}={ph[i]:.3f}" for i in range(n_ph.value)), flush=True)
         except Exception as exc:  # report and go on to the next layer
             print(f"{name}: C={C} {S}x{S}: FAILED {type(exc).__name__}: {exc}", flush=True)
 
