@@ -545,6 +545,7 @@ struct EpiDecNchw {
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
   static constexpr bool kPrefetchAcc = true;
+  static constexpr bool kPadN64 = true;   // N % 64 != 0: the padding columns of diff's last slab are written (zeros)
   static constexpr uint32_t kSmemBytes = kWarps * 4096 + 2 * 256 * sizeof(float);
   const Params& p;
   uint8_t* tbuf;  // channel-major [32 channels][32 tokens] bf16 copy of d (2 KB)
@@ -608,7 +609,8 @@ struct EpiDecNchw {
     const size_t grp = static_cast<size_t>(ti.tile_m) * 4 + wq;
     float* part0 = p.part + (grp * 2 + 0) * 3 * g.N;
     float* part1 = p.part + (grp * 2 + 1) * 3 * g.N;
-    const int col = col0 + lane;  // this lane's channel (N % 64 == 0: always < N)
+    const int col = col0 + lane;  // this lane's channel
+    const bool col_ok = col < g.N;  // false only in the padding of the last slab (N % 64 != 0)
     {  // (1) sum d, sum d^2 of channel col0 + lane from its row of the channel-major copy
       const uint4* rp = reinterpret_cast<const uint4*>(tbuf + lane * 64);
       uint32_t w[16];
@@ -633,9 +635,11 @@ struct EpiDecNchw {
           else if (i < nrows) { a1 += d; q1 += d * d; }
         }
       }
-      part0[col] = a0;
-      part0[g.N + col] = q0;
-      if (n1 > 0) { part1[col] = a1; part1[g.N + col] = q1; }
+      if (col_ok) {
+        part0[col] = a0;
+        part0[g.N + col] = q0;
+        if (n1 > 0) { part1[col] = a1; part1[g.N + col] = q1; }
+      }
     }
     {  // (2) sum diff^2 of the same channel from the (64B-swizzled) diff tile; rows >= M hold zeros
       float s = 0.f;
@@ -646,19 +650,19 @@ struct EpiDecNchw {
         const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
         s += f * f;
       }
-      part0[2 * g.N + col] = s;
+      if (col_ok) part0[2 * g.N + col] = s;
     }
     // (3) d back to NCHW.  out_kind 1: one TMA store for the positions of image b0 (clipped at the image end); the
     // positions of a second image in a straddling warp (n0, n1 multiples of 8 there) are copied with 16-byte stores.
     // out_kind 2 / 3: rows that TMA cannot address (HW % 8 != 0) or fp32 outputs -- every lane writes its channel's
     // tokens from the staged tile itself, one image segment after the other.
     if (p.out_kind == 1) {
-      if (n1 > 0) {
+      if (n1 > 0 && col_ok) {
         const uint4* src = reinterpret_cast<const uint4*>(tbuf + lane * 64 + n0 * 2);
         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
         for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
       }
-    } else if (p.out_kind != 0) {
+    } else if (p.out_kind != 0 && col_ok) {
       const uint16_t* src = reinterpret_cast<const uint16_t*>(tbuf + lane * 64);
       const int hw0 = row0 - b0 * p.hw;
 #pragma unroll
@@ -691,7 +695,7 @@ struct EpiDecNchw {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (p.out_kind == 1) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);
+      if (p.out_kind == 1 && col0 < g.N) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);   // clipped at C
       tma_store_3d(&p.tm_diff, fbuf, col0 & 63, row0, col0 >> 6);
       bulk_commit();
     }

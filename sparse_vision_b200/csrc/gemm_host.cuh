@@ -61,13 +61,14 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, u
 // Slab-major bf16 matrix: logical [rows, cols] stored as [cols/64][rows][64], i.e. every 64-column slab keeps all its
 // rows contiguous (128 bytes per row).  A 128 x 64 operand tile or a 32 x 64 epilogue slab is then ONE contiguous
 // block of memory instead of 128-byte pieces at a row pitch of cols*2 bytes, which is what DRAM pages like; rows
-// beyond `rows` are clipped / zero-filled exactly as in the row-major case.  Needs cols % 64 == 0.
+// beyond `rows` are clipped / zero-filled exactly as in the row-major case.  cols % 64 != 0: the last slab is stored
+// whole and its padding columns must hold zeros wherever the matrix is a K operand (the writers see to that).
 // Coordinates are {0, row, col / 64}; box = 64 x box_rows x 1.
 inline int make_tmap_bf16_slab(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   auto fn = tmap_encode_fn();
   if (!fn) return -1;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (cols % 64)) return -2;
-  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  if (reinterpret_cast<uintptr_t>(ptr) & 127) return -2;
+  cuuint64_t gdim[3] = {64, rows, (cols + 63) / 64};
   cuuint64_t gstride[2] = {128, rows * 128};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -103,8 +104,8 @@ inline int make_store_tmap_bf16_chunk(CUtensorMap* out, void* ptr, uint64_t rows
 inline int make_store_tmap_bf16_slab32(CUtensorMap* out, void* ptr, uint64_t rows, uint64_t cols) {
   auto fn = tmap_encode_fn();
   if (!fn) return -1;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 127) || (cols % 64)) return -2;
-  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  if (reinterpret_cast<uintptr_t>(ptr) & 127) return -2;
+  cuuint64_t gdim[3] = {64, rows, (cols + 63) / 64};
   cuuint64_t gstride[2] = {128, rows * 128};
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};

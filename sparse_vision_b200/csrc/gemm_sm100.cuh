@@ -117,6 +117,11 @@ template <class E> struct epi_skips_acc_load<E, decltype(void(E::kSkipAccLoad))>
 template <class E, class = void> struct epi_ones_col { static constexpr bool value = false; };
 template <class E> struct epi_ones_col<E, decltype(void(E::kOnesCol))> { static constexpr bool value = E::kOnesCol; };
 // Epilogues may define `static constexpr bool kPrefetchAcc = true` to double-buffer the TMEM reads in registers.
+// Epilogues with `static constexpr bool kPadN64 = true` write a slab-major output and are also handed the all-zero
+// accumulator chunks between N and the end of N's last 64-column slab, so that the slab's padding columns get defined
+// (zero) contents: the matrix is the K operand of a later GEMM.
+template <class E, class = void> struct epi_pads_n64 { static constexpr bool value = false; };
+template <class E> struct epi_pads_n64<E, decltype(void(E::kPadN64))> { static constexpr bool value = E::kPadN64; };
 template <class E, class = void> struct epi_prefetches_acc { static constexpr bool value = false; };
 template <class E> struct epi_prefetches_acc<E, decltype(void(E::kPrefetchAcc))> { static constexpr bool value = E::kPrefetchAcc; };
 
@@ -347,6 +352,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = wq * 32 + lane;
     const int tid = ew * 32 + lane;
     Epi epi(ep, epi_smem, ew, BLOCK_N);
+    const int n_lim = epi_pads_n64<Epi>::value ? ((p.N + 63) & ~63) : p.N;
     uint32_t acc = 0, acc_phase = 0;
     long long w_acc = 0;
     (void)w_acc;
@@ -369,14 +375,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (epi_prefetches_acc<Epi>::value) {
         float v[2][32];
         const int c_begin = cgroup * kChunksPerWarp;
-        if (ti.n0 + c_begin * 32 < p.N) tmem_ld_32x32(t_addr + c_begin * 32, v[0]);
+        if (ti.n0 + c_begin * 32 < n_lim) tmem_ld_32x32(t_addr + c_begin * 32, v[0]);
 #pragma unroll
         for (int ci = 0; ci < kChunksPerWarp; ++ci) {
           const int c = c_begin + ci;
           const int col0 = ti.n0 + c * 32;
-          if (col0 < p.N) {
+          if (col0 < n_lim) {
             tmem_ld_wait();
-            if (ci + 1 < kChunksPerWarp && col0 + 32 < p.N) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(ci + 1) & 1]);
+            if (ci + 1 < kChunksPerWarp && col0 + 32 < n_lim) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(ci + 1) & 1]);
             epi.chunk(p, ti, row, col0, v[ci & 1], wq, lane, ci);
           }
         }
@@ -385,7 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ci = 0; ci < kChunksPerWarp; ++ci) {
           const int c = cgroup * kChunksPerWarp + ci;
           const int col0 = ti.n0 + c * 32;
-          if (col0 < p.N) {
+          if (col0 < n_lim) {
             float v[32];
             if constexpr (!epi_skips_acc_load<Epi>::value) {
               tmem_ld_32x32(t_addr + c * 32, v);

@@ -151,7 +151,8 @@ template <int VEC> struct Row8<float, VEC> {
 
 // NCHW [B,C,HW] (bf16 or fp32) -> bf16 tokens [B*HW, C]; sae_mlp.py:44 'b c h w -> (b h w) c'.
 // grid (ceil(HW/64), ceil(C/64), B), 256 threads; bf16 staged in smem with a 2-element row pad.
-// slab_rows > 0: write the slab-major layout [C/64][slab_rows = B*HW][64] (gemm_host.cuh) instead of [B*HW, C].
+// slab_rows > 0: write the slab-major layout [ceil(C/64)][slab_rows = B*HW][64] (gemm_host.cuh) instead of [B*HW, C];
+// the padding columns of the last slab (C % 64 != 0) are written as zeros.
 // xpart != null: also emit, per image, HW tile and channel, the statistics of the bf16-rounded x that the loss
 // metrics need (sum, sum of squares, min, max): xpart[((b * gridDim.x + tile) * 4 + q) * C + c].
 template <typename TIn, int VEC>
@@ -199,7 +200,7 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
   uint16_t* ob = reinterpret_cast<uint16_t*>(out);
   for (int i = threadIdx.x; i < 64 * 8; i += 256) {
     const int p = i >> 3, co = (i & 7) * 8;
-    if (p0 + p < HW && c0 + co < C) {
+    if (p0 + p < HW && (c0 + co < C || slab_rows > 0)) {   // tile rows of channels >= C hold zeros
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)

@@ -196,10 +196,10 @@ inline int nchw_vec(const void* p, int hw, int elem_bytes) {
   if (hw % 4 == 0 && (a % (4 * elem_bytes)) == 0) return 4;
   return 1;
 }
-// slab_major: write [C/64][T][64] instead of [T, C] (NCHW inputs with C % 64 == 0 only; see gemm_host.cuh)
+// slab_major: write [ceil(C/64)][T][64] instead of [T, C] (NCHW inputs only; see gemm_host.cuh)
 inline int pack_acts(cudaStream_t st, const svb_acts* x, bf16* buf, bool slab_major = false, float* xpart = nullptr) {
   const long long T = x->n_images * static_cast<long long>(x->hw);
-  if (slab_major && (x->layout != SVB_NCHW || x->hw == 1 || x->C % 64)) return fail(SVB_ERR_BAD_ARG, "slab-major pack needs NCHW input with C % 64 == 0");
+  if (slab_major && (x->layout != SVB_NCHW || x->hw == 1)) return fail(SVB_ERR_BAD_ARG, "slab-major pack needs NCHW input");
   const long long slab_rows = slab_major ? T : 0;
   if (x->layout == SVB_TOKENS || x->hw == 1) {
     const size_t n = static_cast<size_t>(T) * x->C;

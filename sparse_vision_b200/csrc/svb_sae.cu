@@ -60,7 +60,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
   p.xs = false; p.es = false; p.fused_dec = false;
-  const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
+  // X / D / DIFF may be slab-major with a zero-padded last slab (C % 64 != 0): size them for ceil(C / 64) slabs
+  const size_t TC = static_cast<size_t>(p.T) * (cdiv(p.C, 64) * 64), TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
   p.Web = a.take<bf16>(FC);
   p.Wdb = a.take<bf16>(FC);
@@ -179,12 +180,14 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // Slab-major workspaces (every 128 x 64 operand tile / 32 x 64 epilogue slab is one contiguous block):
   // E and dPre' whenever F % 64 == 0; X, D, DIFF when we pack X ourselves from NCHW and the fused post-decoder pass runs.
   pl.es = F % 64 == 0;
-  pl.xs = !pl.zero_copy_x && C % 64 == 0 && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
+  const bool slab_ok = !pl.zero_copy_x && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
   // Fused decoder epilogue: needs the slab-major path and >= 32 tokens per image (a warp's 32 tokens then touch at
   // most two images).  d goes back to the caller's NCHW tensor by TMA when that can address it (bf16, 16-byte row
   // pitch), else by 8- / 16-byte stores from the staged tiles (fp32 outputs, 14x14 maps).
   void* dec_out = out ? out->dec_out : nullptr;
-  pl.fused_dec = pl.xs && pl.hw >= 32 && (!dec_out || pl.hw % 4 == 0);   // 7x7 maps: element-wise stores are too slow
+  pl.fused_dec = slab_ok && pl.hw >= 32 && (!dec_out || pl.hw % 4 == 0);   // 7x7 maps: element-wise stores are too slow
+  // C % 64 != 0 (mixed3b: 480, mixed4d: 528): only the fused epilogue keeps the last slab's padding columns zero
+  pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
   int out_kind = 0;
   if (dec_out)
     out_kind = out->dec_dtype == SVB_F32 ? 3
