@@ -540,7 +540,9 @@ struct EpiDecNchw {
     void* out;                        // the caller's NCHW output tensor (null: d is not handed back)
     int hw;                           // tokens per image (>= 32)
     int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base); 2: bf16 and
-                                      // 3: fp32 with plain stores from the staged tile (any HW / alignment)
+                                      // 3: fp32 with plain stores from the staged tile (any HW / alignment);
+                                      // 4: tm_out is a channel-major [C][T] workspace (make_store_tmap_bf16_cmajor)
+                                      //    that a copy kernel turns into the caller's tensor (HW % 4 != 0)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -662,7 +664,7 @@ struct EpiDecNchw {
         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
         for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
       }
-    } else if (p.out_kind != 0 && col_ok) {
+    } else if ((p.out_kind == 2 || p.out_kind == 3) && col_ok) {
       const uint16_t* src = reinterpret_cast<const uint16_t*>(tbuf + lane * 64);
       const int hw0 = row0 - b0 * p.hw;
 #pragma unroll
@@ -696,6 +698,7 @@ struct EpiDecNchw {
     __syncwarp();
     if (lane == 0) {
       if (p.out_kind == 1 && col0 < g.N) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);   // clipped at C
+      if (p.out_kind == 4 && col0 < g.N) tma_store_2d(&p.tm_out, tbuf, row0, col0);                    // clipped at T, C
       tma_store_3d(&p.tm_diff, fbuf, col0 & 63, row0, col0 >> 6);
       bulk_commit();
     }

@@ -129,6 +129,22 @@ inline int make_tmap_nchw_bf16(CUtensorMap* out, void* ptr, uint64_t B, uint64_t
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+// Channel-major bf16 copy of the decoder output, [C][ld] with ld >= T a multiple of 8: the fused decoder epilogue
+// stores its channel-major 32 x 32 tiles here when the caller's NCHW rows are not TMA-addressable (HW % 4 != 0, e.g.
+// 7x7 maps); coordinates {token, channel}, box 32 x 32, no swizzle.
+inline int make_store_tmap_bf16_cmajor(CUtensorMap* out, void* ptr, uint64_t C, uint64_t T, uint64_t ld) {
+  auto fn = tmap_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) return -2;
+  cuuint64_t gdim[2] = {T, C};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
 inline int device_sm_count() {
   static int n = 0;
   if (!n) {

@@ -212,6 +212,27 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
   }
 }
 
+// Channel-major decoder output [C][ld] (tokens t = b*HW + p contiguous per channel) -> the caller's NCHW tensor
+// [B, C, HW]: every image's HW-long run of a channel is copied as it is.  grid (ceil(T / 1024), C), 256 threads x 4.
+template <typename TOut>
+static __global__ void __launch_bounds__(256)
+cmajor_to_nchw_kernel(const bf16* __restrict__ dt, TOut* __restrict__ out, int C, int HW, long long T, long long ld) {
+  const int c = blockIdx.y;
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(dt) + static_cast<size_t>(c) * ld;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long t = blockIdx.x * 1024LL + k * 256 + threadIdx.x;
+    if (t < T) {
+      const long long b = t / HW;
+      const int p = static_cast<int>(t - b * HW);
+      const size_t o = (static_cast<size_t>(b) * C + c) * HW + p;
+      const uint16_t h = src[t];
+      if (sizeof(TOut) == 2) reinterpret_cast<uint16_t*>(out)[o] = h;
+      else reinterpret_cast<float*>(out)[o] = __uint_as_float(static_cast<uint32_t>(h) << 16);
+    }
+  }
+}
+
 // Fused "after the decoder" pass for NCHW inputs: ONE sweep over d (token-major bf16) and x (NCHW) that
 //   * writes d back in NCHW (what the hook returns, model_pipeline.py:425,432; utils.py:2478) when d_out != null, and
 //   * accumulates, per image and channel, sum x, sum x^2, sum d, sum d^2, sum (d-x), sum (d-x)^2, min x, max x

@@ -67,7 +67,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.Wdb = a.take<bf16>(FC);
   p.fold = a.take<float>(F);
   p.E = a.take<bf16>(TF);
-  p.D = a.take<bf16>(TC);
+  p.D = a.take<bf16>(TC + 8 * static_cast<size_t>(p.C));   // + slack: also the channel-major [C][round8(T)] copy of d
   if (!train) return;
   p.DP = a.take<bf16>(TF);
   p.DIFF = a.take<bf16>(TC);
@@ -183,15 +183,18 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   const bool slab_ok = !pl.zero_copy_x && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
   // Fused decoder epilogue: needs the slab-major path and >= 32 tokens per image (a warp's 32 tokens then touch at
   // most two images).  d goes back to the caller's NCHW tensor by TMA when that can address it (bf16, 16-byte row
-  // pitch), else by 8- / 16-byte stores from the staged tiles (fp32 outputs, 14x14 maps).
+  // pitch), else by 8- / 16-byte stores from the staged tiles (fp32 outputs, 14x14 maps), else (7x7 maps: HW % 4 != 0)
+  // through a channel-major copy that a small kernel scatters into the NCHW tensor beside the dE GEMM.
   void* dec_out = out ? out->dec_out : nullptr;
-  pl.fused_dec = slab_ok && pl.hw >= 32 && (!dec_out || pl.hw % 4 == 0);   // 7x7 maps: element-wise stores are too slow
+  pl.fused_dec = slab_ok && pl.hw >= 32;
   // C % 64 != 0 (mixed3b: 480, mixed4d: 528): only the fused epilogue keeps the last slab's padding columns zero
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
   int out_kind = 0;
   if (dec_out)
-    out_kind = out->dec_dtype == SVB_F32 ? 3
+    out_kind = pl.hw % 4 != 0 ? 4
+               : out->dec_dtype == SVB_F32 ? 3
                : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 2;
+  const long long ld_t = (pl.T + 7) & ~7LL;   // row pitch of the channel-major copy (out_kind 4)
   prof_begin_step(h);
   prof_mark(h, st, 0);
   // weight prologue on the side stream, next to the activation pack
@@ -226,10 +229,18 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     e2.out = dec_out; e2.out_kind = out_kind;
     if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
     if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
+    if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
     // the statistics folds only feed the tail of the step: side stream, beside the dE GEMM
     SVB_TRY(side_fork(h, st));
+    if (out_kind == 4) {
+      const dim3 grid(static_cast<unsigned>(cdiv(pl.T, 1024)), C);
+      if (out->dec_dtype == SVB_F32)
+        (cmajor_to_nchw_kernel<float><<<grid, 256, 0, h->side>>>(pl.D, static_cast<float*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
+      else
+        (cmajor_to_nchw_kernel<bf16><<<grid, 256, 0, h->side>>>(pl.D, static_cast<bf16*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
+    }
     (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, h->side>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
     (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, h->side>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
     SVB_LAUNCH_CHECK("decoder statistics");
