@@ -225,12 +225,15 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  prof_begin_step(h);   // phases as in svb_sae.cu; "dec_gemm" covers the decoder and the via_gate GEMM
+  prof_mark(h, st, 0);
   // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
   SVB_TRY(side_fork(h, st));
   SVB_TRY(run_prep(h->side, pl, p, true));
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
   SVB_TRY(side_join(h, st));
 
+  prof_mark(h, st, 1);
   EpiGatedEnc::Params e1{};
   e1.dot = pl.dot; e1.b_gate = p->b_gate; e1.b_mag = p->b_mag; e1.exp_r = pl.exp_r;
   e1.e_bf16 = pl.E; e1.rp_bf16 = pl.RP; e1.l1_partial = pl.l1_part;
@@ -240,6 +243,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
             : (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F) || make_store_tmap_bf16(&e1.tm_rp, pl.RP, T, F, F)))
     return fail(SVB_ERR_TMAP, "tensor maps for E / relu_pi");
   SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
+  prof_mark(h, st, 2);
   // per-image activity bits of e from its 1-bit mask: side stream, beside the decoder GEMM
   SVB_TRY(side_fork(h, st));
   (mask_to_activity_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(pl.words, 4)), 128, 0, h->side>>>(
@@ -256,6 +260,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   SVB_TRY(run_post_dec(h->side, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
                        out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
+  prof_mark(h, st, 3);
+  prof_mark(h, st, 4);
   EpiGatedDPre::Params e3{};
   e3.mask_e = pl.mask_e; e3.mask_rp = pl.mask_rp; e3.exp_r = pl.exp_r; e3.words = pl.words;
   e3.colsum_mag = pl.cs_mag; e3.colsum_a = pl.cs_a;
@@ -264,6 +270,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_a, pl.A, T, F) : make_store_tmap_bf16(&e3.tm_a, pl.A, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for A'");
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
+  prof_mark(h, st, 5);
   // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
   // decoder weight-gradient GEMM runs (svb_set_comm_stream).
   const size_t FC = static_cast<size_t>(F) * C;
@@ -299,12 +306,15 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
   ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
   (grads_tail_kernel<<<1, 1024, 0, ss>>>(ta), svb::count_launch());
+  prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
   SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, false, pl.es)), "dW_dec");
+  prof_mark(h, st, 7);
   SVB_TRY(side_join(h, st));
   SVB_TRY(run_assemble(st, aa, 2));
   (gated_rmag_kernel<<<cdiv(F, 32), 256, 0, st>>>(flat + pl.o_gwd, pl.Wdb, p->b_mag, pl.csum_mag, s, C, F, flat + pl.o_gr), svb::count_launch());
   SVB_LAUNCH_CHECK("gated grad assembly");
+  prof_mark(h, st, 8);
   h->gradbuf = flat;
   h->sum_elems = static_cast<int64_t>(pl.sum_elems);
   h->max_elems = static_cast<int64_t>(pl.max_elems);
@@ -350,6 +360,7 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
     (step_finalize_kernel<<<1, 1024, 0, st>>>(fa), svb::count_launch());
     SVB_LAUNCH_CHECK("gated finalize");
   }
+  prof_mark(h, st, 9);
   return 0;
 }
 

@@ -1,9 +1,10 @@
 """Development timing of the GatedSae training step at cfg3 (C=512, 14x14, k=16, B=256 images per GPU)."""
 import sys, os, time
+import ctypes as C_
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sae_oracle as O
-from sparse_vision_b200 import ops
+from sparse_vision_b200 import ops, _lib as L
 
 def main():
     B, C, H, W, k = 256, 512, 14, 14, 16
@@ -35,6 +36,17 @@ def main():
     flops = (12 if kind == "gated_sae" else 10) * C * F * T
     print(f"{kind} B={B} C={C} HW={H}x{W} k={k}: {ms_step:.3f} ms/step  {T / ms_step * 1e3 / 1e6:.1f} M act-vec/s  "
           f"{flops / ms_step * 1e-9:.0f} TFLOP/s algorithmic  stats={ {kk: round(v, 4) for kk, v in res.scalars().items() if kk in ('loss', 'rec', 'l1', 'aux')} }")
+
+    lib, h = L.load(), L.handle(dev)
+    L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
+    for i in range(5):
+        fn(xs[i % 2], params, ms, vs, i + 20, 1e-3, lam, k, optimizer="constrained_adam")
+    torch.cuda.synchronize()
+    ph = (C_.c_float * 16)()
+    n_ph, n_st = C_.c_int32(0), C_.c_int32(0)
+    L.check(lib.svb_profile_read(h, 16, ph, C_.byref(n_ph), C_.byref(n_st)), "svb_profile_read")
+    L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
+    print("    " + "  ".join(f"{lib.svb_profile_phase_name(i).decode()}={ph[i]:.3f}" for i in range(n_ph.value)), flush=True)
 
 if __name__ == "__main__":
     main()
