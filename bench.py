@@ -49,14 +49,35 @@ def _synthetic_acts(n_images, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML
+    in-process every ~5 ms when nvidia-ml-py is importable (the timed region is only tens of milliseconds long), else
+    an `nvidia-smi -lms 100` child process."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.mask, self.max_mhz, self.run, self.live = None, [], 0, None, False, False
 
-    def start(self):
+    def prepare(self):
+        """Everything slow (NVML init / the nvidia-smi child) happens here, before the barrier that opens the timed
+        region; start() only flips a flag."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(self.index).uuid
+            try:
+                self.dev = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.run = pynvml, True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -66,11 +87,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            if self.live:
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(reasons(self.dev))
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def start(self):
+        self.live = True
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.t.join(timeout=1.0)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, b in self.BITS.items() if self.mask & b), "samples": len(sm),
+                    "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -91,7 +134,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def _peaks():
@@ -288,10 +331,11 @@ def run_svb(args):
     L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.prepare()
     launches0 = lib.svb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.start()
     ev0.record()
     for i in range(args.steps):
         res = one_step(xdev[i % 2])
