@@ -175,34 +175,56 @@ def cpu_reference_throughput(n_images, steps, warmup, threads=None):
     return tokens / dt, dt * 1e3, torch.get_num_threads()
 
 
-def gated_section(dev, peaks, n_images=256, iters=10):
+def gated_section(dev, peaks, n_images=256, iters=10, world=1):
     """configs[2]: GatedSae on inception4c-shaped activations (C=512, 14x14, expansion 16 -> F=8192), one fused training
-    step per call on bf16 NCHW activations resident in HBM; 12*C*F FLOP per token."""
+    step per call on bf16 NCHW activations resident in HBM; 12*C*F FLOP per token.  world > 1:
+    data parallel like the main workload (n_images per GPU, peer-memory all-reduce of the flat gradient buffer; every
+    rank calls this, times are the max over ranks)."""
     from sparse_vision_b200 import ops
     from sparse_vision_b200.models.gated_sae import GatedSae
+    from sparse_vision_b200.parallel import DataParallelStep
+    import torch.distributed as dist
     Cc, side, k = 512, 14, 16
     F, T = Cc * k, n_images * side * side
+    rank = dist.get_rank() if world > 1 else 0
     torch.manual_seed(0)
     model = GatedSae(Cc, k)
     params = [p.detach().clone().to(dev) for p in model.param_list()]
     ms_ = [torch.zeros_like(p) for p in params]
     vs_ = [torch.zeros_like(p) for p in params]
-    g = torch.Generator(device="cpu").manual_seed(21)
+    g = torch.Generator(device="cpu").manual_seed(21 + rank)
     xs = [torch.relu(torch.randn(n_images, Cc, side, side, generator=g)).to(torch.bfloat16).to(dev) for _ in range(2)]
+    dp = DataParallelStep("gated_sae") if world > 1 else None
+
+    def step(i, no):
+        if dp is None:
+            return ops.gated_train_step(xs[i % 2], params, ms_, vs_, no, LR, 0.1, k, optimizer="constrained_adam")
+        return dp.step(xs[i % 2], params, ms_, vs_, no, LR, 0.1, k, "constrained_adam", (0.9, 0.999),
+                       n_images * world, T * world, want_dec=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for i in range(3):
-        res = ops.gated_train_step(xs[i % 2], params, ms_, vs_, i + 1, LR, 0.1, k, optimizer="constrained_adam")
-    torch.cuda.synchronize()
+        res = step(i, i + 1)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
-        res = ops.gated_train_step(xs[i % 2], params, ms_, vs_, i + 4, LR, 0.1, k, optimizer="constrained_adam")
+        res = step(i, i + 4)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    tf = 12.0 * Cc * F * T / (ms * 1e-3) / 1e12
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    tf = 12.0 * Cc * F * T / (ms * 1e-3) / 1e12          # per GPU
     sc = res.scalars()
-    return {"workload": "configs[2]: GatedSae C=512 14x14 k=16 F=8192, 256 images = 50176 tokens, constrained_adam, bf16 NCHW",
-            "ms_per_step": ms, "act_vec_per_s": T / (ms * 1e-3), "algorithmic_tflops": tf,
+    return {"workload": f"configs[2]: GatedSae C=512 14x14 k=16 F=8192, 256 images = 50176 tokens per GPU, "
+                        f"constrained_adam, bf16 NCHW, dp{world}",
+            "n_gpus": world, "ms_per_step": ms, "act_vec_per_s": world * T / (ms * 1e-3), "algorithmic_tflops_per_gpu": tf,
             "frac_of_sustained_peak": tf / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
             "final_step_stats": {kk: sc[kk] for kk in ("loss", "rec", "l1", "aux")}}
 
@@ -390,6 +412,9 @@ def run_svb(args):
     value = g_tokens / (ms_step * 1e-3)
     e2e_value = g_tokens / (ms_e2e / n_e2e * 1e-3)
 
+    # configs[2] (GatedSae, quoted on 2/4/8 GPUs) rides along: collective at N > 1, so every rank runs it
+    gated = gated_section(dev, _peaks(), world=world) if not args.no_ie else None
+
     if rank == 0:
         peaks = _peaks()
         gemm_phases = {k: v for k, v in phases.items() if k.endswith("_gemm")}
@@ -427,7 +452,8 @@ def run_svb(args):
         }
         if world == 1 and not args.no_ie:
             line["ie"] = ie_section(dev, peaks)
-            line["gated"] = gated_section(dev, peaks)
+        if gated is not None:
+            line["gated"] = gated
         if cpu_v is not None:
             line["cpu_baseline"] = {
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",

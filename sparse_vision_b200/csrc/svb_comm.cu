@@ -16,7 +16,7 @@ using namespace svb;
 
 namespace {
 
-constexpr int kCommBlocks = 64, kCommThreads = 512, kMaxRanks = 8;
+constexpr int kCommBlocks = 128, kCommThreads = 512, kMaxRanks = 8;
 
 struct CommArgs {
   float* buf[kMaxRanks];      // every rank's flat buffer (own entry = local pointer)
@@ -61,48 +61,55 @@ __device__ __forceinline__ float4 combine(float4 a, const float4 v) {
   else { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
   return a;
 }
-template <bool MAX>
+// W = compile-time bound on the world size (2, 4 or 8): 16 / W elements per thread and iteration, so that 16
+// independent 16-byte loads over NVLink are in flight per thread whatever the world size (64 registers).
+template <bool MAX, int W>
 __device__ __forceinline__ void reduce_section(const CommArgs& a, long long begin, long long n) {
   // slice of this rank, in float4 units so that every access is 16 bytes (section starts are 16-byte aligned)
   const long long n4 = (n + 3) / 4;
   const long long per = (n4 + a.world - 1) / a.world;
   const long long lo = a.rank * per, hi = min(n4, lo + per);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  // two elements per thread and iteration: 2 * world independent 16-byte loads over NVLink are in flight at once
-  for (long long i = lo + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi; i += 2 * stride) {
-    const long long e0 = begin + 4 * i, e1 = e0 + 4 * stride;
-    const bool two = i + stride < hi;
-    float4 v0[kMaxRanks], v1[kMaxRanks];
+  constexpr int kUnroll = 16 / W;
+  for (long long i = lo + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi; i += kUnroll * stride) {
+    float4 v[kUnroll][W];
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r) {
-      if (r < a.world) {
-        v0[r] = *reinterpret_cast<const float4*>(a.buf[r] + e0);
-        if (two) v1[r] = *reinterpret_cast<const float4*>(a.buf[r] + e1);
-      }
-    }
-    float4 acc0 = v0[0], acc1 = v1[0];
+    for (int u = 0; u < kUnroll; ++u) {
+      if (i + u * stride < hi) {
+        const long long e = begin + 4 * (i + u * stride);
 #pragma unroll
-    for (int r = 1; r < kMaxRanks; ++r) {
-      if (r < a.world) {
-        acc0 = combine<MAX>(acc0, v0[r]);
-        if (two) acc1 = combine<MAX>(acc1, v1[r]);
+        for (int r = 0; r < W; ++r)
+          if (r < a.world) v[u][r] = *reinterpret_cast<const float4*>(a.buf[r] + e);
       }
     }
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r) {
-      if (r < a.world) {
-        *reinterpret_cast<float4*>(a.buf[r] + e0) = acc0;
-        if (two) *reinterpret_cast<float4*>(a.buf[r] + e1) = acc1;
+    for (int u = 0; u < kUnroll; ++u) {
+      if (i + u * stride < hi) {
+        const long long e = begin + 4 * (i + u * stride);
+        float4 acc = v[u][0];   // always in rank order 0..world-1: bit-identical on every rank
+#pragma unroll
+        for (int r = 1; r < W; ++r)
+          if (r < a.world) acc = combine<MAX>(acc, v[u][r]);
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+          if (r < a.world) *reinterpret_cast<float4*>(a.buf[r] + e) = acc;
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(kCommThreads) allreduce_flat_kernel(const CommArgs a) {
+template <int W>
+__device__ __forceinline__ void allreduce_body(const CommArgs& a) {
   cta_rendezvous(a, 0);                                 // every rank's buffer is complete
-  reduce_section<false>(a, 0, a.n_sum);
-  reduce_section<true>(a, (a.n_sum + 3) / 4 * 4, a.n_max);
+  reduce_section<false, W>(a, 0, a.n_sum);
+  reduce_section<true, W>(a, (a.n_sum + 3) / 4 * 4, a.n_max);
   cta_rendezvous(a, 1);                                 // every slice has landed everywhere
+}
+
+__global__ void __launch_bounds__(kCommThreads) allreduce_flat_kernel(const CommArgs a) {
+  if (a.world <= 2) allreduce_body<2>(a);
+  else if (a.world <= 4) allreduce_body<4>(a);
+  else allreduce_body<8>(a);
 }
 
 }  // namespace
