@@ -10,7 +10,8 @@ reductions on the GPU (svb_node_ie_layer).  Edge IE / faithfulness (:476-944) ar
 
 Data parallel: shard the images of each batch across ranks; every rank accumulates un-normalised sums (scale = 1)
 and token counts; one all-reduce(SUM) per layer at the end gives the same global means as the reference's
-sample-weighted running average (:455-462).
+sample-weighted running average (:455-462).  The batch-mean criterion is compensated per batch (see compute_node_ie);
+tests/dp_ie_worker.py checks two ranks against one.
 """
 import torch
 import torch.distributed as dist
@@ -78,8 +79,8 @@ class IE:
                 enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False)
                 dead, sparsity, _ = measure_inactive_units(enc, self.exp_fac[name])        # 2-D call, as at :155
                 err_tok = x.permute(0, 2, 3, 1).reshape(-1, c).float() - dec
-                enc_sum = enc.reshape(b, h * w, -1).sum(0).t().reshape(-1, h, w)
-                err_sum = err_tok.reshape(b, h * w, c).sum(0).t().reshape(c, h, w)
+                enc_sum = enc.reshape(b, h * w, -1).sum(0).t().reshape(-1, h, w).contiguous()   # all-reduced later
+                err_sum = err_tok.reshape(b, h * w, c).sum(0).t().reshape(c, h, w).contiguous()
                 x_sum = x.float().sum(0)
                 if name not in sums:
                     sums[name] = {"enc": enc_sum, "err": err_sum, "x": x_sum, "dead": dead, "sp": sparsity * bs}
@@ -113,8 +114,15 @@ class IE:
         Returns (ie_sae_features {layer: [F]}, ie_sae_error {layer: scalar}, ie_model_neurons {layer: [C]})."""
         feat, err, neur, tokens = {}, {}, {}, {}
         for inputs, targets in batches:
-            if inputs.shape[0] == 0:
+            # The reference's criterion is a MEAN over the batch (utils.py:128-129), so d loss / d x carries 1 / B.  A
+            # rank that holds bs of the batch's bs_global images gets 1 / bs from its local mean; IE is linear in the
+            # gradient, so the rank's sums are rescaled by bs / bs_global.  (Collective: every rank calls it once per
+            # batch, also with an empty shard.)
+            bs = inputs.shape[0]
+            bs_global = self._all_reduce_counts(bs)
+            if bs == 0:
                 continue
+            ratio = bs / bs_global
             inputs, targets = inputs.to(self.device), targets.to(self.device)
             acts, grads = self._forward_collect(inputs, targets)
             for name, x in acts.items():
@@ -123,6 +131,8 @@ class IE:
                     x.float() if x.dtype not in (torch.float32, torch.bfloat16) else x, grads[name].to(x.dtype),
                     [p.detach() for p in sae.param_list()], averages["encoder_output_average"][name],
                     averages["sae_error_average"][name], averages["original_layer_output_average"][name], scale=1.0)
+                if ratio != 1.0:
+                    f, e, n = f * ratio, e * ratio, n * ratio
                 t = x.shape[0] * x.shape[2] * x.shape[3]
                 if name not in feat:
                     feat[name], err[name], neur[name], tokens[name] = f, e.reshape(1).clone(), n, t

@@ -18,3 +18,14 @@ def test_two_rank_step_matches_single_rank():
                           os.path.join(ROOT, "tests", "dp_worker.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "dp parity ok" in res.stdout
+
+
+def test_two_rank_attribution_matches_single_rank():
+    """the attribution pass shards by image; two ranks must reproduce one process's averages / node IE."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633",
+                          os.path.join(ROOT, "tests", "dp_ie_worker.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "dp ie parity ok" in res.stdout
