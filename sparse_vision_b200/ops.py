@@ -104,6 +104,14 @@ def _train_out(x, a, F, want_dec, dec_dtype):
     return out, StepResult(stats, dead, freq, n_active, dec)
 
 
+def _single_pixel_fixup(x, res):
+    """[B,C,1,1] inputs: the reference's variance_explained (utils.py:2012-2030) takes the unbiased variance over the
+    H*W = 1 positions of every (image, channel) and therefore reports nan; the library treats such inputs as B tokens."""
+    if x.dim() == 4 and x.shape[2] * x.shape[3] == 1:
+        res.stats[L.STAT["var_expl"]] = float("nan")
+    return res
+
+
 def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
                    betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None):
     """One pass of ModelPipeline.hook's train branch (model_pipeline.py:380-420) for SaeMLP, fully on device.
@@ -116,7 +124,7 @@ def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, o
     L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
                                         C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_sae_train_step")
-    return res
+    return _single_pixel_fixup(x, res)
 
 
 def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
@@ -130,7 +138,7 @@ def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor,
     L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
                                           C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_gated_train_step")
-    return res
+    return _single_pixel_fixup(x, res)
 
 
 class SplitStep:
@@ -174,7 +182,7 @@ class SplitStep:
         L.check(fn(self.h, L.stream_ptr(), C.byref(self.a), C.byref(self.p), C.byref(st), C.byref(opt), self.lam,
                    int(expansion_factor), int(global_tokens), int(global_images), C.byref(self.out)),
                 "svb_*_step_apply")
-        return self.res
+        return _single_pixel_fixup(self.x, self.res)
 
 
 def set_comm_stream(device, stream):
