@@ -1,5 +1,6 @@
 """Development timing of the SaeMLP training step on the InceptionV1 layer shapes the reference trains SAEs on
-(utils.py:2662-2741: mixed3a k=8, the others k=4), B=256 images per GPU, bf16 NCHW input."""
+(utils.py:2662-2741: mixed3a k=8, the others k=4; torchvision GoogLeNet as utils.py:280 loads it -- mixed4a/4b/4c all
+have 512 channels), B=256 images per GPU, bf16 NCHW input."""
 import sys, os
 import ctypes as C_
 import torch
@@ -7,19 +8,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sae_oracle as O
 from sparse_vision_b200 import ops, _lib as L
 
-LAYERS = [("mixed3a", 256, 28, 8), ("mixed3b", 480, 28, 4), ("mixed4a", 508, 14, 4), ("mixed4b", 512, 14, 4),
+LAYERS = [("mixed3a", 256, 28, 8), ("mixed3b", 480, 28, 4), ("mixed4a", 512, 14, 4),
           ("mixed4d", 528, 14, 4), ("mixed4e", 832, 14, 4), ("mixed5a", 832, 7, 4), ("mixed5b", 1024, 7, 4)]
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    dt = torch.float32 if len(sys.argv) > 2 and sys.argv[2] == "fp32" else torch.bfloat16   # activation dtype (in and out)
+    only = sys.argv[3] if len(sys.argv) > 3 else None
     dev = torch.device("cuda", 0)
     for name, C, S, k in LAYERS:
+        if only and name != only:
+            continue
         torch.manual_seed(0)
         p = O.init_sae_mlp(C, k)
         params = [p[kk].clone().to(dev) for kk in O.SAE_MLP_KEYS]
         ms = [torch.zeros_like(q) for q in params]
         vs = [torch.zeros_like(q) for q in params]
-        xs = [torch.relu(torch.randn(B, C, S, S, device=dev)).bfloat16() for _ in range(2)]
+        xs = [torch.relu(torch.randn(B, C, S, S, device=dev)).to(dt) for _ in range(2)]
         try:
             for i in range(3):
                 ops.sae_train_step(xs[i % 2], params, ms, vs, i + 1, 1e-3, 0.1, k, optimizer="constrained_adam")
