@@ -413,7 +413,8 @@ def run_svb(args):
     e2e_value = g_tokens / (ms_e2e / n_e2e * 1e-3)
 
     # configs[2] (GatedSae, quoted on 2/4/8 GPUs) rides along: collective at N > 1, so every rank runs it
-    gated = gated_section(dev, _peaks(), world=world) if not args.no_ie else None
+    # (at N > 1 only on request: a failed collective there must never cost the main line)
+    gated = gated_section(dev, _peaks(), world=world) if (not args.no_ie and (world == 1 or args.gated_dp)) else None
 
     if rank == 0:
         peaks = _peaks()
@@ -491,7 +492,9 @@ def main():
     ap.add_argument("--impl", default="svb", choices=["svb", "reference"])
     ap.add_argument("--images", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--cpu-images", type=int, default=8, help="images per step of the CPU reference sample")
-    ap.add_argument("--no-ie", action="store_true", help="skip the indirect-effect section")
+    ap.add_argument("--no-ie", action="store_true", help="skip the indirect-effect and GatedSae sections")
+    ap.add_argument("--gated-dp", action="store_true",
+                    help="N > 1: also time the data-parallel GatedSae step (configs[2]) and report it under 'gated'")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "svb":
         args.warmup = 3
