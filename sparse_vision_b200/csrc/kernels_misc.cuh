@@ -150,7 +150,11 @@ template <int VEC> struct Row8<float, VEC> {
 };
 
 // NCHW [B,C,HW] (bf16 or fp32) -> bf16 tokens [B*HW, C]; sae_mlp.py:44 'b c h w -> (b h w) c'.
-// grid (ceil(HW/64), ceil(C/64), B), 256 threads; bf16 staged in smem with a 2-element row pad.
+// grid (ceil(HW/64), ceil(C/64), B), 256 threads.  A thread reads 8 positions of TWO neighbouring channels, interleaves
+// them into 8 words (channel pair of one position each) and stores those into a [64 positions][32 channel pairs] tile
+// whose 16-byte groups are XOR-swizzled by the position octet, so that both the 4-byte writes and the 16-byte reads of
+// the second phase (8 channels of one position = one output store) are bank-conflict free.  (The first version
+// gathered 8 two-byte values per output store and was issue- / LSU-bound at 52 us; profiles/r01g.)
 // slab_rows > 0: write the slab-major layout [ceil(C/64)][slab_rows = B*HW][64] (gemm_host.cuh) instead of [B*HW, C];
 // the padding columns of the last slab (C % 64 != 0) are written as zeros.
 // xpart != null: also emit, per image, HW tile and channel, the statistics of the bf16-rounded x that the loss
@@ -159,55 +163,71 @@ template <typename TIn, int VEC>
 static __global__ void __launch_bounds__(256)
 pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, int HW, long long slab_rows,
                       float* __restrict__ xpart) {
-  __shared__ uint16_t tile[64][66];  // [c][hw]
+  __shared__ __align__(16) uint32_t tile[64][32];  // [position][channel pair], groups of 4 words swizzled
   const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const TIn* xb = x + static_cast<size_t>(b) * C * HW;
+  {
+    const int c2 = threadIdx.x >> 3, oct = threadIdx.x & 7, po = oct * 8;
+    const int ch = c0 + 2 * c2;                      // C is even: ch < C <=> ch + 1 < C
+    const int nv = ch < C ? max(0, min(8, HW - (p0 + po))) : 0;
+    uint32_t w[8];                                   // w[k] = (x[ch][po + k], x[ch + 1][po + k]) as bf16 pairs
+    if (sizeof(TIn) == 2 && VEC == 8) {              // bf16, 16-byte aligned rows: no conversion at all
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+      if (nv > 0) {
+        q0 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(ch) * HW + p0 + po));
+        q1 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(ch + 1) * HW + p0 + po));
+      }
+      w[0] = __byte_perm(q0.x, q1.x, 0x5410); w[1] = __byte_perm(q0.x, q1.x, 0x7632);
+      w[2] = __byte_perm(q0.y, q1.y, 0x5410); w[3] = __byte_perm(q0.y, q1.y, 0x7632);
+      w[4] = __byte_perm(q0.z, q1.z, 0x5410); w[5] = __byte_perm(q0.z, q1.z, 0x7632);
+      w[6] = __byte_perm(q0.w, q1.w, 0x5410); w[7] = __byte_perm(q0.w, q1.w, 0x7632);
+    } else {
+      float v0[8], v1[8];
+      Row8<TIn, VEC>::load(xb + static_cast<size_t>(ch) * HW + p0 + po, nv, v0);
+      Row8<TIn, VEC>::load(xb + static_cast<size_t>(ch + 1) * HW + p0 + po, nv, v1);
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int i = threadIdx.x + 256 * it;
-    const int c = i >> 3, po = (i & 7) * 8;
-    float v[8];
-    const int nv = (c0 + c < C) ? max(0, min(8, HW - (p0 + po))) : 0;
-    Row8<TIn, VEC>::load(xb + static_cast<size_t>(c0 + c) * HW + p0 + po, nv, v);
-    uint32_t w[4];
+      for (int k = 0; k < 8; ++k) w[k] = pack_bf16x2(v0[k], v1[k]);
+    }
+    const int col = (((c2 >> 2) ^ oct) << 2) | (c2 & 3);   // (po + k) >> 3 == oct for every k
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[c][po]);
+    for (int k = 0; k < 8; ++k) tile[po + k][col] = w[k];
+    if (xpart) {  // the 8 lanes that share the channel pair combine their 8 positions each (fixed butterfly order)
+      float s0 = 0.f, q0 = 0.f, mn0 = INFINITY, mx0 = -INFINITY, s1 = 0.f, q1 = 0.f, mn1 = INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = w[k];
-    if (xpart) {  // the 8 lanes that share channel c combine their 8 positions each (fixed butterfly order)
-      float sx = 0.f, sx2 = 0.f, mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float lo = bf16lo(w[k]), hi = bf16hi(w[k]);
-        if (2 * k < nv) { sx += lo; sx2 += lo * lo; mn = fminf(mn, lo); mx = fmaxf(mx, lo); }
-        if (2 * k + 1 < nv) { sx += hi; sx2 += hi * hi; mn = fminf(mn, hi); mx = fmaxf(mx, hi); }
+      for (int k = 0; k < 8; ++k) {
+        if (k < nv) {
+          const float lo = bf16lo(w[k]), hi = bf16hi(w[k]);
+          s0 += lo; q0 += lo * lo; mn0 = fminf(mn0, lo); mx0 = fmaxf(mx0, lo);
+          s1 += hi; q1 += hi * hi; mn1 = fminf(mn1, hi); mx1 = fmaxf(mx1, hi);
+        }
       }
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sx2 += __shfl_xor_sync(0xffffffffu, sx2, o);
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+        mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
       }
-      if ((threadIdx.x & 7) == 0 && c0 + c < C) {
-        float* o = xpart + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 4 * C + c0 + c;
-        o[0] = sx; o[C] = sx2; o[2 * C] = mn; o[3 * C] = mx;
+      if (oct == 0 && ch < C) {
+        float* o = xpart + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 4 * C + ch;
+        *reinterpret_cast<float2*>(o) = make_float2(s0, s1);
+        *reinterpret_cast<float2*>(o + C) = make_float2(q0, q1);
+        *reinterpret_cast<float2*>(o + 2 * C) = make_float2(mn0, mn1);
+        *reinterpret_cast<float2*>(o + 3 * C) = make_float2(mx0, mx1);
       }
     }
   }
   __syncthreads();
   uint16_t* ob = reinterpret_cast<uint16_t*>(out);
-  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
-    const int p = i >> 3, co = (i & 7) * 8;
-    if (p0 + p < HW && (c0 + co < C || slab_rows > 0)) {   // tile rows of channels >= C hold zeros
-      uint32_t w[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        w[k] = static_cast<uint32_t>(tile[co + 2 * k][p]) | (static_cast<uint32_t>(tile[co + 2 * k + 1][p]) << 16);
+  for (int it = 0; it < 2; ++it) {
+    const int j = threadIdx.x + 256 * it;
+    const int p = j >> 3, g = j & 7, co = g * 8;    // 8 channels of one position: one 16-byte group of the tile row
+    if (p0 + p < HW && (c0 + co < C || slab_rows > 0)) {   // tile rows of channels >= C hold zeros
+      const uint4 q = *reinterpret_cast<const uint4*>(&tile[p][(g ^ (p >> 3)) << 2]);
       const size_t t = static_cast<size_t>(b) * HW + p0 + p;
       const size_t off = slab_rows > 0 ? (static_cast<size_t>(blockIdx.y) * slab_rows + t) * 64 + co : t * C + c0 + co;
-      *reinterpret_cast<uint4*>(ob + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(ob + off) = q;
     }
   }
 }
