@@ -20,6 +20,9 @@ struct GatedPlan {
   uint32_t *act_bits, *mask_e, *mask_rp, *cnt_part;
   int cnt_chunks;
   bool es;  // slab-major E / relu_pi / A' (F % 64 == 0), see gemm_host.cuh
+  bool xs, fused_dec;   // slab-major X / DIFF and the fused NCHW decoder epilogue, as in svb_sae.cu
+  int nt_hw;
+  float *xpart, *dpart;
   size_t o_gwg, o_gbg, o_gbm, o_gr, o_gwd, o_gbd, o_sums, o_chansq, o_count, o_max, sum_elems, max_elems;
 };
 
@@ -35,7 +38,9 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
   p.es = F % 64 == 0;
-  const size_t TC = static_cast<size_t>(p.T) * p.C, TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
+  p.xs = false; p.fused_dec = false;
+  // X / D / DIFF may be slab-major with a zero-padded last slab (C % 64 != 0): size them for ceil(C / 64) slabs
+  const size_t TC = static_cast<size_t>(p.T) * (cdiv(p.C, 64) * 64) + 8 * static_cast<size_t>(p.C), TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
   p.Wgb = a.take<bf16>(FC);
   p.Wdb = a.take<bf16>(FC);
@@ -72,6 +77,9 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.P_wg = a.take<float>(static_cast<size_t>(p.s_wg) * FC);
   p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
   p.nact_f = a.take<float>(p.n_img);
+  p.nt_hw = cdiv(p.hw, 64);
+  p.xpart = a.take<float>(static_cast<size_t>(p.n_img) * p.nt_hw * 4 * p.C);
+  p.dpart = a.take<float>(static_cast<size_t>(p.tiles_m) * 4 * 2 * 3 * p.C);
   p.o_gwg = 0; p.o_gbg = FC; p.o_gbm = FC + F; p.o_gr = FC + 2 * static_cast<size_t>(F);
   p.o_gwd = FC + 3 * static_cast<size_t>(F);
   p.o_gbd = 2 * FC + 3 * static_cast<size_t>(F);
@@ -227,10 +235,21 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
   prof_begin_step(h);   // phases as in svb_sae.cu; "dec_gemm" covers the decoder and the via_gate GEMM
   prof_mark(h, st, 0);
+  // slab-major X / DIFF + fused NCHW decoder epilogue under the same conditions as svb_sae_step_grads
+  void* dec_out = out ? out->dec_out : nullptr;
+  const bool slab_ok = !pl.zero_copy_x && post_dec_fusable(x, dec_out, out ? out->dec_layout : SVB_NCHW);
+  pl.fused_dec = slab_ok && pl.hw >= 32;
+  pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
+  int out_kind = 0;
+  if (dec_out)
+    out_kind = pl.hw % 4 != 0 ? 4
+               : out->dec_dtype == SVB_F32 ? 3
+               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 2;
+  const long long ld_t = (pl.T + 7) & ~7LL;
   // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
   SVB_TRY(side_fork(h, st));
   SVB_TRY(run_prep(h->side, pl, p, true));
-  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X));
+  if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs, pl.fused_dec ? pl.xpart : nullptr));
   SVB_TRY(side_join(h, st));
 
   prof_mark(h, st, 1);
@@ -242,23 +261,48 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   if (pl.es ? (make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) || make_store_tmap_bf16_slab(&e1.tm_rp, pl.RP, T, F))
             : (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F) || make_store_tmap_bf16(&e1.tm_rp, pl.RP, T, F, F)))
     return fail(SVB_ERR_TMAP, "tensor maps for E / relu_pi");
-  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1)), "gated enc");
+  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "gated enc");
   prof_mark(h, st, 2);
   // per-image activity bits of e from its 1-bit mask: side stream, beside the decoder GEMM
   SVB_TRY(side_fork(h, st));
   (mask_to_activity_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(pl.words, 4)), 128, 0, h->side>>>(
       pl.mask_e, pl.act_bits, pl.T, pl.hw, pl.words), svb::count_launch());
-  EpiDec::Params e2{};
-  e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
-  if (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C))
-    return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
   EpiDec::Params e2v{};
-  e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part;   // via_gate: aux loss value only
-  // statistics + NCHW write-back of d only feed the end of the step: side stream, beside the via / dE GEMMs
-  SVB_TRY(side_fork(h, st));
-  SVB_TRY(run_post_dec(h->side, x, X, pl.D, pl.T, out ? out->dec_out : nullptr, out ? out->dec_dtype : SVB_BF16,
-                       out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar));
+  e2v.bias = p->b_dec; e2v.x = X; e2v.sq_partial = pl.aux_part; e2v.x_slab = pl.xs;   // via_gate: aux loss value only
+  if (pl.fused_dec) {
+    // decoder epilogue writes NCHW d, DIFF (slab-major) and the per-image channel statistics itself (EpiDecNchw)
+    EpiDecNchw::Params e2{};
+    e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
+    e2.out = dec_out; e2.out_kind = out_kind;
+    if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
+    if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
+    if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
+    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
+    // the statistics folds (and the scatter of a channel-major d) only feed the end of the step: side stream
+    SVB_TRY(side_fork(h, st));
+    if (out_kind == 4) {
+      const dim3 grid(static_cast<unsigned>(cdiv(pl.T, 1024)), C);
+      if (out->dec_dtype == SVB_F32)
+        (cmajor_to_nchw_kernel<float><<<grid, 256, 0, h->side>>>(pl.D, static_cast<float*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
+      else
+        (cmajor_to_nchw_kernel<bf16><<<grid, 256, 0, h->side>>>(pl.D, static_cast<bf16*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
+    }
+    (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, h->side>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
+    (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, h->side>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
+    SVB_LAUNCH_CHECK("decoder statistics");
+  } else {
+    EpiDec::Params e2{};
+    e2.bias = p->b_dec; e2.x = X; e2.d_bf16 = pl.D; e2.diff_bf16 = pl.DIFF; e2.sq_partial = pl.sq_part;
+    e2.out_slab = pl.xs; e2.x_slab = pl.xs;
+    if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
+              : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
+      return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
+    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
+    // statistics + NCHW write-back of d only feed the end of the step: side stream, beside the via / dE GEMMs
+    SVB_TRY(side_fork(h, st));
+    SVB_TRY(run_post_dec(h->side, x, X, pl.D, pl.T, dec_out, out ? out->dec_dtype : SVB_BF16,
+                         out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
+  }
   SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
   prof_mark(h, st, 3);
   prof_mark(h, st, 4);
@@ -269,7 +313,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.block_n = 256; e3.slab_major = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_a, pl.A, T, F) : make_store_tmap_bf16(&e3.tm_a, pl.A, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for A'");
-  SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3)), "gated dE");
+  SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "gated dE");
   prof_mark(h, st, 5);
   // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
   // decoder weight-gradient GEMM runs (svb_set_comm_stream).
@@ -277,7 +321,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
   EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, false)), "dW_gate");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_gate");
   // reductions + gate-side assembly + tail on the side stream, beside the dW_dec GEMM
   SVB_TRY(side_fork(h, st));
   cudaStream_t ss = h->side;
@@ -303,12 +347,12 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 8;
   ta.aux_part = pl.aux_part; ta.n_aux = pl.sms * 8;
   ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
-  ta.var_part = pl.var_part; ta.n_var_part = cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
+  ta.var_part = pl.var_part; ta.n_var_part = pl.fused_dec ? cdiv(C, 32) : cdiv(C, 8); ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;
   ta.flat = flat; ta.o_sums = pl.o_sums; ta.o_chansq = pl.o_chansq; ta.o_max = pl.o_max; ta.C = C;
   (grads_tail_kernel<<<1, 1024, 0, ss>>>(ta), svb::count_launch());
   prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, false, pl.es)), "dW_dec");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
   prof_mark(h, st, 7);
   SVB_TRY(side_join(h, st));
   SVB_TRY(run_assemble(st, aa, 2));
