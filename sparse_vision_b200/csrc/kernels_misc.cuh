@@ -233,22 +233,28 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
 }
 
 // Channel-major decoder output [C][ld] (tokens t = b*HW + p contiguous per channel) -> the caller's NCHW tensor
-// [B, C, HW]: every image's HW-long run of a channel is copied as it is.  grid (ceil(T / 1024), C), 256 threads x 4.
-template <typename TOut>
+// [B, C, HW]: every image's HW-long run of a channel is copied as it is.  grid (ceil(T / (1024 * VEC)), C), 256 threads,
+// 4 pieces of VEC elements per thread; VEC = 4 needs HW % 4 == 0 (a piece never straddles two images) and an 8-byte
+// aligned bf16 output.
+template <typename TOut, int VEC>
 static __global__ void __launch_bounds__(256)
 cmajor_to_nchw_kernel(const bf16* __restrict__ dt, TOut* __restrict__ out, int C, int HW, long long T, long long ld) {
   const int c = blockIdx.y;
   const uint16_t* src = reinterpret_cast<const uint16_t*>(dt) + static_cast<size_t>(c) * ld;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const long long t = blockIdx.x * 1024LL + k * 256 + threadIdx.x;
+    const long long t = (blockIdx.x * 1024LL + k * 256 + threadIdx.x) * VEC;
     if (t < T) {
       const long long b = t / HW;
       const int p = static_cast<int>(t - b * HW);
       const size_t o = (static_cast<size_t>(b) * C + c) * HW + p;
-      const uint16_t h = src[t];
-      if (sizeof(TOut) == 2) reinterpret_cast<uint16_t*>(out)[o] = h;
-      else reinterpret_cast<float*>(out)[o] = __uint_as_float(static_cast<uint32_t>(h) << 16);
+      if (VEC == 4) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + o) = *reinterpret_cast<const uint2*>(src + t);
+      } else {
+        const uint16_t h = src[t];
+        if (sizeof(TOut) == 2) reinterpret_cast<uint16_t*>(out)[o] = h;
+        else reinterpret_cast<float*>(out)[o] = __uint_as_float(static_cast<uint32_t>(h) << 16);
+      }
     }
   }
 }

@@ -380,6 +380,19 @@ inline int run_adam_multi(cudaStream_t st, const AdamSeg* segs, int nseg, const 
 inline void launch_cadam(cudaStream_t st, float* w, float* g, float* m, float* v, int C, int F, const AdamCoef& k) {
   (constrained_adam_decoder_kernel<<<cdiv(F, kCadamCols), kCadamCols * kCadamRows, 0, st>>>(w, g, m, v, C, F, k), svb::count_launch());
 }
+// Scatter of the channel-major copy of d (EpiDecNchw out_kind 4) into the caller's NCHW tensor
+inline int run_cmajor_to_nchw(cudaStream_t st, const bf16* dt, void* out, int out_dtype, int C, int hw, long long T,
+                              long long ld) {
+  if (out_dtype == SVB_F32) {
+    (cmajor_to_nchw_kernel<float, 1><<<dim3(static_cast<unsigned>(cdiv(T, 1024)), C), 256, 0, st>>>(dt, static_cast<float*>(out), C, hw, T, ld), svb::count_launch());
+  } else if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    (cmajor_to_nchw_kernel<bf16, 4><<<dim3(static_cast<unsigned>(cdiv(T, 4096)), C), 256, 0, st>>>(dt, static_cast<bf16*>(out), C, hw, T, ld), svb::count_launch());
+  } else {
+    (cmajor_to_nchw_kernel<bf16, 1><<<dim3(static_cast<unsigned>(cdiv(T, 1024)), C), 256, 0, st>>>(dt, static_cast<bf16*>(out), C, hw, T, ld), svb::count_launch());
+  }
+  SVB_LAUNCH_CHECK("cmajor_to_nchw");
+  return 0;
+}
 // Rows of EpiDPre's per-CTA column-sum partials for a B-stationary launch (mirrors launch_gemm's grid choice).
 inline int bstat_groups(int sms, int tiles_n, int tiles_m) {
   int groups = sms / tiles_n;

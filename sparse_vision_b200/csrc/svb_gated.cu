@@ -242,9 +242,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
   int out_kind = 0;
   if (dec_out)
-    out_kind = pl.hw % 4 != 0 ? 4
-               : out->dec_dtype == SVB_F32 ? 3
-               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 2;
+    out_kind = out->dec_dtype == SVB_F32 ? (pl.hw % 4 == 0 ? 3 : 4)
+               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;
   // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
   SVB_TRY(side_fork(h, st));
@@ -280,13 +279,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
     SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
     // the statistics folds (and the scatter of a channel-major d) only feed the end of the step: side stream
     SVB_TRY(side_fork(h, st));
-    if (out_kind == 4) {
-      const dim3 grid(static_cast<unsigned>(cdiv(pl.T, 1024)), C);
-      if (out->dec_dtype == SVB_F32)
-        (cmajor_to_nchw_kernel<float><<<grid, 256, 0, h->side>>>(pl.D, static_cast<float*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
-      else
-        (cmajor_to_nchw_kernel<bf16><<<grid, 256, 0, h->side>>>(pl.D, static_cast<bf16*>(dec_out), C, pl.hw, pl.T, ld_t), svb::count_launch());
-    }
+    if (out_kind == 4) SVB_TRY(run_cmajor_to_nchw(h->side, pl.D, dec_out, out->dec_dtype, C, pl.hw, pl.T, ld_t));
     (dec_stats_image_kernel<<<dim3(static_cast<unsigned>(pl.n_img), cdiv(C, 64)), 256, 0, h->side>>>(pl.dpart, pl.xpart, pl.st, C, pl.hw, pl.nt_hw, pl.T), svb::count_launch());
     (dec_stats_channel_kernel<<<cdiv(C, 32), 1024, 0, h->side>>>(pl.st, pl.chan, pl.var_part, static_cast<int>(pl.n_img), C), svb::count_launch());
     SVB_LAUNCH_CHECK("decoder statistics");
