@@ -537,12 +537,11 @@ struct EpiDecNchw {
     const __nv_bfloat16* x;           // slab-major [M, N] targets (the SAE input)
     float* sq_partial;                // [gridDim.x * kWarps]: one running sum per CTA and epilogue warp
     float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_image_kernel
-    void* out;                        // the caller's NCHW output tensor (null: d is not handed back)
+    void* out;                        // out_kind 1: the caller's NCHW bf16 tensor (second-image pieces of straddling warps)
     int hw;                           // tokens per image (>= 32)
     int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base);
-                                      // 3: fp32 with plain 16-byte stores from the staged tile (HW % 4 == 0);
                                       // 4: tm_out is a channel-major [C][T] workspace (make_store_tmap_bf16_cmajor)
-                                      //    that a copy kernel turns into the caller's tensor
+                                      //    that a copy kernel turns into the caller's tensor (any HW, bf16 or fp32)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -656,30 +655,12 @@ struct EpiDecNchw {
     }
     // (3) d back to NCHW.  out_kind 1: one TMA store for the positions of image b0 (clipped at the image end); the
     // positions of a second image in a straddling warp (n0, n1 multiples of 8 there) are copied with 16-byte stores.
-    // out_kind 3 (fp32 outputs): every lane writes its channel's tokens from the staged tile itself, one image segment
-    // after the other.  out_kind 4: one TMA store into the channel-major workspace.
+    // out_kind 4: one TMA store into the channel-major workspace.
     if (p.out_kind == 1) {
       if (n1 > 0 && col_ok) {
         const uint4* src = reinterpret_cast<const uint4*>(tbuf + lane * 64 + n0 * 2);
         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (static_cast<size_t>(b0 + 1) * g.N + col) * p.hw);
         for (int q = 0; q < (n1 >> 3); ++q) dst[q] = src[q];
-      }
-    } else if (p.out_kind == 3 && col_ok) {
-      const uint16_t* src = reinterpret_cast<const uint16_t*>(tbuf + lane * 64);
-      const int hw0 = row0 - b0 * p.hw;
-#pragma unroll
-      for (int seg = 0; seg < 2; ++seg) {
-        const int cnt = seg == 0 ? n0 : n1, first = seg == 0 ? 0 : n0;
-        if (cnt <= 0) continue;
-        float* dst = static_cast<float*>(p.out) + (static_cast<size_t>(b0 + seg) * g.N + col) * p.hw + (seg == 0 ? hw0 : 0);
-        if (((reinterpret_cast<uintptr_t>(dst) & 15) | (first & 3) | (cnt & 3)) == 0) {
-          for (int i = 0; i < cnt; i += 4) {
-            const uint2 w = *reinterpret_cast<const uint2*>(src + first + i);
-            *reinterpret_cast<float4*>(dst + i) = make_float4(bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y));
-          }
-        } else {
-          for (int i = 0; i < cnt; ++i) dst[i] = __uint_as_float(static_cast<uint32_t>(src[first + i]) << 16);
-        }
       }
     }
     // (4) asynchronous stores of both tiles

@@ -235,7 +235,7 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
 // Channel-major decoder output [C][ld] (tokens t = b*HW + p contiguous per channel) -> the caller's NCHW tensor
 // [B, C, HW]: every image's HW-long run of a channel is copied as it is.  grid (ceil(T / (1024 * VEC)), C), 256 threads,
 // 4 pieces of VEC elements per thread; VEC = 4 needs HW % 4 == 0 (a piece never straddles two images) and an 8-byte
-// aligned bf16 output.
+// (bf16) / 16-byte (fp32) aligned output.
 template <typename TOut, int VEC>
 static __global__ void __launch_bounds__(256)
 cmajor_to_nchw_kernel(const bf16* __restrict__ dt, TOut* __restrict__ out, int C, int HW, long long T, long long ld) {
@@ -249,7 +249,9 @@ cmajor_to_nchw_kernel(const bf16* __restrict__ dt, TOut* __restrict__ out, int C
       const int p = static_cast<int>(t - b * HW);
       const size_t o = (static_cast<size_t>(b) * C + c) * HW + p;
       if (VEC == 4) {
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + o) = *reinterpret_cast<const uint2*>(src + t);
+        const uint2 w = *reinterpret_cast<const uint2*>(src + t);
+        if (sizeof(TOut) == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + o) = w;
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y));
       } else {
         const uint16_t h = src[t];
         if (sizeof(TOut) == 2) reinterpret_cast<uint16_t*>(out)[o] = h;

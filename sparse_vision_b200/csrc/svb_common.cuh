@@ -383,7 +383,9 @@ inline void launch_cadam(cudaStream_t st, float* w, float* g, float* m, float* v
 // Scatter of the channel-major copy of d (EpiDecNchw out_kind 4) into the caller's NCHW tensor
 inline int run_cmajor_to_nchw(cudaStream_t st, const bf16* dt, void* out, int out_dtype, int C, int hw, long long T,
                               long long ld) {
-  if (out_dtype == SVB_F32) {
+  if (out_dtype == SVB_F32 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    (cmajor_to_nchw_kernel<float, 4><<<dim3(static_cast<unsigned>(cdiv(T, 4096)), C), 256, 0, st>>>(dt, static_cast<float*>(out), C, hw, T, ld), svb::count_launch());
+  } else if (out_dtype == SVB_F32) {
     (cmajor_to_nchw_kernel<float, 1><<<dim3(static_cast<unsigned>(cdiv(T, 1024)), C), 256, 0, st>>>(dt, static_cast<float*>(out), C, hw, T, ld), svb::count_launch());
   } else if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
     (cmajor_to_nchw_kernel<bf16, 4><<<dim3(static_cast<unsigned>(cdiv(T, 4096)), C), 256, 0, st>>>(dt, static_cast<bf16*>(out), C, hw, T, ld), svb::count_launch());

@@ -242,8 +242,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
   int out_kind = 0;
   if (dec_out)
-    out_kind = out->dec_dtype == SVB_F32 ? (pl.hw % 4 == 0 ? 3 : 4)
-               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
+    out_kind = (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;
   // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
   SVB_TRY(side_fork(h, st));

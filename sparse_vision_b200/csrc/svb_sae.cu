@@ -183,17 +183,16 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   const bool slab_ok = !pl.zero_copy_x && post_dec_fusable(x, out ? out->dec_out : nullptr, out ? out->dec_layout : SVB_NCHW);
   // Fused decoder epilogue: needs the slab-major path and >= 32 tokens per image (a warp's 32 tokens then touch at
   // most two images).  bf16 d goes back to the caller's NCHW tensor by TMA when that can address it (16-byte row pitch:
-  // HW % 8 == 0); other bf16 outputs (14x14, 7x7 maps) leave as a channel-major TMA copy that a small kernel scatters
-  // into the NCHW tensor beside the dE GEMM (measured faster than 8-byte stores from the epilogue: mixed4a 0.63 ->
-  // 0.60 ms); fp32 outputs are written by 16-byte stores from the staged tiles (HW % 4 == 0) or through the same copy.
+  // HW % 8 == 0); every other output (14x14 / 7x7 maps, fp32) leaves as a channel-major bf16 TMA copy that a small
+  // vectorised kernel scatters / widens into the NCHW tensor beside the dE GEMM -- measured faster than 8- / 16-byte
+  // stores from the epilogue warps (same box: mixed4a 0.63 -> 0.60 ms bf16, mixed3b fp32 2.00 -> 1.95 ms).
   void* dec_out = out ? out->dec_out : nullptr;
   pl.fused_dec = slab_ok && pl.hw >= 32;
   // C % 64 != 0 (mixed3b: 480, mixed4d: 528): only the fused epilogue keeps the last slab's padding columns zero
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
   int out_kind = 0;
   if (dec_out)
-    out_kind = out->dec_dtype == SVB_F32 ? (pl.hw % 4 == 0 ? 3 : 4)
-               : (pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
+    out_kind = (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;   // row pitch of the channel-major copy (out_kind 4)
   prof_begin_step(h);
   prof_mark(h, st, 0);
