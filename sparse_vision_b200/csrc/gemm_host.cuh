@@ -145,6 +145,11 @@ inline int make_store_tmap_bf16_cmajor(CUtensorMap* out, void* ptr, uint64_t C, 
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
 inline int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -204,10 +209,13 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
 
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, Epi, BSTAT>;
   const uint32_t smem = Cfg::kSmemBytes;
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device: a process that drives several GPUs must set it on each of them
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return -4;
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -4;
-    configured = true;
+    configured[dev] = true;
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
   int grid = num_tiles < sms ? num_tiles : sms;
@@ -254,10 +262,12 @@ int launch_gemm2_bstat(cudaStream_t stream, const void* A, int64_t lda, const vo
   const int groups = gemm2_groups(M, N, max_ctas);
   if (groups < 1) return -5;
   auto kern = gemm2_bstat_kernel<B_MN, Epi>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return -4;
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -4;
-    configured = true;
+    configured[dev] = true;
   }
   (kern<<<2 * p.tiles_n * groups, 64 + Epi::kWarps * 32, Cfg::kSmemBytes, stream>>>(tmA, tmB, p, ep), svb::count_launch());
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
