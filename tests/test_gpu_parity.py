@@ -383,3 +383,45 @@ def test_full_size_cfg2_step_properties():
     l1 = enc.float().abs().mean().item()
     assert abs(sc1["l1"] - l1) <= 1e-2 * l1
     assert abs(sc1["loss"] - (sc1["rec"] + 5.0 * sc1["l1"])) <= 1e-5 * sc1["loss"]
+
+
+def test_full_size_cfg3_gated_step_properties():
+    """BASELINE configs[2] at its FULL per-GPU size (GatedSae, 256 images, C=512, 14x14, F=8192): bit-reproducibility
+    and the step's scalars against what the forward API's tensors imply (losses/sparse_loss.py:68-76,
+    utils.py:2455-2473), plus the dead-unit mask against the encoder output (utils.py:2032-2069)."""
+    ops = _ops()
+    B, C, H, W, k = 256, 512, 14, 14, 16
+    F = C * k
+    lam = 0.1
+    torch.manual_seed(0)
+    p = O.init_gated_sae(C, k)
+    planted = torch.randperm(F, generator=torch.Generator().manual_seed(1))[:F // 20]
+    p["b_gate"][planted] = -50.0
+    p["b_mag"][planted] = -50.0
+    x = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5))).bfloat16().cuda()
+
+    def run():
+        params = [p[key].clone().cuda() for key in O.GATED_KEYS]
+        ms = [torch.zeros_like(q) for q in params]
+        vs = [torch.zeros_like(q) for q in params]
+        res = ops.gated_train_step(x, params, ms, vs, 1, 1e-3, lam, k, optimizer="constrained_adam")
+        return params, res.scalars(), res.dec.clone(), res.dead.clone()
+
+    params1, sc1, dec1, dead1 = run()
+    params2, sc2, dec2, dead2 = run()
+    assert sc1 == sc2 and torch.equal(dec1, dec2) and torch.equal(dead1, dead2)          # bit-reproducible
+    for a, b in zip(params1, params2):
+        assert torch.equal(a, b)
+    xf = x.float()
+    rec = ((dec1.float() - xf) ** 2).mean().item()
+    assert abs(sc1["rec"] - rec) <= 1e-2 * rec
+    enc, dec_f, rp, via = ops.gated_forward(x, *[p[key].clone().cuda() for key in O.GATED_KEYS], out_dtype=torch.bfloat16)
+    x_tok = xf.permute(0, 2, 3, 1).reshape(-1, C)
+    l1 = rp.float().abs().mean().item()
+    aux = ((via.float() - x_tok) ** 2).mean().item()
+    assert abs(sc1["l1"] - l1) <= 1e-2 * l1
+    assert abs(sc1["aux"] - aux) <= 1e-2 * aux
+    assert abs(sc1["loss"] - (sc1["rec"] + lam * sc1["l1"] + sc1["aux"])) <= 1e-5 * sc1["loss"]
+    active = (enc.reshape(B, H * W, F) != 0).any(dim=1).any(dim=0)
+    assert torch.equal(dead1.bool(), ~active)
+    assert int(sc1["n_dead"]) == int((~active).sum().item()) >= F // 20
