@@ -425,3 +425,47 @@ def test_full_size_cfg3_gated_step_properties():
     active = (enc.reshape(B, H * W, F) != 0).any(dim=1).any(dim=0)
     assert torch.equal(dead1.bool(), ~active)
     assert int(sc1["n_dead"]) == int((~active).sum().item()) >= F // 20
+
+
+@pytest.mark.parametrize("B,C,H,W,k", [
+    (1, 24, 5, 7, 3),       # F = 72: ragged N tiles, row-major chunks
+    (3, 40, 6, 6, 5),       # F = 200
+    (2, 480, 28, 28, 4),    # mixed3b: K = 480
+    (9, 832, 7, 7, 4),      # mixed5a
+])
+@pytest.mark.parametrize("kind", ["sae_mlp", "gated_sae"])
+def test_forward_api_shapes_vs_oracle(B, C, H, W, k, kind):
+    """svb_sae_forward / svb_gated_forward (what SaeMLP.forward / GatedSae.forward and the attribution pass call) on
+    NCHW and token inputs, fp32 and bf16 outputs, against the oracle's forward."""
+    ops = _ops()
+    torch.manual_seed(0)
+    keys = O.SAE_MLP_KEYS if kind == "sae_mlp" else O.GATED_KEYS
+    p = O.init_sae_mlp(C, k) if kind == "sae_mlp" else O.init_gated_sae(C, k)
+    p["decoder.bias"].normal_(0, 0.05, generator=torch.Generator().manual_seed(2))
+    if kind == "gated_sae":
+        p["r_mag"].normal_(0, 0.1, generator=torch.Generator().manual_seed(3))
+        p["b_mag"].normal_(0, 0.05, generator=torch.Generator().manual_seed(4))
+    x = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(9))).bfloat16().float()
+    want = O.sae_mlp_forward(p, x) if kind == "sae_mlp" else O.gated_forward(p, x)
+    params = [p[key].clone().cuda() for key in keys]
+    fwd = ops.sae_forward if kind == "sae_mlp" else ops.gated_forward
+    x_tok = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    near_tie = None
+    if kind == "gated_sae":
+        pi = torch.nn.functional.linear(x_tok - p["decoder.bias"], p["W_gate"], p["b_gate"])
+        near_tie = (pi.abs() < 2e-2 * pi.std()).numpy()
+        assert near_tie.mean() < 0.05
+    for xin, dt in ((x.cuda(), torch.float32), (x.cuda().bfloat16(), torch.bfloat16), (x_tok.cuda().bfloat16(), torch.float32)):
+        got = fwd(xin, *params, out_dtype=dt)
+        names = ("enc", "dec", "pre") if kind == "sae_mlp" else ("enc", "dec", "relu_pi", "via")
+        for a, b, nm in zip(got, want, names):
+            if a is None:
+                continue
+            assert a.dtype == (torch.float32 if nm == "pre" else dt) and tuple(a.shape) == tuple(b.shape), nm
+            tol = (2 if nm in ("dec", "via") else 1) * REL * (2 if dt == torch.bfloat16 else 1)
+            an, bn = a.float().cpu().numpy(), b.numpy()
+            if kind == "gated_sae" and nm == "enc":
+                # a gated unit whose pi is within bf16 rounding of zero flips its gate and the whole magnitude appears
+                # or vanishes (heaviside, gated_sae.py:39): such near-ties are taken out of the element-wise comparison
+                an, bn = np.where(near_tie, 0.0, an), np.where(near_tie, 0.0, bn)
+            assert _relerr(an, bn) < tol, (nm, str(dt))
