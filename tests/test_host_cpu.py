@@ -215,3 +215,35 @@ def test_get_specific_sae_model_loads_reference_format_checkpoint(tmp_path):
     assert all(not p.requires_grad for p in sae.parameters())
     for a, b in zip(sae.state_dict().values(), src.state_dict().values()):
         assert torch.equal(a, b)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py must have the size and field offsets gcc gives the structs of include/svb.h (the
+    header is plain C: this also checks that it compiles as C, which is what a cgo / FFI binding would do)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from sparse_vision_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"svb_acts": L.Acts, "svb_sae_params": L.SaeParams, "svb_gated_params": L.GatedParams,
+             "svb_adam_state": L.AdamState, "svb_opt_config": L.OptConfig, "svb_activity_out": L.ActivityOut,
+             "svb_train_out": L.TrainOut, "svb_sae_forward_out": L.SaeForwardOut,
+             "svb_gated_forward_out": L.GatedForwardOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svb.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("SVB_STATS_LEN %d\\n", (int)SVB_STATS_LEN);', '  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    assert int(out["SVB_STATS_LEN"]) == L.STATS_LEN
