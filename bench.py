@@ -414,7 +414,12 @@ def run_svb(args):
 
     # configs[2] (GatedSae, quoted on 2/4/8 GPUs) rides along: collective at N > 1, so every rank runs it
     # (at N > 1 only on request: a failed collective there must never cost the main line)
-    gated = gated_section(dev, _peaks(), world=world) if (not args.no_ie and (world == 1 or args.gated_dp)) else None
+    gated = None
+    if not args.no_ie and (world == 1 or args.gated_dp):
+        try:
+            gated = gated_section(dev, _peaks(), world=world)
+        except Exception as exc:       # a failure of a side section must never cost the main line
+            gated = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         peaks = _peaks()
@@ -452,7 +457,10 @@ def run_svb(args):
             "final_step_stats": {k: last_stats[k] for k in ("loss", "rec", "l1", "n_dead")},
         }
         if world == 1 and not args.no_ie:
-            line["ie"] = ie_section(dev, peaks)
+            try:
+                line["ie"] = ie_section(dev, peaks)
+            except Exception as exc:
+                line["ie"] = {"error": f"{type(exc).__name__}: {exc}"}
         if gated is not None:
             line["gated"] = gated
         if cpu_v is not None:
