@@ -226,7 +226,7 @@ def test_adam_step_and_reinit(golden_dir):
     (3, 528, 14, 14, 4, "sae_mlp"),      # C not a multiple of 64/128/256 (K and N tails)
     (3, 64, 12, 12, 4, "sae_mlp"),       # fused NCHW decoder epilogue: 144-pixel images straddle warps, ragged last tile
     (5, 128, 8, 8, 8, "sae_mlp"),        # fused path with two images per 128-token tile
-    (4, 128, 14, 14, 4, "sae_mlp"),      # fused path, 196-pixel maps: rows TMA cannot address -> plain NCHW stores
+    (4, 128, 14, 14, 4, "sae_mlp"),      # fused path, 196-pixel maps: rows TMA cannot address -> channel-major copy + scatter
     # the remaining InceptionV1 layer shapes of cfg4 (utils.py:2662-2741), at a reduced batch
     (2, 480, 28, 28, 4, "sae_mlp"),      # mixed3b: C % 64 = 32 -> token-major fallback path, K = 480
     (3, 512, 14, 14, 4, "sae_mlp"),      # mixed4a-c
@@ -290,8 +290,8 @@ def test_train_step_vs_oracle_larger(B, C, H, W, k, kind):
 
 @pytest.mark.parametrize("B,C,H,W", [
     (3, 64, 8, 8),      # bf16 rows TMA can address (HW % 8 == 0)
-    (3, 64, 14, 14),    # HW % 4 == 0: 8-byte stores from the staged tiles
-    (9, 64, 7, 7),      # HW % 4 != 0: channel-major copy + scatter kernel
+    (3, 64, 14, 14),    # HW % 8 != 0: channel-major copy + vectorised (4-element) scatter kernel
+    (9, 64, 7, 7),      # HW % 4 != 0: channel-major copy + element-wise scatter kernel
     (3, 96, 7, 7),      # ... with a zero-padded last slab (C % 64 != 0)
     (2, 64, 5, 5),      # fewer than 32 tokens per image: un-fused path
 ])
