@@ -36,7 +36,7 @@ class ModelPipeline:
 
     def __init__(self, model, sae_model, sae_model_name, sae_layer, sae_optimizer_name="constrained_adam",
                  sae_learning_rate=1e-3, sae_lambda_sparse=5.0, sae_expansion_factor=8, dead_neurons_steps=None,
-                 device=None, reinit_index_dir=None, data_parallel=False):
+                 device=None, reinit_index_dir=None, data_parallel=False, global_batch_images=None):
         self.model = model
         self.sae_model = sae_model
         self.sae_model_name = sae_model_name
@@ -55,6 +55,9 @@ class ModelPipeline:
             raise ValueError("the fused SAE step supports 'adam' and 'constrained_adam'")
         self.reinit_index_dir = reinit_index_dir
         self.dp = DataParallelStep(sae_model_name) if data_parallel else None
+        # data parallel with a FIXED global batch (equal shards, drop_last): the caller states the global image count
+        # and the hook skips the per-step count exchange (one tiny all-reduce + host sync, parallel.global_counts)
+        self.global_batch_images = global_batch_images
         self.train_batch_idx = 0
         self.epoch_batch_idx = 0
         self.train_dead_neurons = {}
@@ -95,7 +98,10 @@ class ModelPipeline:
             if self.dp is not None:
                 n_img = output.shape[0]
                 hw = output.shape[2] * output.shape[3] if output.dim() == 4 else 1
-                g_img, g_tok = global_counts(n_img, hw, device=output.device)
+                if self.global_batch_images:
+                    g_img, g_tok = int(self.global_batch_images), int(self.global_batch_images) * hw
+                else:
+                    g_img, g_tok = global_counts(n_img, hw, device=output.device)
                 res = self.dp.step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
                                    self.sae_expansion_factor, self.sae_optimizer_name, group["betas"], g_img, g_tok,
                                    eps=group["eps"])
