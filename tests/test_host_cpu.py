@@ -247,3 +247,37 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
     assert int(out["SVB_STATS_LEN"]) == L.STATS_LEN
+
+
+def test_small_host_helpers_match_reference_golden(golden_dir):
+    """reshape_tensor, reshape_encoder_output_average, average_over_W_H, variance_explained, get_top_k_samples and
+    CustomCrossEntropyLoss against outputs of the REAL reference functions (oracle/gen_golden_utils.py)."""
+    import numpy as np
+    from sparse_vision_b200 import utils as U
+    g = np.load(os.path.join(golden_dir, "utils_small.npz"))
+    T = lambda k: torch.from_numpy(g[k])   # noqa: E731
+    t, flag = U.reshape_tensor(T("x4"))
+    assert torch.equal(t, T("reshape4")) and bool(flag) == bool(g["reshape4_flag"])
+    t, flag = U.reshape_tensor(T("x2"))
+    assert torch.equal(t, T("reshape2")) and bool(flag) == bool(g["reshape2_flag"])
+    r = U.reshape_encoder_output_average(T("avg"), 3)
+    assert tuple(r.shape) == tuple(g["avg_reshaped_b3"].shape) and torch.equal(r, T("avg_reshaped_b3"))
+    a, b = U.average_over_W_H(T("x4"), T("d4"))
+    assert torch.allclose(a, T("avgwh_a"), rtol=0, atol=1e-7) and torch.allclose(b, T("avgwh_b"), rtol=0, atol=1e-7)
+    a, b = U.average_over_W_H(T("x2"), None)
+    assert torch.equal(a, T("avgwh2_a")) and b is None
+    assert abs(float(U.variance_explained(T("x4"), T("d4"))) - float(g["var_expl4"])) <= 1e-6
+    assert abs(float(U.variance_explained(T("x2"), T("d2"))) - float(g["var_expl2"])) <= 1e-6
+    k, bs, F = 4, 5, 6
+    for largest in (True, False):
+        state = (torch.empty(0, F), torch.empty(0, F, dtype=torch.long), bs, torch.empty(0, F, dtype=torch.long))
+        for batch in (1, 2, 3):
+            tag = f"topk_{int(largest)}_{batch}"
+            state = U.get_top_k_samples(state, T(tag + "_v").clone(), T(tag + "_i").clone(), T(tag + "_f").clone(),
+                                        batch, largest, k)
+            assert torch.equal(state[0], T(tag + "_out_v")), tag
+            assert torch.equal(state[1], T(tag + "_out_i")), tag        # top-k indices: bit-exact
+            assert torch.equal(state[3], T(tag + "_out_f")), tag
+            assert state[2] == bs
+    nll = U.CustomCrossEntropyLoss()(T("nll_probs"), T("nll_targets"))
+    assert abs(float(nll) - float(g["nll"])) <= 1e-6
