@@ -281,3 +281,79 @@ def test_small_host_helpers_match_reference_golden(golden_dir):
             assert state[2] == bs
     nll = U.CustomCrossEntropyLoss()(T("nll_probs"), T("nll_targets"))
     assert abs(float(nll) - float(g["nll"])) <= 1e-6
+
+
+_IE_DP_WORKER = r'''
+import collections, os, sys, torch, torch.distributed as dist
+from torch import nn
+sys.path.insert(0, sys.argv[1])
+from oracle import sae_oracle as O
+import sparse_vision_b200.ops as ops
+import sparse_vision_b200.compute_ie as cie
+from sparse_vision_b200.models.sae_mlp import SaeMLP
+from sparse_vision_b200.parallel import shard_images
+
+# host orchestration only: the CUDA entry points are replaced by the CPU oracle (tests may use it; the product may not)
+KEYS = O.SAE_MLP_KEYS
+def fake_sae_forward(x, w_enc, b_enc, w_dec, b_dec, want_pre=True, **kw):
+    enc, dec, pre = O.sae_mlp_forward(dict(zip(KEYS, (w_enc, b_enc, w_dec, b_dec))), x.float())
+    return enc, dec, (pre if want_pre else None)
+def fake_node_ie_layer(x, grad, params, enc_avg, err_avg, x_avg, scale=None):
+    f, e, n = O.node_ie_layer(dict(zip(KEYS, params)), x.float(), grad.float(), enc_avg, err_avg, x_avg)
+    T = x.shape[0] * x.shape[2] * x.shape[3]
+    sc = (1.0 / T) if scale is None else scale
+    return f * T * sc, torch.as_tensor(e * T * sc).reshape(()), n * T * sc
+ops.sae_forward, ops.node_ie_layer = fake_sae_forward, fake_node_ie_layer
+cie.measure_inactive_units = O.measure_inactive_units
+
+def build():
+    torch.manual_seed(3)
+    net = nn.Sequential(collections.OrderedDict(
+        c1=nn.Conv2d(3, 8, 3, padding=1), r1=nn.ReLU(), p1=nn.MaxPool2d(2),
+        c2=nn.Conv2d(8, 16, 3, padding=1), r2=nn.ReLU(),
+        gap=nn.AdaptiveAvgPool2d(1), fl=nn.Flatten(), fc=nn.Linear(16, 5))).eval()
+    names = {"r1": (8, 2), "r2": (16, 2)}
+    torch.manual_seed(5)
+    saes = {n: SaeMLP(c, k) for n, (c, k) in names.items()}
+    mods = dict(net.named_modules())
+    return cie.IE(net, {n: mods[n] for n in names}, saes, {n: k for n, (_, k) in names.items()},
+                  device=torch.device("cpu")), names
+
+batches = [(torch.randn(6 - i, 3, 8, 8, generator=torch.Generator().manual_seed(40 + i)),
+            torch.randint(0, 5, (6 - i,), generator=torch.Generator().manual_seed(50 + i))) for i in range(2)]
+ie, names = build()                                   # one process, whole batches, BEFORE the group exists
+avg1 = ie.compute_average([x for x, _ in batches])
+f1, e1, n1 = ie.compute_node_ie(batches, avg1)
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+ie, names = build()
+local = []
+for x, y in batches:
+    lo, hi = shard_images(x.shape[0], r, w)           # 3 + 3 and 3 + 2 images
+    local.append((x[lo:hi], y[lo:hi]))
+avg2 = ie.compute_average([x for x, _ in local])
+f2, e2, n2 = ie.compute_node_ie(local, avg2)
+for n in names:
+    for key in ("encoder_output_average", "sae_error_average", "original_layer_output_average"):
+        assert torch.allclose(avg2[key][n], avg1[key][n], rtol=1e-5, atol=1e-6), (n, key)
+    assert torch.equal(avg2["dead_units"][n], avg1["dead_units"][n]), n
+    assert abs(avg2["sparsity"][n] - avg1["sparsity"][n]) < 1e-6, n
+    assert torch.allclose(f2[n], f1[n], rtol=1e-4, atol=1e-7), (n, "features")
+    assert abs(float(e2[n]) - float(e1[n])) <= 1e-4 * abs(float(e1[n])) + 1e-9, (n, "error")
+    assert torch.allclose(n2[n], n1[n], rtol=1e-4, atol=1e-7), (n, "neurons")
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_attribution_pass_sharded_gloo_world2(tmp_path):
+    """SURVEY.md 8e on the CPU: the host side of the sharded attribution pass (per-batch gradient-scale compensation,
+    count / sum all-reduces, uneven shards) gives one process's result; device work is stood in for by the oracle."""
+    script = tmp_path / "ie_dp_worker.py"
+    script.write_text(_IE_DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
