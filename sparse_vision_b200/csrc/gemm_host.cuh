@@ -145,6 +145,9 @@ inline int make_store_tmap_bf16_cmajor(CUtensorMap* out, void* ptr, uint64_t C, 
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+// one-shot request for the next launch_gemm call of this thread: walk the M tiles in reverse (GemmProblem::reverse_m)
+inline int& gemm_reverse_m_flag() { static thread_local int f = 0; return f; }
+inline int gemm_reverse_m() { int& f = gemm_reverse_m_flag(); const int v = f; f = 0; return v; }
 constexpr int kMaxDevices = 64;
 inline int current_device() {
   int dev = -1;
@@ -187,6 +190,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   p.a_slab = a_slab ? 1 : 0;
   p.b_slab = b_slab ? 1 : 0;
   p.a_prefetch = a_prefetch;
+  p.reverse_m = gemm_reverse_m();
 #ifdef SVB_GEMM_TRACE
   p.trace = gemm_trace_ptr();
 #endif

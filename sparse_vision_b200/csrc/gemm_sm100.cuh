@@ -34,6 +34,8 @@ struct GemmProblem {
   unsigned long long a_policy = 0, b_policy = 0;  // L2 eviction policy of the operand loads (0 = default)
   int a_slab = 0, b_slab = 0;  // operand stored slab-major ([cols/64][rows][64], 3-D tensor map; see gemm_host.cuh)
   int a_prefetch = 0;          // B-stationary schedule: L2-prefetch the A tiles this many steps of the CTA's walk ahead
+  int reverse_m = 0;           // streaming schedule: walk the M tiles from the last to the first (the kernel that wrote
+                               // A just before left its LAST tiles in L2)
 #ifdef SVB_GEMM_TRACE
   long long* trace = nullptr;  // bring-up only: [gridDim.x][4] cycles the producer / MMA thread / epilogue spent waiting
   int a_skip = 0;              // bring-up only (timing, wrong results): load only every a_skip-th A stage from memory
@@ -129,7 +131,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmProblem& p, int t, int
   TileInfo ti;
   ti.tile_n = t % p.tiles_n;
   const int r = t / p.tiles_n;
-  ti.tile_m = r % p.tiles_m;
+  ti.tile_m = p.reverse_m ? p.tiles_m - 1 - r % p.tiles_m : r % p.tiles_m;
   ti.split = r / p.tiles_m;
   ti.m0 = ti.tile_m * kBlockM;
   ti.n0 = ti.tile_n * block_n;
@@ -206,7 +208,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto decode = [&](int t) -> TileInfo {
     if constexpr (BSTAT) {
       TileInfo ti;
-      ti.tile_n = fixed_n; ti.tile_m = t; ti.split = 0; ti.m0 = t * kBlockM; ti.n0 = fixed_n * BLOCK_N;
+      const int tm = p.reverse_m ? p.tiles_m - 1 - t : t;
+      ti.tile_n = fixed_n; ti.tile_m = tm; ti.split = 0; ti.m0 = tm * kBlockM; ti.n0 = fixed_n * BLOCK_N;
       ti.cta_slot = static_cast<int>(blockIdx.x) / p.tiles_n;
       return ti;
     } else {
