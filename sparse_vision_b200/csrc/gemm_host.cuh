@@ -145,9 +145,6 @@ inline int make_store_tmap_bf16_cmajor(CUtensorMap* out, void* ptr, uint64_t C, 
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-// one-shot request for the next launch_gemm call of this thread: walk the M tiles in reverse (GemmProblem::reverse_m)
-inline int& gemm_reverse_m_flag() { static thread_local int f = 0; return f; }
-inline int gemm_reverse_m() { int& f = gemm_reverse_m_flag(); const int v = f; f = 0; return v; }
 constexpr int kMaxDevices = 64;
 inline int current_device() {
   int dev = -1;
@@ -169,7 +166,8 @@ inline int device_sm_count() {
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi, bool BSTAT = false>
 int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int k_splits_req, const typename Epi::Params& ep, int* splits_out = nullptr, int max_ctas = 0,
-                unsigned long long a_policy = 0, bool a_slab = false, bool b_slab = false, int a_prefetch = 0) {
+                unsigned long long a_policy = 0, bool a_slab = false, bool b_slab = false, int a_prefetch = 0,
+                bool reverse_m = false) {
   using Cfg = GemmCfg<BLOCK_N, Epi::kSmemBytes, BSTAT>;
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8)) return -2;  // pitches are validated by the tensor-map encoder
   CUtensorMap tmA, tmB;
@@ -190,7 +188,7 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
   p.a_slab = a_slab ? 1 : 0;
   p.b_slab = b_slab ? 1 : 0;
   p.a_prefetch = a_prefetch;
-  p.reverse_m = gemm_reverse_m();
+  p.reverse_m = reverse_m ? 1 : 0;
 #ifdef SVB_GEMM_TRACE
   p.trace = gemm_trace_ptr();
 #endif

@@ -275,8 +275,8 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
     if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
     if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
-    gemm_reverse_m_flag() = 1;   // newest E tiles first (still in L2), as in svb_sae.cu
-    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
+    // newest E tiles first (still in L2), as in svb_sae.cu
+    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
     // the statistics folds (and the scatter of a channel-major d) only feed the end of the step: side stream
     SVB_TRY(side_fork(h, st));
     if (out_kind == 4) SVB_TRY(run_cmajor_to_nchw(h->side, pl.D, dec_out, out->dec_dtype, C, pl.hw, pl.T, ld_t));

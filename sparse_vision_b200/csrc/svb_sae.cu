@@ -231,8 +231,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     // the encoder wrote E from the first token tile to the last, so its newest ~100 MB are still in L2: walk the
     // token tiles backwards and the decoder's first reads are hits (-3.5 us of 210)
-    gemm_reverse_m_flag() = 1;
-    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec (fused NCHW)");
+    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
     // the statistics folds only feed the tail of the step: side stream, beside the dE GEMM
     SVB_TRY(side_fork(h, st));
