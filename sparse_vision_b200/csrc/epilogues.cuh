@@ -7,7 +7,7 @@
 // 128B swizzle, bank-conflict free) and one lane issues a TMA tensor store, so global writes are full 128-byte lines
 // instead of 32 scattered 16-byte pieces per instruction (which made the first version of the encoder GEMM 4x
 // slower than its MMA time).  All floating-point reductions are written as per-(tile,warp) partials and summed later
-// in a fixed order, so a step is bit-reproducible; integer activity bits use atomicOr (order-independent).
+// in a fixed order, so a step is bit-reproducible.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -55,48 +55,11 @@ __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, float (&
     o[8 * i + 6] = bf16lo(q.w); o[8 * i + 7] = bf16hi(q.w);
   }
 }
-__device__ __forceinline__ void load_row_f32(const float* src, float (&o)[32], int nvalid) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i * 4 < nvalid) q = __ldg(reinterpret_cast<const float4*>(src) + i);
-    o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
-  }
-}
-
 __device__ __forceinline__ void lds_row_f32(const float* src, float (&o)[32]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 q = reinterpret_cast<const float4*>(src)[i];
     o[4 * i] = q.x; o[4 * i + 1] = q.y; o[4 * i + 2] = q.z; o[4 * i + 3] = q.w;
-  }
-}
-
-// Sum over the 32 lanes of v[j] for every j with 31 shuffles: lane j returns column j's sum.  Destroys v.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
-// OR the per-row activity word into the per-image bit matrix.  A warp's 32 rows usually lie in one image.
-__device__ __forceinline__ void publish_activity(uint32_t* act_bits, int words_per_img, int word_idx, uint32_t word,
-                                                 int row, int M, int hw, int row0_warp, int lane) {
-  const int last_row = min(row0_warp + 31, M - 1);
-  if (row0_warp > last_row) return;
-  const int b_first = row0_warp / hw, b_last = last_row / hw;
-  const int my_b = row < M ? row / hw : -1;
-  for (int b = b_first; b <= b_last; ++b) {
-    const uint32_t ored = __reduce_or_sync(0xffffffffu, my_b == b ? word : 0u);
-    if (lane == 0 && ored) atomicOr(&act_bits[static_cast<size_t>(b) * words_per_img + word_idx], ored);
   }
 }
 
@@ -148,7 +111,6 @@ struct SlabWriterT {
   }
 };
 typedef SlabWriterT<1> SlabWriter1;
-typedef SlabWriterT<2> SlabWriter2;
 
 // Per-warp staging of ONE 32-row x 32-column bf16 chunk (2 KB, 64-byte rows, 64B swizzle) that leaves through a TMA
 // tensor store.  Half the shared memory of a slab writer: with the 128 KB resident weight tile of the B-stationary

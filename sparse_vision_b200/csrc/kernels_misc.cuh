@@ -783,10 +783,13 @@ static __global__ void activity_bits_rows_kernel(const T* __restrict__ t, uint32
 }
 
 // ------------------------------------------------------------------------------------------------ gradients
-// Gradient assembly for the SaeMLP step.  All inputs are in "unscaled" units (see EpiDPre); s = 2/(T_global*C).
+// Gradient assembly for the SaeMLP step (assemble_grads_kernel below).  All inputs are in "unscaled" units (see
+// EpiDPre); s = 2/(T_global*C).
 //   g_wdec[i] = s * sum_k P_wd[k][i]
 //   g_wenc[f,c] = s * (sum_k P_we[k][f,c] - csum[f]*b_dec[c])     (G5 used x, not x - b_dec: rank-1 fix-up)
 //   g_benc[f] = s * csum[f]
+//   g_bdec[c] = s * (colsum(DIFF)[c] - sum_f csum[f] * W_enc[f,c])
+// sum_splits_kernel: plain split-K reduction of svb_gemm_bf16.
 static __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, size_t n, float scale,
                                   float* __restrict__ out) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -795,40 +798,6 @@ static __global__ void sum_splits_kernel(const float* __restrict__ part, int spl
     for (int k = 0; k < splits; ++k) a += part[static_cast<size_t>(k) * n + i];
     out[i] = a * scale;
   }
-}
-static __global__ void wenc_grad_kernel(const float* __restrict__ part, int splits, int F, int C,
-                                 const float* __restrict__ csum, const float* __restrict__ b_dec, float scale,
-                                 float* __restrict__ out) {
-  const size_t n = static_cast<size_t>(F) * C;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float a = 0.f;
-    for (int k = 0; k < splits; ++k) a += part[static_cast<size_t>(k) * n + i];
-    const int f = static_cast<int>(i / C), c = static_cast<int>(i % C);
-    out[i] = (a - csum[f] * b_dec[c]) * scale;
-  }
-}
-// vecmat partials: out[chunk][c] = sum_{f in chunk} v[f] * W[f,c]   (W row-major [F,C]); 256 threads over c.
-template <typename TW>
-static __global__ void vecmat_partial_kernel(const float* __restrict__ v, const TW* __restrict__ W, int F, int C,
-                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int chunks = gridDim.y;
-  const int per = (F + chunks - 1) / chunks;
-  const int f0 = blockIdx.y * per, f1 = min(F, f0 + per);
-  if (c >= C) return;
-  float a = 0.f;
-  for (int f = f0; f < f1; ++f) a += v[f] * to_f32<TW>(W[static_cast<size_t>(f) * C + c]);
-  out[static_cast<size_t>(blockIdx.y) * C + c] = a;
-}
-// g_bdec[c] = s * (dsum[c] - sum_chunks vm[chunk][c])
-static __global__ void bdec_grad_kernel(const float* __restrict__ dsum, const float* __restrict__ vm, int chunks, int C,
-                                 float scale, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f;
-  for (int k = 0; k < chunks; ++k) a += vm[static_cast<size_t>(k) * C + c];
-  out[c] = (dsum[c] - a) * scale;
 }
 
 // ------------------------------------------------------------------------------------------------ merged step kernels
