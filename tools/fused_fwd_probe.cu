@@ -30,7 +30,10 @@ namespace {
 
 constexpr int kC = 256;                 // channels = K of GEMM1 = N of GEMM2
 constexpr int kFT = 256;                // feature tile = N of GEMM1 = K chunk of GEMM2
-constexpr int kStages = 3;
+#ifndef PROBE_STAGES
+#define PROBE_STAGES 3
+#endif
+constexpr int kStages = PROBE_STAGES;
 constexpr uint32_t kTileA = 128 * 64 * 2;      // 16 KB: one 128-row x 64-column K-major block
 constexpr uint32_t kTileB = 256 * 64 * 2;      // 32 KB: one 256-row x 64-column K-major block
 constexpr uint32_t kXsOff = 0, kEsOff = 4 * kTileA, kRingOff = 8 * kTileA, kBarOff = kRingOff + kStages * kTileB;
