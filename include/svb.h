@@ -101,7 +101,8 @@ typedef struct svb_adam_state {
 typedef struct svb_opt_config {
   int32_t optimizer; /* svb_optimizer */
   int32_t step;      /* Adam step count AFTER this update (1 on the first step) */
-  float lr, beta1, beta2, eps;
+  double lr, beta1, beta2, eps; /* doubles, like the Python floats torch.optim.Adam holds: 1 - beta2 = 1e-4 must not
+                                 * pick up the 1.7e-4 relative error of a float32 0.9999 */
 } svb_opt_config;
 
 /* Scalars of one step, device float[SVB_STATS_LEN] (read them with one D2H copy per logging interval instead of
@@ -185,6 +186,11 @@ int svb_comm_connect(svb_handle* h, int32_t rank, int32_t world, const void* ipc
 int svb_comm_capacity(svb_handle* h, int64_t* n_floats);
 int svb_comm_allreduce(svb_handle* h, void* stream);
 int svb_comm_destroy(svb_handle* h);
+/* How long a rank waits in the exchange kernel for a peer (default 120 s, or the environment variable
+ * SVB_COMM_TIMEOUT_S when the buffer is allocated).  A peer that never arrives does not hang or trap the GPU: the
+ * launch gives up and svb_comm_status reports 1 + that rank (sticky; 0 = all exchanges completed; synchronises). */
+int svb_comm_set_timeout(svb_handle* h, double seconds);
+int svb_comm_status(svb_handle* h, int32_t* status);
 
 /* GatedSae forward / step — models/gated_sae.py:28-56, losses/sparse_loss.py:68-76. */
 typedef struct svb_gated_forward_out {

@@ -45,8 +45,8 @@ class AdamState(C.Structure):
 
 
 class OptConfig(C.Structure):
-    _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float),
-                ("beta2", C.c_float), ("eps", C.c_float)]
+    _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double)]
 
 
 class ActivityOut(C.Structure):
@@ -92,6 +92,8 @@ SYMBOLS = {
     "svb_comm_capacity": (C.c_int, [_vp, _P(C.c_int64)]),
     "svb_comm_allreduce": (C.c_int, [_vp, _vp]),
     "svb_comm_destroy": (C.c_int, [_vp]),
+    "svb_comm_set_timeout": (C.c_int, [_vp, C.c_double]),
+    "svb_comm_status": (C.c_int, [_vp, _P(C.c_int32)]),
     "svb_grad_early_elems": (C.c_int, [_vp, _P(C.c_int64)]),
     "svb_gated_forward": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), _P(GatedForwardOut)]),
     "svb_gated_train_step": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), _P(AdamState), _P(OptConfig), C.c_float,
@@ -174,8 +176,9 @@ def handle(device=None):
     return _handles[dev]
 
 
-def stream_ptr():
-    return _vp(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The current torch stream OF `device` (the tensors' device, which need not be the current one)."""
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

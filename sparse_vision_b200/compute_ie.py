@@ -94,7 +94,22 @@ class IE:
         n_global = self._all_reduce_counts(n_samples)
         out = {"encoder_output_average": {}, "sae_error_average": {}, "original_layer_output_average": {},
                "dead_units": {}, "sparsity": {}}
-        for name, s in sums.items():
+        if self._dp():
+            # every rank must issue the same collectives, also one whose shards were all empty: such a rank learns the
+            # layer shapes from its peers and contributes zeros (dead = all-True is the neutral element of the AND)
+            shapes = {n: (s["enc"].shape[0],) + tuple(s["x"].shape) for n, s in sums.items()}
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, shapes)
+            for g in gathered:
+                for n, (f, c, h, w) in g.items():
+                    if n not in sums:
+                        z = lambda *s: torch.zeros(*s, device=self.device)
+                        sums[n] = {"enc": z(f, h, w), "err": z(c, h, w), "x": z(c, h, w),
+                                   "dead": torch.ones(f, dtype=torch.bool, device=self.device), "sp": 0.0}
+        for name in self.layers:
+            if name not in sums:
+                continue
+            s = sums[name]
             sp = torch.tensor([s["sp"]], device=self.device, dtype=torch.float64)
             dead_i = s["dead"].to(torch.int32)
             if self._dp():
@@ -141,8 +156,20 @@ class IE:
                     err[name] += e
                     neur[name] += n
                     tokens[name] += t
-        for name in feat:
+        for name in self.layers:          # the same collectives on every rank (see compute_average)
+            if name not in feat:
+                if not self._dp():
+                    continue
+                n_f = self.saes[name].hidden_size
+                n_c = self.saes[name].act_size
+                feat[name] = torch.zeros(n_f, device=self.device)
+                err[name] = torch.zeros(1, device=self.device)
+                neur[name] = torch.zeros(n_c, device=self.device)
+                tokens[name] = 0
             tg = self._all_reduce_counts(tokens[name])
+            if tg == 0:                   # no rank saw this layer
+                del feat[name], err[name], neur[name]
+                continue
             if self._dp():
                 for t in (feat[name], err[name], neur[name]):
                     dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -1027,6 +1027,7 @@ static __global__ void __launch_bounds__(1024) step_finalize_kernel(const Finali
     a.stats[SVB_STAT_VAR_EXPL] = 1.f - o[4] / o[3];
     a.stats[SVB_STAT_SPARSITY] = (o[5] / a.B_g) / (static_cast<float>(a.F) / a.expansion);
     a.stats[SVB_STAT_N_DEAD] = nds;
+    for (int i = SVB_STAT_N_DEAD + 1; i < SVB_STATS_LEN; ++i) a.stats[i] = 0.f;   // callers hand in uninitialised blocks
   }
 }
 
@@ -1034,13 +1035,13 @@ static __global__ void __launch_bounds__(1024) step_finalize_kernel(const Finali
 struct AdamCoef {
   float lr_over_bc1;    // lr / (1 - beta1^t)
   float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^t)
-  float beta1, beta2, eps;
+  float beta2, omb1, omb2, eps;   // beta2, 1 - beta1, 1 - beta2 (each rounded from the double), eps
 };
 __device__ __forceinline__ float adam_elem(float w, float g, float& m, float& v, const AdamCoef& k) {
   // torch.optim.Adam single-tensor update: m.lerp_(g, 1-b1); v = b2*v + (1-b2) g^2;
   // w -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
-  m = m + (g - m) * (1.f - k.beta1);
-  v = v * k.beta2 + (1.f - k.beta2) * g * g;
+  m = m + (g - m) * k.omb1;
+  v = v * k.beta2 + k.omb2 * g * g;
   const float denom = sqrtf(v) * k.inv_sqrt_bc2 + k.eps;
   return w - k.lr_over_bc1 * (m / denom);
 }

@@ -53,6 +53,7 @@ extern "C" int svb_grad_early_elems(svb_handle* h, int64_t* elems) {
 
 extern "C" int svb_profile_enable(svb_handle* h, int32_t enable) {
   if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  SVB_ON_DEVICE(h);
   Profiler& p = h->prof;
   if (enable && !p.created) {
     for (int s = 0; s < kProfMaxSteps; ++s)
@@ -68,6 +69,7 @@ extern "C" int svb_profile_enable(svb_handle* h, int32_t enable) {
 extern "C" int svb_profile_read(svb_handle* h, int32_t max_phases, float* ms_avg_host, int32_t* n_phases,
                                 int32_t* n_steps) {
   if (!h || !ms_avg_host || !n_phases || !n_steps) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   Profiler& p = h->prof;
   if (!p.created) return fail(SVB_ERR_BAD_ARG, "profiling was never enabled");
   SVB_CUDA(cudaDeviceSynchronize());
@@ -103,6 +105,7 @@ extern "C" int svb_adam_step(svb_handle* h, void* stream, int32_t n_tensors, flo
                              const float* const* grads, float* const* m, float* const* v, const int64_t* rows,
                              const int64_t* cols, int32_t decoder_index, const svb_opt_config* opt) {
   if (!h || !params || !grads || !m || !v || !rows || !cols || !opt) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const AdamCoef k = adam_coef(opt);
@@ -130,6 +133,7 @@ extern "C" int svb_reinit_dead(svb_handle* h, void* stream, const svb_sae_params
                                const svb_adam_state* adam, const uint8_t* dead, const float* new_w_enc,
                                const float* new_w_dec, float new_b_enc) {
   if (!h || !p || !dead || !new_w_enc || !new_w_dec) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(p->F) * C;
   (reinit_scatter_kernel<<<grid_for(n), 256, 0, st>>>(dead, p->F, C, p->w_enc, p->b_enc, p->w_dec, new_w_enc, new_w_dec,
@@ -145,6 +149,7 @@ extern "C" int svb_reinit_dead(svb_handle* h, void* stream, const svb_sae_params
 extern "C" int svb_measure_inactive(svb_handle* h, void* stream, const void* t, int32_t dtype, int32_t layout,
                                     int64_t n_images, int32_t hw, int32_t F, const svb_activity_out* act) {
   if (!h || !t || !act) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (n_images <= 0 || hw <= 0 || F <= 0) return fail(SVB_ERR_BAD_ARG, "empty tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int words = (F + 31) / 32;
@@ -183,6 +188,7 @@ extern "C" int svb_measure_inactive(svb_handle* h, void* stream, const void* t, 
 // ---------------------------------------------------------------------------------------------------- layout
 extern "C" int svb_pack_tokens(svb_handle* h, void* stream, const svb_acts* x, void* out_bf16_tokens) {
   if (!h || !out_bf16_tokens) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_acts(x));
   return pack_acts(static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out_bf16_tokens));
 }
@@ -190,6 +196,7 @@ extern "C" int svb_pack_tokens(svb_handle* h, void* stream, const svb_acts* x, v
 extern "C" int svb_unpack_tokens(svb_handle* h, void* stream, const void* tokens, int32_t tokens_dtype,
                                  int64_t n_images, int32_t hw, int32_t C, void* out_nchw, int32_t out_dtype) {
   if (!h || !tokens || !out_nchw) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (tokens_dtype != SVB_BF16) return fail(SVB_ERR_UNSUPPORTED, "svb_unpack_tokens takes bf16 tokens");
   return unpack_to(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(tokens), n_images, hw, C, out_nchw,
                    out_dtype, SVB_NCHW);
@@ -223,6 +230,7 @@ int launch_ie_channelwise(cudaStream_t st, int sms, const T* a, const T* g, cons
 extern "C" int svb_ie_channelwise(svb_handle* h, void* stream, const void* a, const void* g, int32_t dtype,
                                   const float* avg, int64_t n_images, int32_t hw, int32_t F, float scale, float* out) {
   if (!h || !a || !g || !avg || !out) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (n_images <= 0 || hw <= 0 || F <= 0) return fail(SVB_ERR_BAD_ARG, "empty input");
   const int V = dtype == SVB_F32 ? 4 : 8;
   if (F % V) return fail(SVB_ERR_UNSUPPORTED, "F=%d must be a multiple of %d for 16-byte loads", F, V);
@@ -252,6 +260,7 @@ extern "C" int svb_ie_channelwise(svb_handle* h, void* stream, const void* a, co
 extern "C" int svb_ie_allchannels(svb_handle* h, void* stream, const void* err, const void* g, int32_t dtype,
                                   const float* avg, int64_t n_images, int32_t C, int32_t hw, float scale, float* out) {
   if (!h || !err || !g || !avg || !out) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (n_images <= 0 || hw <= 0 || C <= 0) return fail(SVB_ERR_BAD_ARG, "empty input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n_pix = n_images * static_cast<long long>(hw);
@@ -278,6 +287,7 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
                                  const float* x_avg, float scale, float* ie_features, float* ie_error,
                                  float* ie_neurons) {
   if (!h || !grad || !p || !enc_avg || !err_avg || !x_avg) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_acts(x));
   if (!p->w_enc || !p->b_enc || !p->w_dec || !p->b_dec || p->F <= 0 || p->F % 8)
     return fail(SVB_ERR_BAD_ARG, "bad SAE parameters");
@@ -378,6 +388,7 @@ extern "C" int svb_gemm_bf16(svb_handle* h, void* stream, const void* A, int32_t
                              int32_t b_mn, int64_t ldb, int32_t M, int32_t N, int32_t K, void* out, int32_t out_dtype,
                              int64_t ldo, float alpha, const float* bias, int32_t relu) {
   if (!h || !A || !B || !out) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
   if (out_dtype != SVB_F32 && out_dtype != SVB_BF16) return fail(SVB_ERR_BAD_ARG, "bad out dtype");
   if (N % 8 || ldo % 8) return fail(SVB_ERR_UNSUPPORTED, "N and ldo must be multiples of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -10,6 +10,7 @@
 //   3. a second flag round makes sure all slices have landed before the optimiser half of the step reads them.
 // Compared with two NCCL calls per step (~55 us at 2 GPUs, almost all launch / protocol latency for 4 MB) this is one
 // launch, the MAX section rides along, and the result is bit-identical on every rank and from run to run.
+#include <cstdlib>
 #include "svb_common.cuh"
 
 using namespace svb;
@@ -21,10 +22,18 @@ constexpr int kCommBlocks = 128, kCommThreads = 512, kMaxRanks = 8;
 struct CommArgs {
   float* buf[kMaxRanks];      // every rank's flat buffer (own entry = local pointer)
   uint32_t* flag[kMaxRanks];  // every rank's flag array [2 rounds][kCommBlocks][kMaxRanks]
+  uint32_t* status;           // LOCAL status word: 0 = fine, else 1 + the peer that never arrived (sticky, host-readable)
   long long n_sum, n_max;
+  unsigned long long timeout_ns;
   int rank, world;
   uint32_t epoch;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -35,7 +44,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 // Round `round` of the cross-GPU rendezvous of CTA b: signal every peer's twin CTA, then wait for all of them.
-// A lost peer must end as a trapped launch, never as a hung GPU.
+// Ranks may legitimately be seconds apart (data loading, rank-0-only checkpointing), so the wait is long
+// (svb_comm_set_timeout / SVB_COMM_TIMEOUT_S, default 120 s of %globaltimer).  A peer that never arrives must end
+// neither as a hung GPU nor as a poisoned context: the launch gives up, records who was missing in the sticky status
+// word (svb_comm_status reads it on the host; the step's results are then undefined) and every other wait of this and
+// of later launches returns at once.
 __device__ __forceinline__ void cta_rendezvous(const CommArgs& a, int round) {
   __syncthreads();
   if (threadIdx.x < a.world) {
@@ -43,12 +56,15 @@ __device__ __forceinline__ void cta_rendezvous(const CommArgs& a, int round) {
     __threadfence_system();
     st_release_sys(a.flag[peer] + (static_cast<size_t>(round) * kCommBlocks + blockIdx.x) * kMaxRanks + a.rank, a.epoch);
     const uint32_t* mine = a.flag[a.rank] + (static_cast<size_t>(round) * kCommBlocks + blockIdx.x) * kMaxRanks + peer;
-    const long long t0 = clock64();
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
     while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
-      if (clock64() - t0 > 8000000000LL) {  // ~4 s
-        printf("svb: peer %d never arrived at the all-reduce (rank %d, block %d, round %d)\n", peer, a.rank,
-               blockIdx.x, round);
-        __trap();
+      if ((++spins & 1023u) == 0) {
+        if (*reinterpret_cast<volatile uint32_t*>(a.status) != 0) break;
+        if (globaltimer_ns() - t0 > a.timeout_ns) {
+          atomicCAS(a.status, 0u, 1u + static_cast<uint32_t>(peer));
+          break;
+        }
       }
     }
   }
@@ -115,6 +131,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_flat_kernel(const Comm
 }  // namespace
 
 struct svb_comm {
+  double timeout_s = 120.0;
   int rank = 0, world = 1;
   float* base = nullptr;         // local region: [capacity floats | flags]
   int64_t capacity = 0;          // floats
@@ -123,12 +140,21 @@ struct svb_comm {
   uint32_t epoch = 0;
 };
 
-static size_t comm_flag_bytes() { return sizeof(uint32_t) * 2 * kCommBlocks * kMaxRanks; }
+// flags of the two rendezvous rounds, then 64 bytes whose first word is the status
+static size_t comm_flag_bytes() { return sizeof(uint32_t) * 2 * kCommBlocks * kMaxRanks + 64; }
+static uint32_t* comm_status_word(svb_comm* c) {
+  return reinterpret_cast<uint32_t*>(c->base + c->capacity) + 2 * kCommBlocks * kMaxRanks;
+}
 
 extern "C" int svb_comm_alloc(svb_handle* h, int64_t n_floats, void* ipc_handle_out) {
   if (!h || n_floats <= 0 || !ipc_handle_out) return fail(SVB_ERR_BAD_ARG, "svb_comm_alloc: bad argument");
+  SVB_ON_DEVICE(h);
   if (h->comm_ctx) return fail(SVB_ERR_BAD_ARG, "svb_comm_alloc: a communication buffer already exists");
   svb_comm* c = new svb_comm();
+  if (const char* env = getenv("SVB_COMM_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0) c->timeout_s = v;
+  }
   c->capacity = (n_floats + 63) / 64 * 64;
   const size_t bytes = static_cast<size_t>(c->capacity) * 4 + comm_flag_bytes();
   void* p = nullptr;
@@ -156,6 +182,7 @@ extern "C" int svb_comm_alloc(svb_handle* h, int64_t n_floats, void* ipc_handle_
 
 extern "C" int svb_comm_connect(svb_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
   if (!h || !h->comm_ctx || !ipc_handles) return fail(SVB_ERR_BAD_ARG, "svb_comm_connect: call svb_comm_alloc first");
+  SVB_ON_DEVICE(h);
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
     return fail(SVB_ERR_UNSUPPORTED, "svb_comm_connect: world size %d (1..%d ranks of one node)", world, kMaxRanks);
   svb_comm* c = h->comm_ctx;
@@ -185,6 +212,7 @@ extern "C" int svb_comm_capacity(svb_handle* h, int64_t* n_floats) {
 
 extern "C" int svb_comm_allreduce(svb_handle* h, void* stream) {
   if (!h || !h->comm_ctx || !h->comm_ctx->connected) return fail(SVB_ERR_BAD_ARG, "svb_comm_allreduce: not connected");
+  SVB_ON_DEVICE(h);
   svb_comm* c = h->comm_ctx;
   if (!h->gradbuf || h->gradbuf != c->base)
     return fail(SVB_ERR_BAD_ARG, "svb_comm_allreduce: the last svb_*_step_grads did not use the communication buffer");
@@ -194,9 +222,44 @@ extern "C" int svb_comm_allreduce(svb_handle* h, void* stream) {
     a.flag[r] = reinterpret_cast<uint32_t*>(static_cast<float*>(c->peer_base[r]) + c->capacity);
   }
   a.n_sum = h->sum_elems; a.n_max = h->max_elems; a.rank = c->rank; a.world = c->world;
+  a.status = comm_status_word(c);
+  a.timeout_ns = static_cast<unsigned long long>(c->timeout_s * 1e9);
   a.epoch = ++c->epoch;
-  (allreduce_flat_kernel<<<kCommBlocks, kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(a), svb::count_launch());
-  SVB_LAUNCH_CHECK("allreduce_flat");
+  // The twin-CTA rendezvous needs all kCommBlocks CTAs of every rank on the machine at the same time: a cooperative
+  // launch guarantees exactly that (the grid starts only when all of it fits; it is refused if it never can).
+  static int coop_ok = -1;
+  if (coop_ok < 0) {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allreduce_flat_kernel, kCommThreads, 0);
+    coop_ok = (coop && per_sm * h->sms >= kCommBlocks) ? 1 : 0;
+  }
+  if (!coop_ok)
+    return fail(SVB_ERR_UNSUPPORTED, "svb_comm_allreduce: %d co-resident CTAs are not available on this device", kCommBlocks);
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(allreduce_flat_kernel), dim3(kCommBlocks),
+                                              dim3(kCommThreads), args, 0, static_cast<cudaStream_t>(stream));
+  svb::count_launch();
+  if (e != cudaSuccess) return fail(SVB_ERR_CUDA, "cooperative launch of the all-reduce failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int svb_comm_set_timeout(svb_handle* h, double seconds) {
+  if (!h || !h->comm_ctx || !(seconds > 0)) return fail(SVB_ERR_BAD_ARG, "svb_comm_set_timeout: no buffer / bad value");
+  h->comm_ctx->timeout_s = seconds;
+  return 0;
+}
+
+// 0 = every all-reduce so far completed; 1 + r = rank r never arrived at some rendezvous within the timeout (sticky: the
+// parameters of that step and of every later one are undefined).  Synchronises with the device.
+extern "C" int svb_comm_status(svb_handle* h, int32_t* status) {
+  if (!h || !status) return fail(SVB_ERR_BAD_ARG, "null argument");
+  *status = 0;
+  if (!h->comm_ctx) return 0;
+  SVB_ON_DEVICE(h);
+  uint32_t v = 0;
+  SVB_CUDA(cudaMemcpy(&v, comm_status_word(h->comm_ctx), 4, cudaMemcpyDeviceToHost));
+  *status = static_cast<int32_t>(v);
   return 0;
 }
 

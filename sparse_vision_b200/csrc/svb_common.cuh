@@ -106,6 +106,22 @@ struct svb_handle {
 
 namespace svb {
 float* comm_flat_or(svb_handle* h, float* arena_flat, size_t need_floats);
+
+// Every entry point runs on the device its handle was created on, whatever the caller's current device is (tensors on
+// cuda:1 while the default device is cuda:0): switch for the duration of the call, restore on the way out.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define SVB_ON_DEVICE(h)                           \
+  svb::DeviceGuard device_guard_((h)->device);     \
+  if (!device_guard_.ok) return svb::fail(SVB_ERR_CUDA, "could not switch to device %d of the handle", (h)->device)
 }
 
 namespace svb {
@@ -408,9 +424,10 @@ inline AdamCoef adam_coef(const svb_opt_config* o) {
   const double bc2 = 1.0 - pow(static_cast<double>(o->beta2), o->step);
   k.lr_over_bc1 = static_cast<float>(static_cast<double>(o->lr) / bc1);
   k.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-  k.beta1 = o->beta1;
-  k.beta2 = o->beta2;
-  k.eps = o->eps;
+  k.beta2 = static_cast<float>(o->beta2);
+  k.omb1 = static_cast<float>(1.0 - o->beta1);   // rounded once from the double, as torch does with its Python scalars
+  k.omb2 = static_cast<float>(1.0 - o->beta2);
+  k.eps = static_cast<float>(o->eps);
   return k;
 }
 

@@ -185,6 +185,7 @@ int run_prep(cudaStream_t st, const GatedPlan& pl, const svb_gated_params* p, bo
 extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
                                  const svb_gated_forward_out* out) {
   if (!h || !out) return fail(SVB_ERR_BAD_ARG, "null handle/out");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GatedPlan pl;
@@ -226,6 +227,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
 extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_gated_params* p,
                                     float lambda_sparse, int64_t global_tokens, const svb_train_out* out) {
   if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GatedPlan pl;
@@ -363,6 +365,7 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
                                     int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
                                     const svb_train_out* out) {
   if (!h || !adam || !opt) return fail(SVB_ERR_BAD_ARG, "null handle/adam/opt");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   for (int i = 0; i < 6; ++i)
     if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);

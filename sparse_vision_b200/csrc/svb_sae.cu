@@ -139,6 +139,7 @@ int run_prep(cudaStream_t st, const SaePlan& pl, const svb_sae_params* p, bool t
 extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
                                const svb_sae_forward_out* out) {
   if (!h || !out) return fail(SVB_ERR_BAD_ARG, "null handle/out");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SaePlan pl;
@@ -170,6 +171,7 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
 extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x, const svb_sae_params* p,
                                   float lambda_sparse, int64_t global_tokens, const svb_train_out* out) {
   if (!h) return fail(SVB_ERR_BAD_ARG, "null handle");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SaePlan pl;
@@ -322,6 +324,7 @@ extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x
                                   int32_t expansion_factor, int64_t global_tokens, int64_t global_images,
                                   const svb_train_out* out) {
   if (!h || !adam || !opt) return fail(SVB_ERR_BAD_ARG, "null handle/adam/opt");
+  SVB_ON_DEVICE(h);
   SVB_TRY(check_params(x, p));
   for (int i = 0; i < 4; ++i)
     if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);

@@ -81,10 +81,16 @@ class ModelPipeline:
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             ms.append(st["exp_avg"])
             vs.append(st["exp_avg_sq"])
+        steps = set()
         for p in params:
-            self.sae_optimizer.state[p]["step"] += 1
-        step = int(self.sae_optimizer.state[params[0]]["step"].item())
-        return [p.data for p in params], ms, vs, step
+            st = self.sae_optimizer.state[p]
+            if st["step"].is_cuda:         # load_state_dict(map_location=cuda) leaves the counters on the GPU: a .item()
+                st["step"] = st["step"].cpu()   # there would synchronise the host with the device on every step
+            st["step"] += 1
+            steps.add(int(st["step"].item()))
+        if len(steps) != 1:
+            raise ValueError(f"the fused SAE step needs one Adam step count for all parameters, found {sorted(steps)}")
+        return [p.data for p in params], ms, vs, steps.pop()
 
     # ------------------------------------------------------------------ the hook (model_pipeline.py:363-432)
     def hook(self, module, input, output, name, use_sae=True, train_sae=True):
@@ -188,6 +194,9 @@ class ModelPipeline:
         ckpt = torch.load(path, map_location=self.device)
         self.sae_model.load_state_dict(ckpt["model_state_dict"])
         self.sae_optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        for st in self.sae_optimizer.state.values():      # Adam's step counters live on the host (no per-step sync)
+            if torch.is_tensor(st.get("step")) and st["step"].is_cuda:
+                st["step"] = st["step"].cpu()
         self.train_batch_idx = ckpt["training_step"]                              # model_pipeline.py:255-262
         return ckpt["epoch"]
 

@@ -58,7 +58,7 @@ def sae_forward(x, w_enc, b_enc, w_dec, b_dec, want_pre=True, want_dec=True, out
     pre = torch.empty((T, F), device=x.device, dtype=torch.float32) if want_pre else None
     dec = torch.empty((T, Cc), device=x.device, dtype=out_dtype) if want_dec else None
     out = L.SaeForwardOut(L.ptr(enc), L.dtype_code(enc), L.ptr(pre), L.ptr(dec), L.dtype_code(dec) if want_dec else 0)
-    L.check(L.load().svb_sae_forward(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(out)),
+    L.check(L.load().svb_sae_forward(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(out)),
             "svb_sae_forward")
     return enc, dec, pre
 
@@ -74,7 +74,7 @@ def gated_forward(x, w_gate, b_gate, b_mag, r_mag, w_dec, b_dec, out_dtype=torch
     via = torch.empty((T, Cc), device=x.device, dtype=out_dtype)
     code = L.dtype_code(enc)
     out = L.GatedForwardOut(L.ptr(enc), code, L.ptr(dec), code, L.ptr(rp), code, L.ptr(via), code)
-    L.check(L.load().svb_gated_forward(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(out)),
+    L.check(L.load().svb_gated_forward(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(out)),
             "svb_gated_forward")
     return enc, dec, rp, via
 
@@ -93,11 +93,17 @@ class StepResult:
 
 
 def _train_out(x, a, F, want_dec, dec_dtype):
+    """Outputs of one step.  The four small results are views of ONE uninitialised allocation (the finalise kernel
+    writes every element): a fresh block per step, so a StepResult a caller keeps is never overwritten, but no fill
+    kernel and a single allocator call per step."""
     dev = x.device
-    stats = torch.zeros(L.STATS_LEN, device=dev, dtype=torch.float32)
-    dead = torch.empty(F, device=dev, dtype=torch.uint8)
-    freq = torch.empty(F, device=dev, dtype=torch.float32)
-    n_active = torch.empty(a.n_images, device=dev, dtype=torch.int32)
+    n_img = int(a.n_images)
+    words = L.STATS_LEN + F + n_img
+    block = torch.empty(words * 4 + F, device=dev, dtype=torch.uint8)
+    f32 = block[:words * 4].view(torch.float32)
+    stats, freq = f32[:L.STATS_LEN], f32[L.STATS_LEN:L.STATS_LEN + F]
+    n_active = block[(L.STATS_LEN + F) * 4:words * 4].view(torch.int32)
+    dead = block[words * 4:]
     dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype) if want_dec else None
     out = L.TrainOut(L.ptr(dec), L.dtype_code(dec) if want_dec else 0, a.layout, L.ptr(stats),
                      L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active)))
@@ -121,7 +127,7 @@ def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, o
     out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
     st = _adam_state(adam_m, adam_v)
     opt = _opt(optimizer, step, lr, betas, eps)
-    L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
+    L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
                                         C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_sae_train_step")
     return _single_pixel_fixup(x, res)
@@ -135,7 +141,7 @@ def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor,
     out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
     st = _adam_state(adam_m, adam_v)
     opt = _opt(optimizer, step, lr, betas, eps)
-    L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(), C.byref(a), C.byref(p), C.byref(st),
+    L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
                                           C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_gated_train_step")
     return _single_pixel_fixup(x, res)
@@ -156,7 +162,7 @@ class SplitStep:
 
     def grads(self, global_tokens=0):
         fn = self.lib.svb_sae_step_grads if self.kind == "sae_mlp" else self.lib.svb_gated_step_grads
-        L.check(fn(self.h, L.stream_ptr(), C.byref(self.a), C.byref(self.p), self.lam, int(global_tokens),
+        L.check(fn(self.h, L.stream_ptr(self.x.device), C.byref(self.a), C.byref(self.p), self.lam, int(global_tokens),
                    C.byref(self.out)), "svb_*_step_grads")
         buf, n_sum, n_max = L._vp(), C.c_int64(), C.c_int64()
         L.check(self.lib.svb_sae_grad_buffer(self.h, C.byref(buf), C.byref(n_sum), C.byref(n_max)),
@@ -165,7 +171,7 @@ class SplitStep:
 
     def peer_allreduce(self):
         """In-place all-reduce of the flat buffer over NVLink peer memory (parallel.connect_peer_memory first)."""
-        L.check(self.lib.svb_comm_allreduce(self.h, L.stream_ptr()), "svb_comm_allreduce")
+        L.check(self.lib.svb_comm_allreduce(self.h, L.stream_ptr(self.x.device)), "svb_comm_allreduce")
 
     def early_elems(self):
         """Leading elements of the flat buffer that are final once the communication stream set with
@@ -179,7 +185,7 @@ class SplitStep:
         fn = self.lib.svb_sae_step_apply if self.kind == "sae_mlp" else self.lib.svb_gated_step_apply
         st = _adam_state(adam_m, adam_v)
         opt = _opt(optimizer, step, lr, betas, eps)
-        L.check(fn(self.h, L.stream_ptr(), C.byref(self.a), C.byref(self.p), C.byref(st), C.byref(opt), self.lam,
+        L.check(fn(self.h, L.stream_ptr(self.x.device), C.byref(self.a), C.byref(self.p), C.byref(st), C.byref(opt), self.lam,
                    int(expansion_factor), int(global_tokens), int(global_images), C.byref(self.out)),
                 "svb_*_step_apply")
         return _single_pixel_fixup(self.x, self.res)
@@ -190,6 +196,14 @@ def set_comm_stream(device, stream):
     every following svb_*_step_grads call on `device` (include/svb.h: svb_set_comm_stream)."""
     L.check(L.load().svb_set_comm_stream(L.handle(device), None if stream is None else stream.cuda_stream),
             "svb_set_comm_stream")
+
+
+def comm_status(device):
+    """0 when every peer-memory all-reduce on `device` completed; 1 + r when rank r never arrived within the timeout
+    (include/svb.h: svb_comm_status).  Synchronises with the device: call it per logging interval, not per step."""
+    st = C.c_int32()
+    L.check(L.load().svb_comm_status(L.handle(device), C.byref(st)), "svb_comm_status")
+    return st.value
 
 
 def wrap_device_buffer(address, n_elems, device):
@@ -214,7 +228,7 @@ def adam_step(params, grads, ms, vs, step, lr, betas, eps=1e-8, optimizer="adam"
     cols = (C.c_int64 * n)(*[p.shape[1] if p.dim() == 2 else p.numel() for p in params])
     gs = [None if g is None else g.contiguous() for g in grads]
     L.check(L.load().svb_adam_step(
-        L.handle(dev), L.stream_ptr(), n, arr(*[_f32c(p).data_ptr() for p in params]),
+        L.handle(dev), L.stream_ptr(dev), n, arr(*[_f32c(p).data_ptr() for p in params]),
         arr(*[0 if g is None else _f32c(g).data_ptr() for g in gs]), arr(*[_f32c(m).data_ptr() for m in ms]),
         arr(*[_f32c(v).data_ptr() for v in vs]), rows, cols, int(decoder_index),
         C.byref(_opt(optimizer, step, lr, betas, eps))), "svb_adam_step")
@@ -226,7 +240,7 @@ def reinit_dead(params, adam_m, adam_v, dead_mask_u8, new_w_enc, new_w_dec, new_
     p = _sae_params(*params)
     Cc = params[0].shape[1]
     st = _adam_state(adam_m, adam_v) if adam_m is not None else None
-    L.check(L.load().svb_reinit_dead(L.handle(params[0].device), L.stream_ptr(), C.byref(p), Cc,
+    L.check(L.load().svb_reinit_dead(L.handle(params[0].device), L.stream_ptr(params[0].device), C.byref(p), Cc,
                                      C.byref(st) if st is not None else None, L.ptr(dead_mask_u8.contiguous()),
                                      L.ptr(_f32c(new_w_enc)), L.ptr(_f32c(new_w_dec)), float(new_b_enc)),
             "svb_reinit_dead")
@@ -250,7 +264,7 @@ def measure_inactive(t):
     freq = torch.empty(f, device=t.device, dtype=torch.float32)
     n_active = torch.empty(rows, device=t.device, dtype=torch.int32)
     act = L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active))
-    L.check(L.load().svb_measure_inactive(L.handle(t.device), L.stream_ptr(), L.ptr(t), L.dtype_code(t), layout,
+    L.check(L.load().svb_measure_inactive(L.handle(t.device), L.stream_ptr(t.device), L.ptr(t), L.dtype_code(t), layout,
                                           n_img, hw, f, C.byref(act)), "svb_measure_inactive")
     return dead, freq, n_active
 
@@ -267,7 +281,7 @@ def ie_channelwise(a, avg, g, batch_size, scale=None):
     avg = avg.contiguous().float()
     out = torch.empty(F, device=a.device, dtype=torch.float32)
     sc = (1.0 / a.shape[0]) if scale is None else scale
-    L.check(L.load().svb_ie_channelwise(L.handle(a.device), L.stream_ptr(), L.ptr(a), L.ptr(g), L.dtype_code(a),
+    L.check(L.load().svb_ie_channelwise(L.handle(a.device), L.stream_ptr(a.device), L.ptr(a), L.ptr(g), L.dtype_code(a),
                                         L.ptr(avg), batch_size, H * W, F, float(sc), L.ptr(out)),
             "svb_ie_channelwise")
     return out
@@ -284,7 +298,7 @@ def ie_allchannels(err, avg, g, batch_size, scale=None):
     avg = avg.contiguous().float()
     out = torch.empty(1, device=err.device, dtype=torch.float32)
     sc = (1.0 / (B * H * W)) if scale is None else scale
-    L.check(L.load().svb_ie_allchannels(L.handle(err.device), L.stream_ptr(), L.ptr(err), L.ptr(g),
+    L.check(L.load().svb_ie_allchannels(L.handle(err.device), L.stream_ptr(err.device), L.ptr(err), L.ptr(g),
                                         L.dtype_code(err), L.ptr(avg), B, Cc, H * W, float(sc), L.ptr(out)),
             "svb_ie_allchannels")
     return out[0]
@@ -302,7 +316,7 @@ def node_ie_layer(x, grad, params, enc_avg, err_avg, x_avg, scale=None):
     err = torch.empty(1, device=dev, dtype=torch.float32)
     neur = torch.empty(a.C, device=dev, dtype=torch.float32)
     sc = (1.0 / _tokens(x)) if scale is None else scale
-    L.check(L.load().svb_node_ie_layer(L.handle(dev), L.stream_ptr(), C.byref(a), L.ptr(grad), C.byref(p),
+    L.check(L.load().svb_node_ie_layer(L.handle(dev), L.stream_ptr(dev), C.byref(a), L.ptr(grad), C.byref(p),
                                        L.ptr(enc_avg.contiguous().float()), L.ptr(err_avg.contiguous().float()),
                                        L.ptr(x_avg.contiguous().float()), float(sc), L.ptr(feat), L.ptr(err),
                                        L.ptr(neur)), "svb_node_ie_layer")
@@ -320,7 +334,7 @@ def gemm_bf16(A, B, a_mn=False, b_mn=False, out_dtype=torch.float32, alpha=1.0, 
     if K != Kb:
         raise ValueError(f"gemm_bf16: inner dimensions differ ({K} vs {Kb})")
     out = torch.empty((M, N), device=A.device, dtype=out_dtype)
-    L.check(L.load().svb_gemm_bf16(L.handle(A.device), L.stream_ptr(), L.ptr(A), int(a_mn), A.shape[1], L.ptr(B),
+    L.check(L.load().svb_gemm_bf16(L.handle(A.device), L.stream_ptr(A.device), L.ptr(A), int(a_mn), A.shape[1], L.ptr(B),
                                    int(b_mn), B.shape[1], M, N, K, L.ptr(out), L.dtype_code(out), N, float(alpha),
                                    L.ptr(bias.contiguous().float()) if bias is not None else None, int(relu)),
             "svb_gemm_bf16")

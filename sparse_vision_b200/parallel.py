@@ -117,5 +117,16 @@ class DataParallelStep:
             flat = ops.wrap_device_buffer(addr, n_sum + n_max, x_local.device)
             early = ss.early_elems() if self.comm_stream is not None else 0
             all_reduce_flat(flat, n_sum, n_max, self.group, early=early, comm_stream=self.comm_stream)
+        self.device = x_local.device
         return ss.apply(adam_m, adam_v, step, lr, expansion_factor, optimizer, betas, eps=eps,
                         global_tokens=global_tokens, global_images=global_images)
+
+    def check(self):
+        """Raises if a peer never arrived at one of the exchanges so far (the parameters are undefined from that step
+        on).  Synchronises with the device: call it per logging interval / before a checkpoint, not per step."""
+        if self.peer and getattr(self, "device", None) is not None:
+            from . import ops
+            st = ops.comm_status(self.device)
+            if st:
+                raise RuntimeError(f"data-parallel exchange: rank {st - 1} never arrived at an all-reduce "
+                                   f"(timeout; SVB_COMM_TIMEOUT_S)")

@@ -27,9 +27,9 @@ class _SvbAdamMixin:
     def _svb_step(self):
         for group in self.param_groups:
             b1, b2 = group["betas"]
-            params, grads, ms, vs = [], [], [], []
-            step_no = None
-            dec_index = -1
+            # torch.optim.Adam keeps one step count PER PARAMETER (a parameter that had no gradient in some step, or
+            # state loaded from a checkpoint, may be at a different count): one libsvb call per distinct count
+            by_step = {}
             for p in group["params"]:
                 if p.grad is None and p is not self._svb_constrained:
                     continue
@@ -40,24 +40,21 @@ class _SvbAdamMixin:
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if st["step"].is_cuda:                        # e.g. after load_state_dict(map_location=cuda)
+                    st["step"] = st["step"].cpu()
                 if p.grad is not None:
                     st["step"] += 1
-                    step_no = int(st["step"].item())
-                if p is self._svb_constrained:
-                    dec_index = len(params)
-                params.append(p.data)
-                grads.append(p.grad)
-                ms.append(st["exp_avg"])
-                vs.append(st["exp_avg_sq"])
-            if not params:
-                continue
-            if step_no is None:
-                step_no = 1
-            new_grads = ops.adam_step(params, grads, ms, vs, step_no, group["lr"], (b1, b2), group["eps"],
-                                      optimizer=self._svb_optimizer, decoder_index=dec_index)
-            # the projected decoder gradient is visible on p.grad afterwards, as in the reference (utils.py:74)
-            if dec_index >= 0 and grads[dec_index] is not None and new_grads[dec_index] is not grads[dec_index]:
-                grads[dec_index].copy_(new_grads[dec_index])
+                # the constrained tensor without a gradient is only renormalised (utils.py:76-79): any step count does
+                by_step.setdefault(max(int(st["step"].item()), 1), []).append(p)
+            for step_no, plist in by_step.items():
+                grads = [p.grad for p in plist]
+                dec_index = next((i for i, p in enumerate(plist) if p is self._svb_constrained), -1)
+                new_grads = ops.adam_step([p.data for p in plist], grads, [self.state[p]["exp_avg"] for p in plist],
+                                          [self.state[p]["exp_avg_sq"] for p in plist], step_no, group["lr"], (b1, b2),
+                                          group["eps"], optimizer=self._svb_optimizer, decoder_index=dec_index)
+                # the projected decoder gradient is visible on p.grad afterwards, as in the reference (utils.py:74)
+                if dec_index >= 0 and grads[dec_index] is not None and new_grads[dec_index] is not grads[dec_index]:
+                    grads[dec_index].copy_(new_grads[dec_index])
 
 
 class Adam(_SvbAdamMixin, torch.optim.Adam):

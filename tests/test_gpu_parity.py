@@ -341,10 +341,31 @@ def test_step_is_deterministic():
         assert torch.equal(a, b)
 
 
-def test_full_size_cfg2_step_properties():
-    """BASELINE configs[1] at its FULL size (256 images, C=256, 28x28, F=2048): properties that do not need the CPU
-    oracle -- bit-reproducibility, the step's scalars against what the returned tensors imply, and the dead-unit mask
-    against the encoder output of the forward API."""
+def _check_step_against_oracle(kind, p, keys, x_cpu_f32, lam, k, sc, dead, freq, dec, params, B):
+    """One fused step (scalars `sc`, dead mask, frequencies, reconstruction, updated `params`) against
+    oracle.train_step on the same bf16-representable activations.  Mutates `p` (the oracle's parameters)."""
+    st = O.new_adam_state(p, keys)
+    ref = O.train_step(kind, p, st, x_cpu_f32, lam, "constrained_adam", 1e-3, k)
+    for key in SCALARS:
+        tol = REL * max(abs(ref[key]), 1e-3)
+        assert abs(sc[key] - ref[key]) <= tol, f"{key}: got {sc[key]} want {ref[key]}"
+    assert np.array_equal(dead.cpu().numpy().astype(bool), ref["dead"].numpy()), "dead-unit mask differs from the oracle"
+    assert int(sc["n_dead"]) == int(ref["dead"].sum())
+    F = ref["freq"].numel()
+    dfreq = np.abs(freq.cpu().numpy() - ref["freq"].numpy())
+    assert dfreq.max() <= 1.0 / B + 1e-6, f"freq max diff {dfreq.max()}"
+    assert (dfreq > 1e-6).sum() <= max(F // 1000, 1), f"{(dfreq > 1e-6).sum()} units differ in frequency"
+    assert _relerr(dec.float().cpu().numpy(), ref["dec"].numpy()) < 2 * REL
+    for q, key in zip(params, keys):
+        diff = np.abs(q.cpu().numpy() - p[key].numpy())
+        assert diff.max() <= 2.5e-3, f"{key} max diff {diff.max()}"
+        assert np.quantile(diff, 0.95) <= 2e-4, f"{key} p95 diff {np.quantile(diff, 0.95)}"
+
+
+def test_full_size_cfg2_step_vs_oracle_and_properties():
+    """BASELINE configs[1] at its FULL size (256 images, C=256, 28x28, F=2048 = 200,704 tokens): the fused step against
+    oracle.train_step on the same activations (scalars, dead-unit mask, frequencies, reconstruction, updated
+    parameters), plus bit-reproducibility and the step's scalars against what the returned tensors imply."""
     ops = _ops()
     B, C, H, W, k = 256, 256, 28, 28, 8
     F = C * k
@@ -383,9 +404,13 @@ def test_full_size_cfg2_step_properties():
     l1 = enc.float().abs().mean().item()
     assert abs(sc1["l1"] - l1) <= 1e-2 * l1
     assert abs(sc1["loss"] - (sc1["rec"] + 5.0 * sc1["l1"])) <= 1e-5 * sc1["loss"]
+    del enc, dec_f, xf, df
+    # the CPU oracle on all 200,704 tokens (a few seconds and a few GB of host memory)
+    _check_step_against_oracle("sae_mlp", p, O.SAE_MLP_KEYS, x.float().cpu(), 5.0, k, sc1, dead1, res1.freq, dec1,
+                               params1, B)
 
 
-def test_full_size_cfg3_gated_step_properties():
+def test_full_size_cfg3_gated_step_vs_oracle_and_properties():
     """BASELINE configs[2] at its FULL per-GPU size (GatedSae, 256 images, C=512, 14x14, F=8192): bit-reproducibility
     and the step's scalars against what the forward API's tensors imply (losses/sparse_loss.py:68-76,
     utils.py:2455-2473), plus the dead-unit mask against the encoder output (utils.py:2032-2069)."""
@@ -405,10 +430,10 @@ def test_full_size_cfg3_gated_step_properties():
         ms = [torch.zeros_like(q) for q in params]
         vs = [torch.zeros_like(q) for q in params]
         res = ops.gated_train_step(x, params, ms, vs, 1, 1e-3, lam, k, optimizer="constrained_adam")
-        return params, res.scalars(), res.dec.clone(), res.dead.clone()
+        return params, res.scalars(), res.dec.clone(), res.dead.clone(), res.freq.clone()
 
-    params1, sc1, dec1, dead1 = run()
-    params2, sc2, dec2, dead2 = run()
+    params1, sc1, dec1, dead1, freq1 = run()
+    params2, sc2, dec2, dead2, _ = run()
     assert sc1 == sc2 and torch.equal(dec1, dec2) and torch.equal(dead1, dead2)          # bit-reproducible
     for a, b in zip(params1, params2):
         assert torch.equal(a, b)
@@ -425,6 +450,9 @@ def test_full_size_cfg3_gated_step_properties():
     active = (enc.reshape(B, H * W, F) != 0).any(dim=1).any(dim=0)
     assert torch.equal(dead1.bool(), ~active)
     assert int(sc1["n_dead"]) == int((~active).sum().item()) >= F // 20
+    del enc, dec_f, rp, via, x_tok
+    # the CPU oracle on all 50,176 tokens x 8,192 features
+    _check_step_against_oracle("gated_sae", p, O.GATED_KEYS, x.float().cpu(), lam, k, sc1, dead1, freq1, dec1, params1, B)
 
 
 @pytest.mark.parametrize("B,C,H,W,k", [
@@ -469,3 +497,77 @@ def test_forward_api_shapes_vs_oracle(B, C, H, W, k, kind):
                 # or vanishes (heaviside, gated_sae.py:39): such near-ties are taken out of the element-wise comparison
                 an, bn = np.where(near_tie, 0.0, an), np.where(near_tie, 0.0, bn)
             assert _relerr(an, bn) < tol, (nm, str(dt))
+
+
+# ------------------------------------------------------------------------------------------------ module granularity
+@pytest.mark.parametrize("kind,opt_name", [("sae_mlp", "constrained_adam"), ("sae_mlp", "adam"),
+                                           ("gated_sae", "constrained_adam")])
+def test_module_autograd_backward_and_optimizer_step_vs_oracle(kind, opt_name):
+    """The reference's own sequence at module granularity (model_pipeline.py:380-388): sae_inference_and_loss ->
+    loss.backward() through the models' autograd Functions -> optimizer.step() of the Adam / ConstrainedAdam front --
+    gradients, losses and the updated parameters against the oracle (= the reference's autograd), three steps."""
+    from sparse_vision_b200 import utils as U
+    B, C, H, W, k = 4, 64, 9, 9, 4
+    lam = 5.0 if kind == "sae_mlp" else 0.1
+    keys = O.SAE_MLP_KEYS if kind == "sae_mlp" else O.GATED_KEYS
+    crit_name = "sae_loss" if kind == "sae_mlp" else "gated_sae_loss"
+    torch.manual_seed(0)
+    model = U.load_model(kind, img_size=C, expansion_factor=k)
+    with torch.no_grad():
+        model.decoder.bias.normal_(0, 0.05, generator=torch.Generator().manual_seed(2))
+    p = {key: v.detach().clone() for key, v in model.state_dict().items()}
+    assert list(p) == list(keys)
+    model = model.cuda()
+    opt, _ = U.get_optimizer(opt_name, model, 1e-3)
+    crit = U.get_criterion(crit_name)
+    st = O.new_adam_state(p, keys)
+    for step in range(3):
+        x = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(60 + step))).bfloat16().float()
+        with torch.enable_grad():
+            out = U.sae_inference_and_loss(kind, model, crit_name, x.cuda(), crit, lam)
+        loss, rec, l1, nrmse, rmse, aux, enc, pre, dec = out
+        assert enc.shape == (B, C * k, H, W) and dec.shape == x.shape and (pre is None) == (kind == "gated_sae")
+        opt.zero_grad()
+        loss.backward()
+        grads = {key: q.grad.detach().clone().cpu() for key, q in zip(keys, model.param_list())}
+        opt.step()
+        opt.zero_grad()
+        ref = O.train_step(kind, p, st, x, lam, opt_name, 1e-3, k)
+        for name, got in (("loss", loss), ("rec", rec), ("l1", l1), ("nrmse", nrmse), ("rmse", rmse), ("aux", aux)):
+            assert abs(float(got) - ref[name]) <= REL * max(abs(ref[name]), 1e-3), (step, name, float(got), ref[name])
+        for key in keys:
+            want = ref["grads"][key].numpy()
+            fro = np.linalg.norm(grads[key].numpy() - want) / max(np.linalg.norm(want), 1e-12)
+            assert fro <= 2e-2, (step, key, fro)
+        assert _relerr(dec.detach().float().cpu().numpy(), ref["dec"].numpy()) < 2 * REL
+        for key, q in zip(keys, model.param_list()):
+            diff = np.abs(q.detach().cpu().numpy() - p[key].numpy())
+            assert diff.max() <= 2.5e-3 * (step + 1) and np.quantile(diff, 0.95) <= 3e-4 * (step + 1), (step, key, diff.max())
+        # the optimizer front keeps torch.optim.Adam's state layout (sae_mlp.py:148-176 indexes it)
+        s0 = opt.state[model.param_list()[0]]
+        assert set(s0) >= {"step", "exp_avg", "exp_avg_sq"} and int(s0["step"]) == step + 1
+        np.testing.assert_allclose(s0["exp_avg"].cpu().numpy(), st["m"][keys[0]].numpy(), rtol=0,
+                                   atol=2e-2 * float(st["m"][keys[0]].abs().max()))
+
+
+def test_apply_sae_ablation_vs_reference_golden(golden_dir):
+    """utils.py:2786-2820 with `nodes=` / `ablation=` (the branch compute_faithfulness uses): features outside `nodes`
+    are replaced by their average before decoding -- against the reference's own output (ie_small.npz:ablated_dec)."""
+    from sparse_vision_b200 import utils as U
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    g = _load(golden_dir, "ie_small.npz")
+    sae = SaeMLP(24, 4)
+    sae.load_state_dict({k: torch.from_numpy(g["init." + k]) for k in O.SAE_MLP_KEYS})
+    sae = sae.cuda().eval()
+    x = torch.from_numpy(g["x"]).cuda()
+    nodes = torch.from_numpy(g["nodes"]).cuda()
+    assert 0 < int(nodes.sum()) < nodes.numel()
+    enc_avg = torch.from_numpy(g["enc_avg"]).cuda()
+    with torch.no_grad():
+        enc, dec, new_dec = U.apply_sae(sae, x, nodes=nodes, ablation=enc_avg)
+        enc0, dec0, same = U.apply_sae(sae, x)
+    assert _relerr(enc.cpu().numpy(), g["enc"]) < REL
+    assert _relerr(dec.cpu().numpy(), g["dec"]) < 2 * REL
+    assert _relerr(new_dec.cpu().numpy(), g["ablated_dec"]) < 2 * REL
+    assert torch.equal(same, dec0)                                   # no nodes: the reconstruction itself (:2809)
+    assert _relerr(new_dec.cpu().numpy(), g["dec"]) > 10 * REL       # the ablation did change the output
