@@ -190,6 +190,10 @@ def _traffic():
     return {}
 
 
+CONFIG_WORKLOAD = ("configs[1]: SaeMLP (pixels-as-tokens) C=256 28x28 k=8 F=2048 constrained_adam lambda=5, 256 images = "
+                   "200704 tokens per GPU per step, GoogLeNet inception3a-shaped activations")
+
+
 def cpu_reference_throughput(n_images, steps, warmup, threads=None):
     """The reference algorithm on the host cores: oracle/sae_oracle.py (a restatement pinned to the real reference by
     tests/golden) running the same step on a bounded sample of the same workload (same C, F, HW, optimizer)."""
@@ -210,14 +214,96 @@ def cpu_reference_throughput(n_images, steps, warmup, threads=None):
     return tokens / dt, dt * 1e3, torch.get_num_threads()
 
 
+def cpu_reference_pipeline(n_images, steps, warmup):
+    """The reference's whole train batch on the host cores (model_pipeline.py:603-708): frozen GoogLeNet forward whose
+    inception3a hook runs the SAE training step (oracle) and hands the reconstruction back, the unhooked copy's forward,
+    KL divergence / same-classification.  Returns (tokens/s, ms per batch)."""
+    import copy
+    from oracle import sae_oracle as O
+    from sparse_vision_b200.producer import synthetic_googlenet
+    base = synthetic_googlenet(seed=0)
+    ref_copy = copy.deepcopy(base)
+    torch.manual_seed(0)
+    p = O.init_sae_mlp(C_ACT, EXPANSION)
+    st = O.new_adam_state(p, O.SAE_MLP_KEYS)
+
+    def hook(_m, _i, out):
+        with torch.enable_grad():                       # model_pipeline.py:380
+            r = O.train_step("sae_mlp", p, st, out.detach(), LAMBDA, "constrained_adam", LR, EXPANSION)
+        return r["dec"]
+
+    base.inception3a.register_forward_hook(hook)
+    x = torch.randn(n_images, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+
+    def batch():
+        with torch.no_grad():
+            out = base(x)
+            orig = ref_copy(x)
+            lp_o, lp_m = torch.log_softmax(orig, 1), torch.log_softmax(out, 1)
+            kld = torch.nn.functional.kl_div(lp_o, lp_m, reduction="sum", log_target=True).item() / n_images
+            same = (orig.argmax(1) == out.argmax(1)).sum().item() / n_images
+        return kld, same
+
+    for _ in range(warmup):
+        batch()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        batch()
+    dt = (time.perf_counter() - t0) / steps
+    return n_images * HW_SIDE * HW_SIDE / dt, dt * 1e3
+
+
+def gpu_eager_reference(dev, x_bf16, iters=5):
+    """SURVEY.md 8(d) / BASELINE.md 3, "the real kernel to beat": the reference algorithm (oracle/sae_oracle.py, i.e. the
+    reference modules' own PyTorch ops) run unchanged in eager mode ON THIS GPU at the full configs[1] size -- fp32 as the
+    reference ships it, with TF32 allowed, and under bf16 autocast.  Every FLOP there is a cuBLAS call."""
+    from oracle import sae_oracle as O
+    out = {}
+    x = x_bf16.float()
+    T = x.shape[0] * x.shape[2] * x.shape[3]
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+            torch.manual_seed(0)
+            p = {k: v.to(dev) for k, v in O.init_sae_mlp(C_ACT, EXPANSION).items()}
+            st = O.new_adam_state(p, O.SAE_MLP_KEYS)
+
+            def step():
+                if mode == "bf16_autocast":
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return O.train_step("sae_mlp", p, st, x, LAMBDA, "constrained_adam", LR, EXPANSION)
+                return O.train_step("sae_mlp", p, st, x, LAMBDA, "constrained_adam", LR, EXPANSION)
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                r = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[mode] = {"ms_per_step": ms, "act_vec_per_s": T / (ms * 1e-3), "loss": r["loss"]}
+            del p, st, r
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    out["what"] = ("oracle.train_step (the reference's PyTorch ops: 6 cuBLAS GEMMs, ~30 elementwise / reduction kernels, "
+                   "6+ host syncs) on cuda, same 200704-token batch")
+    return out
+
+
 def gated_section(dev, peaks, n_images=256, iters=10, world=1):
     """configs[2]: GatedSae on inception4c-shaped activations (C=512, 14x14, expansion 16 -> F=8192), one fused training
     step per call on bf16 NCHW activations resident in HBM; 12*C*F FLOP per token.  world > 1:
     data parallel like the main workload (n_images per GPU, peer-memory all-reduce of the flat gradient buffer; every
     rank calls this, times are the max over ranks)."""
-    from sparse_vision_b200 import ops
+    from sparse_vision_b200 import _lib as L, ops
     from sparse_vision_b200.models.gated_sae import GatedSae
     from sparse_vision_b200.parallel import DataParallelStep
+    import ctypes as C
     import torch.distributed as dist
     Cc, side, k = 512, 14, 16
     F, T = Cc * k, n_images * side * side
@@ -245,35 +331,63 @@ def gated_section(dev, peaks, n_images=256, iters=10, world=1):
     for i in range(3):
         res = step(i, i + 1)
     barrier()
+    lib, h = L.load(), L.handle(dev)
+    L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
         res = step(i, i + 4)
     e1.record()
     barrier()
+    phases = _read_phases(lib, h)
+    L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
     t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     tf = 12.0 * Cc * F * T / (ms * 1e-3) / 1e12          # per GPU
     sc = res.scalars()
+    if dp is not None:
+        dp.check()
     return {"workload": f"configs[2]: GatedSae C=512 14x14 k=16 F=8192, 256 images = 50176 tokens per GPU, "
                         f"constrained_adam, bf16 NCHW, dp{world}",
             "n_gpus": world, "ms_per_step": ms, "act_vec_per_s": world * T / (ms * 1e-3), "algorithmic_tflops_per_gpu": tf,
+            "frac_of_burst_peak": tf / peaks["bf16_burst"] if peaks["bf16_burst"] else None,
             "frac_of_sustained_peak": tf / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
+            "phases_ms": phases,
             "final_step_stats": {kk: sc[kk] for kk in ("loss", "rec", "l1", "aux")}}
 
 
-def ie_section(dev, peaks, n_images=64, iters=20):
+def _read_phases(lib, h):
+    import ctypes as C
+    from sparse_vision_b200 import _lib as L
+    phase_ms = (C.c_float * 16)()
+    n_ph, n_st = C.c_int32(), C.c_int32()
+    L.check(lib.svb_profile_read(h, 16, phase_ms, C.byref(n_ph), C.byref(n_st)), "svb_profile_read")
+    return {lib.svb_profile_phase_name(i).decode(): float(phase_ms[i]) for i in range(n_ph.value)}
+
+
+def ie_section(dev, peaks, n_images=64, iters=20, world=1):
     """IE images/sec (second half of the BASELINE.json metric) at cfg5 / mixed3a: F=2048 SAE features on 28x28 maps.
     Times (a) the stand-alone compute_ie_channel_wise reduction (utils.py:2606-2637) on fp32 and bf16 [T,F] inputs —
     HBM roofline, algorithmic bytes 2*T*F*s + F*HW*4 + F*4 — and (b) the fused per-layer node-IE
-    (encoder GEMM, decoder GEMM, g W_dec GEMM and the three reductions) in images/s."""
+    (encoder GEMM, decoder GEMM, g W_dec GEMM and the three reductions) in images/s.  world > 1: the pass shards by
+    image with no data-path collective, so every rank times its own n_images and the job rate is world x n_images over
+    the slowest rank's time."""
+    import torch.distributed as dist
     from sparse_vision_b200 import ops
     F, HW, Cc = C_ACT * EXPANSION, HW_SIDE * HW_SIDE, C_ACT
     T = n_images * HW
-    g = torch.Generator(device="cpu").manual_seed(7)
+    rank = dist.get_rank() if world > 1 else 0
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
     out = {}
+
+    def job_ms(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     avg = torch.rand(F, HW_SIDE, HW_SIDE, generator=g).to(dev)
     for name, dt, sz in (("f32", torch.float32, 4), ("bf16", torch.bfloat16, 2)):
         # two rotating input sets so that every timed launch reads from HBM, not L2 (2 x 2 x T*F*sz > 126 MB)
@@ -288,16 +402,17 @@ def ie_section(dev, peaks, n_images=64, iters=20):
             ops.ie_channelwise(sets[i % 2][0], avg, sets[i % 2][1], n_images)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        ms = job_ms(e0.elapsed_time(e1) / iters)
         nbytes = 2.0 * T * F * sz + F * HW * 4 + F * 4
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": gbs / peaks["hbm"] if peaks["hbm"] else None, "images_per_s": n_images / (ms * 1e-3)}
+                     "frac": gbs / peaks["hbm"] if peaks["hbm"] else None, "per": "GPU",
+                     "images_per_s": world * n_images / (ms * 1e-3)}
         del sets
     # fused node-IE of one layer on bf16 NCHW activations / gradients
     model = _make_params()
     params = [p.detach().clone().to(dev) for p in model.param_list()]
-    x = [_synthetic_acts(n_images, 900 + i).to(torch.bfloat16).to(dev) for i in range(2)]
+    x = [_synthetic_acts(n_images, 900 + i + 10 * rank).to(torch.bfloat16).to(dev) for i in range(2)]
     gr = [torch.randn(n_images, Cc, HW_SIDE, HW_SIDE, generator=g).to(torch.bfloat16).to(dev) for _ in range(2)]
     err_avg = torch.zeros(Cc, HW_SIDE, HW_SIDE, device=dev)
     x_avg = x[0].float().mean(0)
@@ -310,12 +425,110 @@ def ie_section(dev, peaks, n_images=64, iters=20):
         ops.node_ie_layer(x[i % 2], gr[i % 2], params, avg, err_avg, x_avg)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out["node_ie_layer"] = {"ms": ms, "images_per_s": n_images / (ms * 1e-3),
+    ms = job_ms(e0.elapsed_time(e1) / iters)
+    out["node_ie_layer"] = {"ms": ms, "images_per_s": world * n_images / (ms * 1e-3),
                             "what": "svb_node_ie_layer: enc + dec + g*W_dec GEMMs and 3 reductions, one layer"}
-    out["config"] = {"workload": "configs[4] / mixed3a: C=256, F=2048, 28x28, %d images per call" % n_images,
+    out["n_gpus"] = world
+    out["config"] = {"workload": "configs[4] / mixed3a: C=256, F=2048, 28x28, %d images per call per GPU" % n_images,
                      "peak_source": peaks["source"] + ", hbm copy"}
     return out
+
+
+IE_LAYERS = {"mixed3a": 8, "mixed4c": 4, "mixed5b": 4}   # cfg5: three GoogLeNet layers, expansion per utils.py:2671-2724
+
+
+def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
+    """configs[4] end to end: IE.compute_average then IE.compute_node_ie (compute_ie.py:95-226, :365-472) over three
+    GoogLeNet layers on 224x224 images -- ONE frozen forward + backward of the base model per batch (cuDNN) and, per
+    layer, the SAE encoder / decoder / g W_dec GEMMs and the three reductions of libsvb.  Images are sharded across the
+    ranks; the only exchange is the final all-reduce of the per-layer sums."""
+    import torch.distributed as dist
+    from sparse_vision_b200.compute_ie import IE
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    from sparse_vision_b200.producer import GOOGLENET_LAYERS, hooked_layers
+    rank = dist.get_rank() if world > 1 else 0
+    saes = {}
+    for j, (n, k) in enumerate(IE_LAYERS.items()):
+        torch.manual_seed(5 + j)
+        saes[n] = SaeMLP(GOOGLENET_LAYERS[n][1], k).to(dev)
+    dt = next(base.parameters()).dtype
+    g = torch.Generator().manual_seed(40 + rank)
+    batches = [(torch.randn(n_images, 3, 224, 224, generator=g).to(dev, dt),
+                torch.randint(0, 1000, (n_images,), generator=g).to(dev)) for _ in range(n_batches)]
+    ie = IE(base, hooked_layers(base, list(IE_LAYERS)), saes, dict(IE_LAYERS), device=dev)
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t[0])
+
+    avg, _ = timed(lambda: ie.compute_average([b[0] for b in batches]))          # warm-up (cuDNN autotune, arena)
+    ie.compute_node_ie(batches[:1], avg)
+    avg, ms_avg = timed(lambda: ie.compute_average([b[0] for b in batches]))
+    (feat, err, neur), ms_ie = timed(lambda: ie.compute_node_ie(batches, avg))
+    n_job = world * n_images * n_batches
+    top = {n: [int(i) for i in torch.topk(feat[n], 5).indices.tolist()] for n in feat}
+    return {"workload": f"configs[4]: node IE over {list(IE_LAYERS)} of GoogLeNet ({dt}), {n_images} images x {n_batches} "
+                        f"batches per GPU, 224x224", "n_gpus": world,
+            "compute_average_images_per_s": n_job / (ms_avg * 1e-3), "compute_node_ie_images_per_s": n_job / (ms_ie * 1e-3),
+            "ms_per_batch_node_ie": ms_ie / n_batches, "ms_per_batch_average": ms_avg / n_batches,
+            "top5_features": top}
+
+
+def dp_parity_check(dev, world, rank):
+    """N > 1 (the driver's GPU-test box has one GPU): two data-parallel steps of each SAE kind on a small shape, every
+    rank on its image shard, against ONE rank stepping on the whole batch with the same library; replicas must stay
+    bit-identical across ranks.  Runs before the timed region; returns a dict for the JSON line."""
+    import torch.distributed as dist
+    from sparse_vision_b200 import ops
+    from sparse_vision_b200.models.gated_sae import GatedSae
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    from sparse_vision_b200.parallel import DataParallelStep, shard_images
+    worst, identical, ok = 0.0, True, True
+    for kind, cls in (("sae_mlp", SaeMLP), ("gated_sae", GatedSae)):
+        Cc, k, B, H = 64, 4, 3 * world, 7
+        torch.manual_seed(0)
+        m = cls(Cc, k)
+        init = [p.detach().clone() for p in m.param_list()]
+        x = torch.relu(torch.randn(B, Cc, H, H, generator=torch.Generator().manual_seed(11))).bfloat16()
+        lo, hi = shard_images(B, rank, world)
+        params = [p.clone().to(dev) for p in init]
+        ms_ = [torch.zeros_like(q) for q in params]
+        vs_ = [torch.zeros_like(q) for q in params]
+        dp = DataParallelStep(kind)
+        for step in (1, 2):
+            res = dp.step(x[lo:hi].to(dev), params, ms_, vs_, step, 1e-3, 0.5, k, "constrained_adam", (0.9, 0.999), B, B * H * H)
+        dp.check()
+        ref_params = [p.clone().to(dev) for p in init]
+        rm = [torch.zeros_like(q) for q in ref_params]
+        rv = [torch.zeros_like(q) for q in ref_params]
+        fn = ops.sae_train_step if kind == "sae_mlp" else ops.gated_train_step
+        for step in (1, 2):
+            ref = fn(x.to(dev), ref_params, rm, rv, step, 1e-3, 0.5, k, optimizer="constrained_adam")
+        got, want = res.scalars(), ref.scalars()
+        for key in ("loss", "rec", "l1", "var_expl", "sparsity", "n_dead"):
+            ok &= abs(got[key] - want[key]) <= 1e-4 * max(abs(want[key]), 1e-3)
+        ok &= bool(torch.equal(res.dead, ref.dead))
+        for a, b in zip(params, ref_params):
+            d = (a - b).abs()
+            worst = max(worst, d.max().item())
+            ok &= d.max().item() <= 4.2e-3 and d.mean().item() <= 2e-5   # a sign flip of a ~0 gradient: 2*lr per step
+            other = a.clone()
+            dist.broadcast(other, src=0)
+            identical &= bool(torch.equal(other, a))
+    flag = torch.tensor([1 if (ok and identical) else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"ok": bool(flag.item()), "replicas_bit_identical": identical, "max_param_diff_vs_single_rank": worst,
+            "what": "2 DP steps (SaeMLP + GatedSae, C=64 k=4 7x7, 3 images per rank) vs one rank on the whole batch"}
 
 
 def run_reference(args):
@@ -323,16 +536,22 @@ def run_reference(args):
     if rank != 0:
         return 0
     n_img = args.cpu_images
-    value, ms, cores = cpu_reference_throughput(n_img, args.steps, max(args.warmup, 1), os.cpu_count())
-    sample = f"{n_img} images = {n_img * HW_SIDE * HW_SIDE} tokens per step of the same workload (fp32, torch CPU)"
+    warm = max(args.warmup, 1)
+    value, ms, cores = cpu_reference_throughput(n_img, args.steps, warm, os.cpu_count())
+    e2e_value, e2e_ms = cpu_reference_pipeline(n_img, max(args.steps // 4, 2), 1)
+    sample = (f"{n_img} images = {n_img * HW_SIDE * HW_SIDE} tokens per step of the same workload (fp32, torch CPU, "
+              f"{cores} threads); per-token cost is batch-independent")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: SaeMLP C=256 28x28 k=8 constrained_adam lambda=5 (CPU sample)",
-                   "images_per_step": n_img, "tokens_per_step": n_img * HW_SIDE * HW_SIDE},
+        "config": {"workload": CONFIG_WORKLOAD, "sample_images_per_step": n_img,
+                   "sample_tokens_per_step": n_img * HW_SIDE * HW_SIDE},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms_per_step": e2e_ms,
+                "note": "ModelPipeline-equivalent train batch on the CPU: GoogLeNet forward with the SAE training step in "
+                        "the inception3a hook + unhooked copy forward + KLD, same sample size"},
         "gpu_launches": 0,
     }
     _emit(line)
@@ -340,10 +559,13 @@ def run_reference(args):
 
 
 def run_svb(args):
+    import copy
+    import math
     import torch.distributed as dist
     from sparse_vision_b200 import _lib as L, ops
+    from sparse_vision_b200.model_pipeline import ModelPipeline
     from sparse_vision_b200.parallel import DataParallelStep
-    import ctypes as C
+    from sparse_vision_b200.producer import synthetic_googlenet, to_producer_format
 
     world, rank, local = _env_int("WORLD_SIZE", 1), _env_int("RANK", 0), _env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -352,17 +574,24 @@ def run_svb(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    skip = set(args.skip.split(",")) if args.skip else set()
     B = args.images
     T = B * HW_SIDE * HW_SIDE
     F = C_ACT * EXPANSION
+    peaks = _peaks()
+    dp_parity = None
+    if world > 1 and "dp_parity" not in skip:
+        try:
+            dp_parity = dp_parity_check(dev, world, rank)
+        except Exception as exc:
+            dp_parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
     model = _make_params()
     params = [p.detach().clone().to(dev) for p in model.param_list()]
     ms_ = [torch.zeros_like(p) for p in params]
     vs_ = [torch.zeros_like(p) for p in params]
     numa_node = _bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else None
     # two distinct resident batches (2 x 103 MB > 126 MB L2), bf16 NCHW as the base model would emit them
-    host = [_synthetic_acts(B, 1234 + 17 * rank + i).to(torch.bfloat16).pin_memory() for i in range(2)]
-    xdev = [h.to(dev) for h in host]
+    xdev = [_synthetic_acts(B, 1234 + 17 * rank + i).to(torch.bfloat16).to(dev) for i in range(2)]
     lib, h = L.load(), L.handle(dev)
     dp = DataParallelStep("sae_mlp") if world > 1 else None
     g_images, g_tokens = B * world, T * world
@@ -380,6 +609,12 @@ def run_svb(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def job_max(*vals):
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
     for i in range(args.warmup):
         res = one_step(xdev[i % 2])
@@ -401,110 +636,186 @@ def run_svb(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.svb_launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    phase_ms = (C.c_float * 16)()
-    n_ph, n_st = C.c_int32(), C.c_int32()
-    L.check(lib.svb_profile_read(h, 16, phase_ms, C.byref(n_ph), C.byref(n_st)), "svb_profile_read")
+    phases = _read_phases(lib, h)
     L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
-    phases = {lib.svb_profile_phase_name(i).decode(): float(phase_ms[i]) for i in range(n_ph.value)}
     last_stats = res.scalars()
-
-    # ---------------------------------------------------------------- e2e: host buffers in, result scalars out
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty_like(xdev[0]) for _ in range(2)]
-    stats_host = torch.empty(L.STATS_LEN, dtype=torch.float32).pin_memory()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-    main = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    copy_stream.wait_event(e0)
-    n_e2e = args.steps
-    with torch.cuda.stream(copy_stream):
-        stage[0].copy_(host[0], non_blocking=True)
-        ready[0].record(copy_stream)
-    for i in range(n_e2e):
-        cur, nxt = i % 2, (i + 1) % 2
-        if i + 1 < n_e2e:
-            with torch.cuda.stream(copy_stream):
-                if i >= 1:
-                    copy_stream.wait_event(freed[nxt])
-                stage[nxt].copy_(host[nxt], non_blocking=True)     # H2D of step i+1 overlaps the compute of step i
-                ready[nxt].record(copy_stream)
-        main.wait_event(ready[cur])
-        r = one_step(stage[cur])
-        freed[cur].record(main)
-        stats_host.copy_(r.stats, non_blocking=True)               # D2H of the step's result
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    (ms_total,) = job_max(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = g_tokens / (ms_step * 1e-3)
-    e2e_value = g_tokens / (ms_e2e / n_e2e * 1e-3)
 
-    # configs[2] (GatedSae, quoted on 2/4/8 GPUs) rides along: collective at N > 1, so every rank runs it
-    # (at N > 1 only on request: a failed collective there must never cost the main line)
-    gated = None
-    if not args.no_ie and (world == 1 or args.gated_dp):
+    # ---------------------------------------------------------------- sustained leg: seconds of back-to-back steps
+    sustained = None
+    if "sustained" not in skip and args.sustain_s > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms_step)))
+        L.check(lib.svb_profile_enable(h, 1), "svb_profile_enable")
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.prepare()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler2.start()
+        s0.record()
+        for i in range(n_sus):
+            res = one_step(xdev[i % 2])
+        s1.record()
+        barrier()
+        clocks2 = sampler2.stop() if rank == 0 else None
+        phases_sus = _read_phases(lib, h)          # the last 128 steps of the leg
+        L.check(lib.svb_profile_enable(h, 0), "svb_profile_enable")
+        (ms_sus,) = job_max(s0.elapsed_time(s1))
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,
+                     "value": g_tokens / (ms_sus / n_sus * 1e-3), "clocks": clocks2, "phases_ms_last_128_steps": phases_sus}
+    if dp is not None:
+        dp.check()
+
+    # ---------------------------------------------------------------- e2e: host images in -> ModelPipeline.hook -> stats out
+    e2e = None
+    base = None
+    if "e2e" not in skip:
+        base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=args.channels_last)
+        base_copy = copy.deepcopy(base)
+        sae = _make_params().to(dev)
+        pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", LR, LAMBDA, EXPANSION,
+                             data_parallel=world > 1, global_batch_images=g_images if world > 1 else None,
+                             model_copy=base_copy)
+        pipe.register_hooks(train_sae=True)
+        gi = torch.Generator().manual_seed(77 + rank)
+        host = [torch.randn(B, 3, 224, 224, generator=gi).to(torch.bfloat16).pin_memory() for _ in range(2)]
+        tgt = torch.randint(0, 1000, (B,), generator=gi).to(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty(host[0].shape, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+        if args.channels_last:
+            stage = [s.contiguous(memory_format=torch.channels_last) for s in stage]
+            host = [hh.contiguous(memory_format=torch.channels_last).pin_memory() for hh in host]
+        stats_host = torch.empty(L.STATS_LEN + 3, dtype=torch.float32).pin_memory()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
+        for i in range(3):                                    # warm-up: cuDNN heuristics, arena growth
+            stage[i % 2].copy_(host[i % 2], non_blocking=True)
+            pipe.train_batch(stage[i % 2], targets=tgt)
+        barrier()
+        launches_e0 = lib.svb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        copy_stream.wait_event(e0)
+        n_e2e = args.steps
+        with torch.cuda.stream(copy_stream):
+            stage[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n_e2e):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < n_e2e:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(freed[nxt])
+                    stage[nxt].copy_(host[nxt], non_blocking=True)     # H2D of batch i+1 overlaps the compute of batch i
+                    ready[nxt].record(copy_stream)
+            main.wait_event(ready[cur])
+            pipe.train_batch(stage[cur], targets=tgt)
+            freed[cur].record(main)
+            stats_host[:L.STATS_LEN].copy_(pipe._last.stats, non_blocking=True)       # D2H of the batch's results
+            stats_host[L.STATS_LEN:].copy_(pipe.batch_model_stats, non_blocking=True)
+        e1.record()
+        barrier()
+        (ms_e2e,) = job_max(e0.elapsed_time(e1))
+        if pipe.dp is not None:
+            pipe.dp.check()
+        pipe.remove_hooks()
+        sh = stats_host.tolist()
+        e2e = {"value": g_tokens / (ms_e2e / n_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": host[0].numel() * 2 * world, "d2h_bytes_per_step": (L.STATS_LEN + 3) * 4 * world,
+               "ms_per_step": ms_e2e / n_e2e, "images_per_s": g_images / (ms_e2e / n_e2e * 1e-3),
+               "svb_launches_per_step": (lib.svb_launch_count() - launches_e0) / n_e2e,
+               "last_batch": {"loss": sh[0], "rec": sh[1], "kld": sh[L.STATS_LEN], "same_classification": sh[L.STATS_LEN + 1],
+                              "loss_diff": sh[L.STATS_LEN + 2]},
+               "numa_node_rank0": numa_node,
+               "note": "ModelPipeline.train_batch on pinned host images (bf16 3x224x224): H2D (overlapped on a copy stream) "
+                       "-> frozen GoogLeNet forward (bf16%s, cuDNN) whose inception3a hook runs the fused SAE training step "
+                       "and hands the reconstruction back -> rest of the network -> unhooked copy forward -> KLD / "
+                       "same-classification -> stats + comparison scalars D2H" % (", channels_last" if args.channels_last else "")}
+        del pipe, base_copy, host, stage
+
+    # ---------------------------------------------------------------- side sections (collective at N > 1: every rank runs them)
+    def guarded(fn):
         try:
-            gated = gated_section(dev, _peaks(), world=world)
+            return fn()
         except Exception as exc:       # a failure of a side section must never cost the main line
-            gated = {"error": f"{type(exc).__name__}: {exc}"}
+            return {"error": f"{type(exc).__name__}: {exc}"}
+
+    gated = guarded(lambda: gated_section(dev, peaks, world=world)) if "gated" not in skip else None
+    ie = guarded(lambda: ie_section(dev, peaks, world=world)) if "ie" not in skip else None
+    ie_pipe = None
+    if "ie_pipeline" not in skip:
+        if base is None:
+            base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=False)
+        ie_pipe = guarded(lambda: ie_pipeline_section(dev, base, world=world))
 
     if rank == 0:
-        peaks = _peaks()
         gemm_phases = {k: v for k, v in phases.items() if k.endswith("_gemm")}
         dom = max(gemm_phases, key=gemm_phases.get) if gemm_phases else None
         flops_per_gemm = 2.0 * T * C_ACT * F
+        step_flops = 10.0 * C_ACT * F * T
         achieved = flops_per_gemm / (gemm_phases[dom] * 1e-3) / 1e12 if dom else None
-        peak = peaks["bf16_sustained"]
         traffic = _traffic()
         roofline = {
-            "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": (achieved / peak) if achieved and peak else None,
-            "traffic": traffic.get(dom), "peak_source": peaks["source"] + ", sustained bf16",
+            "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+            "frac": (achieved / peaks["bf16_burst"]) if achieved and peaks["bf16_burst"] else None,
+            "frac_burst": (achieved / peaks["bf16_burst"]) if achieved and peaks["bf16_burst"] else None,
+            "traffic": traffic.get(dom),
+            "peak_source": peaks["source"] + ": burst bf16 for the %d-step (%.0f ms) timed region; the sustained figure "
+                                              "is used for the seconds-long leg only" % (args.steps, ms_total),
             "algorithmic_flops_per_launch": flops_per_gemm,
-            "step_tflops": 10.0 * C_ACT * F * T / (ms_step * 1e-3) / 1e12,
-            "step_frac_of_peak": 10.0 * C_ACT * F * T / (ms_step * 1e-3) / 1e12 / peak if peak else None,
+            "step_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+            "step_frac_burst": step_flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_burst"] if peaks["bf16_burst"] else None,
             "phases_ms": phases,
         }
-        cpu_v, cpu_ms, cores = cpu_reference_throughput(args.cpu_images, 2, 1, os.cpu_count()) if world == 1 else (None, None, None)
+        if sustained:
+            sus_ph = {k: v for k, v in sustained["phases_ms_last_128_steps"].items() if k.endswith("_gemm")}
+            if dom in sus_ph and sus_ph[dom] > 0 and peaks["bf16_sustained"]:
+                roofline["achieved_sustained"] = flops_per_gemm / (sus_ph[dom] * 1e-3) / 1e12
+                roofline["peak_sustained"] = peaks["bf16_sustained"]
+                roofline["frac_sustained"] = roofline["achieved_sustained"] / peaks["bf16_sustained"]
+            st_tf = step_flops / (sustained["ms_per_step"] * 1e-3) / 1e12
+            sustained["step_tflops"] = st_tf
+            sustained["step_frac_sustained"] = st_tf / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: SaeMLP (pixels-as-tokens) C=256 28x28 k=8 F=2048 constrained_adam "
-                                   "lambda=5, 256 images = 200704 tokens per GPU, bf16 NCHW activations",
-                       "images_per_gpu": B, "tokens_per_gpu": T, "parallelism": f"dp{world}",
+            "config": {"workload": CONFIG_WORKLOAD, "images_per_gpu": B, "tokens_per_gpu": T, "parallelism": f"dp{world}",
+                       "activations": "bf16 NCHW resident in HBM for `value`; produced by the frozen GoogLeNet from host "
+                                      "images for `e2e`",
                        "l2": "two rotating 103 MB input batches + ~2.2 GB per-step working set, both > 126 MB L2"},
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host[0].numel() * 2 * world,
-                    "d2h_bytes_per_step": L.STATS_LEN * 4 * world, "ms_per_step": ms_e2e / n_e2e,
-                    "numa_node_rank0": numa_node,
-                    "note": "pinned host activations -> svb_sae_train_step -> stats block to host, H2D of step i+1 "
-                            "overlapped with step i on a copy stream"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "final_step_stats": {k: last_stats[k] for k in ("loss", "rec", "l1", "n_dead")},
         }
-        if world == 1 and not args.no_ie:
-            try:
-                line["ie"] = ie_section(dev, peaks)
-            except Exception as exc:
-                line["ie"] = {"error": f"{type(exc).__name__}: {exc}"}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if sustained is not None:
+            line["sustained"] = sustained
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
+        if ie is not None:
+            line["ie"] = ie
+        if ie_pipe is not None:
+            line["ie_pipeline"] = ie_pipe
         if gated is not None:
             line["gated"] = gated
-        if cpu_v is not None:
+        if world == 1 and "gpu_eager" not in skip:
+            line["gpu_eager_reference"] = guarded(lambda: gpu_eager_reference(dev, xdev[0]))
+            ge = line["gpu_eager_reference"]
+            if "error" not in ge:
+                for mode in ("fp32", "tf32", "bf16_autocast"):
+                    ge[mode]["speedup_of_this_repo"] = ge[mode]["ms_per_step"] / ms_step
+        if world == 1 and "cpu" not in skip:
+            cpu_v, cpu_ms, cores = cpu_reference_throughput(args.cpu_images, 3, 1, os.cpu_count())
             line["cpu_baseline"] = {
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_images} images = {args.cpu_images * HW_SIDE * HW_SIDE} tokens per step, "
-                          f"1 warm-up + 2 timed steps of oracle/sae_oracle.py (fp32 torch CPU)"}
+                          f"1 warm-up + 3 timed steps of oracle/sae_oracle.py (fp32 torch CPU, {cores} threads)"}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -539,11 +850,16 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=8, help="images per step of the CPU reference sample")
     ap.add_argument("--no-ie", action="store_true", help="skip the indirect-effect and GatedSae sections")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA node")
-    ap.add_argument("--gated-dp", action="store_true",
-                    help="N > 1: also time the data-parallel GatedSae step (configs[2]) and report it under 'gated'")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained leg in seconds (0: skip)")
+    ap.add_argument("--skip", default="", help="comma-separated sections to skip: sustained,e2e,gated,ie,ie_pipeline,"
+                                               "gpu_eager,cpu,dp_parity")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="e2e: run the producer GoogLeNet in channels_last (NHWC activations = zero-copy token matrix)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "svb":
         args.warmup = 3
+    if args.no_ie:
+        args.skip = ",".join(filter(None, [args.skip, "gated,ie,ie_pipeline"]))
     _quiet_stdout()
     return run_reference(args) if args.impl == "reference" else run_svb(args)
 

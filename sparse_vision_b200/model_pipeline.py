@@ -36,8 +36,13 @@ class ModelPipeline:
 
     def __init__(self, model, sae_model, sae_model_name, sae_layer, sae_optimizer_name="constrained_adam",
                  sae_learning_rate=1e-3, sae_lambda_sparse=5.0, sae_expansion_factor=8, dead_neurons_steps=None,
-                 device=None, reinit_index_dir=None, data_parallel=False, global_batch_images=None):
+                 device=None, reinit_index_dir=None, data_parallel=False, global_batch_images=None, model_copy=None,
+                 model_criterion=None):
         self.model = model
+        # the unhooked original the modified model is compared with per batch (model_pipeline.py:694-708)
+        self.model_copy = model_copy
+        self.model_criterion = model_criterion or torch.nn.CrossEntropyLoss()
+        self.batch_model_stats = None
         self.sae_model = sae_model
         self.sae_model_name = sae_model_name
         if sae_model_name not in ("sae_mlp", "gated_sae"):
@@ -66,6 +71,9 @@ class ModelPipeline:
         self._last = None
         for p in self.model.parameters():
             p.requires_grad = False
+        if self.model_copy is not None:
+            for p in self.model_copy.parameters():
+                p.requires_grad = False
         # per-batch quantities, keyed like the reference (model_pipeline.py:394-420)
         self.batch_dead_units, self.batch_sparsity, self.batch_neuron_frequency = {}, {}, {}
 
@@ -156,12 +164,32 @@ class ModelPipeline:
         return self._last.scalars()
 
     # ------------------------------------------------------------------ one training batch + dead-neuron schedule
-    def train_batch(self, inputs, epoch=0):
-        """model_pipeline.py:603-793 for one batch: frozen base-model forward (the hook trains the SAE), then
-        train_batch_idx bookkeeping, dead-mask accumulation and the re-initialisation schedule."""
+    def compare_with_original(self, inputs, outputs, targets=None):
+        """model_pipeline.py:694-708: the unhooked copy of the base model on the same inputs -> KL divergence between the
+        two class distributions (sum over classes and images / batch size), the share of images both classify alike and
+        (with targets) the loss difference.  Stays on the device: batch_model_stats = float32[3] (kld, same, loss_diff)."""
+        with torch.no_grad():
+            out_orig = self.model_copy(inputs)
+            lp_orig = torch.nn.functional.log_softmax(out_orig.float(), dim=1)
+            lp_mod = torch.nn.functional.log_softmax(outputs.float(), dim=1)
+            kld = torch.nn.functional.kl_div(lp_orig, lp_mod, reduction="sum", log_target=True) / inputs.size(0)
+            same = (out_orig.argmax(dim=1) == outputs.argmax(dim=1)).float().mean()
+            if targets is not None:
+                diff = self.model_criterion(outputs.float(), targets) - self.model_criterion(out_orig.float(), targets)
+            else:
+                diff = torch.zeros((), device=kld.device)
+            self.batch_model_stats = torch.stack([kld, same, diff])
+        return self.batch_model_stats
+
+    def train_batch(self, inputs, epoch=0, targets=None):
+        """model_pipeline.py:603-793 for one batch: frozen base-model forward (the hook trains the SAE), the comparison
+        with the unhooked copy when one was given, then train_batch_idx bookkeeping, dead-mask accumulation and the
+        re-initialisation schedule."""
         self.epoch_batch_idx += 1
         with torch.no_grad():
             outputs = self.model(inputs)
+        if self.model_copy is not None:
+            self.compare_with_original(inputs, outputs, targets)
         self.train_batch_idx += 1
         for key, dead in self.batch_dead_units.items():                      # :744-748 (AND == product of bools)
             self.train_dead_neurons[key] = dead if key not in self.train_dead_neurons \

@@ -74,6 +74,15 @@ def test_cfg4_googlenet_hook_training_dead_masks_bit_exact(googlenet, tmp_path, 
             base(x.cuda())
     grab.remove()
     assert acts[0].shape == (B, C, int(HW ** 0.5), int(HW ** 0.5))
+    # Pre-bias at the channel means (what the x - b_dec of sae_mlp.py:49 is for).  GoogLeNet activations are post-ReLU,
+    # i.e. every channel has a positive mean; with b_dec = 0 Adam's first steps (each weight moves by lr whatever the
+    # gradient's size) shift all pre-activations of a unit coherently and hundreds of units die within ten steps, each
+    # of them passing through "active on one token" -- there no bf16 path can reproduce an fp32 mask bit for bit.
+    # Centred, the dead set over the 64 steps is exactly the planted one on both sides (data with a margin).
+    b_dec = torch.stack([a.mean(dim=(0, 2, 3)) for a in acts[:2]]).mean(0).bfloat16().float()
+    p["decoder.bias"] = b_dec.clone()
+    with torch.no_grad():
+        sae.decoder.bias.copy_(b_dec)
     # units that die later in the run (both sides get the same edit): gives the 2nd / 3rd re-initialisation work to do
     replant = {20: 11, 38: 12}
 
@@ -103,9 +112,10 @@ def test_cfg4_googlenet_hook_training_dead_masks_bit_exact(googlenet, tmp_path, 
         sc, dead, action = got[i]
         assert torch.equal(dead, ref["dead"]), f"{layer}: dead-unit mask differs at step {i + 1}"
         for key in ("loss", "rec", "l1", "nrmse", "rmse", "var_expl", "sparsity"):
-            rel = abs(sc[key] - float(ref[key])) / max(abs(float(ref[key])), 1e-3)
+            # var_expl = 1 - Var(dec)/Var(x) sits near 0 early in training: its natural scale is the ratio (~1), not itself
+            rel = abs(sc[key] - float(ref[key])) / max(abs(float(ref[key])), 5e-2 if key == "var_expl" else 1e-3)
             worst[key] = max(worst.get(key, 0.0), rel)
-            assert rel <= 2e-2, (layer, i, key, sc[key], float(ref[key]))
+            assert rel <= 1e-2, (layer, i, key, sc[key], float(ref[key]))      # north_star: 1e-2 relative
         acc = ref["dead"].clone() if acc is None else acc & ref["dead"]
         want = O.dead_neuron_action(i + 1, DEAD_STEPS)
         assert action == want, (i, action, want)
@@ -117,11 +127,12 @@ def test_cfg4_googlenet_hook_training_dead_masks_bit_exact(googlenet, tmp_path, 
     assert all(n >= n_plant for n in n_re), n_re
     # multi-step drift of the parameters (bf16 GEMM operands vs fp32): Adam moves a weight by ~lr per step whatever
     # the gradient's size, so single weights whose gradient is ~0 may walk apart by up to 2*lr*steps; the bulk may not
+    # (measured, profiles/r02a_cfg4_parity.txt: max 0.011 / mean 2.1e-4 after 64 steps, max 0.005 / mean 1e-4 after 20)
     drift = {}
     for key, q in zip(O.SAE_MLP_KEYS, sae.param_list()):
         d = (q.detach().cpu() - p[key]).abs()
         drift[key] = (d.max().item(), d.mean().item())
-        assert d.max().item() <= 2e-3 * steps + 1e-6 and d.mean().item() <= 1e-4 * steps, (layer, key, drift[key])
+        assert d.max().item() <= 5e-4 * steps + 1e-6 and d.mean().item() <= 1e-5 * steps, (layer, key, drift[key])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "cfg4_parity.txt"), "a") as fh:
         fh.write(f"{layer} B={B} steps={steps} reinit={n_re} worst_rel={ {k_: round(v, 5) for k_, v in worst.items()} } "

@@ -546,8 +546,8 @@ def test_module_autograd_backward_and_optimizer_step_vs_oracle(kind, opt_name):
         # the optimizer front keeps torch.optim.Adam's state layout (sae_mlp.py:148-176 indexes it)
         s0 = opt.state[model.param_list()[0]]
         assert set(s0) >= {"step", "exp_avg", "exp_avg_sq"} and int(s0["step"]) == step + 1
-        np.testing.assert_allclose(s0["exp_avg"].cpu().numpy(), st["m"][keys[0]].numpy(), rtol=0,
-                                   atol=2e-2 * float(st["m"][keys[0]].abs().max()))
+        m_ref = st["m"][keys[0]].numpy()
+        assert np.linalg.norm(s0["exp_avg"].cpu().numpy() - m_ref) <= 3e-2 * np.linalg.norm(m_ref)
 
 
 def test_apply_sae_ablation_vs_reference_golden(golden_dir):
