@@ -672,12 +672,13 @@ def run_svb(args):
     e2e = None
     base = None
     if "e2e" not in skip:
-        base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=args.channels_last)
-        base_copy = copy.deepcopy(base)
+        base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=args.channels_last,
+                                  fold_bn=not args.no_fold_bn)
+        base_copy = copy.deepcopy(base) if args.two_pass else None
         sae = _make_params().to(dev)
         pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", LR, LAMBDA, EXPANSION,
                              data_parallel=world > 1, global_batch_images=g_images if world > 1 else None,
-                             model_copy=base_copy)
+                             model_copy=base_copy, compare_in_one_pass=not args.two_pass)
         pipe.register_hooks(train_sae=True)
         gi = torch.Generator().manual_seed(77 + rank)
         host = [torch.randn(B, 3, 224, 224, generator=gi).to(torch.bfloat16).pin_memory() for _ in range(2)]
@@ -730,10 +731,13 @@ def run_svb(args):
                "last_batch": {"loss": sh[0], "rec": sh[1], "kld": sh[L.STATS_LEN], "same_classification": sh[L.STATS_LEN + 1],
                               "loss_diff": sh[L.STATS_LEN + 2]},
                "numa_node_rank0": numa_node,
+               "producer": {"channels_last": bool(args.channels_last), "batchnorm_folded": not args.no_fold_bn,
+                            "original_model": "second forward of an unhooked copy" if args.two_pass else
+                            "same pass: the hook hands [reconstruction; original activation] (2B) to the rest of the net"},
                "note": "ModelPipeline.train_batch on pinned host images (bf16 3x224x224): H2D (overlapped on a copy stream) "
-                       "-> frozen GoogLeNet forward (bf16%s, cuDNN) whose inception3a hook runs the fused SAE training step "
-                       "and hands the reconstruction back -> rest of the network -> unhooked copy forward -> KLD / "
-                       "same-classification -> stats + comparison scalars D2H" % (", channels_last" if args.channels_last else "")}
+                       "-> frozen GoogLeNet forward (bf16, cuDNN) whose inception3a hook runs the fused SAE training step "
+                       "and hands the reconstruction back -> rest of the network for the modified AND the original "
+                       "activations -> KLD / same-classification / loss difference -> stats + comparison scalars D2H"}
         del pipe, base_copy, host, stage
 
     # ---------------------------------------------------------------- side sections (collective at N > 1: every rank runs them)
@@ -853,6 +857,10 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained leg in seconds (0: skip)")
     ap.add_argument("--skip", default="", help="comma-separated sections to skip: sustained,e2e,gated,ie,ie_pipeline,"
                                                "gpu_eager,cpu,dp_parity")
+    ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")
+    ap.add_argument("--two-pass", action="store_true",
+                    help="e2e: compare with a second forward of an unhooked copy (the reference's structure) instead of "
+                         "carrying the original activations through the same pass")
     ap.add_argument("--channels-last", action="store_true",
                     help="e2e: run the producer GoogLeNet in channels_last (NHWC activations = zero-copy token matrix)")
     args = ap.parse_args()

@@ -212,6 +212,29 @@ int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts* x, const s
                          const svb_train_out* out);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Eval-epoch metrics on the device.
+ *
+ * svb_spatial_mean    — utils.py:1996-2010 average_over_W_H: mean over the hw positions of every (image, unit).
+ *                       `t` is [n_images*hw, F] (SVB_TOKENS, the layout the SAE kernels emit) or [n_images, F, hw]
+ *                       (SVB_NCHW), f32 or bf16; out is float[n_images, F].
+ * svb_topk_columns    — model_pipeline.py:357-360 (torch.topk(use_output, k, dim=0[, largest=False])) and the merge of
+ *                       utils.py:1445-1481 in one call: per column, the k largest (or smallest) of the n0 rows of
+ *                       source 0 followed by the n1 rows of source 1 (n1 = 0: plain per-batch top-k), sorted, ties by
+ *                       lower position, NaN largest.  idx / files are optional int64 [n, F] payloads gathered along
+ *                       (utils.py:1476-1477); a NULL idx stands for the row number.  Outputs are [k, F].
+ * svb_histogram_update — utils.py:1934-1963: hist[bins, n_units] += torch.histc(vals[:, unit_idx[u]], bins, mins[u],
+ *                       maxs[u]) for every listed unit (integer counts, deterministic).
+ */
+int svb_spatial_mean(svb_handle* h, void* stream, const void* t, int32_t dtype, int32_t layout, int64_t n_images,
+                     int32_t hw, int32_t F, float* out);
+int svb_topk_columns(svb_handle* h, void* stream, const float* vals0, const int64_t* idx0, const int64_t* files0,
+                     int32_t n0, const float* vals1, const int64_t* idx1, const int64_t* files1, int32_t n1, int32_t F,
+                     int32_t k, int32_t largest, float* out_vals, int64_t* out_idx, int64_t* out_files);
+int svb_histogram_update(svb_handle* h, void* stream, const float* vals, int64_t rows, int32_t F,
+                         const int64_t* unit_idx, int32_t n_units, const float* mins, const float* maxs, int32_t bins,
+                         float* hist);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Optimiser step on caller-provided gradients — utils.py:50-97 (ConstrainedAdam.step / torch.optim.Adam).
  * `decoder_index` is the position of decoder.weight in the lists (projected + renormalised when the optimizer is
  * SVB_CONSTRAINED_ADAM; -1 for none); rows/cols give each tensor's 2-D shape (vectors: rows = 1).

@@ -113,6 +113,10 @@ SYMBOLS = {
     "svb_node_ie_layer": (C.c_int, [_vp, _vp, _P(Acts), _vp, _P(SaeParams), _fp, _fp, _fp, C.c_float, _fp, _fp, _fp]),
     "svb_gemm_bf16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, _vp, C.c_int32, C.c_int64, C.c_float, _fp, C.c_int32]),
+    "svb_spatial_mean": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp]),
+    "svb_topk_columns": (C.c_int, [_vp, _vp, _fp, _vp, _vp, C.c_int32, _fp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, _fp, _vp, _vp]),
+    "svb_histogram_update": (C.c_int, [_vp, _vp, _fp, C.c_int64, C.c_int32, _vp, C.c_int32, _fp, _fp, C.c_int32, _fp]),
     "svb_pack_tokens": (C.c_int, [_vp, _vp, _P(Acts), _vp]),
     "svb_unpack_tokens": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32]),
 }

@@ -17,7 +17,8 @@ import torch
 from . import ops
 from ._lib import STAT
 from .parallel import DataParallelStep, global_counts
-from .utils import get_criterion, get_optimizer, measure_inactive_units, sae_inference_and_loss, variance_explained
+from .utils import (average_over_W_H, batch_top_k, get_criterion, get_optimizer, get_top_k_samples,
+                    measure_inactive_units, sae_inference_and_loss, update_histogram, variance_explained)
 
 
 def dead_neuron_action(train_batch_idx, dead_neurons_steps):
@@ -37,12 +38,17 @@ class ModelPipeline:
     def __init__(self, model, sae_model, sae_model_name, sae_layer, sae_optimizer_name="constrained_adam",
                  sae_learning_rate=1e-3, sae_lambda_sparse=5.0, sae_expansion_factor=8, dead_neurons_steps=None,
                  device=None, reinit_index_dir=None, data_parallel=False, global_batch_images=None, model_copy=None,
-                 model_criterion=None):
+                 model_criterion=None, compare_in_one_pass=False):
         self.model = model
         # the unhooked original the modified model is compared with per batch (model_pipeline.py:694-708)
         self.model_copy = model_copy
         self.model_criterion = model_criterion or torch.nn.CrossEntropyLoss()
         self.batch_model_stats = None
+        # compare_in_one_pass: instead of a second forward of an unhooked copy, the hook hands BOTH the reconstruction
+        # and the original activation on (batch 2B) and the rest of the frozen network processes them together: the
+        # layers in front of the SAE layer run once instead of twice and the logits of the original model fall out of
+        # the same pass (a frozen eval-mode network treats samples independently, so the results are the same)
+        self.compare_in_one_pass = compare_in_one_pass
         self.sae_model = sae_model
         self.sae_model_name = sae_model_name
         if sae_model_name not in ("sae_mlp", "gated_sae"):
@@ -76,6 +82,16 @@ class ModelPipeline:
                 p.requires_grad = False
         # per-batch quantities, keyed like the reference (model_pipeline.py:394-420)
         self.batch_dead_units, self.batch_sparsity, self.batch_neuron_frequency = {}, {}, {}
+        # eval-epoch recording (model_pipeline.py:80-104): top / small k samples per unit and activation histograms
+        self.record_top_samples = False
+        self.k = 25
+        self.get_histogram = False
+        self.histogram_info = {}
+        self.batch_top_k_values, self.batch_top_k_indices = {}, {}
+        self.batch_small_k_values, self.batch_small_k_indices = {}, {}
+        self.top_k_samples, self.small_k_samples = {}, {}
+        self.eval_dead_neurons = {}
+        self.used_batch_size = None
 
     # ------------------------------------------------------------------ optimizer state shared with the fused step
     def _adam_tensors(self):
@@ -128,17 +144,71 @@ class ModelPipeline:
             self._last = res
             self.batch_dead_units[(name, "sae")] = res.dead          # uint8 on the device; AND-ed in train_batch()
             self.batch_neuron_frequency[(name, "sae")] = res.freq
+            if self.compare_in_one_pass:
+                return torch.cat((res.dec, output.to(res.dec.dtype)), dim=0)
             return res.dec                                           # replaces the layer output (:425,432)
         with torch.no_grad():
             r = sae_inference_and_loss(self.sae_model_name, self.sae_model, self.sae_criterion_name, output,
                                        self.sae_criterion, self.sae_lambda_sparse)
         loss, rec, l1, nrmse, rmse, aux, enc, pre, dec = r
-        dead, sparsity, freq = measure_inactive_units(enc, self.sae_expansion_factor)
         self._last = {"loss": loss, "rec": rec, "l1": l1, "nrmse": nrmse, "rmse": rmse, "aux": aux,
-                      "sparsity": sparsity, "var_expl": variance_explained(output, dec)}
-        self.batch_dead_units[(name, "sae")] = dead.to(torch.uint8)
-        self.batch_neuron_frequency[(name, "sae")] = freq
+                      "var_expl": variance_explained(output, dec)}
+        self.compute_and_store_batch_wise_metrics("sae", enc, name, self.sae_expansion_factor, output_2=pre)
+        if (name, "sae") in self.batch_sparsity:
+            self._last["sparsity"] = self.batch_sparsity[(name, "sae")]
         return dec.to(output.dtype)
+
+    # ------------------------------------------------------------------ per-batch metrics (model_pipeline.py:278-360)
+    def compute_and_store_batch_wise_metrics(self, model_key, output, name, expansion_factor=1, output_2=None):
+        """Spatial means of the (pre-ReLU) activations -> histograms or activity metrics, and the k largest / smallest
+        samples of every unit in this batch, all on the device."""
+        output_avg, output_2_avg = average_over_W_H(output, output_2)
+        if self.get_histogram:
+            self.histogram_info = update_histogram(self.histogram_info, name, model_key, output_avg, self.device,
+                                                   output_2=output_2_avg)
+        else:
+            dead, sparsity, freq = measure_inactive_units(output, expansion_factor)
+            self.batch_sparsity[(name, model_key)] = sparsity
+            self.batch_dead_units[(name, model_key)] = dead.to(torch.uint8)
+            self.batch_neuron_frequency[(name, model_key)] = freq
+        if self.record_top_samples:
+            use_output = output_2_avg if output_2 is not None else output_avg          # :349-354
+            k = min(self.k, use_output.shape[0])
+            tv, ti, sv, si = batch_top_k(use_output, k)
+            key = (name, model_key)
+            self.batch_top_k_values[key], self.batch_top_k_indices[key] = tv, ti
+            self.batch_small_k_values[key], self.batch_small_k_indices[key] = sv, si
+
+    def eval_batch(self, inputs, filename_indices=None):
+        """model_pipeline.py:603-664 + :862-909 for one evaluation batch: frozen forward with the SAE in inference
+        mode, dead-unit AND over the epoch, and the merge of this batch's top / small k samples into the running ones.
+        filename_indices: int64 [batch] dataset positions of the batch's samples (default: running sample numbers)."""
+        self.epoch_batch_idx += 1
+        if self.used_batch_size is None:
+            self.used_batch_size = inputs.shape[0]
+        with torch.no_grad():
+            outputs = self.model(inputs)
+        for key, dead in self.batch_dead_units.items():                                  # :870-878
+            self.eval_dead_neurons[key] = dead if key not in self.eval_dead_neurons else self.eval_dead_neurons[key] & dead
+        if self.record_top_samples:
+            if filename_indices is None:
+                filename_indices = torch.arange(inputs.shape[0], device=inputs.device) + \
+                    (self.epoch_batch_idx - 1) * self.used_batch_size
+            filename_indices = filename_indices.to(device=inputs.device, dtype=torch.int64)
+            for key in self.batch_top_k_values:
+                ti, si = self.batch_top_k_indices[key], self.batch_small_k_indices[key]
+                if key not in self.top_k_samples:                                        # :881-893
+                    self.top_k_samples[key] = (self.batch_top_k_values[key], ti, self.used_batch_size, filename_indices[ti])
+                    self.small_k_samples[key] = (self.batch_small_k_values[key], si, self.used_batch_size,
+                                                 filename_indices[si])
+                else:                                                                    # :895-909
+                    self.top_k_samples[key] = get_top_k_samples(
+                        self.top_k_samples[key], self.batch_top_k_values[key], ti, filename_indices[ti],
+                        self.epoch_batch_idx, largest=True, k=self.k)
+                    self.small_k_samples[key] = get_top_k_samples(
+                        self.small_k_samples[key], self.batch_small_k_values[key], si, filename_indices[si],
+                        self.epoch_batch_idx, largest=False, k=self.k)
+        return outputs
 
     def register_hooks(self, train_sae=True):
         """model_pipeline.py:445-475: a forward hook on the SAE layer."""
@@ -164,12 +234,13 @@ class ModelPipeline:
         return self._last.scalars()
 
     # ------------------------------------------------------------------ one training batch + dead-neuron schedule
-    def compare_with_original(self, inputs, outputs, targets=None):
+    def compare_with_original(self, inputs, outputs, targets=None, out_orig=None):
         """model_pipeline.py:694-708: the unhooked copy of the base model on the same inputs -> KL divergence between the
         two class distributions (sum over classes and images / batch size), the share of images both classify alike and
         (with targets) the loss difference.  Stays on the device: batch_model_stats = float32[3] (kld, same, loss_diff)."""
         with torch.no_grad():
-            out_orig = self.model_copy(inputs)
+            if out_orig is None:
+                out_orig = self.model_copy(inputs)
             lp_orig = torch.nn.functional.log_softmax(out_orig.float(), dim=1)
             lp_mod = torch.nn.functional.log_softmax(outputs.float(), dim=1)
             kld = torch.nn.functional.kl_div(lp_orig, lp_mod, reduction="sum", log_target=True) / inputs.size(0)
@@ -188,7 +259,10 @@ class ModelPipeline:
         self.epoch_batch_idx += 1
         with torch.no_grad():
             outputs = self.model(inputs)
-        if self.model_copy is not None:
+        if self.compare_in_one_pass and self.hooks and self.train_sae:
+            outputs, out_orig = outputs[:inputs.shape[0]], outputs[inputs.shape[0]:]
+            self.compare_with_original(inputs, outputs, targets, out_orig=out_orig)
+        elif self.model_copy is not None:
             self.compare_with_original(inputs, outputs, targets)
         self.train_batch_idx += 1
         for key, dead in self.batch_dead_units.items():                      # :744-748 (AND == product of bools)

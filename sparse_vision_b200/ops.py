@@ -269,6 +269,73 @@ def measure_inactive(t):
     return dead, freq, n_active
 
 
+# --------------------------------------------------------------------------------------------------- eval metrics
+def spatial_mean(t, n_images=None):
+    """utils.py:1996-2010 average_over_W_H on the device: [B,F,H,W] -> [B,F]; token-major [B*hw, F] with n_images
+    given -> [B,F]; a 2-D tensor without n_images is returned as it is (already one value per sample and unit)."""
+    if not t.is_cuda:
+        raise ValueError("CUDA tensor required")
+    if t.dim() == 2 and n_images is None:
+        return t
+    t = t.contiguous()
+    if t.dim() == 4:
+        b, f, hh, ww = t.shape
+        layout, hw = L.SVB_NCHW, hh * ww
+    elif t.dim() == 2:
+        b, f, layout = int(n_images), t.shape[1], L.SVB_TOKENS
+        hw = t.shape[0] // b
+        if hw * b != t.shape[0]:
+            raise ValueError("token count is not a multiple of n_images")
+    else:
+        raise ValueError(f"Output has unexpected shape {t.dim()}.")
+    out = torch.empty((b, f), device=t.device, dtype=torch.float32)
+    L.check(L.load().svb_spatial_mean(L.handle(t.device), L.stream_ptr(t.device), L.ptr(t), L.dtype_code(t), layout, b,
+                                      hw, f, L.ptr(out)), "svb_spatial_mean")
+    return out
+
+
+def _i64(t):
+    if t is None:
+        return None
+    if t.dtype != torch.int64 or not t.is_cuda:
+        raise ValueError("index payloads must be int64 CUDA tensors")
+    return t.contiguous()
+
+
+def topk_columns(values, k, largest=True, indices=None, files=None, values2=None, indices2=None, files2=None):
+    """torch.topk(values, k, dim=0, largest=largest) per column on the device; with a second source the candidates are
+    the rows of `values` followed by the rows of `values2` (the merge of utils.py:1463-1477).  indices / files are
+    optional int64 payloads of the same shape as their values, gathered along; indices=None stands for the row number.
+    Returns (values [k,F], indices [k,F] int64, files [k,F] int64 | None)."""
+    v0 = values.contiguous().float()
+    n0, F = v0.shape
+    v1 = values2.contiguous().float() if values2 is not None else None
+    n1 = v1.shape[0] if v1 is not None else 0
+    i0, f0, i1, f1 = _i64(indices), _i64(files), _i64(indices2), _i64(files2)
+    want_files = f0 is not None or f1 is not None
+    out_v = torch.empty((k, F), device=v0.device, dtype=torch.float32)
+    out_i = torch.empty((k, F), device=v0.device, dtype=torch.int64)
+    out_f = torch.empty((k, F), device=v0.device, dtype=torch.int64) if want_files else None
+    L.check(L.load().svb_topk_columns(L.handle(v0.device), L.stream_ptr(v0.device), L.ptr(v0), L.ptr(i0), L.ptr(f0), n0,
+                                      L.ptr(v1), L.ptr(i1), L.ptr(f1), n1, F, int(k), int(bool(largest)), L.ptr(out_v),
+                                      L.ptr(out_i), L.ptr(out_f)), "svb_topk_columns")
+    return out_v, out_i, out_f
+
+
+def histogram_update(hist, values, unit_idx, mins, maxs):
+    """hist [bins, U] (float32, updated in place) += per-unit torch.histc of values[:, unit_idx[u]] (utils.py:1956-1960)."""
+    values = values.contiguous().float()
+    bins, U = hist.shape
+    if not hist.is_contiguous() or hist.dtype != torch.float32:
+        raise ValueError("hist must be a contiguous float32 [bins, units] tensor")
+    idx = _i64(unit_idx)
+    L.check(L.load().svb_histogram_update(L.handle(values.device), L.stream_ptr(values.device), L.ptr(values),
+                                          values.shape[0], values.shape[1], L.ptr(idx), U,
+                                          L.ptr(mins.contiguous().float()), L.ptr(maxs.contiguous().float()), bins,
+                                          L.ptr(hist)), "svb_histogram_update")
+    return hist
+
+
 # --------------------------------------------------------------------------------------------------- IE
 def ie_channelwise(a, avg, g, batch_size, scale=None):
     """utils.py:2606-2637: a, g [B*H*W, F] (f32/bf16), avg [F,H,W] f32 -> [F]."""

@@ -55,8 +55,24 @@ def synthetic_googlenet(seed=0, calibration_images=8, image_size=224):
     return model
 
 
-def to_producer_format(model, device, dtype=torch.bfloat16, channels_last=True):
+def fold_batchnorm(model):
+    """Folds every eval-mode BatchNorm into the convolution in front of it (exact algebra for a frozen model): one cuDNN
+    kernel and one pass over the activations per layer instead of three.  In place; returns the model."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    for m in model.modules():
+        conv, bn = getattr(m, "conv", None), getattr(m, "bn", None)
+        if isinstance(conv, torch.nn.Conv2d) and isinstance(bn, torch.nn.BatchNorm2d):
+            m.conv = fuse_conv_bn_eval(conv.eval(), bn.eval())
+            m.bn = torch.nn.Identity()
+    for p in model.parameters():
+        p.requires_grad = False
+    return model
+
+
+def to_producer_format(model, device, dtype=torch.bfloat16, channels_last=True, fold_bn=False):
     """Moves the frozen base model to `device` in the format the SAE kernels read without a copy."""
+    if fold_bn:
+        model = fold_batchnorm(model.float())
     model = model.to(device=device, dtype=dtype)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)

@@ -188,13 +188,20 @@ def sae_inference_and_loss(sae_model_name, sae_model, sae_criterion_name, output
 
 
 # --------------------------------------------------------------------------------------------------- activity
+def _spatial_mean(t):
+    if t.dim() != 4:
+        return t
+    if not t.is_cuda:
+        return torch.mean(t, dim=(2, 3))
+    tok = t.permute(0, 2, 3, 1)
+    if tok.is_contiguous():            # a [B,F,H,W] VIEW of the token-major tensor the SAE kernels emit: no copy
+        return ops.spatial_mean(tok.reshape(-1, t.shape[1]), n_images=t.shape[0])
+    return ops.spatial_mean(t)
+
+
 def average_over_W_H(output, output_2):
-    """utils.py:1996-2010."""
-    if output.dim() == 4:
-        output = torch.mean(output, dim=(2, 3))
-    if output_2 is not None and output_2.dim() == 4:
-        output_2 = torch.mean(output_2, dim=(2, 3))
-    return output, output_2
+    """utils.py:1996-2010: spatial means [B, #units] of conv-shaped activations (one HBM pass on libsvb)."""
+    return _spatial_mean(output), (None if output_2 is None else _spatial_mean(output_2))
 
 
 def variance_explained(output, decoder_output):
@@ -228,6 +235,16 @@ def get_top_k_samples(top_k_samples, batch_top_k_values, batch_top_k_indices, ba
     batch's top-k."""
     prev_values, prev_indices, batch_size, prev_files = top_k_samples
     batch_top_k_indices += (eval_batch_idx - 1) * batch_size
+    if prev_values.is_cuda and prev_values.shape[0] + batch_top_k_values.shape[0] >= k:
+        # one kernel: candidates = previous rows followed by the batch's, sorted per unit, payloads gathered along
+        if prev_values.shape[0] == 0:
+            new_values, new_indices, new_files = ops.topk_columns(
+                batch_top_k_values, k, largest, indices=batch_top_k_indices, files=batch_filename_indices)
+        else:
+            new_values, new_indices, new_files = ops.topk_columns(
+                prev_values, k, largest, indices=prev_indices, files=prev_files, values2=batch_top_k_values,
+                indices2=batch_top_k_indices, files2=batch_filename_indices)
+        return new_values, new_indices, batch_size, new_files
     values = torch.cat((prev_values, batch_top_k_values), dim=0)
     indices = torch.cat((prev_indices, batch_top_k_indices), dim=0)
     files = torch.cat((prev_files, batch_filename_indices), dim=0)
@@ -235,6 +252,34 @@ def get_top_k_samples(top_k_samples, batch_top_k_values, batch_top_k_indices, ba
         return values, indices, batch_size, files
     new_values, pos = torch.topk(values, k=k, dim=0, largest=largest)
     return new_values, torch.gather(indices, 0, pos), batch_size, torch.gather(files, 0, pos)
+
+
+def batch_top_k(use_output, k):
+    """model_pipeline.py:357-360: the k largest and k smallest values of every unit over the batch and the in-batch
+    indices of the samples they come from -> (top values, top indices, small values, small indices), each [k, #units].
+    (The reference calls torch.topk four times; here two launches of the device top-k.)"""
+    top_v, top_i, _ = ops.topk_columns(use_output, k, largest=True)
+    small_v, small_i, _ = ops.topk_columns(use_output, k, largest=False)
+    return top_v, top_i, small_v, small_i
+
+
+def update_histogram(histogram_info, name, model_key, output, device, output_2=None):
+    """utils.py:1934-1963: add this batch's activations (spatial means [B, #units]; the pre-ReLU encoder output for the
+    SAE) of the selected units to their histograms.  histogram_info[(name, model_key)] =
+    (histogram_matrix [bins, U], top_values [U], small_values [U], neuron_indices [U])."""
+    histogram_matrix, top_values, small_values, neuron_indices = histogram_info[(name, model_key)]
+    if output_2 is not None and model_key == "sae":
+        activations = output_2
+    elif output_2 is None and model_key != "sae":
+        activations = output
+    else:
+        raise ValueError(f"model_key is {model_key} but output_2 is {output_2}")
+    idx = torch.as_tensor(neuron_indices, dtype=torch.int64, device=activations.device)
+    histogram_matrix = histogram_matrix.to(activations.device)
+    ops.histogram_update(histogram_matrix, activations, idx, small_values.to(activations.device),
+                         top_values.to(activations.device))
+    histogram_info[(name, model_key)] = (histogram_matrix, top_values, small_values, neuron_indices)
+    return histogram_info
 
 
 # --------------------------------------------------------------------------------------------------- indirect effects
