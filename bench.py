@@ -592,6 +592,8 @@ def run_svb(args):
     numa_node = _bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else None
     # two distinct resident batches (2 x 103 MB > 126 MB L2), bf16 NCHW as the base model would emit them
     xdev = [_synthetic_acts(B, 1234 + 17 * rank + i).to(torch.bfloat16).to(dev) for i in range(2)]
+    if args.acts_format == "channels_last":     # the same values as a channels_last producer emits them: NHWC = tokens
+        xdev = [t.contiguous(memory_format=torch.channels_last) for t in xdev]
     lib, h = L.load(), L.handle(dev)
     dp = DataParallelStep("sae_mlp") if world > 1 else None
     g_images, g_tokens = B * world, T * world
@@ -642,6 +644,26 @@ def run_svb(args):
     (ms_total,) = job_max(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = g_tokens / (ms_step * 1e-3)
+
+    # the same step on the OTHER memory format of the same activations (NCHW needs the pack pass; channels_last is read
+    # in place), for the record
+    other_fmt = None
+    if "other_format" not in skip:
+        alt = [t.contiguous() if args.acts_format == "channels_last" else t.contiguous(memory_format=torch.channels_last)
+               for t in xdev]
+        for i in range(3):
+            one_step(alt[i % 2])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(args.steps):
+            one_step(alt[i % 2])
+        a1.record()
+        barrier()
+        (ms_alt,) = job_max(a0.elapsed_time(a1))
+        other_fmt = {"format": "nchw" if args.acts_format == "channels_last" else "channels_last",
+                     "ms_per_step": ms_alt / args.steps, "value": g_tokens / (ms_alt / args.steps * 1e-3)}
+        del alt
 
     # ---------------------------------------------------------------- sustained leg: seconds of back-to-back steps
     sustained = None
@@ -788,8 +810,9 @@ def run_svb(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": CONFIG_WORKLOAD, "images_per_gpu": B, "tokens_per_gpu": T, "parallelism": f"dp{world}",
-                       "activations": "bf16 NCHW resident in HBM for `value`; produced by the frozen GoogLeNet from host "
-                                      "images for `e2e`",
+                       "activations": "bf16 %s resident in HBM for `value`; produced by the frozen GoogLeNet from host "
+                                      "images for `e2e`" % ("channels_last ([B,C,H,W] whose memory is the token matrix: read in "
+                                                            "place, no layout copy)" if args.acts_format == "channels_last" else "NCHW"),
                        "l2": "two rotating 103 MB input batches + ~2.2 GB per-step working set, both > 126 MB L2"},
             "roofline": roofline,
             "gpu_launches": int(launches),
@@ -798,6 +821,8 @@ def run_svb(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if other_fmt is not None:
+            line["other_activation_format"] = other_fmt
         if sustained is not None:
             line["sustained"] = sustained
         if dp_parity is not None:
@@ -856,13 +881,16 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained leg in seconds (0: skip)")
     ap.add_argument("--skip", default="", help="comma-separated sections to skip: sustained,e2e,gated,ie,ie_pipeline,"
-                                               "gpu_eager,cpu,dp_parity")
+                                               "gpu_eager,cpu,dp_parity,other_format")
+    ap.add_argument("--acts-format", default="channels_last", choices=["nchw", "channels_last"],
+                    help="memory format of the resident activations of the `value` leg")
     ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")
     ap.add_argument("--two-pass", action="store_true",
                     help="e2e: compare with a second forward of an unhooked copy (the reference's structure) instead of "
                          "carrying the original activations through the same pass")
-    ap.add_argument("--channels-last", action="store_true",
-                    help="e2e: run the producer GoogLeNet in channels_last (NHWC activations = zero-copy token matrix)")
+    ap.add_argument("--producer-nchw", dest="channels_last", action="store_false",
+                    help="e2e: run the producer GoogLeNet in NCHW instead of channels_last (whose NHWC activations are "
+                         "the zero-copy token matrix)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "svb":
         args.warmup = 3

@@ -197,10 +197,21 @@ def dtype_code(t):
     raise ValueError(f"unsupported dtype {t.dtype}: sparse_vision_b200 takes float32 or bfloat16 tensors")
 
 
+def is_channels_last_tokens(x):
+    """True for a 4-D bf16 tensor whose memory is NHWC-dense (what a channels_last cuDNN model emits) and that is not
+    also NCHW-dense (H*W == 1 or C == 1 are both at once; those take the ordinary route)."""
+    return (x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[2] * x.shape[3] > 1 and x.shape[1] > 1
+            and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
+
+
 def acts_of(x):
     """Builds svb_acts from a [B,C,H,W] or [N,C] CUDA tensor (made contiguous)."""
     if not x.is_cuda:
         raise ValueError("sparse_vision_b200 runs on CUDA tensors only (no CPU fallback)")
+    if is_channels_last_tokens(x):
+        # a channels_last [B,C,H,W] tensor IS the token matrix [(b h w), C] of sae_mlp.py:44: no layout copy
+        b, c, h, w = x.shape
+        return Acts(ptr(x), dtype_code(x), SVB_TOKENS, b, h * w, c), x
     x = x.contiguous()
     if x.dim() == 4:
         b, c, h, w = x.shape

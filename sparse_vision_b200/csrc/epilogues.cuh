@@ -504,6 +504,11 @@ struct EpiDecNchw {
     int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base);
                                       // 4: tm_out is a channel-major [C][T] workspace (make_store_tmap_bf16_cmajor)
                                       //    that a copy kernel turns into the caller's tensor (any HW, bf16 or fp32)
+                                      // 2: token-major bf16 [M, N] through tm_out (make_store_tmap_bf16_chunk): the
+                                      //    caller's channels_last tensor, no layout change at all (tok = 1 only)
+    int x_slab;                       // x is slab-major (1) or the caller's row-major token matrix [M, N] (0)
+    int tok;                          // 1: token-major in / out: d is staged token-major, the per-channel sums are
+                                      //    read back column-wise like those of diff (no channel-major copy exists)
   };
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
@@ -535,7 +540,11 @@ struct EpiDecNchw {
                                         int wq, int lane, int) {
     const bool row_ok = row < g.M;
     float xv[32], b[32];
-    load_row_bf16(p.x + (row_ok ? slab_offset(row, col0, g.M) : 0), xv, row_ok ? 32 : 0);  // issued early
+    if (p.x_slab)  // issued early; the padding columns of the last slab exist (zeros)
+      load_row_bf16(p.x + (row_ok ? slab_offset(row, col0, g.M) : 0), xv, row_ok ? 32 : 0);
+    else           // row-major [M, N]: columns >= N (padding chunks of the last diff slab) are not there
+      load_row_bf16(p.x + (row_ok ? static_cast<size_t>(row) * g.N + min(col0, g.N - 8) : 0), xv,
+                    row_ok ? max(0, min(32, g.N - col0)) : 0);
     lds_row_f32(cv + (col0 - ti.n0), b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
@@ -554,11 +563,18 @@ struct EpiDecNchw {
     // the stores of the previous chunk must have finished READING the two staging tiles
     if (lane == 0) bulk_wait_read<0>();
     __syncwarp();
-    uint16_t* tb = reinterpret_cast<uint16_t*>(tbuf) + lane;
+    if (p.tok) {  // token-major [32 tokens][32 channels], 64B-swizzled like the diff tile
+      uint8_t* drow = tbuf + lane * 64;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      tb[(2 * j) * 32] = static_cast<uint16_t>(dpk[j] & 0xFFFFu);
-      tb[(2 * j + 1) * 32] = static_cast<uint16_t>(dpk[j] >> 16);
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(drow + ((i ^ ((lane >> 1) & 3)) << 4)) = make_uint4(dpk[4 * i], dpk[4 * i + 1], dpk[4 * i + 2], dpk[4 * i + 3]);
+    } else {
+      uint16_t* tb = reinterpret_cast<uint16_t*>(tbuf) + lane;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        tb[(2 * j) * 32] = static_cast<uint16_t>(dpk[j] & 0xFFFFu);
+        tb[(2 * j + 1) * 32] = static_cast<uint16_t>(dpk[j] >> 16);
+      }
     }
     uint8_t* frow = fbuf + lane * 64;
 #pragma unroll
@@ -574,7 +590,22 @@ struct EpiDecNchw {
     float* part1 = p.part + (grp * 2 + 1) * 3 * g.N;
     const int col = col0 + lane;  // this lane's channel
     const bool col_ok = col < g.N;  // false only in the padding of the last slab (N % 64 != 0)
-    {  // (1) sum d, sum d^2 of channel col0 + lane from its row of the channel-major copy
+    if (p.tok) {  // (1) sum d, sum d^2 of channel col0 + lane: its column of the token-major tile
+      float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+      const uint8_t* cp = tbuf + ((lane & 7) << 1);
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const uint16_t h = *reinterpret_cast<const uint16_t*>(cp + r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4));
+        const float d = __uint_as_float(static_cast<uint32_t>(h) << 16);
+        if (r < n0) { a0 += d; q0 += d * d; }
+        else { a1 += d; q1 += d * d; }          // rows >= nrows hold zeros
+      }
+      if (col_ok) {
+        part0[col] = a0;
+        part0[g.N + col] = q0;
+        if (n1 > 0) { part1[col] = a1; part1[g.N + col] = q1; }
+      }
+    } else {  // (1) sum d, sum d^2 of channel col0 + lane from its row of the channel-major copy
       const uint4* rp = reinterpret_cast<const uint4*>(tbuf + lane * 64);
       uint32_t w[16];
 #pragma unroll
@@ -631,6 +662,7 @@ struct EpiDecNchw {
     if (lane == 0) {
       if (p.out_kind == 1 && col0 < g.N) tma_store_3d(&p.tm_out, tbuf, row0 - b0 * p.hw, col0, b0);   // clipped at C
       if (p.out_kind == 4 && col0 < g.N) tma_store_2d(&p.tm_out, tbuf, row0, col0);                    // clipped at T, C
+      if (p.out_kind == 2 && col0 < g.N) tma_store_2d(&p.tm_out, tbuf, col0, row0);                    // token-major, clipped
       tma_store_3d(&p.tm_diff, fbuf, col0 & 63, row0, col0 >> 6);
       bulk_commit();
     }

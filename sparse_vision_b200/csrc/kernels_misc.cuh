@@ -232,6 +232,62 @@ pack_nchw_tile_kernel(const TIn* __restrict__ x, bf16* __restrict__ out, int C, 
   }
 }
 
+// Token-major activations X [B*HW, C] (bf16; what a channels_last base model emits, read zero-copy by the GEMMs) ->
+// the statistics the loss metrics need, in the pack kernel's format: xpart[((b * NT + tile) * 4 + q) * C + c] with
+// q = sum x, sum x^2, min x, max x over the 64 positions of HW tile `tile` of image b.  One WARP per (image, tile,
+// 256-channel group): lane owns 8 consecutive channels (one 16-byte load per row, 8 rows in flight), walks the 64 rows
+// in order and writes its results straight from registers -- no shared memory, no synchronisation, read-only and
+// HBM-bound (103 MB at cfg2).  grid = ceil(B * NT * ceil(C/256) / 4) blocks of 4 warps.
+static __global__ void __launch_bounds__(128)
+x_stats_tokens_kernel(const bf16* __restrict__ x, float* __restrict__ xpart, int C, int HW, int NT, long long n_warps) {
+  const long long wid = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (wid >= n_warps) return;
+  const int lane = threadIdx.x & 31;
+  const int cgroups = (C + 255) / 256;
+  const int cg = static_cast<int>(wid % cgroups);
+  const long long bt = wid / cgroups;                 // b * NT + tile
+  const int tile = static_cast<int>(bt % NT);
+  const long long b = bt / NT;
+  const int c0 = cg * 256 + lane * 8;
+  if (c0 >= C) return;
+  const int p0 = tile * 64, np = min(64, HW - p0);
+  const bf16* xb = x + (static_cast<size_t>(b) * HW + p0) * C + c0;
+  float s[8], q[8], mn[8], mx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; mn[k] = INFINITY; mx[k] = -INFINITY; }
+  for (int r0 = 0; r0 < np; r0 += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = r0 + i < np ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r0 + i) * C)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (r0 + i < np) {
+        const uint32_t ws[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = bf16lo(ws[k]), hi = bf16hi(ws[k]);
+          s[2 * k] += lo; q[2 * k] += lo * lo; mn[2 * k] = fminf(mn[2 * k], lo); mx[2 * k] = fmaxf(mx[2 * k], lo);
+          s[2 * k + 1] += hi; q[2 * k + 1] += hi * hi; mn[2 * k + 1] = fminf(mn[2 * k + 1], hi); mx[2 * k + 1] = fmaxf(mx[2 * k + 1], hi);
+        }
+      }
+    }
+  }
+  float* o = xpart + static_cast<size_t>(bt) * 4 * C + c0;
+  *reinterpret_cast<float4*>(o) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(o + C) = make_float4(q[0], q[1], q[2], q[3]);
+  *reinterpret_cast<float4*>(o + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
+  *reinterpret_cast<float4*>(o + 2 * C) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+  *reinterpret_cast<float4*>(o + 2 * C + 4) = make_float4(mn[4], mn[5], mn[6], mn[7]);
+  *reinterpret_cast<float4*>(o + 3 * C) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+  *reinterpret_cast<float4*>(o + 3 * C + 4) = make_float4(mx[4], mx[5], mx[6], mx[7]);
+}
+inline void launch_x_stats_tokens(cudaStream_t st, const bf16* x, float* xpart, int C, int HW, int NT, long long n_img) {
+  const long long n_warps = n_img * NT * ((C + 255) / 256);
+  (x_stats_tokens_kernel<<<static_cast<unsigned>((n_warps + 3) / 4), 128, 0, st>>>(x, xpart, C, HW, NT, n_warps), svb::count_launch());
+}
+
 // Channel-major decoder output [C][ld] (tokens t = b*HW + p contiguous per channel) -> the caller's NCHW tensor
 // [B, C, HW]: every image's HW-long run of a channel is copied as it is.  grid (ceil(T / (1024 * VEC)), C), 256 threads,
 // 4 pieces of VEC elements per thread; VEC = 4 needs HW % 4 == 0 (a piece never straddles two images) and an 8-byte

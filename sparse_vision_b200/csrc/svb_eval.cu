@@ -110,7 +110,8 @@ topk_columns_kernel(const float* __restrict__ v0, const int64_t* __restrict__ i0
 
 // ------------------------------------------------------------------------------------------------ histograms
 // hist[bin, u] += #{rows r : vals[r, unit_idx[u]] falls into bin} with torch.histc's CUDA binning (values outside
-// [min, max] are ignored, max itself belongs to the last bin, min == max widens the range by one on both sides).
+// [min, max] are ignored, max itself belongs to the last bin; min == max means "use the data's own minimum and
+// maximum", and only if those coincide too the range is widened by one on both sides).
 __global__ void __launch_bounds__(256)
 histogram_columns_kernel(const float* __restrict__ vals, long long rows, int F, const int64_t* __restrict__ unit_idx,
                          const float* __restrict__ mins, const float* __restrict__ maxs, int bins,
@@ -121,7 +122,23 @@ histogram_columns_kernel(const float* __restrict__ vals, long long rows, int F, 
   __syncthreads();
   const long long col = unit_idx ? unit_idx[u] : u;
   float lo = mins[u], hi = maxs[u];
-  if (lo == hi) { lo -= 1.f; hi += 1.f; }
+  if (lo == hi) {   // block-uniform branch: the column's own range
+    __shared__ float smin[8], smax[8];
+    float a = INFINITY, b = -INFINITY;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+      const float x = vals[r * F + col];
+      a = fminf(a, x); b = fmaxf(b, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = a; smax[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    lo = smin[0]; hi = smax[0];
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); }
+    if (lo == hi) { lo -= 1.f; hi += 1.f; }
+  }
   for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
     const float x = vals[r * F + col];
     if (x >= lo && x <= hi) {

@@ -240,16 +240,26 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   // slab-major X / DIFF + fused NCHW decoder epilogue under the same conditions as svb_sae_step_grads
   void* dec_out = out ? out->dec_out : nullptr;
   const bool slab_ok = !pl.zero_copy_x && post_dec_fusable(x, dec_out, out ? out->dec_layout : SVB_NCHW);
-  pl.fused_dec = slab_ok && pl.hw >= 32;
+  // zero-copy token-major (channels_last) activations through the fused decoder epilogue, as in svb_sae_step_grads
+  const bool tok_fused = pl.zero_copy_x && x->layout == SVB_TOKENS && pl.hw >= 32 && x->n_images <= 65535 &&
+                         (!dec_out || (out->dec_layout == SVB_TOKENS && out->dec_dtype == SVB_BF16 &&
+                                       (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0));
+  pl.fused_dec = (slab_ok && pl.hw >= 32) || tok_fused;
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
+  const bool ds = pl.xs || tok_fused;   // DIFF slab-major
   int out_kind = 0;
-  if (dec_out)
+  if (dec_out && tok_fused) out_kind = 2;
+  else if (dec_out)
     out_kind = (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;
   // weight prologue on the side stream, next to the activation pack (svb_common.cuh: side_fork / side_join)
   SVB_TRY(side_fork(h, st));
   SVB_TRY(run_prep(h->side, pl, p, true));
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs, pl.fused_dec ? pl.xpart : nullptr));
+  if (tok_fused) {  // zero-copy tokens: only their statistics are needed (svb_sae.cu)
+    launch_x_stats_tokens(st, X, pl.xpart, C, pl.hw, pl.nt_hw, pl.n_img);
+    SVB_LAUNCH_CHECK("x_stats_tokens");
+  }
   SVB_TRY(side_join(h, st));
 
   prof_mark(h, st, 1);
@@ -273,8 +283,9 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
     // decoder epilogue writes NCHW d, DIFF (slab-major) and the per-image channel statistics itself (EpiDecNchw)
     EpiDecNchw::Params e2{};
     e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
-    e2.out = dec_out; e2.out_kind = out_kind;
+    e2.out = dec_out; e2.out_kind = out_kind; e2.x_slab = pl.xs ? 1 : 0; e2.tok = tok_fused ? 1 : 0;
     if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
+    if (out_kind == 2 && make_store_tmap_bf16_chunk(&e2.tm_out, dec_out, T, C, C)) return fail(SVB_ERR_TMAP, "tensor map for the token-major output");
     if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     // newest E tiles first (still in L2), as in svb_sae.cu
@@ -308,7 +319,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.block_n = 256; e3.slab_major = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_a, pl.A, T, F) : make_store_tmap_bf16(&e3.tm_a, pl.A, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for A'");
-  SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "gated dE");
+  SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, ds, false)), "gated dE");
   prof_mark(h, st, 5);
   // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
   // decoder weight-gradient GEMM runs (svb_set_comm_stream).
@@ -347,7 +358,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   (grads_tail_kernel<<<1, 1024, 0, ss>>>(ta), svb::count_launch());
   prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, ds, pl.es)), "dW_dec");
   prof_mark(h, st, 7);
   SVB_TRY(side_join(h, st));
   SVB_TRY(run_assemble(st, aa, 2));

@@ -28,7 +28,8 @@ struct SaePlan {
   int s_wd, s_we;  // split-K slices
   int sms;
   bool zero_copy_x, bstat;  // bstat: the K <= 256 GEMMs run B-stationary (per-CTA column-sum partials)
-  bool xs, es;              // slab-major workspaces: X / D / DIFF (xs) and E / dPre' (es), see gemm_host.cuh
+  bool xs, es, ds;          // slab-major workspaces: X / D (xs), E / dPre' (es) and DIFF (ds), see gemm_host.cuh
+  bool tok_fused;           // zero-copy token-major input (channels_last) through the fused decoder epilogue
   bool fused_dec;           // decoder epilogue writes NCHW d and the channel statistics itself (EpiDecNchw)
   int nt_hw;                // HW tiles of 64 positions (x statistics of the pack kernel)
   float *xpart, *dpart;
@@ -59,7 +60,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.tn_f = cdiv(F, 256);
   p.tn_c = cdiv(p.C, 256);
   p.zero_copy_x = acts_are_bf16_tokens(x);
-  p.xs = false; p.es = false; p.fused_dec = false;
+  p.xs = false; p.es = false; p.ds = false; p.fused_dec = false; p.tok_fused = false;
   // X / D / DIFF may be slab-major with a zero-padded last slab (C % 64 != 0): size them for ceil(C / 64) slabs
   const size_t TC = static_cast<size_t>(p.T) * (cdiv(p.C, 64) * 64), TF = static_cast<size_t>(p.T) * F, FC = static_cast<size_t>(F) * p.C;
   p.X = p.zero_copy_x ? nullptr : a.take<bf16>(TC);
@@ -189,11 +190,20 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // vectorised kernel scatters / widens into the NCHW tensor beside the dE GEMM -- measured faster than 8- / 16-byte
   // stores from the epilogue warps (same box: mixed4a 0.63 -> 0.60 ms bf16, mixed3b fp32 2.00 -> 1.95 ms).
   void* dec_out = out ? out->dec_out : nullptr;
-  pl.fused_dec = slab_ok && pl.hw >= 32;
+  // Token-major bf16 activations of a conv layer (a channels_last base model: [B,C,H,W] whose memory IS the [(b h w), C]
+  // token matrix) are read in place by the encoder / dW_enc GEMMs and the fused decoder epilogue, and d goes back in
+  // the same format through one TMA store per chunk: no pack pass, no layout copy anywhere (models/sae_mlp.py:44).
+  // Their x statistics come from a read-only kernel beside the encoder GEMM.
+  pl.tok_fused = pl.zero_copy_x && x->layout == SVB_TOKENS && pl.hw >= 32 && x->n_images <= 65535 &&
+                 (!dec_out || (out->dec_layout == SVB_TOKENS && out->dec_dtype == SVB_BF16 &&
+                               (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0));
+  pl.fused_dec = (slab_ok && pl.hw >= 32) || pl.tok_fused;
   // C % 64 != 0 (mixed3b: 480, mixed4d: 528): only the fused epilogue keeps the last slab's padding columns zero
   pl.xs = slab_ok && (C % 64 == 0 || pl.fused_dec);
+  pl.ds = pl.xs || pl.tok_fused;
   int out_kind = 0;
-  if (dec_out)
+  if (dec_out && pl.tok_fused) out_kind = 2;
+  else if (dec_out)
     out_kind = (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;   // row pitch of the channel-major copy (out_kind 4)
   prof_begin_step(h);
@@ -202,6 +212,13 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   SVB_TRY(side_fork(h, st));
   SVB_TRY(run_prep(h->side, pl, p, true));
   if (!pl.zero_copy_x) SVB_TRY(pack_acts(st, x, pl.X, pl.xs, pl.fused_dec ? pl.xpart : nullptr));
+  // zero-copy tokens: only their statistics are needed (one read-only pass, where the pack pass would be).  Measured:
+  // hidden on the side stream beside the encoder GEMM it gets the 4 SMs the 144-CTA GEMM leaves free, runs for the
+  // whole encoder AND decoder phase and costs the decoder 0.03 ms; here it is 0.02 ms beside the weight prologue.
+  if (pl.tok_fused) {
+    launch_x_stats_tokens(st, X, pl.xpart, C, pl.hw, pl.nt_hw, pl.n_img);
+    SVB_LAUNCH_CHECK("x_stats_tokens");
+  }
   SVB_TRY(side_join(h, st));
 
   prof_mark(h, st, 1);
@@ -227,8 +244,9 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   if (pl.fused_dec) {
     EpiDecNchw::Params e2{};
     e2.bias = p->b_dec; e2.x = X; e2.sq_partial = pl.sq_part; e2.part = pl.dpart; e2.hw = pl.hw;
-    e2.out = dec_out; e2.out_kind = out_kind;
+    e2.out = dec_out; e2.out_kind = out_kind; e2.x_slab = pl.xs ? 1 : 0; e2.tok = pl.tok_fused ? 1 : 0;
     if (make_store_tmap_bf16_slab32(&e2.tm_diff, pl.DIFF, T, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
+    if (out_kind == 2 && make_store_tmap_bf16_chunk(&e2.tm_out, dec_out, T, C, C)) return fail(SVB_ERR_TMAP, "tensor map for the token-major output");
     if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     // the encoder wrote E from the first token tile to the last, so its newest ~100 MB are still in L2: walk the
@@ -262,13 +280,13 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
     if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "dE (B-stationary)");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false, kAPrefetch)), "dE (B-stationary)");
   } else {
     EpiDPreNoSum::Params e3{};
     e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
     if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
       return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.xs, false)), "dE");
+    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false)), "dE");
   }
   prof_mark(h, st, 5);
   // Weight gradients, split-K over tokens.  The encoder side goes first: with its assembly done, the leading part of
@@ -306,7 +324,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
   prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.xs, pl.es)), "dW_dec");
+  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.ds, pl.es)), "dW_dec");
   prof_mark(h, st, 7);
   // rest of the gradient assembly: the decoder weight gradient, after everything forked above has joined
   SVB_TRY(side_join(h, st));

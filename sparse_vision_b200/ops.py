@@ -104,7 +104,10 @@ def _train_out(x, a, F, want_dec, dec_dtype):
     stats, freq = f32[:L.STATS_LEN], f32[L.STATS_LEN:L.STATS_LEN + F]
     n_active = block[(L.STATS_LEN + F) * 4:words * 4].view(torch.int32)
     dead = block[words * 4:]
-    dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype) if want_dec else None
+    dec = None
+    if want_dec:   # the reconstruction goes back in the layout the activations came in (channels_last stays so)
+        fmt = torch.channels_last if L.is_channels_last_tokens(x) else torch.contiguous_format
+        dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype, memory_format=fmt)
     out = L.TrainOut(L.ptr(dec), L.dtype_code(dec) if want_dec else 0, a.layout, L.ptr(stats),
                      L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active)))
     return out, StepResult(stats, dead, freq, n_active, dec)
@@ -374,7 +377,8 @@ def ie_allchannels(err, avg, g, batch_size, scale=None):
 def node_ie_layer(x, grad, params, enc_avg, err_avg, x_avg, scale=None):
     """compute_ie.py:242-267,442-453 for one layer / one batch -> (ie_sae_features [F], ie_sae_error, ie_neurons [C])."""
     a, x = L.acts_of(x)
-    grad = grad.contiguous()
+    # the gradient is read through the same descriptor as x: same memory format
+    grad = grad.contiguous(memory_format=torch.channels_last) if L.is_channels_last_tokens(x) else grad.contiguous()
     if grad.dtype != x.dtype or grad.shape != x.shape:
         raise ValueError("grad must match x in dtype and shape")
     p = _sae_params(*params)

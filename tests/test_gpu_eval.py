@@ -90,7 +90,7 @@ def test_histogram_matches_torch_histc():
     tops = torch.tensor([vals[:, u].max().item() for u in units])
     smalls = torch.tensor([vals[:, u].min().item() for u in units])
     tops[1], smalls[1] = 0.5, -0.5                 # values outside the range are ignored
-    tops[2] = smalls[2] = 0.25                      # min == max: torch widens the range by one on both sides
+    tops[2] = smalls[2] = 0.25                      # min == max: torch uses the data's own range
     info = {("l", "orig"): (torch.zeros(bins, len(units)), tops, smalls, units)}
     want = torch.zeros(bins, len(units))
     for rep in range(2):                           # accumulates over batches
@@ -106,7 +106,7 @@ def test_histogram_matches_torch_histc():
 def test_eval_batches_top_samples_vs_oracle():
     """Three eval batches through ModelPipeline.hook (SAE in inference mode): losses, dead-unit AND and the running
     top / small k samples of every unit against the CPU oracle.  Index parity: exact for every unit whose oracle values
-    are separated by more than the bf16 error of the spatial means at the ranks that matter (>= 90 % of the units)."""
+    are separated by more than the bf16 error of the spatial means; near ties may swap, never anything else."""
     import sparse_vision_b200.models.sae_mlp as M
     from sparse_vision_b200.model_pipeline import ModelPipeline
 
@@ -144,8 +144,10 @@ def test_eval_batches_top_samples_vs_oracle():
         want_v, want_i = torch.topk(allm, K + 1, dim=0, largest=largest)
         e = (vals.cpu() - want_v[:K]).abs().max().item()             # bf16 GEMM operands vs the fp32 oracle
         err = max(err, e)
-        gaps = (want_v[:-1] - want_v[1:]).abs().min(dim=0).values    # smallest gap among the ranks 1..K+1 of every unit
-        decided = gaps > 4 * e
-        assert decided.float().mean() >= 0.5, decided.float().mean()
-        assert torch.equal(idx.cpu()[:, decided], want_i[:K][:, decided])
+        # the sample recorded at rank j must be the oracle's rank-j sample, or one whose oracle value is within the bf16
+        # error of it (a near tie the two precisions may order differently)
+        picked = torch.gather(allm, 0, idx.cpu())
+        assert (picked - want_v[:K]).abs().max().item() <= 2 * e + 1e-6
+        exact = (idx.cpu() == want_i[:K]).float().mean().item()
+        assert exact >= 0.9, exact
     assert err <= 1e-2 * allm.abs().max().item()

@@ -571,3 +571,66 @@ def test_apply_sae_ablation_vs_reference_golden(golden_dir):
     assert _relerr(new_dec.cpu().numpy(), g["ablated_dec"]) < 2 * REL
     assert torch.equal(same, dec0)                                   # no nodes: the reconstruction itself (:2809)
     assert _relerr(new_dec.cpu().numpy(), g["dec"]) > 10 * REL       # the ablation did change the output
+
+
+# ------------------------------------------------------------------------------------------------ channels_last
+@pytest.mark.parametrize("B,C,H,W,k,kind", [
+    (3, 64, 8, 8, 4, "sae_mlp"),         # two images per 128-token tile
+    (4, 128, 14, 14, 4, "sae_mlp"),      # 196-pixel maps: image boundaries inside warps
+    (9, 64, 7, 7, 4, "sae_mlp"),         # 49-pixel maps
+    (2, 480, 28, 28, 4, "sae_mlp"),      # mixed3b: C % 64 = 32 -> zero-padded last DIFF slab, K tail in the encoder
+    (3, 528, 14, 14, 4, "sae_mlp"),      # mixed4d
+    (8, 256, 28, 28, 8, "sae_mlp"),      # cfg2 shape
+    (2, 64, 5, 5, 4, "sae_mlp"),         # fewer than 32 tokens per image: un-fused path
+    (6, 128, 14, 14, 4, "gated_sae"),
+    (3, 512, 14, 14, 16, "gated_sae"),   # cfg3 shape
+])
+def test_channels_last_activations_are_read_in_place(B, C, H, W, k, kind):
+    """north_star item 5 / models/sae_mlp.py:44: B*H*W pixels as tokens WITHOUT a layout copy.  A channels_last bf16
+    [B,C,H,W] tensor (what a channels_last cuDNN base model emits) is the token matrix itself; the step must read it in
+    place, hand the reconstruction back in the same format, and agree with the step on the NCHW copy of the same
+    values (same GEMMs, same operands) and with the oracle."""
+    ops = _ops()
+    from sparse_vision_b200 import _lib as L
+    torch.manual_seed(0)
+    keys = O.SAE_MLP_KEYS if kind == "sae_mlp" else O.GATED_KEYS
+    p = O.init_sae_mlp(C, k) if kind == "sae_mlp" else O.init_gated_sae(C, k)
+    F = C * k
+    planted = torch.randperm(F, generator=torch.Generator().manual_seed(1))[:max(F // 20, 1)]
+    for key in (("encoder.bias",) if kind == "sae_mlp" else ("b_gate", "b_mag")):
+        p[key][planted] = -50.0
+    p["decoder.bias"].normal_(0, 0.05, generator=torch.Generator().manual_seed(2))
+    lam = 5.0 if kind == "sae_mlp" else 0.1
+    x = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(77))).bfloat16().cuda()
+    x_cl = x.contiguous(memory_format=torch.channels_last)
+    assert L.is_channels_last_tokens(x_cl) and not L.is_channels_last_tokens(x)
+    a_cl, x_same = L.acts_of(x_cl)
+    assert x_same.data_ptr() == x_cl.data_ptr() and a_cl.layout == L.SVB_TOKENS and a_cl.hw == H * W   # zero copy
+    step_fn = ops.sae_train_step if kind == "sae_mlp" else ops.gated_train_step
+    runs = []
+    launches = []
+    for xin in (x, x_cl):
+        params = [p[key].clone().cuda() for key in keys]
+        ms = [torch.zeros_like(q) for q in params]
+        vs = [torch.zeros_like(q) for q in params]
+        n0 = L.load().svb_launch_count()
+        res = step_fn(xin, params, ms, vs, 1, 1e-3, lam, k, optimizer="constrained_adam")
+        launches.append(L.load().svb_launch_count() - n0)
+        runs.append((res, params))
+    (r0, p0), (r1, p1) = runs
+    assert r1.dec.shape == x.shape and r1.dec.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(r1.dec.contiguous(), r0.dec), "reconstruction differs between the two layouts"
+    assert torch.equal(r1.dead, r0.dead) and torch.equal(r1.freq, r0.freq)
+    s0, s1 = r0.scalars(), r1.scalars()
+    for key in SCALARS + ["n_dead"]:
+        assert abs(s1[key] - s0[key]) <= 1e-5 * max(abs(s0[key]), 1e-3), (key, s1[key], s0[key])
+    for a, b, key in zip(p1, p0, keys):
+        assert (a - b).abs().max().item() <= 1e-6, key       # same GEMMs on the same operand values
+    if H * W >= 32:
+        assert launches[1] <= launches[0], launches            # no pack kernel; the x statistics ride on a side stream
+    st = O.new_adam_state(p, keys)
+    ref = O.train_step(kind, p, st, x.float().cpu(), lam, "constrained_adam", 1e-3, k)
+    for key in SCALARS:
+        assert abs(s1[key] - ref[key]) <= REL * max(abs(ref[key]), 1e-3), (key, s1[key], ref[key])
+    assert np.array_equal(r1.dead.cpu().numpy().astype(bool), ref["dead"].numpy())
+    assert _relerr(r1.dec.float().cpu().numpy(), ref["dec"].numpy()) < 2 * REL
