@@ -22,11 +22,13 @@ def main():
     shutil.copy(launches, os.path.join(prof, f"{tag}_launches.csv"))
     rows = list(csv.DictReader(io.StringIO(txt)))
     names = [r["Kernel Name"] for r in rows]
-    starts = [i for i, n in enumerate(names) if "pack_nchw" in n]
+    # the first kernel of a step: the pack pass (NCHW input) or the x-statistics pass (channels_last input, read in place)
+    starts = [i for i, n in enumerate(names) if "pack_nchw" in n or "x_stats_tokens" in n]
     s, e = starts[-3], starts[-2]          # one complete step near the end
     step = rows[s:e]
     total = sum(float(r["Metric Value"]) for r in step) / 1000
-    out = [f"# {tag} — ncu launch list of one training step (`python bench.py --steps 3 --warmup 3`)", "",
+    cmd = os.environ.get("SVB_NCU_CMD", "python bench.py --steps 3 --warmup 3")
+    out = [f"# {tag} — ncu launch list of one training step (`{cmd}`)", "",
            "`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and serialised — compare SHARES.",
            "", "| # | kernel | grid | us | share |", "|---|---|---|---|---|"]
     for i, r in enumerate(step):
@@ -55,7 +57,7 @@ def main():
             lab = "dWenc_gemm" if seen["dW"] == 1 else "dWdec_gemm"   # the encoder-side weight gradient runs first
         labels.append(lab)
     md = [f"# {tag} — `ncu --set full --clock-control none` of the five GEMM launches of one training step", "",
-          f"Command: `ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 15 -c 5 python bench.py --steps 3 --warmup 3` (report: `{os.path.basename(rep)}`).",
+          f"Command: `ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 15 -c 5 {os.environ.get('SVB_NCU_CMD', 'python bench.py --steps 3 --warmup 3')}` (report: `{os.path.basename(rep)}`).",
           "", "| metric | " + " | ".join(labels) + " |", "|---|" + "---|" * len(labels)]
     traffic = {}
     for w in want:
