@@ -394,3 +394,141 @@ def node_ie_layer_via_autograd(p, x, downstream):
     # pass-through gradient: overwrite whatever flows into x_d with grad_original (compute_ie.py:265)
     x_d.backward(grad_original)
     return enc.detach(), enc_leaf.grad.detach(), grad_original
+
+
+# ----------------------------------------------------------------------------------------------- edge IE / faithfulness
+def edge_ie_pass(layers, saes, feature_indices, enc_avg, err_avg, forward_from, loss_fn, inputs_list):
+    """compute_ie.py:476-711 (compute_edge_ie) with plain autograd instead of nnsight -- a LITERAL restatement: for
+    every pair of consecutive layers (u, d) the upstream layer is intervened on with the stop-gradient
+    x_u~ = dec_u + (x_u - dec_u).detach() (:242-267, no pass-through), the downstream SAE is applied WITHOUT
+    stop-gradient, and for every selected downstream feature j the scalar mean_t(grad_m_d[t, j] * enc_d[t, j]) is
+    back-propagated to enc_u and dec_u (:589-611); the SAE error of d likewise (:633-650); the last layer's downstream
+    node is the model loss (:672-700).  Parity unpinned (the reference needs nnsight + pretrained GoogLeNet).
+
+    layers: ordered names; saes: {name: param dict}; forward_from(name_or_None, tensor) -> {name: raw layer output for
+    every LATER layer, "out": logits} running the base model from the output of layer `name` (None: from the inputs);
+    loss_fn(logits, targets); inputs_list: [(inputs, targets)].  Returns {name_u: [n_u + 1, n_d + 1]}."""
+    vals = {}
+    for i, nu in enumerate(layers):
+        n_d = len(feature_indices[layers[i + 1]]) if i + 1 < len(layers) else 0
+        vals[nu] = torch.zeros(len(feature_indices[nu]) + 1, n_d + 1)
+    for batch_idx, (inputs, targets) in enumerate(inputs_list, start=1):
+        b = inputs.shape[0]
+        # gradients of the model loss w.r.t. every layer output of the un-intervened model (get_grad_original :270-311)
+        acts = forward_from(None, inputs.detach())
+        leaves = {}
+        x = inputs.detach()
+        outs = {}
+        prev = None
+        for name in layers:                                   # re-run layer by layer so that every output is a leaf
+            o = forward_from(prev, x)[name]
+            leaves[name] = o.detach().requires_grad_(True)
+            outs[name] = leaves[name]
+            x, prev = leaves[name], name
+        logits = forward_from(prev, x)["out"]
+        grad_orig = {}
+        g = torch.autograd.grad(loss_fn(logits, targets), leaves[layers[-1]])[0]
+        grad_orig[layers[-1]] = g
+        for i in range(len(layers) - 2, -1, -1):              # chain the segments backwards
+            nu, nd = layers[i], layers[i + 1]
+            od = forward_from(nu, leaves[nu])[nd]
+            grad_orig[nu] = torch.autograd.grad(od, leaves[nu], grad_outputs=grad_orig[nd])[0]
+        del acts
+
+        def upstream(nu, x_u):
+            p = saes[nu]
+            h, w = x_u.shape[2:]
+            x_u = x_u.detach().requires_grad_(True)            # the reference's inputs require grad (:404)
+            x_tok, _ = to_tokens(x_u)
+            enc = torch.relu(F.linear(x_tok - p["decoder.bias"], p["encoder.weight"], p["encoder.bias"]))
+            enc.retain_grad()
+            dec = from_tokens(F.linear(enc, p["decoder.weight"], p["decoder.bias"]), b, h, w)
+            dec.retain_grad()
+            err = (x_u - dec).detach()                         # stop-gradient (:256-259)
+            return enc, dec, err, dec + err
+
+        def update(nu, enc_u, err_u, g_feat, g_err, col):
+            sel = feature_indices[nu]
+            ie_f = compute_ie_channel_wise(enc_u[:, sel], enc_avg[nu][sel], g_feat, b)
+            ie_e = compute_ie_all_channels(err_u, err_avg[nu], g_err, b)
+            batch_ie = torch.cat((ie_f, ie_e.reshape(1)))
+            vals[nu][:, col] = batch_ie if batch_idx == 1 else (vals[nu][:, col] * (batch_idx - 1) + batch_ie) / batch_idx
+
+        for i in range(len(layers) - 1):
+            nu, nd = layers[i], layers[i + 1]
+            pd = {k: v.detach() for k, v in saes[nd].items()}
+            x_u = leaves[nu].detach()
+            # grad of the loss w.r.t. the downstream encoder output under the node-IE intervention (:561-566)
+            g_d = grad_orig[nd].detach()
+            grad_m_d = to_tokens(g_d)[0] @ pd["decoder.weight"]
+            enc_u, dec_u, err_u, x_t = upstream(nu, x_u)
+            x_d = forward_from(nu, x_t)[nd]
+            xd_tok, _ = to_tokens(x_d)
+            enc_d = torch.relu(F.linear(xd_tok - pd["decoder.bias"], pd["encoder.weight"], pd["encoder.bias"]))
+            dec_d = F.linear(enc_d, pd["decoder.weight"], pd["decoder.bias"])
+            err_d = xd_tok - dec_d                              # no stop-gradient downstream (:583-586)
+            for col, j in enumerate(feature_indices[nd]):
+                prod = (grad_m_d[:, j] * enc_d[:, j]).mean()
+                enc_u.grad = None
+                dec_u.grad = None
+                prod.backward(retain_graph=True)
+                update(nu, enc_u.detach(), err_u, enc_u.grad[:, feature_indices[nu]].clone(), dec_u.grad.clone(), col)
+            prod = (to_tokens(g_d)[0] * err_d).sum(dim=1).mean()
+            enc_u.grad = None
+            dec_u.grad = None
+            prod.backward()
+            update(nu, enc_u.detach(), err_u, enc_u.grad[:, feature_indices[nu]].clone(), dec_u.grad.clone(), -1)
+        # last layer: the downstream node is the model loss (:672-700)
+        nu = layers[-1]
+        enc_u, dec_u, err_u, x_t = upstream(nu, leaves[nu].detach())
+        loss_fn(forward_from(nu, x_t)["out"], targets).backward()
+        update(nu, enc_u.detach(), err_u, enc_u.grad[:, feature_indices[nu]].clone(), dec_u.grad.clone(), 0)
+    return vals
+
+
+def faithfulness_pass(layers, saes, enc_avg, err_avg, x_avg, ie_feat, ie_err, ie_neur, run_with, loss_fn, inputs_list,
+                      threshold, model_or_sae="sae"):
+    """compute_ie.py:715-944 (compute_faithfulness): losses of the circuit (features / errors whose |IE| exceeds the
+    threshold kept, the rest mean-ablated), of the circuit with all SAE errors zero- or mean-ablated, of the empty
+    circuit and of the full model, averaged over batches; faithfulness = (m(C) - m(empty)) / (m(M) - m(empty)).
+    run_with(inputs, fn) runs the base model replacing every layer's output by fn(name, output)."""
+    nodes = {n: ie_feat[n].abs() > threshold for n in layers}
+    err_nodes = {n: bool(abs(float(ie_err[n])) > threshold) for n in layers}
+    neur_nodes = {n: ie_neur[n].abs() > threshold for n in layers}
+    sums = {"zero": 0.0, "mean": 0.0, "C": 0.0, "empty": 0.0, "M": 0.0}
+    with torch.no_grad():
+        for inputs, targets in inputs_list:
+            m = lambda fn: float(loss_fn(run_with(inputs, fn), targets))
+            if model_or_sae == "sae":
+                def circuit(kind):
+                    def fn(name, x):
+                        keep = nodes[name] if kind != "empty" else torch.zeros_like(nodes[name])
+                        _, dec, new_dec = apply_sae(saes[name], x, nodes=keep, ablation=enc_avg[name])
+                        if kind == "zero":
+                            return new_dec
+                        if kind in ("mean", "empty"):
+                            return new_dec + err_avg[name]
+                        err = x - dec
+                        if not err_nodes[name]:
+                            err = err_avg[name]
+                        return new_dec + err
+                    return fn
+                for kind in ("zero", "mean", "C", "empty"):
+                    sums[kind] += m(circuit(kind))
+            else:
+                def c_model(name, x):
+                    x = x.clone()
+                    x[:, ~neur_nodes[name]] = x_avg[name][~neur_nodes[name]]
+                    return x
+                sums["C"] += m(c_model)
+                sums["empty"] += m(lambda name, x: x_avg[name].unsqueeze(0).expand_as(x).clone())
+            sums["M"] += m(lambda name, x: x)
+    n = len(inputs_list)
+    avg = {k: v / n for k, v in sums.items()}
+    out = {"m_C": avg["C"], "m_empty": avg["empty"], "m_M": avg["M"],
+           "faithfulness": (avg["C"] - avg["empty"]) / (avg["M"] - avg["empty"])}
+    if model_or_sae == "sae":
+        out["faithfulness_sae_errors_zero_ablated"] = (avg["zero"] - avg["empty"]) / (avg["M"] - avg["empty"])
+        out["faithfulness_sae_errors_mean_ablated"] = (avg["mean"] - avg["empty"]) / (avg["M"] - avg["empty"])
+        out["m_C_zero"], out["m_C_mean"] = avg["zero"], avg["mean"]
+    return out

@@ -6,7 +6,8 @@ layer, and then ANOTHER full forward+backward per SAE layer with the interventio
 the pass-through gradient.  Under exactly that intervention  d loss / d enc == rearrange(grad_original) @ W_dec  (the
 reference's own check: supplementary_files_2/nnsight_intervention_check.py:194-195,212-213), so ONE forward+backward
 with plain torch hooks yields x_l and g_l for every layer and the per-layer work becomes three GEMMs and three
-reductions on the GPU (svb_node_ie_layer).  Edge IE / faithfulness (:476-944) are out of scope.
+reductions on the GPU (svb_node_ie_layer).  Edge IE (:476-711) and faithfulness (:715-944) are restated on the same
+building blocks (compute_edge_ie, compute_faithfulness below).
 
 Data parallel: shard the images of each batch across ranks; every rank accumulates un-normalised sums (scale = 1)
 and token counts; one all-reduce(SUM) per layer at the end gives the same global means as the reference's
@@ -177,6 +178,176 @@ class IE:
             err[name] = (err[name] / tg)[0]
             neur[name] = neur[name] / tg
         return feat, err, neur
+
+    # ------------------------------------------------------------------ compute_edge_ie (:476-711)
+    def _forward_segments(self, inputs, names):
+        """One forward of the frozen model in which every layer of `names` hands a detached leaf on: outs[n] is the
+        layer's raw output (its graph reaches back to the previous leaf only), leaves[n] the leaf the rest of the
+        network consumed.  The network is thereby cut into differentiable segments leaf_i -> out_{i+1}."""
+        outs, leaves, handles = {}, {}, []
+
+        def make_hook(name):
+            def hook(_m, _i, out):
+                outs[name] = out
+                leaves[name] = out.detach().requires_grad_(True)
+                return leaves[name]
+            return hook
+
+        for name in names:
+            handles.append(self.layers[name].register_forward_hook(make_hook(name)))
+        try:
+            with torch.enable_grad():
+                logits = self.model(inputs)
+        finally:
+            for h in handles:
+                h.remove()
+        return outs, leaves, logits
+
+    def compute_edge_ie(self, batches, averages, custom_layers, feature_indices):
+        """compute_ie.py:476-711.  custom_layers: ordered subset of the hooked layers; feature_indices: {layer: [SAE
+        feature indices]} (:81-88).  For every pair of consecutive layers (u, d), every selected downstream feature j
+        and the downstream SAE error, the reference back-propagates  mean_t(dloss/d node_d * node_d)  from d to the
+        upstream encoder output / SAE error (one traced forward + backward per node) and reduces the result with
+        compute_ie_channel_wise / compute_ie_all_channels; the last layer's downstream node is the model loss.
+
+        Here ONE forward per batch cuts the network into segments; the cotangent of every downstream node at the
+        downstream layer output is written down in closed form
+            feature j : 1/T * (g_d W_dec)[t, j] * 1[enc_d[t, j] > 0] * W_enc[j, :]
+            SAE error : 1/T * (g_d - ((g_d W_dec) * 1[enc_d > 0]) W_enc)          (no stop-gradient downstream, :583-586)
+        pulled back to the upstream layer by one vector-Jacobian product of the segment (cuDNN, the base model is a
+        library), and the upstream part -- encoder, g W_dec, the three reductions -- is svb_node_ie_layer.
+        Returns {name_u: float32 [len(features_u) + 1, len(features_d) + 1]} (rows: features then SAE error; columns:
+        downstream features then downstream SAE error; one column for the model loss at the last layer), averaged over
+        the batches like :357-360 (every batch counts once)."""
+        from . import ops as O
+        names = list(custom_layers)
+        vals = {}
+        for i, nu in enumerate(names):
+            n_d = len(feature_indices[names[i + 1]]) if i + 1 < len(names) else 0
+            vals[nu] = torch.zeros(len(feature_indices[nu]) + 1, n_d + 1, device=self.device)
+        sel = {n: torch.as_tensor(list(feature_indices[n]), dtype=torch.long, device=self.device) for n in names}
+        bf = torch.bfloat16
+        batch_idx = 0
+        for inputs, targets in batches:
+            if inputs.shape[0] == 0:
+                continue
+            batch_idx += 1
+            inputs, targets = inputs.to(self.device), targets.to(self.device)
+            outs, leaves, logits = self._forward_segments(inputs, names)
+            with torch.enable_grad():
+                loss = self.model_criterion(logits, targets)
+            g = {names[-1]: torch.autograd.grad(loss, leaves[names[-1]], retain_graph=True)[0]}
+            for i in range(len(names) - 2, -1, -1):                      # get_grad_original (:270-311), segment by segment
+                g[names[i]] = torch.autograd.grad(outs[names[i + 1]], leaves[names[i]], grad_outputs=g[names[i + 1]],
+                                                  retain_graph=True)[0]
+
+            def upstream_ie(nu, grad_u):
+                x_u = leaves[nu].detach()
+                x_u = x_u.float() if x_u.dtype not in (torch.float32, bf) else x_u
+                f, e, _ = O.node_ie_layer(x_u, grad_u.to(x_u.dtype), [p.detach() for p in self.saes[nu].param_list()],
+                                          averages["encoder_output_average"][nu], averages["sae_error_average"][nu],
+                                          averages["original_layer_output_average"][nu])
+                return torch.cat((f[sel[nu]], e.reshape(1)))
+
+            def update(nu, col, batch_ie):
+                vals[nu][:, col] = batch_ie if batch_idx == 1 else (vals[nu][:, col] * (batch_idx - 1) + batch_ie) / batch_idx
+
+            for i in range(len(names) - 1):
+                nu, nd = names[i], names[i + 1]
+                sae_d = self.saes[nd]
+                w_enc, b_enc, w_dec, b_dec = [p.detach() for p in sae_d.param_list()]
+                x_d = outs[nd]
+                b, c, h, w = x_d.shape
+                t_d = b * h * w
+                xd = x_d.detach()
+                enc_d, _, _ = O.sae_forward(xd.float() if xd.dtype not in (torch.float32, bf) else xd, w_enc, b_enc, w_dec,
+                                            b_dec, want_pre=False, want_dec=False)
+                active = enc_d > 0                                              # relu'(pre) = 1[pre > 0] = 1[enc > 0]
+                g_tok = g[nd].detach().permute(0, 2, 3, 1).reshape(t_d, c).float()
+                g_enc = O.gemm_bf16(g_tok.to(bf), w_dec.to(bf), b_mn=True)      # [T, F] = g W_dec (d loss / d enc_d, :561-566)
+
+                def pull_back(v_tok):
+                    v = v_tok.reshape(b, h, w, c).permute(0, 3, 1, 2).to(x_d.dtype)
+                    return torch.autograd.grad(x_d, leaves[nu], grad_outputs=v, retain_graph=True)[0]
+
+                for col, j in enumerate(feature_indices[nd]):
+                    coef = g_enc[:, j] * active[:, j] / t_d                     # [T]
+                    update(nu, col, upstream_ie(nu, pull_back(coef[:, None] * w_enc[j][None, :])))
+                back = O.gemm_bf16((g_enc * active).to(bf), w_enc.to(bf), b_mn=True)   # [T, C] = ((g W_dec) * mask) W_enc
+                update(nu, -1, upstream_ie(nu, pull_back((g_tok - back) / t_d)))
+                del enc_d, active, g_enc, back
+            update(names[-1], 0, upstream_ie(names[-1], g[names[-1]]))           # downstream node = model loss (:672-700)
+        return vals
+
+    # ------------------------------------------------------------------ compute_faithfulness (:715-944)
+    def _loss_with(self, inputs, targets, replace):
+        """Model loss with every hooked layer's output replaced by replace(name, output) (layers in network order, so
+        later layers see the modified activations, as in the reference's sequential nnsight interventions)."""
+        handles = [m.register_forward_hook(lambda _m, _i, out, n=n: replace(n, out)) for n, m in self.layers.items()]
+        try:
+            with torch.no_grad():
+                return self.model_criterion(self.model(inputs), targets)
+        finally:
+            for h in handles:
+                h.remove()
+
+    def compute_faithfulness(self, batches, averages, node_ie, feature_node_threshold=0.0, model_or_sae="sae"):
+        """compute_ie.py:715-944.  node_ie = (ie_sae_features, ie_sae_error, ie_model_neurons) as compute_node_ie returns
+        them.  Nodes whose |IE| exceeds the threshold form the circuit C; everything else is mean-ablated
+        (apply_sae(nodes=, ablation=), utils.py:2795-2807).  Returns the batch-averaged losses m(C), m(C) with all SAE
+        errors zero- / mean-ablated, m(empty), m(M) and the faithfulness values (m(C) - m(empty)) / (m(M) - m(empty))."""
+        from .utils import apply_sae
+        ie_feat, ie_err, ie_neur = node_ie
+        thr = feature_node_threshold                                           # error threshold = feature threshold (:722)
+        nodes = {n: ie_feat[n].abs() > thr for n in self.layers}
+        err_nodes = {n: bool(abs(float(ie_err[n])) > thr) for n in self.layers}
+        neur_nodes = {n: ie_neur[n].abs() > thr for n in self.layers}
+        enc_avg, err_avg = averages["encoder_output_average"], averages["sae_error_average"]
+        x_avg = averages["original_layer_output_average"]
+        sums = torch.zeros(5, device=self.device, dtype=torch.float64)          # zero, mean, C, empty, M
+        n_batches = 0
+
+        def circuit(kind):
+            def fn(name, x):
+                keep = nodes[name] if kind != "empty" else torch.zeros_like(nodes[name])
+                _, dec, new_dec = apply_sae(self.saes[name], x, nodes=keep, ablation=enc_avg[name])
+                if kind == "zero":
+                    out = new_dec
+                elif kind in ("mean", "empty"):
+                    out = new_dec + err_avg[name]
+                else:
+                    out = new_dec + ((x - dec) if err_nodes[name] else err_avg[name])
+                return out.to(x.dtype)
+            return fn
+
+        def model_circuit(name, x):
+            x = x.clone()
+            x[:, ~neur_nodes[name]] = x_avg[name][~neur_nodes[name]].to(x.dtype)
+            return x
+
+        for inputs, targets in batches:
+            if inputs.shape[0] == 0:
+                continue
+            n_batches += 1
+            inputs, targets = inputs.to(self.device), targets.to(self.device)
+            if model_or_sae == "sae":
+                for k, kind in enumerate(("zero", "mean", "C", "empty")):
+                    sums[k] += self._loss_with(inputs, targets, circuit(kind)).double()
+            else:
+                sums[2] += self._loss_with(inputs, targets, model_circuit).double()
+                sums[3] += self._loss_with(inputs, targets,
+                                           lambda n, x: x_avg[n].to(x.dtype).unsqueeze(0).expand_as(x).clone()).double()
+            with torch.no_grad():
+                sums[4] += self.model_criterion(self.model(inputs), targets).double()
+        zero, mean, m_c, empty, m_m = (sums / max(n_batches, 1)).tolist()          # ONE device->host copy
+        out = {"m_C": m_c, "m_empty": empty, "m_M": m_m, "faithfulness": (m_c - empty) / (m_m - empty),
+               "feature_node_threshold": thr, "error_node_threshold": thr}
+        if model_or_sae == "sae":
+            out["m_C_zero"], out["m_C_mean"] = zero, mean
+            out["faithfulness_sae_errors_zero_ablated"] = (zero - empty) / (m_m - empty)
+            out["faithfulness_sae_errors_mean_ablated"] = (mean - empty) / (m_m - empty)
+            out["nodes_in_circuit"] = {n: int(v.sum()) for n, v in nodes.items()}
+        return out
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
