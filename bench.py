@@ -618,6 +618,28 @@ def run_svb(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t]
 
+    # the same step on the OTHER memory format of the same activations (NCHW needs the pack pass; channels_last is read
+    # in place), for the record
+    other_fmt = None
+    if "other_format" not in skip:
+        alt = [t.contiguous() if args.acts_format == "channels_last" else t.contiguous(memory_format=torch.channels_last)
+               for t in xdev]
+        for i in range(3):
+            one_step(alt[i % 2])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(args.steps):
+            one_step(alt[i % 2])
+        a1.record()
+        barrier()
+        (ms_alt,) = job_max(a0.elapsed_time(a1))
+        other_fmt = {"format": "nchw" if args.acts_format == "channels_last" else "channels_last",
+                     "ms_per_step": ms_alt / args.steps, "value": g_tokens / (ms_alt / args.steps * 1e-3),
+                     "note": "timed BEFORE the main region (3 warm-up steps); on these boxes the first tens of milliseconds after "
+                             "idle run ~2 % slower whatever the format"}
+        del alt
+
     for i in range(args.warmup):
         res = one_step(xdev[i % 2])
     barrier()
@@ -644,26 +666,6 @@ def run_svb(args):
     (ms_total,) = job_max(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = g_tokens / (ms_step * 1e-3)
-
-    # the same step on the OTHER memory format of the same activations (NCHW needs the pack pass; channels_last is read
-    # in place), for the record
-    other_fmt = None
-    if "other_format" not in skip:
-        alt = [t.contiguous() if args.acts_format == "channels_last" else t.contiguous(memory_format=torch.channels_last)
-               for t in xdev]
-        for i in range(3):
-            one_step(alt[i % 2])
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(args.steps):
-            one_step(alt[i % 2])
-        a1.record()
-        barrier()
-        (ms_alt,) = job_max(a0.elapsed_time(a1))
-        other_fmt = {"format": "nchw" if args.acts_format == "channels_last" else "channels_last",
-                     "ms_per_step": ms_alt / args.steps, "value": g_tokens / (ms_alt / args.steps * 1e-3)}
-        del alt
 
     # ---------------------------------------------------------------- sustained leg: seconds of back-to-back steps
     sustained = None

@@ -227,6 +227,11 @@ int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts* x, const s
  */
 int svb_spatial_mean(svb_handle* h, void* stream, const void* t, int32_t dtype, int32_t layout, int64_t n_images,
                      int32_t hw, int32_t F, float* out);
+/* compute_ie.py:146-207: sums over the images of a batch, per position -- out[per_image] = sum_b t[b*per_image + i] for
+ * t = [n_images, per_image] (f32 / bf16; e.g. token-major encoder output with per_image = HW*F, or an NCHW layer output
+ * with per_image = C*HW).  Images are added in order (deterministic). */
+int svb_image_sum(svb_handle* h, void* stream, const void* t, int32_t dtype, int64_t n_images, int64_t per_image,
+                  float* out);
 int svb_topk_columns(svb_handle* h, void* stream, const float* vals0, const int64_t* idx0, const int64_t* files0,
                      int32_t n0, const float* vals1, const int64_t* idx1, const int64_t* files1, int32_t n1, int32_t F,
                      int32_t k, int32_t largest, float* out_vals, int64_t* out_idx, int64_t* out_files);

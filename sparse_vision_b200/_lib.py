@@ -114,6 +114,7 @@ SYMBOLS = {
     "svb_gemm_bf16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, _vp, C.c_int32, C.c_int64, C.c_float, _fp, C.c_int32]),
     "svb_spatial_mean": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp]),
+    "svb_image_sum": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int64, _fp]),
     "svb_topk_columns": (C.c_int, [_vp, _vp, _fp, _vp, _vp, C.c_int32, _fp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, _fp, _vp, _vp]),
     "svb_histogram_update": (C.c_int, [_vp, _vp, _fp, C.c_int64, C.c_int32, _vp, C.c_int32, _fp, _fp, C.c_int32, _fp]),

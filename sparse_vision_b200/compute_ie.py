@@ -77,12 +77,14 @@ class IE:
             for name, x in acts.items():
                 sae = self.saes[name]
                 b, c, h, w = x.shape
-                enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False)
+                enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False,
+                                              out_dtype=torch.bfloat16)
                 dead, sparsity, _ = measure_inactive_units(enc, self.exp_fac[name])        # 2-D call, as at :155
-                err_tok = x.permute(0, 2, 3, 1).reshape(-1, c).float() - dec
-                enc_sum = enc.reshape(b, h * w, -1).sum(0).t().reshape(-1, h, w).contiguous()   # all-reduced later
-                err_sum = err_tok.reshape(b, h * w, c).sum(0).t().reshape(c, h, w).contiguous()
-                x_sum = x.float().sum(0)
+                # per-position sums over the images on libsvb (one read of each tensor); the SAE error x - dec is
+                # never materialised: its sum is the difference of the two sums
+                enc_sum = ops.image_sum(enc, b).t().reshape(-1, h, w).contiguous()         # [F,H,W]; all-reduced later
+                x_sum = ops.image_sum(x if x.dtype in (torch.float32, torch.bfloat16) else x.float(), b)   # [C,H,W]
+                err_sum = x_sum - ops.image_sum(dec, b).t().reshape(c, h, w)
                 if name not in sums:
                     sums[name] = {"enc": enc_sum, "err": err_sum, "x": x_sum, "dead": dead, "sp": sparsity * bs}
                 else:

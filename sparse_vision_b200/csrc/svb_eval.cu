@@ -57,6 +57,28 @@ spatial_mean_nchw_kernel(const T* __restrict__ t, float* __restrict__ out, long 
   if (lane == 0) out[row] = acc / static_cast<float>(hw);
 }
 
+// Sum over images: t [n_images, R, F] (token-major rows of R positions per image, or R = 1 with F = C*HW for an NCHW
+// tensor) -> out [R, F] = sum_b t[b].  One thread per 16 bytes of a row, images in order (deterministic); the running
+// sums of compute_ie.py:146-207 (encoder output, SAE error, layer output per position) are these.
+template <typename T>
+__global__ void __launch_bounds__(256)
+image_sum_kernel(const T* __restrict__ t, float* __restrict__ out, long long n_images, long long per_image) {
+  constexpr int V = Vec16<T>::kN;
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * V;
+  if (i >= per_image) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (long long b = 0; b < n_images; ++b) {
+    float v[8];
+    Vec16<T>::load(t + b * per_image + i, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) out[i + k] = acc[k];
+}
+
 // ------------------------------------------------------------------------------------------------ top-k over rows, per column
 // Candidates of column f: rows 0..n0-1 of source 0 followed by rows 0..n1-1 of source 1 (the running top-k and the
 // batch's, utils.py:1463-1467; n1 = 0 for a plain per-batch top-k).  A 64-bit key (value mapped to an order-preserving
@@ -178,6 +200,25 @@ extern "C" int svb_spatial_mean(svb_handle* h, void* stream, const void* t, int3
       (spatial_mean_tokens_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(t), out, hw, F), svb::count_launch());
   }
   SVB_LAUNCH_CHECK("spatial_mean");
+  return 0;
+}
+
+extern "C" int svb_image_sum(svb_handle* h, void* stream, const void* t, int32_t dtype, int64_t n_images,
+                             int64_t per_image, float* out) {
+  if (!h || !t || !out) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (n_images <= 0 || per_image <= 0) return fail(SVB_ERR_BAD_ARG, "empty tensor");
+  const int V = dtype == SVB_F32 ? 4 : 8;
+  if (dtype != SVB_F32 && dtype != SVB_BF16) return fail(SVB_ERR_BAD_ARG, "bad dtype %d", dtype);
+  if (per_image % V || (reinterpret_cast<uintptr_t>(t) & 15))
+    return fail(SVB_ERR_UNSUPPORTED, "svb_image_sum needs %d | elements per image and a 16-byte aligned pointer", V);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((per_image / V + 255) / 256);
+  if (dtype == SVB_F32)
+    (image_sum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(t), out, n_images, per_image), svb::count_launch());
+  else
+    (image_sum_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(t), out, n_images, per_image), svb::count_launch());
+  SVB_LAUNCH_CHECK("image_sum");
   return 0;
 }
 

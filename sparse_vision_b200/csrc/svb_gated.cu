@@ -397,8 +397,12 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
   segs[ns++] = AdamSeg{p->r_mag, flat + pl.o_gr, adam->m[3], adam->v[3], static_cast<unsigned long long>(F)};
   segs[ns++] = AdamSeg{p->b_dec, flat + pl.o_gbd, adam->m[5], adam->v[5], static_cast<unsigned long long>(C)};
   if (opt->optimizer != SVB_CONSTRAINED_ADAM) segs[ns++] = AdamSeg{p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], FC};
-  SVB_TRY(run_adam_multi(st, segs, ns, k));
-  if (opt->optimizer == SVB_CONSTRAINED_ADAM) launch_cadam(st, p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k);
+  // independent pieces of the tail side by side, as in svb_sae_step_apply
+  const bool cadam = opt->optimizer == SVB_CONSTRAINED_ADAM;
+  SVB_TRY(side_fork(h, st));
+  cudaStream_t s2 = h->side;
+  SVB_TRY(run_adam_multi(cadam ? s2 : st, segs, ns, k));
+  if (cadam) launch_cadam(st, p->w_dec, flat + pl.o_gwd, adam->m[4], adam->v[4], C, F, k);
   SVB_LAUNCH_CHECK("gated adam");
   if (out && (out->stats || out->activity.dead || out->activity.freq)) {
     FinalizeArgs fa{};
@@ -408,9 +412,10 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
     fa.B_g = static_cast<float>(global_images > 0 ? global_images : pl.n_img);
     fa.lambda = lambda_sparse;   // utils.py:2473: loss = rec + lambda * l1 + aux
     fa.stats = out->stats; fa.dead = out->activity.dead; fa.freq = out->activity.freq;
-    (step_finalize_kernel<<<1, 1024, 0, st>>>(fa), svb::count_launch());
+    (step_finalize_kernel<<<1, 1024, 0, s2>>>(fa), svb::count_launch());
     SVB_LAUNCH_CHECK("gated finalize");
   }
+  SVB_TRY(side_join(h, st));
   prof_mark(h, st, 9);
   return 0;
 }

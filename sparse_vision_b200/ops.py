@@ -297,6 +297,22 @@ def spatial_mean(t, n_images=None):
     return out
 
 
+def image_sum(t, n_images):
+    """Sum over the images of a batch, per position (compute_ie.py:146-207): t is [n_images * R, F] token-major or
+    [n_images, C, H, W]; returns float32 [R, F] resp. [C, H, W]."""
+    if not t.is_cuda:
+        raise ValueError("CUDA tensor required")
+    t = t.contiguous()
+    per = t.numel() // int(n_images)
+    if per * int(n_images) != t.numel():
+        raise ValueError("element count is not a multiple of n_images")
+    shape = tuple(t.shape[1:]) if t.dim() == 4 else (t.shape[0] // int(n_images), t.shape[1])
+    out = torch.empty(shape, device=t.device, dtype=torch.float32)
+    L.check(L.load().svb_image_sum(L.handle(t.device), L.stream_ptr(t.device), L.ptr(t), L.dtype_code(t), int(n_images),
+                                   per, L.ptr(out)), "svb_image_sum")
+    return out
+
+
 def _i64(t):
     if t is None:
         return None

@@ -116,3 +116,42 @@ def test_checkpoint_round_trip_resumes_bit_exact(tmp_path):
         pipe_c.train_batch(x)
     for a, c in zip(sae_a.param_list(), sae_c.param_list()):
         assert torch.equal(a, c), "resumed training diverged from the uninterrupted run"
+
+
+def test_original_model_comparison_one_pass_equals_unhooked_copy():
+    """model_pipeline.py:694-708 (KL divergence / same classification / loss difference against the unhooked original):
+    carrying the original activation through the SAME forward pass (the hook hands [reconstruction; original] on, batch
+    2B) must give what a second forward of an unhooked copy gives, and must not change the SAE training."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import copy
+    import sparse_vision_b200.models.sae_mlp as M
+    from sparse_vision_b200.model_pipeline import ModelPipeline
+
+    C, k, B = 64, 4, 8
+
+    def make(one_pass):
+        torch.manual_seed(0)
+        base = nn.Sequential(collections.OrderedDict(
+            conv=nn.Conv2d(3, C, 3, padding=1), act=nn.ReLU(), c2=nn.Conv2d(C, 32, 3, padding=1), r2=nn.ReLU(),
+            gap=nn.AdaptiveAvgPool2d(1), fl=nn.Flatten(), fc=nn.Linear(32, 10))).eval().cuda()
+        sae = M.SaeMLP(C, k).cuda()
+        pipe = ModelPipeline(base, sae, "sae_mlp", "act", "constrained_adam", 1e-3, 5.0, k,
+                             model_copy=None if one_pass else copy.deepcopy(base), compare_in_one_pass=one_pass)
+        pipe.register_hooks(train_sae=True)
+        return pipe, sae
+
+    xs = [torch.randn(B, 3, 16, 16, generator=torch.Generator().manual_seed(7 + i)).cuda() for i in range(3)]
+    ys = [torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(70 + i)).cuda() for i in range(3)]
+    (pa, sa), (pb, sb) = make(False), make(True)
+    for x, y in zip(xs, ys):
+        oa, _ = pa.train_batch(x, targets=y)
+        ob, _ = pb.train_batch(x, targets=y)
+        assert oa.shape == ob.shape == (B, 10)
+        assert torch.allclose(oa, ob, rtol=1e-5, atol=1e-6)
+        assert pa.batch_model_stats.shape == (3,)
+        assert torch.allclose(pa.batch_model_stats, pb.batch_model_stats, rtol=1e-4, atol=1e-6), \
+            (pa.batch_model_stats, pb.batch_model_stats)
+        assert float(pa.batch_model_stats[0]) > 0          # the SAE does change the model's distribution
+    for a, b in zip(sa.param_list(), sb.param_list()):
+        assert torch.equal(a, b)

@@ -303,7 +303,10 @@ def fake_node_ie_layer(x, grad, params, enc_avg, err_avg, x_avg, scale=None):
     T = x.shape[0] * x.shape[2] * x.shape[3]
     sc = (1.0 / T) if scale is None else scale
     return f * T * sc, torch.as_tensor(e * T * sc).reshape(()), n * T * sc
-ops.sae_forward, ops.node_ie_layer = fake_sae_forward, fake_node_ie_layer
+def fake_image_sum(t, n_images):
+    t = t.float()
+    return t.sum(0) if t.dim() == 4 else t.reshape(n_images, -1, t.shape[1]).sum(0)
+ops.sae_forward, ops.node_ie_layer, ops.image_sum = fake_sae_forward, fake_node_ie_layer, fake_image_sum
 cie.measure_inactive_units = O.measure_inactive_units
 
 def build():
