@@ -702,7 +702,8 @@ def run_svb(args):
         sae = _make_params().to(dev)
         pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", LR, LAMBDA, EXPANSION,
                              data_parallel=world > 1, global_batch_images=g_images if world > 1 else None,
-                             model_copy=base_copy, compare_in_one_pass=not args.two_pass)
+                             model_copy=base_copy, compare_in_one_pass=not args.two_pass,
+                             cuda_graph=world == 1 and not args.no_graph)
         pipe.register_hooks(train_sae=True)
         gi = torch.Generator().manual_seed(77 + rank)
         host = [torch.randn(B, 3, 224, 224, generator=gi).to(torch.bfloat16).pin_memory() for _ in range(2)]
@@ -716,7 +717,7 @@ def run_svb(args):
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         main = torch.cuda.current_stream()
-        for i in range(3):                                    # warm-up: cuDNN heuristics, arena growth
+        for i in range(5):                                    # warm-up: cuDNN heuristics, arena growth, graph capture
             stage[i % 2].copy_(host[i % 2], non_blocking=True)
             pipe.train_batch(stage[i % 2], targets=tgt)
         barrier()
@@ -755,6 +756,7 @@ def run_svb(args):
                "last_batch": {"loss": sh[0], "rec": sh[1], "kld": sh[L.STATS_LEN], "same_classification": sh[L.STATS_LEN + 1],
                               "loss_diff": sh[L.STATS_LEN + 2]},
                "numa_node_rank0": numa_node,
+               "cuda_graph": pipe._graph is not None,
                "producer": {"channels_last": bool(args.channels_last), "batchnorm_folded": not args.no_fold_bn,
                             "original_model": "second forward of an unhooked copy" if args.two_pass else
                             "same pass: the hook hands [reconstruction; original activation] (2B) to the rest of the net"},
@@ -886,6 +888,8 @@ def main():
                                                "gpu_eager,cpu,dp_parity,other_format")
     ap.add_argument("--acts-format", default="channels_last", choices=["nchw", "channels_last"],
                     help="memory format of the resident activations of the `value` leg")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="e2e: launch every batch eagerly instead of replaying one captured CUDA graph (N = 1)")
     ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")
     ap.add_argument("--two-pass", action="store_true",
                     help="e2e: compare with a second forward of an unhooked copy (the reference's structure) instead of "

@@ -103,6 +103,10 @@ typedef struct svb_opt_config {
   int32_t step;      /* Adam step count AFTER this update (1 on the first step) */
   double lr, beta1, beta2, eps; /* doubles, like the Python floats torch.optim.Adam holds: 1 - beta2 = 1e-4 must not
                                  * pick up the 1.7e-4 relative error of a float32 0.9999 */
+  int32_t* step_dev; /* NULL, or a DEVICE int32 holding the number of steps taken so far: the call increments it on the
+                      * device and derives the bias corrections from it (`step` is then ignored).  This is what lets a
+                      * whole training batch be captured in a CUDA graph and replayed: nothing step-dependent is baked
+                      * into the launch parameters. */
 } svb_opt_config;
 
 /* Scalars of one step, device float[SVB_STATS_LEN] (read them with one D2H copy per logging interval instead of

@@ -46,7 +46,7 @@ class AdamState(C.Structure):
 
 class OptConfig(C.Structure):
     _fields_ = [("optimizer", C.c_int32), ("step", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
-                ("beta2", C.c_double), ("eps", C.c_double)]
+                ("beta2", C.c_double), ("eps", C.c_double), ("step_dev", _vp)]
 
 
 class ActivityOut(C.Structure):

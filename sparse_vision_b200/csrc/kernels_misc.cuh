@@ -1092,7 +1092,17 @@ struct AdamCoef {
   float lr_over_bc1;    // lr / (1 - beta1^t)
   float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^t)
   float beta2, omb1, omb2, eps;   // beta2, 1 - beta1, 1 - beta2 (each rounded from the double), eps
+  const float* dev;               // null, or device {lr_over_bc1, inv_sqrt_bc2} written by adam_step_coef_kernel
+  __device__ __forceinline__ void resolve() {
+    if (dev) { lr_over_bc1 = dev[0]; inv_sqrt_bc2 = dev[1]; }
+  }
 };
+// Device-resident step counter (svb_opt_config::step_dev): t = ++(*step); out = {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)}.
+static __global__ void adam_step_coef_kernel(int32_t* step, double lr, double b1, double b2, float* out) {
+  const int t = ++(*step);
+  out[0] = static_cast<float>(lr / (1.0 - pow(b1, static_cast<double>(t))));
+  out[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(b2, static_cast<double>(t))));
+}
 __device__ __forceinline__ float adam_elem(float w, float g, float& m, float& v, const AdamCoef& k) {
   // torch.optim.Adam single-tensor update: m.lerp_(g, 1-b1); v = b2*v + (1-b2) g^2;
   // w -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
@@ -1103,6 +1113,7 @@ __device__ __forceinline__ float adam_elem(float w, float g, float& m, float& v,
 }
 static __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, AdamCoef k, bf16* __restrict__ w_bf16) {
+  k.resolve();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float mi = m[i], vi = v[i];
@@ -1118,7 +1129,8 @@ struct AdamMultiArgs {
   int blk0[7];
   int nseg;
 };
-static __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamMultiArgs a, const AdamCoef k) {
+static __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamMultiArgs a, AdamCoef k) {
+  k.resolve();
   int sgi = 0;
 #pragma unroll
   for (int i = 1; i < 6; ++i)
@@ -1139,6 +1151,7 @@ constexpr int kCadamCols = 16, kCadamRows = 64;
 static __global__ void __launch_bounds__(kCadamCols * kCadamRows)
 constrained_adam_decoder_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int C, int F, AdamCoef k) {
+  k.resolve();
   __shared__ float s[kCadamRows][kCadamCols + 1];
   __shared__ float col_a[kCadamCols], col_b[kCadamCols];
   const int cl = threadIdx.x % kCadamCols, gl = threadIdx.x / kCadamCols;

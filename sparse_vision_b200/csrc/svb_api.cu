@@ -20,6 +20,11 @@ extern "C" int svb_create(svb_handle** out) {
   svb_handle* h = new svb_handle();
   h->device = dev;
   h->sms = prop.multiProcessorCount;
+  if (cudaMalloc(&h->coef_dev, 2 * sizeof(float)) != cudaSuccess) {   // here, not lazily: never inside a stream capture
+    cudaGetLastError();
+    delete h;
+    return fail(SVB_ERR_NOMEM, "cudaMalloc failed in svb_create");
+  }
   *out = h;
   return 0;
 }
@@ -29,6 +34,7 @@ extern "C" int svb_destroy(svb_handle* h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->ev_early) cudaEventDestroy(h->ev_early);
   if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+  if (h->coef_dev) cudaFree(h->coef_dev);
   svb_comm_destroy(h);
   delete h;
   return 0;
@@ -106,9 +112,9 @@ extern "C" int svb_adam_step(svb_handle* h, void* stream, int32_t n_tensors, flo
                              const int64_t* cols, int32_t decoder_index, const svb_opt_config* opt) {
   if (!h || !params || !grads || !m || !v || !rows || !cols || !opt) return fail(SVB_ERR_BAD_ARG, "null argument");
   SVB_ON_DEVICE(h);
-  if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const AdamCoef k = adam_coef(opt);
+  AdamCoef k;
+  SVB_TRY(adam_coef_for(h, st, opt, &k));
   for (int i = 0; i < n_tensors; ++i) {
     if (!params[i] || !m[i] || !v[i]) return fail(SVB_ERR_BAD_ARG, "null tensor %d", i);
     if (!grads[i]) continue;  // parameter without gradient: torch.optim.Adam skips it

@@ -102,6 +102,7 @@ struct svb_handle {
   // internal side stream: small kernels that only feed the end of the step run beside the GEMMs (fork / join below)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* coef_dev = nullptr;        // {lr / bc1, 1 / sqrt(bc2)} of the running step when the step count lives on the device
 };
 
 namespace svb {
@@ -420,6 +421,7 @@ inline int bstat_groups(int sms, int tiles_n, int tiles_m) {
 
 inline AdamCoef adam_coef(const svb_opt_config* o) {
   AdamCoef k;
+  k.dev = nullptr;
   const double bc1 = 1.0 - pow(static_cast<double>(o->beta1), o->step);
   const double bc2 = 1.0 - pow(static_cast<double>(o->beta2), o->step);
   k.lr_over_bc1 = static_cast<float>(static_cast<double>(o->lr) / bc1);
@@ -431,4 +433,24 @@ inline AdamCoef adam_coef(const svb_opt_config* o) {
   return k;
 }
 
+}  // namespace svb
+
+namespace svb {
+// Adam coefficients of a call: from the host step count, or (svb_opt_config::step_dev) from a device counter that a
+// one-thread kernel on `st` increments first -- everything enqueued after it on `st` (and on streams forked from it)
+// sees the new values.
+inline int adam_coef_for(svb_handle* h, cudaStream_t st, const svb_opt_config* o, AdamCoef* k) {
+  if (!o->step_dev) {
+    if (o->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
+    *k = adam_coef(o);
+    return 0;
+  }
+  svb_opt_config tmp = *o;
+  tmp.step = 1;
+  *k = adam_coef(&tmp);
+  (adam_step_coef_kernel<<<1, 1, 0, st>>>(o->step_dev, o->lr, o->beta1, o->beta2, h->coef_dev), svb::count_launch());
+  SVB_LAUNCH_CHECK("adam_step_coef");
+  k->dev = h->coef_dev;
+  return 0;
+}
 }  // namespace svb

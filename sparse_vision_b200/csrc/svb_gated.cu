@@ -380,7 +380,6 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
   SVB_TRY(check_params(x, p));
   for (int i = 0; i < 6; ++i)
     if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);
-  if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GatedPlan pl;
   SVB_TRY(plan(h, pl, x, p->F, true));
@@ -388,7 +387,8 @@ extern "C" int svb_gated_step_apply(svb_handle* h, void* stream, const svb_acts*
   const int C = pl.C, F = pl.F;
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
-  const AdamCoef k = adam_coef(opt);
+  AdamCoef k;
+  SVB_TRY(adam_coef_for(h, st, opt, &k));
   AdamSeg segs[6];
   int ns = 0;
   segs[ns++] = AdamSeg{p->w_gate, flat + pl.o_gwg, adam->m[0], adam->v[0], FC};

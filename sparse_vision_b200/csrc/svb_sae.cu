@@ -346,7 +346,6 @@ extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x
   SVB_TRY(check_params(x, p));
   for (int i = 0; i < 4; ++i)
     if (!adam->m[i] || !adam->v[i]) return fail(SVB_ERR_BAD_ARG, "null Adam state tensor %d", i);
-  if (opt->step < 1) return fail(SVB_ERR_BAD_ARG, "Adam step must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SaePlan pl;
   SVB_TRY(plan(h, pl, x, p->F, true));
@@ -354,7 +353,8 @@ extern "C" int svb_sae_step_apply(svb_handle* h, void* stream, const svb_acts* x
   const int C = pl.C, F = pl.F;
   const size_t FC = static_cast<size_t>(F) * C;
   float* flat = pl.flat;
-  const AdamCoef k = adam_coef(opt);
+  AdamCoef k;
+  SVB_TRY(adam_coef_for(h, st, opt, &k));
   AdamSeg segs[4];
   int ns = 0;
   segs[ns++] = AdamSeg{p->w_enc, flat + pl.o_gwe, adam->m[0], adam->v[0], FC};

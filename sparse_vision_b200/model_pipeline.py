@@ -38,7 +38,7 @@ class ModelPipeline:
     def __init__(self, model, sae_model, sae_model_name, sae_layer, sae_optimizer_name="constrained_adam",
                  sae_learning_rate=1e-3, sae_lambda_sparse=5.0, sae_expansion_factor=8, dead_neurons_steps=None,
                  device=None, reinit_index_dir=None, data_parallel=False, global_batch_images=None, model_copy=None,
-                 model_criterion=None, compare_in_one_pass=False):
+                 model_criterion=None, compare_in_one_pass=False, cuda_graph=False):
         self.model = model
         # the unhooked original the modified model is compared with per batch (model_pipeline.py:694-708)
         self.model_copy = model_copy
@@ -49,6 +49,18 @@ class ModelPipeline:
         # layers in front of the SAE layer run once instead of twice and the logits of the original model fall out of
         # the same pass (a frozen eval-mode network treats samples independently, so the results are the same)
         self.compare_in_one_pass = compare_in_one_pass
+        # cuda_graph: after three eager batches the whole training batch -- frozen base-model forward, the fused SAE
+        # step inside the hook, the comparison with the original model -- is captured ONCE in a CUDA graph and replayed
+        # for every later batch of the same shape (one launch instead of several hundred).  The Adam step count then
+        # lives on the device (svb_opt_config::step_dev); the per-batch results are static tensors that the next
+        # replay overwrites.  Single process only (the peer-memory exchange keeps host-side epochs).
+        self.cuda_graph = bool(cuda_graph) and not data_parallel
+        self._graph = None
+        self._graph_eager_left = 3
+        self._graph_static = None
+        self._step_dev = None
+        self._capturing = False
+        self._graph_ws = 0
         self.sae_model = sae_model
         self.sae_model_name = sae_model_name
         if sae_model_name not in ("sae_mlp", "gated_sae"):
@@ -110,7 +122,8 @@ class ModelPipeline:
             st = self.sae_optimizer.state[p]
             if st["step"].is_cuda:         # load_state_dict(map_location=cuda) leaves the counters on the GPU: a .item()
                 st["step"] = st["step"].cpu()   # there would synchronise the host with the device on every step
-            st["step"] += 1
+            if not self._capturing:        # a capture records the step, it does not take one
+                st["step"] += 1
             steps.add(int(st["step"].item()))
         if len(steps) != 1:
             raise ValueError(f"the fused SAE step needs one Adam step count for all parameters, found {sorted(steps)}")
@@ -125,6 +138,8 @@ class ModelPipeline:
         if train_sae:
             params, ms, vs, step = self._adam_tensors()
             kw = dict(optimizer=self.sae_optimizer_name, betas=group["betas"], eps=group["eps"])
+            if self._capturing:
+                kw["step_dev"] = self._step_dev
             if self.dp is not None:
                 n_img = output.shape[0]
                 hw = output.shape[2] * output.shape[3] if output.dim() == 4 else 1
@@ -252,11 +267,7 @@ class ModelPipeline:
             self.batch_model_stats = torch.stack([kld, same, diff])
         return self.batch_model_stats
 
-    def train_batch(self, inputs, epoch=0, targets=None):
-        """model_pipeline.py:603-793 for one batch: frozen base-model forward (the hook trains the SAE), the comparison
-        with the unhooked copy when one was given, then train_batch_idx bookkeeping, dead-mask accumulation and the
-        re-initialisation schedule."""
-        self.epoch_batch_idx += 1
+    def _forward_and_compare(self, inputs, targets):
         with torch.no_grad():
             outputs = self.model(inputs)
         if self.compare_in_one_pass and self.hooks and self.train_sae:
@@ -264,10 +275,62 @@ class ModelPipeline:
             self.compare_with_original(inputs, outputs, targets, out_orig=out_orig)
         elif self.model_copy is not None:
             self.compare_with_original(inputs, outputs, targets)
+        return outputs
+
+    def _graphed_forward(self, inputs, targets):
+        """Capture on the fourth batch, replay afterwards (see `cuda_graph` in __init__)."""
+        from . import _lib as L
+        ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
+        if self._graph is not None and ws != self._graph_ws:
+            # another call on this device grew (= re-allocated) the library's workspace: the captured launches point into
+            # the old one.  Drop the graph and capture again.
+            self._graph, self._graph_eager_left = None, 1
+        if self._graph is None:
+            if self._graph_eager_left > 0:                 # cuDNN heuristics, workspace growth, lazy optimizer state
+                self._graph_eager_left -= 1
+                return self._forward_and_compare(inputs, targets)
+            params = self.sae_model.param_list()
+            host_step = int(self.sae_optimizer.state[params[0]]["step"].item())
+            self._step_dev = torch.tensor([host_step], dtype=torch.int32, device=inputs.device)
+            static_in = inputs.clone()
+            static_tgt = None if targets is None else targets.clone()
+            torch.cuda.synchronize(inputs.device)
+            self._graph = torch.cuda.CUDAGraph()
+            self._capturing = True
+            try:
+                with torch.cuda.graph(self._graph):
+                    static_out = self._forward_and_compare(static_in, static_tgt)
+            finally:
+                self._capturing = False
+            self._graph_static = (static_in, static_tgt, static_out, self._last, self.batch_model_stats,
+                                  dict(self.batch_dead_units), dict(self.batch_neuron_frequency))
+            self._graph_ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
+        static_in, static_tgt, static_out, last, model_stats, dead, freq = self._graph_static
+        if tuple(inputs.shape) != tuple(static_in.shape):
+            raise ValueError(f"cuda_graph=True replays batches of shape {tuple(static_in.shape)}; got {tuple(inputs.shape)}")
+        static_in.copy_(inputs)
+        if static_tgt is not None:
+            static_tgt.copy_(targets)
+        self._graph.replay()
+        for p in self.sae_model.param_list():              # the host-side counters follow (checkpoints, re-initialisation)
+            self.sae_optimizer.state[p]["step"] += 1
+        self._last, self.batch_model_stats = last, model_stats
+        self.batch_dead_units, self.batch_neuron_frequency = dict(dead), dict(freq)
+        return static_out
+
+    def train_batch(self, inputs, epoch=0, targets=None):
+        """model_pipeline.py:603-793 for one batch: frozen base-model forward (the hook trains the SAE), the comparison
+        with the unhooked copy when one was given, then train_batch_idx bookkeeping, dead-mask accumulation and the
+        re-initialisation schedule."""
+        self.epoch_batch_idx += 1
+        graphed = self.cuda_graph and self.hooks and self.train_sae
+        outputs = self._graphed_forward(inputs, targets) if graphed else self._forward_and_compare(inputs, targets)
         self.train_batch_idx += 1
         for key, dead in self.batch_dead_units.items():                      # :744-748 (AND == product of bools)
-            self.train_dead_neurons[key] = dead if key not in self.train_dead_neurons \
-                else self.train_dead_neurons[key] & dead
+            if key not in self.train_dead_neurons:                          # (a replayed graph overwrites `dead`: copy)
+                self.train_dead_neurons[key] = dead.clone() if graphed else dead
+            else:
+                self.train_dead_neurons[key] = self.train_dead_neurons[key] & dead
         action = None
         if self.dead_neurons_steps:
             action = dead_neuron_action(self.train_batch_idx, self.dead_neurons_steps)

@@ -39,9 +39,11 @@ def _adam_state(ms, vs):
     return st
 
 
-def _opt(optimizer, step, lr, betas, eps):
+def _opt(optimizer, step, lr, betas, eps, step_dev=None):
     code = {"adam": L.SVB_ADAM, "constrained_adam": L.SVB_CONSTRAINED_ADAM}[optimizer]
-    return L.OptConfig(code, int(step), float(lr), float(betas[0]), float(betas[1]), float(eps))
+    if step_dev is not None and (step_dev.dtype != torch.int32 or not step_dev.is_cuda or step_dev.numel() != 1):
+        raise ValueError("step_dev must be a one-element int32 CUDA tensor")
+    return L.OptConfig(code, int(step), float(lr), float(betas[0]), float(betas[1]), float(eps), L.ptr(step_dev))
 
 
 def _tokens(x):
@@ -122,14 +124,16 @@ def _single_pixel_fixup(x, res):
 
 
 def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
-                   betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None):
+                   betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None):
     """One pass of ModelPipeline.hook's train branch (model_pipeline.py:380-420) for SaeMLP, fully on device.
-    params = (encoder.weight, encoder.bias, decoder.weight, decoder.bias); updated in place with the Adam moments."""
+    params = (encoder.weight, encoder.bias, decoder.weight, decoder.bias); updated in place with the Adam moments.
+    step_dev: optional int32 CUDA scalar holding the steps taken so far; the call increments it on the device and
+    `step` is ignored (CUDA-graph capture: nothing step-dependent in the launch parameters)."""
     a, x = L.acts_of(x)
     p = _sae_params(*params)
     out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
     st = _adam_state(adam_m, adam_v)
-    opt = _opt(optimizer, step, lr, betas, eps)
+    opt = _opt(optimizer, step, lr, betas, eps, step_dev)
     L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
                                         C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_sae_train_step")
@@ -137,13 +141,13 @@ def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, o
 
 
 def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
-                     betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None):
+                     betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None):
     """Same for GatedSae; params = (W_gate, b_gate, b_mag, r_mag, decoder.weight, decoder.bias)."""
     a, x = L.acts_of(x)
     p = _gated_params(*params)
     out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
     st = _adam_state(adam_m, adam_v)
-    opt = _opt(optimizer, step, lr, betas, eps)
+    opt = _opt(optimizer, step, lr, betas, eps, step_dev)
     L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
                                           C.byref(opt), float(lam), int(expansion_factor), C.byref(out)),
             "svb_gated_train_step")

@@ -155,3 +155,54 @@ def test_original_model_comparison_one_pass_equals_unhooked_copy():
         assert float(pa.batch_model_stats[0]) > 0          # the SAE does change the model's distribution
     for a, b in zip(sa.param_list(), sb.param_list()):
         assert torch.equal(a, b)
+
+
+def test_cuda_graphed_training_batches_equal_eager(tmp_path, monkeypatch):
+    """the whole training batch (frozen forward, fused SAE step in the hook, comparison with the
+    original model) captured in a CUDA graph and replayed must reproduce the eager run bit for bit -- including the Adam
+    bias corrections (step count on the device) and a dead-unit re-initialisation between replays."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import sparse_vision_b200.models.sae_mlp as M
+    from sparse_vision_b200.model_pipeline import ModelPipeline
+
+    C, k, B = 64, 4, 8
+
+    def make(graph):
+        torch.manual_seed(0)
+        base = nn.Sequential(collections.OrderedDict(
+            conv=nn.Conv2d(3, C, 3, padding=1), act=nn.ReLU(), c2=nn.Conv2d(C, 32, 3, padding=1), r2=nn.ReLU(),
+            gap=nn.AdaptiveAvgPool2d(1), fl=nn.Flatten(), fc=nn.Linear(32, 10))).eval().cuda()
+        sae = M.SaeMLP(C, k)
+        with torch.no_grad():
+            sae.encoder.bias[:9] = -50.0
+        sae = sae.cuda()
+        pipe = ModelPipeline(base, sae, "sae_mlp", "act", "constrained_adam", 1e-3, 5.0, k, dead_neurons_steps=3,
+                             compare_in_one_pass=True, cuda_graph=graph)
+        pipe.register_hooks(train_sae=True)
+        return pipe, sae
+
+    xs = [torch.randn(B, 3, 16, 16, generator=torch.Generator().manual_seed(7 + i)).cuda() for i in range(10)]
+    ys = [torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(70 + i)).cuda() for i in range(10)]
+    runs = []
+    for graph in (False, True):
+        pipe, sae = make(graph)
+        torch.manual_seed(123)                       # the re-initialisation draws
+        log = []
+        for x, y in zip(xs, ys):
+            out, action = pipe.train_batch(x, targets=y)
+            log.append((pipe.batch_scalars(), pipe.batch_model_stats.clone(), out.clone(), action,
+                        pipe._last.dead.clone()))
+        runs.append((pipe, sae, log))
+    (pe, se, le), (pg, sg, lg) = runs
+    assert pg._graph is not None and pe._graph is None
+    assert any(a == "reinit" for _, _, _, a, _ in lg)
+    for i, ((s0, m0, o0, a0, d0), (s1, m1, o1, a1, d1)) in enumerate(zip(le, lg)):
+        assert a0 == a1 and s0 == s1, (i, s0, s1)
+        assert torch.equal(m0, m1) and torch.equal(o0, o1) and torch.equal(d0, d1), i
+    for a, b in zip(se.param_list(), sg.param_list()):
+        assert torch.equal(a, b)
+    for p0, p1 in zip(se.param_list(), sg.param_list()):
+        s0, s1 = pe.sae_optimizer.state[p0], pg.sae_optimizer.state[p1]
+        assert int(s0["step"]) == int(s1["step"]) == 10 and torch.equal(s0["exp_avg"], s1["exp_avg"])
+    assert int(pg._step_dev.item()) == 10
