@@ -6,7 +6,6 @@
 #include <cstdio>
 #include <cstring>
 #include "gemm_sm100.cuh"
-#include "gemm2_sm100.cuh"
 
 namespace svb {
 
@@ -228,50 +227,6 @@ int launch_gemm(cudaStream_t stream, const void* A, int64_t lda, const void* B, 
     grid = groups * p.tiles_n;
   }
   (kern<<<grid, 64 + Epi::kWarps * 32, smem, stream>>>(tmA, tmB, p, ep), svb::count_launch());
-  return cudaGetLastError() == cudaSuccess ? 0 : -4;
-}
-
-// Two-CTA B-stationary launch (gemm2_sm100.cuh): K <= 256, A K-major (row-major pitch lda, or slab-major), B K-major
-// [N, K] or MN-major [K, N] with pitch ldb.  *groups_out receives the number of pair groups per N tile (the epilogue's
-// per-CTA partials have 2 * groups slots).  Returns 0 or a negative svb error code.
-inline int gemm2_groups(int M, int N, int max_ctas = 0) {
-  const int sms = max_ctas > 0 ? max_ctas : device_sm_count();
-  const int tiles_n = (N + 255) / 256, pair_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
-  if (tiles_n > sms / 2) return 0;
-  int groups = (sms / 2) / tiles_n;
-  if (groups > pair_tiles) groups = pair_tiles;
-  return groups;
-}
-template <bool B_MN, class Epi>
-int launch_gemm2_bstat(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                       const typename Epi::Params& ep, bool a_slab = false, int max_ctas = 0) {
-  using Cfg = Gemm2Cfg<Epi::kSmemBytes>;
-  if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || K > Cfg::kResidentKBlocks * kBlockK) return -2;
-  CUtensorMap tmA, tmB;
-  int rc = a_slab ? make_tmap_bf16_slab(&tmA, A, M, K, kBlockM) : make_tmap_bf16_2d(&tmA, A, M, K, lda, kBlockM);
-  if (rc) return rc;
-  rc = !B_MN ? make_tmap_bf16_2d(&tmB, B, N, K, ldb, 128) : make_tmap_bf16_2d(&tmB, B, K, N, ldb, kBlockK);
-  if (rc) return rc;
-  GemmProblem p;
-  p.M = M; p.N = N; p.K = K;
-  p.k_splits = 1; p.k_per_split = ((K + kBlockK - 1) / kBlockK) * kBlockK;
-  p.tiles_m = (M + kBlockM - 1) / kBlockM;
-  p.tiles_n = (N + 255) / 256;
-  p.a_slab = a_slab ? 1 : 0;
-#ifdef SVB_GEMM_TRACE
-  p.trace = gemm_trace_ptr();
-#endif
-  const int groups = gemm2_groups(M, N, max_ctas);
-  if (groups < 1) return -5;
-  auto kern = gemm2_bstat_kernel<B_MN, Epi>;
-  static bool configured[kMaxDevices] = {};
-  const int dev = current_device();
-  if (dev < 0 || dev >= kMaxDevices) return -4;
-  if (!configured[dev]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -4;
-    configured[dev] = true;
-  }
-  (kern<<<2 * p.tiles_n * groups, 64 + Epi::kWarps * 32, Cfg::kSmemBytes, stream>>>(tmA, tmB, p, ep), svb::count_launch());
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

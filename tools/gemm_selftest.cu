@@ -10,6 +10,7 @@
 #define SVB_GEMM_TRACE 1
 #include "../sparse_vision_b200/csrc/gemm_host.cuh"
 #include "../sparse_vision_b200/csrc/epilogues.cuh"
+#include "gemm2_sm100.cuh"
 
 using namespace svb;
 
