@@ -364,7 +364,24 @@ def _read_phases(lib, h):
     phase_ms = (C.c_float * 16)()
     n_ph, n_st = C.c_int32(), C.c_int32()
     L.check(lib.svb_profile_read(h, 16, phase_ms, C.byref(n_ph), C.byref(n_st)), "svb_profile_read")
-    return {lib.svb_profile_phase_name(i).decode(): float(phase_ms[i]) for i in range(n_ph.value)}
+    ph = {lib.svb_profile_phase_name(i).decode(): float(phase_ms[i]) for i in range(n_ph.value)}
+    if lib.svb_last_step_flags(h) & 1 and "dE_gemm" in ph:
+        # SVB_STEP_FUSED_BWD: one kernel did the dE GEMM, the ReLU mask and the dW_enc GEMM (two GEMMs of work)
+        out = {}
+        for k, v in ph.items():
+            if k == "dE_gemm":
+                out[FUSED_BWD_PHASE] = v + ph.get("dWenc_gemm", 0.0)
+            elif k != "dWenc_gemm":
+                out[k] = v
+        return out
+    return ph
+
+
+FUSED_BWD_PHASE = "dE+dWenc_fused_gemm"
+
+
+def _gemms_in_phase(name):
+    return 2 if name == FUSED_BWD_PHASE else 1
 
 
 def ie_section(dev, peaks, n_images=64, iters=20, world=1):
@@ -787,7 +804,7 @@ def run_svb(args):
     if rank == 0:
         gemm_phases = {k: v for k, v in phases.items() if k.endswith("_gemm")}
         dom = max(gemm_phases, key=gemm_phases.get) if gemm_phases else None
-        flops_per_gemm = 2.0 * T * C_ACT * F
+        flops_per_gemm = 2.0 * T * C_ACT * F * (_gemms_in_phase(dom) if dom else 1)   # algorithmic FLOP of the dominant launch
         step_flops = 10.0 * C_ACT * F * T
         achieved = flops_per_gemm / (gemm_phases[dom] * 1e-3) / 1e12 if dom else None
         traffic = _traffic()

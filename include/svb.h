@@ -54,6 +54,13 @@ int64_t svb_workspace_bytes(const svb_handle* h);
 /* Number of kernels the library has launched in this process (bench.py reports the per-step delta). */
 int64_t svb_launch_count(void);
 
+/* Which fused kernels the last svb_sae_step_grads call of this handle used (bit flags), so that per-phase timings
+ * can be attributed: SVB_STEP_FUSED_BWD = the dE GEMM, the ReLU mask and the dW_enc GEMM ran as ONE kernel (C <= 256,
+ * C % 64 == 0; model_pipeline.py:385 backward of models/sae_mlp.py:49-52) -- its time is reported in the "dE_gemm"
+ * phase and the "dWenc_gemm" phase is empty. */
+#define SVB_STEP_FUSED_BWD 1
+int32_t svb_last_step_flags(const svb_handle* h);
+
 /* Per-phase timing of the SaeMLP training step with CUDA events recorded on the caller's stream between the phases
  * (pack+prep, enc GEMM, dec GEMM, channel stats, dE GEMM, dW_dec GEMM, dW_enc GEMM, gradient assembly, Adam).
  * svb_profile_read synchronises the device and returns the mean milliseconds per phase over the recorded steps

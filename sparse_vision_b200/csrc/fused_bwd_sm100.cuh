@@ -15,6 +15,7 @@
 // TMEM: acc1 double-buffered (2 x 128 columns) + acc2 (256 columns).  Shared memory: W tile 64 KB resident, P 32 KB,
 // DIFF 4 x 16 KB k-blocks, X 2 x 32 KB k-blocks (each with its own full / empty barrier, refilled one block ahead).
 #pragma once
+#include <cstdlib>
 #include "gemm_host.cuh"
 #include "epilogues.cuh"
 
@@ -240,6 +241,15 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// SVB_FUSED_BWD=0 in the environment keeps the two un-fused GEMMs (A/B measurements, bring-up).
+inline bool fused_bwd_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SVB_FUSED_BWD");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 // Slots the launcher will use (sizes the split-K workspaces): S = min(sms / tiles_f, token blocks).

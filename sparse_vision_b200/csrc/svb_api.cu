@@ -41,6 +41,7 @@ extern "C" int svb_destroy(svb_handle* h) {
 }
 
 extern "C" int64_t svb_launch_count(void) { return static_cast<int64_t>(launch_counter()); }
+extern "C" int32_t svb_last_step_flags(const svb_handle* h) { return h ? h->step_flags : 0; }
 
 // ---------------------------------------------------------------------------------------------------- profiling
 static const char* kPhaseNames[] = {"pack+prep", "enc_gemm", "dec_gemm", "channel_stats", "dE_gemm",

@@ -94,6 +94,7 @@ struct svb_handle {
   // description of the flat reduction buffer of the last *_step_grads call
   float* gradbuf = nullptr;
   int64_t sum_elems = 0, max_elems = 0;
+  int32_t step_flags = 0;           // SVB_STEP_* bits of the last *_step_grads call (svb_last_step_flags)
   int64_t early_elems = 0;          // leading elements that are final when `comm` is released (0: no early bucket)
   // data-parallel overlap: an optional caller stream that is made to wait for the early bucket (svb_set_comm_stream)
   cudaStream_t comm = nullptr;

@@ -235,6 +235,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const int T = static_cast<int>(pl.T), C = pl.C, F = pl.F;
   const double Tg = global_tokens > 0 ? static_cast<double>(global_tokens) : static_cast<double>(pl.T);
   const bf16* X = pl.zero_copy_x ? static_cast<const bf16*>(x->x) : pl.X;
+  h->step_flags = 0;
   prof_begin_step(h);   // phases as in svb_sae.cu; "dec_gemm" covers the decoder and the via_gate GEMM
   prof_mark(h, st, 0);
   // slab-major X / DIFF + fused NCHW decoder epilogue under the same conditions as svb_sae_step_grads

@@ -15,6 +15,7 @@
 //   adam      (Constrained)Adam on all four tensors; stats + activity outputs finalised
 // The backward runs in units of T*C/2 (dPre' = dPre * T*C/2) so bf16 intermediates stay O(1).
 #include "svb_common.cuh"
+#include "fused_bwd_sm100.cuh"
 
 using namespace svb;
 
@@ -31,6 +32,7 @@ struct SaePlan {
   bool xs, es, ds;          // slab-major workspaces: X / D (xs), E / dPre' (es) and DIFF (ds), see gemm_host.cuh
   bool tok_fused;           // zero-copy token-major input (channels_last) through the fused decoder epilogue
   bool fused_dec;           // decoder epilogue writes NCHW d and the channel statistics itself (EpiDecNchw)
+  bool fused_bwd;           // dE GEMM -> mask -> dW_enc GEMM in one kernel, dPre' never written (fused_bwd_sm100.cuh)
   int nt_hw;                // HW tiles of 64 positions (x statistics of the pack kernel)
   float *xpart, *dpart;
   int cs_rows;              // rows of colsum_part
@@ -70,7 +72,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.E = a.take<bf16>(TF);
   p.D = a.take<bf16>(TC + 8 * static_cast<size_t>(p.C));   // + slack: also the channel-major [C][round8(T)] copy of d
   if (!train) return;
-  p.DP = a.take<bf16>(TF);
+  p.fused_bwd = fused_bwd_enabled() && fused_bwd_supported(p.T, p.C, F, sms);
+  p.DP = p.fused_bwd ? nullptr : a.take<bf16>(TF);   // the fused backward keeps dPre' on the SM
   p.DIFF = a.take<bf16>(TC);
   p.mask = a.take<uint32_t>(static_cast<size_t>(p.T) * 4 * cdiv(p.words, 4));   // group-major, see mask_index
   // cleared by the step prologue: activity bits and the per-(CTA, warp) loss partials (contiguous on purpose)
@@ -87,8 +90,10 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
   p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
-  p.s_we = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
-  p.cs_rows = p.s_we;   // per-feature column sums of dPre': one row per split of the dW_enc GEMM (EpiPartialOnes)
+  p.s_we = p.fused_bwd ? fused_bwd_slots(p.T, F, sms) : planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  // per-feature column sums of dPre': one row per split of the dW_enc GEMM (EpiPartialOnes), or two (token halves) per
+  // slot of the fused backward
+  p.cs_rows = p.fused_bwd ? 2 * p.s_we : p.s_we;
   p.colsum_part = a.take<float>(static_cast<size_t>(p.cs_rows) * F);
   p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
   p.P_we = a.take<float>(static_cast<size_t>(p.s_we) * FC);
@@ -206,6 +211,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   else if (dec_out)
     out_kind = (out->dec_dtype == SVB_BF16 && pl.hw % 8 == 0 && (reinterpret_cast<uintptr_t>(dec_out) & 15) == 0) ? 1 : 4;
   const long long ld_t = (pl.T + 7) & ~7LL;   // row pitch of the channel-major copy (out_kind 4)
+  h->step_flags = pl.fused_bwd ? SVB_STEP_FUSED_BWD : 0;
   prof_begin_step(h);
   prof_mark(h, st, 0);
   // weight prologue on the side stream, next to the activation pack
@@ -273,30 +279,34 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
                          out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
   }
   prof_mark(h, st, 4);
-  // G3 dE -> dPre'
   const float l1c = static_cast<float>(static_cast<double>(lambda_sparse) * C / (2.0 * F));
-  if (pl.bstat) {
-    EpiDPreNoSum::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
-    if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
-      return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false, kAPrefetch)), "dE (B-stationary)");
-  } else {
-    EpiDPreNoSum::Params e3{};
-    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
-    if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
-      return fail(SVB_ERR_TMAP, "tensor map for dPre");
-    SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false)), "dE");
-  }
-  prof_mark(h, st, 5);
   // Weight gradients, split-K over tokens.  The encoder side goes first: with its assembly done, the leading part of
   // the flat buffer [gW_enc | gb_enc] is final and can be all-reduced while the decoder weight-gradient GEMM runs.
   const size_t FC = static_cast<size_t>(F) * C;
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
-  // (its extra ones column yields the per-feature column sums of dPre' that db_enc and the rank-1 fix-up need)
-  EpiPartialOnes::Params e5{pl.P_we, C, static_cast<long long>(FC), pl.colsum_part};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartialOnes>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
+  if (pl.fused_bwd) {
+    // G3 + G5 in one kernel: dPre' = 1[E>0] (DIFF W_dec + lambda*C/(2F)) goes from TMEM through shared memory straight
+    // into the dW_enc MMA; P_we holds one partial per token slot, colsum_part two rows per slot
+    SVB_GEMM(launch_fused_bwd(st, pl.Wdb, pl.DIFF, pl.ds, C, X, pl.xs, C, pl.mask, T, C, F, l1c, pl.P_we, pl.colsum_part, pl.sms),
+             "fused dE -> dW_enc");
+    prof_mark(h, st, 5);
+  } else {
+    // G3 dE -> dPre'
+    EpiDPreNoSum::Params e3{};
+    e3.mask_words = pl.mask; e3.words = pl.words; e3.colsum_partial = nullptr; e3.l1c = l1c; e3.out_slab = pl.es;
+    if (pl.es ? make_store_tmap_bf16_slab32(&e3.tm_dpre, pl.DP, T, F) : make_store_tmap_bf16_chunk(&e3.tm_dpre, pl.DP, T, F, F))
+      return fail(SVB_ERR_TMAP, "tensor map for dPre");
+    if (pl.bstat) {
+      SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false, kAPrefetch)), "dE (B-stationary)");
+    } else {
+      SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false)), "dE");
+    }
+    prof_mark(h, st, 5);
+    // (its extra ones column yields the per-feature column sums of dPre' that db_enc and the rank-1 fix-up need)
+    EpiPartialOnes::Params e5{pl.P_we, C, static_cast<long long>(FC), pl.colsum_part};
+    SVB_GEMM((launch_gemm<256, true, true, EpiPartialOnes>(st, pl.DP, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_enc");
+  }
   // column-sum reduction + encoder-side assembly on the side stream, beside the dW_dec GEMM
   SVB_TRY(side_fork(h, st));
   SVB_TRY(reduce_rows(h->side, pl.colsum_part, pl.cs_rows, F, 1.f, pl.stage, pl.csum));
