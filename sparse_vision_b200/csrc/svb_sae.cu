@@ -90,7 +90,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
   p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
-  p.s_we = p.fused_bwd ? fused_bwd_slots(p.T, F, sms) : planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  p.s_we = p.fused_bwd ? fused_bwd_slots(p.T, p.C, F, sms) : planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
   // per-feature column sums of dPre': one row per split of the dW_enc GEMM (EpiPartialOnes), or two (token halves) per
   // slot of the fused backward
   p.cs_rows = p.fused_bwd ? 2 * p.s_we : p.s_we;

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#define SVB_FBW_TRACE 1
 #include "../sparse_vision_b200/csrc/fused_bwd_sm100.cuh"
 
 using namespace svb;
@@ -66,7 +67,7 @@ int run(int T, int C, int F, bool slab, bool check, int iters) {
   std::vector<uint32_t> hM((size_t)T * 4 * ((words + 3) / 4), 0u);
   for (int t = 0; t < T; ++t)
     for (int w = 0; w < words; ++w) hM[mask_index(t, w, T)] = rnd() & rnd();   // ~25 % active
-  const int slots = fused_bwd_slots(T, F);
+  const int slots = fused_bwd_slots(T, C, F);
   if (!fused_bwd_supported(T, C, F)) { printf("shape not supported\n"); return 2; }
   __nv_bfloat16 *dD, *dX, *dW, *dDr, *dXr;
   uint32_t* dM;
@@ -110,8 +111,8 @@ int run(int T, int C, int F, bool slab, bool check, int iters) {
       for (int k = 0; k < 2 * slots; ++k) s += cs[(size_t)k * F + f];
       if (s != rc_[f] && ++bc <= 5) printf("colsum mismatch at f=%d: %g vs %g\n", f, s, rc_[f]);
     }
-    printf("check T=%d C=%d F=%d %s slots=%d: dW mismatches %zu / %zu, colsum mismatches %zu / %d -> %s\n", T, C, F,
-           slab ? "slab" : "rowmajor", slots, bw, rw.size(), bc, F, (bw | bc) ? "FAIL" : "PASS");
+    printf("check T=%d C=%d F=%d %s %s slots=%d: dW mismatches %zu / %zu, colsum mismatches %zu / %d -> %s\n", T, C, F,
+           slab ? "slab" : "rowmajor", fused_bwd_two_cta(C) ? "2-CTA" : "1-CTA", slots, bw, rw.size(), bc, F, (bw | bc) ? "FAIL" : "PASS");
     cudaFree(rDP); cudaFree(rDPf); cudaFree(rdW); cudaFree(rcs);
     rc = (bw | bc) ? 1 : 0;
   } else {
@@ -124,8 +125,29 @@ int run(int T, int C, int F, bool slab, bool check, int iters) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
-    printf("perf T=%d C=%d F=%d %s: %.4f ms per call = %.0f TFLOP/s over both GEMMs (un-fused dE + dW_enc in the step: ~0.40 ms)\n",
-           T, C, F, slab ? "slab" : "rowmajor", ms, 4.0 * T * C * F / (ms * 1e-3) * 1e-12);
+    {   // one more launch with the wait-cycle trace on: who waits for whom
+      const int grid = (fused_bwd_two_cta(C) ? 2 * ((F + 255) / 256) : (F + 127) / 128) * slots;
+      long long* dT;
+      CK(cudaMalloc(&dT, (size_t)grid * 8 * 8)); CK(cudaMemset(dT, 0, (size_t)grid * 8 * 8));
+      fused_bwd_trace_ptr() = dT;
+      CK(cudaEventRecord(e0));
+      launch_fused_bwd(0, dW, dD, slab, C, dX, slab, C, dM, T, C, F, l1c, dPart, dCs);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      fused_bwd_trace_ptr() = nullptr;
+      float ms1 = 0; CK(cudaEventElapsedTime(&ms1, e0, e1));
+      std::vector<long long> tr((size_t)grid * 8);
+      CK(cudaMemcpy(tr.data(), dT, tr.size() * 8, cudaMemcpyDeviceToHost));
+      double avg[8] = {0}; int cnt[8] = {0};
+      for (int b = 0; b < grid; ++b) for (int q = 0; q < 8; ++q) if (tr[(size_t)b * 8 + q] || q < 2 || q >= 6) { avg[q] += tr[(size_t)b * 8 + q]; cnt[q]++; }
+      const char* nm[8] = {"prod:d_empty", "prod:x_empty", "mma:acc1_empty", "mma:d_full", "mma:p_full", "mma:x_full", "epi:acc1_full", "epi:p_empty"};
+      printf("  trace (traced launch %.4f ms = %.0f kcycles at 1.965 GHz); mean wait kcycles per CTA:", ms1, ms1 * 1965.0);
+      for (int q = 0; q < 8; ++q) printf(" %s=%.0f", nm[q], cnt[q] ? avg[q] / cnt[q] / 1e3 : 0.0);
+      printf("\n");
+      cudaFree(dT);
+    }
+    printf("perf T=%d C=%d F=%d %s %s: %.4f ms per call = %.0f TFLOP/s over both GEMMs (un-fused dE + dW_enc in the step: ~0.40 ms)\n",
+           T, C, F, slab ? "slab" : "rowmajor", fused_bwd_two_cta(C) ? "2-CTA" : "1-CTA", ms, 4.0 * T * C * F / (ms * 1e-3) * 1e-12);
     rc = 0;
   }
   cudaFree(dD); cudaFree(dX); cudaFree(dW); cudaFree(dDr); cudaFree(dXr); cudaFree(dM); cudaFree(dPart); cudaFree(dCs);
