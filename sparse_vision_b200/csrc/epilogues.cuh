@@ -9,6 +9,7 @@
 // slower than its MMA time).  All floating-point reductions are written as per-(tile,warp) partials and summed later
 // in a fixed order, so a step is bit-reproducible.
 #pragma once
+#include <type_traits>
 #include "gemm_sm100.cuh"
 
 namespace svb {
@@ -149,6 +150,41 @@ struct ChunkWriter {
   }
 };
 
+// The same with NBUF rotating 2 KB tiles per warp: put() only waits for the store issued NBUF chunks ago.  For kernels
+// that have the shared memory to spare (the two-CTA B-stationary GEMM keeps only half a weight tile per SM), so that an
+// epilogue warp never stalls on the TMA engine's read of its previous chunk inside a tile.
+template <int NBUF>
+struct ChunkWriterN {
+  static constexpr uint32_t kBytesPerWarp = NBUF * 2048;
+  __host__ __device__ static constexpr uint32_t bytes(int warps) { return warps * kBytesPerWarp; }
+  uint8_t* base0;
+  uint8_t* base;
+  int which;
+  __device__ void init(uint8_t* epi_smem, int ew) { base0 = epi_smem + ew * kBytesPerWarp; base = base0; which = 0; }
+  __device__ __forceinline__ void put(int lane, const float (&v)[32]) {
+    if (lane == 0) bulk_wait_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* row = base + lane * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(row + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8_bf16(v + 8 * i);
+  }
+  __device__ __forceinline__ void flush(const CUtensorMap* tm, int col0, int row0, int lane, int slab_major) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (slab_major) tma_store_3d(tm, base, col0 & 63, row0, col0 >> 6);
+      else tma_store_2d(tm, base, col0, row0);
+      bulk_commit();
+    }
+    which = which + 1 == NBUF ? 0 : which + 1;
+    base = base0 + which * 2048;
+  }
+  __device__ void drain(int lane) {
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ fp32 partials
 // Split-K slices of the weight-gradient GEMMs: out[split][row][col] = acc (fp32, direct 16-byte stores; the
 // epilogue is a negligible part of these K = T GEMMs, so no staging and a full 4-stage operand ring).
@@ -278,8 +314,10 @@ struct EpiStore {
 // element: the ReLU mask the backward needs, and what the per-image activity bits of utils.py:2033-2047 are derived
 // from by mask_to_activity_kernel) and sum|e| partials (sparse_loss.py:41).
 // API = true additionally offers fp32 stores of e / pre (svb_sae_forward); the training step instantiates API = false.
-template <bool API>
+// NBUF > 1: rotating chunk staging (ChunkWriterN) for the two-CTA encoder GEMM.
+template <bool API, int NBUF = 1>
 struct EpiEncT {
+  using Writer = typename std::conditional<NBUF == 1, ChunkWriter, ChunkWriterN<NBUF>>::type;
   struct Params {
     alignas(64) CUtensorMap tm_e;  // bf16 e [M,N], 32 x 32 chunks (make_store_tmap_bf16_chunk / _slab32; valid when e_bf16 != null)
     const float* bias;             // [N]
@@ -294,9 +332,9 @@ struct EpiEncT {
   static constexpr int kWarps = 8;
   static constexpr int kColVecs = 1;
   static constexpr bool kPrefetchAcc = true;
-  static constexpr uint32_t kSmemBytes = ChunkWriter::bytes(kWarps) + 2 * 256 * sizeof(float);
+  static constexpr uint32_t kSmemBytes = Writer::bytes(kWarps) + 2 * 256 * sizeof(float);
   const Params& p;
-  ChunkWriter slab;
+  Writer slab;
   ColVecStage<1, kWarps * 32> stage;
   float* cv_base;
   const float* cv;
@@ -304,7 +342,7 @@ struct EpiEncT {
   uint32_t words[4];
   int ew, cpw, c_first;  // chunks per warp, this warp's first 32-column chunk inside the tile
   __device__ EpiEncT(const Params& p_, uint8_t* smem, int ew_, int block_n)
-      : p(p_), cv_base(reinterpret_cast<float*>(smem + ChunkWriter::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
+      : p(p_), cv_base(reinterpret_cast<float*>(smem + Writer::bytes(kWarps))), cv(cv_base), sum(0.f), total(0.f), ew(ew_),
         cpw((block_n / 32) / (kWarps / 4)), c_first((ew_ / 4) * ((block_n / 32) / (kWarps / 4))) {
     slab.init(smem, ew_);
   }
@@ -389,6 +427,7 @@ struct EpiEncT {
   }
 };
 typedef EpiEncT<false> EpiEnc;     // training step
+typedef EpiEncT<false, 4> EpiEnc4; // training step, two-CTA GEMM: 4 rotating chunk tiles per warp
 typedef EpiEncT<true> EpiEncApi;   // svb_sae_forward (optional fp32 e / pre outputs)
 
 // ------------------------------------------------------------------------------------------------ decoder
@@ -491,26 +530,30 @@ struct EpiDec {
 //     tile.  dec_stats_image_kernel folds the groups of an image together.  No token-major d is written at all.
 // Staging is per chunk (2 x 2 KB per warp) on purpose: 34 KB of epilogue smem leave room for FOUR 48 KB operand
 // stages, and this GEMM streams E from HBM -- with three stages it ran at 4.1 TB/s, with four at 4.9 TB/s.
-struct EpiDecNchw {
-  struct Params {
-    alignas(64) CUtensorMap tm_diff;  // slab-major bf16 diff [M, N], box 32 cols x 32 rows x 1, 64B swizzle
-    alignas(64) CUtensorMap tm_out;   // NCHW bf16 output seen as {HW, C, B}, box {32, 32, 1}, no swizzle (out != null)
-    const float* bias;                // [N] decoder bias
-    const __nv_bfloat16* x;           // slab-major [M, N] targets (the SAE input)
-    float* sq_partial;                // [gridDim.x * kWarps]: one running sum per CTA and epilogue warp
-    float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_image_kernel
-    void* out;                        // out_kind 1: the caller's NCHW bf16 tensor (second-image pieces of straddling warps)
-    int hw;                           // tokens per image (>= 32)
-    int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base);
-                                      // 4: tm_out is a channel-major [C][T] workspace (make_store_tmap_bf16_cmajor)
-                                      //    that a copy kernel turns into the caller's tensor (any HW, bf16 or fp32)
-                                      // 2: token-major bf16 [M, N] through tm_out (make_store_tmap_bf16_chunk): the
-                                      //    caller's channels_last tensor, no layout change at all (tok = 1 only)
-    int x_slab;                       // x is slab-major (1) or the caller's row-major token matrix [M, N] (0)
-    int tok;                          // 1: token-major in / out: d is staged token-major, the per-channel sums are
-                                      //    read back column-wise like those of diff (no channel-major copy exists)
-  };
-  static constexpr int kWarps = 8;
+struct EpiDecNchwParams {
+  alignas(64) CUtensorMap tm_diff;  // slab-major bf16 diff [M, N], box 32 cols x 32 rows x 1, 64B swizzle
+  alignas(64) CUtensorMap tm_out;   // NCHW bf16 output seen as {HW, C, B}, box {32, 32, 1}, no swizzle (out != null)
+  const float* bias;                // [N] decoder bias
+  const __nv_bfloat16* x;           // slab-major [M, N] targets (the SAE input)
+  float* sq_partial;                // [gridDim.x * kWarps]: one running sum per CTA and epilogue warp
+  float* part;                      // [(tiles_m * 4 groups) * 2 slots][3][N], see dec_stats_image_kernel
+  void* out;                        // out_kind 1: the caller's NCHW bf16 tensor (second-image pieces of straddling warps)
+  int hw;                           // tokens per image (>= 32)
+  int out_kind;                     // 1: bf16 through tm_out (HW % 8 == 0, 16-byte aligned base);
+                                    // 4: tm_out is a channel-major [C][T] workspace (make_store_tmap_bf16_cmajor)
+                                    //    that a copy kernel turns into the caller's tensor (any HW, bf16 or fp32)
+                                    // 2: token-major bf16 [M, N] through tm_out (make_store_tmap_bf16_chunk): the
+                                    //    caller's channels_last tensor, no layout change at all (tok = 1 only)
+  int x_slab;                       // x is slab-major (1) or the caller's row-major token matrix [M, N] (0)
+  int tok;                          // 1: token-major in / out: d is staged token-major, the per-channel sums are
+                                    //    read back column-wise like those of diff (no channel-major copy exists)
+};
+// WARPS = 8: epilogue of gemm_bf16_kernel; WARPS = 16: decoder epilogue of the fused forward kernel (fused_fwd_sm100.cuh),
+// which also places the bias vector itself (use_colvec_at) because 16 x 4 KB of staging fill the aliased E tile.
+template <int WARPS>
+struct EpiDecNchwT {
+  using Params = EpiDecNchwParams;
+  static constexpr int kWarps = WARPS;
   static constexpr int kColVecs = 1;
   static constexpr bool kPrefetchAcc = true;
   static constexpr bool kPadN64 = true;   // N % 64 != 0: the padding columns of diff's last slab are written (zeros)
@@ -523,9 +566,10 @@ struct EpiDecNchw {
   const float* cv;
   float sq;
   int ew;
-  __device__ EpiDecNchw(const Params& p_, uint8_t* smem, int ew_, int)
+  __device__ EpiDecNchwT(const Params& p_, uint8_t* smem, int ew_, int)
       : p(p_), tbuf(smem + ew_ * 4096), fbuf(smem + ew_ * 4096 + 2048),
         cv_base(reinterpret_cast<float*>(smem + kWarps * 4096)), cv(cv_base), sq(0.f), ew(ew_) {}
+  __device__ void use_colvec_at(float* dst) { cv_base = dst; cv = dst; }   // colvec_commit(0, tid) then writes there
   __device__ void colvec_fetch(const GemmProblem& g, const TileInfo& ti, int tid) {
     const float* const src[1] = {p.bias};
     stage.fetch(src, ti.n0, g.N, tid);
@@ -677,6 +721,7 @@ struct EpiDecNchw {
     }
   }
 };
+typedef EpiDecNchwT<8> EpiDecNchw;
 
 // ------------------------------------------------------------------------------------------------ dE -> dPre
 // acc = diff * W_dec  (unscaled dE);  dPre' = 1[e>0] * (acc + l1c)  with l1c = lambda*C/(2F), i.e. the whole

@@ -1,4 +1,8 @@
 // Two-CTA (cta_group::2) variant of the B-stationary GEMM for K <= 256:  D[M,N] = A[M,K] * B[N,K]^T.
+// (Round 1 measured this kernel SLOWER than the single-CTA one and parked it under tools/; the cause was not the
+// pairing but the `.release.cluster` qualifier on the epilogue's remote mbarrier arrives -- a MEMBAR.ALL.GPU per
+// arrive, see ptx_cluster.cuh.  With default-semantics arrives the output-bound K = 256 probe runs at 0.154 ms
+// against 0.173-0.194 ms single-CTA, and the SaeMLP encoder GEMM uses it.)
 //
 // A cluster of two CTAs (an SM pair) owns one 256-column N tile and walks 256-row "pair tiles" of M; CTA r of the
 // pair computes rows [256*tp + 128*r, +128).  One thread of the leader CTA issues tcgen05.mma.cta_group::2 with
@@ -12,8 +16,8 @@
 // (tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs), warps 2.. = epilogue in both
 // CTAs on their own TMEM (the peer's epilogue warps release the accumulator stage with remote mbarrier arrives).
 #pragma once
-#include "../sparse_vision_b200/csrc/gemm_sm100.cuh"
-#include "../sparse_vision_b200/csrc/ptx_cluster.cuh"
+#include "gemm_sm100.cuh"
+#include "ptx_cluster.cuh"
 
 namespace svb {
 
@@ -254,8 +258,7 @@ gemm2_bstat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }  // namespace svb
 
 // ---------------------------------------------------------------------------------------------------------------- host
-// (moved here from gemm_host.cuh together with the kernel: bring-up only, a measured negative result -- DESIGN.md 4)
-#include "../sparse_vision_b200/csrc/gemm_host.cuh"
+#include "gemm_host.cuh"
 namespace svb {
 // Two-CTA B-stationary launch (gemm2_sm100.cuh): K <= 256, A K-major (row-major pitch lda, or slab-major), B K-major
 // [N, K] or MN-major [K, N] with pitch ldb.  *groups_out receives the number of pair groups per N tile (the epilogue's

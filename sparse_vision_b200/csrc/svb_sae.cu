@@ -16,6 +16,7 @@
 // The backward runs in units of T*C/2 (dPre' = dPre * T*C/2) so bf16 intermediates stay O(1).
 #include "svb_common.cuh"
 #include "fused_bwd_sm100.cuh"
+#include "gemm2_sm100.cuh"
 
 using namespace svb;
 
@@ -53,6 +54,14 @@ constexpr int kVmChunks = 32;
 // steps (0.187 / 0.193 at 4 / 8: the lines are evicted again), but inside the step, where X / DIFF were written just
 // before, it changes nothing (0.241 vs 0.236 ms), so it is off.
 constexpr int kAPrefetch = 0;
+// SVB_ENC_2CTA=0 keeps the single-CTA B-stationary encoder GEMM (A/B measurements).
+bool enc_two_cta() {
+  static const bool on = [] {
+    const char* e = getenv("SVB_ENC_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) {
   p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
@@ -235,7 +244,14 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   e1.words = pl.words; e1.e_slab = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab32(&e1.tm_e, pl.E, T, F) : make_store_tmap_bf16_chunk(&e1.tm_e, pl.E, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for E");
-  if (pl.bstat) {
+  if (pl.bstat && enc_two_cta() && gemm2_groups(T, F, pl.sms) >= 1) {
+    // SM pairs (cta_group::2): each CTA keeps half of the resident weight tile and reads 8 KB instead of 12 KB of
+    // operands per MMA step from shared memory, which this output-bound GEMM shares with its own TMA stores
+    EpiEnc4::Params e14{};
+    e14.tm_e = e1.tm_e; e14.bias = e1.bias; e14.e_bf16 = e1.e_bf16; e14.l1_partial = e1.l1_partial;
+    e14.mask_words = e1.mask_words; e14.words = e1.words; e14.e_slab = e1.e_slab;
+    SVB_GEMM((launch_gemm2_bstat<false, EpiEnc4>(st, X, C, pl.Web, C, T, F, C, e14, pl.xs, pl.sms)), "enc (two-CTA B-stationary)");
+  } else if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary)");
   } else {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");

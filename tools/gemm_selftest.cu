@@ -7,10 +7,11 @@
 #include <vector>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #define SVB_GEMM_TRACE 1
 #include "../sparse_vision_b200/csrc/gemm_host.cuh"
 #include "../sparse_vision_b200/csrc/epilogues.cuh"
-#include "gemm2_sm100.cuh"
+#include "../sparse_vision_b200/csrc/gemm2_sm100.cuh"
 
 using namespace svb;
 
@@ -260,6 +261,7 @@ static int perf() {
   return 0;
 }
 
+template <class T> struct TypeTag { using type = T; };
 // EpiEnc feature toggles: which fused output costs what (cfg2 shape)
 static int perf_enc_variants() {
   const int M = 200704, N = 2048, K = 256, HW = 784, words = N / 32;
@@ -280,25 +282,56 @@ static int perf_enc_variants() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  for (int variant = 0; variant < 5; ++variant) {
-    EpiEnc::Params ep;
+  auto run = [&](auto tag, bool two, int variant, bool slab) {
+    using E = typename decltype(tag)::type;
+    typename E::Params ep;
     memset(&ep, 0, sizeof(ep));
-    ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.words = words;
-    make_store_tmap_bf16_chunk(&ep.tm_e, dE, M, N, N);
+    ep.bias = dbias; ep.e_bf16 = (__nv_bfloat16*)dE; ep.words = words; ep.e_slab = slab ? 1 : 0;
+    if (slab) make_store_tmap_bf16_slab32(&ep.tm_e, dE, M, N); else make_store_tmap_bf16_chunk(&ep.tm_e, dE, M, N, N);
     if (variant == 2 || variant == 4) ep.mask_words = dmask;
     if (variant == 3 || variant == 4) ep.l1_partial = dl1;
-    for (int it = 0; it < 3; ++it) launch_gemm<256, false, false, EpiEnc, true>(0, dA, K, dB, K, M, N, K, 1, ep);
+    auto launch = [&]() {
+      if (two) launch_gemm2_bstat<false, E>(0, dA, K, dB, K, M, N, K, ep);
+      else launch_gemm<256, false, false, E, true>(0, dA, K, dB, K, M, N, K, 1, ep);
+    };
+    for (int it = 0; it < 3; ++it) launch();
     CK(cudaDeviceSynchronize());
     const int iters = 10;
     cudaEventRecord(e0);
-    for (int it = 0; it < iters; ++it) launch_gemm<256, false, false, EpiEnc, true>(0, dA, K, dB, K, M, N, K, 1, ep);
+    for (int it = 0; it < iters; ++it) launch();
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
-    printf("[perf EpiEnc variant %d: mask=%d l1=%d] %.3f ms  %.1f TFLOP/s\n", variant,
-           ep.mask_words != nullptr, ep.l1_partial != nullptr, ms, 2.0 * M * N * K / ms * 1e-9);
+    printf("[perf %s %s variant %d: mask=%d l1=%d %s] %.3f ms  %.1f TFLOP/s\n", two ? "2-CTA" : "1-CTA",
+           sizeof(typename E::Writer) > sizeof(ChunkWriter) ? "EpiEnc4" : "EpiEnc", variant, ep.mask_words != nullptr,
+           ep.l1_partial != nullptr, slab ? "slab" : "rowmajor", ms, 2.0 * M * N * K / ms * 1e-9);
+    long long* tr;
+    CK(cudaMalloc(&tr, 148 * 4 * sizeof(long long)));
+    CK(cudaMemset(tr, 0, 148 * 4 * sizeof(long long)));
+    gemm_trace_ptr() = tr;
+    launch();
+    CK(cudaDeviceSynchronize());
+    gemm_trace_ptr() = nullptr;
+    long long h[148 * 4];
+    CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int n = 0, nl = 0;
+    for (int b = 0; b < 144; ++b) {
+      s0 += h[b * 4]; s3 += h[b * 4 + 3]; ++n;
+      if (!two || (b & 1) == 0) { s1 += h[b * 4 + 1]; s2 += h[b * 4 + 2]; ++nl; }
+    }
+    printf("    wait kcycles per CTA: producer on free slot %.0f | MMA on operands %.0f | MMA on free accumulator %.0f | epilogue warp 0 on accumulator %.0f   (kernel ~%.0f kcycles)\n",
+           s0 / n / 1e3, s1 / nl / 1e3, s2 / nl / 1e3, s3 / n / 1e3, ms * 1.965e6 / 1e3);
+    cudaFree(tr);
+  };
+  for (int variant : {0, 4}) {
+    for (int slab = 0; slab < 2; ++slab) {
+      run(TypeTag<EpiEnc>{}, false, variant, slab);
+      run(TypeTag<EpiEnc>{}, true, variant, slab);
+      run(TypeTag<EpiEnc4>{}, true, variant, slab);
+    }
   }
   return 0;
 }
