@@ -61,6 +61,19 @@ int64_t svb_launch_count(void);
 #define SVB_STEP_FUSED_BWD 1
 int32_t svb_last_step_flags(const svb_handle* h);
 
+/* Process-wide kernel-selection switches, for A/B measurements and for the tests that pin the fused / paired kernels
+ * against the plain ones (results agree within the parity tolerances whatever the values).  Defaults may be preset
+ * through the environment variable named beside each key.  svb_get_tuning returns -1 for an unknown key. */
+enum svb_tuning_key {
+  SVB_TUNE_FUSED_BWD = 0,    /* 1: dE GEMM -> ReLU mask -> dW_enc GEMM as one kernel when C <= 256, C % 64 == 0 (SVB_FUSED_BWD) */
+  SVB_TUNE_FBW_2CTA = 1,     /* 1: that kernel on SM pairs (cta_group::2) when C % 128 == 0                      (SVB_FBW_2CTA) */
+  SVB_TUNE_GEMM_PAIRS = 2,   /* 1: streaming GEMMs with more than one 128-row tile run on SM pairs                 (SVB_GEMM2) */
+  SVB_TUNE_ENC_2CTA = 3,     /* 1: B-stationary encoder GEMM on SM pairs (default 0: measured slower)             (SVB_ENC_2CTA) */
+  SVB_TUNE_FBW_PREFETCH = 4  /* L2 prefetch distance (token blocks) of the fused backward, default 0              (SVB_FBW_PF) */
+};
+int svb_set_tuning(int32_t key, int32_t value);
+int32_t svb_get_tuning(int32_t key);
+
 /* Per-phase timing of the SaeMLP training step with CUDA events recorded on the caller's stream between the phases
  * (pack+prep, enc GEMM, dec GEMM, channel stats, dE GEMM, dW_dec GEMM, dW_enc GEMM, gradient assembly, Adam).
  * svb_profile_read synchronises the device and returns the mean milliseconds per phase over the recorded steps

@@ -525,14 +525,8 @@ fused_bwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (warp == 1) tmem2_dealloc(tmem_base, 512);
 }
 
-// SVB_FUSED_BWD=0 in the environment keeps the two un-fused GEMMs (A/B measurements, bring-up).
-inline bool fused_bwd_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("SVB_FUSED_BWD");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
+// tuning(kTuneFusedBwd) = 0 keeps the two un-fused GEMMs (A/B measurements, tests).
+inline bool fused_bwd_enabled() { return tuning(kTuneFusedBwd) != 0; }
 
 #ifdef SVB_FBW_TRACE
 inline long long*& fused_bwd_trace_ptr() {
@@ -540,22 +534,11 @@ inline long long*& fused_bwd_trace_ptr() {
   return p;
 }
 #endif
-inline int fused_bwd_prefetch() {
-  static const int pf = [] {
-    const char* e = getenv("SVB_FBW_PF");
-    return e ? atoi(e) : 0;   // measured: no gain inside the step (0.369-0.376 ms at 0..6 blocks ahead)
-  }();
-  return pf;
-}
+// measured: no gain inside the step (0.369-0.376 ms at 0..6 blocks ahead), so 0 by default
+inline int fused_bwd_prefetch() { return tuning(kTuneFbwPrefetch); }
 
-// SVB_FBW_2CTA=0 keeps the single-CTA kernel for every shape (A/B measurements).
-inline bool fused_bwd_two_cta(int C) {
-  static const bool on = [] {
-    const char* e = getenv("SVB_FBW_2CTA");
-    return !(e && e[0] == '0');
-  }();
-  return on && C % 128 == 0;
-}
+// tuning(kTuneFbwTwoCta) = 0 keeps the single-CTA kernel for every shape.
+inline bool fused_bwd_two_cta(int C) { return tuning(kTuneFbwTwoCta) != 0 && C % 128 == 0; }
 // Slots the launcher will use (sizes the split-K workspaces): S = min(sms / tiles_f, token blocks), or with SM pairs
 // and 256-feature pair tiles for the two-CTA kernel.
 inline int fused_bwd_slots(long long T, int C, int F, int max_ctas = 0) {

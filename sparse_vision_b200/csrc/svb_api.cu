@@ -1,6 +1,7 @@
 // Handle lifecycle, optimiser / re-initialisation / activity entry points, layout helpers and the indirect-effect
 // reductions of the C ABI (include/svb.h).
 #include "svb_common.cuh"
+#include "gemm2_sm100.cuh"
 
 using namespace svb;
 
@@ -42,6 +43,12 @@ extern "C" int svb_destroy(svb_handle* h) {
 
 extern "C" int64_t svb_launch_count(void) { return static_cast<int64_t>(launch_counter()); }
 extern "C" int32_t svb_last_step_flags(const svb_handle* h) { return h ? h->step_flags : 0; }
+extern "C" int svb_set_tuning(int32_t key, int32_t value) {
+  if (key < 0 || key >= kTuneCount) return fail(SVB_ERR_BAD_ARG, "unknown tuning key %d", key);
+  tuning(key) = value;
+  return 0;
+}
+extern "C" int32_t svb_get_tuning(int32_t key) { return (key < 0 || key >= kTuneCount) ? -1 : tuning(key); }
 
 // ---------------------------------------------------------------------------------------------------- profiling
 static const char* kPhaseNames[] = {"pack+prep", "enc_gemm", "dec_gemm", "channel_stats", "dE_gemm",
@@ -341,16 +348,16 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   EpiEnc::Params e1{};
   e1.bias = fold; e1.e_bf16 = E; e1.words = (F + 31) / 32;
   if (make_store_tmap_bf16_chunk(&e1.tm_e, E, Ti, F, F)) return fail(SVB_ERR_TMAP, "tensor map for E");
-  SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, Xp, C, Web, C, Ti, F, C, 1, e1)), "enc");
+  SVB_GEMM((launch_gemm_s<false, false, EpiEnc>(st, Xp, C, Web, C, Ti, F, C, 1, e1)), "enc");
   // DIFF = dec - x = -(sae error)
   EpiDec::Params e2{};
   e2.bias = p->b_dec; e2.x = Xp; e2.diff_bf16 = DIFF;
   if (make_store_tmap_bf16(&e2.tm_diff, DIFF, Ti, C, C)) return fail(SVB_ERR_TMAP, "tensor map for DIFF");
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, E, F, Wdb, F, Ti, C, F, 1, e2)), "dec");
+  SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, E, F, Wdb, F, Ti, C, F, 1, e2)), "dec");
   // enc.grad = g W_dec   (nnsight_intervention_check.py:194-195)
   EpiStore::Params e3;
   make_store_params(&e3, GE, F, nullptr, 1.f, 0, 1, Ti, F);
-  SVB_GEMM((launch_gemm<256, false, true, EpiStore>(st, Gp, C, Wdb, F, Ti, F, C, 1, e3)), "g W_dec");
+  SVB_GEMM((launch_gemm_s<false, true, EpiStore>(st, Gp, C, Wdb, F, Ti, F, C, 1, e3)), "g W_dec");
   if (ie_features)
     SVB_TRY(launch_ie_channelwise<bf16>(st, h->sms, E, GE, avgT_f, T, HW, F, scale, partial, chunks_f, stage, ie_features));
   if (ie_neurons)

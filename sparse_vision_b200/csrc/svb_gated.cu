@@ -3,6 +3,7 @@
 // "via gate" pass (loss value only — it is computed under no_grad in the reference and carries no gradient), dE,
 // dW_dec and a single dW_gate GEMM whose operand A' = dPi + exp(r_mag) * dMag merges both sub-layer gradients.
 #include "svb_common.cuh"
+#include "gemm2_sm100.cuh"
 #include "epilogues_gated.cuh"
 
 using namespace svb;
@@ -71,8 +72,8 @@ void carve(Arena& a, GatedPlan& p, const svb_acts* x, int F, bool train, int sms
   p.chan = a.take<float>(4 * p.C);
   p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
-  p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
-  p.s_wg = planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
+  p.s_wd = planned_splits_s(p.C, F, static_cast<int>(p.T), 0, sms);
+  p.s_wg = planned_splits_s(F, p.C, static_cast<int>(p.T), 0, sms);
   p.P_wd = a.take<float>(static_cast<size_t>(p.s_wd) * FC);
   p.P_wg = a.take<float>(static_cast<size_t>(p.s_wg) * FC);
   p.vm = a.take<float>(static_cast<size_t>(kVmChunks) * p.C);
@@ -204,14 +205,14 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
   e1.words = pl.words;
   e1.tma = make_store_tmap_bf16(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F) == 0 &&
            make_store_tmap_bf16(&e1.tm_rp, e1.rp_bf16, T, pl.F, pl.F) == 0;
-  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, pl.C, pl.Wgb, pl.C, T, pl.F, pl.C, 1, e1)), "gated enc");
+  SVB_GEMM((launch_gemm_s<false, false, EpiGatedEnc>(st, X, pl.C, pl.Wgb, pl.C, T, pl.F, pl.C, 1, e1)), "gated enc");
   if (out->dec) {
     EpiDec::Params e2{};
     e2.bias = p->b_dec;
     e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
     e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
     if (e2.d_bf16 && make_store_tmap_bf16(&e2.tm_d, e2.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map");
-    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
   }
   if (out->via) {
     EpiDec::Params e3{};
@@ -219,7 +220,7 @@ extern "C" int svb_gated_forward(svb_handle* h, void* stream, const svb_acts* x,
     e3.d_bf16 = out->via_dtype == SVB_BF16 ? static_cast<bf16*>(out->via) : nullptr;
     e3.d_f32 = out->via_dtype == SVB_F32 ? static_cast<float*>(out->via) : nullptr;
     if (e3.d_bf16 && make_store_tmap_bf16(&e3.tm_d, e3.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map");
-    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.rp_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e3)), "via");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, e1.rp_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e3)), "via");
   }
   return 0;
 }
@@ -272,7 +273,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   if (pl.es ? (make_store_tmap_bf16_slab(&e1.tm_e, pl.E, T, F) || make_store_tmap_bf16_slab(&e1.tm_rp, pl.RP, T, F))
             : (make_store_tmap_bf16(&e1.tm_e, pl.E, T, F, F) || make_store_tmap_bf16(&e1.tm_rp, pl.RP, T, F, F)))
     return fail(SVB_ERR_TMAP, "tensor maps for E / relu_pi");
-  SVB_GEMM((launch_gemm<256, false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "gated enc");
+  SVB_GEMM((launch_gemm_s<false, false, EpiGatedEnc>(st, X, C, pl.Wgb, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "gated enc");
   prof_mark(h, st, 2);
   // per-image activity bits of e from its 1-bit mask: side stream, beside the decoder GEMM
   SVB_TRY(side_fork(h, st));
@@ -290,7 +291,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
     if (out_kind == 1 && make_tmap_nchw_bf16(&e2.tm_out, dec_out, pl.n_img, C, pl.hw)) return fail(SVB_ERR_TMAP, "tensor map for the NCHW output");
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     // newest E tiles first (still in L2), as in svb_sae.cu
-    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
     // the statistics folds (and the scatter of a channel-major d) only feed the end of the step: side stream
     SVB_TRY(side_fork(h, st));
     if (out_kind == 4) SVB_TRY(run_cmajor_to_nchw(h->side, pl.D, dec_out, out->dec_dtype, C, pl.hw, pl.T, ld_t));
@@ -304,13 +305,13 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
     if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
               : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
       return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
     // statistics + NCHW write-back of d only feed the end of the step: side stream, beside the via / dE GEMMs
     SVB_TRY(side_fork(h, st));
     SVB_TRY(run_post_dec(h->side, x, X, pl.D, pl.T, dec_out, out ? out->dec_dtype : SVB_BF16,
                          out ? out->dec_layout : SVB_NCHW, pl.st, pl.chan, pl.var_part, pl.rowvar, pl.xs));
   }
-  SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
+  SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, pl.RP, F, pl.Wdb, F, T, C, F, 1, e2v, nullptr, 0, 0, pl.es, false)), "via");
   prof_mark(h, st, 3);
   prof_mark(h, st, 4);
   EpiGatedDPre::Params e3{};
@@ -320,6 +321,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   e3.block_n = 256; e3.slab_major = pl.es;
   if (pl.es ? make_store_tmap_bf16_slab(&e3.tm_a, pl.A, T, F) : make_store_tmap_bf16(&e3.tm_a, pl.A, T, F, F))
     return fail(SVB_ERR_TMAP, "tensor map for A'");
+  // (single-CTA: on SM pairs this epilogue-heavy GEMM measured 0.424 against 0.398 ms at cfg3)
   SVB_GEMM((launch_gemm<256, false, true, EpiGatedDPre>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, ds, false)), "gated dE");
   prof_mark(h, st, 5);
   // Weight gradients: the gate side first, so that [gW_gate | gb_gate | gb_mag | gr_mag] can be all-reduced while the
@@ -328,7 +330,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   const float s = static_cast<float>(2.0 / (Tg * C));
   float* flat = pl.flat;
   EpiPartial::Params e5{pl.P_wg, C, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_gate");
+  SVB_GEMM((launch_gemm_s<true, true, EpiPartial>(st, pl.A, F, X, C, F, C, T, 0, e5, nullptr, 0, 0, pl.es, pl.xs)), "dW_gate");
   // reductions + gate-side assembly + tail on the side stream, beside the dW_dec GEMM
   SVB_TRY(side_fork(h, st));
   cudaStream_t ss = h->side;
@@ -359,7 +361,7 @@ extern "C" int svb_gated_step_grads(svb_handle* h, void* stream, const svb_acts*
   (grads_tail_kernel<<<1, 1024, 0, ss>>>(ta), svb::count_launch());
   prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, ds, pl.es)), "dW_dec");
+  SVB_GEMM((launch_gemm_s<true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, ds, pl.es)), "dW_dec");
   prof_mark(h, st, 7);
   SVB_TRY(side_join(h, st));
   SVB_TRY(run_assemble(st, aa, 2));

@@ -54,14 +54,9 @@ constexpr int kVmChunks = 32;
 // steps (0.187 / 0.193 at 4 / 8: the lines are evicted again), but inside the step, where X / DIFF were written just
 // before, it changes nothing (0.241 vs 0.236 ms), so it is off.
 constexpr int kAPrefetch = 0;
-// SVB_ENC_2CTA=0 keeps the single-CTA B-stationary encoder GEMM (A/B measurements).
-bool enc_two_cta() {
-  static const bool on = [] {
-    const char* e = getenv("SVB_ENC_2CTA");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
+// tuning(kTuneEncTwoCta) = 1 runs the encoder GEMM on SM pairs: measured 0.250 against 0.214 ms with the real epilogue
+// (mask words + l1), so off by default.
+bool enc_two_cta() { return tuning(kTuneEncTwoCta) != 0; }
 
 void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) {
   p.C = x->C; p.F = F; p.hw = x->hw; p.n_img = x->n_images; p.sms = sms;
@@ -98,7 +93,7 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   p.chan = a.take<float>(4 * p.C);
   p.var_part = a.take<float>(2 * cdiv(p.C, 8) + 2);
   p.rowvar = a.take<float>(p.hw == 1 ? 2 * static_cast<size_t>(p.T) : 2);
-  p.s_wd = planned_splits<256>(p.C, F, static_cast<int>(p.T), 0);
+  p.s_wd = planned_splits_s(p.C, F, static_cast<int>(p.T), 0, sms);
   p.s_we = p.fused_bwd ? fused_bwd_slots(p.T, p.C, F, sms) : planned_splits<256>(F, p.C, static_cast<int>(p.T), 0);
   // per-feature column sums of dPre': one row per split of the dW_enc GEMM (EpiPartialOnes), or two (token halves) per
   // slot of the fused backward
@@ -171,14 +166,14 @@ extern "C" int svb_sae_forward(svb_handle* h, void* stream, const svb_acts* x, c
   e1.pre_f32 = out->pre;
   e1.words = pl.words;
   if (make_store_tmap_bf16_chunk(&e1.tm_e, e1.e_bf16, T, pl.F, pl.F)) return fail(SVB_ERR_TMAP, "tensor map for enc output");
-  SVB_GEMM((launch_gemm<256, false, false, EpiEncApi>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
+  SVB_GEMM((launch_gemm_s<false, false, EpiEncApi>(st, X, pl.C, pl.Web, pl.C, T, pl.F, pl.C, 1, e1)), "enc");
   if (out->dec) {
     EpiDec::Params e2{};
     e2.bias = p->b_dec;
     e2.d_bf16 = out->dec_dtype == SVB_BF16 ? static_cast<bf16*>(out->dec) : nullptr;
     e2.d_f32 = out->dec_dtype == SVB_F32 ? static_cast<float*>(out->dec) : nullptr;
     if (e2.d_bf16 && make_store_tmap_bf16(&e2.tm_d, e2.d_bf16, T, pl.C, pl.C)) return fail(SVB_ERR_TMAP, "tensor map for dec output");
-    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, e1.e_bf16, pl.F, pl.Wdb, pl.F, T, pl.C, pl.F, 1, e2)), "dec");
   }
   return 0;
 }
@@ -254,7 +249,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   } else if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary)");
   } else {
-    SVB_GEMM((launch_gemm<256, false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");
+    SVB_GEMM((launch_gemm_s<false, false, EpiEnc>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false)), "enc");
   }
   prof_mark(h, st, 2);
   // per-image activity bits from the masks: side stream, beside the decoder GEMM (joined before the assembly)
@@ -273,7 +268,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (out_kind == 4 && make_store_tmap_bf16_cmajor(&e2.tm_out, pl.D, C, pl.T, ld_t)) return fail(SVB_ERR_TMAP, "tensor map for the channel-major output");
     // the encoder wrote E from the first token tile to the last, so its newest ~100 MB are still in L2: walk the
     // token tiles backwards and the decoder's first reads are hits (-3.5 us of 210)
-    SVB_GEMM((launch_gemm<256, false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDecNchw>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false, 0, /*reverse_m=*/true)), "dec (fused NCHW)");
     prof_mark(h, st, 3);
     // the statistics folds only feed the tail of the step: side stream, beside the dE GEMM
     SVB_TRY(side_fork(h, st));
@@ -288,7 +283,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (pl.xs ? (make_store_tmap_bf16_slab(&e2.tm_d, pl.D, T, C) || make_store_tmap_bf16_slab(&e2.tm_diff, pl.DIFF, T, C))
               : (make_store_tmap_bf16(&e2.tm_d, pl.D, T, C, C) || make_store_tmap_bf16(&e2.tm_diff, pl.DIFF, T, C, C)))
       return fail(SVB_ERR_TMAP, "tensor maps for D / DIFF");
-    SVB_GEMM((launch_gemm<256, false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
+    SVB_GEMM((launch_gemm_s<false, false, EpiDec>(st, pl.E, F, pl.Wdb, F, T, C, F, 1, e2, nullptr, 0, 0, pl.es, false)), "dec");
     prof_mark(h, st, 3);
     // channel statistics + the decoder output handed back to the model (model_pipeline.py:425,432), one pass
     SVB_TRY(run_post_dec(st, x, X, pl.D, pl.T, dec_out, out ? out->dec_dtype : SVB_BF16,
@@ -316,7 +311,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     if (pl.bstat) {
       SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum, true>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false, kAPrefetch)), "dE (B-stationary)");
     } else {
-      SVB_GEMM((launch_gemm<256, false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false)), "dE");
+      SVB_GEMM((launch_gemm_s<false, true, EpiDPreNoSum>(st, pl.DIFF, C, pl.Wdb, F, T, F, C, 1, e3, nullptr, 0, 0, pl.ds, false)), "dE");
     }
     prof_mark(h, st, 5);
     // (its extra ones column yields the per-feature column sums of dPre' that db_enc and the rank-1 fix-up need)
@@ -350,7 +345,7 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   h->early_elems = h->comm ? static_cast<int64_t>(pl.o_gwd) : 0;
   prof_mark(h, st, 6);
   EpiPartial::Params e4{pl.P_wd, F, static_cast<long long>(FC)};
-  SVB_GEMM((launch_gemm<256, true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.ds, pl.es)), "dW_dec");
+  SVB_GEMM((launch_gemm_s<true, true, EpiPartial>(st, pl.DIFF, C, pl.E, F, C, F, T, 0, e4, nullptr, 0, 0, pl.ds, pl.es)), "dW_dec");
   prof_mark(h, st, 7);
   // rest of the gradient assembly: the decoder weight gradient, after everything forked above has joined
   SVB_TRY(side_join(h, st));

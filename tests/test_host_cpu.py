@@ -360,3 +360,14 @@ def test_attribution_pass_sharded_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_tuning_keys_round_trip():
+    """svb_set_tuning / svb_get_tuning (include/svb.h): host-side state only, no device needed."""
+    from sparse_vision_b200 import _lib as L
+    lib = L.load()
+    assert lib.svb_get_tuning(99) == -1 and lib.svb_set_tuning(99, 1) != 0
+    for key in range(5):
+        old = lib.svb_get_tuning(key)
+        assert lib.svb_set_tuning(key, old + 1) == 0 and lib.svb_get_tuning(key) == old + 1
+        lib.svb_set_tuning(key, old)

@@ -1,4 +1,4 @@
-// Stand-alone check + timing of the fused SaeMLP forward (sparse_vision_b200/csrc/fused_fwd_sm100.cuh: encoder GEMM ->
+// Stand-alone check + timing of the fused SaeMLP forward (tools/fused_fwd_sm100.cuh: encoder GEMM ->
 // bias / ReLU / mask -> decoder GEMM -> decoder epilogue, one two-CTA kernel) against naive kernels on integer-valued
 // inputs: E, the mask words, the token-major d output and DIFF are compared bit for bit, the two loss sums to 1e-5.
 //   fused_fwd_probe check      small shapes (T tails, C = 64..256, several tiles per pair so every barrier phase wraps)
@@ -9,7 +9,7 @@
 #include <cmath>
 #include <vector>
 #define SVB_FFW_TRACE 1
-#include "../sparse_vision_b200/csrc/fused_fwd_sm100.cuh"
+#include "fused_fwd_sm100.cuh"
 
 using namespace svb;
 

@@ -16,11 +16,17 @@
 // tile (128 of the 256 feature rows of W_enc[j], C/2 of the channel rows of W_dec[:, j]): 128 KB per CTA and feature
 // tile instead of 256 KB -- the un-paired bring-up version (tools/fused_fwd_probe.cu, round 1) was bound by exactly
 // that stream.
+//
+// STATUS: bit-exact against naive kernels on five shapes (tools/fused_fwd_probe.cu), but NOT on the product path: at cfg2 it
+// takes 0.44 ms against 0.41 ms for the separate encoder and decoder GEMMs.  TMEM holds acc1 (256 columns) and ONE acc2
+// (256 columns), so the decoder epilogue of a token tile (17 kcycles) cannot overlap the next tile's GEMM2s, and the
+// encoder-style epilogue (2.8 kcycles per 128 x 256 tile with 8 warps, no faster with 16) leaves the tensor pipe at 58 %
+// even with every store stubbed out (0.32 ms).  DESIGN.md section 8 has the measurements.
 #pragma once
 #include <cstdlib>
-#include "gemm_host.cuh"
-#include "epilogues.cuh"
-#include "ptx_cluster.cuh"
+#include "../sparse_vision_b200/csrc/gemm_host.cuh"
+#include "../sparse_vision_b200/csrc/epilogues.cuh"
+#include "../sparse_vision_b200/csrc/ptx_cluster.cuh"
 
 namespace svb {
 
@@ -354,14 +360,6 @@ inline int& fused_fwd_dbg() {
   return v;
 }
 #endif
-// SVB_FUSED_FWD=0 keeps the separate encoder and decoder GEMMs.
-inline bool fused_fwd_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("SVB_FUSED_FWD");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
 inline bool fused_fwd_supported(long long T, int C, int F, int max_ctas = 0) {
   const int sms = max_ctas > 0 ? max_ctas : device_sm_count();
   return C % 64 == 0 && C >= 64 && C <= 256 && F % 256 == 0 && F >= 256 && T > 0 && T < (1ll << 31) - 512 && sms >= 2;

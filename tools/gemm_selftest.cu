@@ -45,6 +45,7 @@ struct Case {
   bool bstat = false;     // B-stationary schedule (K <= 256)
   bool two_cta = false;   // cta_group::2 B-stationary kernel (gemm2_sm100.cuh)
   bool ones = false;      // EpiPartialOnes: also check the row sums of A from the extra ones column
+  bool two_stream = false;  // cta_group::2 STREAMING kernel (gemm2_stream_kernel): any K, split-K, either major-ness
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -65,7 +66,7 @@ static int run(const Case& c) {
   CK(cudaMalloc(&dB, Bh.size() * 2));
   CK(cudaMemcpy(dA, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, Bh.data(), Bh.size() * 2, cudaMemcpyHostToDevice));
-  const int splits = planned_splits<BN>(c.M, c.N, c.K, c.splits);
+  const int splits = c.two_stream ? planned_splits2(c.M, c.N, c.K, c.splits) : planned_splits<BN>(c.M, c.N, c.K, c.splits);
   CK(cudaMalloc(&dC, (size_t)splits * c.M * c.N * 4));
   CK(cudaMemset(dC, 0xFF, (size_t)splits * c.M * c.N * 4));
   int used = 0;
@@ -77,7 +78,8 @@ static int run(const Case& c) {
     ep.out = dC; ep.ld = c.N; ep.alpha = 1.0f; ep.out_bf16 = 1;
     if (make_store_tmap_bf16(&ep.tm, dC, c.M, c.N, c.N) == 0) ep.tm_valid = 1;
     else { printf("[%s] store tensor map failed\n", c.name); return 1; }
-    if (c.two_cta) {
+    if (c.two_stream) rc = launch_gemm2_stream<AMN, BMN, EpiStore>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
+    else if (c.two_cta) {
       if constexpr (!AMN) { rc = launch_gemm2_bstat<BMN, EpiStore>(0, dA, c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, ep); used = 1; }
       else { printf("[%s] the 2-CTA kernel needs a K-major A\n", c.name); return 1; }
     } else if (c.bstat) rc = launch_gemm<BN, AMN, BMN, EpiStore, true>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, 1, ep, &used);
@@ -93,6 +95,10 @@ static int run(const Case& c) {
    } else { printf("[%s] the ones column needs BLOCK_N=256\n", c.name); return 1; }
   } else {
     EpiPartial::Params ep{dC, c.N, (long long)c.M * c.N};
+    if (c.two_stream) {
+      if constexpr (BN == 256) rc = launch_gemm2_stream<AMN, BMN, EpiPartial>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep, &used);
+      else { printf("[%s] the 2-CTA kernels need BLOCK_N=256\n", c.name); return 1; }
+    } else
     rc = launch_gemm<BN, AMN, BMN, EpiPartial>(0, dA, AMN ? c.M : c.K, dB, BMN ? c.N : c.K, c.M, c.N, c.K, c.splits, ep,
                                                &used);
   }
@@ -185,6 +191,16 @@ static const Case kCases[] = {
     {"kk_2cta_k24_ntail", 5000, 200, 24, false, false, 256, 1, true, true, true},
     {"kmn_2cta", 3000, 768, 16, false, true, 256, 1, true, true, true},
     {"kk_2cta_mtail_odd", 128 * 7 + 3, 256, 16, false, false, 256, 1, true, true, true},
+    {"s2_kk_deepk", 256, 512, 2048, false, false, 256, 1, false, false, false, false, true},
+    {"s2_kk_mtail", 300, 256, 256, false, false, 256, 1, false, false, false, false, true},
+    {"s2_kk_many_tiles", 128 * 400 + 5, 256, 192, false, false, 256, 1, false, false, false, false, true},
+    {"s2_kk_ntail", 700, 200, 72, false, false, 256, 1, false, false, false, false, true},
+    {"s2_kmn_dE", 300, 512, 256, false, true, 256, 1, false, false, false, false, true},
+    {"s2_mnmn_splitk", 256, 512, 3000, true, true, 256, 3, false, false, false, false, true},
+    {"s2_mnmn_auto", 256, 2048, 6272, true, true, 256, 0, false, false, false, false, true},
+    {"s2_mnmn_tail", 200, 264, 1000, true, true, 256, 0, false, false, false, false, true},
+    {"s2_mnmn_m512", 512, 1024, 5000, true, true, 256, 0, false, false, false, false, true},
+    {"s2_kk_bf16_tma_many", 128 * 300 + 40, 512, 16, false, false, 256, 1, true, false, false, false, true},
     {"mnmn_ones_splitk", 256, 512, 3000, true, true, 256, 3, false, false, false, true},
     {"mnmn_ones_auto_tail", 200, 264, 1000, true, true, 256, 0, false, false, false, true},
     {"kk_ones", 300, 256, 192, false, false, 256, 1, false, false, false, true},
@@ -790,6 +806,53 @@ static int perf_dec() {
   CK(cudaMemset(bias, 0, N * 4));
   perf_dec_one<EpiStore>("EpiStore", dA, dB, dD, bias, M, N, K);
   perf_dec_one<EpiStorePad>("EpiStore padded", dA, dB, dD, bias, M, N, K);
+  {  // the same GEMM on SM pairs (streaming two-CTA kernel): each CTA loads half of every W_dec k-block
+    EpiStore::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = dD; ep.ld = N; ep.bias = bias; ep.alpha = 1.f; ep.relu = 0; ep.out_bf16 = 1;
+    if (make_store_tmap_bf16(&ep.tm, dD, M, N, N) == 0) ep.tm_valid = 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rev = 0; rev < 2; ++rev) {
+      for (int it = 0; it < 3; ++it) launch_gemm2_stream<false, false, EpiStore>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, false, false, rev);
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      for (int it = 0; it < 10; ++it) launch_gemm2_stream<false, false, EpiStore>(0, dA, K, dB, K, M, N, K, 1, ep, nullptr, 0, false, false, rev);
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ms /= 10;
+      printf("[perf dec 2-CTA streaming EpiStore stages=%d reverse_m=%d] %.3f ms  %.1f TFLOP/s  A stream %.1f GB/s\n",
+             Gemm2StreamCfg<EpiStore::kSmemBytes>::kStages, rev, ms, 2.0 * M * N * K / ms * 1e-9, (double)M * K * 2 / ms * 1e-6);
+    }
+  }
+  {  // dW_dec shape: DIFF^T [256 x T] * E [T x 2048], split-K, fp32 partials; single-CTA against pairs
+    const int M2 = 256, N2 = 2048, K2 = 200704;
+    float* dP;
+    CK(cudaMalloc(&dP, (size_t)16 * M2 * N2 * 4));
+    EpiPartial::Params ep{dP, N2, (long long)M2 * N2};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int two = 0; two < 2; ++two) {
+      int used = 0;
+      auto launch = [&]() {
+        if (two) launch_gemm2_stream<true, true, EpiPartial>(0, dD, M2, dA, N2, M2, N2, K2, 0, ep, &used);
+        else launch_gemm<256, true, true, EpiPartial>(0, dD, M2, dA, N2, M2, N2, K2, 0, ep, &used);
+      };
+      for (int it = 0; it < 3; ++it) launch();
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      for (int it = 0; it < 10; ++it) launch();
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ms /= 10;
+      printf("[perf dWdec %s splits=%d] %.3f ms  %.1f TFLOP/s  B stream %.1f GB/s\n", two ? "2-CTA streaming" : "1-CTA", used, ms,
+             2.0 * M2 * N2 * K2 / ms * 1e-9, (double)N2 * K2 * 2 / ms * 1e-6);
+    }
+  }
   return 0;
 }
 
