@@ -444,7 +444,7 @@ def ie_section(dev, peaks, n_images=64, iters=20, world=1):
     torch.cuda.synchronize()
     ms = job_ms(e0.elapsed_time(e1) / iters)
     out["node_ie_layer"] = {"ms": ms, "images_per_s": world * n_images / (ms * 1e-3),
-                            "what": "svb_node_ie_layer: enc + dec + g*W_dec GEMMs and 3 reductions, one layer"}
+                            "what": "svb_node_ie_layer, one layer: ONE fused kernel keeps a = relu(x W_enc^T + b) and G = g W_dec in TMEM and reduces |G (avg - a)| and sum_f a G on the spot (no [T,F] tensor is written, no decoder GEMM), + the neuron / error passes over [T,C]"}
     out["n_gpus"] = world
     out["config"] = {"workload": "configs[4] / mixed3a: C=256, F=2048, 28x28, %d images per call per GPU" % n_images,
                      "peak_source": peaks["source"] + ", hbm copy"}

@@ -169,4 +169,39 @@ static __global__ void ie_allchannels_tokens_kernel(const bf16* __restrict__ q, 
   }
 }
 
+// SAE-error node of the FUSED node-IE layer (fused_ie_sm100.cuh): the decoder output is never formed, because
+//   sum_c g[t,c] (err_avg[pos,c] - err[t,c]),  err = x - (a W_dec^T + b_dec)
+//     = sum_c g[t,c] (err_avg[pos,c] - x[t,c] + b_dec[c])  +  sum_f a[t,f] G[t,f]
+// and the fused kernel leaves the second sum as `nrows` partial rows qrows[r][t].  One warp per token, 8 tokens per block.
+static __global__ void ie_error_tokens_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ g,
+                                                    const float* __restrict__ avgT, const float* __restrict__ bias,
+                                                    const float* __restrict__ qrows, int nrows, long long Tn, int C, int HW,
+                                                    float* __restrict__ partial) {
+  __shared__ float s[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long t = blockIdx.x * 8LL + w;
+  float acc = 0.f;
+  if (t < Tn) {
+    const int hw = static_cast<int>(t % HW);
+    for (int c = lane * 8; c < C; c += 256) {
+      float xv[8], gv[8];
+      Vec16<bf16>::load(x + t * C + c, xv);
+      Vec16<bf16>::load(g + t * C + c, gv);
+      const float* m = avgT + static_cast<size_t>(hw) * C + c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += gv[k] * (__ldg(m + k) - xv[k] + __ldg(bias + c + k));
+    }
+    for (int r = lane; r < nrows; r += 32) acc += __ldg(qrows + static_cast<size_t>(r) * Tn + t);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s[w] = t < Tn ? fabsf(acc) : 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += s[k];
+    partial[blockIdx.x] = r;
+  }
+}
+
 }  // namespace svb

@@ -2,6 +2,7 @@
 // reductions of the C ABI (include/svb.h).
 #include "svb_common.cuh"
 #include "gemm2_sm100.cuh"
+#include "fused_ie_sm100.cuh"
 
 using namespace svb;
 
@@ -47,6 +48,10 @@ extern "C" int svb_set_tuning(int32_t key, int32_t value) {
   if (key < 0 || key >= kTuneCount) return fail(SVB_ERR_BAD_ARG, "unknown tuning key %d", key);
   tuning(key) = value;
   return 0;
+}
+extern "C" int svb_debug_trace(int32_t which, long long* device_buffer) {   // bring-up: wait-cycle trace of a fused kernel
+  if (which == 0) { fused_ie_trace_ptr() = device_buffer; return 0; }
+  return fail(SVB_ERR_BAD_ARG, "unknown trace %d", which);
 }
 extern "C" int32_t svb_get_tuning(int32_t key) { return (key < 0 || key >= kTuneCount) ? -1 : tuning(key); }
 
@@ -295,7 +300,9 @@ extern "C" int svb_ie_allchannels(svb_handle* h, void* stream, const void* err, 
   return 0;
 }
 
-// Node-IE for one layer: encoder GEMM, decoder GEMM, G = g W_dec GEMM, then the three reductions on bf16 tokens.
+// Node-IE for one layer.  C % 128 == 0, C <= 256: ONE fused kernel keeps a and G = g W_dec in TMEM and reduces them on the
+// spot (fused_ie_sm100.cuh), plus the two small [T, C] passes.  Other shapes: encoder GEMM, decoder GEMM, G = g W_dec GEMM,
+// then the three reductions on bf16 tokens.
 extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x, const void* grad,
                                  const svb_sae_params* p, const float* enc_avg, const float* err_avg,
                                  const float* x_avg, float scale, float* ie_features, float* ie_error,
@@ -314,14 +321,22 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   svb_acts gx = *x;
   gx.x = grad;
   const bool zx = acts_are_bf16_tokens(x), zg = acts_are_bf16_tokens(&gx);
-  bf16 *X = nullptr, *G = nullptr, *Web, *Wdb, *E, *GE, *DIFF;
-  float *fold, *avgT_f, *avgT_c, *avgT_e, *partial, *stage, *tokpart;
+  // Fused path (fused_ie_sm100.cuh): a and G stay in TMEM, no decoder GEMM; C % 128 == 0, C <= 256
+  const bool fused = tuning(kTuneFusedIe) != 0 && fused_ie_supported(T, C, F, h->sms);
+  const int ie_slots = fused ? fused_ie_slots(T, F, h->sms) : 0, q_rows = fused ? fused_ie_qrows(F) : 0;
+  bf16 *X = nullptr, *G = nullptr, *Web, *Wdb, *E = nullptr, *GE = nullptr, *DIFF = nullptr;
+  float *fold, *avgT_f = nullptr, *avgT_c, *avgT_e, *partial, *stage, *tokpart, *ie_part = nullptr, *q_part = nullptr;
   auto carve = [&](Arena& ar) {
     if (!zx) X = ar.take<bf16>(TC);
     if (!zg) G = ar.take<bf16>(TC);
     Web = ar.take<bf16>(FC); Wdb = ar.take<bf16>(FC); fold = ar.take<float>(F);
-    E = ar.take<bf16>(TF); GE = ar.take<bf16>(TF); DIFF = ar.take<bf16>(TC);
-    avgT_f = ar.take<float>(static_cast<size_t>(HW) * F);
+    if (fused) {
+      ie_part = ar.take<float>(static_cast<size_t>(2 * ie_slots) * F);
+      q_part = ar.take<float>(static_cast<size_t>(q_rows) * T);
+    } else {
+      E = ar.take<bf16>(TF); GE = ar.take<bf16>(TF); DIFF = ar.take<bf16>(TC);
+      avgT_f = ar.take<float>(static_cast<size_t>(HW) * F);
+    }
     avgT_c = ar.take<float>(static_cast<size_t>(HW) * C);
     avgT_e = ar.take<float>(static_cast<size_t>(HW) * C);
     partial = ar.take<float>(static_cast<size_t>(chunks_f > chunks_c ? chunks_f : chunks_c) * (F > C ? F : C));
@@ -340,10 +355,22 @@ extern "C" int svb_node_ie_layer(svb_handle* h, void* stream, const svb_acts* x,
   if (!zg) SVB_TRY(pack_acts(st, &gx, G));
   (prep_encoder_kernel<<<cdiv(F, 8), 256, 0, st>>>(p->w_enc, p->b_enc, p->b_dec, Web, fold, nullptr, F, C), svb::count_launch());
   (convert_kernel<float, bf16><<<grid_for(FC), 256, 0, st>>>(p->w_dec, Wdb, FC), svb::count_launch());
-  (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(enc_avg, avgT_f, F, HW), svb::count_launch());
+  if (!fused) (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(F, 32)), dim3(32, 8), 0, st>>>(enc_avg, avgT_f, F, HW), svb::count_launch());
   (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(x_avg, avgT_c, C, HW), svb::count_launch());
   (transpose_f32_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 32)), dim3(32, 8), 0, st>>>(err_avg, avgT_e, C, HW), svb::count_launch());
   SVB_LAUNCH_CHECK("node_ie prep");
+  if (fused) {
+    SVB_GEMM(launch_fused_node_ie(st, Xp, Gp, Web, Wdb, fold, enc_avg, Ti, C, F, HW, ie_part, q_part, h->sms), "fused node-IE");
+    if (ie_features) SVB_TRY(reduce_rows(st, ie_part, 2 * ie_slots, F, scale, stage, ie_features));
+    if (ie_neurons)
+      SVB_TRY(launch_ie_channelwise<bf16>(st, h->sms, Xp, Gp, avgT_c, T, HW, C, scale, partial, chunks_c, stage, ie_neurons));
+    if (ie_error) {
+      (ie_error_tokens_fused_kernel<<<tok_blocks, 256, 0, st>>>(Xp, Gp, avgT_e, p->b_dec, q_part, q_rows, T, C, HW, tokpart), svb::count_launch());
+      (reduce_flat_kernel<<<1, 1024, 0, st>>>(tokpart, static_cast<size_t>(tok_blocks), scale, ie_error), svb::count_launch());
+      SVB_LAUNCH_CHECK("ie_error (fused)");
+    }
+    return 0;
+  }
   // a = SAE_enc(x)
   EpiEnc::Params e1{};
   e1.bias = fold; e1.e_bf16 = E; e1.words = (F + 31) / 32;

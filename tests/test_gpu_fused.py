@@ -1,5 +1,5 @@
-"""The fused encoder backward (dE GEMM -> ReLU mask -> dW_enc GEMM in one kernel, single-CTA and SM-pair variants) and the
-SM-pair streaming GEMMs against the plain kernels and against the oracle's autograd gradients.
+"""The fused encoder backward (dE GEMM -> ReLU mask -> dW_enc GEMM in one kernel, single-CTA and SM-pair variants), the
+SM-pair streaming GEMMs and the fused node-IE layer against the plain kernels and against the oracle.
 
 svb_set_tuning (include/svb.h) selects the kernels at run time, so one process can run the same seeded step through every
 combination.  All variants round dPre' to bf16 in the same place, so their gradients differ only by fp32 summation order
@@ -15,14 +15,15 @@ from oracle import sae_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FUSED_BWD, FBW_2CTA, GEMM_PAIRS, ENC_2CTA, FBW_PREFETCH = range(5)
+FUSED_BWD, FBW_2CTA, GEMM_PAIRS, ENC_2CTA, FBW_PREFETCH, FUSED_IE = range(6)
 
 
 @contextlib.contextmanager
 def tuning(**kw):
     from sparse_vision_b200 import _lib as L
     lib = L.load()
-    keys = {"fused_bwd": FUSED_BWD, "fbw_2cta": FBW_2CTA, "pairs": GEMM_PAIRS, "enc_2cta": ENC_2CTA, "prefetch": FBW_PREFETCH}
+    keys = {"fused_bwd": FUSED_BWD, "fbw_2cta": FBW_2CTA, "pairs": GEMM_PAIRS, "enc_2cta": ENC_2CTA, "prefetch": FBW_PREFETCH,
+            "fused_ie": FUSED_IE}
     old = {k: lib.svb_get_tuning(keys[k]) for k in kw}
     try:
         for k, v in kw.items():
@@ -113,3 +114,42 @@ def test_fused_backward_gradients_vs_oracle_autograd(B, C, H, W, k):
     for key in O.SAE_MLP_KEYS:
         want = leaves[key].grad.numpy().reshape(-1)
         assert _fro(sg[key], want) <= 2e-2, f"{key}: {_fro(sg[key], want)}"
+
+
+@pytest.mark.parametrize("B,C,H,W,k", [
+    (5, 256, 28, 28, 8),     # the cfg5 / mixed3a layer shape: F = 2048, 16-byte loads of the running average
+    (9, 128, 7, 7, 4),       # 7x7 maps: HW % 4 != 0 (scalar loads of the average), 441 tokens (token tail)
+    (3, 256, 14, 14, 3),     # F = 768: three pair tiles, several slots
+])
+def test_fused_node_ie_layer_vs_oracle_and_unfused(B, C, H, W, k):
+    """svb_node_ie_layer with a and G = g W_dec kept in TMEM (fused_ie_sm100.cuh) against the oracle
+    (compute_ie.py:420-453, utils.py:2574-2637) and against the GEMM + reduction path; identical top-k feature sets."""
+    from sparse_vision_b200 import ops
+    torch.manual_seed(0)
+    p = O.init_sae_mlp(C, k)
+    F = C * k
+    p["decoder.bias"].normal_(0, 0.05, generator=torch.Generator().manual_seed(2))
+    gen = torch.Generator().manual_seed(77)
+    x = torch.relu(torch.randn(B, C, H, W, generator=gen)).bfloat16().float()
+    g = (torch.randn(B, C, H, W, generator=gen) * 0.1).bfloat16().float()
+    # plant a margin between the leading features so that the top-k sets do not depend on bf16 rounding
+    lead = torch.randperm(F, generator=gen)[:5]
+    for r, f in enumerate(lead):
+        p["encoder.weight"][f] *= 3.0 + 0.6 * r
+    enc_avg = torch.rand(F, H, W, generator=gen)
+    err_avg = torch.randn(C, H, W, generator=gen) * 0.05
+    x_avg = x.mean(0)
+    params = [p[key].clone().cuda() for key in O.SAE_MLP_KEYS]
+    args = (x.cuda().bfloat16().contiguous(memory_format=torch.channels_last),
+            g.cuda().bfloat16().contiguous(memory_format=torch.channels_last), params, enc_avg.cuda(), err_avg.cuda(), x_avg.cuda())
+    with tuning(fused_ie=1):
+        feat, err, neur = [t.float().cpu() for t in ops.node_ie_layer(*args)]
+    with tuning(fused_ie=0):
+        feat0, err0, neur0 = [t.float().cpu() for t in ops.node_ie_layer(*args)]
+    rf, re, rn = O.node_ie_layer(p, x, g, enc_avg, err_avg, x_avg)
+    assert (feat - rf).abs().max() <= 2e-2 * rf.abs().max() and (feat0 - rf).abs().max() <= 2e-2 * rf.abs().max()
+    assert (feat - feat0).abs().max() <= 2e-2 * rf.abs().max()
+    assert abs(float(err) - float(re)) <= 1e-2 * abs(float(re)) and abs(float(err0) - float(re)) <= 1e-2 * abs(float(re))
+    assert (neur - rn).abs().max() <= 1e-2 * rn.abs().max() and torch.equal(neur, neur0)
+    top = set(torch.topk(rf, 5).indices.tolist())
+    assert set(torch.topk(feat, 5).indices.tolist()) == top == set(torch.topk(feat0, 5).indices.tolist())
