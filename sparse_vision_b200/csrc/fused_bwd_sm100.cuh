@@ -242,10 +242,12 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       uint32_t pk[2][16];
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
+        // lane l holds the mask word of token l (bit f = feature f of this warp): transposed, this lane's word has
+        // bit j = token j of its own feature
+        const uint32_t tw = transpose_bits32(mw[ci], lane);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const uint32_t wj = __shfl_sync(0xffffffffu, mw[ci], j);
-          const float x = ((wj >> lane) & 1u) ? v[ci][j] + p.l1c : 0.f;
+          const float x = (tw & (1u << j)) ? v[ci][j] + p.l1c : 0.f;
           v[ci][j] = x;
           csum += x;
         }
@@ -482,10 +484,12 @@ fused_bwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       uint32_t pk[2][16];
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
+        // lane l holds the mask word of token l (bit f = feature f of this warp): transposed, this lane's word has
+        // bit j = token j of its own feature
+        const uint32_t tw = transpose_bits32(mw[ci], lane);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const uint32_t wj = __shfl_sync(0xffffffffu, mw[ci], j);
-          const float x = ((wj >> lane) & 1u) ? v[ci][j] + p.l1c : 0.f;
+          const float x = (tw & (1u << j)) ? v[ci][j] + p.l1c : 0.f;
           v[ci][j] = x;
           csum += x;
         }
