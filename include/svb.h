@@ -70,7 +70,8 @@ enum svb_tuning_key {
   SVB_TUNE_GEMM_PAIRS = 2,   /* 1: streaming GEMMs with more than one 128-row tile run on SM pairs                 (SVB_GEMM2) */
   SVB_TUNE_ENC_2CTA = 3,     /* 1: B-stationary encoder GEMM on SM pairs (default 0: measured slower)             (SVB_ENC_2CTA) */
   SVB_TUNE_FBW_PREFETCH = 4, /* L2 prefetch distance (token blocks) of the fused backward, default 0              (SVB_FBW_PF) */
-  SVB_TUNE_FUSED_IE = 5      /* 1: svb_node_ie_layer keeps a and G = g W_dec in TMEM (one kernel) when C % 128 == 0, C <= 256 (SVB_FUSED_IE) */
+  SVB_TUNE_FUSED_IE = 5,     /* 1: svb_node_ie_layer keeps a and G = g W_dec in TMEM (one kernel) when C % 128 == 0, C <= 256 (SVB_FUSED_IE) */
+  SVB_TUNE_ENC16 = 6         /* 1: the B-stationary encoder GEMM (C <= 256) runs 16 epilogue warps instead of 8 (default 0: measured 0.221 against 0.212 ms, the staging costs an operand stage) (SVB_ENC16) */
 };
 int svb_set_tuning(int32_t key, int32_t value);
 /* Bring-up aid: which = 0 makes the fused node-IE kernel write the cycles its roles spend waiting into device_buffer

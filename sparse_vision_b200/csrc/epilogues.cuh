@@ -315,7 +315,10 @@ struct EpiStore {
 // from by mask_to_activity_kernel) and sum|e| partials (sparse_loss.py:41).
 // API = true additionally offers fp32 stores of e / pre (svb_sae_forward); the training step instantiates API = false.
 // NBUF > 1: rotating chunk staging (ChunkWriterN) for the two-CTA encoder GEMM.
-template <bool API, int NBUF = 1>
+// WARPS = 16: four epilogue warps per TMEM lane quarter, two chunks each.  The epilogue is ~260 instructions per 32 x 32
+// chunk and with two warps per scheduler it issues only half of the cycles (ncu: issue active 50 %, stalls = fixed-latency
+// waits and scoreboards), which is what bounds the K = 256 encoder GEMM (4.5 kcycles per tile for 1 kcycle of MMA).
+template <bool API, int NBUF = 1, int WARPS = 8>
 struct EpiEncT {
   using Writer = typename std::conditional<NBUF == 1, ChunkWriter, ChunkWriterN<NBUF>>::type;
   struct Params {
@@ -329,7 +332,7 @@ struct EpiEncT {
     int words;                     // ceil(N/32)
     int e_slab;                    // e_bf16 / tm_e are slab-major (gemm_host.cuh)
   };
-  static constexpr int kWarps = 8;
+  static constexpr int kWarps = WARPS;
   static constexpr int kColVecs = 1;
   static constexpr bool kPrefetchAcc = true;
   static constexpr uint32_t kSmemBytes = Writer::bytes(kWarps) + 2 * 256 * sizeof(float);
@@ -410,6 +413,8 @@ struct EpiEncT {
       uint32_t* dst = p.mask_words + mask_index(row, w0, g.M);
       if (nw == 4) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+      } else if (nw == 2 && cpw == 2) {   // 16 warps: a warp's two words are 8 contiguous, 8-byte aligned bytes
+        *reinterpret_cast<uint2*>(dst) = make_uint2(words[0], words[1]);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -428,6 +433,7 @@ struct EpiEncT {
 };
 typedef EpiEncT<false> EpiEnc;     // training step
 typedef EpiEncT<false, 4> EpiEnc4; // training step, two-CTA GEMM: 4 rotating chunk tiles per warp
+typedef EpiEncT<false, 1, 16> EpiEnc16;  // training step, B-stationary GEMM with 16 epilogue warps
 typedef EpiEncT<true> EpiEncApi;   // svb_sae_forward (optional fp32 e / pre outputs)
 
 // ------------------------------------------------------------------------------------------------ decoder

@@ -18,15 +18,15 @@ inline unsigned long long& launch_counter() {
 inline void count_launch() { ++launch_counter(); }
 
 // Process-wide kernel-selection switches (svb_set_tuning / svb_get_tuning in svb.h; keys = SVB_TUNE_* there).  Defaults
-// come from the environment once: SVB_FUSED_BWD, SVB_FBW_2CTA, SVB_GEMM2, SVB_ENC_2CTA, SVB_FBW_PF, SVB_FUSED_IE.  They exist for A/B
+// come from the environment once: SVB_FUSED_BWD, SVB_FBW_2CTA, SVB_GEMM2, SVB_ENC_2CTA, SVB_FBW_PF, SVB_FUSED_IE, SVB_ENC16.  They exist for A/B
 // measurements and for the tests that pin the fused kernels against the un-fused path; results agree within the
 // parity tolerances whatever their values.
-enum { kTuneFusedBwd = 0, kTuneFbwTwoCta = 1, kTuneGemmPairs = 2, kTuneEncTwoCta = 3, kTuneFbwPrefetch = 4, kTuneFusedIe = 5, kTuneCount = 6 };
+enum { kTuneFusedBwd = 0, kTuneFbwTwoCta = 1, kTuneGemmPairs = 2, kTuneEncTwoCta = 3, kTuneFbwPrefetch = 4, kTuneFusedIe = 5, kTuneEnc16 = 6, kTuneCount = 7 };
 inline int& tuning(int key) {
   static int v[kTuneCount];
   static const bool init = [] {
-    const char* names[kTuneCount] = {"SVB_FUSED_BWD", "SVB_FBW_2CTA", "SVB_GEMM2", "SVB_ENC_2CTA", "SVB_FBW_PF", "SVB_FUSED_IE"};
-    const int defaults[kTuneCount] = {1, 1, 1, 0, 0, 1};
+    const char* names[kTuneCount] = {"SVB_FUSED_BWD", "SVB_FBW_2CTA", "SVB_GEMM2", "SVB_ENC_2CTA", "SVB_FBW_PF", "SVB_FUSED_IE", "SVB_ENC16"};
+    const int defaults[kTuneCount] = {1, 1, 1, 0, 0, 1, 0};
     for (int i = 0; i < kTuneCount; ++i) {
       const char* e = getenv(names[i]);
       v[i] = e ? atoi(e) : defaults[i];

@@ -83,8 +83,8 @@ void carve(Arena& a, SaePlan& p, const svb_acts* x, int F, bool train, int sms) 
   // cleared by the step prologue: activity bits and the per-(CTA, warp) loss partials (contiguous on purpose)
   const size_t z0 = a.off;
   p.act_bits = a.take<uint32_t>(static_cast<size_t>(p.n_img) * p.words);
-  p.l1_part = a.take<float>(static_cast<size_t>(sms) * 8);
-  p.sq_part = a.take<float>(static_cast<size_t>(sms) * 8);
+  p.l1_part = a.take<float>(static_cast<size_t>(sms) * 16);   // one per CTA and epilogue warp (8 or 16 of them)
+  p.sq_part = a.take<float>(static_cast<size_t>(sms) * 16);
   p.zero_words = (a.off - z0) / 4;
   p.bstat = p.C <= 256 && p.tn_f <= sms;
   p.stage = a.take<float>(static_cast<size_t>(32) * (F > p.C ? F : p.C));
@@ -246,6 +246,14 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
     e14.tm_e = e1.tm_e; e14.bias = e1.bias; e14.e_bf16 = e1.e_bf16; e14.l1_partial = e1.l1_partial;
     e14.mask_words = e1.mask_words; e14.words = e1.words; e14.e_slab = e1.e_slab;
     SVB_GEMM((launch_gemm2_bstat<false, EpiEnc4>(st, X, C, pl.Web, C, T, F, C, e14, pl.xs, pl.sms)), "enc (two-CTA B-stationary)");
+  } else if (pl.bstat && tuning(kTuneEnc16) != 0) {
+    // 16 epilogue warps (off by default): the epilogue (~260 instructions per 32 x 32 chunk) bounds this GEMM and two
+    // warps per scheduler issue only half of the cycles, but 32 KB of staging leave four operand stages instead of five
+    // and the variant measured 0.221 against 0.212 ms
+    EpiEnc16::Params e16{};
+    e16.tm_e = e1.tm_e; e16.bias = e1.bias; e16.e_bf16 = e1.e_bf16; e16.l1_partial = e1.l1_partial;
+    e16.mask_words = e1.mask_words; e16.words = e1.words; e16.e_slab = e1.e_slab;
+    SVB_GEMM((launch_gemm<256, false, false, EpiEnc16, true>(st, X, C, pl.Web, C, T, F, C, 1, e16, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary, 16 epilogue warps)");
   } else if (pl.bstat) {
     SVB_GEMM((launch_gemm<256, false, false, EpiEnc, true>(st, X, C, pl.Web, C, T, F, C, 1, e1, nullptr, 0, 0, pl.xs, false, kAPrefetch)), "enc (B-stationary)");
   } else {
@@ -334,8 +342,8 @@ extern "C" int svb_sae_step_grads(svb_handle* h, void* stream, const svb_acts* x
   // the one-block tail (decoder-bias gradient, loss sums, per-channel statistics) needs nothing from the dW_dec GEMM
   TailArgs ta{};
   ta.chan = pl.chan; ta.vm = pl.vm; ta.vm_chunks = kVmChunks; ta.g_bdec = flat + pl.o_gbd; ta.s = s;
-  ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 8;
-  ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 8;
+  ta.sq_part = pl.sq_part; ta.n_sq = pl.sms * 16;
+  ta.l1_part = pl.l1_part; ta.n_l1 = pl.sms * 16;
   ta.nact_f = pl.nact_f; ta.n_img = static_cast<int>(pl.n_img);
   ta.var_part = pl.var_part; ta.n_var_part = pl.fused_dec ? cdiv(C, 32) : cdiv(C, 8);
   ta.rowvar = pl.rowvar; ta.n_rows = pl.hw == 1 ? pl.T : 0;

@@ -367,7 +367,7 @@ def test_tuning_keys_round_trip():
     from sparse_vision_b200 import _lib as L
     lib = L.load()
     assert lib.svb_get_tuning(99) == -1 and lib.svb_set_tuning(99, 1) != 0
-    for key in range(6):
+    for key in range(7):
         old = lib.svb_get_tuning(key)
         assert lib.svb_set_tuning(key, old + 1) == 0 and lib.svb_get_tuning(key) == old + 1
         lib.svb_set_tuning(key, old)
