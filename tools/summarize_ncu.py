@@ -11,7 +11,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PHASE = {"EpiEncT": "enc_gemm", "EpiDecNchw": "dec_gemm", "EpiDec": "dec_gemm", "EpiDPreT": "dE_gemm"}
+PHASE = {"EpiEncT": "enc_gemm", "EpiDecNchw": "dec_gemm", "EpiDec": "dec_gemm", "EpiDPreT": "dE_gemm",
+         "fused_bwd": "dE+dWenc_fused_gemm", "EpiPartialOnes": "dWenc_gemm", "EpiPartial": "dWdec_gemm"}
 
 
 def main():
@@ -40,7 +41,10 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rr[0], rr[1], rr[2:]
-    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -56,8 +60,8 @@ def main():
             seen["dW"] += 1
             lab = "dWenc_gemm" if seen["dW"] == 1 else "dWdec_gemm"   # the encoder-side weight gradient runs first
         labels.append(lab)
-    md = [f"# {tag} — `ncu --set full --clock-control none` of the five GEMM launches of one training step", "",
-          f"Command: `ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 15 -c 5 {os.environ.get('SVB_NCU_CMD', 'python bench.py --steps 3 --warmup 3')}` (report: `{os.path.basename(rep)}`).",
+    md = [f"# {tag} — `ncu --set full --clock-control none` of the tensor-core launches of one training step", "",
+          f"Command: `ncu --set full --clock-control none --import-source on -k regex:\"gemm|fused_bwd\" --launch-skip <3 steps> --launch-count <1 step> {os.environ.get('SVB_NCU_CMD', 'python bench.py --steps 3 --warmup 3')}` (report: `{os.path.basename(rep)}`).",
           "", "| metric | " + " | ".join(labels) + " |", "|---|" + "---|" * len(labels)]
     traffic = {}
     for w in want:
