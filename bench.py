@@ -686,6 +686,34 @@ def run_svb(args):
     ms_step = ms_total / args.steps
     value = g_tokens / (ms_step * 1e-3)
 
+    # ---------------------------------------------------------------- strong scaling (N > 1): the SAME global batch of B images
+    # split across the ranks (report both); small shards under-fill the GPUs, so this is the harder number
+    strong = None
+    if world > 1 and "strong" not in skip and B % world == 0:
+        Bs = B // world
+        xs_strong = [t[:Bs].contiguous(memory_format=torch.channels_last) if args.acts_format == "channels_last"
+                     else t[:Bs].contiguous() for t in xdev]
+        gi, gt = B, T
+
+        def strong_step(x):
+            step_no[0] += 1
+            return dp.step(x, params, ms_, vs_, step_no[0], LR, LAMBDA, EXPANSION, "constrained_adam", (0.9, 0.999), gi, gt,
+                           want_dec=True)
+        for i in range(max(args.warmup, 3)):
+            strong_step(xs_strong[i % 2])
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(args.steps):
+            strong_step(xs_strong[i % 2])
+        q1.record()
+        barrier()
+        (ms_strong,) = job_max(q0.elapsed_time(q1))
+        strong = {"scaling": "strong", "global_batch_images": B, "images_per_gpu": Bs, "ms_per_step": ms_strong / args.steps,
+                  "value": T / (ms_strong / args.steps * 1e-3), "unit": UNIT,
+                  "note": "same global batch as the N = 1 run, sharded by image; value = global tokens / max-over-ranks step time"}
+        del xs_strong
+
     # ---------------------------------------------------------------- sustained leg: seconds of back-to-back steps
     sustained = None
     if "sustained" not in skip and args.sustain_s > 0:
@@ -845,6 +873,8 @@ def run_svb(args):
             "clocks": clocks,
             "final_step_stats": {k: last_stats[k] for k in ("loss", "rec", "l1", "n_dead")},
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
         if e2e is not None:
             line["e2e"] = e2e
         if other_fmt is not None:
@@ -907,7 +937,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained leg in seconds (0: skip)")
     ap.add_argument("--skip", default="", help="comma-separated sections to skip: sustained,e2e,gated,ie,ie_pipeline,"
-                                               "gpu_eager,cpu,dp_parity,other_format")
+                                               "gpu_eager,cpu,dp_parity,other_format,strong")
     ap.add_argument("--acts-format", default="channels_last", choices=["nchw", "channels_last"],
                     help="memory format of the resident activations of the `value` leg")
     ap.add_argument("--no-graph", action="store_true",

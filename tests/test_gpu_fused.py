@@ -75,6 +75,9 @@ def _fro(a, b):
     (4, 64, 12, 12, 4, True),     # C = 64: single-CTA kernel (C % 128 != 0)
     (3, 192, 10, 10, 4, False),   # C = 192: single-CTA kernel, three k-blocks
     (2, 256, 28, 28, 8, True),    # the cfg2 layer shape at a small batch
+    (1, 128, 5, 5, 3, False),     # 25 tokens (less than one block, one slot), F = 384: the second CTA of the last pair is half empty
+    (1, 256, 6, 6, 1, True),      # F = 256 = C (expansion 1): one pair tile, 36 tokens
+    (7, 64, 3, 3, 12, False),     # 63 tokens, single-CTA kernel with six feature tiles
 ])
 def test_fused_backward_and_pair_gemms_match_the_plain_kernels(B, C, H, W, k, channels_last):
     p, x, xg = _setup(B, C, H, W, k, channels_last)
@@ -153,3 +156,24 @@ def test_fused_node_ie_layer_vs_oracle_and_unfused(B, C, H, W, k):
     assert (neur - rn).abs().max() <= 1e-2 * rn.abs().max() and torch.equal(neur, neur0)
     top = set(torch.topk(rf, 5).indices.tolist())
     assert set(torch.topk(feat, 5).indices.tolist()) == top == set(torch.topk(feat0, 5).indices.tolist())
+
+
+def test_fused_backward_on_plain_token_matrices():
+    """cfg1-style 2-D activations [T, C] (no image structure, hw = 1): the fused backward reads them in place."""
+    from sparse_vision_b200 import ops
+    T, C, k, lam = 300, 256, 4, 5.0
+    torch.manual_seed(0)
+    p = O.init_sae_mlp(C, k)
+    x = torch.relu(torch.randn(T, C, generator=torch.Generator().manual_seed(5))).bfloat16().float()
+    xg = x.cuda().bfloat16()
+    with tuning(fused_bwd=0, pairs=0):
+        base, fl0 = _flat_grads(xg, p, lam)
+    got, fl1 = _flat_grads(xg, p, lam)
+    assert fl0 & 1 == 0 and fl1 & 1 == 1
+    sb, sg = _sections(base, C, C * k), _sections(got, C, C * k)
+    for key in ("encoder.weight", "encoder.bias", "decoder.weight", "decoder.bias"):
+        assert _fro(sg[key], sb[key]) <= 2e-3, key
+    leaves = {key: p[key].clone().requires_grad_(True) for key in O.SAE_MLP_KEYS}
+    O.sae_inference_and_loss("sae_mlp", leaves, x, lam)[0].backward()
+    for key in O.SAE_MLP_KEYS:
+        assert _fro(sg[key], leaves[key].grad.numpy().reshape(-1)) <= 2e-2, key
