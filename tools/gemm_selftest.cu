@@ -342,12 +342,10 @@ static int perf_enc_variants() {
            s0 / n / 1e3, s1 / nl / 1e3, s2 / nl / 1e3, s3 / n / 1e3, ms * 1.965e6 / 1e3);
     cudaFree(tr);
   };
-  for (int variant : {0, 4}) {
-    for (int slab = 0; slab < 2; ++slab) {
-      run(TypeTag<EpiEnc>{}, false, variant, slab);
-      run(TypeTag<EpiEnc>{}, true, variant, slab);
-      run(TypeTag<EpiEnc4>{}, true, variant, slab);
-    }
+  for (int variant : {0, 2, 3, 4}) {
+    run(TypeTag<EpiEnc>{}, false, variant, true);
+    run(TypeTag<EpiEnc>{}, true, variant, true);
+    run(TypeTag<EpiEnc4>{}, true, variant, true);
   }
   return 0;
 }
