@@ -27,7 +27,7 @@ def main():
         if m:
             fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()[:110]
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m and fn:
             op = m.group(1)
             total[op] += 1
