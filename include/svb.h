@@ -74,9 +74,6 @@ enum svb_tuning_key {
   SVB_TUNE_ENC16 = 6         /* 1: the B-stationary encoder GEMM (C <= 256) runs 16 epilogue warps instead of 8 (default 0: measured 0.221 against 0.212 ms, the staging costs an operand stage) (SVB_ENC16) */
 };
 int svb_set_tuning(int32_t key, int32_t value);
-/* Bring-up aid: which = 0 makes the fused node-IE kernel write the cycles its roles spend waiting into device_buffer
- * ([grid][8] int64; NULL switches it off). */
-int svb_debug_trace(int32_t which, long long* device_buffer);
 int32_t svb_get_tuning(int32_t key);
 
 /* Per-phase timing of the SaeMLP training step with CUDA events recorded on the caller's stream between the phases

@@ -79,7 +79,6 @@ SYMBOLS = {
     "svb_last_step_flags": (C.c_int32, [_vp]),
     "svb_set_tuning": (C.c_int, [C.c_int32, C.c_int32]),
     "svb_get_tuning": (C.c_int32, [C.c_int32]),
-    "svb_debug_trace": (C.c_int, [C.c_int32, _vp]),
     "svb_profile_enable": (C.c_int, [_vp, C.c_int32]),
     "svb_profile_read": (C.c_int, [_vp, C.c_int32, _P(C.c_float), _P(C.c_int32), _P(C.c_int32)]),
     "svb_profile_phase_name": (C.c_char_p, [C.c_int32]),

@@ -31,9 +31,17 @@ struct FusedIeParams {
   const float* avg;        // [F, HW] fp32: running average of the encoder output (the reference's own layout)
   float* ie_part;          // [2 * slots][F]: sum_t |G (avg - a)| per slot and token half
   float* q_part;           // [tiles_f * 8][T]: sum over the warp's 32 features of a * G, row = (pair tile * 2 + rank) * 4 + lane quarter
-  long long* trace;        // bring-up: [grid][8] wait cycles (null: off)
+#ifdef SVB_FIE_TRACE
+  long long* trace;        // bring-up only: [grid][8] cycles spent waiting
+#endif
 };
+#ifdef SVB_FIE_TRACE
 #define FIE_WAIT(slot_, call) do { const long long t0_ = clock64(); call; tr[slot_] += clock64() - t0_; } while (0)
+#define FIE_TRACE_DECL long long tr[8] = {0}
+#else
+#define FIE_WAIT(slot_, call) call
+#define FIE_TRACE_DECL
+#endif
 
 namespace fie {
 constexpr int kUnits = 8;                          // ring of 8 KB k-blocks: [64 tokens][64 channels]
@@ -99,7 +107,7 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
         for (int j = 0; j < 2; ++j) tma2_load_2d(Wds + kb * 16384 + j * 8192, &tmWd, w_full_l, f0 + 64 * j, kb * 64);   // W_dec [C, F], box 64 x 64
       }
       uint32_t stage = 0, phase = 0;
-      long long tr[8] = {0};
+      FIE_TRACE_DECL;
       for (int i = 0; i < n; ++i) {
         const int t0 = (slot + i * p.slots) * 128 + static_cast<int>(rank) * 64;   // this CTA's 64 tokens of the block
         for (int op = 0; op < 2; ++op) {                                            // x k-blocks, then g k-blocks
@@ -111,7 +119,9 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
           }
         }
       }
+#ifdef SVB_FIE_TRACE
       if (p.trace) p.trace[blockIdx.x * 8 + 0] = tr[0];
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
@@ -119,7 +129,7 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
       constexpr uint32_t idesc_a = make_idesc_bf16(256, 128, false, false);
       constexpr uint32_t idesc_g = make_idesc_bf16(256, 128, true, false);
       uint32_t stage = 0, phase = 0;
-      long long tr[8] = {0};
+      FIE_TRACE_DECL;
       mbar_wait(&bar->w_full, 0);
       for (int i = 0; i < n; ++i) {
         const int a = i & 1;
@@ -145,7 +155,9 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
         }
         umma2_commit_both(&bar->acc_full[a]);
       }
+#ifdef SVB_FIE_TRACE
       if (p.trace) { p.trace[blockIdx.x * 8 + 1] = tr[1]; p.trace[blockIdx.x * 8 + 2] = tr[2]; }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 4 lane quarters x 2 token halves, both CTAs
@@ -171,8 +183,10 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float ie = 0.f;
+#ifdef SVB_FIE_TRACE
     long long tr[8] = {0};
     const long long tr_start = clock64();
+#endif
     if (n > 0) fetch_avg(static_cast<long long>(slot) * 128 + h * 64);
     for (int i = 0; i < n; ++i) {
       const int a = i & 1;
@@ -221,10 +235,12 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
         if (t0 + lane < p.T) q_row[t0 + lane] = q[0];
       }
     }
+#ifdef SVB_FIE_TRACE
     if (p.trace && ew == 0 && lane == 0) {
       for (int q_ = 3; q_ < 6; ++q_) p.trace[blockIdx.x * 8 + q_] = tr[q_];
       p.trace[blockIdx.x * 8 + 6] = clock64() - tr_start;
     }
+#endif
     if (f_ok) p.ie_part[static_cast<size_t>(2 * slot + h) * p.F + f] = ie;
   }
 
@@ -234,10 +250,12 @@ fused_node_ie_kernel(const __grid_constant__ CUtensorMap tmWe, const __grid_cons
   if (warp == 1) tmem2_dealloc(tmem_base, 512);
 }
 
-inline long long*& fused_ie_trace_ptr() {   // bring-up: device buffer [grid][8] of wait cycles (svb_debug_trace)
+#ifdef SVB_FIE_TRACE
+inline long long*& fused_ie_trace_ptr() {   // bring-up: device buffer [grid][8] of wait cycles
   static long long* p = nullptr;
   return p;
 }
+#endif
 inline int fused_ie_slots(long long T, int F, int max_ctas = 0) {
   const int pairs = (max_ctas > 0 ? max_ctas : device_sm_count()) / 2;
   const int tiles_f = (F + 255) / 256;
@@ -268,7 +286,9 @@ inline int launch_fused_node_ie(cudaStream_t stream, const void* x, const void* 
   p.tiles_f = (F + 255) / 256;
   p.slots = fused_ie_slots(T, F, max_ctas);
   p.fold = fold; p.avg = avg; p.ie_part = ie_part; p.q_part = q_part;
+#ifdef SVB_FIE_TRACE
   p.trace = fused_ie_trace_ptr();
+#endif
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (dev < 0 || dev >= kMaxDevices) return -4;

@@ -49,10 +49,6 @@ extern "C" int svb_set_tuning(int32_t key, int32_t value) {
   tuning(key) = value;
   return 0;
 }
-extern "C" int svb_debug_trace(int32_t which, long long* device_buffer) {   // bring-up: wait-cycle trace of a fused kernel
-  if (which == 0) { fused_ie_trace_ptr() = device_buffer; return 0; }
-  return fail(SVB_ERR_BAD_ARG, "unknown trace %d", which);
-}
 extern "C" int32_t svb_get_tuning(int32_t key) { return (key < 0 || key >= kTuneCount) ? -1 : tuning(key); }
 
 // ---------------------------------------------------------------------------------------------------- profiling

@@ -37,15 +37,3 @@ for fmt in ("nchw", "channels_last"):
         print(f"node_ie_layer {fmt:13s} fused={fused}: {ms:.4f} ms per 64-image layer = {B / ms * 1e3:.0f} images/s")
 lib.svb_set_tuning(5, 1)
 
-# wait-cycle trace of the fused kernel (one call)
-import ctypes  # noqa: E402
-tr = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
-lib.svb_debug_trace(0, ctypes.c_void_p(tr.data_ptr()))
-ops.node_ie_layer(x.contiguous(memory_format=torch.channels_last), gr.contiguous(memory_format=torch.channels_last), params, avg,
-                  err_avg, x_avg)
-torch.cuda.synchronize()
-lib.svb_debug_trace(0, None)
-t = tr.view(148, 8)[:144].double()
-names = ["prod:ring_empty", "mma:acc_empty", "mma:ring_full", "epi:acc_full", "epi:avg_wait", "epi:tmem_ld_wait", "epi:total"]
-lead = t[0::2]
-print("mean kcycles per CTA:", {n: round(float((lead if n.startswith("mma") else t)[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)})
