@@ -351,6 +351,30 @@ def gated_section(dev, peaks, n_images=256, iters=10, world=1):
     ms = float(t[0])
     tf = 12.0 * Cc * F * T / (ms * 1e-3) / 1e12          # per GPU
     sc = res.scalars()
+    strong = None
+    if dp is not None and n_images % world == 0:
+        # strong scaling (cfg3 weak AND strong): the same 256-image batch sharded across the ranks
+        ns = n_images // world
+        xss = [x[:ns].contiguous() for x in xs]
+        no = [4 + 2 * iters]
+
+        def sstep(i):
+            no[0] += 1
+            return dp.step(xss[i % 2], params, ms_, vs_, no[0], LR, 0.1, k, "constrained_adam", (0.9, 0.999), n_images, T,
+                           want_dec=True)
+        for i in range(3):
+            sstep(i)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(iters):
+            sstep(i)
+        q1.record()
+        barrier()
+        ts = torch.tensor([q0.elapsed_time(q1) / iters], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "global_batch_images": n_images, "images_per_gpu": ns, "ms_per_step": float(ts[0]),
+                  "act_vec_per_s": T / (float(ts[0]) * 1e-3)}
     if dp is not None:
         dp.check()
     return {"workload": f"configs[2]: GatedSae C=512 14x14 k=16 F=8192, 256 images = 50176 tokens per GPU, "
@@ -358,7 +382,7 @@ def gated_section(dev, peaks, n_images=256, iters=10, world=1):
             "n_gpus": world, "ms_per_step": ms, "act_vec_per_s": world * T / (ms * 1e-3), "algorithmic_tflops_per_gpu": tf,
             "frac_of_burst_peak": tf / peaks["bf16_burst"] if peaks["bf16_burst"] else None,
             "frac_of_sustained_peak": tf / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
-            "phases_ms": phases,
+            "phases_ms": phases, "strong_scaling": strong,
             "final_step_stats": {kk: sc[kk] for kk in ("loss", "rec", "l1", "aux")}}
 
 
