@@ -519,11 +519,15 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
     avg, _ = timed(lambda: ie.compute_average([b[0] for b in batches]))          # warm-up (cuDNN autotune, arena)
     # one full untimed pass: on a fresh box the first process pays cuDNN's lazy kernel loading for the backward of every
     # layer shape somewhere inside the first complete pass (measured: 38-86 ms per batch in a first pass, 10 ms afterwards)
-    _, ms_ie_first = timed(lambda: ie.compute_node_ie(batches, avg))
+    # Two full untimed passes: right after torch.cuda.empty_cache() the caching allocator is cold, and the first passes pay
+    # cudaMalloc for every activation / gradient size of the base model's backward (measured on fresh boxes: 164 and 62 ms
+    # per batch for the first two passes, 10.0 ms from the third on)
+    warm = [timed(lambda: ie.compute_node_ie(batches, avg))[1] for _ in range(2)]
+    ms_ie_first = warm[0]
     avg, ms_avg = timed(lambda: ie.compute_average([b[0] for b in batches]))
     passes = [timed(lambda: ie.compute_node_ie(batches, avg)) for _ in range(3)]
     (feat, err, neur), _ = passes[-1]
-    ms_ie = sum(p[1] for p in passes) / len(passes)      # mean of three timed passes after one full untimed pass
+    ms_ie = sum(p[1] for p in passes) / len(passes)      # mean of three timed passes
     n_job = world * n_images * n_batches
     top = {n: [int(i) for i in torch.topk(feat[n], 5).indices.tolist()] for n in feat}
     return {"workload": f"configs[4]: node IE over {list(IE_LAYERS)} of GoogLeNet ({dt}), {n_images} images x {n_batches} "
