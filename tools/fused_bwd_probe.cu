@@ -75,7 +75,10 @@ int run(int T, int C, int F, bool slab, bool check, int iters) {
   CK(cudaMalloc(&dD, hD.size() * 2)); CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dW, hW.size() * 2));
   CK(cudaMalloc(&dDr, hD.size() * 2)); CK(cudaMalloc(&dXr, hX.size() * 2));
   CK(cudaMalloc(&dM, hM.size() * 4));
-  CK(cudaMalloc(&dPart, (size_t)slots * F * C * 4)); CK(cudaMalloc(&dCs, (size_t)2 * slots * F * 4));
+  // both outputs get a 4 KB guard band behind them (0xA5 pattern) that the kernel must leave untouched
+  const size_t nPart = (size_t)slots * F * C, nCs = (size_t)2 * slots * F, kGuard = 1024;
+  CK(cudaMalloc(&dPart, (nPart + kGuard) * 4)); CK(cudaMalloc(&dCs, (nCs + kGuard) * 4));
+  CK(cudaMemset(dPart + nPart, 0xA5, kGuard * 4)); CK(cudaMemset(dCs + nCs, 0xA5, kGuard * 4));
   const std::vector<__nv_bfloat16> sD = slab ? to_slab(hD, T, C) : hD, sX = slab ? to_slab(hX, T, C) : hX;
   CK(cudaMemcpy(dD, sD.data(), sD.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dX, sX.data(), sX.size() * 2, cudaMemcpyHostToDevice));
@@ -101,6 +104,13 @@ int run(int T, int C, int F, bool slab, bool check, int iters) {
     CK(cudaMemcpy(rw.data(), rdW, rw.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(rc_.data(), rcs, rc_.size() * 4, cudaMemcpyDeviceToHost));
     size_t bw = 0, bc = 0;
+    {
+      std::vector<uint32_t> g1(kGuard), g2(kGuard);
+      CK(cudaMemcpy(g1.data(), dPart + nPart, kGuard * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(g2.data(), dCs + nCs, kGuard * 4, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < kGuard; ++i)
+        if (g1[i] != 0xA5A5A5A5u || g2[i] != 0xA5A5A5A5u) { printf("guard band overwritten at word %zu\n", i); ++bw; break; }
+    }
     for (size_t i = 0; i < rw.size(); ++i) {
       float s = 0.f;
       for (int k = 0; k < slots; ++k) s += part[(size_t)k * F * C + i];
