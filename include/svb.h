@@ -209,6 +209,14 @@ int svb_grad_early_elems(svb_handle* h, int64_t* elems);
  * fixed rank order => bit-identical results everywhere).  All ranks must call it once per step, in step order. */
 int svb_comm_alloc(svb_handle* h, int64_t n_floats, void* ipc_handle_out_host);
 int svb_comm_connect(svb_handle* h, int32_t rank, int32_t world, const void* ipc_handles_host);
+/* NVLS variant: the caller owns a SYMMETRIC region of svb_comm_region_bytes(n_floats) zeroed bytes on every rank (same
+ * size everywhere), mapped into this process for all ranks (region_ptrs_host[r], r = rank: the local pointer), plus --
+ * optionally -- a multicast mapping of it (NULL: plain peer loads / stores as with svb_comm_connect).  With a multicast
+ * pointer the SUM section is reduced by the NVSwitch (multimem.ld_reduce / multimem.st).  parallel.py obtains such a
+ * region from torch.distributed._symmetric_memory.  The region must outlive the handle's use of it. */
+int svb_comm_region_bytes(int64_t n_floats, int64_t* bytes, int64_t* capacity_floats);
+int svb_comm_attach(svb_handle* h, int32_t rank, int32_t world, int64_t n_floats, const void* const* region_ptrs_host,
+                    void* multicast_ptr);
 int svb_comm_capacity(svb_handle* h, int64_t* n_floats);
 int svb_comm_allreduce(svb_handle* h, void* stream);
 int svb_comm_destroy(svb_handle* h);

@@ -92,6 +92,8 @@ SYMBOLS = {
     "svb_set_comm_stream": (C.c_int, [_vp, _vp]),
     "svb_comm_alloc": (C.c_int, [_vp, C.c_int64, _vp]),
     "svb_comm_connect": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp]),
+    "svb_comm_region_bytes": (C.c_int, [C.c_int64, _P(C.c_int64), _P(C.c_int64)]),
+    "svb_comm_attach": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _P(_vp), _vp]),
     "svb_comm_capacity": (C.c_int, [_vp, _P(C.c_int64)]),
     "svb_comm_allreduce": (C.c_int, [_vp, _vp]),
     "svb_comm_destroy": (C.c_int, [_vp]),

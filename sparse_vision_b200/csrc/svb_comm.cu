@@ -10,6 +10,12 @@
 //   3. a second flag round makes sure all slices have landed before the optimiser half of the step reads them.
 // Compared with two NCCL calls per step (~55 us at 2 GPUs, almost all launch / protocol latency for 4 MB) this is one
 // launch, the MAX section rides along, and the result is bit-identical on every rank and from run to run.
+//
+// NVLS: when the buffer is SYMMETRIC memory with a multicast mapping (svb_comm_attach: the caller -- parallel.py through
+// torch.distributed._symmetric_memory, which does the VMM allocation, the file-descriptor exchange and the multicast
+// binding -- hands over every rank's pointer and the multicast pointer), step 2 of the SUM section is one
+// multimem.ld_reduce (the NVSwitch adds the W replicas) and one multimem.st (the switch broadcasts the sum) per 16
+// bytes instead of W loads and W stores over NVLink.
 #include <cstdlib>
 #include "svb_common.cuh"
 
@@ -21,6 +27,7 @@ constexpr int kCommBlocks = 128, kCommThreads = 512, kMaxRanks = 8;
 
 struct CommArgs {
   float* buf[kMaxRanks];      // every rank's flat buffer (own entry = local pointer)
+  float* mc;                  // multicast mapping of the same buffer on all ranks (NVLS), or null
   uint32_t* flag[kMaxRanks];  // every rank's flag array [2 rounds][kCommBlocks][kMaxRanks]
   uint32_t* status;           // LOCAL status word: 0 = fine, else 1 + the peer that never arrived (sticky, host-readable)
   long long n_sum, n_max;
@@ -114,10 +121,37 @@ __device__ __forceinline__ void reduce_section(const CommArgs& a, long long begi
   }
 }
 
+// SUM section through the switch: rank r owns slice r; multimem.ld_reduce returns the sum of the W replicas of 16 bytes,
+// multimem.st writes it to all of them.  The same value lands on every rank, so replicas stay bit-identical.
+__device__ __forceinline__ void reduce_sum_nvls(const CommArgs& a, long long n) {
+  const long long n4 = (n + 3) / 4;
+  const long long per = (n4 + a.world - 1) / a.world;
+  const long long lo = a.rank * per, hi = min(n4, lo + per);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int kUnroll = 8;
+  for (long long i = lo + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi; i += kUnroll * stride) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (i + u * stride < hi)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(a.mc + 4 * (i + u * stride))
+                     : "memory");
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (i + u * stride < hi)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + 4 * (i + u * stride)),
+                     "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                     : "memory");
+  }
+}
+
 template <int W>
 __device__ __forceinline__ void allreduce_body(const CommArgs& a) {
   cta_rendezvous(a, 0);                                 // every rank's buffer is complete
-  reduce_section<false, W>(a, 0, a.n_sum);
+  if (a.mc) reduce_sum_nvls(a, a.n_sum);
+  else reduce_section<false, W>(a, 0, a.n_sum);
   reduce_section<true, W>(a, (a.n_sum + 3) / 4 * 4, a.n_max);
   cta_rendezvous(a, 1);                                 // every slice has landed everywhere
 }
@@ -136,6 +170,8 @@ struct svb_comm {
   float* base = nullptr;         // local region: [capacity floats | flags]
   int64_t capacity = 0;          // floats
   void* peer_base[kMaxRanks] = {nullptr};
+  float* mc = nullptr;           // multicast mapping (NVLS) or null
+  bool owned = true;             // false: the region belongs to the caller (svb_comm_attach)
   bool connected = false;
   uint32_t epoch = 0;
 };
@@ -204,6 +240,41 @@ extern "C" int svb_comm_connect(svb_handle* h, int32_t rank, int32_t world, cons
   return 0;
 }
 
+extern "C" int svb_comm_region_bytes(int64_t n_floats, int64_t* bytes, int64_t* capacity_floats) {
+  if (n_floats <= 0 || !bytes) return fail(SVB_ERR_BAD_ARG, "svb_comm_region_bytes: bad argument");
+  const int64_t cap = (n_floats + 63) / 64 * 64;
+  *bytes = cap * 4 + static_cast<int64_t>(comm_flag_bytes());
+  if (capacity_floats) *capacity_floats = cap;
+  return 0;
+}
+
+extern "C" int svb_comm_attach(svb_handle* h, int32_t rank, int32_t world, int64_t n_floats, const void* const* region_ptrs_host,
+                               void* multicast_ptr) {
+  if (!h || !region_ptrs_host || n_floats <= 0) return fail(SVB_ERR_BAD_ARG, "svb_comm_attach: bad argument");
+  SVB_ON_DEVICE(h);
+  if (h->comm_ctx) return fail(SVB_ERR_BAD_ARG, "svb_comm_attach: a communication buffer already exists");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(SVB_ERR_UNSUPPORTED, "svb_comm_attach: world size %d (1..%d ranks of one node)", world, kMaxRanks);
+  for (int r = 0; r < world; ++r)
+    if (!region_ptrs_host[r] || (reinterpret_cast<uintptr_t>(region_ptrs_host[r]) & 15))
+      return fail(SVB_ERR_BAD_ARG, "svb_comm_attach: region pointer of rank %d is null or not 16-byte aligned", r);
+  if (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) return fail(SVB_ERR_BAD_ARG, "svb_comm_attach: misaligned multicast pointer");
+  svb_comm* c = new svb_comm();
+  if (const char* env = getenv("SVB_COMM_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0) c->timeout_s = v;
+  }
+  c->capacity = (n_floats + 63) / 64 * 64;
+  c->rank = rank; c->world = world;
+  for (int r = 0; r < world; ++r) c->peer_base[r] = const_cast<void*>(region_ptrs_host[r]);
+  c->base = static_cast<float*>(c->peer_base[rank]);
+  c->mc = static_cast<float*>(multicast_ptr);
+  c->owned = false;
+  c->connected = true;
+  h->comm_ctx = c;
+  return 0;
+}
+
 extern "C" int svb_comm_capacity(svb_handle* h, int64_t* n_floats) {
   if (!h || !n_floats) return fail(SVB_ERR_BAD_ARG, "null argument");
   *n_floats = h->comm_ctx ? h->comm_ctx->capacity : 0;
@@ -221,6 +292,7 @@ extern "C" int svb_comm_allreduce(svb_handle* h, void* stream) {
     a.buf[r] = static_cast<float*>(c->peer_base[r]);
     a.flag[r] = reinterpret_cast<uint32_t*>(static_cast<float*>(c->peer_base[r]) + c->capacity);
   }
+  a.mc = c->mc;
   a.n_sum = h->sum_elems; a.n_max = h->max_elems; a.rank = c->rank; a.world = c->world;
   a.status = comm_status_word(c);
   a.timeout_ns = static_cast<unsigned long long>(c->timeout_s * 1e9);
@@ -267,9 +339,11 @@ extern "C" int svb_comm_destroy(svb_handle* h) {
   if (!h || !h->comm_ctx) return 0;
   svb_comm* c = h->comm_ctx;
   cudaDeviceSynchronize();
-  for (int r = 0; r < c->world; ++r)
-    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
-  if (c->base) cudaFree(c->base);
+  if (c->owned) {
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->base) cudaFree(c->base);
+  }
   delete c;
   h->comm_ctx = nullptr;
   return 0;

@@ -53,6 +53,65 @@ def global_counts(n_images_local, hw, group=None, device=None):
     return n, n * hw
 
 
+_SYMM_KEEPALIVE = {}   # device index -> (symmetric tensor, rendezvous handle): the region must outlive the library's use of it
+
+
+def connect_symmetric_memory(device, n_floats, group=None):
+    """Sets up the exchange buffer in torch SYMMETRIC memory (torch.distributed._symmetric_memory does the VMM allocation,
+    the file-descriptor exchange between the ranks and the multicast binding) and hands every rank's mapping plus the
+    multicast pointer to the library (svb_comm_attach): with a multicast pointer the SUM section of the all-reduce goes
+    through the NVSwitch (multimem.ld_reduce / multimem.st, "NVLS").  Returns 'nvls', 'symm' (symmetric memory without
+    multicast: plain peer loads / stores) or None when it is unavailable on ANY rank -- the caller then falls back to CUDA
+    IPC (connect_peer_memory).  SVB_DP_NVLS=0 skips it."""
+    import os
+    from . import _lib as L
+    if os.environ.get("SVB_DP_NVLS", "1") == "0":
+        return None
+    lib, h = L.load(), L.handle(device)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    cap = ctypes.c_int64()
+    lib.svb_comm_capacity(h, ctypes.byref(cap))
+    if cap.value >= n_floats:      # an earlier step on this device already connected a large enough buffer
+        return _SYMM_KEEPALIVE[key][2] if key in _SYMM_KEEPALIVE else None    # None: it is an IPC buffer, keep it
+    if cap.value > 0:
+        lib.svb_comm_destroy(h)
+        _SYMM_KEEPALIVE.pop(key, None)
+    nbytes, capf = ctypes.c_int64(), ctypes.c_int64()
+    L.check(lib.svb_comm_region_bytes(int(n_floats), ctypes.byref(nbytes), ctypes.byref(capf)), "svb_comm_region_bytes")
+    ok, t, hd, ptrs, mc = world <= 8, None, None, None, 0
+    if ok:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            with torch.cuda.device(device):
+                t = symm.empty(nbytes.value // 4, dtype=torch.float32, device=device)
+                t.zero_()
+                torch.cuda.synchronize(device)
+                hd = symm.rendezvous(t, (group if group is not None else dist.group.WORLD).group_name)
+            ptrs = [int(p) for p in hd.buffer_ptrs]
+            mc = int(hd.multicast_ptr or 0)
+            off = t.data_ptr() - ptrs[rank]          # the tensor may sit at an offset inside its symmetric block
+            ptrs = [p + off for p in ptrs]
+            mc = mc + off if mc else 0
+            ok = len(ptrs) == world and off >= 0
+        except Exception:
+            ok = False
+    flags = torch.tensor([1 if ok else 0, 1 if mc else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)      # also: every rank has zeroed its region by now
+    ok, use_mc = bool(flags[0].item()), bool(flags[1].item())
+    if ok:
+        arr = (ctypes.c_void_p * world)(*ptrs)
+        ok = lib.svb_comm_attach(h, rank, world, int(n_floats), arr, ctypes.c_void_p(mc if use_mc else 0)) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if not bool(flag.item()):
+        lib.svb_comm_destroy(h)
+        return None
+    mode = "nvls" if use_mc else "symm"
+    _SYMM_KEEPALIVE[key] = (t, hd, mode)
+    return mode
+
+
 def connect_peer_memory(device, n_floats, group=None):
     """Sets up the library's peer-memory exchange buffer on `device` for all ranks of `group` (one node, <= 8 GPUs):
     svb_comm_alloc -> all-gather of the 64-byte CUDA IPC handles -> svb_comm_connect.  Returns True when EVERY rank
@@ -85,8 +144,10 @@ def connect_peer_memory(device, n_floats, group=None):
 class DataParallelStep:
     """grads() on the local shard -> all-reduce -> apply().  `kind` is 'sae_mlp' or 'gated_sae'.
 
-    exchange = 'peer' (default on CUDA): the flat buffer lives in CUDA-IPC peer memory and ONE kernel of the library
-    reduces it over NVLink (svb_comm_allreduce); falls back to 'nccl' when peer memory cannot be set up.
+    exchange = 'peer' (default on CUDA): the flat buffer lives in memory every rank maps and ONE kernel of the library
+    reduces it over NVLink (svb_comm_allreduce) -- in torch symmetric memory with the SUM section reduced by the NVSwitch
+    (`mode` 'nvls') when that is available, else in CUDA-IPC peer memory (`mode` 'ipc'); falls back to 'nccl' when
+    neither can be set up.
     exchange = 'nccl': torch.distributed all-reduce (also the CPU / gloo path); overlap=True additionally sends the
     encoder-side gradients on a communication stream while the decoder weight-gradient GEMM runs."""
 
@@ -97,6 +158,7 @@ class DataParallelStep:
         self.overlap = overlap
         self.comm_stream = None
         self.peer = None   # None: not tried yet, True / False afterwards
+        self.mode = None   # 'nvls' | 'symm' | 'ipc' once the peer exchange is connected
 
     def step(self, x_local, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer, betas,
              global_images, global_tokens, want_dec=True, eps=1e-8):
@@ -108,7 +170,10 @@ class DataParallelStep:
         ss = ops.SplitStep(self.kind, x_local, params, lam, want_dec=want_dec)
         addr, n_sum, n_max = ss.grads(global_tokens=global_tokens)
         if multi and x_local.is_cuda and self.exchange == "peer" and self.peer is None:
-            self.peer = connect_peer_memory(x_local.device, n_sum + n_max, self.group)
+            self.mode = connect_symmetric_memory(x_local.device, n_sum + n_max, self.group)
+            if self.mode is None and connect_peer_memory(x_local.device, n_sum + n_max, self.group):
+                self.mode = "ipc"
+            self.peer = self.mode is not None
             if self.peer:   # once: rebuild this step's buffer inside the exchange region
                 addr, n_sum, n_max = ss.grads(global_tokens=global_tokens)
         if self.peer:

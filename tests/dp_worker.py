@@ -39,6 +39,8 @@ def main():
                           B * H * W)
         if exch == "peer":
             assert dp.peer, "peer-memory exchange could not be set up on this box"
+            if rank == 0:
+                print(f"{kind}: peer exchange mode = {dp.mode}", flush=True)
         got = res.scalars()
         if rank == 0:
             ref_params = [p[kk].clone().to(dev) for kk in keys]
