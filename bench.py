@@ -931,6 +931,10 @@ def run_svb(args):
         }
         if strong is not None:
             line["strong_scaling"] = strong
+        if dp is not None:
+            line["exchange"] = {"mode": dp.mode, "what": "one kernel of libsvb on memory every rank maps; 'nvls': torch symmetric memory, "
+                                "SUM section reduced by the NVSwitch (multimem.ld_reduce / multimem.st); 'ipc': CUDA-IPC peer "
+                                "memory, peer loads / stores"}
         if e2e is not None:
             line["e2e"] = e2e
         if other_fmt is not None:
