@@ -796,8 +796,9 @@ def run_svb(args):
     e2e = None
     base = None
     if "e2e" not in skip:
+        fuse_producer = args.channels_last and not args.no_fold_bn and not args.no_fuse_producer
         base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=args.channels_last,
-                                  fold_bn=not args.no_fold_bn)
+                                  fold_bn=not args.no_fold_bn, fuse=fuse_producer)
         base_copy = copy.deepcopy(base) if args.two_pass else None
         sae = _make_params().to(dev)
         pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", LR, LAMBDA, EXPANSION,
@@ -858,6 +859,7 @@ def run_svb(args):
                "numa_node_rank0": numa_node,
                "cuda_graph": pipe._graph is not None,
                "producer": {"channels_last": bool(args.channels_last), "batchnorm_folded": not args.no_fold_bn,
+                            "fused_forward": bool(fuse_producer),
                             "original_model": "second forward of an unhooked copy" if args.two_pass else
                             "same pass: the hook hands [reconstruction; original activation] (2B) to the rest of the net"},
                "note": "ModelPipeline.train_batch on pinned host images (bf16 3x224x224): H2D (overlapped on a copy stream) "
@@ -1002,6 +1004,9 @@ def main():
                     help="memory format of the resident activations of the `value` leg")
     ap.add_argument("--no-graph", action="store_true",
                     help="e2e: launch every batch eagerly instead of replaying one captured CUDA graph (N = 1)")
+    ap.add_argument("--no-fuse-producer", action="store_true",
+                    help="e2e: torchvision's eager forward (ATen max-pool / add_ / relu_ / cat) instead of "
+                         "producer.fuse_forward (libsvb max-pool and bias+relu+concat kernels between the cuDNN convolutions)")
     ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")
     ap.add_argument("--two-pass", action="store_true",
                     help="e2e: compare with a second forward of an unhooked copy (the reference's structure) instead of "

@@ -274,6 +274,32 @@ int svb_histogram_update(svb_handle* h, void* stream, const float* vals, int64_t
                          float* hist);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Memory-bound layers of the frozen activation producer (utils.py:277-281 builds the base model,
+ * model_pipeline.py:445-475, 662-708 run it around the hook).  bf16, NHWC ("channels_last": [n, h, w, c] in memory).
+ *
+ * svb_maxpool_nhwc      — torch.nn.MaxPool2d(kernel, stride, pad, ceil_mode) of torchvision's GoogLeNet (3/2, 3/1 and
+ *                         2/2 windows; padding counts as -inf, NaN propagates); OH / OW are torch's output sizes and
+ *                         are checked.  Exact.
+ * svb_bias_relu_scatter — what follows every convolution of the model (BasicConv2d: conv -> folded BatchNorm bias ->
+ *                         relu) and the torch.cat of an inception block in one pass: out = relu(src + bias) for a dense
+ *                         [positions, C] convolution output, channel range [c_begin, c_begin + c_count) written to
+ *                         dst[position * dst_channels + dst_offset + (c - c_begin)].  The ranges are consecutive, cover
+ *                         C, and every count / offset is a multiple of 8.  Bit-identical to add_ + relu_ on bf16 tensors.
+ */
+#define SVB_MAX_CHAN_SEGMENTS 4
+typedef struct svb_chan_segment {
+  void* dst;            /* bf16 [positions, dst_channels] */
+  int32_t c_begin;      /* first source channel of the range */
+  int32_t c_count;
+  int32_t dst_channels; /* row length of dst in channels */
+  int32_t dst_offset;   /* first channel of the range inside a dst row */
+} svb_chan_segment;
+int svb_maxpool_nhwc(svb_handle* h, void* stream, const void* in, int64_t n_images, int32_t H, int32_t W, int32_t C,
+                     int32_t kernel, int32_t stride, int32_t pad, int32_t ceil_mode, void* out, int32_t OH, int32_t OW);
+int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* src, const void* bias, int64_t positions, int32_t C,
+                          const svb_chan_segment* seg, int32_t n_seg, int32_t relu);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Optimiser step on caller-provided gradients — utils.py:50-97 (ConstrainedAdam.step / torch.optim.Adam).
  * `decoder_index` is the position of decoder.weight in the lists (projected + renormalised when the optimizer is
  * SVB_CONSTRAINED_ADAM; -1 for none); rows/cols give each tensor's 2-D shape (vectors: rows = 1).

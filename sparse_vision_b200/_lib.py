@@ -67,6 +67,13 @@ class GatedForwardOut(C.Structure):
                 ("relu_pi", _vp), ("relu_pi_dtype", C.c_int32), ("via", _vp), ("via_dtype", C.c_int32)]
 
 
+class ChanSegment(C.Structure):
+    _fields_ = [("dst", _vp), ("c_begin", C.c_int32), ("c_count", C.c_int32), ("dst_channels", C.c_int32),
+                ("dst_offset", C.c_int32)]
+
+
+MAX_CHAN_SEGMENTS = 4
+
 # every symbol include/svb.h declares: (name, restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
@@ -106,6 +113,9 @@ SYMBOLS = {
     "svb_gated_step_grads": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), C.c_float, C.c_int64, _P(TrainOut)]),
     "svb_gated_step_apply": (C.c_int, [_vp, _vp, _P(Acts), _P(GatedParams), _P(AdamState), _P(OptConfig), C.c_float,
                                        C.c_int32, C.c_int64, C.c_int64, _P(TrainOut)]),
+    "svb_maxpool_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
+    "svb_bias_relu_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _P(ChanSegment), C.c_int32, C.c_int32]),
     "svb_adam_step": (C.c_int, [_vp, _vp, C.c_int32, _P(_vp), _P(_vp), _P(_vp), _P(_vp), _P(C.c_int64),
                                 _P(C.c_int64), C.c_int32, _P(OptConfig)]),
     "svb_reinit_dead": (C.c_int, [_vp, _vp, _P(SaeParams), C.c_int32, _P(AdamState), _vp, _fp, _fp, C.c_float]),

@@ -430,3 +430,52 @@ def gemm_bf16(A, B, a_mn=False, b_mn=False, out_dtype=torch.float32, alpha=1.0, 
                                    L.ptr(bias.contiguous().float()) if bias is not None else None, int(relu)),
             "svb_gemm_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------- activation producer
+def _is_nhwc_bf16(x):
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def pool_output_size(n, kernel, stride, pad, ceil_mode):
+    """torch's pooling_output_shape for dilation 1 (what nn.MaxPool2d produces)."""
+    o = (n + 2 * pad - (kernel - 1) - 1 + (stride - 1 if ceil_mode else 0)) // stride + 1
+    if ceil_mode and (o - 1) * stride >= n + pad:
+        o -= 1
+    return o
+
+
+def maxpool_nhwc(x, kernel, stride, pad=0, ceil_mode=False):
+    """torch.nn.functional.max_pool2d on a bf16 channels_last CUDA tensor (include/svb.h: svb_maxpool_nhwc); exact."""
+    if not _is_nhwc_bf16(x):
+        raise ValueError("maxpool_nhwc takes a bf16 channels_last CUDA tensor [B,C,H,W]")
+    b, c, h, w = x.shape
+    oh, ow = pool_output_size(h, kernel, stride, pad, ceil_mode), pool_output_size(w, kernel, stride, pad, ceil_mode)
+    out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    L.check(L.load().svb_maxpool_nhwc(L.handle(x.device), L.stream_ptr(x.device), L.ptr(x), b, h, w, c, int(kernel),
+                                      int(stride), int(pad), int(bool(ceil_mode)), L.ptr(out), oh, ow), "svb_maxpool_nhwc")
+    return out
+
+
+def bias_relu_scatter(src, bias, dests, relu=True):
+    """relu(src + bias) of a dense bf16 channels_last convolution output, written in ONE pass into channel ranges of
+    other channels_last tensors (include/svb.h: svb_bias_relu_scatter).  `dests` is a list of (tensor, channel_offset,
+    channel_count): consecutive source channel ranges in order; each tensor has the batch / spatial size of `src`.
+    `dests = [(src, 0, C)]` is the in-place bias + relu.  Bit-identical to `src.add_(bias).relu_()` + torch.cat."""
+    if not _is_nhwc_bf16(src):
+        raise ValueError("bias_relu_scatter takes a bf16 channels_last CUDA tensor [B,C,H,W]")
+    b, c, h, w = src.shape
+    if bias.dtype != torch.bfloat16 or bias.numel() != c or not bias.is_contiguous():
+        raise ValueError("bias must be a contiguous bf16 vector of C elements")
+    if not 1 <= len(dests) <= L.MAX_CHAN_SEGMENTS:
+        raise ValueError(f"1..{L.MAX_CHAN_SEGMENTS} destinations")
+    segs = (L.ChanSegment * len(dests))()
+    begin = 0
+    for i, (dst, off, count) in enumerate(dests):
+        if not _is_nhwc_bf16(dst) or dst.shape[0] != b or tuple(dst.shape[2:]) != (h, w) or dst.device != src.device:
+            raise ValueError("every destination is a bf16 channels_last tensor with the batch and spatial size of src")
+        segs[i] = L.ChanSegment(dst.data_ptr(), begin, int(count), dst.shape[1], int(off))
+        begin += int(count)
+    L.check(L.load().svb_bias_relu_scatter(L.handle(src.device), L.stream_ptr(src.device), L.ptr(src), L.ptr(bias),
+                                           b * h * w, c, segs, len(dests), int(bool(relu))), "svb_bias_relu_scatter")

@@ -69,13 +69,16 @@ def fold_batchnorm(model):
     return model
 
 
-def to_producer_format(model, device, dtype=torch.bfloat16, channels_last=True, fold_bn=False):
-    """Moves the frozen base model to `device` in the format the SAE kernels read without a copy."""
+def to_producer_format(model, device, dtype=torch.bfloat16, channels_last=True, fold_bn=False, fuse=False):
+    """Moves the frozen base model to `device` in the format the SAE kernels read without a copy.  fuse=True (with
+    fold_bn, bf16 and channels_last) also swaps in the fused forward below."""
     if fold_bn:
         model = fold_batchnorm(model.float())
     model = model.to(device=device, dtype=dtype)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
+    if fuse:
+        model = fuse_forward(model)
     return model
 
 
@@ -83,3 +86,91 @@ def hooked_layers(model, names):
     """{reference layer name: module} for IE(...) / ModelPipeline(...)."""
     mods = dict(model.named_modules())
     return {n: mods[module_name(n)] for n in names}
+
+
+# ------------------------------------------------------------------------------------------------ fused forward
+# torchvision's eager forward of the frozen network, bf16 / channels_last / BatchNorm folded, 256 images, spends 4.5 of
+# its 10.6 ms in ATen's NHWC max-pool, 2.4 ms in the bias add_ and relu_ behind every cuDNN convolution and 0.65 ms in
+# the torch.cat of the nine inception blocks -- kernels that only move bytes (tools/prof_producer.py).  fuse_forward()
+# swaps the classes of those modules for the ones below: the module tree, the names the hooks are registered under and
+# the state_dict stay what they were; the convolutions still go to cuDNN; everything between them is two kernels of
+# libsvb (svb_maxpool_nhwc, svb_bias_relu_scatter).  Inputs that are not bf16 channels_last CUDA tensors take
+# torchvision's own forward.
+def _fast_input(x):
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and not x.requires_grad
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _conv_nobias(x, conv):
+    return torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def _make_fused_classes():
+    from torchvision.models.googlenet import BasicConv2d, Inception
+    from . import ops
+
+    class FusedBasicConv2d(BasicConv2d):
+        """conv (cuDNN, no bias) -> relu(. + folded BatchNorm bias) in place, one pass instead of two."""
+
+        def forward(self, x):
+            if not (_fast_input(x) and isinstance(self.bn, torch.nn.Identity) and self.conv.bias is not None):
+                return super().forward(x)
+            y = _conv_nobias(x, self.conv)
+            ops.bias_relu_scatter(y, self.conv.bias, [(y, 0, y.shape[1])])
+            return y
+
+    class FusedMaxPool2d(torch.nn.MaxPool2d):
+        def forward(self, x):
+            k, s, p = self.kernel_size, self.stride, self.padding
+            if not (_fast_input(x) and isinstance(k, int) and isinstance(s, int) and isinstance(p, int)
+                    and self.dilation == 1 and not self.return_indices and (k, s) in ((3, 1), (3, 2), (2, 2))):
+                return super().forward(x)
+            return ops.maxpool_nhwc(x, k, s, p, self.ceil_mode)
+
+    class FusedInception(Inception):
+        """The three 1x1 convolutions that read the block's input run as ONE convolution (weights concatenated once);
+        every branch's relu(conv + bias) is written straight into its channel range of the block output."""
+
+        def _merged(self):
+            convs = [self.branch1.conv, self.branch2[0].conv, self.branch3[0].conv]
+            w = getattr(self, "_svb_w1", None)
+            if w is None or w.device != convs[0].weight.device or w.dtype != convs[0].weight.dtype:
+                self._svb_w1 = torch.cat([c.weight for c in convs]).contiguous(memory_format=torch.channels_last)
+                self._svb_b1 = torch.cat([c.bias for c in convs]).contiguous()
+            return self._svb_w1, self._svb_b1
+
+        def forward(self, x):
+            convs = [self.branch1, self.branch2[0], self.branch2[1], self.branch3[0], self.branch3[1], self.branch4[1]]
+            if not (_fast_input(x) and all(isinstance(m.bn, torch.nn.Identity) and m.conv.bias is not None for m in convs)):
+                return super().forward(x)
+            b, _, h, w = x.shape
+            c1, c3r, c3, c5r, c5, cp = (m.conv.out_channels for m in convs)
+            new = lambda c: torch.empty((b, c, h, w), device=x.device, dtype=x.dtype,   # noqa: E731
+                                        memory_format=torch.channels_last)
+            out, t3, t5 = new(c1 + c3 + c5 + cp), new(c3r), new(c5r)
+            w1, b1 = self._merged()
+            y = torch.nn.functional.conv2d(x, w1, None)
+            ops.bias_relu_scatter(y, b1, [(out, 0, c1), (t3, 0, c3r), (t5, 0, c5r)])
+            y = _conv_nobias(t3, self.branch2[1].conv)
+            ops.bias_relu_scatter(y, self.branch2[1].conv.bias, [(out, c1, c3)])
+            y = _conv_nobias(t5, self.branch3[1].conv)
+            ops.bias_relu_scatter(y, self.branch3[1].conv.bias, [(out, c1 + c3, c5)])
+            y = _conv_nobias(self.branch4[0](x), self.branch4[1].conv)
+            ops.bias_relu_scatter(y, self.branch4[1].conv.bias, [(out, c1 + c3 + c5, cp)])
+            return out
+
+    return BasicConv2d, Inception, FusedBasicConv2d, FusedMaxPool2d, FusedInception
+
+
+def fuse_forward(model):
+    """In place: GoogLeNet's BasicConv2d / MaxPool2d / Inception modules get the fused forwards above (class swap; the
+    parameters, module names, hooks and state_dict are untouched).  Needs a BatchNorm-folded model to take effect."""
+    BasicConv2d, Inception, FusedBasicConv2d, FusedMaxPool2d, FusedInception = _make_fused_classes()
+    for m in model.modules():
+        if type(m) is BasicConv2d:
+            m.__class__ = FusedBasicConv2d
+        elif type(m) is torch.nn.MaxPool2d:
+            m.__class__ = FusedMaxPool2d
+        elif type(m) is Inception:
+            m.__class__ = FusedInception
+    return model

@@ -1,0 +1,154 @@
+"""The memory-bound layers of the frozen activation producer (utils.py:277-281,
+model_pipeline.py:445-475): svb_maxpool_nhwc against torch.nn.functional.max_pool2d (bit-exact, every window GoogLeNet
+uses plus ragged sizes), svb_bias_relu_scatter against add_ + relu_ + torch.cat (bit-exact), and the fused forward of
+the whole network against torchvision's eager forward of the same frozen model."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("B,C,H,W,k,s,p,ceil", [
+    (3, 64, 112, 112, 3, 2, 0, True),     # maxpool1
+    (2, 192, 56, 56, 3, 2, 0, True),      # maxpool2
+    (2, 480, 28, 28, 3, 2, 0, True),      # maxpool3
+    (2, 832, 14, 14, 2, 2, 0, True),      # maxpool4
+    (2, 192, 28, 28, 3, 1, 1, True),      # inception branch4 pools
+    (2, 528, 14, 14, 3, 1, 1, True),
+    (3, 832, 7, 7, 3, 1, 1, True),
+    (2, 8, 5, 9, 3, 2, 0, False),         # ragged: floor mode, odd sizes, one channel vector
+    (1, 24, 6, 11, 3, 2, 1, True),
+    (2, 16, 3, 3, 2, 2, 0, True),
+    (1, 40, 1, 1, 3, 1, 1, False),
+    (2, 72, 13, 2, 3, 1, 1, False),
+])
+def test_maxpool_nhwc_is_exact(B, C, H, W, k, s, p, ceil):
+    from sparse_vision_b200 import ops
+    x = _nhwc(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(C + H)))
+    want = F.max_pool2d(x, k, s, p, ceil_mode=ceil)
+    got = ops.maxpool_nhwc(x, k, s, p, ceil)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+    # and against the CPU implementation in fp32 (max is exact in any precision)
+    assert torch.equal(got.float().cpu(), F.max_pool2d(x.float().cpu(), k, s, p, ceil_mode=ceil))
+
+
+def test_maxpool_nhwc_nan_and_inf():
+    from sparse_vision_b200 import ops
+    x = torch.randn(1, 8, 6, 6, generator=torch.Generator().manual_seed(3))
+    x[0, 0, 2, 2] = float("nan")
+    x[0, 1, 0, 0] = float("-inf")
+    x[0, 2, 5, 5] = float("inf")
+    x = _nhwc(x)
+    want, got = F.max_pool2d(x, 3, 1, 1, ceil_mode=True), ops.maxpool_nhwc(x, 3, 1, 1, True)
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and torch.isnan(got).sum() == 9
+    assert torch.equal(torch.nan_to_num(got, nan=0.0), torch.nan_to_num(want, nan=0.0))
+
+
+def test_maxpool_nhwc_rejects_what_it_cannot_do():
+    from sparse_vision_b200 import ops
+    from sparse_vision_b200._lib import SvbError
+    with pytest.raises(ValueError):
+        ops.maxpool_nhwc(torch.randn(1, 8, 4, 4).cuda(), 3, 2)                      # fp32
+    with pytest.raises(ValueError):
+        ops.maxpool_nhwc(torch.randn(1, 8, 4, 4).cuda().bfloat16(), 3, 2)           # NCHW-contiguous
+    with pytest.raises(SvbError):
+        ops.maxpool_nhwc(_nhwc(torch.randn(1, 12, 4, 4)), 3, 2)                     # C % 8
+    with pytest.raises(SvbError):
+        ops.maxpool_nhwc(_nhwc(torch.randn(1, 8, 9, 9)), 5, 1, 2)                   # window GoogLeNet does not have
+
+
+@pytest.mark.parametrize("B,H,W,chans", [(4, 28, 28, (64, 96, 16)), (3, 14, 14, (112, 144, 32)), (2, 7, 7, (384,)),
+                                         (5, 3, 5, (8, 8, 8, 8)), (1, 1, 1, (16, 24))])
+def test_bias_relu_scatter_matches_add_relu_cat(B, H, W, chans):
+    """One source convolution output split over its destinations (the merged 1x1 convolution of an inception block),
+    each landing at a channel offset inside a wider tensor whose other channels must stay untouched."""
+    from sparse_vision_b200 import ops
+    g = torch.Generator().manual_seed(sum(chans))
+    C = sum(chans)
+    src = _nhwc(torch.randn(B, C, H, W, generator=g) * 3)
+    bias = (torch.randn(C, generator=g)).cuda().bfloat16()
+    want = src.clone().add_(bias.view(1, C, 1, 1)).relu_()
+    dests, begin = [], 0
+    for i, c in enumerate(chans):
+        wide = _nhwc(torch.full((B, c + 16 * (i + 1), H, W), -7.0))
+        dests.append((wide, 8 * (i + 1), c))
+    ops.bias_relu_scatter(src, bias, dests)
+    for (wide, off, c) in dests:
+        assert torch.equal(wide[:, off:off + c], want[:, begin:begin + c])
+        rest = torch.cat([wide[:, :off], wide[:, off + c:]], 1)
+        assert bool((rest == -7.0).all())
+        begin += c
+    # in place, without relu
+    y = src.clone(memory_format=torch.channels_last)
+    ops.bias_relu_scatter(y, bias, [(y, 0, C)], relu=False)
+    assert torch.equal(y, src.clone().add_(bias.view(1, C, 1, 1)))
+
+
+def test_bias_relu_scatter_checks_its_arguments():
+    from sparse_vision_b200 import ops
+    from sparse_vision_b200._lib import SvbError
+    src = _nhwc(torch.randn(2, 16, 4, 4))
+    bias = torch.zeros(16).cuda().bfloat16()
+    with pytest.raises(SvbError):
+        ops.bias_relu_scatter(src, bias, [(src, 0, 8)])                     # does not cover C
+    with pytest.raises(SvbError):
+        ops.bias_relu_scatter(src, bias, [(src, 4, 16)])                    # offset not a multiple of 8 / outside the row
+    with pytest.raises(ValueError):
+        ops.bias_relu_scatter(src, bias.float(), [(src, 0, 16)])
+    with pytest.raises(ValueError):
+        ops.bias_relu_scatter(src, bias, [(_nhwc(torch.randn(2, 16, 5, 4)), 0, 16)])
+
+
+def test_fused_forward_matches_the_eager_model():
+    """fuse_forward changes which kernels run between the convolutions, not the function: every hooked layer and the
+    logits agree with torchvision's eager forward of the same frozen bf16 model to bf16 rounding (the merged 1x1
+    convolution may pick another cuDNN kernel, i.e. another summation order), the state_dict and module names are
+    unchanged, and the hooks still fire on the same modules."""
+    import copy
+    from sparse_vision_b200.producer import GOOGLENET_LAYERS, fuse_forward, synthetic_googlenet, to_producer_format
+    dev = torch.device("cuda:0")
+    eager = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=True, fold_bn=True)
+    fused = fuse_forward(copy.deepcopy(eager))
+    assert list(fused.state_dict().keys()) == list(eager.state_dict().keys())
+    assert [n for n, _ in fused.named_modules()] == [n for n, _ in eager.named_modules()]
+    x = _nhwc(torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(5)))
+    seen = {}
+
+    def grab(tag):
+        def hook(mod, inp, out):
+            seen.setdefault(tag, {})[mod._svb_name] = out
+        return hook
+    for tag, model in (("eager", eager), ("fused", fused)):
+        for name, (mod_name, _, _) in GOOGLENET_LAYERS.items():
+            m = dict(model.named_modules())[mod_name]
+            m._svb_name = name
+            m.register_forward_hook(grab(tag))
+    launches0 = __import__("sparse_vision_b200")._lib.load().svb_launch_count()
+    with torch.no_grad():
+        want, got = eager(x), fused(x)
+    assert __import__("sparse_vision_b200")._lib.load().svb_launch_count() - launches0 >= 3 + 4 + 9 * 5
+    for name, (_, C, hw) in GOOGLENET_LAYERS.items():
+        a, b = seen["eager"][name].float(), seen["fused"][name].float()
+        assert tuple(b.shape[1:2]) == (C,) and b.shape[2] * b.shape[3] == hw
+        assert seen["fused"][name].is_contiguous(memory_format=torch.channels_last)
+        err = (a - b).abs().max().item()
+        assert err <= 4e-2 * a.abs().max().item(), (name, err, a.abs().max().item())
+        assert (a - b).abs().mean().item() <= 4e-3 * a.abs().mean().item() + 1e-6, name
+    assert (want.float() - got.float()).abs().max().item() <= 4e-2 * want.float().abs().max().item()
+    # a tensor that asks for gradients (what the IE passes send through the layers behind a hooked one) and an fp32 /
+    # NCHW model take torchvision's own forward
+    xg = x[:2].clone().requires_grad_(True)
+    fused(xg).float().sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad.float()).all()

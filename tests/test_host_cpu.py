@@ -229,13 +229,14 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     pairs = {"svb_acts": L.Acts, "svb_sae_params": L.SaeParams, "svb_gated_params": L.GatedParams,
              "svb_adam_state": L.AdamState, "svb_opt_config": L.OptConfig, "svb_activity_out": L.ActivityOut,
              "svb_train_out": L.TrainOut, "svb_sae_forward_out": L.SaeForwardOut,
-             "svb_gated_forward_out": L.GatedForwardOut}
+             "svb_gated_forward_out": L.GatedForwardOut, "svb_chan_segment": L.ChanSegment}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svb.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
         for fname, _ in cls._fields_:
             lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
-    lines += ['  printf("SVB_STATS_LEN %d\\n", (int)SVB_STATS_LEN);', '  return 0;', '}']
+    lines += ['  printf("SVB_STATS_LEN %d\\n", (int)SVB_STATS_LEN);',
+              '  printf("SVB_MAX_CHAN_SEGMENTS %d\\n", (int)SVB_MAX_CHAN_SEGMENTS);', '  return 0;', '}']
     src = tmp_path / "abi.c"
     src.write_text("\n".join(lines))
     exe = tmp_path / "abi"
@@ -247,6 +248,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
     assert int(out["SVB_STATS_LEN"]) == L.STATS_LEN
+    assert int(out["SVB_MAX_CHAN_SEGMENTS"]) == L.MAX_CHAN_SEGMENTS
 
 
 def test_small_host_helpers_match_reference_golden(golden_dir):
@@ -371,3 +373,35 @@ def test_tuning_keys_round_trip():
         old = lib.svb_get_tuning(key)
         assert lib.svb_set_tuning(key, old + 1) == 0 and lib.svb_get_tuning(key) == old + 1
         lib.svb_set_tuning(key, old)
+
+
+def test_fuse_forward_keeps_the_module_tree_and_the_cpu_function():
+    """producer.fuse_forward swaps module classes only: names, state_dict and hooks are those of torchvision's model,
+    and a tensor the fused kernels do not take (CPU, fp32) goes through torchvision's own forward, bit for bit."""
+    import copy
+    from sparse_vision_b200.producer import fold_batchnorm, fuse_forward, synthetic_googlenet
+    base = fold_batchnorm(synthetic_googlenet(seed=3, calibration_images=2, image_size=96))
+    fused = fuse_forward(copy.deepcopy(base))
+    assert list(fused.state_dict().keys()) == list(base.state_dict().keys())
+    assert [n for n, _ in fused.named_modules()] == [n for n, _ in base.named_modules()]
+    assert type(fused.inception3a).__name__ == "FusedInception" and type(fused.maxpool1).__name__ == "FusedMaxPool2d"
+    fired = []
+    fused.inception4c.register_forward_hook(lambda m, i, o: fired.append(tuple(o.shape)))
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.equal(fused(x), base(x))
+    assert fired == [(2, 512, 6, 6)]
+    again = copy.deepcopy(fused)                      # the swapped classes survive a deepcopy (model_copy in the pipeline)
+    with torch.no_grad():
+        assert torch.equal(again(x), base(x))
+
+
+def test_pool_output_size_is_torchs():
+    from sparse_vision_b200.ops import pool_output_size
+    for n in range(1, 40):
+        for k, s, p in ((3, 2, 0), (3, 1, 1), (2, 2, 0), (3, 2, 1)):
+            for ceil in (False, True):
+                if n + 2 * p < k:
+                    continue
+                want = torch.nn.functional.max_pool2d(torch.zeros(1, 1, n, n), k, s, p, ceil_mode=ceil).shape[-1]
+                assert pool_output_size(n, k, s, p, ceil) == want, (n, k, s, p, ceil)
