@@ -299,6 +299,18 @@ int svb_maxpool_nhwc(svb_handle* h, void* stream, const void* in, int64_t n_imag
 int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* src, const void* bias, int64_t positions, int32_t C,
                           const svb_chan_segment* seg, int32_t n_seg, int32_t relu);
 
+/* GoogLeNet's stem convolution (torchvision googlenet.py conv1: 7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 input)
+ * with the folded BatchNorm bias and the ReLU in its epilogue: x bf16 NHWC [n, 224, 224, 3] -> out bf16 NHWC
+ * [n, 112, 112, 64] = relu(conv(x, w) + bias), fp32 accumulation, ONE rounding to bf16.  The im2col matrix is never
+ * built: with 3 channels a kernel row is 21 contiguous values of the input row (csrc/svb_producer.cu).
+ * svb_conv1_pack_weights lays the [64, 3, 7, 7] bf16 weights (element strides given) out once as the kernel's
+ * B operand: `packed` is SVB_CONV1_PACKED_ELEMS bf16 values. */
+#define SVB_CONV1_PACKED_ELEMS (64 * 232)
+int svb_conv1_pack_weights(svb_handle* h, void* stream, const void* w, int64_t stride_o, int64_t stride_i,
+                           int64_t stride_h, int64_t stride_w, void* packed);
+int svb_conv1_7x7s2_nhwc(svb_handle* h, void* stream, const void* x, int64_t n_images, const void* packed_w,
+                         const void* bias, int32_t relu, void* out);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Optimiser step on caller-provided gradients — utils.py:50-97 (ConstrainedAdam.step / torch.optim.Adam).
  * `decoder_index` is the position of decoder.weight in the lists (projected + renormalised when the optimizer is

@@ -73,6 +73,7 @@ class ChanSegment(C.Structure):
 
 
 MAX_CHAN_SEGMENTS = 4
+CONV1_PACKED_ELEMS = 64 * 232
 
 # every symbol include/svb.h declares: (name, restype, argtypes)
 _P = C.POINTER
@@ -116,6 +117,8 @@ SYMBOLS = {
     "svb_maxpool_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
     "svb_bias_relu_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _P(ChanSegment), C.c_int32, C.c_int32]),
+    "svb_conv1_pack_weights": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "svb_conv1_7x7s2_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, _vp]),
     "svb_adam_step": (C.c_int, [_vp, _vp, C.c_int32, _P(_vp), _P(_vp), _P(_vp), _P(_vp), _P(C.c_int64),
                                 _P(C.c_int64), C.c_int32, _P(OptConfig)]),
     "svb_reinit_dead": (C.c_int, [_vp, _vp, _P(SaeParams), C.c_int32, _P(AdamState), _vp, _fp, _fp, C.c_float]),

@@ -188,3 +188,148 @@ extern "C" int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* sr
   SVB_LAUNCH_CHECK("bias_relu_scatter");
   return 0;
 }
+
+namespace {
+// ------------------------------------------------------------------------------------------------ stem convolution
+// GoogLeNet's conv1 (7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 -> 112x112; googlenet.py of torchvision, built by
+// the reference at utils.py:277-281) + folded BatchNorm bias + ReLU.  cuDNN pads the 3 input channels to 8 and runs a
+// 256x64 implicit-GEMM kernel: 1.6 ms for 256 images, 40 % of the whole fused forward.  With 3 channels the 7 kernel
+// columns of one kernel row are 21 CONTIGUOUS bf16 values of the NHWC input row, so the im2col matrix never has to
+// exist: for a fixed kernel row kh,  A[ow][k] = in_row[2*oh + kh - 3][6*ow + k - 10]  for k = 1 + 3*kw + c  (k = 0 and
+// k = 22..31 meet zero weights), i.e. the A fragments of mma.sync.m16n8k16 are plain 32-bit shared-memory loads from
+// the staged input rows at a 12-byte row pitch (conflict-free: 3*g + t words).  The one-element shift (k = 1 + ...)
+// makes every fragment pair 4-byte aligned while the global rows are staged with aligned 16-byte copies.
+// CTA = 4 output rows of one image (448 pixels) x 64 channels, 7 warps, each warp two passes of 32 pixels x 64
+// channels (64 fp32 accumulators); K = 7 kernel rows x 32.  Shared memory: 13 input rows (zero padded) + the weights as
+// [64][232] bf16 (pitch 464 B: ldmatrix rows fall on distinct banks), 48 000 B static.
+constexpr int kC1RowsPerCta = 4, kC1InRows = 2 * kC1RowsPerCta + 5, kC1RowElems = 704, kC1WPitch = 232;
+constexpr int kC1Threads = 224;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(kC1Threads, 2)
+conv1_7x7s2_kernel(const uint4* __restrict__ x, const uint4* __restrict__ wt, const __nv_bfloat16* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ out, int relu) {
+  __shared__ __align__(16) uint16_t s_w[64 * kC1WPitch];
+  __shared__ __align__(16) uint16_t s_in[kC1InRows * kC1RowElems];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.x / 28, oh0 = (blockIdx.x % 28) * kC1RowsPerCta;
+  for (int i = tid; i < 64 * kC1WPitch / 8; i += kC1Threads) reinterpret_cast<uint4*>(s_w)[i] = __ldg(wt + i);
+  constexpr int kVecPerRow = kC1RowElems / 8;          // 88: 2 zero vectors, 84 of data (224 px x 3 ch), 2 zero vectors
+  for (int i = tid; i < kC1InRows * kVecPerRow; i += kC1Threads) {
+    const int r = i / kVecPerRow, v = i % kVecPerRow, ih = 2 * oh0 - 3 + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (v >= 2 && v < 86 && ih >= 0 && ih < 224) val = __ldg(x + (static_cast<long long>(n) * 224 + ih) * 84 + (v - 2));
+    reinterpret_cast<uint4*>(s_in)[i] = val;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const uint32_t* s_in32 = reinterpret_cast<const uint32_t*>(s_in);
+  // ldmatrix.x4: lane l addresses row (l & 7) of matrix (l >> 3); matrices = (n-tile, k 0-7), (n-tile, k 8-15),
+  // (n-tile + 1, k 0-7), (n-tile + 1, k 8-15)
+  const uint16_t* b_lane = s_w + ((lane & 7) + ((lane >> 4) << 3)) * kC1WPitch + (((lane >> 3) & 1) << 3);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int mt0 = 4 * warp + 2 * pass;
+    int a_base[2], rl[2], owb[2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      rl[mi] = (mt0 + mi) / 7;
+      owb[mi] = ((mt0 + mi) % 7) * 16;
+      a_base[mi] = (2 * rl[mi]) * (kC1RowElems / 2) + 3 * (owb[mi] + g) + t + 3;   // word index of (kh = 0, ks = 0)
+    }
+    float acc[2][8][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mi][nt][q] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t b[4][4];
+#pragma unroll
+        for (int np = 0; np < 4; ++np) ldmatrix_x4(b[np], b_lane + np * 16 * kC1WPitch + kh * 32 + ks * 16);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const int w0 = a_base[mi] + kh * (kC1RowElems / 2) + ks * 8;
+          uint32_t a[4];
+          a[0] = s_in32[w0];
+          a[1] = s_in32[w0 + 24];
+          a[2] = s_in32[w0 + 4];
+          a[3] = s_in32[w0 + 28];
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16_16816(acc[mi][2 * np], a, b[np][0], b[np][1]);
+            mma_bf16_16816(acc[mi][2 * np + 1], a, b[np][2], b[np][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      __nv_bfloat16* orow = out + ((static_cast<long long>(n) * 112 + oh0 + rl[mi]) * 112 + owb[mi] + g) * 64 + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(bias + nt * 8 + 2 * t);
+        const float b0 = __low2float(bb), b1 = __high2float(bb);
+        float v0 = acc[mi][nt][0] + b0, v1 = acc[mi][nt][1] + b1, v2 = acc[mi][nt][2] + b0, v3 = acc[mi][nt][3] + b1;
+        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        *reinterpret_cast<__nv_bfloat162*>(orow + nt * 8) = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * 64 + nt * 8) = __floats2bfloat162_rn(v2, v3);
+      }
+    }
+  }
+}
+
+// w [64, 3, 7, 7] (any strides, bf16) -> wt [64][232]: wt[n][kh * 32 + 1 + 3 * kw + c] = w[n][c][kh][kw], zeros elsewhere
+__global__ void conv1_pack_weights_kernel(const __nv_bfloat16* __restrict__ w, long long sn, long long sc, long long sh,
+                                          long long sw, uint16_t* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * kC1WPitch) return;
+  const int n = i / kC1WPitch, k = i % kC1WPitch, kh = k / 32, kk = k % 32 - 1;
+  uint16_t v = 0;
+  if (kh < 7 && kk >= 0 && kk < 21)
+    v = *reinterpret_cast<const uint16_t*>(w + n * sn + (kk % 3) * sc + kh * sh + (kk / 3) * sw);
+  wt[i] = v;
+}
+}  // namespace
+
+extern "C" int svb_conv1_pack_weights(svb_handle* h, void* stream, const void* w, int64_t stride_o, int64_t stride_i,
+                                      int64_t stride_h, int64_t stride_w, void* packed) {
+  if (!h || !w || !packed) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(SVB_ERR_BAD_ARG, "packed weights must be 16-byte aligned");
+  (conv1_pack_weights_kernel<<<cdiv(64 * kC1WPitch, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+       static_cast<const __nv_bfloat16*>(w), stride_o, stride_i, stride_h, stride_w, static_cast<uint16_t*>(packed)),
+   svb::count_launch());
+  SVB_LAUNCH_CHECK("conv1_pack_weights");
+  return 0;
+}
+
+extern "C" int svb_conv1_7x7s2_nhwc(svb_handle* h, void* stream, const void* x, int64_t n_images, const void* packed_w,
+                                    const void* bias, int32_t relu, void* out) {
+  if (!h || !x || !packed_w || !bias || !out) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (n_images <= 0 || n_images * 28 > 2147483647LL) return fail(SVB_ERR_BAD_ARG, "bad image count");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed_w) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias) & 3))
+    return fail(SVB_ERR_UNSUPPORTED, "svb_conv1_7x7s2_nhwc needs 16-byte aligned tensors");
+  (conv1_7x7s2_kernel<<<static_cast<unsigned>(n_images * 28), kC1Threads, 0, static_cast<cudaStream_t>(stream)>>>(
+       static_cast<const uint4*>(x), static_cast<const uint4*>(packed_w), static_cast<const __nv_bfloat16*>(bias),
+       static_cast<__nv_bfloat16*>(out), relu),
+   svb::count_launch());
+  SVB_LAUNCH_CHECK("conv1_7x7s2");
+  return 0;
+}

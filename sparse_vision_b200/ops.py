@@ -479,3 +479,30 @@ def bias_relu_scatter(src, bias, dests, relu=True):
         begin += int(count)
     L.check(L.load().svb_bias_relu_scatter(L.handle(src.device), L.stream_ptr(src.device), L.ptr(src), L.ptr(bias),
                                            b * h * w, c, segs, len(dests), int(bool(relu))), "svb_bias_relu_scatter")
+
+
+def conv1_pack_weights(weight):
+    """[64, 3, 7, 7] bf16 CUDA weights (any memory format) -> the packed B operand of conv1_stem."""
+    if not (weight.is_cuda and weight.dtype == torch.bfloat16 and tuple(weight.shape) == (64, 3, 7, 7)):
+        raise ValueError("conv1_pack_weights takes the bf16 CUDA weights [64, 3, 7, 7] of GoogLeNet's conv1")
+    packed = torch.empty(L.CONV1_PACKED_ELEMS, device=weight.device, dtype=torch.bfloat16)
+    so, si, sh, sw = weight.stride()
+    L.check(L.load().svb_conv1_pack_weights(L.handle(weight.device), L.stream_ptr(weight.device), L.ptr(weight), so, si,
+                                            sh, sw, L.ptr(packed)), "svb_conv1_pack_weights")
+    return packed
+
+
+def conv1_stem(x, packed_weight, bias, relu=True):
+    """relu(conv2d(x, w, stride 2, pad 3) + bias) for GoogLeNet's 7x7 stem on bf16 channels_last [B, 3, 224, 224] images
+    (include/svb.h: svb_conv1_7x7s2_nhwc) -> bf16 channels_last [B, 64, 112, 112]."""
+    if not _is_nhwc_bf16(x) or tuple(x.shape[1:]) != (3, 224, 224):
+        raise ValueError("conv1_stem takes bf16 channels_last CUDA images [B, 3, 224, 224]")
+    if packed_weight.numel() != L.CONV1_PACKED_ELEMS or packed_weight.dtype != torch.bfloat16:
+        raise ValueError("packed_weight comes from conv1_pack_weights")
+    if bias.dtype != torch.bfloat16 or bias.numel() != 64 or not bias.is_contiguous():
+        raise ValueError("bias must be a contiguous bf16 vector of 64 elements")
+    out = torch.empty((x.shape[0], 64, 112, 112), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    L.check(L.load().svb_conv1_7x7s2_nhwc(L.handle(x.device), L.stream_ptr(x.device), L.ptr(x), x.shape[0],
+                                          L.ptr(packed_weight), L.ptr(bias), int(bool(relu)), L.ptr(out)),
+            "svb_conv1_7x7s2_nhwc")
+    return out

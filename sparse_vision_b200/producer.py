@@ -112,9 +112,20 @@ def _make_fused_classes():
     class FusedBasicConv2d(BasicConv2d):
         """conv (cuDNN, no bias) -> relu(. + folded BatchNorm bias) in place, one pass instead of two."""
 
+        def _is_stem(self, x):
+            c = self.conv
+            return (tuple(x.shape[1:]) == (3, 224, 224) and tuple(c.weight.shape) == (64, 3, 7, 7) and c.stride == (2, 2)
+                    and c.padding == (3, 3) and c.dilation == (1, 1) and c.groups == 1)
+
         def forward(self, x):
             if not (_fast_input(x) and isinstance(self.bn, torch.nn.Identity) and self.conv.bias is not None):
                 return super().forward(x)
+            if self._is_stem(x):          # conv1: libsvb's own implicit-GEMM kernel, bias + relu in its epilogue
+                w = self.conv.weight
+                key = (w.data_ptr(), w._version, w.device)
+                if getattr(self, "_svb_key", None) != key:
+                    self._svb_packed, self._svb_key = ops.conv1_pack_weights(w), key
+                return ops.conv1_stem(x, self._svb_packed, self.conv.bias)
             y = _conv_nobias(x, self.conv)
             ops.bias_relu_scatter(y, self.conv.bias, [(y, 0, y.shape[1])])
             return y

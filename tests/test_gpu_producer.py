@@ -112,15 +112,18 @@ def test_bias_relu_scatter_checks_its_arguments():
 
 
 def test_fused_forward_matches_the_eager_model():
-    """fuse_forward changes which kernels run between the convolutions, not the function: every hooked layer and the
-    logits agree with torchvision's eager forward of the same frozen bf16 model to bf16 rounding (the merged 1x1
-    convolution may pick another cuDNN kernel, i.e. another summation order), the state_dict and module names are
-    unchanged, and the hooks still fire on the same modules."""
+    """fuse_forward changes which kernels run, not the function.  The yardstick is the SAME frozen model in fp32 (bf16
+    weights widened, TF32 off): at every hooked layer and at the logits the fused bf16 forward must be as close to it
+    as torchvision's eager bf16 forward is (both round every activation to bf16; the fused stem rounds once where
+    conv + add_ round twice, the merged 1x1 convolutions may sum in another order).  The state_dict and module names
+    are unchanged and the hooks fire on the same modules."""
     import copy
+    from sparse_vision_b200 import _lib as L
     from sparse_vision_b200.producer import GOOGLENET_LAYERS, fuse_forward, synthetic_googlenet, to_producer_format
     dev = torch.device("cuda:0")
     eager = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=True, fold_bn=True)
     fused = fuse_forward(copy.deepcopy(eager))
+    exact = copy.deepcopy(eager).float()
     assert list(fused.state_dict().keys()) == list(eager.state_dict().keys())
     assert [n for n, _ in fused.named_modules()] == [n for n, _ in eager.named_modules()]
     x = _nhwc(torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(5)))
@@ -130,25 +133,76 @@ def test_fused_forward_matches_the_eager_model():
         def hook(mod, inp, out):
             seen.setdefault(tag, {})[mod._svb_name] = out
         return hook
-    for tag, model in (("eager", eager), ("fused", fused)):
+    for tag, model in (("eager", eager), ("fused", fused), ("exact", exact)):
         for name, (mod_name, _, _) in GOOGLENET_LAYERS.items():
             m = dict(model.named_modules())[mod_name]
             m._svb_name = name
             m.register_forward_hook(grab(tag))
-    launches0 = __import__("sparse_vision_b200")._lib.load().svb_launch_count()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = exact(x.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    launches0 = L.load().svb_launch_count()
     with torch.no_grad():
         want, got = eager(x), fused(x)
-    assert __import__("sparse_vision_b200")._lib.load().svb_launch_count() - launches0 >= 3 + 4 + 9 * 5
+    assert L.load().svb_launch_count() - launches0 >= 3 + 4 + 9 * 5
+    report = []
     for name, (_, C, hw) in GOOGLENET_LAYERS.items():
-        a, b = seen["eager"][name].float(), seen["fused"][name].float()
+        r, a, b = seen["exact"][name], seen["eager"][name].float(), seen["fused"][name].float()
         assert tuple(b.shape[1:2]) == (C,) and b.shape[2] * b.shape[3] == hw
         assert seen["fused"][name].is_contiguous(memory_format=torch.channels_last)
-        err = (a - b).abs().max().item()
-        assert err <= 4e-2 * a.abs().max().item(), (name, err, a.abs().max().item())
-        assert (a - b).abs().mean().item() <= 4e-3 * a.abs().mean().item() + 1e-6, name
-    assert (want.float() - got.float()).abs().max().item() <= 4e-2 * want.float().abs().max().item()
-    # a tensor that asks for gradients (what the IE passes send through the layers behind a hooked one) and an fp32 /
-    # NCHW model take torchvision's own forward
+        e_eager, e_fused = (a - r).abs().mean().item(), (b - r).abs().mean().item()
+        report.append((name, e_eager / r.abs().mean().item(), e_fused / r.abs().mean().item()))
+        assert e_fused <= 1.25 * e_eager + 1e-6, report
+        assert (b - r).abs().max().item() <= 1.5 * (a - r).abs().max().item() + 1e-6, report
+    e_eager, e_fused = (want.float() - ref).abs().mean().item(), (got.float() - ref).abs().mean().item()
+    assert e_fused <= 1.25 * e_eager + 1e-6, (report, e_eager, e_fused)
+    print("relative mean error vs fp32 (layer, eager bf16, fused bf16):", report)
+    # a tensor that asks for gradients (what the IE passes send through the layers behind a hooked one) takes
+    # torchvision's own forward
     xg = x[:2].clone().requires_grad_(True)
     fused(xg).float().sum().backward()
     assert xg.grad is not None and torch.isfinite(xg.grad.float()).all()
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_conv1_stem_matches_conv2d(B):
+    """GoogLeNet's 7x7 / stride-2 stem: against F.conv2d in fp32 on the same bf16-rounded operands (the kernel
+    accumulates in fp32 and rounds once), every border row / column included; bit-exact on integer-valued data."""
+    from sparse_vision_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(64, generator=g).cuda().bfloat16()
+    x = _nhwc(torch.randn(B, 3, 224, 224, generator=g))
+    for wt in (w, w.contiguous(memory_format=torch.channels_last)):
+        got = ops.conv1_stem(x, ops.conv1_pack_weights(wt), bias)
+        want = F.relu(F.conv2d(x.float(), w.float(), bias.float(), stride=2, padding=3))
+        assert got.shape == (B, 64, 112, 112) and got.is_contiguous(memory_format=torch.channels_last)
+        err = (got.float() - want).abs()
+        assert err.max().item() <= 2e-2 * want.abs().max().item(), err.max().item()       # bf16 output rounding + TF32-free fp32 reference
+        assert err.mean().item() <= 2e-3 * want.abs().mean().item()
+    # small integers: every product and partial sum is exact in fp32 and the result is exact in bf16 where |y| <= 256
+    xi = _nhwc(torch.randint(-2, 3, (B, 3, 224, 224), generator=g).float())
+    wi = torch.randint(-1, 2, (64, 3, 7, 7), generator=g).float().cuda().bfloat16()
+    bi = torch.randint(-3, 4, (64,), generator=g).float().cuda().bfloat16()
+    got = ops.conv1_stem(xi, ops.conv1_pack_weights(wi), bi, relu=False).float()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = F.conv2d(xi.float(), wi.float(), bi.float(), stride=2, padding=3)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert want.abs().max().item() <= 256
+    assert torch.equal(got, want)
+
+
+def test_conv1_stem_rejects_other_shapes():
+    from sparse_vision_b200 import ops
+    w = torch.zeros(64, 3, 7, 7).cuda().bfloat16()
+    with pytest.raises(ValueError):
+        ops.conv1_stem(_nhwc(torch.zeros(1, 3, 96, 96)), ops.conv1_pack_weights(w), torch.zeros(64).cuda().bfloat16())
+    with pytest.raises(ValueError):
+        ops.conv1_pack_weights(torch.zeros(64, 3, 3, 3).cuda().bfloat16())

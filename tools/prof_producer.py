@@ -55,6 +55,14 @@ def main():
             gb = (inp.numel() + feats.numel()) * 2 / 1e9
             print(f"  {name:12s} {t:7.3f} ms  in {tuple(inp.shape)} out {tuple(feats.shape)}  {gb:.3f} GB in+out "
                   f"-> {gb / (t * 1e-3):7.0f} GB/s")
+        if args.fuse:
+            from sparse_vision_b200 import ops
+            c1 = model.conv1
+            packed = ops.conv1_pack_weights(c1.conv.weight)
+            t = timed(lambda: ops.conv1_stem(x, packed, c1.conv.bias), n=20)
+            flop = 2.0 * args.batch * 112 * 112 * 64 * 147
+            print(f"  conv1_stem kernel alone: {t:.3f} ms  ({flop / t / 1e9:.0f} useful TFLOP/s, "
+                  f"{(x.numel() + args.batch * 64 * 112 * 112) * 2 / t / 1e6:.0f} GB/s in+out)")
         if args.table:
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
