@@ -28,13 +28,12 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 // in [N, H, W, C8] / out [N, OH, OW, C8] in 16-byte vectors of 8 bf16 channels.  One thread: one (image, output row,
 // strip of SW output columns, channel vector); threads run over the channel vectors first (coalesced 16-byte accesses).
 // The (SW-1)*S+K input columns of a strip are reduced vertically once and shared by the windows of the strip; all of
-// a thread's loads are independent (18 / 27 of them in flight for 3x3 windows at stride 1 / 2).
+// a thread's loads are independent and unpredicated (18 / 27 of them in flight for 3x3 windows at stride 1 / 2).
 template <int K, int S, int SW>
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int C8, int pad, int OH,
                     int OW, int strips, long long total) {
   constexpr int NC = (SW - 1) * S + K;
-  constexpr uint32_t kNegInf2 = 0xFF80FF80u;
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % C8);
@@ -45,18 +44,22 @@ maxpool_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H
   const long long n = r / OH;
   const int ow0 = s * SW, ih0 = oh * S - pad, iw0 = ow0 * S - pad;
   const uint4* img = in + n * H * W * C8 + c;
+  // Positions outside the image count as -inf.  Every window that is stored starts inside the image (or its left / top
+  // padding), so clamping a coordinate into the image only repeats a value the same window already holds: the loads
+  // need no predicates and all of them are issued before the first max.
+  int roff[K];
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh) roff[kh] = min(max(ih0 + kh, 0), H - 1) * W;
   uint4 col[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
-    uint4 m = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
-    const int iw = iw0 + j;
-    if (iw >= 0 && iw < W) {
+    const int iw = min(max(iw0 + j, 0), W - 1);
+    uint4 v[K];
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh) {
-        const int ih = ih0 + kh;
-        if (ih >= 0 && ih < H) m = max8(m, __ldg(img + (static_cast<long long>(ih) * W + iw) * C8));
-      }
-    }
+    for (int kh = 0; kh < K; ++kh) v[kh] = __ldg(img + static_cast<long long>(roff[kh] + iw) * C8);
+    uint4 m = v[0];
+#pragma unroll
+    for (int kh = 1; kh < K; ++kh) m = max8(m, v[kh]);
     col[j] = m;
   }
   uint4* orow = out + ((n * OH + oh) * OW + ow0) * C8 + c;
