@@ -15,7 +15,7 @@ import os
 import torch
 
 from . import ops
-from ._lib import STAT
+from ._lib import STAT, is_channels_last_tokens
 from .parallel import DataParallelStep, global_counts
 from .utils import (average_over_W_H, batch_top_k, get_criterion, get_optimizer, get_top_k_samples,
                     measure_inactive_units, sae_inference_and_loss, update_histogram, variance_explained)
@@ -150,6 +150,18 @@ class ModelPipeline:
                 res = self.dp.step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
                                    self.sae_expansion_factor, self.sae_optimizer_name, group["betas"], g_img, g_tok,
                                    eps=group["eps"])
+            both = None
+            if self.compare_in_one_pass and self.dp is None and output.dim() == 4:
+                # [reconstruction; original] for the rest of the network: the step writes its reconstruction straight
+                # into the first half of the 2B batch, the original is copied behind it -- no torch.cat pass
+                fmt = torch.channels_last if is_channels_last_tokens(output) else torch.contiguous_format
+                x_in = output if fmt == torch.channels_last else output.contiguous()
+                both = torch.empty((2 * output.shape[0],) + tuple(output.shape[1:]), device=output.device,
+                                   dtype=output.dtype, memory_format=fmt)
+                kw["dec_out"] = both[:output.shape[0]]
+                output = x_in
+            if self.dp is not None:
+                pass
             elif self.sae_model_name == "sae_mlp":
                 res = ops.sae_train_step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
                                          self.sae_expansion_factor, **kw)
@@ -159,6 +171,9 @@ class ModelPipeline:
             self._last = res
             self.batch_dead_units[(name, "sae")] = res.dead          # uint8 on the device; AND-ed in train_batch()
             self.batch_neuron_frequency[(name, "sae")] = res.freq
+            if both is not None:
+                both[output.shape[0]:].copy_(output)
+                return both
             if self.compare_in_one_pass:
                 return torch.cat((res.dec, output.to(res.dec.dtype)), dim=0)
             return res.dec                                           # replaces the layer output (:425,432)

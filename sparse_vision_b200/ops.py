@@ -94,7 +94,7 @@ class StepResult:
         return {k: s[i] for k, i in L.STAT.items()}
 
 
-def _train_out(x, a, F, want_dec, dec_dtype):
+def _train_out(x, a, F, want_dec, dec_dtype, dec_out=None):
     """Outputs of one step.  The four small results are views of ONE uninitialised allocation (the finalise kernel
     writes every element): a fresh block per step, so a StepResult a caller keeps is never overwritten, but no fill
     kernel and a single allocator call per step."""
@@ -109,7 +109,13 @@ def _train_out(x, a, F, want_dec, dec_dtype):
     dec = None
     if want_dec:   # the reconstruction goes back in the layout the activations came in (channels_last stays so)
         fmt = torch.channels_last if L.is_channels_last_tokens(x) else torch.contiguous_format
-        dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype, memory_format=fmt)
+        if dec_out is not None:     # caller-provided destination (e.g. the first half of a larger batch tensor)
+            if (dec_out.shape != x.shape or dec_out.device != dev or dec_out.dtype != (dec_dtype or x.dtype)
+                    or not dec_out.is_contiguous(memory_format=fmt)):
+                raise ValueError("dec_out must have the shape, device, dtype and memory format of the reconstruction")
+            dec = dec_out
+        else:
+            dec = torch.empty(x.shape, device=dev, dtype=dec_dtype or x.dtype, memory_format=fmt)
     out = L.TrainOut(L.ptr(dec), L.dtype_code(dec) if want_dec else 0, a.layout, L.ptr(stats),
                      L.ActivityOut(L.ptr(dead), L.ptr(freq), L.ptr(n_active)))
     return out, StepResult(stats, dead, freq, n_active, dec)
@@ -124,14 +130,16 @@ def _single_pixel_fixup(x, res):
 
 
 def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
-                   betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None):
+                   betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None, dec_out=None):
     """One pass of ModelPipeline.hook's train branch (model_pipeline.py:380-420) for SaeMLP, fully on device.
     params = (encoder.weight, encoder.bias, decoder.weight, decoder.bias); updated in place with the Adam moments.
     step_dev: optional int32 CUDA scalar holding the steps taken so far; the call increments it on the device and
-    `step` is ignored (CUDA-graph capture: nothing step-dependent in the launch parameters)."""
+    `step` is ignored (CUDA-graph capture: nothing step-dependent in the launch parameters).
+    dec_out: optional destination of the reconstruction (shape / dtype / memory format of x), e.g. a slice of a larger
+    batch tensor, instead of a fresh allocation."""
     a, x = L.acts_of(x)
     p = _sae_params(*params)
-    out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
+    out, res = _train_out(x, a, p.F, want_dec, dec_dtype, dec_out)
     st = _adam_state(adam_m, adam_v)
     opt = _opt(optimizer, step, lr, betas, eps, step_dev)
     L.check(L.load().svb_sae_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
@@ -141,11 +149,11 @@ def sae_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, o
 
 
 def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer="constrained_adam",
-                     betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None):
+                     betas=(0.9, 0.999), eps=1e-8, want_dec=True, dec_dtype=None, step_dev=None, dec_out=None):
     """Same for GatedSae; params = (W_gate, b_gate, b_mag, r_mag, decoder.weight, decoder.bias)."""
     a, x = L.acts_of(x)
     p = _gated_params(*params)
-    out, res = _train_out(x, a, p.F, want_dec, dec_dtype)
+    out, res = _train_out(x, a, p.F, want_dec, dec_dtype, dec_out)
     st = _adam_state(adam_m, adam_v)
     opt = _opt(optimizer, step, lr, betas, eps, step_dev)
     L.check(L.load().svb_gated_train_step(L.handle(x.device), L.stream_ptr(x.device), C.byref(a), C.byref(p), C.byref(st),
