@@ -858,7 +858,8 @@ def run_svb(args):
         e2e = {"value": g_tokens / (ms_e2e / n_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": host[0].numel() * 2 * world, "d2h_bytes_per_step": (L.STATS_LEN + 3) * 4 * world,
                "ms_per_step": ms_e2e / n_e2e, "images_per_s": g_images / (ms_e2e / n_e2e * 1e-3),
-               "svb_launches_per_step": (lib.svb_launch_count() - launches_e0) / n_e2e,
+               "svb_launches_per_step": (pipe.graph_svb_launches if pipe._graph is not None
+                                         else (lib.svb_launch_count() - launches_e0) / n_e2e),
                "last_batch": {"loss": sh[0], "rec": sh[1], "kld": sh[L.STATS_LEN], "same_classification": sh[L.STATS_LEN + 1],
                               "loss_diff": sh[L.STATS_LEN + 2]},
                "numa_node_rank0": numa_node,

@@ -61,6 +61,7 @@ class ModelPipeline:
         self._step_dev = None
         self._capturing = False
         self._graph_ws = 0
+        self.graph_svb_launches = 0
         self.sae_model = sae_model
         self.sae_model_name = sae_model_name
         if sae_model_name not in ("sae_mlp", "gated_sae"):
@@ -312,11 +313,14 @@ class ModelPipeline:
             torch.cuda.synchronize(inputs.device)
             self._graph = torch.cuda.CUDAGraph()
             self._capturing = True
+            launches0 = L.load().svb_launch_count()
             try:
                 with torch.cuda.graph(self._graph):
                     static_out = self._forward_and_compare(static_in, static_tgt)
             finally:
                 self._capturing = False
+            # kernels of libsvb inside one replay (svb_launch_count only sees launches issued through the C ABI)
+            self.graph_svb_launches = L.load().svb_launch_count() - launches0
             self._graph_static = (static_in, static_tgt, static_out, self._last, self.batch_model_stats,
                                   dict(self.batch_dead_units), dict(self.batch_neuron_frequency))
             self._graph_ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
