@@ -29,19 +29,20 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 // strip of SW output columns, channel vector); threads run over the channel vectors first (coalesced 16-byte accesses).
 // The (SW-1)*S+K input columns of a strip are reduced vertically once and shared by the windows of the strip; all of
 // a thread's loads are independent and unpredicated (18 / 27 of them in flight for 3x3 windows at stride 1 / 2).
-template <int K, int S, int SW>
+// Idx: unsigned (32-bit divisions; every GoogLeNet shape) or long long (more than 2^31 work items).
+template <int K, int S, int SW, typename Idx>
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int C8, int pad, int OH,
                     int OW, int strips, long long total) {
   constexpr int NC = (SW - 1) * S + K;
-  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= total) return;
-  const int c = static_cast<int>(i % C8);
-  long long r = i / C8;
-  const int s = static_cast<int>(r % strips);
-  r /= strips;
-  const int oh = static_cast<int>(r % OH);
-  const long long n = r / OH;
+  const Idx i = static_cast<Idx>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= static_cast<Idx>(total)) return;
+  const int c = static_cast<int>(i % static_cast<Idx>(C8));
+  Idx r = i / static_cast<Idx>(C8);
+  const int s = static_cast<int>(r % static_cast<Idx>(strips));
+  r /= static_cast<Idx>(strips);
+  const int oh = static_cast<int>(r % static_cast<Idx>(OH));
+  const long long n = static_cast<long long>(r / static_cast<Idx>(OH));
   const int ow0 = s * SW, ih0 = oh * S - pad, iw0 = ow0 * S - pad;
   const uint4* img = in + n * H * W * C8 + c;
   // Positions outside the image count as -inf.  Every window that is stored starts inside the image (or its left / top
@@ -91,10 +92,11 @@ __device__ __forceinline__ uint32_t bias_relu2(uint32_t v, uint32_t b, bool relu
 
 // src [positions, C8] (dense convolution output), bias [C8]; every channel vector goes to the destination whose
 // channel range holds it: dst[seg][(t * ld8 + off8 + (c - begin8))].  Two vectors per thread, half the tensor apart.
-__device__ __forceinline__ void bias_relu_emit(long long i, uint4 v, const uint4* __restrict__ bias, const SegTable& tab,
+template <typename Idx>
+__device__ __forceinline__ void bias_relu_emit(Idx i, uint4 v, const uint4* __restrict__ bias, const SegTable& tab,
                                                int C8, bool relu) {
-  const int c = static_cast<int>(i % C8);
-  const long long t = i / C8;
+  const int c = static_cast<int>(i % static_cast<Idx>(C8));
+  const long long t = static_cast<long long>(i / static_cast<Idx>(C8));
   const uint4 b = __ldg(bias + c);
   const uint4 o = make_uint4(bias_relu2(v.x, b.x, relu), bias_relu2(v.y, b.y, relu), bias_relu2(v.z, b.z, relu),
                              bias_relu2(v.w, b.w, relu));
@@ -104,13 +106,15 @@ __device__ __forceinline__ void bias_relu_emit(long long i, uint4 v, const uint4
       tab.dst[sgi][t * tab.ld8[sgi] + tab.off8[sgi] + (c - tab.begin8[sgi])] = o;
   }
 }
+template <typename Idx>
 __global__ void __launch_bounds__(256)
 bias_relu_scatter_kernel(const uint4* __restrict__ src, const uint4* __restrict__ bias, const __grid_constant__ SegTable tab,
-                         int C8, long long total, int relu) {
-  const long long half = (total + 1) / 2;
-  const long long i0 = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+                         int C8, long long total_, int relu) {
+  const Idx total = static_cast<Idx>(total_);
+  const Idx half = (total + 1) / 2;
+  const Idx i0 = static_cast<Idx>(blockIdx.x) * 256 + threadIdx.x;
   if (i0 >= half) return;
-  const long long i1 = i0 + half;
+  const Idx i1 = i0 + half;
   const bool two = i1 < total;
   const uint4 v0 = __ldcs(src + i0);
   const uint4 v1 = two ? __ldcs(src + i1) : make_uint4(0, 0, 0, 0);
@@ -123,9 +127,14 @@ void launch_pool(cudaStream_t st, const void* in, void* out, int64_t N, int H, i
   constexpr int SW = 4;
   const int strips = (OW + SW - 1) / SW;
   const long long total = static_cast<long long>(N) * OH * strips * C8;
-  (maxpool_nhwc_kernel<K, S, SW><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-       static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, C8, pad, OH, OW, strips, total),
-   svb::count_launch());
+  if (total < (1LL << 31))
+    (maxpool_nhwc_kernel<K, S, SW, unsigned><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+         static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, C8, pad, OH, OW, strips, total),
+     svb::count_launch());
+  else
+    (maxpool_nhwc_kernel<K, S, SW, long long><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+         static_cast<const uint4*>(in), static_cast<uint4*>(out), H, W, C8, pad, OH, OW, strips, total),
+     svb::count_launch());
 }
 
 // torch's pooling_output_shape (ATen/native/Pool.h) for dilation 1
@@ -185,9 +194,14 @@ extern "C" int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* sr
   if (covered != C) return fail(SVB_ERR_BAD_ARG, "the destinations cover %d of %d channels", covered, C);
   const long long total = positions * (C / 8);
   const long long half = (total + 1) / 2;
-  (bias_relu_scatter_kernel<<<static_cast<unsigned>((half + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-       static_cast<const uint4*>(src), static_cast<const uint4*>(bias), tab, C / 8, total, relu),
-   svb::count_launch());
+  if (total < (1LL << 31))
+    (bias_relu_scatter_kernel<unsigned><<<static_cast<unsigned>((half + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+         static_cast<const uint4*>(src), static_cast<const uint4*>(bias), tab, C / 8, total, relu),
+     svb::count_launch());
+  else
+    (bias_relu_scatter_kernel<long long><<<static_cast<unsigned>((half + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+         static_cast<const uint4*>(src), static_cast<const uint4*>(bias), tab, C / 8, total, relu),
+     svb::count_launch());
   SVB_LAUNCH_CHECK("bias_relu_scatter");
   return 0;
 }
