@@ -127,6 +127,12 @@ def _make_fused_classes():
                     self._svb_packed, self._svb_key = ops.conv1_pack_weights(w), key
                 return ops.conv1_stem(x, self._svb_packed, self.conv.bias)
             y = _conv_nobias(x, self.conv)
+            if getattr(self, "_svb_defer_bias", False):
+                # the next module is a max-pool: relu(max(y) + b) == max(relu(y + b)) exactly (a per-channel constant,
+                # a monotone rounding and a monotone relu commute with max), so the bias pass runs on the POOLED tensor
+                # (a quarter of the bytes).  The raw convolution output is tagged; FusedMaxPool2d finishes it.
+                y._svb_pending_bias = self.conv.bias
+                return y
             ops.bias_relu_scatter(y, self.conv.bias, [(y, 0, y.shape[1])])
             return y
 
@@ -135,8 +141,15 @@ def _make_fused_classes():
             k, s, p = self.kernel_size, self.stride, self.padding
             if not (_fast_input(x) and isinstance(k, int) and isinstance(s, int) and isinstance(p, int)
                     and self.dilation == 1 and not self.return_indices and (k, s) in ((3, 1), (3, 2), (2, 2))):
+                pending = getattr(x, "_svb_pending_bias", None)
+                if pending is not None:          # cannot pool this one here: finish the deferred bias + relu first
+                    x = x.add(pending.view(1, -1, 1, 1)).relu_()
                 return super().forward(x)
-            return ops.maxpool_nhwc(x, k, s, p, self.ceil_mode)
+            y = ops.maxpool_nhwc(x, k, s, p, self.ceil_mode)
+            pending = getattr(x, "_svb_pending_bias", None)
+            if pending is not None:
+                ops.bias_relu_scatter(y, pending, [(y, 0, y.shape[1])])
+            return y
 
     class FusedInception(Inception):
         """The three 1x1 convolutions that read the block's input run as ONE convolution (weights concatenated once);
@@ -177,6 +190,11 @@ def fuse_forward(model):
     """In place: GoogLeNet's BasicConv2d / MaxPool2d / Inception modules get the fused forwards above (class swap; the
     parameters, module names, hooks and state_dict are untouched).  Needs a BatchNorm-folded model to take effect."""
     BasicConv2d, Inception, FusedBasicConv2d, FusedMaxPool2d, FusedInception = _make_fused_classes()
+    # GoogLeNet._forward: conv2 -> conv3 -> maxpool2; conv3's bias + relu pass moves behind the pool (see FusedBasicConv2d)
+    kids = list(model.named_children())
+    for (_, a), (_, b) in zip(kids, kids[1:]):
+        if type(a) is BasicConv2d and type(b) is torch.nn.MaxPool2d and not a._forward_hooks:
+            a._svb_defer_bias = True
     for m in model.modules():
         if type(m) is BasicConv2d:
             m.__class__ = FusedBasicConv2d

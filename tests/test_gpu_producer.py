@@ -161,6 +161,13 @@ def test_fused_forward_matches_the_eager_model():
     e_eager, e_fused = (want.float() - ref).abs().mean().item(), (got.float() - ref).abs().mean().item()
     assert e_fused <= 1.25 * e_eager + 1e-6, (report, e_eager, e_fused)
     print("relative mean error vs fp32 (layer, eager bf16, fused bf16):", report)
+    # conv3's bias + relu pass runs BEHIND maxpool2 on the fused model (relu(max(y) + b) == max(relu(y + b))): the pooled
+    # tensor is bit-identical to conv -> add_ -> relu_ -> max_pool2d
+    h = _nhwc(torch.randn(3, 64, 56, 56, generator=torch.Generator().manual_seed(8)))
+    with torch.no_grad():
+        raw = fused.conv3(h)
+        assert getattr(raw, "_svb_pending_bias", None) is not None
+        assert torch.equal(fused.maxpool2(raw), eager.maxpool2(eager.conv3(h)))
     # a tensor that asks for gradients (what the IE passes send through the layers behind a hooked one) takes
     # torchvision's own forward
     xg = x[:2].clone().requires_grad_(True)
@@ -206,3 +213,43 @@ def test_conv1_stem_rejects_other_shapes():
         ops.conv1_stem(_nhwc(torch.zeros(1, 3, 96, 96)), ops.conv1_pack_weights(w), torch.zeros(64).cuda().bfloat16())
     with pytest.raises(ValueError):
         ops.conv1_pack_weights(torch.zeros(64, 3, 3, 3).cuda().bfloat16())
+
+
+def test_pipeline_on_the_fused_producer_trains_the_same_sae():
+    """ModelPipeline.train_batch (hook on inception3a, same-pass comparison with the original model) on the fused
+    producer: eager launches and the CUDA-graphed batch are bit-identical to each other, and the SAE statistics follow
+    the run on torchvision's eager forward (the activations at mixed3a differ by bf16 rounding only)."""
+    import copy
+    from sparse_vision_b200.model_pipeline import ModelPipeline
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    from sparse_vision_b200.producer import fuse_forward, synthetic_googlenet, to_producer_format
+    dev = torch.device("cuda:0")
+    eager = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=True, fold_bn=True)
+    B = 8
+    xs = [_nhwc(torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(50 + i))) for i in range(6)]
+    ys = [torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(90 + i)).cuda() for i in range(6)]
+
+    def run(base, graph):
+        torch.manual_seed(0)
+        sae = SaeMLP(256, 8).to(dev)
+        pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", 1e-3, 5.0, 8,
+                             compare_in_one_pass=True, cuda_graph=graph)
+        pipe.register_hooks(train_sae=True)
+        log = []
+        for x, y in zip(xs, ys):
+            out, _ = pipe.train_batch(x, targets=y)
+            log.append((pipe.batch_scalars(), pipe.batch_model_stats.clone(), out.clone()))
+        pipe.remove_hooks()
+        return pipe, sae, log
+
+    _, s_ref, l_ref = run(copy.deepcopy(eager), False)
+    _, s_fe, l_fe = run(fuse_forward(copy.deepcopy(eager)), False)
+    p_fg, s_fg, l_fg = run(fuse_forward(copy.deepcopy(eager)), True)
+    assert p_fg._graph is not None and p_fg.graph_svb_launches >= 60   # 16 of the SAE step + the producer's own kernels
+    for (sc_e, ms_e, out_e), (sc_g, ms_g, out_g) in zip(l_fe, l_fg):
+        assert sc_e == sc_g and torch.equal(ms_e, ms_g) and torch.equal(out_e, out_g)
+    for a, b in zip(s_fe.param_list(), s_fg.param_list()):
+        assert torch.equal(a, b)
+    for step, ((sc_r, ms_r, _), (sc_f, ms_f, _)) in enumerate(zip(l_ref, l_fe)):
+        for key in ("loss", "rec", "l1", "var_expl"):
+            assert abs(sc_f[key] - sc_r[key]) <= 3e-2 * max(abs(sc_r[key]), 1e-3), (step, key, sc_f[key], sc_r[key])
