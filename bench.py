@@ -498,7 +498,9 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
         saes[n] = SaeMLP(GOOGLENET_LAYERS[n][1], k).to(dev)
     dt = next(base.parameters()).dtype
     g = torch.Generator().manual_seed(40 + rank)
-    batches = [(torch.randn(n_images, 3, 224, 224, generator=g).to(dev, dt),
+    fmt = (torch.channels_last if base.conv1.conv.weight.is_contiguous(memory_format=torch.channels_last)
+           and not base.conv1.conv.weight.is_contiguous() else torch.contiguous_format)
+    batches = [(torch.randn(n_images, 3, 224, 224, generator=g).to(dev, dt).contiguous(memory_format=fmt),
                 torch.randint(0, 1000, (n_images,), generator=g).to(dev)) for _ in range(n_batches)]
     ie = IE(base, hooked_layers(base, list(IE_LAYERS)), saes, dict(IE_LAYERS), device=dev)
 
@@ -536,6 +538,8 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
     top = {n: [int(i) for i in torch.topk(feat[n], 5).indices.tolist()] for n in feat}
     return {"workload": f"configs[4]: node IE over {list(IE_LAYERS)} of GoogLeNet ({dt}), {n_images} images x {n_batches} "
                         f"batches per GPU, 224x224", "n_gpus": world,
+            "base_model": ("layers up to the first hooked one forward-only, channels_last, fused producer kernels; NCHW behind it"
+                           if fmt == torch.channels_last else "NCHW, torchvision's eager forward"),
             "compute_average_images_per_s": n_job / (ms_avg * 1e-3), "compute_node_ie_images_per_s": n_job / (ms_ie * 1e-3),
             "ms_per_batch_node_ie": ms_ie / n_batches, "ms_per_batch_average": ms_avg / n_batches,
             "ms_per_batch_node_ie_passes": [p[1] / n_batches for p in passes],
@@ -885,11 +889,17 @@ def run_svb(args):
     ie = guarded(lambda: ie_section(dev, peaks, world=world)) if "ie" not in skip else None
     ie_pipe = None
     if "ie_pipeline" not in skip:
-        # NCHW for the attribution pass: it needs the BACKWARD of the base model, and cuDNN's bf16 channels_last backward
-        # of GoogLeNet is 4x slower than the NCHW one here (44.5 vs 9.4-12.2 ms per 64-image batch, measured)
+        # The attribution pass needs the BACKWARD of the base model from the loss down to the first hooked layer; cuDNN's
+        # bf16 channels_last backward of GoogLeNet is 4x slower than the NCHW one here (44.5 vs 9.4-12.2 ms per 64-image
+        # batch, measured), so everything behind the first hooked layer is NCHW.  The layers in front of it run forward
+        # only (IE._forward_collect cuts the graph there): channels_last on the fused producer kernels.
         base = None
         torch.cuda.empty_cache()
-        ie_base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=False, fold_bn=True)
+        from sparse_vision_b200.producer import to_attribution_format
+        if args.ie_nchw:
+            ie_base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=False, fold_bn=True)
+        else:
+            ie_base = to_attribution_format(synthetic_googlenet(seed=0), dev, next(iter(IE_LAYERS)), torch.bfloat16)
         ie_pipe = guarded(lambda: ie_pipeline_section(dev, ie_base, world=world))
 
     if rank == 0:
@@ -1013,6 +1023,8 @@ def main():
     ap.add_argument("--no-fuse-producer", action="store_true",
                     help="e2e: torchvision's eager forward (ATen max-pool / add_ / relu_ / cat) instead of "
                          "producer.fuse_forward (libsvb max-pool and bias+relu+concat kernels between the cuDNN convolutions)")
+    ap.add_argument("--ie-nchw", action="store_true",
+                    help="ie_pipeline: the whole base model in NCHW on torchvision's eager forward (no fused head)")
     ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")
     ap.add_argument("--two-pass", action="store_true",
                     help="e2e: compare with a second forward of an unhooked copy (the reference's structure) instead of "

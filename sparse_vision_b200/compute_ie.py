@@ -36,13 +36,23 @@ class IE:
 
     # ------------------------------------------------------------------ activations (+ gradients) of every layer
     def _forward_collect(self, inputs, targets=None):
+        """One forward of the frozen model collecting the hooked layers' outputs and, with `targets`, the gradient of the
+        loss at each of them (get_grad_original, compute_ie.py:270-311).  The reference makes the INPUT IMAGES require
+        grad (:404) and back-propagates to them; only the gradients at the hooked layers are used, so here the first
+        hooked layer the forward reaches hands a detached leaf on: the layers in front of it run without an autograd
+        graph (and on the fused producer kernels when the model has them) and the backward stops there instead of going
+        through the 112x112 / 56x56 stem.  The gradients at the hooked layers are the same numbers."""
         acts, grads, handles = {}, {}, []
 
         def make_hook(name):
             def hook(_m, _i, out):
+                ret = None
+                if targets is not None and not out.requires_grad:
+                    out = ret = out.detach().contiguous().requires_grad_(True)
                 acts[name] = out
-                if targets is not None and out.requires_grad:
+                if targets is not None:
                     out.register_hook(lambda g, n=name: grads.__setitem__(n, g))
+                return ret
             return hook
 
         for name, module in self.layers.items():
@@ -52,9 +62,8 @@ class IE:
                 with torch.no_grad():
                     self.model(inputs)
             else:
-                inputs = inputs.detach().requires_grad_(True)        # compute_ie.py:404
                 with torch.enable_grad():
-                    out = self.model(inputs)
+                    out = self.model(inputs.detach())
                     self.model_criterion(out, targets).backward()    # get_grad_original :299-311
         finally:
             for h in handles:

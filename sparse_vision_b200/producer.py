@@ -191,7 +191,7 @@ def fuse_forward(model):
     parameters, module names, hooks and state_dict are untouched).  Needs a BatchNorm-folded model to take effect."""
     BasicConv2d, Inception, FusedBasicConv2d, FusedMaxPool2d, FusedInception = _make_fused_classes()
     # GoogLeNet._forward: conv2 -> conv3 -> maxpool2; conv3's bias + relu pass moves behind the pool (see FusedBasicConv2d)
-    kids = list(model.named_children())
+    kids = list(model.named_children())      # (a ModuleList of the leading modules works too: to_attribution_format)
     for (_, a), (_, b) in zip(kids, kids[1:]):
         if type(a) is BasicConv2d and type(b) is torch.nn.MaxPool2d and not a._forward_hooks:
             a._svb_defer_bias = True
@@ -202,4 +202,24 @@ def fuse_forward(model):
             m.__class__ = FusedMaxPool2d
         elif type(m) is Inception:
             m.__class__ = FusedInception
+    return model
+
+
+def to_attribution_format(model, device, first_layer, dtype=torch.bfloat16, fold_bn=True):
+    """The frozen base model for the IE passes (compute_ie.py:365-472), which need its BACKWARD from the loss down to the
+    first hooked layer: the modules up to and including `first_layer` (reference or torchvision name) run forward only --
+    channels_last on the fused producer kernels -- and everything behind it stays NCHW (cuDNN's bf16 channels_last
+    backward of GoogLeNet is 4x slower than its NCHW one here).  IE._forward_collect turns the first hooked layer's output
+    into an NCHW leaf, which is where the two formats meet.  Feed it channels_last images."""
+    if fold_bn:
+        model = fold_batchnorm(model.float())
+    model = model.to(device=device, dtype=dtype)
+    first = module_name(first_layer)
+    names = [n for n, _ in model.named_children()]
+    if first not in names:
+        raise ValueError(f"{first_layer} is not a top-level module of the model")
+    head = torch.nn.ModuleList([m for n, m in model.named_children()][:names.index(first) + 1])
+    head.to(memory_format=torch.channels_last)
+    if fold_bn and dtype == torch.bfloat16:
+        fuse_forward(head)
     return model
