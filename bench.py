@@ -482,7 +482,7 @@ def ie_section(dev, peaks, n_images=64, iters=20, world=1):
 IE_LAYERS = {"mixed3a": 8, "mixed4c": 4, "mixed5b": 4}   # cfg5: three GoogLeNet layers, expansion per utils.py:2671-2724
 
 
-def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
+def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1, graph=True):
     """configs[4] end to end: IE.compute_average then IE.compute_node_ie (compute_ie.py:95-226, :365-472) over three
     GoogLeNet layers on 224x224 images -- ONE frozen forward + backward of the base model per batch (cuDNN) and, per
     layer, the SAE encoder / decoder / g W_dec GEMMs and the three reductions of libsvb.  Images are sharded across the
@@ -502,7 +502,7 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
            and not base.conv1.conv.weight.is_contiguous() else torch.contiguous_format)
     batches = [(torch.randn(n_images, 3, 224, 224, generator=g).to(dev, dt).contiguous(memory_format=fmt),
                 torch.randint(0, 1000, (n_images,), generator=g).to(dev)) for _ in range(n_batches)]
-    ie = IE(base, hooked_layers(base, list(IE_LAYERS)), saes, dict(IE_LAYERS), device=dev)
+    ie = IE(base, hooked_layers(base, list(IE_LAYERS)), saes, dict(IE_LAYERS), device=dev, cuda_graph=graph)
 
     def timed(fn):
         if world > 1:
@@ -538,13 +538,17 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1):
     top = {n: [int(i) for i in torch.topk(feat[n], 5).indices.tolist()] for n in feat}
     return {"workload": f"configs[4]: node IE over {list(IE_LAYERS)} of GoogLeNet ({dt}), {n_images} images x {n_batches} "
                         f"batches per GPU, 224x224", "n_gpus": world,
-            "base_model": ("layers up to the first hooked one forward-only, channels_last, fused producer kernels; NCHW behind it"
-                           if fmt == torch.channels_last else "NCHW, torchvision's eager forward"),
+            "base_model": ("NCHW, torchvision's eager forward" if fmt != torch.channels_last else
+                           "channels_last; forward-only on the fused producer kernels up to the first hooked layer; " +
+                           ("cuDNN autograd + libsvb differentiable max-pool behind it"
+                            if base.inception5b.branch1.conv.weight.is_contiguous(memory_format=torch.channels_last)
+                            and not base.inception5b.branch1.conv.weight.is_contiguous() else "NCHW behind it")),
             "compute_average_images_per_s": n_job / (ms_avg * 1e-3), "compute_node_ie_images_per_s": n_job / (ms_ie * 1e-3),
             "ms_per_batch_node_ie": ms_ie / n_batches, "ms_per_batch_average": ms_avg / n_batches,
             "ms_per_batch_node_ie_passes": [p[1] / n_batches for p in passes],
             "ms_per_batch_node_ie_first_pass": ms_ie_first / n_batches,
             "ms_per_batch_node_ie_untimed_passes": [w / n_batches for w in warm],
+            "cuda_graph": bool(ie._graphs),
             "top5_features": top}
 
 
@@ -889,18 +893,19 @@ def run_svb(args):
     ie = guarded(lambda: ie_section(dev, peaks, world=world)) if "ie" not in skip else None
     ie_pipe = None
     if "ie_pipeline" not in skip:
-        # The attribution pass needs the BACKWARD of the base model from the loss down to the first hooked layer; cuDNN's
-        # bf16 channels_last backward of GoogLeNet is 4x slower than the NCHW one here (44.5 vs 9.4-12.2 ms per 64-image
-        # batch, measured), so everything behind the first hooked layer is NCHW.  The layers in front of it run forward
-        # only (IE._forward_collect cuts the graph there): channels_last on the fused producer kernels.
+        # The attribution pass needs the BACKWARD of the base model from the loss down to the first hooked layer
+        # (IE._forward_collect cuts the graph there).  bf16 channels_last throughout: forward-only in front of the leaf on
+        # the fused producer kernels; behind it cuDNN through torch autograd and libsvb's differentiable max-pool.
+        # --ie-nchw-tail / --ie-nchw are the earlier arrangements (NCHW behind the leaf / everywhere).
         base = None
         torch.cuda.empty_cache()
         from sparse_vision_b200.producer import to_attribution_format
         if args.ie_nchw:
             ie_base = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=False, fold_bn=True)
         else:
-            ie_base = to_attribution_format(synthetic_googlenet(seed=0), dev, next(iter(IE_LAYERS)), torch.bfloat16)
-        ie_pipe = guarded(lambda: ie_pipeline_section(dev, ie_base, world=world))
+            ie_base = to_attribution_format(synthetic_googlenet(seed=0), dev, next(iter(IE_LAYERS)), torch.bfloat16,
+                                            nchw_tail=args.ie_nchw_tail)
+        ie_pipe = guarded(lambda: ie_pipeline_section(dev, ie_base, world=world, graph=not args.no_graph))
 
     if rank == 0:
         gemm_phases = {k: v for k, v in phases.items() if k.endswith("_gemm")}
@@ -1023,6 +1028,8 @@ def main():
     ap.add_argument("--no-fuse-producer", action="store_true",
                     help="e2e: torchvision's eager forward (ATen max-pool / add_ / relu_ / cat) instead of "
                          "producer.fuse_forward (libsvb max-pool and bias+relu+concat kernels between the cuDNN convolutions)")
+    ap.add_argument("--ie-nchw-tail", action="store_true",
+                    help="ie_pipeline: NCHW (torchvision's forward, ATen's max-pools) behind the first hooked layer")
     ap.add_argument("--ie-nchw", action="store_true",
                     help="ie_pipeline: the whole base model in NCHW on torchvision's eager forward (no fused head)")
     ap.add_argument("--no-fold-bn", action="store_true", help="e2e: keep the producer's BatchNorm layers un-folded")

@@ -299,6 +299,17 @@ int svb_maxpool_nhwc(svb_handle* h, void* stream, const void* in, int64_t n_imag
 int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* src, const void* bias, int64_t positions, int32_t C,
                           const svb_chan_segment* seg, int32_t n_seg, int32_t relu);
 
+/* The differentiable pair for the IE passes (compute_ie.py:270-311 back-propagates the loss through the base model's
+ * layers behind the first hooked one).  svb_maxpool_nhwc_argmax also writes, per output element, the window offset
+ * kh * kernel + kw of its maximum (one byte; ties and NaN resolved like torch.nn.functional.max_pool2d_with_indices:
+ * the first maximum in (kh, kw) order); svb_maxpool_nhwc_backward routes grad_out through those indices:
+ * grad_in[n, ih, iw, c] = sum of grad_out over the windows whose maximum sits there (a gather: deterministic). */
+int svb_maxpool_nhwc_argmax(svb_handle* h, void* stream, const void* in, int64_t n_images, int32_t H, int32_t W,
+                            int32_t C, int32_t kernel, int32_t stride, int32_t pad, int32_t ceil_mode, void* out,
+                            uint8_t* argmax, int32_t OH, int32_t OW);
+int svb_maxpool_nhwc_backward(svb_handle* h, void* stream, const void* grad_out, const uint8_t* argmax,
+                              int64_t n_images, int32_t H, int32_t W, int32_t C, int32_t kernel, int32_t stride,
+                              int32_t pad, int32_t OH, int32_t OW, void* grad_in);
 /* GoogLeNet's stem convolution (torchvision googlenet.py conv1: 7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 input)
  * with the folded BatchNorm bias and the ReLU in its epilogue: x bf16 NHWC [n, 224, 224, 3] -> out bf16 NHWC
  * [n, 112, 112, 64] = relu(conv(x, w) + bias), fp32 accumulation, ONE rounding to bf16.  The im2col matrix is never

@@ -116,6 +116,10 @@ SYMBOLS = {
                                        C.c_int32, C.c_int64, C.c_int64, _P(TrainOut)]),
     "svb_maxpool_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32]),
+    "svb_maxpool_nhwc_argmax": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_int32]),
+    "svb_maxpool_nhwc_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "svb_bias_relu_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _P(ChanSegment), C.c_int32, C.c_int32]),
     "svb_conv1_pack_weights": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "svb_conv1_7x7s2_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, _vp]),

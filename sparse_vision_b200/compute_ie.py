@@ -22,9 +22,14 @@ from .utils import measure_inactive_units
 
 
 class IE:
-    def __init__(self, model, layers, saes, exp_fac, model_criterion=None, device=None):
+    def __init__(self, model, layers, saes, exp_fac, model_criterion=None, device=None, cuda_graph=False):
         """model: frozen base classifier (eval mode); layers: ordered {name: module} of the hooked layers
-        (compute_ie.py:52); saes: {name: SaeMLP} (:63-72); exp_fac: {name: expansion factor}."""
+        (compute_ie.py:52); saes: {name: SaeMLP} (:63-72); exp_fac: {name: expansion factor}.
+        cuda_graph: compute_node_ie captures the work of one batch -- frozen forward, backward down to the first hooked
+        layer, svb_node_ie_layer per layer: ~500 launches whose host side (Python, autograd, ctypes) takes longer than the
+        3 ms they run -- ONCE per batch shape in a CUDA graph and replays it for every later batch of that shape."""
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         self.model = model
         self.layers = dict(layers)
         self.saes = saes
@@ -48,7 +53,7 @@ class IE:
             def hook(_m, _i, out):
                 ret = None
                 if targets is not None and not out.requires_grad:
-                    out = ret = out.detach().contiguous().requires_grad_(True)
+                    out = ret = out.detach().requires_grad_(True)
                 acts[name] = out
                 if targets is not None:
                     out.register_hook(lambda g, n=name: grads.__setitem__(n, g))
@@ -136,6 +141,49 @@ class IE:
         return out
 
     # ------------------------------------------------------------------ compute_node_ie (:365-472)
+    def _batch_node_ie(self, inputs, targets, averages):
+        """One batch: {layer: (ie_features [F], ie_error [1], ie_neurons [C], tokens)} as un-normalised sums."""
+        acts, grads = self._forward_collect(inputs, targets)
+        out = {}
+        for name, x in acts.items():
+            sae = self.saes[name]
+            f, e, n = ops.node_ie_layer(
+                x.float() if x.dtype not in (torch.float32, torch.bfloat16) else x, grads[name].to(x.dtype),
+                [p.detach() for p in sae.param_list()], averages["encoder_output_average"][name],
+                averages["sae_error_average"][name], averages["original_layer_output_average"][name], scale=1.0)
+            out[name] = (f, e.reshape(1), n, x.shape[0] * x.shape[2] * x.shape[3])
+        return out
+
+    def _graphed_batch_node_ie(self, inputs, targets, averages):
+        from . import _lib as L
+        key = (tuple(inputs.shape), inputs.dtype, inputs.stride(), tuple(targets.shape), targets.dtype,
+               tuple(averages["encoder_output_average"][n].data_ptr() for n in self.layers
+                     if n in averages["encoder_output_average"]))
+        ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
+        entry = self._graphs.get(key)
+        if entry is not None and entry[4] != ws:      # the library's workspace was re-allocated since the capture
+            entry = None
+        if entry is None:
+            static_in, static_tgt = inputs.clone(), targets.clone()
+            side = torch.cuda.Stream(device=inputs.device)
+            side.wait_stream(torch.cuda.current_stream(inputs.device))
+            with torch.cuda.stream(side):              # cuDNN plans, autograd buffers, workspace growth
+                for _ in range(2):
+                    self._batch_node_ie(static_in, static_tgt, averages)
+            torch.cuda.current_stream(inputs.device).wait_stream(side)
+            torch.cuda.synchronize(inputs.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._batch_node_ie(static_in, static_tgt, averages)
+            ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
+            entry = (graph, static_in, static_tgt, static_out, ws)
+            self._graphs[key] = entry
+        graph, static_in, static_tgt, static_out, _ = entry
+        static_in.copy_(inputs)
+        static_tgt.copy_(targets)
+        graph.replay()
+        return static_out
+
     def compute_node_ie(self, batches, averages):
         """batches: iterable of (inputs, targets).  averages: the dict compute_average returned (what :372 loads).
         Returns (ie_sae_features {layer: [F]}, ie_sae_error {layer: scalar}, ie_model_neurons {layer: [C]})."""
@@ -151,21 +199,16 @@ class IE:
                 continue
             ratio = bs / bs_global
             inputs, targets = inputs.to(self.device), targets.to(self.device)
-            acts, grads = self._forward_collect(inputs, targets)
-            for name, x in acts.items():
-                sae = self.saes[name]
-                f, e, n = ops.node_ie_layer(
-                    x.float() if x.dtype not in (torch.float32, torch.bfloat16) else x, grads[name].to(x.dtype),
-                    [p.detach() for p in sae.param_list()], averages["encoder_output_average"][name],
-                    averages["sae_error_average"][name], averages["original_layer_output_average"][name], scale=1.0)
+            per_layer = (self._graphed_batch_node_ie if self.cuda_graph and inputs.is_cuda
+                         else self._batch_node_ie)(inputs, targets, averages)
+            for name, (f, e, n, t) in per_layer.items():
                 if ratio != 1.0:
                     f, e, n = f * ratio, e * ratio, n * ratio
-                t = x.shape[0] * x.shape[2] * x.shape[3]
                 if name not in feat:
-                    feat[name], err[name], neur[name], tokens[name] = f, e.reshape(1).clone(), n, t
+                    feat[name], err[name], neur[name], tokens[name] = f.clone(), e.reshape(1).clone(), n.clone(), t
                 else:
                     feat[name] += f
-                    err[name] += e
+                    err[name] += e.reshape(1)
                     neur[name] += n
                     tokens[name] += t
         for name in self.layers:          # the same collectives on every rank (see compute_average)

@@ -207,6 +207,179 @@ extern "C" int svb_bias_relu_scatter(svb_handle* h, void* stream, const void* sr
 }
 
 namespace {
+// ------------------------------------------------------------------------------------------------ differentiable max-pool
+// The IE passes (compute_ie.py:270-311, get_grad_original) back-propagate the loss through the layers behind the first
+// hooked one; ATen's max-pool forward + backward are 2.5 of the 5.5 ms of that pass (64 images).  Forward with indices:
+// one thread per (image, output position, 8-channel vector) scans the window in ATen's order (kh outer, kw inner) with
+// ATen's rule `(val > max) || isnan(val)` on packed bf16 pairs, so ties go to the FIRST maximum exactly as in
+// max_pool2d_with_indices; the index is the window offset kh*K + kw (one byte per element).  All loads are issued
+// unpredicated with clamped coordinates; positions outside the image are skipped in the comparison.
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_argmax_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint2* __restrict__ arg, int H, int W,
+                           int C8, int pad, int OH, int OW, unsigned total) {
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % static_cast<unsigned>(C8));
+  unsigned r = i / static_cast<unsigned>(C8);
+  const int ow = static_cast<int>(r % static_cast<unsigned>(OW));
+  r /= static_cast<unsigned>(OW);
+  const int oh = static_cast<int>(r % static_cast<unsigned>(OH));
+  const long long n = r / static_cast<unsigned>(OH);
+  const int ih0 = oh * S - pad, iw0 = ow * S - pad;
+  const uint4* img = in + n * H * W * C8 + c;
+  uint4 v[K * K];
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw)
+      v[kh * K + kw] = __ldg(img + (static_cast<long long>(min(max(ih0 + kh, 0), H - 1)) * W + min(max(iw0 + kw, 0), W - 1)) * C8);
+  uint32_t m[4] = {0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u};   // -inf pairs
+  uint32_t idx[4];
+  bool first = true;
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const uint32_t code = static_cast<uint32_t>(kh * K + kw) * 0x00010001u;
+      if (first) {   // ATen starts maxidx at the first position inside the image
+        first = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) idx[q] = code;
+      }
+      const uint32_t w[4] = {v[kh * K + kw].x, v[kh * K + kw].y, v[kh * K + kw].z, v[kh * K + kw].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&m[q]);
+        // (val > max) || isnan(val): ordered greater-than, or val unordered with itself
+        const uint32_t take = __hgt2_mask(a, b) | __hneu2_mask(a, a);
+        m[q] = (w[q] & take) | (m[q] & ~take);
+        idx[q] = (code & take) | (idx[q] & ~take);
+      }
+    }
+  }
+  const long long o = ((n * OH + oh) * OW + ow) * C8 + c;
+  out[o] = make_uint4(m[0], m[1], m[2], m[3]);
+  // pack the eight 16-bit indices into eight bytes (element order preserved)
+  uint2 a8;
+  a8.x = (idx[0] & 0xFFu) | ((idx[0] >> 8) & 0xFF00u) | ((idx[1] & 0xFFu) << 16) | ((idx[1] & 0xFF0000u) << 8);
+  a8.y = (idx[2] & 0xFFu) | ((idx[2] >> 8) & 0xFF00u) | ((idx[3] & 0xFFu) << 16) | ((idx[3] & 0xFF0000u) << 8);
+  arg[o] = a8;
+}
+
+// grad_in[n, ih, iw, c] = sum of grad_out over the windows whose maximum sits at (ih, iw): a gather over the at most
+// ceil(K/S)^2 windows that cover the position (deterministic, no atomics), fp32 accumulation, one rounding.
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_backward_kernel(const uint4* __restrict__ gout, const uint2* __restrict__ arg, uint4* __restrict__ gin,
+                             int H, int W, int C8, int pad, int OH, int OW, unsigned total) {
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % static_cast<unsigned>(C8));
+  unsigned r = i / static_cast<unsigned>(C8);
+  const int iw = static_cast<int>(r % static_cast<unsigned>(W));
+  r /= static_cast<unsigned>(W);
+  const int ih = static_cast<int>(r % static_cast<unsigned>(H));
+  const long long n = r / static_cast<unsigned>(H);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh) {
+    const int th = ih + pad - kh;
+    if (th < 0 || th % S != 0 || th / S >= OH) continue;
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      const int tw = iw + pad - kw;
+      if (tw < 0 || tw % S != 0 || tw / S >= OW) continue;
+      const long long o = ((n * OH + th / S) * OW + tw / S) * C8 + c;
+      const uint2 a8 = __ldg(arg + o);
+      const uint4 g = __ldg(gout + o);
+      const uint32_t code = static_cast<uint32_t>(kh * K + kw);
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t byte = ((e < 4 ? a8.x : a8.y) >> (8 * (e & 3))) & 0xFFu;
+        const float ge = __uint_as_float((e & 1) ? (gw[e >> 1] & 0xFFFF0000u) : (gw[e >> 1] << 16));
+        if (byte == code) acc[e] += ge;
+      }
+    }
+  }
+  uint32_t o4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+    o4[q] = *reinterpret_cast<uint32_t*>(&p2);
+  }
+  gin[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+}
+}  // namespace
+
+extern "C" int svb_maxpool_nhwc_argmax(svb_handle* h, void* stream, const void* in, int64_t n_images, int32_t H, int32_t W,
+                                       int32_t C, int32_t kernel, int32_t stride, int32_t pad, int32_t ceil_mode,
+                                       void* out, uint8_t* argmax, int32_t OH, int32_t OW) {
+  if (!h || !in || !out || !argmax) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (n_images <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(SVB_ERR_BAD_ARG, "empty tensor");
+  if (C % 8 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(argmax) & 7))
+    return fail(SVB_ERR_UNSUPPORTED, "svb_maxpool_nhwc_argmax needs C %% 8 == 0 (C = %d) and aligned pointers", C);
+  if (pad < 0 || 2 * pad > kernel) return fail(SVB_ERR_BAD_ARG, "pad must be at most half the kernel size");
+  if (OH != pool_out_size(H, kernel, stride, pad, ceil_mode) || OW != pool_out_size(W, kernel, stride, pad, ceil_mode))
+    return fail(SVB_ERR_BAD_ARG, "output is %d x %d, expected %d x %d", OH, OW,
+                pool_out_size(H, kernel, stride, pad, ceil_mode), pool_out_size(W, kernel, stride, pad, ceil_mode));
+  const long long total = n_images * OH * OW * (C / 8);
+  if (total >= (1LL << 32) || n_images * H * W * (C / 8) >= (1LL << 32)) return fail(SVB_ERR_UNSUPPORTED, "tensor too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256), tot = static_cast<unsigned>(total);
+#define SVB_POOL_ARG(K_, S_)                                                                                           \
+  (maxpool_nhwc_argmax_kernel<K_, S_><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), \
+                                                               reinterpret_cast<uint2*>(argmax), H, W, C / 8, pad, OH, \
+                                                               OW, tot),                                               \
+   svb::count_launch())
+  if (kernel == 3 && stride == 1) SVB_POOL_ARG(3, 1);
+  else if (kernel == 3 && stride == 2) SVB_POOL_ARG(3, 2);
+  else if (kernel == 2 && stride == 2) SVB_POOL_ARG(2, 2);
+  else return fail(SVB_ERR_UNSUPPORTED, "max-pool %dx%d stride %d is not one of GoogLeNet's (3/1, 3/2, 2/2)", kernel,
+                   kernel, stride);
+#undef SVB_POOL_ARG
+  SVB_LAUNCH_CHECK("maxpool_nhwc_argmax");
+  return 0;
+}
+
+extern "C" int svb_maxpool_nhwc_backward(svb_handle* h, void* stream, const void* grad_out, const uint8_t* argmax,
+                                         int64_t n_images, int32_t H, int32_t W, int32_t C, int32_t kernel,
+                                         int32_t stride, int32_t pad, int32_t OH, int32_t OW, void* grad_in) {
+  if (!h || !grad_out || !argmax || !grad_in) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (n_images <= 0 || H <= 0 || W <= 0 || C <= 0 || OH <= 0 || OW <= 0) return fail(SVB_ERR_BAD_ARG, "empty tensor");
+  if (C % 8 || (reinterpret_cast<uintptr_t>(grad_out) & 15) || (reinterpret_cast<uintptr_t>(grad_in) & 15) ||
+      (reinterpret_cast<uintptr_t>(argmax) & 7))
+    return fail(SVB_ERR_UNSUPPORTED, "svb_maxpool_nhwc_backward needs C %% 8 == 0 (C = %d) and aligned pointers", C);
+  const long long total = n_images * H * W * (C / 8);
+  if (total >= (1LL << 32) || n_images * OH * OW * (C / 8) >= (1LL << 32)) return fail(SVB_ERR_UNSUPPORTED, "tensor too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256), tot = static_cast<unsigned>(total);
+#define SVB_POOL_BWD(K_, S_)                                                                                       \
+  (maxpool_nhwc_backward_kernel<K_, S_><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(grad_out),               \
+                                                                 reinterpret_cast<const uint2*>(argmax),            \
+                                                                 static_cast<uint4*>(grad_in), H, W, C / 8, pad, OH, \
+                                                                 OW, tot),                                          \
+   svb::count_launch())
+  if (kernel == 3 && stride == 1) SVB_POOL_BWD(3, 1);
+  else if (kernel == 3 && stride == 2) SVB_POOL_BWD(3, 2);
+  else if (kernel == 2 && stride == 2) SVB_POOL_BWD(2, 2);
+  else return fail(SVB_ERR_UNSUPPORTED, "max-pool %dx%d stride %d is not one of GoogLeNet's (3/1, 3/2, 2/2)", kernel,
+                   kernel, stride);
+#undef SVB_POOL_BWD
+  SVB_LAUNCH_CHECK("maxpool_nhwc_backward");
+  return 0;
+}
+
+namespace {
 // ------------------------------------------------------------------------------------------------ stem convolution
 // GoogLeNet's conv1 (7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 -> 112x112; googlenet.py of torchvision, built by
 // the reference at utils.py:277-281) + folded BatchNorm bias + ReLU.  cuDNN pads the 3 input channels to 8 and runs a

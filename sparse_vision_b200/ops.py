@@ -514,3 +514,39 @@ def conv1_stem(x, packed_weight, bias, relu=True):
                                           L.ptr(packed_weight), L.ptr(bias), int(bool(relu)), L.ptr(out)),
             "svb_conv1_7x7s2_nhwc")
     return out
+
+
+class _MaxPoolNhwcFn(torch.autograd.Function):
+    """max_pool2d on bf16 channels_last CUDA tensors with a backward (svb_maxpool_nhwc_argmax /
+    svb_maxpool_nhwc_backward): what the IE passes differentiate through behind the first hooked layer."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, stride, pad, ceil_mode):
+        b, c, h, w = x.shape
+        oh, ow = pool_output_size(h, kernel, stride, pad, ceil_mode), pool_output_size(w, kernel, stride, pad, ceil_mode)
+        out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        arg = torch.empty((b, oh, ow, c), device=x.device, dtype=torch.uint8)
+        L.check(L.load().svb_maxpool_nhwc_argmax(L.handle(x.device), L.stream_ptr(x.device), L.ptr(x), b, h, w, c,
+                                                 int(kernel), int(stride), int(pad), int(bool(ceil_mode)), L.ptr(out),
+                                                 L.ptr(arg), oh, ow), "svb_maxpool_nhwc_argmax")
+        ctx.save_for_backward(arg)
+        ctx.geom = (b, c, h, w, int(kernel), int(stride), int(pad), oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        b, c, h, w, kernel, stride, pad, oh, ow = ctx.geom
+        g = grad_out.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        grad_in = torch.empty((b, c, h, w), device=g.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+        L.check(L.load().svb_maxpool_nhwc_backward(L.handle(g.device), L.stream_ptr(g.device), L.ptr(g), L.ptr(arg), b, h,
+                                                   w, c, kernel, stride, pad, oh, ow, L.ptr(grad_in)),
+                "svb_maxpool_nhwc_backward")
+        return grad_in, None, None, None, None
+
+
+def maxpool_nhwc_autograd(x, kernel, stride, pad=0, ceil_mode=False):
+    """maxpool_nhwc for a tensor that requires grad (indices kept for the backward; ties like torch's)."""
+    if not _is_nhwc_bf16(x):
+        raise ValueError("maxpool_nhwc_autograd takes a bf16 channels_last CUDA tensor [B,C,H,W]")
+    return _MaxPoolNhwcFn.apply(x, kernel, stride, pad, ceil_mode)

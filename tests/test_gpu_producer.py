@@ -253,3 +253,75 @@ def test_pipeline_on_the_fused_producer_trains_the_same_sae():
     for step, ((sc_r, ms_r, _), (sc_f, ms_f, _)) in enumerate(zip(l_ref, l_fe)):
         for key in ("loss", "rec", "l1", "var_expl"):
             assert abs(sc_f[key] - sc_r[key]) <= 3e-2 * max(abs(sc_r[key]), 1e-3), (step, key, sc_f[key], sc_r[key])
+
+
+@pytest.mark.parametrize("B,C,H,W,k,s,p", [(2, 480, 28, 28, 3, 2, 0), (2, 256, 28, 28, 3, 1, 1), (2, 832, 14, 14, 2, 2, 0),
+                                           (3, 832, 7, 7, 3, 1, 1), (1, 16, 5, 6, 3, 2, 0), (2, 8, 9, 4, 3, 1, 1)])
+def test_maxpool_nhwc_autograd_matches_torch(B, C, H, W, k, s, p):
+    """Forward with indices + gather backward against torch: the forward is exact; the gradient lands on the same
+    positions as max_pool2d's (ties go to the first maximum in window order -- post-ReLU data with many exact zeros
+    and a coarse grid of positive values makes ties the common case here) and equals the fp32 backward on the same
+    values up to the one bf16 rounding of the sum."""
+    from sparse_vision_b200 import ops
+    g = torch.Generator().manual_seed(B * C + H)
+    x = _nhwc(torch.relu(torch.randn(B, C, H, W, generator=g)).mul(4).round().div(4))      # ties: zeros and a 0.25 grid
+    xa = x.clone().requires_grad_(True)
+    ya = ops.maxpool_nhwc_autograd(xa, k, s, p, True)
+    xt = x.float().requires_grad_(True)
+    yt = F.max_pool2d(xt, k, s, p, ceil_mode=True)
+    assert torch.equal(ya.float(), yt) and ya.is_contiguous(memory_format=torch.channels_last)
+    go = _nhwc(torch.randn(yt.shape, generator=g))
+    ya.backward(go)
+    yt.backward(go.float())
+    want = xt.grad
+    assert xa.grad.dtype == torch.bfloat16 and xa.grad.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(xa.grad.float() != 0, want.bfloat16().float() != 0)
+    assert torch.equal(xa.grad, want.bfloat16())
+    # and against ATen's bf16 backward of the same pool (it accumulates overlapping windows in bf16: a few ulps apart)
+    xb = x.clone().requires_grad_(True)
+    F.max_pool2d(xb, k, s, p, ceil_mode=True).backward(go)
+    assert (xa.grad.float() - xb.grad.float()).abs().max().item() <= 0.05 * go.float().abs().max().item() + 1e-6
+
+
+def test_node_ie_on_the_attribution_format_model_eager_graph_and_nchw():
+    """IE.compute_node_ie on producer.to_attribution_format (bf16 channels_last, fused forward-only head, libsvb's
+    differentiable max-pool behind the leaf): the CUDA-graphed batches reproduce the eager ones bit for bit (also the
+    second sweep, which only replays), and both follow the same frozen model run in NCHW on torchvision's forward and
+    ATen's pools (same function, other kernels: bf16 rounding apart)."""
+    import copy
+    from sparse_vision_b200.compute_ie import IE
+    from sparse_vision_b200.models.sae_mlp import SaeMLP
+    from sparse_vision_b200.producer import (GOOGLENET_LAYERS, hooked_layers, synthetic_googlenet, to_attribution_format,
+                                             to_producer_format)
+    dev = torch.device("cuda:0")
+    layers = {"mixed3a": 8, "mixed4c": 4, "mixed5b": 4}
+    raw = synthetic_googlenet(seed=0)
+    fast = to_attribution_format(copy.deepcopy(raw), dev)
+    plain = to_producer_format(copy.deepcopy(raw), dev, torch.bfloat16, channels_last=False, fold_bn=True)
+    saes = {}
+    for j, (n, k) in enumerate(layers.items()):
+        torch.manual_seed(5 + j)
+        saes[n] = SaeMLP(GOOGLENET_LAYERS[n][1], k).to(dev)
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(6, 3, 224, 224, generator=g).cuda().bfloat16(), torch.randint(0, 1000, (6,), generator=g).cuda())
+               for _ in range(3)]
+    batches_cl = [(x.contiguous(memory_format=torch.channels_last), y) for x, y in batches]
+
+    def run(model, data, graph):
+        ie = IE(model, hooked_layers(model, list(layers)), saes, dict(layers), device=dev, cuda_graph=graph)
+        avg = ie.compute_average([b[0] for b in data])
+        first = ie.compute_node_ie(data, avg)
+        return first, ie.compute_node_ie(data, avg), ie
+
+    (f_e, e_e, n_e), _, _ = run(fast, batches_cl, False)
+    (f_g, e_g, n_g), (f_g2, e_g2, n_g2), ie_g = run(fast, batches_cl, True)
+    assert len(ie_g._graphs) == 1
+    for name in layers:
+        for a, b, c in ((f_e, f_g, f_g2), (n_e, n_g, n_g2)):
+            assert torch.equal(a[name], b[name]) and torch.equal(a[name], c[name]), name
+        assert torch.equal(e_e[name], e_g[name]) and torch.equal(e_e[name], e_g2[name])
+    (f_p, e_p, n_p), _, _ = run(plain, batches, False)
+    for name in layers:
+        scale = f_p[name].abs().max().item()
+        assert (f_e[name] - f_p[name]).abs().max().item() <= 0.15 * scale, name    # a random-weight net amplifies bf16 rounding
+        assert (f_e[name] - f_p[name]).abs().mean().item() <= 0.05 * f_p[name].abs().mean().item(), name
