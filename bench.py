@@ -518,19 +518,17 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1, graph=True
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return r, float(t[0])
 
-    avg, _ = timed(lambda: ie.compute_average([b[0] for b in batches]))          # warm-up (cuDNN autotune, arena)
-    # one full untimed pass: on a fresh box the first process pays cuDNN's lazy kernel loading for the backward of every
-    # layer shape somewhere inside the first complete pass (measured: 38-86 ms per batch in a first pass, 10 ms afterwards)
-    # Two full untimed passes: right after torch.cuda.empty_cache() the caching allocator is cold, and the first passes pay
-    # cudaMalloc for every activation / gradient size of the base model's backward (measured on fresh boxes: 164 and 62 ms
-    # per batch for the first two passes, 10.0 ms from the third on)
-    warm = [timed(lambda: ie.compute_node_ie(batches, avg))[1] for _ in range(2)]
-    ms_ie_first = warm[0]
+    # The reference's order: the averages over all batches first, then the attribution passes with them.
+    timed(lambda: ie.compute_average([b[0] for b in batches]))          # warm-up (cuDNN heuristics, arena, allocator)
+    timed(lambda: ie.compute_average([b[0] for b in batches]))
     avg, ms_avg = timed(lambda: ie.compute_average([b[0] for b in batches]))
-    # compute_average leaves the caching allocator with other block sizes than the attribution pass needs: in a full
-    # bench run (after the e2e / gated / IE sections) the first pass behind it paid 62 ms per batch again, the next
-    # ones 10.0 -- so one more untimed pass in front of the three timed ones
-    warm.append(timed(lambda: ie.compute_node_ie(batches, avg))[1])
+    # Untimed attribution passes: on a fresh box the first one pays cuDNN's lazy kernel loading for the backward of every
+    # layer shape, the allocator's first cudaMallocs and (cuda_graph) the capture of the batch graph -- torch.cuda.graph
+    # also empties the caching allocator, which is why the averages are timed BEFORE the first capture (timed after it,
+    # compute_average paid 100 ms per batch of fresh cudaMallocs).  Measured: 100-260 ms per batch for the first pass,
+    # steady from the second on.
+    warm = [timed(lambda: ie.compute_node_ie(batches, avg))[1] for _ in range(3)]
+    ms_ie_first = warm[0]
     passes = [timed(lambda: ie.compute_node_ie(batches, avg)) for _ in range(3)]
     (feat, err, neur), _ = passes[-1]
     ms_ie = sum(p[1] for p in passes) / len(passes)      # mean of three timed passes
@@ -541,8 +539,8 @@ def ie_pipeline_section(dev, base, n_images=64, n_batches=3, world=1, graph=True
             "base_model": ("NCHW, torchvision's eager forward" if fmt != torch.channels_last else
                            "channels_last; forward-only on the fused producer kernels up to the first hooked layer; " +
                            ("cuDNN autograd + libsvb differentiable max-pool behind it"
-                            if base.inception5b.branch1.conv.weight.is_contiguous(memory_format=torch.channels_last)
-                            and not base.inception5b.branch1.conv.weight.is_contiguous() else "NCHW behind it")),
+                            if base.inception5b.branch2[1].conv.weight.is_contiguous(memory_format=torch.channels_last)
+                            and not base.inception5b.branch2[1].conv.weight.is_contiguous() else "NCHW behind it")),
             "compute_average_images_per_s": n_job / (ms_avg * 1e-3), "compute_node_ie_images_per_s": n_job / (ms_ie * 1e-3),
             "ms_per_batch_node_ie": ms_ie / n_batches, "ms_per_batch_average": ms_avg / n_batches,
             "ms_per_batch_node_ie_passes": [p[1] / n_batches for p in passes],

@@ -76,6 +76,26 @@ class IE:
         return {k: v.detach() for k, v in acts.items()}, grads
 
     # ------------------------------------------------------------------ compute_average (:95-226)
+    def _batch_average(self, inputs):
+        """One batch: {layer: (sum of encoder outputs [F,H,W], of SAE errors [C,H,W], of layer outputs [C,H,W] over the
+        images, dead units bool [F], sparsity as a device scalar)} -- no host synchronisation."""
+        acts, _ = self._forward_collect(inputs)
+        out = {}
+        for name, x in acts.items():
+            sae = self.saes[name]
+            b, c, h, w = x.shape
+            enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False,
+                                          out_dtype=torch.bfloat16)
+            dead, _, n_active = ops.measure_inactive(enc)                                  # 2-D call, as at :155
+            sparsity = torch.mean(n_active / (enc.shape[1] / self.exp_fac[name]))          # utils.py:2062-2066
+            # per-position sums over the images on libsvb (one read of each tensor); the SAE error x - dec is
+            # never materialised: its sum is the difference of the two sums
+            enc_sum = ops.image_sum(enc, b).t().reshape(-1, h, w).contiguous()             # [F,H,W]; all-reduced later
+            x_sum = ops.image_sum(x if x.dtype in (torch.float32, torch.bfloat16) else x.float(), b)   # [C,H,W]
+            err_sum = x_sum - ops.image_sum(dec, b).t().reshape(c, h, w)
+            out[name] = (enc_sum, err_sum, x_sum, dead.bool(), sparsity)
+        return out
+
     def compute_average(self, batches):
         """batches: iterable of input tensors (or (inputs, ...) tuples).  Returns dicts keyed by layer:
         encoder_output_average [F,H,W], sae_error_average [C,H,W], original_layer_output_average [C,H,W],
@@ -87,27 +107,19 @@ class IE:
                 continue
             bs = inputs.shape[0]
             n_samples += bs
-            acts, _ = self._forward_collect(inputs)
-            for name, x in acts.items():
-                sae = self.saes[name]
-                b, c, h, w = x.shape
-                enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False,
-                                              out_dtype=torch.bfloat16)
-                dead, sparsity, _ = measure_inactive_units(enc, self.exp_fac[name])        # 2-D call, as at :155
-                # per-position sums over the images on libsvb (one read of each tensor); the SAE error x - dec is
-                # never materialised: its sum is the difference of the two sums
-                enc_sum = ops.image_sum(enc, b).t().reshape(-1, h, w).contiguous()         # [F,H,W]; all-reduced later
-                x_sum = ops.image_sum(x if x.dtype in (torch.float32, torch.bfloat16) else x.float(), b)   # [C,H,W]
-                err_sum = x_sum - ops.image_sum(dec, b).t().reshape(c, h, w)
+            per_layer = (self._graphed(self._batch_average, inputs) if self.cuda_graph and inputs.is_cuda
+                         else self._batch_average(inputs))
+            for name, (enc_sum, err_sum, x_sum, dead, sp) in per_layer.items():
                 if name not in sums:
-                    sums[name] = {"enc": enc_sum, "err": err_sum, "x": x_sum, "dead": dead, "sp": sparsity * bs}
+                    sums[name] = {"enc": enc_sum.clone(), "err": err_sum.clone(), "x": x_sum.clone(), "dead": dead.clone(),
+                                  "sp": sp.double() * bs}
                 else:
                     s = sums[name]
                     s["enc"] += enc_sum
                     s["err"] += err_sum
                     s["x"] += x_sum
                     s["dead"] = s["dead"] & dead                                          # :201
-                    s["sp"] += sparsity * bs
+                    s["sp"] = s["sp"] + sp.double() * bs
         n_global = self._all_reduce_counts(n_samples)
         out = {"encoder_output_average": {}, "sae_error_average": {}, "original_layer_output_average": {},
                "dead_units": {}, "sparsity": {}}
@@ -122,12 +134,13 @@ class IE:
                     if n not in sums:
                         z = lambda *s: torch.zeros(*s, device=self.device)
                         sums[n] = {"enc": z(f, h, w), "err": z(c, h, w), "x": z(c, h, w),
-                                   "dead": torch.ones(f, dtype=torch.bool, device=self.device), "sp": 0.0}
+                                   "dead": torch.ones(f, dtype=torch.bool, device=self.device),
+                                   "sp": torch.zeros((), dtype=torch.float64, device=self.device)}
         for name in self.layers:
             if name not in sums:
                 continue
             s = sums[name]
-            sp = torch.tensor([s["sp"]], device=self.device, dtype=torch.float64)
+            sp = s["sp"].reshape(1).to(device=self.device, dtype=torch.float64)
             dead_i = s["dead"].to(torch.int32)
             if self._dp():
                 for t in (s["enc"], s["err"], s["x"], sp):
@@ -154,35 +167,42 @@ class IE:
             out[name] = (f, e.reshape(1), n, x.shape[0] * x.shape[2] * x.shape[3])
         return out
 
-    def _graphed_batch_node_ie(self, inputs, targets, averages):
+    def _graphed(self, fn, *tensors, extra=(), key=()):
+        """fn(*tensors, *extra) captured once per (function, tensor shapes / strides, key) in a CUDA graph and replayed:
+        the tensors are copied into the capture's static inputs, the result is the capture's static output (read it
+        before the next replay).  Two eager runs on a side stream come first (cuDNN plans, autograd buffers, growth of
+        the library's workspace); a re-allocated workspace invalidates the capture."""
         from . import _lib as L
-        key = (tuple(inputs.shape), inputs.dtype, inputs.stride(), tuple(targets.shape), targets.dtype,
-               tuple(averages["encoder_output_average"][n].data_ptr() for n in self.layers
-                     if n in averages["encoder_output_average"]))
-        ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
-        entry = self._graphs.get(key)
-        if entry is not None and entry[4] != ws:      # the library's workspace was re-allocated since the capture
+        dev = tensors[0].device
+        k = (fn.__name__, tuple((tuple(t.shape), t.dtype, t.stride()) for t in tensors), tuple(key))
+        ws = L.load().svb_workspace_bytes(L.handle(dev))
+        entry = self._graphs.get(k)
+        if entry is not None and entry[3] != ws:
             entry = None
         if entry is None:
-            static_in, static_tgt = inputs.clone(), targets.clone()
-            side = torch.cuda.Stream(device=inputs.device)
-            side.wait_stream(torch.cuda.current_stream(inputs.device))
-            with torch.cuda.stream(side):              # cuDNN plans, autograd buffers, workspace growth
+            static = [t.clone() for t in tensors]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._batch_node_ie(static_in, static_tgt, averages)
-            torch.cuda.current_stream(inputs.device).wait_stream(side)
-            torch.cuda.synchronize(inputs.device)
+                    fn(*static, *extra)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self._batch_node_ie(static_in, static_tgt, averages)
-            ws = L.load().svb_workspace_bytes(L.handle(inputs.device))
-            entry = (graph, static_in, static_tgt, static_out, ws)
-            self._graphs[key] = entry
-        graph, static_in, static_tgt, static_out, _ = entry
-        static_in.copy_(inputs)
-        static_tgt.copy_(targets)
+                static_out = fn(*static, *extra)
+            entry = (graph, static, static_out, L.load().svb_workspace_bytes(L.handle(dev)))
+            self._graphs[k] = entry
+        graph, static, static_out, _ = entry
+        for dst, src in zip(static, tensors):
+            dst.copy_(src)
         graph.replay()
         return static_out
+
+    def _graphed_batch_node_ie(self, inputs, targets, averages):
+        key = tuple(averages["encoder_output_average"][n].data_ptr() for n in self.layers
+                    if n in averages["encoder_output_average"])      # the averages are baked into the capture by address
+        return self._graphed(self._batch_node_ie, inputs, targets, extra=(averages,), key=key)
 
     def compute_node_ie(self, batches, averages):
         """batches: iterable of (inputs, targets).  averages: the dict compute_average returned (what :372 loads).

@@ -311,11 +311,17 @@ def test_node_ie_on_the_attribution_format_model_eager_graph_and_nchw():
         ie = IE(model, hooked_layers(model, list(layers)), saes, dict(layers), device=dev, cuda_graph=graph)
         avg = ie.compute_average([b[0] for b in data])
         first = ie.compute_node_ie(data, avg)
+        ie.last_avg = avg
         return first, ie.compute_node_ie(data, avg), ie
 
-    (f_e, e_e, n_e), _, _ = run(fast, batches_cl, False)
+    (f_e, e_e, n_e), _, ie_e = run(fast, batches_cl, False)
     (f_g, e_g, n_g), (f_g2, e_g2, n_g2), ie_g = run(fast, batches_cl, True)
-    assert len(ie_g._graphs) == 1
+    assert len(ie_g._graphs) == 2                      # one capture for compute_average's batches, one for compute_node_ie's
+    for key in ("encoder_output_average", "sae_error_average", "original_layer_output_average", "dead_units"):
+        for name in layers:
+            assert torch.equal(ie_e.last_avg[key][name], ie_g.last_avg[key][name]), (key, name)
+    for name in layers:
+        assert abs(ie_e.last_avg["sparsity"][name] - ie_g.last_avg["sparsity"][name]) <= 1e-9
     for name in layers:
         for a, b, c in ((f_e, f_g, f_g2), (n_e, n_g, n_g2)):
             assert torch.equal(a[name], b[name]) and torch.equal(a[name], c[name]), name
