@@ -310,6 +310,19 @@ int svb_maxpool_nhwc_argmax(svb_handle* h, void* stream, const void* in, int64_t
 int svb_maxpool_nhwc_backward(svb_handle* h, void* stream, const void* grad_out, const uint8_t* argmax,
                               int64_t n_images, int32_t H, int32_t W, int32_t C, int32_t kernel, int32_t stride,
                               int32_t pad, int32_t OH, int32_t OW, void* grad_in);
+/* Backward of svb_bias_relu_scatter for the IE passes: the dense gradient of a convolution output whose relu(. + bias)
+ * went to channel range(s) of other tensors.  dst[t, c_begin + c] = y[t, y_offset + c] > 0 ? grad[t, grad_offset + c] : 0
+ * (torch's threshold_backward: grad * (result > 0)); `y` holds the forward RESULT of the range, `grad` the gradient
+ * that arrived for it.  Ranges consecutive from 0, covering C; everything a multiple of 8; bf16. */
+typedef struct svb_grad_segment {
+  const void* grad;       /* bf16 [positions, grad_channels] */
+  const void* y;          /* bf16 [positions, y_channels] */
+  int32_t c_begin, c_count;
+  int32_t grad_channels, grad_offset;
+  int32_t y_channels, y_offset;
+} svb_grad_segment;
+int svb_relu_grad_gather(svb_handle* h, void* stream, int64_t positions, int32_t C, const svb_grad_segment* seg,
+                         int32_t n_seg, void* dst);
 /* GoogLeNet's stem convolution (torchvision googlenet.py conv1: 7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 input)
  * with the folded BatchNorm bias and the ReLU in its epilogue: x bf16 NHWC [n, 224, 224, 3] -> out bf16 NHWC
  * [n, 112, 112, 64] = relu(conv(x, w) + bias), fp32 accumulation, ONE rounding to bf16.  The im2col matrix is never

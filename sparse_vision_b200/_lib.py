@@ -72,6 +72,11 @@ class ChanSegment(C.Structure):
                 ("dst_offset", C.c_int32)]
 
 
+class GradSegment(C.Structure):
+    _fields_ = [("grad", _vp), ("y", _vp), ("c_begin", C.c_int32), ("c_count", C.c_int32), ("grad_channels", C.c_int32),
+                ("grad_offset", C.c_int32), ("y_channels", C.c_int32), ("y_offset", C.c_int32)]
+
+
 MAX_CHAN_SEGMENTS = 4
 CONV1_PACKED_ELEMS = 64 * 232
 
@@ -120,6 +125,7 @@ SYMBOLS = {
                                           C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_int32]),
     "svb_maxpool_nhwc_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "svb_relu_grad_gather": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _P(GradSegment), C.c_int32, _vp]),
     "svb_bias_relu_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _P(ChanSegment), C.c_int32, C.c_int32]),
     "svb_conv1_pack_weights": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "svb_conv1_7x7s2_nhwc": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, _vp]),

@@ -380,6 +380,77 @@ extern "C" int svb_maxpool_nhwc_backward(svb_handle* h, void* stream, const void
 }
 
 namespace {
+// ------------------------------------------------------------------------------------------------ backward of bias + relu + concat
+// The inverse of bias_relu_scatter for the IE passes: dst[t, begin + c] = y[t, y_off + c] > 0 ? g[t, g_off + c] : 0, i.e.
+// relu's backward (threshold_backward: grad * (result > 0)) reading the gradient of a block output -- or of a 3x3-reduce
+// tensor -- at its channel range and writing the DENSE gradient of the convolution output that produced the range.
+struct GatherTable {
+  const uint4* g[SVB_MAX_CHAN_SEGMENTS];
+  const uint4* y[SVB_MAX_CHAN_SEGMENTS];
+  int begin8[SVB_MAX_CHAN_SEGMENTS], count8[SVB_MAX_CHAN_SEGMENTS];
+  int g_ld8[SVB_MAX_CHAN_SEGMENTS], g_off8[SVB_MAX_CHAN_SEGMENTS], y_ld8[SVB_MAX_CHAN_SEGMENTS], y_off8[SVB_MAX_CHAN_SEGMENTS];
+  int n;
+};
+__device__ __forceinline__ uint32_t relu_grad2(uint32_t g, uint32_t y) {
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+  return g & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&y), zero);
+}
+__global__ void __launch_bounds__(256)
+relu_grad_gather_kernel(uint4* __restrict__ dst, const __grid_constant__ GatherTable tab, int C8, unsigned total) {
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % static_cast<unsigned>(C8));
+  const long long t = i / static_cast<unsigned>(C8);
+  uint4 o = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int s = 0; s < SVB_MAX_CHAN_SEGMENTS; ++s) {
+    if (s < tab.n && c >= tab.begin8[s] && c < tab.begin8[s] + tab.count8[s]) {
+      const int cc = c - tab.begin8[s];
+      const uint4 g = __ldg(tab.g[s] + t * tab.g_ld8[s] + tab.g_off8[s] + cc);
+      const uint4 y = __ldg(tab.y[s] + t * tab.y_ld8[s] + tab.y_off8[s] + cc);
+      o = make_uint4(relu_grad2(g.x, y.x), relu_grad2(g.y, y.y), relu_grad2(g.z, y.z), relu_grad2(g.w, y.w));
+    }
+  }
+  dst[i] = o;
+}
+}  // namespace
+
+extern "C" int svb_relu_grad_gather(svb_handle* h, void* stream, int64_t positions, int32_t C,
+                                    const svb_grad_segment* seg, int32_t n_seg, void* dst) {
+  if (!h || !seg || !dst) return fail(SVB_ERR_BAD_ARG, "null argument");
+  SVB_ON_DEVICE(h);
+  if (positions <= 0 || C <= 0) return fail(SVB_ERR_BAD_ARG, "empty tensor");
+  if (n_seg < 1 || n_seg > SVB_MAX_CHAN_SEGMENTS) return fail(SVB_ERR_BAD_ARG, "1..%d sources", SVB_MAX_CHAN_SEGMENTS);
+  if (C % 8 || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return fail(SVB_ERR_UNSUPPORTED, "svb_relu_grad_gather needs C %% 8 == 0 (C = %d) and a 16-byte aligned destination", C);
+  GatherTable tab;
+  tab.n = n_seg;
+  int covered = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    const svb_grad_segment& s = seg[i];
+    if (!s.grad || !s.y || (reinterpret_cast<uintptr_t>(s.grad) & 15) || (reinterpret_cast<uintptr_t>(s.y) & 15) ||
+        s.c_begin != covered || s.c_count <= 0 || s.c_count % 8 || s.grad_channels % 8 || s.grad_offset % 8 ||
+        s.y_channels % 8 || s.y_offset % 8 || s.grad_offset < 0 || s.y_offset < 0 ||
+        s.grad_offset + s.c_count > s.grad_channels || s.y_offset + s.c_count > s.y_channels)
+      return fail(SVB_ERR_BAD_ARG, "source %d: channel ranges must be multiples of 8, consecutive from 0 and inside the "
+                  "source rows", i);
+    covered += s.c_count;
+    tab.g[i] = static_cast<const uint4*>(s.grad); tab.y[i] = static_cast<const uint4*>(s.y);
+    tab.begin8[i] = s.c_begin / 8; tab.count8[i] = s.c_count / 8;
+    tab.g_ld8[i] = s.grad_channels / 8; tab.g_off8[i] = s.grad_offset / 8;
+    tab.y_ld8[i] = s.y_channels / 8; tab.y_off8[i] = s.y_offset / 8;
+  }
+  if (covered != C) return fail(SVB_ERR_BAD_ARG, "the sources cover %d of %d channels", covered, C);
+  const long long total = positions * (C / 8);
+  if (total >= (1LL << 32)) return fail(SVB_ERR_UNSUPPORTED, "tensor too large");
+  (relu_grad_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+       static_cast<uint4*>(dst), tab, C / 8, static_cast<unsigned>(total)),
+   svb::count_launch());
+  SVB_LAUNCH_CHECK("relu_grad_gather");
+  return 0;
+}
+
+namespace {
 // ------------------------------------------------------------------------------------------------ stem convolution
 // GoogLeNet's conv1 (7x7, stride 2, pad 3, 3 -> 64 channels, 224x224 -> 112x112; googlenet.py of torchvision, built by
 // the reference at utils.py:277-281) + folded BatchNorm bias + ReLU.  cuDNN pads the 3 input channels to 8 and runs a

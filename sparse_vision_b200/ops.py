@@ -550,3 +550,49 @@ def maxpool_nhwc_autograd(x, kernel, stride, pad=0, ceil_mode=False):
     if not _is_nhwc_bf16(x):
         raise ValueError("maxpool_nhwc_autograd takes a bf16 channels_last CUDA tensor [B,C,H,W]")
     return _MaxPoolNhwcFn.apply(x, kernel, stride, pad, ceil_mode)
+
+
+def relu_grad_gather(sources, like):
+    """Backward of bias_relu_scatter (include/svb.h: svb_relu_grad_gather).  `sources` is a list of
+    (grad, grad_offset, y, y_offset, count): channel range [grad_offset, grad_offset + count) of the gradient tensor
+    `grad` masked by the forward RESULT `y` at [y_offset, ...); the ranges are laid side by side into a new dense bf16
+    channels_last tensor [B, sum(count), H, W] (B, H, W from `like`) = the gradient of the convolution output."""
+    b, _, h, w = like.shape
+    total = sum(int(s[4]) for s in sources)
+    if not 1 <= len(sources) <= L.MAX_CHAN_SEGMENTS:
+        raise ValueError(f"1..{L.MAX_CHAN_SEGMENTS} sources")
+    dst = torch.empty((b, total, h, w), device=like.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    segs = (L.GradSegment * len(sources))()
+    begin = 0
+    for i, (g, g_off, y, y_off, count) in enumerate(sources):
+        for t in (g, y):
+            if not _is_nhwc_bf16(t) or t.shape[0] != b or tuple(t.shape[2:]) != (h, w) or t.device != like.device:
+                raise ValueError("gradients and results are bf16 channels_last tensors of the same batch and spatial size")
+        segs[i] = L.GradSegment(g.data_ptr(), y.data_ptr(), begin, int(count), g.shape[1], int(g_off), y.shape[1], int(y_off))
+        begin += int(count)
+    L.check(L.load().svb_relu_grad_gather(L.handle(like.device), L.stream_ptr(like.device), b * h * w, total, segs,
+                                          len(sources), L.ptr(dst)), "svb_relu_grad_gather")
+    return dst
+
+
+def maxpool_nhwc_with_argmax(x, kernel, stride, pad=0, ceil_mode=False):
+    """(pooled, argmax bytes [B, OH, OW, C]) -- the forward half of maxpool_nhwc_autograd for callers that write their
+    own backward."""
+    b, c, h, w = x.shape
+    oh, ow = pool_output_size(h, kernel, stride, pad, ceil_mode), pool_output_size(w, kernel, stride, pad, ceil_mode)
+    out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    arg = torch.empty((b, oh, ow, c), device=x.device, dtype=torch.uint8)
+    L.check(L.load().svb_maxpool_nhwc_argmax(L.handle(x.device), L.stream_ptr(x.device), L.ptr(x), b, h, w, c, int(kernel),
+                                             int(stride), int(pad), int(bool(ceil_mode)), L.ptr(out), L.ptr(arg), oh, ow),
+            "svb_maxpool_nhwc_argmax")
+    return out, arg
+
+
+def maxpool_nhwc_backward(grad_out, arg, in_shape, kernel, stride, pad):
+    b, c, h, w = in_shape
+    oh, ow = grad_out.shape[2], grad_out.shape[3]
+    grad_in = torch.empty((b, c, h, w), device=grad_out.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    L.check(L.load().svb_maxpool_nhwc_backward(L.handle(grad_out.device), L.stream_ptr(grad_out.device), L.ptr(grad_out),
+                                               L.ptr(arg), b, h, w, c, int(kernel), int(stride), int(pad), oh, ow,
+                                               L.ptr(grad_in)), "svb_maxpool_nhwc_backward")
+    return grad_in

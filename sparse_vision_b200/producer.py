@@ -155,6 +155,45 @@ def _make_fused_classes():
                 ops.bias_relu_scatter(y, pending, [(y, 0, y.shape[1])])
             return y
 
+    def _conv_grad_input(grad, like_input, conv_weight, padding):
+        return torch.ops.aten.convolution_backward(grad, like_input, conv_weight, None, [1, 1], list(padding), [1, 1], False,
+                                                   [0, 0], 1, [True, False, False])[0]
+
+    class _InceptionFn(torch.autograd.Function):
+        """The fused inception forward for a tensor that requires grad (the IE passes behind the first hooked layer),
+        with its backward written out: per branch the ReLU-mask gather of the block gradient's channel range
+        (svb_relu_grad_gather), cuDNN's data gradient of the convolution, libsvb's max-pool backward for branch 4; the
+        three 1x1 convolutions on the block input are ONE data-gradient GEMM over the merged channels."""
+
+        @staticmethod
+        def forward(ctx, x, block):
+            out, t3, t5, arg = block._fused(x, with_argmax=True)
+            ctx.block = block
+            ctx.save_for_backward(x, out, t3, t5, arg)
+            return out
+
+        @staticmethod
+        def backward(ctx, grad_out):
+            x, out, t3, t5, arg = ctx.saved_tensors
+            blk = ctx.block
+            go = grad_out.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            c1, c3r, c3, c5r, c5, cp = blk._widths()
+            w1, _ = blk._merged()
+            g = ops.relu_grad_gather([(go, c1 + c3 + c5, out, c1 + c3 + c5, cp)], x)              # pool projection
+            g = _conv_grad_input(g, x, blk.branch4[1].conv.weight, (0, 0))
+            pool = blk.branch4[0]
+            gx = ops.maxpool_nhwc_backward(g.contiguous(memory_format=torch.channels_last), arg, x.shape, pool.kernel_size,
+                                           pool.stride, pool.padding)
+            g3 = ops.relu_grad_gather([(go, c1, out, c1, c3)], x)
+            g3 = _conv_grad_input(g3, t3, blk.branch2[1].conv.weight, blk.branch2[1].conv.padding)
+            g5 = ops.relu_grad_gather([(go, c1 + c3, out, c1 + c3, c5)], x)
+            g5 = _conv_grad_input(g5, t5, blk.branch3[1].conv.weight, blk.branch3[1].conv.padding)
+            gm = ops.relu_grad_gather([(go, 0, out, 0, c1),
+                                       (g3.contiguous(memory_format=torch.channels_last), 0, t3, 0, c3r),
+                                       (g5.contiguous(memory_format=torch.channels_last), 0, t5, 0, c5r)], x)
+            gx += _conv_grad_input(gm, x, w1, (0, 0))
+            return gx, None
+
     class FusedInception(Inception):
         """The three 1x1 convolutions that read the block's input run as ONE convolution (weights concatenated once);
         every branch's relu(conv + bias) is written straight into its channel range of the block output."""
@@ -167,12 +206,15 @@ def _make_fused_classes():
                 self._svb_b1 = torch.cat([c.bias for c in convs]).contiguous()
             return self._svb_w1, self._svb_b1
 
-        def forward(self, x):
-            convs = [self.branch1, self.branch2[0], self.branch2[1], self.branch3[0], self.branch3[1], self.branch4[1]]
-            if not (_fast_input(x) and all(isinstance(m.bn, torch.nn.Identity) and m.conv.bias is not None for m in convs)):
-                return super().forward(x)
+        def _convs(self):
+            return [self.branch1, self.branch2[0], self.branch2[1], self.branch3[0], self.branch3[1], self.branch4[1]]
+
+        def _widths(self):
+            return tuple(m.conv.out_channels for m in self._convs())
+
+        def _fused(self, x, with_argmax=False):
             b, _, h, w = x.shape
-            c1, c3r, c3, c5r, c5, cp = (m.conv.out_channels for m in convs)
+            c1, c3r, c3, c5r, c5, cp = self._widths()
             new = lambda c: torch.empty((b, c, h, w), device=x.device, dtype=x.dtype,   # noqa: E731
                                         memory_format=torch.channels_last)
             out, t3, t5 = new(c1 + c3 + c5 + cp), new(c3r), new(c5r)
@@ -183,9 +225,26 @@ def _make_fused_classes():
             ops.bias_relu_scatter(y, self.branch2[1].conv.bias, [(out, c1, c3)])
             y = _conv_nobias(t5, self.branch3[1].conv)
             ops.bias_relu_scatter(y, self.branch3[1].conv.bias, [(out, c1 + c3, c5)])
-            y = _conv_nobias(self.branch4[0](x), self.branch4[1].conv)
+            arg = None
+            if with_argmax:
+                pool = self.branch4[0]
+                pooled, arg = ops.maxpool_nhwc_with_argmax(x, pool.kernel_size, pool.stride, pool.padding, pool.ceil_mode)
+            else:
+                pooled = self.branch4[0](x)
+            y = _conv_nobias(pooled, self.branch4[1].conv)
             ops.bias_relu_scatter(y, self.branch4[1].conv.bias, [(out, c1 + c3 + c5, cp)])
-            return out
+            return out, t3, t5, arg
+
+        def forward(self, x):
+            folded = all(isinstance(m.bn, torch.nn.Identity) and m.conv.bias is not None for m in self._convs())
+            if folded and _fast_input(x):
+                return self._fused(x)[0]
+            pool = self.branch4[0]
+            if (folded and x.requires_grad and torch.is_grad_enabled() and _fast_input(x.detach())
+                    and not any(p.requires_grad for p in self.parameters())
+                    and isinstance(pool.kernel_size, int) and (pool.kernel_size, pool.stride) == (3, 1)):
+                return _InceptionFn.apply(x, self)          # frozen block, gradient with respect to its input only
+            return super().forward(x)
 
     return BasicConv2d, Inception, FusedBasicConv2d, FusedMaxPool2d, FusedInception
 

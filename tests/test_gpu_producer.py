@@ -331,3 +331,53 @@ def test_node_ie_on_the_attribution_format_model_eager_graph_and_nchw():
         scale = f_p[name].abs().max().item()
         assert (f_e[name] - f_p[name]).abs().max().item() <= 0.15 * scale, name    # a random-weight net amplifies bf16 rounding
         assert (f_e[name] - f_p[name]).abs().mean().item() <= 0.05 * f_p[name].abs().mean().item(), name
+
+
+def test_relu_grad_gather_matches_threshold_backward():
+    from sparse_vision_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 3, 14, 14
+    out = _nhwc(torch.relu(torch.randn(B, 512, H, W, generator=g)))          # a block output (post-ReLU: exact zeros)
+    t3 = _nhwc(torch.relu(torch.randn(B, 128, H, W, generator=g)))
+    go = _nhwc(torch.randn(B, 512, H, W, generator=g))
+    g3 = _nhwc(torch.randn(B, 128, H, W, generator=g))
+    got = ops.relu_grad_gather([(go, 0, out, 0, 128), (g3, 0, t3, 0, 128), (go, 448, out, 448, 64)], out)
+    want = torch.cat([go[:, :128] * (out[:, :128] > 0), g3 * (t3 > 0), go[:, 448:] * (out[:, 448:] > 0)], 1)
+    assert got.shape == (B, 320, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("name,shape", [("inception3b", (4, 256, 28, 28)), ("inception4d", (3, 512, 14, 14)),
+                                        ("inception5b", (5, 832, 7, 7))])
+def test_fused_inception_backward_matches_autograd(name, shape):
+    """The hand-written backward of the fused inception block (IE passes) against torch autograd through torchvision's
+    forward of the same frozen block: output exact to bf16 rounding, input gradient as close to the fp32 gradient as
+    torch's bf16 autograd is."""
+    import copy
+    from sparse_vision_b200.producer import fuse_forward, synthetic_googlenet, to_producer_format
+    dev = torch.device("cuda:0")
+    eager = to_producer_format(synthetic_googlenet(seed=0), dev, torch.bfloat16, channels_last=True, fold_bn=True)
+    blk_e = getattr(eager, name)
+    blk_f = getattr(fuse_forward(copy.deepcopy(eager)), name)
+    blk_x = copy.deepcopy(blk_e).float()
+    g = torch.Generator().manual_seed(shape[1])
+    x = _nhwc(torch.relu(torch.randn(*shape, generator=g)))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        res = {}
+        for tag, blk, xin in (("eager", blk_e, x.clone()), ("fused", blk_f, x.clone()), ("exact", blk_x, x.float())):
+            xin.requires_grad_(True)
+            y = blk(xin)
+            go = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).cuda().to(y.dtype)
+            go = go.contiguous(memory_format=torch.channels_last)
+            y.backward(go)
+            res[tag] = (y.detach().float(), xin.grad.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert type(blk_f).__name__ == "FusedInception"
+    (y_e, g_e), (y_f, g_f), (y_x, g_x) = res["eager"], res["fused"], res["exact"]
+    assert (y_f - y_x).abs().mean().item() <= 1.25 * (y_e - y_x).abs().mean().item() + 1e-6
+    e_eager, e_fused = (g_e - g_x).abs().mean().item(), (g_f - g_x).abs().mean().item()
+    assert e_fused <= 1.25 * e_eager + 1e-6, (e_eager, e_fused, g_x.abs().mean().item())
+    assert (g_f - g_x).abs().max().item() <= 1.5 * (g_e - g_x).abs().max().item() + 1e-6

@@ -229,7 +229,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     pairs = {"svb_acts": L.Acts, "svb_sae_params": L.SaeParams, "svb_gated_params": L.GatedParams,
              "svb_adam_state": L.AdamState, "svb_opt_config": L.OptConfig, "svb_activity_out": L.ActivityOut,
              "svb_train_out": L.TrainOut, "svb_sae_forward_out": L.SaeForwardOut,
-             "svb_gated_forward_out": L.GatedForwardOut, "svb_chan_segment": L.ChanSegment}
+             "svb_gated_forward_out": L.GatedForwardOut, "svb_chan_segment": L.ChanSegment,
+             "svb_grad_segment": L.GradSegment}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svb.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
