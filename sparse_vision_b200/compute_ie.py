@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .utils import measure_inactive_units
+from .utils import measure_inactive_units_device
 
 
 class IE:
@@ -86,14 +86,13 @@ class IE:
             b, c, h, w = x.shape
             enc, dec, _ = ops.sae_forward(x, *[p.detach() for p in sae.param_list()], want_pre=False,
                                           out_dtype=torch.bfloat16)
-            dead, _, n_active = ops.measure_inactive(enc)                                  # 2-D call, as at :155
-            sparsity = torch.mean(n_active / (enc.shape[1] / self.exp_fac[name]))          # utils.py:2062-2066
+            dead, sparsity, _ = measure_inactive_units_device(enc, self.exp_fac[name])     # 2-D call, as at :155
             # per-position sums over the images on libsvb (one read of each tensor); the SAE error x - dec is
             # never materialised: its sum is the difference of the two sums
             enc_sum = ops.image_sum(enc, b).t().reshape(-1, h, w).contiguous()             # [F,H,W]; all-reduced later
             x_sum = ops.image_sum(x if x.dtype in (torch.float32, torch.bfloat16) else x.float(), b)   # [C,H,W]
             err_sum = x_sum - ops.image_sum(dec, b).t().reshape(c, h, w)
-            out[name] = (enc_sum, err_sum, x_sum, dead.bool(), sparsity)
+            out[name] = (enc_sum, err_sum, x_sum, dead, sparsity)
         return out
 
     def compute_average(self, batches):

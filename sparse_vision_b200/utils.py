@@ -219,14 +219,20 @@ def variance_explained(output, decoder_output):
     return 1 - mod / var
 
 
-def measure_inactive_units(output, expansion_factor):
-    """utils.py:2032-2069 -> (dead units bool [#units], sparsity float, activity frequency [#units])."""
+def measure_inactive_units_device(output, expansion_factor):
+    """measure_inactive_units with the sparsity left on the device as a 0-dim tensor: no host synchronisation (callers
+    that accumulate over batches, CUDA-graph capture)."""
     if output.dim() not in (2, 4):
         raise ValueError(f"Output has unexpected shape {output.dim()}.")
     dead, freq, n_active = ops.measure_inactive(output)
     n_units = output.shape[1]
-    sparsity = torch.mean(n_active / (n_units / expansion_factor)).item()
-    return dead.bool(), sparsity, freq
+    return dead.bool(), torch.mean(n_active / (n_units / expansion_factor)), freq
+
+
+def measure_inactive_units(output, expansion_factor):
+    """utils.py:2032-2069 -> (dead units bool [#units], sparsity float, activity frequency [#units])."""
+    dead, sparsity, freq = measure_inactive_units_device(output, expansion_factor)
+    return dead, sparsity.item(), freq
 
 
 def get_top_k_samples(top_k_samples, batch_top_k_values, batch_top_k_indices, batch_filename_indices, eval_batch_idx,

@@ -310,7 +310,10 @@ def fake_image_sum(t, n_images):
     t = t.float()
     return t.sum(0) if t.dim() == 4 else t.reshape(n_images, -1, t.shape[1]).sum(0)
 ops.sae_forward, ops.node_ie_layer, ops.image_sum = fake_sae_forward, fake_node_ie_layer, fake_image_sum
-cie.measure_inactive_units = O.measure_inactive_units
+def fake_measure_inactive_units_device(out, k):
+    dead, sparsity, freq = O.measure_inactive_units(out, k)
+    return dead, torch.as_tensor(sparsity, dtype=torch.float64), freq
+cie.measure_inactive_units_device = fake_measure_inactive_units_device
 
 def build():
     torch.manual_seed(3)
