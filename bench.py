@@ -815,7 +815,7 @@ def run_svb(args):
         pipe = ModelPipeline(base, sae, "sae_mlp", "inception3a", "constrained_adam", LR, LAMBDA, EXPANSION,
                              data_parallel=world > 1, global_batch_images=g_images if world > 1 else None,
                              model_copy=base_copy, compare_in_one_pass=not args.two_pass,
-                             cuda_graph=world == 1 and not args.no_graph)
+                             cuda_graph=not args.no_graph)
         pipe.register_hooks(train_sae=True)
         gi = torch.Generator().manual_seed(77 + rank)
         host = [torch.randn(B, 3, 224, 224, generator=gi).to(torch.bfloat16).pin_memory() for _ in range(2)]
@@ -857,8 +857,17 @@ def run_svb(args):
         e1.record()
         barrier()
         (ms_e2e,) = job_max(e0.elapsed_time(e1))
+        replicas_identical = None
         if pipe.dp is not None:
             pipe.dp.check()
+            same = True          # every rank stepped the same SAE: the replicas must be bit-identical after the timed batches
+            for prm in sae.param_list():
+                other = prm.detach().clone()
+                dist.broadcast(other, src=0)
+                same &= bool(torch.equal(other, prm.detach()))
+            flag = torch.tensor([1 if same else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            replicas_identical = bool(flag.item())
         pipe.remove_hooks()
         sh = stats_host.tolist()
         e2e = {"value": g_tokens / (ms_e2e / n_e2e * 1e-3), "unit": UNIT,
@@ -869,7 +878,7 @@ def run_svb(args):
                "last_batch": {"loss": sh[0], "rec": sh[1], "kld": sh[L.STATS_LEN], "same_classification": sh[L.STATS_LEN + 1],
                               "loss_diff": sh[L.STATS_LEN + 2]},
                "numa_node_rank0": numa_node,
-               "cuda_graph": pipe._graph is not None,
+               "cuda_graph": pipe._graph is not None, "replicas_bit_identical": replicas_identical,
                "producer": {"channels_last": bool(args.channels_last), "batchnorm_folded": not args.no_fold_bn,
                             "fused_forward": bool(fuse_producer),
                             "original_model": "second forward of an unhooked copy" if args.two_pass else

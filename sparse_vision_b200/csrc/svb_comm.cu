@@ -33,7 +33,8 @@ struct CommArgs {
   long long n_sum, n_max;
   unsigned long long timeout_ns;
   int rank, world;
-  uint32_t epoch;
+  const uint32_t* epoch_ptr;  // LOCAL device word holding the number of this exchange (bumped by a one-thread kernel in
+                              // front of the launch: nothing call-dependent in the launch parameters -> CUDA-graph capture)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -60,12 +61,13 @@ __device__ __forceinline__ void cta_rendezvous(const CommArgs& a, int round) {
   __syncthreads();
   if (threadIdx.x < a.world) {
     const int peer = threadIdx.x;
+    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(a.epoch_ptr);
     __threadfence_system();
-    st_release_sys(a.flag[peer] + (static_cast<size_t>(round) * kCommBlocks + blockIdx.x) * kMaxRanks + a.rank, a.epoch);
+    st_release_sys(a.flag[peer] + (static_cast<size_t>(round) * kCommBlocks + blockIdx.x) * kMaxRanks + a.rank, epoch);
     const uint32_t* mine = a.flag[a.rank] + (static_cast<size_t>(round) * kCommBlocks + blockIdx.x) * kMaxRanks + peer;
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
       if ((++spins & 1023u) == 0) {
         if (*reinterpret_cast<volatile uint32_t*>(a.status) != 0) break;
         if (globaltimer_ns() - t0 > a.timeout_ns) {
@@ -173,13 +175,17 @@ struct svb_comm {
   float* mc = nullptr;           // multicast mapping (NVLS) or null
   bool owned = true;             // false: the region belongs to the caller (svb_comm_attach)
   bool connected = false;
-  uint32_t epoch = 0;
 };
 
 // flags of the two rendezvous rounds, then 64 bytes whose first word is the status
 static size_t comm_flag_bytes() { return sizeof(uint32_t) * 2 * kCommBlocks * kMaxRanks + 64; }
 static uint32_t* comm_status_word(svb_comm* c) {
   return reinterpret_cast<uint32_t*>(c->base + c->capacity) + 2 * kCommBlocks * kMaxRanks;
+}
+// the exchange counter lives beside the status word (zeroed with the region; every rank counts the same exchanges)
+static uint32_t* comm_epoch_word(svb_comm* c) { return comm_status_word(c) + 1; }
+namespace {
+__global__ void comm_epoch_bump_kernel(uint32_t* e) { *e += 1; }
 }
 
 extern "C" int svb_comm_alloc(svb_handle* h, int64_t n_floats, void* ipc_handle_out) {
@@ -296,7 +302,8 @@ extern "C" int svb_comm_allreduce(svb_handle* h, void* stream) {
   a.n_sum = h->sum_elems; a.n_max = h->max_elems; a.rank = c->rank; a.world = c->world;
   a.status = comm_status_word(c);
   a.timeout_ns = static_cast<unsigned long long>(c->timeout_s * 1e9);
-  a.epoch = ++c->epoch;
+  a.epoch_ptr = comm_epoch_word(c);
+  (comm_epoch_bump_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(comm_epoch_word(c)), svb::count_launch());
   // The twin-CTA rendezvous needs all kCommBlocks CTAs of every rank on the machine at the same time: a cooperative
   // launch guarantees exactly that (the grid starts only when all of it fits; it is refused if it never can).
   static int coop_ok = -1;

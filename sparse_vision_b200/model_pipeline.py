@@ -53,8 +53,10 @@ class ModelPipeline:
         # step inside the hook, the comparison with the original model -- is captured ONCE in a CUDA graph and replayed
         # for every later batch of the same shape (one launch instead of several hundred).  The Adam step count then
         # lives on the device (svb_opt_config::step_dev); the per-batch results are static tensors that the next
-        # replay overwrites.  Single process only (the peer-memory exchange keeps host-side epochs).
-        self.cuda_graph = bool(cuda_graph) and not data_parallel
+        # replay overwrites.  Data parallel: only with a fixed global batch (no per-step host exchange of the counts)
+        # and the peer-memory exchange, whose exchange counter lives on the device too; every rank replays its graph
+        # once per batch, in step.
+        self.cuda_graph = bool(cuda_graph) and (not data_parallel or global_batch_images is not None)
         self._graph = None
         self._graph_eager_left = 3
         self._graph_static = None
@@ -141,18 +143,8 @@ class ModelPipeline:
             kw = dict(optimizer=self.sae_optimizer_name, betas=group["betas"], eps=group["eps"])
             if self._capturing:
                 kw["step_dev"] = self._step_dev
-            if self.dp is not None:
-                n_img = output.shape[0]
-                hw = output.shape[2] * output.shape[3] if output.dim() == 4 else 1
-                if self.global_batch_images:
-                    g_img, g_tok = int(self.global_batch_images), int(self.global_batch_images) * hw
-                else:
-                    g_img, g_tok = global_counts(n_img, hw, device=output.device)
-                res = self.dp.step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
-                                   self.sae_expansion_factor, self.sae_optimizer_name, group["betas"], g_img, g_tok,
-                                   eps=group["eps"])
             both = None
-            if self.compare_in_one_pass and self.dp is None and output.dim() == 4:
+            if self.compare_in_one_pass and output.dim() == 4:
                 # [reconstruction; original] for the rest of the network: the step writes its reconstruction straight
                 # into the first half of the 2B batch, the original is copied behind it -- no torch.cat pass
                 fmt = torch.channels_last if is_channels_last_tokens(output) else torch.contiguous_format
@@ -162,7 +154,17 @@ class ModelPipeline:
                 kw["dec_out"] = both[:output.shape[0]]
                 output = x_in
             if self.dp is not None:
-                pass
+                n_img = output.shape[0]
+                hw = output.shape[2] * output.shape[3] if output.dim() == 4 else 1
+                if self.global_batch_images:
+                    g_img, g_tok = int(self.global_batch_images), int(self.global_batch_images) * hw
+                else:
+                    g_img, g_tok = global_counts(n_img, hw, device=output.device)
+                if self._capturing and not self.dp.peer:
+                    raise RuntimeError("cuda_graph=True with data_parallel=True needs the peer-memory exchange")
+                res = self.dp.step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
+                                   self.sae_expansion_factor, self.sae_optimizer_name, group["betas"], g_img, g_tok,
+                                   eps=group["eps"], step_dev=kw.get("step_dev"), dec_out=kw.get("dec_out"))
             elif self.sae_model_name == "sae_mlp":
                 res = ops.sae_train_step(output, params, ms, vs, step, group["lr"], self.sae_lambda_sparse,
                                          self.sae_expansion_factor, **kw)

@@ -165,13 +165,13 @@ def gated_train_step(x, params, adam_m, adam_v, step, lr, lam, expansion_factor,
 class SplitStep:
     """The two halves of a data-parallel step: grads() -> (all-reduce the flat buffer) -> apply()."""
 
-    def __init__(self, kind, x, params, lam, want_dec=True, dec_dtype=None):
+    def __init__(self, kind, x, params, lam, want_dec=True, dec_dtype=None, dec_out=None):
         self.kind = kind
         self.a, self.x = L.acts_of(x)
         self.params = params
         self.p = _sae_params(*params) if kind == "sae_mlp" else _gated_params(*params)
         self.lam = float(lam)
-        self.out, self.res = _train_out(self.x, self.a, self.p.F, want_dec, dec_dtype)
+        self.out, self.res = _train_out(self.x, self.a, self.p.F, want_dec, dec_dtype, dec_out)
         self.lib = L.load()
         self.h = L.handle(self.x.device)
 
@@ -196,10 +196,10 @@ class SplitStep:
         return n.value
 
     def apply(self, adam_m, adam_v, step, lr, expansion_factor, optimizer, betas, eps=1e-8, global_tokens=0,
-              global_images=0):
+              global_images=0, step_dev=None):
         fn = self.lib.svb_sae_step_apply if self.kind == "sae_mlp" else self.lib.svb_gated_step_apply
         st = _adam_state(adam_m, adam_v)
-        opt = _opt(optimizer, step, lr, betas, eps)
+        opt = _opt(optimizer, step, lr, betas, eps, step_dev)
         L.check(fn(self.h, L.stream_ptr(self.x.device), C.byref(self.a), C.byref(self.p), C.byref(st), C.byref(opt), self.lam,
                    int(expansion_factor), int(global_tokens), int(global_images), C.byref(self.out)),
                 "svb_*_step_apply")

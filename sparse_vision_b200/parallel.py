@@ -161,13 +161,13 @@ class DataParallelStep:
         self.mode = None   # 'nvls' | 'symm' | 'ipc' once the peer exchange is connected
 
     def step(self, x_local, params, adam_m, adam_v, step, lr, lam, expansion_factor, optimizer, betas,
-             global_images, global_tokens, want_dec=True, eps=1e-8):
+             global_images, global_tokens, want_dec=True, eps=1e-8, step_dev=None, dec_out=None):
         from . import ops
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
         if self.overlap and self.exchange != "peer" and multi and x_local.is_cuda and self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=x_local.device)
             ops.set_comm_stream(x_local.device, self.comm_stream)
-        ss = ops.SplitStep(self.kind, x_local, params, lam, want_dec=want_dec)
+        ss = ops.SplitStep(self.kind, x_local, params, lam, want_dec=want_dec, dec_out=dec_out)
         addr, n_sum, n_max = ss.grads(global_tokens=global_tokens)
         if multi and x_local.is_cuda and self.exchange == "peer" and self.peer is None:
             self.mode = connect_symmetric_memory(x_local.device, n_sum + n_max, self.group)
@@ -184,7 +184,7 @@ class DataParallelStep:
             all_reduce_flat(flat, n_sum, n_max, self.group, early=early, comm_stream=self.comm_stream)
         self.device = x_local.device
         return ss.apply(adam_m, adam_v, step, lr, expansion_factor, optimizer, betas, eps=eps,
-                        global_tokens=global_tokens, global_images=global_images)
+                        global_tokens=global_tokens, global_images=global_images, step_dev=step_dev)
 
     def check(self):
         """Raises if a peer never arrived at one of the exchanges so far (the parameters are undefined from that step
