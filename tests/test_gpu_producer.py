@@ -326,7 +326,16 @@ def test_node_ie_on_the_attribution_format_model_eager_graph_and_nchw():
         for a, b, c in ((f_e, f_g, f_g2), (n_e, n_g, n_g2)):
             assert torch.equal(a[name], b[name]) and torch.equal(a[name], c[name]), name
         assert torch.equal(e_e[name], e_g[name]) and torch.equal(e_e[name], e_g2[name])
-    (f_p, e_p, n_p), _, _ = run(plain, batches, False)
+    (f_p, e_p, n_p), _, ie_p = run(plain, batches, False)
+    # edge IE and faithfulness cut the network into segments at the hooked layers (leaves): the fused blocks' hand-written
+    # backward is then called once per downstream node with retain_graph -- same numbers as on the plain model up to the
+    # bf16 rounding both carry
+    feats = {"mixed4c": [3, 40, 77], "mixed5b": [5, 9]}
+    edge_f = ie_e.compute_edge_ie(batches_cl[:1], ie_e.last_avg, ["mixed4c", "mixed5b"], feats)
+    edge_p = ie_p.compute_edge_ie(batches[:1], ie_p.last_avg, ["mixed4c", "mixed5b"], feats)
+    for name in edge_p:
+        assert edge_f[name].shape == edge_p[name].shape and torch.isfinite(edge_f[name]).all()
+        assert (edge_f[name] - edge_p[name]).abs().max().item() <= 0.25 * edge_p[name].abs().max().item() + 1e-9, name
     for name in layers:
         scale = f_p[name].abs().max().item()
         assert (f_e[name] - f_p[name]).abs().max().item() <= 0.15 * scale, name    # a random-weight net amplifies bf16 rounding
