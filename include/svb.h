@@ -329,7 +329,7 @@ int svb_relu_grad_gather(svb_handle* h, void* stream, int64_t positions, int32_t
  * built: with 3 channels a kernel row is 21 contiguous values of the input row (csrc/svb_producer.cu).
  * svb_conv1_pack_weights lays the [64, 3, 7, 7] bf16 weights (element strides given) out once as the kernel's
  * B operand: `packed` is SVB_CONV1_PACKED_ELEMS bf16 values. */
-#define SVB_CONV1_PACKED_ELEMS (64 * 232)
+#define SVB_CONV1_PACKED_ELEMS (64 * 168)
 int svb_conv1_pack_weights(svb_handle* h, void* stream, const void* w, int64_t stride_o, int64_t stride_i,
                            int64_t stride_h, int64_t stride_w, void* packed);
 int svb_conv1_7x7s2_nhwc(svb_handle* h, void* stream, const void* x, int64_t n_images, const void* packed_w,

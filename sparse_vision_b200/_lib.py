@@ -78,7 +78,7 @@ class GradSegment(C.Structure):
 
 
 MAX_CHAN_SEGMENTS = 4
-CONV1_PACKED_ELEMS = 64 * 232
+CONV1_PACKED_ELEMS = 64 * 168
 
 # every symbol include/svb.h declares: (name, restype, argtypes)
 _P = C.POINTER

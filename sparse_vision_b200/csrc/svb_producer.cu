@@ -456,14 +456,17 @@ namespace {
 // the reference at utils.py:277-281) + folded BatchNorm bias + ReLU.  cuDNN pads the 3 input channels to 8 and runs a
 // 256x64 implicit-GEMM kernel: 1.6 ms for 256 images, 40 % of the whole fused forward.  With 3 channels the 7 kernel
 // columns of one kernel row are 21 CONTIGUOUS bf16 values of the NHWC input row, so the im2col matrix never has to
-// exist: for a fixed kernel row kh,  A[ow][k] = in_row[2*oh + kh - 3][6*ow + k - 10]  for k = 1 + 3*kw + c  (k = 0 and
-// k = 22..31 meet zero weights), i.e. the A fragments of mma.sync.m16n8k16 are plain 32-bit shared-memory loads from
-// the staged input rows at a 12-byte row pitch (conflict-free: 3*g + t words).  The one-element shift (k = 1 + ...)
-// makes every fragment pair 4-byte aligned while the global rows are staged with aligned 16-byte copies.
+// exist: for kernel row kh,  A[ow][kk] = in_row[2*oh + kh - 3][6*ow + kk - 10]  for kk = 1 + 3*kw + c  (kk = 0 meets a
+// zero weight), i.e. the A fragments of mma.sync.m16n8k16 are plain 32-bit shared-memory loads from the staged input
+// rows at a 12-byte row pitch.  The one-element shift (kk = 1 + ...) makes every fragment pair 4-byte aligned while the
+// global rows are staged with aligned 16-byte copies.  K is FLATTENED over the kernel rows: kf = 22*kh + kk, 154 values
+// padded to 160 = ten k16 steps (padding each kernel row to 32 took fourteen); a fragment pair never straddles a kernel
+// row (22 is even), a k-step may, which costs a two-way bank conflict on those loads.
 // CTA = 4 output rows of one image (448 pixels) x 64 channels, 7 warps, each warp two passes of 32 pixels x 64
-// channels (64 fp32 accumulators); K = 7 kernel rows x 32.  Shared memory: 13 input rows (zero padded) + the weights as
-// [64][232] bf16 (pitch 464 B: ldmatrix rows fall on distinct banks), 48 000 B static.
-constexpr int kC1RowsPerCta = 4, kC1InRows = 2 * kC1RowsPerCta + 5, kC1RowElems = 704, kC1WPitch = 232;
+// channels (64 fp32 accumulators).  Shared memory: 13 input rows (zero padded) + the weights as [64][168] bf16 (pitch
+// 336 B: the eight rows of an ldmatrix fall on distinct banks), 39 808 B static.
+constexpr int kC1RowsPerCta = 4, kC1InRows = 2 * kC1RowsPerCta + 5, kC1RowElems = 704, kC1WPitch = 168;
+constexpr int kC1KSteps = 10, kC1KRow = 22, kC1K = 7 * kC1KRow;
 constexpr int kC1Threads = 224;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -477,91 +480,151 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_r
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+// 16-byte global -> shared copy that bypasses the registers; src_bytes = 0 writes zeros (the zero padding of the rows)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kC1InBytes = kC1InRows * kC1RowElems * 2;                   // one staged tile of input rows
+constexpr int kC1OutPitch = 144, kC1OutBytes = 16 * kC1OutPitch;          // per-warp output staging: 16 pixels x (128 + 16) B
+constexpr int kC1SmemBytes = 64 * kC1WPitch * 2 + 2 * kC1InBytes + (kC1Threads / 32) * kC1OutBytes;   // 74 240 B
+
+// Persistent: the weights are staged once per CTA, the CTA walks tiles (image, block of 4 output rows) with a stride of
+// the grid, and the input rows of the NEXT tile arrive by cp.async while the current one is multiplied.
 __global__ void __launch_bounds__(kC1Threads, 2)
 conv1_7x7s2_kernel(const uint4* __restrict__ x, const uint4* __restrict__ wt, const __nv_bfloat16* __restrict__ bias,
-                   __nv_bfloat16* __restrict__ out, int relu) {
-  __shared__ __align__(16) uint16_t s_w[64 * kC1WPitch];
-  __shared__ __align__(16) uint16_t s_in[kC1InRows * kC1RowElems];
+                   __nv_bfloat16* __restrict__ out, int relu, int n_tiles) {
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  uint16_t* s_w = reinterpret_cast<uint16_t*>(c1_smem);
+  uint8_t* s_in_base = c1_smem + 64 * kC1WPitch * 2;
   const int tid = threadIdx.x;
-  const int n = blockIdx.x / 28, oh0 = (blockIdx.x % 28) * kC1RowsPerCta;
-  for (int i = tid; i < 64 * kC1WPitch / 8; i += kC1Threads) reinterpret_cast<uint4*>(s_w)[i] = __ldg(wt + i);
   constexpr int kVecPerRow = kC1RowElems / 8;          // 88: 2 zero vectors, 84 of data (224 px x 3 ch), 2 zero vectors
-  for (int i = tid; i < kC1InRows * kVecPerRow; i += kC1Threads) {
-    const int r = i / kVecPerRow, v = i % kVecPerRow, ih = 2 * oh0 - 3 + r;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (v >= 2 && v < 86 && ih >= 0 && ih < 224) val = __ldg(x + (static_cast<long long>(n) * 224 + ih) * 84 + (v - 2));
-    reinterpret_cast<uint4*>(s_in)[i] = val;
-  }
-  __syncthreads();
+  auto stage = [&](int tile, int buf) {
+    const int n = tile / 28, oh0 = (tile % 28) * kC1RowsPerCta;
+    uint4* dst = reinterpret_cast<uint4*>(s_in_base + buf * kC1InBytes);
+    for (int i = tid; i < kC1InRows * kVecPerRow; i += kC1Threads) {
+      const int r = i / kVecPerRow, v = i % kVecPerRow, ih = 2 * oh0 - 3 + r;
+      const bool valid = v >= 2 && v < 86 && ih >= 0 && ih < 224;
+      const uint4* src = valid ? x + (static_cast<long long>(n) * 224 + ih) * 84 + (v - 2) : x;
+      cp_async16_zfill(dst + i, src, valid ? 16 : 0);
+    }
+  };
+  int tile = blockIdx.x, buf = 0;
+  if (tile < n_tiles) stage(tile, 0);
+  cp_async_commit();
+  for (int i = tid; i < 64 * kC1WPitch / 8; i += kC1Threads) reinterpret_cast<uint4*>(s_w)[i] = __ldg(wt + i);
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const uint32_t* s_in32 = reinterpret_cast<const uint32_t*>(s_in);
   // ldmatrix.x4: lane l addresses row (l & 7) of matrix (l >> 3); matrices = (n-tile, k 0-7), (n-tile, k 8-15),
   // (n-tile + 1, k 0-7), (n-tile + 1, k 8-15)
   const uint16_t* b_lane = s_w + ((lane & 7) + ((lane >> 4) << 3)) * kC1WPitch + (((lane >> 3) & 1) << 3);
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int mt0 = 4 * warp + 2 * pass;
-    int a_base[2], rl[2], owb[2];
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      rl[mi] = (mt0 + mi) / 7;
-      owb[mi] = ((mt0 + mi) % 7) * 16;
-      a_base[mi] = (2 * rl[mi]) * (kC1RowElems / 2) + 3 * (owb[mi] + g) + t + 3;   // word index of (kh = 0, ks = 0)
-    }
-    float acc[2][8][4];
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[mi][nt][q] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 7; ++kh) {
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+  uint8_t* s_out = s_in_base + 2 * kC1InBytes + warp * kC1OutBytes;
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) stage(next, buf ^ 1);       // buf ^ 1 was released by the barrier at the end of the last round
+    cp_async_commit();
+    cp_async_wait<1>();                             // this tile's rows have landed (the next tile's may be in flight)
+    __syncthreads();
+    const uint32_t* s_in32 = reinterpret_cast<const uint32_t*>(s_in_base + buf * kC1InBytes);
+    const int n = tile / 28, oh0 = (tile % 28) * kC1RowsPerCta;
+  #pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int mt0 = 4 * warp + 2 * pass;
+      int a_base[2], rl[2], owb[2];
+  #pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        rl[mi] = (mt0 + mi) / 7;
+        owb[mi] = ((mt0 + mi) % 7) * 16;
+        a_base[mi] = (2 * rl[mi]) * (kC1RowElems / 2) + 3 * (owb[mi] + g) + 3;   // word index of (kernel row 0, kk = 0)
+      }
+      float acc[2][8][4];
+  #pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+  #pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) acc[mi][nt][q] = 0.f;
+  #pragma unroll
+      for (int j = 0; j < kC1KSteps; ++j) {
         uint32_t b[4][4];
-#pragma unroll
-        for (int np = 0; np < 4; ++np) ldmatrix_x4(b[np], b_lane + np * 16 * kC1WPitch + kh * 32 + ks * 16);
-#pragma unroll
+  #pragma unroll
+        for (int np = 0; np < 4; ++np) ldmatrix_x4(b[np], b_lane + np * 16 * kC1WPitch + j * 16);
+        // word offsets of this thread's two fragment pairs (kf = 16 j + 2 t and + 8): kernel row kh = kf / 22 (the six
+        // padding values behind kf = 153 stay in kernel row 6 and meet zero weights), kk = kf - 22 kh
+        int off[2];
+  #pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int kf = 16 * j + 8 * hh + 2 * t;
+          const int kh = min((kf * 373) >> 13, 6);
+          off[hh] = kh * (kC1RowElems / 2) + ((kf - kC1KRow * kh) >> 1);
+        }
+  #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
-          const int w0 = a_base[mi] + kh * (kC1RowElems / 2) + ks * 8;
           uint32_t a[4];
-          a[0] = s_in32[w0];
-          a[1] = s_in32[w0 + 24];
-          a[2] = s_in32[w0 + 4];
-          a[3] = s_in32[w0 + 28];
-#pragma unroll
+          a[0] = s_in32[a_base[mi] + off[0]];
+          a[1] = s_in32[a_base[mi] + off[0] + 24];
+          a[2] = s_in32[a_base[mi] + off[1]];
+          a[3] = s_in32[a_base[mi] + off[1] + 24];
+  #pragma unroll
           for (int np = 0; np < 4; ++np) {
             mma_bf16_16816(acc[mi][2 * np], a, b[np][0], b[np][1]);
             mma_bf16_16816(acc[mi][2 * np + 1], a, b[np][2], b[np][3]);
           }
         }
       }
-    }
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      __nv_bfloat16* orow = out + ((static_cast<long long>(n) * 112 + oh0 + rl[mi]) * 112 + owb[mi] + g) * 64 + 2 * t;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(bias + nt * 8 + 2 * t);
-        const float b0 = __low2float(bb), b1 = __high2float(bb);
-        float v0 = acc[mi][nt][0] + b0, v1 = acc[mi][nt][1] + b1, v2 = acc[mi][nt][2] + b0, v3 = acc[mi][nt][3] + b1;
-        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-        *reinterpret_cast<__nv_bfloat162*>(orow + nt * 8) = __floats2bfloat162_rn(v0, v1);
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * 64 + nt * 8) = __floats2bfloat162_rn(v2, v3);
+      // Epilogue: bias + relu, then the warp's 16 pixels x 64 channels go through a padded shared-memory tile (stmatrix:
+      // the inverse of ldmatrix; 144-byte row pitch keeps the eight 16-byte rows of a matrix on distinct banks) so that
+      // every global store is 16 bytes per lane and 128 contiguous bytes per pixel.  (Storing the accumulator fragments
+      // directly -- 4 bytes per lane, eight 16-byte pieces per instruction -- cost as many L1 wavefronts as all the
+      // fragment loads of the kernel.)
+  #pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        __syncwarp();
+  #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+  #pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t pk[4];
+  #pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int nt = 4 * q + i4;
+              const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(bias + nt * 8 + 2 * t);
+              float v0 = acc[mi][nt][2 * r] + __low2float(bb), v1 = acc[mi][nt][2 * r + 1] + __high2float(bb);
+              if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
+              pk[i4] = *reinterpret_cast<const uint32_t*>(&o2);
+            }
+            // lane l addresses row (l & 7) of matrix (l >> 3) = n-tile 4 q + (l >> 3)
+            const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(
+                s_out + (8 * r + (lane & 7)) * kC1OutPitch + (4 * q + (lane >> 3)) * 16));
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[0]),
+                         "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        }
+        __syncwarp();
+        uint4* opix = reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * 112 + oh0 + rl[mi]) * 112 + owb[mi]) * 64);
+  #pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int c = it * 32 + lane, row = c >> 3, col = c & 7;
+          opix[row * 8 + col] = *reinterpret_cast<const uint4*>(s_out + row * kC1OutPitch + col * 16);
+        }
       }
     }
+    __syncthreads();                                // every warp is done with this buffer before it is staged again
   }
 }
 
-// w [64, 3, 7, 7] (any strides, bf16) -> wt [64][232]: wt[n][kh * 32 + 1 + 3 * kw + c] = w[n][c][kh][kw], zeros elsewhere
+// w [64, 3, 7, 7] (any strides, bf16) -> wt [64][168]: wt[n][22 * kh + 1 + 3 * kw + c] = w[n][c][kh][kw], zeros elsewhere
 __global__ void conv1_pack_weights_kernel(const __nv_bfloat16* __restrict__ w, long long sn, long long sc, long long sh,
                                           long long sw, uint16_t* __restrict__ wt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * kC1WPitch) return;
-  const int n = i / kC1WPitch, k = i % kC1WPitch, kh = k / 32, kk = k % 32 - 1;
+  const int n = i / kC1WPitch, k = i % kC1WPitch, kh = k / kC1KRow, kk = k % kC1KRow - 1;
   uint16_t v = 0;
-  if (kh < 7 && kk >= 0 && kk < 21)
+  if (k < kC1K && kk >= 0)
     v = *reinterpret_cast<const uint16_t*>(w + n * sn + (kk % 3) * sc + kh * sh + (kk / 3) * sw);
   wt[i] = v;
 }
@@ -587,9 +650,16 @@ extern "C" int svb_conv1_7x7s2_nhwc(svb_handle* h, void* stream, const void* x, 
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed_w) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias) & 3))
     return fail(SVB_ERR_UNSUPPORTED, "svb_conv1_7x7s2_nhwc needs 16-byte aligned tensors");
-  (conv1_7x7s2_kernel<<<static_cast<unsigned>(n_images * 28), kC1Threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  static bool configured[64] = {};
+  if (h->device < 64 && !configured[h->device]) {
+    SVB_CUDA(cudaFuncSetAttribute(conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemBytes));
+    configured[h->device] = true;
+  }
+  const int n_tiles = static_cast<int>(n_images * 28);
+  const int grid = n_tiles < 2 * h->sms ? n_tiles : 2 * h->sms;       // two resident CTAs per SM walk the tiles
+  (conv1_7x7s2_kernel<<<grid, kC1Threads, kC1SmemBytes, static_cast<cudaStream_t>(stream)>>>(
        static_cast<const uint4*>(x), static_cast<const uint4*>(packed_w), static_cast<const __nv_bfloat16*>(bias),
-       static_cast<__nv_bfloat16*>(out), relu),
+       static_cast<__nv_bfloat16*>(out), relu, n_tiles),
    svb::count_launch());
   SVB_LAUNCH_CHECK("conv1_7x7s2");
   return 0;
