@@ -1,5 +1,5 @@
 """Launches each libsvb producer kernel a few times at GoogLeNet's shapes (256 images) so that ncu can capture them:
-    ncu --set full --clock-control none --import-source on -k regex:'maxpool|bias_relu|conv1_7x7' -c 12 \
+    ncu --set full --clock-control none --import-source on -k regex:'maxpool|bias_relu|relu_grad|conv1_7x7' -c 30 \
         -o gpurun_out/producer_full python tools/producer_kernels_run.py
 Also prints event-timed bandwidths (outside ncu)."""
 import os
@@ -57,6 +57,23 @@ def main():
         gb = src.numel() * 2 * 2 / 1e9
         print(f"{name:40s} {t * 1e3:8.1f} us  {gb / t * 1e3:7.0f} GB/s (read + write)")
         del src, dests
+    # the differentiable pair and the ReLU-mask gather of the IE passes (64 images per batch there)
+    Bi = max(B // 4, 1)
+    for name, shape, k, s, p in [("pool fwd+argmax 3/1 C=480 14x14", (Bi, 480, 14, 14), 3, 1, 1),
+                                 ("pool fwd+argmax 3/2 C=480 28x28", (Bi, 480, 28, 28), 3, 2, 0)]:
+        x = nhwc(*shape)
+        y, arg = ops.maxpool_nhwc_with_argmax(x, k, s, p, True)
+        go = torch.randn_like(y)
+        t = timed(lambda: ops.maxpool_nhwc_with_argmax(x, k, s, p, True), n=n, warm=0 if quick else 3)
+        tb = timed(lambda: ops.maxpool_nhwc_backward(go, arg, x.shape, k, s, p), n=n, warm=0 if quick else 3)
+        gb = (x.numel() + y.numel()) * 2 / 1e9
+        print(f"{name:32s} {t * 1e3:8.1f} us fwd {tb * 1e3:8.1f} us bwd  {gb / t * 1e3:7.0f} / {gb / tb * 1e3:7.0f} GB/s (in + out)")
+        del x, y, arg, go
+    out = nhwc(Bi, 512, 14, 14).relu_()
+    go = nhwc(Bi, 512, 14, 14)
+    t = timed(lambda: ops.relu_grad_gather([(go, 128, out, 128, 256)], out), n=n, warm=0 if quick else 3)
+    print(f"relu_grad_gather 256 of 512 ch 14x14     {t * 1e3:8.1f} us")
+    del out, go
     x = nhwc(B, 3, 224, 224)
     w = (torch.randn(64, 3, 7, 7, device="cuda") * 0.1).bfloat16()
     bias = torch.randn(64, device="cuda").bfloat16()
