@@ -200,10 +200,12 @@ def _make_fused_classes():
 
         def _merged(self):
             convs = [self.branch1.conv, self.branch2[0].conv, self.branch3[0].conv]
-            w = getattr(self, "_svb_w1", None)
-            if w is None or w.device != convs[0].weight.device or w.dtype != convs[0].weight.dtype:
+            # rebuilt when a weight was re-assigned, moved or written in place (load_state_dict after fuse_forward)
+            key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+            if getattr(self, "_svb_key", None) != key:
                 self._svb_w1 = torch.cat([c.weight for c in convs]).contiguous(memory_format=torch.channels_last)
                 self._svb_b1 = torch.cat([c.bias for c in convs]).contiguous()
+                self._svb_key = key
             return self._svb_w1, self._svb_b1
 
         def _convs(self):

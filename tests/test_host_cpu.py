@@ -398,6 +398,15 @@ def test_fuse_forward_keeps_the_module_tree_and_the_cpu_function():
     again = copy.deepcopy(fused)                      # the swapped classes survive a deepcopy (model_copy in the pipeline)
     with torch.no_grad():
         assert torch.equal(again(x), base(x))
+    # the concatenated 1x1 weights of a fused block follow weights that are loaded AFTER fuse_forward
+    blk = fused.inception4a
+    w_before, _ = blk._merged()
+    w_before = w_before.clone()
+    state = {k: (v * 0.5 if v.is_floating_point() else v) for k, v in fused.state_dict().items()}
+    fused.load_state_dict(state)
+    w_after, b_after = blk._merged()
+    assert torch.allclose(w_after, w_before * 0.5)
+    assert torch.equal(b_after, torch.cat([blk.branch1.conv.bias, blk.branch2[0].conv.bias, blk.branch3[0].conv.bias]))
 
 
 def test_pool_output_size_is_torchs():
