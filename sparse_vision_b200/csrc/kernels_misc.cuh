@@ -838,6 +838,56 @@ static __global__ void activity_bits_rows_kernel(const T* __restrict__ t, uint32
   bits[i] = m;
 }
 
+// One pass over a token-major bf16 tensor t [n_rows, F] (the 2-D call of measure_inactive_units, compute_ie.py:155: every
+// token is a "sample"): count[f] += #rows with t[r, f] != 0 and n_active[r] = #units with t[r, f] != 0, without the bit
+// matrix in between.  grid (ceil(F / 2048), row chunks of kActRows), 256 threads: a thread owns 8 consecutive units (one
+// 16-byte load per row, the block reads 4 KB of contiguous row), eight counters in registers over the chunk's rows,
+// one float atomicAdd per unit and chunk at the end (integers below 2^24: exact and order-independent); the row counts
+// go through shared-memory counters.  count and n_active must be zero on entry.
+constexpr int kActRows = 64;
+static __global__ void __launch_bounds__(256)
+activity_rows_fused_kernel(const uint4* __restrict__ t, long long n_rows, int F8, float* __restrict__ count,
+                           int32_t* __restrict__ n_active) {
+  __shared__ int s_row[kActRows];
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.y) * kActRows;
+  const int rows = static_cast<int>(min(static_cast<long long>(kActRows), n_rows - r0));
+  if (threadIdx.x < kActRows) s_row[threadIdx.x] = 0;
+  __syncthreads();
+  int cnt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cnt[e] = 0;
+  const bool in = v < F8;
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (in) q = __ldg(t + (r0 + r) * F8 + v);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    int pop = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int lo = (w[k] & 0x00007FFFu) != 0, hi = (w[k] & 0x7FFF0000u) != 0;   // +-0 is inactive, NaN / inf active
+      cnt[2 * k] += lo;
+      cnt[2 * k + 1] += hi;
+      pop += lo + hi;
+    }
+    if (n_active) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+      if ((threadIdx.x & 31) == 0 && pop) atomicAdd(&s_row[r], pop);
+    }
+  }
+  if (in) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (cnt[e]) atomicAdd(count + static_cast<size_t>(v) * 8 + e, static_cast<float>(cnt[e]));
+  }
+  if (n_active) {
+    __syncthreads();
+    if (threadIdx.x < rows && s_row[threadIdx.x]) atomicAdd(n_active + r0 + threadIdx.x, s_row[threadIdx.x]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gradients
 // Gradient assembly for the SaeMLP step (assemble_grads_kernel below).  All inputs are in "unscaled" units (see
 // EpiDPre); s = 2/(T_global*C).

@@ -179,6 +179,17 @@ extern "C" int svb_measure_inactive(svb_handle* h, void* stream, const void* t, 
   float* nact = h->arena.take<float>(n_rows);
   h->gradbuf = nullptr;
   if (n_rows >= (1LL << 31)) return fail(SVB_ERR_UNSUPPORTED, "too many rows");
+  if (!(layout == SVB_NCHW && hw > 1) && dtype == SVB_BF16 && F % 8 == 0 && n_rows >= 1024 && n_rows < (1LL << 24) &&
+      (reinterpret_cast<uintptr_t>(t) & 15) == 0 && cdiv(n_rows, kActRows) <= 65535) {
+    // many rows (the 2-D call on a token-major encoder output: every token is a sample): one fused pass, no bit matrix
+    SVB_CUDA(cudaMemsetAsync(count, 0, sizeof(float) * F, st));
+    if (act->n_active) SVB_CUDA(cudaMemsetAsync(act->n_active, 0, sizeof(int32_t) * n_rows, st));
+    (activity_rows_fused_kernel<<<dim3(cdiv(F / 8, 256), cdiv(n_rows, kActRows)), 256, 0, st>>>(
+         static_cast<const uint4*>(t), n_rows, F / 8, count, act->n_active), svb::count_launch());
+    (activity_finalize_kernel<<<1, 1024, 0, st>>>(count, F, static_cast<float>(n_rows), act->dead, act->freq, nullptr), svb::count_launch());
+    SVB_LAUNCH_CHECK("measure_inactive (fused rows)");
+    return 0;
+  }
   if (layout == SVB_NCHW && hw > 1) {
     (fill_u32_kernel<<<grid_for(static_cast<size_t>(n_rows) * words), 256, 0, st>>>(bits, static_cast<size_t>(n_rows) * words, 0u), svb::count_launch());
     const long long warps = n_images * F;

@@ -186,6 +186,25 @@ def test_measure_inactive_exact():
         assert abs(sp - sparsity) < 1e-6
 
 
+@pytest.mark.parametrize("rows,F", [(3136, 256), (5000, 2048), (1030, 8200), (2048, 72)])
+def test_measure_inactive_many_rows_fused_pass(rows, F):
+    """The 2-D call on a token-major bf16 encoder output (compute_ie.py:155: every token is a sample) takes one fused
+    pass for >= 1024 rows: dead mask, frequency and per-row active counts exact against the oracle, -0.0 inactive."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(rows + F)
+    t = torch.relu(torch.randn(rows, F, generator=gen) - 1.0).bfloat16()
+    t[:, 5] = 0
+    t[10:, 9] = 0
+    t[3, 17] = -0.0
+    t[4, 18] = float("inf")
+    dead, sparsity, freq = O.measure_inactive_units(t.float(), 4)
+    d, f, n_active = ops.measure_inactive(t.cuda())
+    assert np.array_equal(d.cpu().numpy().astype(bool), dead.numpy())
+    np.testing.assert_allclose(f.cpu().numpy(), freq.numpy(), rtol=0, atol=1e-7)
+    assert torch.equal(n_active.cpu().long(), (t.float() != 0).sum(1))
+    assert abs((n_active.float() / (F / 4)).mean().item() - sparsity) < 1e-6
+
+
 def test_adam_step_and_reinit(golden_dir):
     ops = _ops()
     g = _load(golden_dir, "conv_mlp_cadam.npz")
