@@ -207,13 +207,21 @@ class IE:
         """batches: iterable of (inputs, targets).  averages: the dict compute_average returned (what :372 loads).
         Returns (ie_sae_features {layer: [F]}, ie_sae_error {layer: scalar}, ie_model_neurons {layer: [C]})."""
         feat, err, neur, tokens = {}, {}, {}, {}
-        for inputs, targets in batches:
+        # Data parallel with the batches at hand as a list: ONE all-reduce of all local batch sizes up front instead of
+        # one (host-synchronising) exchange per batch -- at 2.3 ms of device work per batch that exchange was a fifth of
+        # the 8-GPU pass.  Every rank passes the same number of batches either way (see below).
+        global_sizes = None
+        if self._dp() and isinstance(batches, (list, tuple)) and len(batches) > 0:
+            t = torch.tensor([int(b[0].shape[0]) for b in batches], device=self.device, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            global_sizes = t.tolist()
+        for i_batch, (inputs, targets) in enumerate(batches):
             # The reference's criterion is a MEAN over the batch (utils.py:128-129), so d loss / d x carries 1 / B.  A
             # rank that holds bs of the batch's bs_global images gets 1 / bs from its local mean; IE is linear in the
             # gradient, so the rank's sums are rescaled by bs / bs_global.  (Collective: every rank calls it once per
             # batch, also with an empty shard.)
             bs = inputs.shape[0]
-            bs_global = self._all_reduce_counts(bs)
+            bs_global = global_sizes[i_batch] if global_sizes is not None else self._all_reduce_counts(bs)
             if bs == 0:
                 continue
             ratio = bs / bs_global
