@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEY = {"UTCHMMA": "tcgen05.mma (5th-gen tensor cores, accumulators in TMEM)", "UTCBAR": "tcgen05.commit -> mbarrier",
        "LDTM": "tcgen05.ld (TMEM -> registers)", "UTCATOMSWS": "tcgen05.alloc / dealloc (TMEM columns)",
-       "LDGSTS": "cp.async (stem convolution: input rows of the next tile)", "LDSM": "ldmatrix", "STSM": "stmatrix", "UTMALDG": "cp.async.bulk.tensor load (TMA)", "UTMASTG": "cp.async.bulk.tensor store (TMA)",
+       "LDGSTS": "cp.async (stem convolution: input rows of the next tile; fused node-IE kernel: staged averages)", "LDSM": "ldmatrix", "STSM": "stmatrix", "UTMALDG": "cp.async.bulk.tensor load (TMA)", "UTMASTG": "cp.async.bulk.tensor store (TMA)",
        "UTMAPF": "TMA L2 prefetch", "UTMACMDFLUSH": "bulk-group commit", "SYNCS": "mbarrier arrive / try_wait",
        "HMMA": "legacy mma.sync (only in the producer's im2col-free stem convolution, conv1_7x7s2_kernel; absent from the SAE path)", "SHFL": "warp shuffles", "ATOMS": "shared atomics",
        "ATOMG": "global atomics", "RED": "global reductions"}
