@@ -127,7 +127,7 @@ def _make_fused_classes():
                     self._svb_packed, self._svb_key = ops.conv1_pack_weights(w), key
                 return ops.conv1_stem(x, self._svb_packed, self.conv.bias)
             y = _conv_nobias(x, self.conv)
-            if getattr(self, "_svb_defer_bias", False):
+            if getattr(self, "_svb_defer_bias", False) and not self._forward_hooks:     # a hook must see the finished output
                 # the next module is a max-pool: relu(max(y) + b) == max(relu(y + b)) exactly (a per-channel constant,
                 # a monotone rounding and a monotone relu commute with max), so the bias pass runs on the POOLED tensor
                 # (a quarter of the bytes).  The raw convolution output is tagged; FusedMaxPool2d finishes it.
