@@ -307,6 +307,11 @@ class ModelPipeline:
             if self._graph_eager_left > 0:                 # cuDNN heuristics, workspace growth, lazy optimizer state
                 self._graph_eager_left -= 1
                 return self._forward_and_compare(inputs, targets)
+            if self.dp is not None and not self.dp.peer:
+                # the exchange fell back to torch.distributed (no peer memory on this machine: the same on every rank):
+                # the data-parallel batch stays eager
+                self.cuda_graph = False
+                return self._forward_and_compare(inputs, targets)
             params = self.sae_model.param_list()
             host_step = int(self.sae_optimizer.state[params[0]]["step"].item())
             self._step_dev = torch.tensor([host_step], dtype=torch.int32, device=inputs.device)

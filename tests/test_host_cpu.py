@@ -418,3 +418,28 @@ def test_pool_output_size_is_torchs():
                     continue
                 want = torch.nn.functional.max_pool2d(torch.zeros(1, 1, n, n), k, s, p, ceil_mode=ceil).shape[-1]
                 assert pool_output_size(n, k, s, p, ceil) == want, (n, k, s, p, ceil)
+
+
+def test_to_attribution_format_layouts_on_cpu():
+    """producer.to_attribution_format: channels_last + fused classes throughout by default; with nchw_tail the modules
+    up to the first hooked layer only.  (On the CPU the fused classes take torchvision's forward: same function.)"""
+    import copy
+    from sparse_vision_b200.producer import synthetic_googlenet, to_attribution_format
+    raw = synthetic_googlenet(seed=2, calibration_images=2, image_size=96)
+    full = to_attribution_format(copy.deepcopy(raw), "cpu", dtype=torch.float32)
+    w = full.inception5b.branch2[1].conv.weight
+    assert w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()
+    assert type(full.inception5b).__name__ == "Inception"          # fp32: nothing to fuse
+    mixed = to_attribution_format(copy.deepcopy(raw), "cpu", "mixed3a", dtype=torch.bfloat16, nchw_tail=True)
+    assert type(mixed.conv1).__name__ == "FusedBasicConv2d" and type(mixed.inception3a).__name__ == "FusedInception"
+    assert type(mixed.inception3b).__name__ == "Inception" and type(mixed.maxpool3).__name__ == "MaxPool2d"
+    assert mixed.conv3.conv.weight.is_contiguous(memory_format=torch.channels_last)
+    assert mixed.inception4a.branch2[1].conv.weight.is_contiguous()
+    assert [n for n, _ in mixed.named_modules()] == [n for n, _ in raw.named_modules()]
+    with pytest.raises(ValueError):
+        to_attribution_format(copy.deepcopy(raw), "cpu", "no_such_layer", nchw_tail=True)
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        want = to_attribution_format(copy.deepcopy(raw), "cpu", dtype=torch.float32, fold_bn=True)(x)
+        got = full(x)
+    assert torch.equal(got, want)
