@@ -443,3 +443,24 @@ def test_to_attribution_format_layouts_on_cpu():
         want = to_attribution_format(copy.deepcopy(raw), "cpu", dtype=torch.float32, fold_bn=True)(x)
         got = full(x)
     assert torch.equal(got, want)
+
+
+def test_producer_ops_have_no_cpu_fallback():
+    """The producer kernels are CUDA-only like the rest of the product path: a CPU tensor (or a wrong format) is refused
+    before any library call instead of being routed to a torch implementation."""
+    from sparse_vision_b200 import ops
+    x = torch.zeros(1, 8, 4, 4, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.zeros(8, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.maxpool_nhwc(x, 3, 2)
+    with pytest.raises(ValueError):
+        ops.maxpool_nhwc_autograd(x, 3, 2)
+    with pytest.raises(ValueError):
+        ops.bias_relu_scatter(x, b, [(x, 0, 8)])
+    with pytest.raises(ValueError):
+        ops.relu_grad_gather([(x, 0, x, 0, 8)], x)
+    with pytest.raises(ValueError):
+        ops.conv1_stem(torch.zeros(1, 3, 224, 224, dtype=torch.bfloat16), torch.zeros(64 * 168, dtype=torch.bfloat16),
+                       torch.zeros(64, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):
+        ops.conv1_pack_weights(torch.zeros(64, 3, 7, 7, dtype=torch.bfloat16))
