@@ -1,5 +1,11 @@
+"""Forward + backward of the frozen GoogLeNet behind the first hooked layer (leaf at inception3a), channels_last against
+NCHW, 64 images: event-timed and as a torch.profiler kernel table.  This is the measurement behind "with the stem out of
+the backward, channels_last is the faster format" (IE passes).  Diagnostic only.
+
+    python tools/prof_base_backward.py
+"""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from sparse_vision_b200.producer import synthetic_googlenet, to_producer_format
 dev = torch.device('cuda:0')
 for cl in (True, False):

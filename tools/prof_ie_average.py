@@ -1,5 +1,10 @@
+"""Kernel-time table (torch.profiler) of ONE IE.compute_average batch (three GoogLeNet layers, 64 images, eager launches):
+where the averages pass spends its time (this is what pointed at svb_measure_inactive's many-row path).  Diagnostic only.
+
+    python tools/prof_ie_average.py
+"""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from sparse_vision_b200.compute_ie import IE
 from sparse_vision_b200.models.sae_mlp import SaeMLP
 from sparse_vision_b200.producer import GOOGLENET_LAYERS, hooked_layers, synthetic_googlenet, to_attribution_format
